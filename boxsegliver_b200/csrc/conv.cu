@@ -1,0 +1,437 @@
+// Host side of the tcgen05 implicit-GEMM convolutions: builds the TMA tensor maps and the
+// IgemmArgs for each reference op and launches igemm_kernel (igemm.cuh).
+//   conv2d fprop / dgrad / wgrad  <- slim.conv2d, NetworksV2/UNet.py:79,85,94 (+ tf.gradients)
+//   convT2d fwd / bwd             <- slim.conv2d_transpose, NetworksV2/UNet.py:91
+#include <algorithm>
+#include "igemm.cuh"
+#include "internal.h"
+
+using namespace bsl;
+
+namespace {
+
+int g_mn_lbo = 8192, g_mn_sbo = 1024, g_mn_kadv = 2048;
+
+template <int MODE, bool B_MN, int BN, int STAGES>
+int launch_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const IgemmArgs& args_in, dim3 grid,
+               cudaStream_t stream) {
+  IgemmArgs args = args_in;
+  args.mn_lbo = g_mn_lbo;
+  args.mn_sbo = g_mn_sbo;
+  args.mn_kadv = g_mn_kadv;
+  auto kern = igemm_kernel<MODE, B_MN, BN, STAGES>;
+  constexpr int smem = igemm_smem_bytes<BN, STAGES>();
+  static bool configured = false;
+  if (!configured) {
+    BSL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, IGEMM_THREADS, smem, stream>>>(a, b, args);
+  BSL_LAUNCH_CHECK(ctx, "igemm_kernel launch");
+  return BSL_OK;
+}
+
+// Stage counts keep two CTAs resident per SM for BN <= 128 (96 KB each) so one CTA's epilogue
+// overlaps the other's main loop; BN = 256 takes the SM alone with a 4-deep ring.
+template <int MODE, bool B_MN>
+int launch_igemm(bsl_ctx* ctx, int bn, const CUtensorMap& a, const CUtensorMap& b, const IgemmArgs& args,
+                 dim3 grid, cudaStream_t stream) {
+  switch (bn) {
+    case 64: return launch_one<MODE, B_MN, 64, 4>(ctx, a, b, args, grid, stream);
+    case 128: return launch_one<MODE, B_MN, 128, 3>(ctx, a, b, args, grid, stream);
+    case 256: return launch_one<MODE, B_MN, 256, 4>(ctx, a, b, args, grid, stream);
+  }
+  return bsl_fail(ctx, BSL_EUNSUPPORTED, "igemm: column tile %d", bn);
+}
+
+int pick_bn(int n) { return n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : 64); }
+
+// Pixel box (w, h, n) with w*h*n == prod, widest along W first (coalesced 128 B rows either way).
+void pick_box(int prod, int W, int H, int N, int* tw, int* th, int* tn) {
+  int w = 1;
+  while (w < 16 && w < W && w < prod) w <<= 1;
+  int h = 1;
+  while (w * h < prod && h < H) h <<= 1;
+  *tw = w;
+  *th = h;
+  *tn = prod / (w * h);
+  (void)N;
+}
+
+int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+void set_tiles(IgemmArgs& a, const int tdim[4], const int tbox[4]) {
+  for (int d = 0; d < 4; ++d) {
+    a.tdim[d] = tdim[d];
+    a.tbox[d] = tbox[d];
+    a.ntile[d] = cdiv(tdim[d], tbox[d]);
+  }
+}
+
+int nhwc_map(bsl_ctx* ctx, const void* base, int c, int w, int h, int n, int ld, const int box[4],
+             CUtensorMap* out) {
+  uint64_t dims[5] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n, 1};
+  uint64_t str[5] = {2, (uint64_t)ld * 2, (uint64_t)w * ld * 2, (uint64_t)h * w * ld * 2,
+                     (uint64_t)n * h * w * ld * 2};
+  uint32_t bx[5] = {64, (uint32_t)box[0], (uint32_t)box[1], (uint32_t)box[2], 1};
+  return bsl_get_tmap(ctx, base, 5, dims, str, bx, out);
+}
+
+// [n, 2h, 2w, c] seen as (c, b:2, w, a:2, n*h): taps of a k2 s2 transposed conv become coordinates.
+int upsampled_map(bsl_ctx* ctx, const void* base, int c, int w, int h, int n, int ld, int tw, int th,
+                  CUtensorMap* out) {
+  uint64_t dims[5] = {(uint64_t)c, 2, (uint64_t)w, 2, (uint64_t)n * h};
+  uint64_t str[5] = {2, (uint64_t)ld * 2, (uint64_t)2 * ld * 2, (uint64_t)2 * w * ld * 2,
+                     (uint64_t)4 * w * ld * 2};
+  uint32_t bx[5] = {64, 1, (uint32_t)tw, 1, (uint32_t)th};
+  return bsl_get_tmap(ctx, base, 5, dims, str, bx, out);
+}
+
+// [n, h, w, c] seen as (c, 1, w, 1, n*h) so it shares pixel coordinates with upsampled_map.
+int rows_map(bsl_ctx* ctx, const void* base, int c, int w, int h, int n, int ld, int tw, int th,
+             CUtensorMap* out) {
+  uint64_t dims[5] = {(uint64_t)c, 1, (uint64_t)w, 1, (uint64_t)n * h};
+  uint64_t str[5] = {2, (uint64_t)ld * 2, (uint64_t)ld * 2, (uint64_t)w * ld * 2, (uint64_t)w * ld * 2};
+  uint32_t bx[5] = {64, 1, (uint32_t)tw, 1, (uint32_t)th};
+  return bsl_get_tmap(ctx, base, 5, dims, str, bx, out);
+}
+
+int matrix_map(bsl_ctx* ctx, const void* base, int inner, int rows, int box_inner, int box_rows,
+               CUtensorMap* out) {
+  uint64_t dims[2] = {(uint64_t)inner, (uint64_t)rows};
+  uint64_t str[2] = {2, (uint64_t)inner * 2};
+  uint32_t bx[2] = {(uint32_t)box_inner, (uint32_t)box_rows};
+  return bsl_get_tmap(ctx, base, 2, dims, str, bx, out);
+}
+
+int check_conv(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
+  if (!ctx) return BSL_EINVAL;
+  if (!d) return bsl_fail(ctx, BSL_EINVAL, "conv2d: null descriptor");
+  if (d->n <= 0 || d->h <= 0 || d->w <= 0 || d->cin <= 0 || d->cout <= 0)
+    return bsl_fail(ctx, BSL_EINVAL, "conv2d: non-positive size");
+  if (!((d->kh == 3 && d->kw == 3) || (d->kh == 1 && d->kw == 1)))
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv2d: kernel %dx%d (3x3 or 1x1 only)", d->kh, d->kw);
+  if (d->cin % 64 || d->cout % 64)
+    return bsl_fail(ctx, BSL_EUNSUPPORTED,
+                    "conv2d tcgen05 path needs cin,cout multiples of 64 (got %d,%d); use "
+                    "bsl_conv2d_small_* for the stem / logits layers", d->cin, d->cout);
+  if (d->x_ld < d->cin || d->y_ld < d->cout || d->x_ld % 8 || d->y_ld % 8)
+    return bsl_fail(ctx, BSL_EINVAL, "conv2d: channel strides must be >= channels and multiples of 8");
+  return BSL_OK;
+}
+
+void conv_taps(IgemmArgs& a, int kh, int kw) {
+  a.ntaps = kh * kw;
+  for (int r = 0; r < kh; ++r)
+    for (int s = 0; s < kw; ++s) {
+      signed char* o = a.tapoff[r * kw + s];
+      o[0] = (signed char)(s - (kw - 1) / 2);  // TF SAME, stride 1: pad_before = (k-1)/2
+      o[1] = (signed char)(r - (kh - 1) / 2);
+      o[2] = 0;
+      o[3] = 0;
+    }
+}
+
+struct SplitPlan {
+  int k_tiles, per, splits;
+};
+
+SplitPlan plan_split(bsl_ctx* ctx, int mn_tiles, int k_tiles) {
+  // Aim for ~2 CTAs per SM in flight, but never fewer than 8 pixel tiles per split.
+  int want = std::max(1, (2 * ctx->sm_count + mn_tiles - 1) / mn_tiles);
+  int splits = std::max(1, std::min(want, k_tiles / 8));
+  int per = cdiv(k_tiles, splits);
+  splits = cdiv(k_tiles, per);
+  return {k_tiles, per, splits};
+}
+
+__global__ void reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, long long n,
+                                     int splits) {
+  long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 acc = *reinterpret_cast<const float4*>(part + i);
+  for (int s = 1; s < splits; ++s) {  // fixed order => bit-reproducible
+    float4 v = *reinterpret_cast<const float4*>(part + s * n + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + i) = acc;
+}
+
+int reduce_splits(bsl_ctx* ctx, const float* part, float* out, long long n, int splits, cudaStream_t s) {
+  int threads = 256;
+  long long blocks = (n / 4 + threads - 1) / threads;
+  reduce_splits_kernel<<<(unsigned)blocks, threads, 0, s>>>(part, out, n, splits);
+  BSL_LAUNCH_CHECK(ctx, "reduce_splits_kernel");
+  return BSL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bsl_debug_set(bsl_ctx* ctx, int key, int value) {
+  switch (key) {
+    case 0: g_mn_lbo = value; return BSL_OK;
+    case 1: g_mn_sbo = value; return BSL_OK;
+    case 2: g_mn_kadv = value; return BSL_OK;
+  }
+  return bsl_fail(ctx, BSL_EINVAL, "debug_set: unknown key %d", key);
+}
+
+int bsl_conv2d_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
+                     void* stream) {
+  int rc = check_conv(ctx, d);
+  if (rc) return rc;
+  if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "conv2d_fprop: null buffer");
+  int box[4] = {0, 0, 0, 1};
+  pick_box(128, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
+  const int bn = pick_bn(d->cout);
+  CUtensorMap ta, tb;
+  if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, box, &ta))) return rc;
+  if ((rc = matrix_map(ctx, w, d->cout, d->kh * d->kw * d->cin, 64, 64, &tb))) return rc;
+  IgemmArgs a = {};
+  const int tdim[4] = {d->w, d->h, d->n, 1};
+  set_tiles(a, tdim, box);
+  conv_taps(a, d->kh, d->kw);
+  a.cblocks = d->cin / 64;
+  a.out = y;
+  a.ostride[0] = d->y_ld;
+  a.ostride[1] = (long long)d->w * d->y_ld;
+  a.ostride[2] = (long long)d->h * d->w * d->y_ld;
+  a.n_group = d->cout;
+  a.n_total = d->cout;
+  a.status = ctx->d_status;
+  dim3 grid(a.ntile[0] * a.ntile[1] * a.ntile[2], d->cout / bn, 1);
+  return launch_igemm<MODE_PIX_M, true>(ctx, bn, ta, tb, a, grid, as_stream(stream));
+}
+
+int bsl_conv2d_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, const void* w, void* dx,
+                     void* stream) {
+  int rc = check_conv(ctx, d);
+  if (rc) return rc;
+  if (!dy || !w || !dx) return bsl_fail(ctx, BSL_EINVAL, "conv2d_dgrad: null buffer");
+  int box[4] = {0, 0, 0, 1};
+  pick_box(128, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
+  const int bn = pick_bn(d->cin);
+  CUtensorMap ta, tb;
+  if ((rc = nhwc_map(ctx, dy, d->cout, d->w, d->h, d->n, d->y_ld, box, &ta))) return rc;
+  // HWIO read as a K-major B: row = tap*cin + ci (GEMM column), 64 consecutive cout = GEMM K.
+  if ((rc = matrix_map(ctx, w, d->cout, d->kh * d->kw * d->cin, 64, bn, &tb))) return rc;
+  IgemmArgs a = {};
+  const int tdim[4] = {d->w, d->h, d->n, 1};
+  set_tiles(a, tdim, box);
+  conv_taps(a, d->kh, d->kw);
+  a.cblocks = d->cout / 64;
+  a.b_flip = 1;
+  a.b_rows_per_tap = d->cin;
+  a.out = dx;
+  a.ostride[0] = d->x_ld;
+  a.ostride[1] = (long long)d->w * d->x_ld;
+  a.ostride[2] = (long long)d->h * d->w * d->x_ld;
+  a.n_group = d->cin;
+  a.n_total = d->cin;
+  a.status = ctx->d_status;
+  dim3 grid(a.ntile[0] * a.ntile[1] * a.ntile[2], d->cin / bn, 1);
+  return launch_igemm<MODE_PIX_M, false>(ctx, bn, ta, tb, a, grid, as_stream(stream));
+}
+
+size_t bsl_conv2d_wgrad_workspace(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
+  if (!ctx || !d || check_conv(ctx, d)) return 0;
+  int box[4] = {0, 0, 0, 1};
+  pick_box(64, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
+  const int k_tiles = cdiv(d->w, box[0]) * cdiv(d->h, box[1]) * cdiv(d->n, box[2]);
+  const int taps = d->kh * d->kw;
+  const int bn = pick_bn(d->cout);
+  const int mn = cdiv(taps * d->cin / 64, 2) * (d->cout / bn);
+  SplitPlan p = plan_split(ctx, mn, k_tiles);
+  return p.splits > 1 ? (size_t)p.splits * taps * d->cin * d->cout * sizeof(float) : 0;
+}
+
+int bsl_conv2d_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* dy, float* dw,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_conv(ctx, d);
+  if (rc) return rc;
+  if (!x || !dy || !dw) return bsl_fail(ctx, BSL_EINVAL, "conv2d_wgrad: null buffer");
+  int box[4] = {0, 0, 0, 1};
+  pick_box(64, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
+  const int taps = d->kh * d->kw;
+  const int bn = pick_bn(d->cout);
+  CUtensorMap ta, tb;
+  if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, box, &ta))) return rc;
+  if ((rc = nhwc_map(ctx, dy, d->cout, d->w, d->h, d->n, d->y_ld, box, &tb))) return rc;
+  IgemmArgs a = {};
+  const int tdim[4] = {d->w, d->h, d->n, 1};
+  set_tiles(a, tdim, box);
+  conv_taps(a, d->kh, d->kw);
+  a.cblocks = d->cin / 64;
+  a.m_total = taps * d->cin;
+  a.n_total = d->cout;
+  a.k_tiles_total = a.ntile[0] * a.ntile[1] * a.ntile[2];
+  const int m_tiles = cdiv(taps * a.cblocks, 2);
+  SplitPlan p = plan_split(ctx, m_tiles * (d->cout / bn), a.k_tiles_total);
+  a.k_tiles_per_split = p.per;
+  const size_t need = p.splits > 1 ? (size_t)p.splits * a.m_total * a.n_total * sizeof(float) : 0;
+  if (need > workspace_bytes || (need && !workspace))
+    return bsl_fail(ctx, BSL_EWORKSPACE, "conv2d_wgrad: workspace %zu < %zu", workspace_bytes, need);
+  a.out = p.splits > 1 ? workspace : (void*)dw;
+  a.status = ctx->d_status;
+  dim3 grid(m_tiles, d->cout / bn, p.splits);
+  rc = launch_igemm<MODE_PIX_K, true>(ctx, bn, ta, tb, a, grid, as_stream(stream));
+  if (rc) return rc;
+  if (p.splits > 1)
+    return reduce_splits(ctx, (const float*)workspace, dw, (long long)a.m_total * a.n_total, p.splits,
+                         as_stream(stream));
+  return BSL_OK;
+}
+
+// ------------------------------------------------------------------ transposed conv k2 s2
+
+static int check_convT(bsl_ctx* ctx, const bsl_convT2d_desc* d) {
+  if (!ctx) return BSL_EINVAL;
+  if (!d) return bsl_fail(ctx, BSL_EINVAL, "convT2d: null descriptor");
+  if (d->n <= 0 || d->h <= 0 || d->w <= 0) return bsl_fail(ctx, BSL_EINVAL, "convT2d: non-positive size");
+  if (d->cin % 64 || d->cout % 64)
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "convT2d needs cin,cout multiples of 64 (got %d,%d)", d->cin,
+                    d->cout);
+  if (d->x_ld < d->cin || d->y_ld < d->cout || d->x_ld % 8 || d->y_ld % 8)
+    return bsl_fail(ctx, BSL_EINVAL, "convT2d: bad channel strides");
+  return BSL_OK;
+}
+
+int bsl_convT2d_fwd(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, const void* w,
+                    const float* bias, void* y, void* stream) {
+  int rc = check_convT(ctx, d);
+  if (rc) return rc;
+  if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "convT2d_fwd: null buffer");
+  int box[4] = {0, 0, 0, 1};
+  pick_box(128, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
+  const int bn = pick_bn(d->cout);
+  CUtensorMap ta, tb;
+  if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, box, &ta))) return rc;
+  // [2,2,cout,cin]: row = tap*cout + co (GEMM column), cin contiguous (GEMM K) => K-major B.
+  if ((rc = matrix_map(ctx, w, d->cin, 4 * d->cout, 64, bn, &tb))) return rc;
+  IgemmArgs a = {};
+  const int tdim[4] = {d->w, d->h, d->n, 1};
+  set_tiles(a, tdim, box);
+  a.ntaps = 1;
+  a.cblocks = d->cin / 64;
+  a.out = y;
+  const long long row = (long long)2 * d->w * d->y_ld;  // one output row
+  a.ostride[0] = 2 * d->y_ld;
+  a.ostride[1] = 2 * row;
+  a.ostride[2] = (long long)2 * d->h * row;
+  a.n_group = d->cout;
+  for (int ta_ = 0; ta_ < 2; ++ta_)
+    for (int tb_ = 0; tb_ < 2; ++tb_) a.group_off[ta_ * 2 + tb_] = ta_ * row + (long long)tb_ * d->y_ld;
+  a.bias = bias;
+  a.relu = d->relu;
+  a.n_total = 4 * d->cout;
+  a.status = ctx->d_status;
+  dim3 grid(a.ntile[0] * a.ntile[1] * a.ntile[2], 4 * d->cout / bn, 1);
+  return launch_igemm<MODE_PIX_M, false>(ctx, bn, ta, tb, a, grid, as_stream(stream));
+}
+
+int bsl_convT2d_bwd_data(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* dyr, const void* w, void* dx,
+                         void* stream) {
+  int rc = check_convT(ctx, d);
+  if (rc) return rc;
+  if (!dyr || !w || !dx) return bsl_fail(ctx, BSL_EINVAL, "convT2d_bwd_data: null buffer");
+  int tw, th, tn;
+  pick_box(128, d->w, d->n * d->h, 1, &tw, &th, &tn);
+  if (tn != 1) th *= tn;  // rows absorb the remainder (boxes may overhang; OOB rows are masked)
+  const int bn = pick_bn(d->cin);
+  CUtensorMap ta, tb;
+  if ((rc = upsampled_map(ctx, dyr, d->cout, d->w, d->h, d->n, d->y_ld, tw, th, &ta))) return rc;
+  if ((rc = matrix_map(ctx, w, d->cin, 4 * d->cout, 64, 64, &tb))) return rc;
+  IgemmArgs a = {};
+  const int tdim[4] = {1, d->w, 1, d->n * d->h};
+  const int tbox[4] = {1, tw, 1, th};
+  set_tiles(a, tdim, tbox);
+  a.ntaps = 4;
+  for (int ta_ = 0; ta_ < 2; ++ta_)
+    for (int tb_ = 0; tb_ < 2; ++tb_) {
+      signed char* o = a.tapoff[ta_ * 2 + tb_];
+      o[0] = (signed char)tb_;
+      o[1] = 0;
+      o[2] = (signed char)ta_;
+      o[3] = 0;
+    }
+  a.cblocks = d->cout / 64;
+  a.out = dx;
+  a.ostride[1] = d->x_ld;
+  a.ostride[3] = (long long)d->w * d->x_ld;
+  a.n_group = d->cin;
+  a.n_total = d->cin;
+  a.status = ctx->d_status;
+  dim3 grid(a.ntile[1] * a.ntile[3], d->cin / bn, 1);
+  return launch_igemm<MODE_PIX_M, true>(ctx, bn, ta, tb, a, grid, as_stream(stream));
+}
+
+static void convT_wgrad_plan(bsl_ctx* ctx, const bsl_convT2d_desc* d, int* tw, int* th, int* bn, int* m_tiles,
+                             SplitPlan* p) {
+  int tn;
+  pick_box(64, d->w, d->n * d->h, 1, tw, th, &tn);
+  if (tn != 1) *th *= tn;
+  *bn = pick_bn(d->cin);
+  *m_tiles = cdiv(4 * d->cout / 64, 2);
+  const int k_tiles = cdiv(d->w, *tw) * cdiv(d->n * d->h, *th);
+  *p = plan_split(ctx, *m_tiles * (d->cin / *bn), k_tiles);
+}
+
+size_t bsl_convT2d_bwd_filter_workspace(bsl_ctx* ctx, const bsl_convT2d_desc* d) {
+  if (!ctx || !d || check_convT(ctx, d)) return 0;
+  int tw, th, bn, m_tiles;
+  SplitPlan p;
+  convT_wgrad_plan(ctx, d, &tw, &th, &bn, &m_tiles, &p);
+  return p.splits > 1 ? (size_t)p.splits * 4 * d->cout * d->cin * sizeof(float) : 0;
+}
+
+int bsl_convT2d_bwd_filter(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, const void* dyr,
+                           float* dw, float* dbias, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_convT(ctx, d);
+  if (rc) return rc;
+  if (!x || !dyr || !dw) return bsl_fail(ctx, BSL_EINVAL, "convT2d_bwd_filter: null buffer");
+  int tw, th, bn, m_tiles;
+  SplitPlan p;
+  convT_wgrad_plan(ctx, d, &tw, &th, &bn, &m_tiles, &p);
+  CUtensorMap ta, tb;
+  if ((rc = upsampled_map(ctx, dyr, d->cout, d->w, d->h, d->n, d->y_ld, tw, th, &ta))) return rc;
+  if ((rc = rows_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, tw, th, &tb))) return rc;
+  IgemmArgs a = {};
+  const int tdim[4] = {1, d->w, 1, d->n * d->h};
+  const int tbox[4] = {1, tw, 1, th};
+  set_tiles(a, tdim, tbox);
+  a.ntaps = 4;
+  for (int ta_ = 0; ta_ < 2; ++ta_)
+    for (int tb_ = 0; tb_ < 2; ++tb_) {
+      signed char* o = a.tapoff[ta_ * 2 + tb_];
+      o[0] = (signed char)tb_;
+      o[1] = 0;
+      o[2] = (signed char)ta_;
+      o[3] = 0;
+    }
+  a.cblocks = d->cout / 64;
+  a.m_total = 4 * d->cout;
+  a.n_total = d->cin;
+  a.k_tiles_total = p.k_tiles;
+  a.k_tiles_per_split = p.per;
+  const size_t need = p.splits > 1 ? (size_t)p.splits * a.m_total * a.n_total * sizeof(float) : 0;
+  if (need > workspace_bytes || (need && !workspace))
+    return bsl_fail(ctx, BSL_EWORKSPACE, "convT2d_bwd_filter: workspace %zu < %zu", workspace_bytes, need);
+  a.out = p.splits > 1 ? workspace : (void*)dw;
+  a.status = ctx->d_status;
+  dim3 grid(m_tiles, d->cin / bn, p.splits);
+  rc = launch_igemm<MODE_PIX_K, true>(ctx, bn, ta, tb, a, grid, as_stream(stream));
+  if (rc) return rc;
+  if (p.splits > 1) {
+    rc = reduce_splits(ctx, (const float*)workspace, dw, (long long)a.m_total * a.n_total, p.splits,
+                       as_stream(stream));
+    if (rc) return rc;
+  }
+  if (dbias)
+    return bsl_channel_sum_bf16(ctx, dyr, (long long)d->n * 4 * d->h * d->w, d->cout, d->y_ld, dbias,
+                                as_stream(stream));
+  return BSL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,54 @@
+// Library-private context shared by the translation units of libbsl_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/bsl_b200.h"
+#include "ptx.cuh"
+
+typedef CUresult (*bsl_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                        const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct bsl_ctx {
+  int device = 0;
+  int sm_count = 148;
+  std::string err;
+  std::mutex mu;
+  bsl::DeviceStatus* d_status = nullptr;
+  bsl_encode_tiled_fn encode_tiled = nullptr;
+  std::unordered_map<std::string, CUtensorMap> tmaps;  // keyed by (ptr, dims, strides, box)
+  void* nccl_lib = nullptr;                            // dlopen handle (comm.cu)
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+int bsl_fail(bsl_ctx* ctx, int code, const char* fmt, ...);
+int bsl_check_cuda(bsl_ctx* ctx, cudaError_t e, const char* what);
+
+#define BSL_CUDA(ctx, expr)                                        \
+  do {                                                             \
+    cudaError_t _e = (expr);                                       \
+    if (_e != cudaSuccess) return bsl_check_cuda(ctx, _e, #expr);  \
+  } while (0)
+
+#define BSL_LAUNCH_CHECK(ctx, what)                                \
+  do {                                                             \
+    cudaError_t _e = cudaGetLastError();                           \
+    if (_e != cudaSuccess) return bsl_check_cuda(ctx, _e, what);   \
+  } while (0)
+
+// Encodes (or fetches from the cache) a bf16 tensor map with 128-byte swizzle and zero OOB fill.
+// dims/strides are innermost-first; strides[0] is implied (2 bytes) and ignored.
+int bsl_get_tmap(bsl_ctx* ctx, const void* base, int rank, const uint64_t* dims,
+                 const uint64_t* strides_bytes, const uint32_t* box, CUtensorMap* out);
+
+// out[c] = sum over pixels of x[p*ld + c] (bf16 in, fp32 out), deterministic two-level reduction.
+int bsl_channel_sum_bf16(bsl_ctx* ctx, const void* x, long long pixels, int c, int ld, float* out,
+                         cudaStream_t stream);
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
