@@ -1,0 +1,438 @@
+// Normalisation (+ReLU, +2x2 max-pool) forward and backward, HBM-bound passes.
+//   slim.batch_norm  (FusedBatchNorm / FusedBatchNormGrad)  <- NetworksV2/base.py:154-162
+//   slim.instance_norm (moments + batch_normalization)      <- NetworksV2/base.py:163-165
+//   slim.max_pool2d 2x2 s2 (MaxPool / MaxPoolGrad)          <- NetworksV2/UNet.py:81
+//   ReluGrad                                                <- slim default activation_fn
+// Statistics are two-level deterministic reductions (reduce.cuh); the apply passes move 16 B per
+// thread per access along the NHWC channel axis.
+#include "reduce.cuh"
+
+using namespace bsl;
+
+namespace bsl {
+__global__ void pixel_reduce_final_kernel(const float* __restrict__ part, int blocks, int kc,
+                                          double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kc) return;
+  const float* p = part + (long long)blockIdx.y * blocks * kc + i;
+  double s = 0.0;
+  for (int b = 0; b < blocks; ++b) s += (double)p[(long long)b * kc];
+  out[(long long)blockIdx.y * kc + i] = s;
+}
+
+static float* g_scratch = nullptr;
+static size_t g_scratch_bytes = 0;
+int bsl_scratch(bsl_ctx* ctx, size_t bytes, float** out) {
+  if (bytes > g_scratch_bytes) {
+    if (g_scratch) cudaFree(g_scratch);
+    size_t want = bytes < (16u << 20) ? (16u << 20) : bytes;
+    g_scratch = nullptr;
+    g_scratch_bytes = 0;
+    BSL_CUDA(ctx, cudaMalloc(&g_scratch, want));
+    g_scratch_bytes = want;
+  }
+  *out = g_scratch;
+  return BSL_OK;
+}
+}  // namespace bsl
+
+namespace {
+
+struct StatsF {
+  static constexpr int K = 2;
+  const __nv_bfloat16* y;
+  int ld;
+  __device__ void operator()(long long p, int, int ch0, float (&acc)[2][8]) const {
+    float v[8];
+    unpack8(ld16(y + p * ld + ch0), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += v[j];
+      acc[1][j] += v[j] * v[j];
+    }
+  }
+};
+
+struct BwdF {
+  static constexpr int K = 2;
+  const __nv_bfloat16* y;
+  const __nv_bfloat16* da;
+  const float* mean;
+  const float* rstd;
+  const float* scale;
+  const float* shift;
+  int y_ld, da_ld, c, relu;
+  __device__ void operator()(long long p, int group, int ch0, float (&acc)[2][8]) const {
+    float v[8], g[8];
+    unpack8(ld16(y + p * y_ld + ch0), v);
+    unpack8(ld16(da + p * da_ld + ch0), g);
+    const int o = group * c + ch0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(v[j], scale[o + j], shift[o + j]);
+      const float dz = (!relu || z > 0.f) ? g[j] : 0.f;
+      const float xh = (v[j] - mean[o + j]) * rstd[o + j];
+      acc[0][j] += dz;
+      acc[1][j] += dz * xh;
+    }
+  }
+};
+
+__global__ void norm_finalize_kernel(int groups, int c, double m, float eps, float decay, int bn_training,
+                                     int use_moving, int center, int scale_flag, const double* __restrict__ sums,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* __restrict__ moving_mean, float* __restrict__ moving_var,
+                                     float* __restrict__ mean_o, float* __restrict__ rstd_o,
+                                     float* __restrict__ scale_o, float* __restrict__ shift_o) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= groups * c) return;
+  const int g = i / c, ch = i - g * c;
+  double mean, var;
+  if (use_moving) {
+    mean = moving_mean[ch];
+    var = moving_var[ch];
+  } else {
+    const double s0 = sums[(long long)g * 2 * c + ch];
+    const double s1 = sums[(long long)g * 2 * c + c + ch];
+    mean = s0 / m;
+    var = s1 / m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    if (bn_training) {  // FusedBatchNorm: moving variance is fed the Bessel-corrected estimate
+      const double unb = var * (m / (m > 1.0 ? m - 1.0 : 1.0));
+      moving_mean[ch] = (float)((double)moving_mean[ch] * decay + mean * (1.0 - (double)decay));
+      moving_var[ch] = (float)((double)moving_var[ch] * decay + unb * (1.0 - (double)decay));
+    }
+  }
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = (scale_flag ? gamma[ch] : 1.f) * rstd;
+  mean_o[i] = (float)mean;
+  rstd_o[i] = rstd;
+  scale_o[i] = sc;
+  shift_o[i] = (center ? beta[ch] : 0.f) - (float)mean * sc;
+}
+
+__global__ void norm_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, __nv_bfloat16* __restrict__ a,
+                                  int a_ld, long long pixels, int hw, int c, int per_sample, int relu,
+                                  const float* __restrict__ scale, const float* __restrict__ shift) {
+  const int cg = c / 8;
+  const long long total = pixels * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / cg;
+    const int ch0 = (int)(i - p * cg) * 8;
+    const int o = (per_sample ? (int)(p / hw) * c : 0) + ch0;
+    float v[8];
+    unpack8(ld16(y + p * y_ld + ch0), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z = fmaf(v[j], scale[o + j], shift[o + j]);
+      v[j] = relu ? fmaxf(z, 0.f) : z;
+    }
+    st16(a + p * a_ld + ch0, pack8(v));
+  }
+}
+
+// Same as norm_apply_kernel, and also emits the 2x2/s2 max-pooled tensor from the same read.
+__global__ void norm_apply_pool_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, __nv_bfloat16* __restrict__ a,
+                                       int a_ld, __nv_bfloat16* __restrict__ pooled, int p_ld, int n, int h, int w,
+                                       int c, int per_sample, int relu, const float* __restrict__ scale,
+                                       const float* __restrict__ shift) {
+  const int cg = c / 8, ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * ho * wo * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int ch0 = (int)(t % cg) * 8; t /= cg;
+    const int xo = (int)(t % wo); t /= wo;
+    const int yo = (int)(t % ho);
+    const int img = (int)(t / ho);
+    const int o = (per_sample ? img * c : 0) + ch0;
+    float sc[8], sh[8], mx[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = scale[o + j]; sh[j] = shift[o + j]; mx[j] = -INFINITY; }
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const long long p = ((long long)img * h + (2 * yo + dy)) * w + (2 * xo + dx);
+        float v[8];
+        unpack8(ld16(y + p * y_ld + ch0), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float z = fmaf(v[j], sc[j], sh[j]);
+          v[j] = relu ? fmaxf(z, 0.f) : z;
+        }
+        const uint4 packed = pack8(v);
+        st16(a + p * a_ld + ch0, packed);
+        float r[8];
+        unpack8(packed, r);  // pool the bf16-rounded values: what the next layer actually sees
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], r[j]);
+      }
+    const long long q = ((long long)img * ho + yo) * wo + xo;
+    st16(pooled + q * p_ld + ch0, pack8(mx));
+  }
+}
+
+__global__ void norm_bwd_finalize_kernel(int groups, int c, double m, const double* __restrict__ sums,
+                                         const float* __restrict__ rstd_unused, float* __restrict__ c1,
+                                         float* __restrict__ c2, float* __restrict__ dgamma,
+                                         float* __restrict__ dbeta) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double sg = 0.0, sb = 0.0;
+  for (int g = 0; g < groups; ++g) {  // fixed order
+    const double s0 = sums[(long long)g * 2 * c + ch];
+    const double s1 = sums[(long long)g * 2 * c + c + ch];
+    c1[g * c + ch] = (float)(s0 / m);
+    c2[g * c + ch] = (float)(s1 / m);
+    sb += s0;
+    sg += s1;
+  }
+  if (dgamma) dgamma[ch] = (float)sg;
+  if (dbeta) dbeta[ch] = (float)sb;
+  (void)rstd_unused;
+}
+
+__global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld,
+                                      const __nv_bfloat16* __restrict__ da, int da_ld,
+                                      __nv_bfloat16* __restrict__ dy, int dy_ld, long long pixels, int hw, int c,
+                                      int per_sample, int relu, const float* __restrict__ mean,
+                                      const float* __restrict__ rstd, const float* __restrict__ scale,
+                                      const float* __restrict__ shift, const float* __restrict__ c1,
+                                      const float* __restrict__ c2) {
+  const int cg = c / 8;
+  const long long total = pixels * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / cg;
+    const int ch0 = (int)(i - p * cg) * 8;
+    const int o = (per_sample ? (int)(p / hw) * c : 0) + ch0;
+    float v[8], g[8];
+    unpack8(ld16(y + p * y_ld + ch0), v);
+    unpack8(ld16(da + p * da_ld + ch0), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(v[j], scale[o + j], shift[o + j]);
+      const float dz = (!relu || z > 0.f) ? g[j] : 0.f;
+      const float xh = (v[j] - mean[o + j]) * rstd[o + j];
+      v[j] = scale[o + j] * (dz - c1[o + j] - xh * c2[o + j]);
+    }
+    st16(dy + p * dy_ld + ch0, pack8(v));
+  }
+}
+
+// da[n,2i+a,2j+b,:] = dskip (optional) + (first max of the window in scan order ? dpool[n,i,j,:] : 0)
+__global__ void maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ act, int a_ld,
+                                       const __nv_bfloat16* __restrict__ dpool, int p_ld,
+                                       const __nv_bfloat16* __restrict__ dskip, int s_ld,
+                                       __nv_bfloat16* __restrict__ out, int o_ld, int n, int h, int w, int c) {
+  const int cg = c / 8, ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * ho * wo * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int ch0 = (int)(t % cg) * 8; t /= cg;
+    const int xo = (int)(t % wo); t /= wo;
+    const int yo = (int)(t % ho);
+    const int img = (int)(t / ho);
+    float v[4][8], g[8];
+    long long pix[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      pix[k] = ((long long)img * h + (2 * yo + (k >> 1))) * w + (2 * xo + (k & 1));
+      unpack8(ld16(act + pix[k] * a_ld + ch0), v[k]);
+    }
+    unpack8(ld16(dpool + (((long long)img * ho + yo) * wo + xo) * p_ld + ch0), g);
+    int arg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int best = 0;
+      float bv = v[0][j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (v[k][j] > bv) { bv = v[k][j]; best = k; }  // strict '>' keeps the FIRST maximum
+      arg[j] = best;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float o[8];
+      if (dskip) unpack8(ld16(dskip + pix[k] * s_ld + ch0), o);
+      else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] += (arg[j] == k) ? g[j] : 0.f;
+      st16(out + pix[k] * o_ld + ch0, pack8(o));
+    }
+  }
+}
+
+__global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ dy,
+                                int dy_ld, __nv_bfloat16* __restrict__ out, int o_ld, long long pixels, int c) {
+  const int cg = c / 8;
+  const long long total = pixels * cg;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / cg;
+    const int ch0 = (int)(i - p * cg) * 8;
+    float v[8], g[8];
+    unpack8(ld16(y + p * y_ld + ch0), v);
+    unpack8(ld16(dy + p * dy_ld + ch0), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = v[j] > 0.f ? g[j] : 0.f;
+    st16(out + p * o_ld + ch0, pack8(g));
+  }
+}
+
+unsigned ew_grid(bsl_ctx* ctx, long long items) {
+  long long b = (items + 255) / 256;
+  const long long cap = 16LL * ctx->sm_count;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int check_norm(bsl_ctx* ctx, const bsl_norm_desc* d) {
+  if (!ctx) return BSL_EINVAL;
+  if (!d) return bsl_fail(ctx, BSL_EINVAL, "norm: null descriptor");
+  if (d->mode != 0 && d->mode != 1) return bsl_fail(ctx, BSL_EINVAL, "norm: mode %d", d->mode);
+  if (d->n <= 0 || d->hw <= 0 || d->c <= 0 || d->c % 8)
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "norm: n=%d hw=%d c=%d (c must be a multiple of 8)", d->n, d->hw, d->c);
+  if (d->x_ld < d->c || d->y_ld < d->c || d->x_ld % 8 || d->y_ld % 8)
+    return bsl_fail(ctx, BSL_EINVAL, "norm: bad channel strides");
+  return BSL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bsl_norm_stats(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, double* sums, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (!x || !sums) return bsl_fail(ctx, BSL_EINVAL, "norm_stats: null buffer");
+  StatsF f{reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld};
+  const int groups = d->mode ? d->n : 1;
+  const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
+  return run_pixel_reduce(ctx, f, ppg, groups, d->c, sums, as_stream(stream));
+}
+
+int bsl_norm_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, int is_training, const double* sums,
+                      const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                      float* mean, float* rstd, float* scale, float* shift, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  const int groups = d->mode ? d->n : 1;
+  const int bn = d->mode == 0;
+  const int use_moving = bn && !is_training;
+  if ((!use_moving && !sums) || !mean || !rstd || !scale || !shift || (d->scale && !gamma) || (d->center && !beta))
+    return bsl_fail(ctx, BSL_EINVAL, "norm_finalize: null buffer");
+  if (bn && (!moving_mean || !moving_var)) return bsl_fail(ctx, BSL_EINVAL, "norm_finalize: moving stats required");
+  const double m = d->mode ? (double)d->hw : (double)d->n * d->hw;
+  const int total = groups * d->c;
+  norm_finalize_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(
+      groups, d->c, m, d->eps, d->decay, bn && is_training, use_moving, d->center, d->scale, sums, gamma, beta,
+      moving_mean, moving_var, mean, rstd, scale, shift);
+  BSL_LAUNCH_CHECK(ctx, "norm_finalize_kernel");
+  return BSL_OK;
+}
+
+int bsl_norm_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const float* scale, const float* shift,
+                   void* y, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (!x || !scale || !shift || !y) return bsl_fail(ctx, BSL_EINVAL, "norm_apply: null buffer");
+  const long long pixels = (long long)d->n * d->hw;
+  norm_apply_kernel<<<ew_grid(ctx, pixels * (d->c / 8)), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld, reinterpret_cast<__nv_bfloat16*>(y), d->y_ld, pixels,
+      d->hw, d->c, d->mode, d->relu, scale, shift);
+  BSL_LAUNCH_CHECK(ctx, "norm_apply_kernel");
+  return BSL_OK;
+}
+
+int bsl_norm_apply_pool(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, const void* x, const float* scale,
+                        const float* shift, void* y, void* pooled, int pooled_ld, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (!x || !scale || !shift || !y || !pooled) return bsl_fail(ctx, BSL_EINVAL, "norm_apply_pool: null buffer");
+  if (h * w != d->hw || (h & 1) || (w & 1) || pooled_ld < d->c || pooled_ld % 8)
+    return bsl_fail(ctx, BSL_EINVAL, "norm_apply_pool: h=%d w=%d must be even and match hw=%d", h, w, d->hw);
+  const long long items = (long long)d->n * (h / 2) * (w / 2) * (d->c / 8);
+  norm_apply_pool_kernel<<<ew_grid(ctx, items), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld, reinterpret_cast<__nv_bfloat16*>(y), d->y_ld,
+      reinterpret_cast<__nv_bfloat16*>(pooled), pooled_ld, d->n, h, w, d->c, d->mode, d->relu, scale, shift);
+  BSL_LAUNCH_CHECK(ctx, "norm_apply_pool_kernel");
+  return BSL_OK;
+}
+
+int bsl_norm_bwd_reduce(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
+                        const float* mean, const float* rstd, const float* scale, const float* shift,
+                        double* sums, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (!x || !dy || !mean || !rstd || !scale || !shift || !sums)
+    return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_reduce: null buffer");
+  BwdF f{reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), mean, rstd, scale,
+         shift, d->x_ld, dy_ld, d->c, d->relu};
+  const int groups = d->mode ? d->n : 1;
+  const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
+  return run_pixel_reduce(ctx, f, ppg, groups, d->c, sums, as_stream(stream));
+}
+
+int bsl_norm_bwd_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, const double* sums, float* c1, float* c2,
+                          float* dgamma, float* dbeta, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (!sums || !c1 || !c2) return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_finalize: null buffer");
+  const int groups = d->mode ? d->n : 1;
+  const double m = d->mode ? (double)d->hw : (double)d->n * d->hw;
+  norm_bwd_finalize_kernel<<<(d->c + 127) / 128, 128, 0, as_stream(stream)>>>(groups, d->c, m, sums, nullptr, c1, c2,
+                                                                             dgamma, dbeta);
+  BSL_LAUNCH_CHECK(ctx, "norm_bwd_finalize_kernel");
+  return BSL_OK;
+}
+
+int bsl_norm_bwd_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
+                       const float* mean, const float* rstd, const float* scale, const float* shift,
+                       const float* c1, const float* c2, void* dx, int dx_ld, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (!x || !dy || !mean || !rstd || !scale || !shift || !c1 || !c2 || !dx)
+    return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_apply: null buffer");
+  const long long pixels = (long long)d->n * d->hw;
+  norm_bwd_apply_kernel<<<ew_grid(ctx, pixels * (d->c / 8)), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld, reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld,
+      reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, pixels, d->hw, d->c, d->mode, d->relu, mean, rstd, scale, shift,
+      c1, c2);
+  BSL_LAUNCH_CHECK(ctx, "norm_bwd_apply_kernel");
+  return BSL_OK;
+}
+
+int bsl_maxpool2x2_bwd_add(bsl_ctx* ctx, int n, int h, int w, int c, const void* act, int act_ld,
+                           const void* dpool, int dpool_ld, const void* dskip, int dskip_ld, void* dact,
+                           int dact_ld, void* stream) {
+  if (!ctx) return BSL_EINVAL;
+  if (!act || !dpool || !dact) return bsl_fail(ctx, BSL_EINVAL, "maxpool_bwd: null buffer");
+  if ((h & 1) || (w & 1) || c % 8) return bsl_fail(ctx, BSL_EUNSUPPORTED, "maxpool_bwd: h,w even, c%%8==0");
+  const long long items = (long long)n * (h / 2) * (w / 2) * (c / 8);
+  maxpool_bwd_add_kernel<<<ew_grid(ctx, items), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(act), act_ld, reinterpret_cast<const __nv_bfloat16*>(dpool), dpool_ld,
+      reinterpret_cast<const __nv_bfloat16*>(dskip), dskip_ld, reinterpret_cast<__nv_bfloat16*>(dact), dact_ld, n, h,
+      w, c);
+  BSL_LAUNCH_CHECK(ctx, "maxpool_bwd_add_kernel");
+  return BSL_OK;
+}
+
+int bsl_relu_bwd(bsl_ctx* ctx, long long pixels, int c, const void* y, int y_ld, const void* dy, int dy_ld,
+                 void* out, int out_ld, void* stream) {
+  if (!ctx) return BSL_EINVAL;
+  if (!y || !dy || !out) return bsl_fail(ctx, BSL_EINVAL, "relu_bwd: null buffer");
+  if (c % 8) return bsl_fail(ctx, BSL_EUNSUPPORTED, "relu_bwd: c%%8");
+  relu_bwd_kernel<<<ew_grid(ctx, pixels * (c / 8)), 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(y), y_ld, reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld,
+      reinterpret_cast<__nv_bfloat16*>(out), out_ld, pixels, c);
+  BSL_LAUNCH_CHECK(ctx, "relu_bwd_kernel");
+  return BSL_OK;
+}
+
+}  // extern "C"

@@ -3,7 +3,7 @@
 // axis, and reduce with warp shuffles + a fixed-order second level (no float atomics), so results
 // are bit-reproducible run to run.
 #include <cuda_bf16.h>
-#include "internal.h"
+#include "reduce.cuh"
 
 namespace {
 
@@ -44,85 +44,38 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, floa
     for (size_t j = n & ~(size_t)3; j < n; ++j) dst[j] = __bfloat162float(src[j]);
 }
 
-// Partial per-channel sums: block b covers pixels [b*ppb, (b+1)*ppb); thread layout is
-// (pixel lane, 8-channel group) so every access is a 16 B load of 8 consecutive channels.
-__global__ void channel_sum_partial_kernel(const __nv_bfloat16* __restrict__ x, long long pixels, int c,
-                                           int ld, long long ppb, float* __restrict__ part) {
-  extern __shared__ float sm[];  // [rows][c]
-  const int groups = c / 8;
-  const int rows = blockDim.x / groups;
-  const int g = threadIdx.x % groups;
-  const int r = threadIdx.x / groups;
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (r < rows) {
-    const long long p0 = blockIdx.x * ppb;
-    const long long p1 = min(pixels, p0 + ppb);
-    for (long long p = p0 + r; p < p1; p += rows) {
-      uint4 v = *reinterpret_cast<const uint4*>(x + p * ld + g * 8);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+struct SumF {
+  static constexpr int K = 1;
+  const __nv_bfloat16* x;
+  int ld;
+  __device__ void operator()(long long p, int, int ch0, float (&acc)[1][8]) const {
+    float v[8];
+    bsl::unpack8(bsl::ld16(x + p * ld + ch0), v);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(h[j]);
-        acc[2 * j] += f.x;
-        acc[2 * j + 1] += f.y;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sm[r * c + g * 8 + j] = acc[j];
+    for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
   }
-  __syncthreads();
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float s = 0.f;
-    for (int rr = 0; rr < rows; ++rr) s += sm[rr * c + ch];
-    part[(long long)blockIdx.x * c + ch] = s;
-  }
-}
+};
 
-__global__ void channel_sum_final_kernel(const float* __restrict__ part, int blocks, int c,
-                                         float* __restrict__ out) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += part[(long long)b * c + ch];
-  out[ch] = s;
+__global__ void f64_to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (float)src[i];
 }
 
 }  // namespace
 
-// Scratch for second-level reductions lives in the context (grown on demand, never shrunk).
-static int scratch(bsl_ctx* ctx, size_t bytes, float** out);
-
 int bsl_channel_sum_bf16(bsl_ctx* ctx, const void* x, long long pixels, int c, int ld, float* out,
                          cudaStream_t stream) {
-  if (c % 8 || c > 2048) return bsl_fail(ctx, BSL_EUNSUPPORTED, "channel_sum: c=%d", c);
-  const int groups = c / 8;
-  int threads = kThreads;
-  if (threads < groups) threads = groups;
-  const int rows = threads / groups;
-  const int blocks = (int)grid_for(pixels, 2048, 4 * ctx->sm_count);
-  const long long ppb = (pixels + blocks - 1) / blocks;
-  float* part = nullptr;
-  int rc = scratch(ctx, (size_t)blocks * c * sizeof(float), &part);
+  // fp64 second level lands in the tail of the scratch arena, then narrows to fp32.
+  SumF f{reinterpret_cast<const __nv_bfloat16*>(x), ld};
+  bsl::ReducePlan p = bsl::plan_reduce(ctx, pixels, 1, c, 1);
+  float* base = nullptr;
+  int rc = bsl::bsl_scratch(ctx, p.scratch_bytes + (size_t)c * sizeof(double) + 16, &base);
   if (rc) return rc;
-  channel_sum_partial_kernel<<<blocks, threads, (size_t)rows * c * sizeof(float), stream>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), pixels, c, ld, ppb, part);
-  BSL_LAUNCH_CHECK(ctx, "channel_sum_partial_kernel");
-  channel_sum_final_kernel<<<(c + 127) / 128, 128, 0, stream>>>(part, blocks, c, out);
-  BSL_LAUNCH_CHECK(ctx, "channel_sum_final_kernel");
-  return BSL_OK;
-}
-
-static float* g_scratch = nullptr;
-static size_t g_scratch_bytes = 0;
-static int scratch(bsl_ctx* ctx, size_t bytes, float** out) {
-  if (bytes > g_scratch_bytes) {
-    // Grown only outside graph capture in practice: first (eager) step sizes it for the model.
-    if (g_scratch) cudaFree(g_scratch);
-    size_t want = bytes < (8u << 20) ? (8u << 20) : bytes;
-    BSL_CUDA(ctx, cudaMalloc(&g_scratch, want));
-    g_scratch_bytes = want;
-  }
-  *out = g_scratch;
+  double* tmp = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + ((p.scratch_bytes + 15) & ~(size_t)15));
+  rc = bsl::run_pixel_reduce(ctx, f, pixels, 1, c, tmp, stream);
+  if (rc) return rc;
+  f64_to_f32_kernel<<<(c + 127) / 128, 128, 0, stream>>>(tmp, out, c);
+  BSL_LAUNCH_CHECK(ctx, "f64_to_f32_kernel");
   return BSL_OK;
 }
 

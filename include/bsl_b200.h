@@ -120,6 +120,119 @@ int bsl_convT2d_bwd_filter(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* 
                            const void* dyr_bf16, float* dw_kkoi_f32, float* dbias_f32, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ stem + logits convolutions
+ * CUDA-core kernels for the two HBM-bound layers (0.26 % of the FLOPs).
+ * Stem:   slim.conv2d(images, 64, 3) on the fp32 input images -- NetworksV2/UNet.py:79 (first call);
+ *         x fp32 [n,h,w,cin], w fp32 HWIO, y bf16 (pre-norm), dw fp32. No dgrad (inputs have none).
+ * Logits: slim.conv2d(x, num_classes, 1, activation_fn=None) + bias -- NetworksV2/UNet.py:100;
+ *         x bf16, w fp32 [cin][classes], logits / dlogits fp32 [n,h,w,classes] dense. */
+int bsl_conv2d_stem_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x_f32, const float* w_hwio_f32,
+                          void* y_bf16, void* stream);
+int bsl_conv2d_stem_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x_f32, const void* dy_bf16,
+                          float* dw_hwio_f32, void* stream);
+int bsl_conv2d_head_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x_bf16, const float* w_f32,
+                          const float* bias_f32, float* logits_f32, void* stream);
+int bsl_conv2d_head_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* dlogits_f32, const float* w_f32,
+                          void* dx_bf16, void* stream);
+int bsl_conv2d_head_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x_bf16, const float* dlogits_f32,
+                          float* dw_f32, float* dbias_f32, void* stream);
+
+/* ------------------------------------------------------------------ normalisation (+ReLU, +pool)
+ * slim.batch_norm (scale=True, runtime is_training, eps 1e-3, decay .999) and slim.instance_norm
+ * (eps 1e-6) as selected by BaseNet._get_normalization -- NetworksV2/base.py:153-169; the ReLU is
+ * slim.conv2d's default activation_fn and the 2x2/s2 max-pool is NetworksV2/UNet.py:81.
+ * Pipeline per layer: stats -> finalize -> apply[_pool]; backward: bwd_reduce -> bwd_finalize ->
+ * bwd_apply. `sums` are fp64 [groups][2][c] with groups = 1 (batch) or n (instance); mean / rstd /
+ * scale / shift / c1 / c2 are fp32 [groups][c]. is_training is a RUNTIME argument (base.py:77). */
+typedef struct {
+  int mode;          /* 0 = batch_norm, 1 = instance_norm */
+  int n, hw, c;      /* hw = product of the spatial dims (2-D or 3-D) */
+  int x_ld, y_ld;    /* channel strides of the pre-norm tensor and of the activation output */
+  float eps;
+  float decay;       /* moving-average decay (batch_norm) */
+  int relu;          /* fuse ReLU after the affine transform */
+  int center, scale; /* beta / gamma present */
+} bsl_norm_desc;
+
+int bsl_norm_stats(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, double* sums, void* stream);
+int bsl_norm_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, int is_training, const double* sums,
+                      const float* gamma, const float* beta, float* moving_mean, float* moving_var,
+                      float* mean, float* rstd, float* scale, float* shift, void* stream);
+int bsl_norm_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const float* scale,
+                   const float* shift, void* y_bf16, void* stream);
+int bsl_norm_apply_pool(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, const void* x_bf16,
+                        const float* scale, const float* shift, void* y_bf16, void* pooled_bf16,
+                        int pooled_ld, void* stream);
+/* dy is the gradient w.r.t. the (post-ReLU) activation, with channel stride dy_ld. */
+int bsl_norm_bwd_reduce(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const void* dy_bf16, int dy_ld,
+                        const float* mean, const float* rstd, const float* scale, const float* shift,
+                        double* sums, void* stream);
+int bsl_norm_bwd_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, const double* sums, float* c1, float* c2,
+                          float* dgamma, float* dbeta, void* stream);
+int bsl_norm_bwd_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const void* dy_bf16, int dy_ld,
+                       const float* mean, const float* rstd, const float* scale, const float* shift,
+                       const float* c1, const float* c2, void* dx_bf16, int dx_ld, void* stream);
+/* MaxPoolGrad (first maximum in scan order wins ties) fused with the skip-connection add:
+ * dact = dskip (nullable) + unpool(dpool). */
+int bsl_maxpool2x2_bwd_add(bsl_ctx* ctx, int n, int h, int w, int c, const void* act_bf16, int act_ld,
+                           const void* dpool_bf16, int dpool_ld, const void* dskip_bf16, int dskip_ld,
+                           void* dact_bf16, int dact_ld, void* stream);
+/* ReluGrad: out = dy * (y > 0). */
+int bsl_relu_bwd(bsl_ctx* ctx, long long pixels, int c, const void* y_bf16, int y_ld, const void* dy_bf16,
+                 int dy_ld, void* out_bf16, int out_ld, void* stream);
+
+/* ------------------------------------------------------------------ losses, masks, Dice counts
+ * loss_metrics._compute_weights / weighted_sparse_softmax_cross_entropy / sparse_dice_loss
+ * (/root/reference/loss_metrics.py:115-226), slim.softmax + (p > 0.5) uint8 masks
+ * (NetworksV2/UNet.py:107-117) and the integer sums behind metric_dice/voe/vd (loss_metrics.py:261-339).
+ * logits / dlogits / prob are dense fp32 [n*hw][classes]; labels int32 [n*hw]. */
+typedef struct {
+  int n, hw, classes;      /* classes in 2..4 */
+  int weight_type;         /* 0 none, 1 numerical, 2 proportion */
+  float numeric_w[8];
+  float proportion_decay;  /* <= 0: not applied */
+  float loss_scale;        /* multiplies dlogits: 1/R under R-way data parallelism */
+} bsl_loss_desc;
+
+size_t bsl_loss_workspace(bsl_ctx* ctx, const bsl_loss_desc* d);
+int bsl_label_counts(bsl_ctx* ctx, const bsl_loss_desc* d, const int* labels, int* counts /*[n][classes]*/,
+                     void* stream);
+int bsl_wxent_fwd_bwd(bsl_ctx* ctx, const bsl_loss_desc* d, const float* logits, const int* labels,
+                      const int* counts, float* loss, float* dlogits /*nullable*/, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int bsl_dice_fwd_bwd(bsl_ctx* ctx, const bsl_loss_desc* d, const float* logits, const int* labels, float* loss,
+                     float* dlogits /*nullable*/, int accumulate, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* Any of prob [n*hw][classes], masks uint8 [classes-1][n*hw], argmax uint8 [n*hw] and
+ * ilr uint32 [n][classes-1][3] = (intersection, left=pred, right=label) may be null. */
+int bsl_softmax_threshold(bsl_ctx* ctx, const bsl_loss_desc* d, const float* logits, const int* labels,
+                          float* prob, uint8_t* masks, uint8_t* argmax, unsigned int* ilr, void* stream);
+
+/* ------------------------------------------------------------------ fused optimizer step
+ * tf.train.AdamOptimizer(lr, 0.9, 0.99) / MomentumOptimizer(lr, 0.9) -- /root/reference/core/solver.py:204-219,
+ * with slim.l2_regularizer folded in (grad += l2_rate * w) -- NetworksV2/base.py:128-135.
+ * Works on flat arenas; also emits the bf16 shadow weights and (optionally) sum(w^2) of the
+ * pre-update weights for the reported regularisation loss. */
+typedef struct {
+  float lr, beta1, beta2, eps;
+  float l2_rate;     /* 0 for parameters without a regulariser (norm gamma / beta) */
+  float grad_scale;  /* applied to g before use */
+  int step;          /* t >= 1 */
+} bsl_adam_desc;
+
+int bsl_adam_step(bsl_ctx* ctx, const bsl_adam_desc* d, float* w, const float* g, float* m, float* v,
+                  void* w_bf16 /*nullable*/, size_t n, double* sumsq_out /*nullable*/, void* stream);
+int bsl_momentum_step(bsl_ctx* ctx, float lr, float momentum, float l2_rate, float grad_scale, float* w,
+                      const float* g, float* acc, void* w_bf16, size_t n, double* sumsq_out, void* stream);
+
+/* ------------------------------------------------------------------ data-parallel gradient exchange
+ * Replaces MirroredStrategy's NCCL all-reduce -- /root/reference/utils/distribution_utils.py:85-98.
+ * One process per GPU; rank 0 creates the 128-byte id, the host distributes it (any side channel). */
+int bsl_comm_unique_id(bsl_ctx* ctx, void* id128);
+int bsl_comm_init(bsl_ctx* ctx, const void* id128, int rank, int world);
+int bsl_allreduce_sum_f32(bsl_ctx* ctx, float* buf, size_t n, void* stream);
+int bsl_comm_destroy(bsl_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif
