@@ -1,0 +1,532 @@
+"""U-Net 2-D training / inference engine on the sm_100a kernels (host side, Python + ctypes only).
+
+What TF's executor does for the reference's graph (/root/reference/NetworksV2/UNet.py:58-155 built by
+BaseNet.__call__, differentiated and updated by Solver, /root/reference/core/solver.py:221-243) this
+module does explicitly: it plans every buffer once, then a step is a fixed sequence of C-ABI enqueues
+on one compute stream (plus a side stream for the gradient all-reduce), replayable as a CUDA graph.
+
+Memory plan (all NHWC, bf16 unless noted):
+  * per conv layer: `y` (pre-norm conv output, kept for backward) and `a` (post norm+ReLU);
+  * skip-concat is zero-copy: encoder level i writes `a` into channels [0,C) of cat_i, the
+    transposed conv writes into [C,2C) (UNet.py:93 order: skip first, up second);
+  * parameters live in flat fp32 arenas W / G / M / V with a bf16 shadow of W for the tensor-core
+    convs; region A (L2-regularised: weights, biases) precedes region B (gamma, beta);
+  * two ping-pong gradient buffers + one dcat_i per level carry activation gradients.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .device import Context, DeviceBuffer, f32_to_bf16_bits
+
+F32 = 4
+BF16 = 2
+
+
+@dataclass
+class EngineConfig:
+    batch: int
+    height: int = 256
+    width: int = 256
+    channel: int = 3
+    classes: tuple = ("Background", "Liver", "Tumor")
+    init_channels: int = 64
+    num_down_samples: int = 4
+    normalizer: str = "batch_norm"
+    weight_decay_rate: float = 1e-5
+    bias_decay: bool = False
+    loss_type: str = "xentropy"
+    loss_weight_type: str = "none"
+    loss_numeric_w: tuple = ()
+    loss_proportion_decay: float = 1000.0
+    optimizer: str = "adam"
+    bn_decay: float = 0.999
+    bn_eps: float = 1e-3
+    in_eps: float = 1e-6
+    training: bool = True            # allocate backward / optimizer state
+    world: int = 1                   # data-parallel replicas (gradient mean over `world`)
+
+    @property
+    def num_classes(self):
+        return len(self.classes)
+
+
+class View:
+    """A strided NHWC window into a device buffer: channels [c0, c0+c) of a tensor with stride ld."""
+
+    def __init__(self, buf: DeviceBuffer, n, h, w, c, ld=None, c0=0, esize=BF16):
+        self.buf, self.n, self.h, self.w, self.c = buf, n, h, w, c
+        self.ld = ld or c
+        self.c0 = c0
+        self.esize = esize
+
+    @property
+    def p(self) -> C.c_void_p:
+        return C.c_void_p(self.buf.ptr + self.c0 * self.esize)
+
+    @property
+    def pixels(self):
+        return self.n * self.h * self.w
+
+    def slice(self, c0, c):
+        return View(self.buf, self.n, self.h, self.w, c, self.ld, self.c0 + c0, self.esize)
+
+
+@dataclass
+class Param:
+    name: str
+    shape: tuple
+    offset: int = 0          # element offset in the arena
+    size: int = 0
+    region: str = "A"        # "A" regularised, "B" not, "S" moving statistics (not trained)
+
+
+@dataclass
+class ConvL:
+    kind: str                # "stem" | "conv" | "convT" | "logits"
+    scope: str
+    cin: int
+    cout: int
+    h: int
+    w: int                   # INPUT spatial size
+    level: int
+    x: View = None
+    y: View = None           # pre-norm conv output (conv/stem), or output (convT)
+    a: View = None           # post-activation
+    pooled: View = None
+    params: dict = field(default_factory=dict)
+    norm: dict = field(default_factory=dict)
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+class UNetEngine:
+    def __init__(self, ctx: Context, cfg: EngineConfig):
+        self.ctx, self.cfg = ctx, cfg
+        if cfg.init_channels % 64:
+            raise ValueError("init_channels must be a multiple of 64 for the tcgen05 conv path")
+        ds = 2 ** cfg.num_down_samples
+        if cfg.height % ds or cfg.width % ds:
+            raise ValueError(f"height/width must be multiples of {ds}")
+        if cfg.loss_type not in ("xentropy", "dice"):
+            raise ValueError("Not supported loss_type: {}".format(cfg.loss_type))  # UNet.py:132
+        if cfg.loss_weight_type not in ("none", "numerical", "proportion"):
+            raise ValueError("Not supported weight type: " + cfg.loss_weight_type)
+        if cfg.loss_weight_type == "numerical" and len(cfg.loss_numeric_w) != cfg.num_classes:
+            raise KeyError("w_type `numerical` need keyword argument `numeric_w` (one value per class)")
+        self.step_count = 0
+        self._bufs = []
+        self._plan_params()
+        self._plan_activations()
+        self.stream = ctx.stream
+        self.comm_stream = None
+        self._graph = None
+
+    # ------------------------------------------------------------------ planning
+    def _alloc(self, nbytes) -> DeviceBuffer:
+        b = self.ctx.alloc(max(int(nbytes), 16))
+        self._bufs.append(b)
+        return b
+
+    def _layer_specs(self):
+        cfg = self.cfg
+        specs = []
+        c, cin = cfg.init_channels, cfg.channel
+        h, w = cfg.height, cfg.width
+        for i in range(cfg.num_down_samples):
+            for j in (1, 2):
+                kind = "stem" if (i == 0 and j == 1) else "conv"
+                specs.append(ConvL(kind, f"UNet/Encode{i + 1}/Repeat/convolution2d_{j}", cin, c, h, w, i))
+                cin = c
+            c *= 2
+            h //= 2
+            w //= 2
+        for j in (1, 2):
+            specs.append(ConvL("conv", f"UNet/ED-Bridge/convolution2d_{j}", cin, c, h, w, cfg.num_down_samples))
+            cin = c
+        for i in reversed(range(cfg.num_down_samples)):
+            c //= 2
+            specs.append(ConvL("convT", f"UNet/Decode{i + 1}/Conv2d_transpose", cin, cin // 2, h, w, i))
+            h *= 2
+            w *= 2
+            for j in (1, 2):
+                specs.append(ConvL("conv", f"UNet/Decode{i + 1}/Repeat/convolution2d_{j}",
+                                   c + cin // 2 if j == 1 else c, c, h, w, i))
+            cin = c
+        specs.append(ConvL("logits", "UNet/AdjustChannels", cin, cfg.num_classes, h, w, 0))
+        return specs
+
+    def _plan_params(self):
+        cfg = self.cfg
+        self.layers = self._layer_specs()
+        ns = "BatchNorm" if cfg.normalizer == "batch_norm" else "InstanceNorm"
+        self.norm_scope = ns
+        plist = []
+        for L in self.layers:
+            if L.kind in ("stem", "conv"):
+                plist.append(Param(f"{L.scope}/weights", (3, 3, L.cin, L.cout)))
+                plist.append(Param(f"{L.scope}/{ns}/gamma", (L.cout,), region="B"))
+                plist.append(Param(f"{L.scope}/{ns}/beta", (L.cout,), region="B"))
+                if cfg.normalizer == "batch_norm":
+                    plist.append(Param(f"{L.scope}/{ns}/moving_mean", (L.cout,), region="S"))
+                    plist.append(Param(f"{L.scope}/{ns}/moving_variance", (L.cout,), region="S"))
+            elif L.kind == "convT":
+                plist.append(Param(f"{L.scope}/weights", (2, 2, L.cout, L.cin)))
+                plist.append(Param(f"{L.scope}/biases", (L.cout,), region="B" if cfg.bias_decay else "A"))
+            else:
+                plist.append(Param(f"{L.scope}/weights", (1, 1, L.cin, L.cout)))
+                plist.append(Param(f"{L.scope}/biases", (L.cout,), region="B" if cfg.bias_decay else "A"))
+        off = 0
+        for region in ("A", "B"):
+            for p in plist:
+                if p.region == region:
+                    p.size = int(np.prod(p.shape))
+                    p.offset = off
+                    off += _align(p.size)
+            if region == "A":
+                self.n_reg = off
+        self.n_train = off
+        soff = 0
+        for p in plist:
+            if p.region == "S":
+                p.size = int(np.prod(p.shape))
+                p.offset = soff
+                soff += _align(p.size)
+        self.n_stats = soff
+        self.params = {p.name: p for p in plist}
+        self.W = self._alloc(self.n_train * F32)
+        self.Wbf = self._alloc(self.n_train * BF16)
+        self.S = self._alloc(max(self.n_stats, 1) * F32)
+        if cfg.training:
+            self.G = self._alloc(self.n_train * F32).zero()
+            self.M = self._alloc(self.n_train * F32).zero()
+            self.V = self._alloc(self.n_train * F32).zero() if cfg.optimizer == "adam" else None
+        self.sumsq = self._alloc(16)
+
+    def _pp(self, arena: DeviceBuffer, name: str, esize=F32) -> C.c_void_p:
+        return C.c_void_p(arena.ptr + self.params[name].offset * esize)
+
+    def _plan_activations(self):
+        cfg = self.cfg
+        n = cfg.batch
+        cat = {}
+        max_act = 0
+        prev_a = None
+        groups_max = n if cfg.normalizer == "instance_norm" else 1
+        small = 0  # floats for per-layer normalisation scalars
+        for L in self.layers:
+            if L.kind in ("stem", "conv"):
+                L.y = View(self._alloc(n * L.h * L.w * L.cout * BF16), n, L.h, L.w, L.cout)
+                is_enc2 = L.scope.startswith("UNet/Encode") and L.scope.endswith("_2")
+                if is_enc2:
+                    cbuf = View(self._alloc(n * L.h * L.w * 2 * L.cout * BF16), n, L.h, L.w, 2 * L.cout)
+                    cat[L.level] = cbuf
+                    L.a = cbuf.slice(0, L.cout)
+                    L.pooled = View(self._alloc(n * (L.h // 2) * (L.w // 2) * L.cout * BF16), n, L.h // 2, L.w // 2,
+                                    L.cout)
+                else:
+                    L.a = View(self._alloc(n * L.h * L.w * L.cout * BF16), n, L.h, L.w, L.cout)
+                if L.kind == "conv":
+                    is_dec1 = L.scope.startswith("UNet/Decode") and L.scope.endswith("_1")
+                    L.x = cat[L.level] if is_dec1 else prev_a
+                prev_a = L.pooled if is_enc2 else L.a
+                g = groups_max
+                L.norm = dict(groups=g, off=small)
+                small += 10 * _align(g * L.cout, 16)  # sums (2 x f64 = 4 float slots), mean, rstd, scale, shift, c1, c2
+                max_act = max(max_act, L.h * L.w * L.cout)
+            elif L.kind == "convT":
+                L.x = prev_a
+                L.a = cat[L.level].slice(L.cout, L.cout)   # upper channel half of the concat buffer
+                L.y = L.a
+                prev_a = cat[L.level]
+            else:
+                L.x = prev_a
+        self.cat = cat
+        self.images = self._alloc(n * cfg.height * cfg.width * cfg.channel * F32)
+        self.labels = self._alloc(n * cfg.height * cfg.width * 4)
+        npx = n * cfg.height * cfg.width
+        self.logits = self._alloc(npx * cfg.num_classes * F32)
+        self.prob = self._alloc(npx * cfg.num_classes * F32)
+        self.masks = self._alloc(npx * (cfg.num_classes - 1))
+        self.argmax = self._alloc(npx)
+        self.ilr = self._alloc(n * (cfg.num_classes - 1) * 3 * 4)
+        self.counts = self._alloc(n * cfg.num_classes * 4)
+        self.loss_dev = self._alloc(16)
+        self.small = self._alloc(max(small, 16) * F32)
+        ld = self._loss_desc()
+        self.loss_ws_bytes = self.ctx.lib.bsl_loss_workspace(self.ctx.h, C.byref(ld))
+        self.loss_ws = self._alloc(self.loss_ws_bytes)
+        if cfg.training:
+            self.dlogits = self._alloc(npx * cfg.num_classes * F32)
+            self.g1 = self._alloc(n * max_act * BF16)
+            self.g2 = self._alloc(n * max_act * BF16)
+            self.dcat = {i: View(self._alloc(v.pixels * v.c * BF16), n, v.h, v.w, v.c) for i, v in cat.items()}
+            ws = 0
+            for L in self.layers:
+                if L.kind == "conv":
+                    d = self._conv_desc(L)
+                    ws = max(ws, self.ctx.lib.bsl_conv2d_wgrad_workspace(self.ctx.h, C.byref(d)))
+                elif L.kind == "convT":
+                    d = self._convT_desc(L)
+                    ws = max(ws, self.ctx.lib.bsl_convT2d_bwd_filter_workspace(self.ctx.h, C.byref(d)))
+            self.wgrad_ws_bytes = int(ws)
+            self.wgrad_ws = self._alloc(max(ws, 16))
+
+    # ------------------------------------------------------------------ descriptors
+    def _conv_desc(self, L: ConvL):
+        k = 1 if L.kind == "logits" else 3
+        x_ld = L.x.ld if L.x is not None else L.cin
+        y_ld = L.y.ld if L.y is not None else L.cout
+        return _lib.Conv2dDesc(self.cfg.batch, L.h, L.w, L.cin, L.cout, k, k, x_ld, y_ld)
+
+    def _convT_desc(self, L: ConvL):
+        return _lib.ConvT2dDesc(self.cfg.batch, L.h, L.w, L.cin, L.cout, L.x.ld, L.a.ld, 1)
+
+    def _norm_desc(self, L: ConvL):
+        cfg = self.cfg
+        bn = cfg.normalizer == "batch_norm"
+        return _lib.NormDesc(0 if bn else 1, cfg.batch, L.h * L.w, L.cout, L.y.ld, L.a.ld,
+                             cfg.bn_eps if bn else cfg.in_eps, cfg.bn_decay, 1, 1, 1)
+
+    def _loss_desc(self):
+        cfg = self.cfg
+        wt = {"none": 0, "numerical": 1, "proportion": 2}[cfg.loss_weight_type]
+        nw = (C.c_float * 8)(*([float(x) for x in cfg.loss_numeric_w] + [0.0] * (8 - len(cfg.loss_numeric_w))))
+        return _lib.LossDesc(cfg.batch, cfg.height * cfg.width, cfg.num_classes, wt, nw,
+                             float(cfg.loss_proportion_decay), 1.0 / cfg.world)
+
+    def _norm_ptrs(self, L: ConvL):
+        """sums (f64 x 2), mean, rstd, scale, shift, c1, c2 carved from the small-scalar arena."""
+        g = L.norm["groups"]
+        n = _align(g * L.cout, 16)
+        base = self.small.ptr + L.norm["off"] * F32
+        names = ["sums", "_s1", "_s2", "_s3", "mean", "rstd", "scale", "shift", "c1", "c2"]
+        return {nm: C.c_void_p(base + i * n * F32) for i, nm in enumerate(names)}
+
+    # ------------------------------------------------------------------ weights
+    def set_weights(self, weights: dict):
+        """Load a {tf variable name: numpy array} map (TF layouts: HWIO, [k,k,Cout,Cin], vectors)."""
+        hostW = np.zeros(self.n_train, np.float32)
+        hostS = np.zeros(max(self.n_stats, 1), np.float32)
+        for name, p in self.params.items():
+            if name not in weights:
+                raise KeyError(f"missing variable {name}")
+            a = np.asarray(weights[name], np.float32)
+            if tuple(a.shape) != tuple(p.shape):
+                raise ValueError(f"{name}: shape {a.shape} != {p.shape}")
+            (hostS if p.region == "S" else hostW)[p.offset:p.offset + p.size] = a.ravel()
+        self.W.upload(hostW)
+        self.Wbf.upload(f32_to_bf16_bits(hostW))
+        self.S.upload(hostS)
+
+    def get_weights(self) -> dict:
+        hostW = self.W.download(np.float32, (self.n_train,))
+        hostS = self.S.download(np.float32, (max(self.n_stats, 1),))
+        out = {}
+        for name, p in self.params.items():
+            src = hostS if p.region == "S" else hostW
+            out[name] = src[p.offset:p.offset + p.size].reshape(p.shape).copy()
+        return out
+
+    def get_grads(self) -> dict:
+        hostG = self.G.download(np.float32, (self.n_train,))
+        return {name: hostG[p.offset:p.offset + p.size].reshape(p.shape).copy()
+                for name, p in self.params.items() if p.region != "S"}
+
+    def init_weights(self, seed: int = 0):
+        """slim.xavier_initializer() weights (seeded numpy stream), zero biases, gamma 1, beta 0, moving 0 / 1."""
+        rng = np.random.default_rng(seed)
+        w = {}
+        for name, p in self.params.items():
+            if name.endswith("/weights"):
+                shp = p.shape
+                rf = shp[0] * shp[1]
+                lim = np.sqrt(6.0 / (rf * shp[2] + rf * shp[3]))
+                w[name] = rng.uniform(-lim, lim, size=shp).astype(np.float32)
+            elif name.endswith(("gamma", "moving_variance")):
+                w[name] = np.ones(p.shape, np.float32)
+            else:
+                w[name] = np.zeros(p.shape, np.float32)
+        self.set_weights(w)
+        return w
+
+    # ------------------------------------------------------------------ inputs
+    def set_inputs(self, images: np.ndarray, labels: np.ndarray | None = None, stream=None):
+        cfg = self.cfg
+        assert images.shape == (cfg.batch, cfg.height, cfg.width, cfg.channel), images.shape
+        self.images.upload(np.ascontiguousarray(images, np.float32), stream)
+        if labels is not None:
+            assert labels.shape == (cfg.batch, cfg.height, cfg.width), labels.shape
+            self.labels.upload(np.ascontiguousarray(labels, np.int32), stream)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, is_training: bool):
+        ctx, s = self.ctx, self.stream
+        call = ctx.call
+        for L in self.layers:
+            if L.kind in ("stem", "conv"):
+                d = self._conv_desc(L)
+                if L.kind == "stem":
+                    call("bsl_conv2d_stem_fprop", C.byref(d), self.images.p, self._pp(self.W, f"{L.scope}/weights"),
+                         L.y.p, s)
+                else:
+                    call("bsl_conv2d_fprop", C.byref(d), L.x.p, self._pp(self.Wbf, f"{L.scope}/weights", BF16),
+                         L.y.p, s)
+                nd = self._norm_desc(L)
+                q = self._norm_ptrs(L)
+                ns = self.norm_scope
+                bn = self.cfg.normalizer == "batch_norm"
+                if not bn or is_training:
+                    call("bsl_norm_stats", C.byref(nd), L.y.p, q["sums"], s)
+                mm = C.c_void_p(self.S.ptr + self.params[f"{L.scope}/{ns}/moving_mean"].offset * F32) if bn else None
+                mv = C.c_void_p(self.S.ptr + self.params[f"{L.scope}/{ns}/moving_variance"].offset * F32) if bn else None
+                call("bsl_norm_finalize", C.byref(nd), C.c_int(1 if is_training else 0), q["sums"],
+                     self._pp(self.W, f"{L.scope}/{ns}/gamma"), self._pp(self.W, f"{L.scope}/{ns}/beta"), mm, mv,
+                     q["mean"], q["rstd"], q["scale"], q["shift"], s)
+                if L.pooled is not None:
+                    call("bsl_norm_apply_pool", C.byref(nd), C.c_int(L.h), C.c_int(L.w), L.y.p, q["scale"], q["shift"],
+                         L.a.p, L.pooled.p, C.c_int(L.pooled.ld), s)
+                else:
+                    call("bsl_norm_apply", C.byref(nd), L.y.p, q["scale"], q["shift"], L.a.p, s)
+            elif L.kind == "convT":
+                d = self._convT_desc(L)
+                call("bsl_convT2d_fwd", C.byref(d), L.x.p, self._pp(self.Wbf, f"{L.scope}/weights", BF16),
+                     self._pp(self.W, f"{L.scope}/biases"), L.a.p, s)
+            else:
+                d = self._conv_desc(L)
+                call("bsl_conv2d_head_fprop", C.byref(d), L.x.p, self._pp(self.W, f"{L.scope}/weights"),
+                     self._pp(self.W, f"{L.scope}/biases"), self.logits.p, s)
+
+    def predict_outputs(self, with_counts: bool):
+        """softmax, `<Cls>Pred` masks, argmax and (optionally) the integer Dice sums, one pass over the logits."""
+        ld = self._loss_desc()
+        self.ctx.call("bsl_softmax_threshold", C.byref(ld), self.logits.p, self.labels.p if with_counts else None,
+                      self.prob.p, self.masks.p, self.argmax.p, self.ilr.p if with_counts else None, self.stream)
+
+    # ------------------------------------------------------------------ loss + backward
+    def loss_backward(self):
+        ctx, s, cfg = self.ctx, self.stream, self.cfg
+        call = ctx.call
+        ld = self._loss_desc()
+        if cfg.loss_type == "xentropy":
+            call("bsl_label_counts", C.byref(ld), self.labels.p, self.counts.p, s)
+            call("bsl_wxent_fwd_bwd", C.byref(ld), self.logits.p, self.labels.p, self.counts.p, self.loss_dev.p,
+                 self.dlogits.p, self.loss_ws.p, C.c_size_t(self.loss_ws_bytes), s)
+        else:
+            call("bsl_dice_fwd_bwd", C.byref(ld), self.logits.p, self.labels.p, self.loss_dev.p, self.dlogits.p,
+                 C.c_int(0), self.loss_ws.p, C.c_size_t(self.loss_ws_bytes), s)
+        n = cfg.batch
+        cur, oth = self.g1, self.g2     # `cur` holds the gradient w.r.t. the current activation
+        ns = self.norm_scope
+        for idx in range(len(self.layers) - 1, -1, -1):
+            L = self.layers[idx]
+            if L.kind == "logits":
+                d = self._conv_desc(L)
+                call("bsl_conv2d_head_wgrad", C.byref(d), L.x.p, self.dlogits.p, self._pp(self.G, f"{L.scope}/weights"),
+                     self._pp(self.G, f"{L.scope}/biases"), s)
+                call("bsl_conv2d_head_dgrad", C.byref(d), self.dlogits.p, self._pp(self.W, f"{L.scope}/weights"),
+                     cur.p, s)
+                self._after_grad(L)
+                continue
+            if L.kind in ("stem", "conv"):
+                if L.pooled is not None:
+                    # `cur` is the gradient w.r.t. the POOLED tensor; merge MaxPoolGrad with the skip gradient
+                    dc = self.dcat[L.level]
+                    call("bsl_maxpool2x2_bwd_add", C.c_int(n), C.c_int(L.h), C.c_int(L.w), C.c_int(L.cout), L.a.p,
+                         C.c_int(L.a.ld), cur.p, C.c_int(L.cout), dc.p, C.c_int(dc.ld), oth.p, C.c_int(L.cout), s)
+                    cur, oth = oth, cur
+                nd = self._norm_desc(L)
+                q = self._norm_ptrs(L)
+                call("bsl_norm_bwd_reduce", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"],
+                     q["scale"], q["shift"], q["sums"], s)
+                call("bsl_norm_bwd_finalize", C.byref(nd), q["sums"], q["c1"], q["c2"],
+                     self._pp(self.G, f"{L.scope}/{ns}/gamma"), self._pp(self.G, f"{L.scope}/{ns}/beta"), s)
+                call("bsl_norm_bwd_apply", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"], q["scale"],
+                     q["shift"], q["c1"], q["c2"], oth.p, C.c_int(L.cout), s)
+                # oth = dY (gradient w.r.t. the conv output), dense with ld = cout
+                d = self._conv_desc(L)
+                d.y_ld = L.cout
+                gw = self._pp(self.G, f"{L.scope}/weights")
+                if L.kind == "stem":
+                    call("bsl_conv2d_stem_wgrad", C.byref(d), self.images.p, oth.p, gw, s)
+                else:
+                    call("bsl_conv2d_wgrad", C.byref(d), L.x.p, oth.p, gw, self.wgrad_ws.p,
+                         C.c_size_t(self.wgrad_ws_bytes), s)
+                    is_dec1 = L.scope.startswith("UNet/Decode") and L.scope.endswith("_1")
+                    wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
+                    if is_dec1:
+                        dc = self.dcat[L.level]
+                        d.x_ld = dc.ld
+                        call("bsl_conv2d_dgrad", C.byref(d), oth.p, wbf, dc.p, s)
+                    else:
+                        d.x_ld = L.cin
+                        call("bsl_conv2d_dgrad", C.byref(d), oth.p, wbf, cur.p, s)
+                self._after_grad(L)
+            elif L.kind == "convT":
+                dc = self.dcat[L.level]
+                dup = dc.slice(L.cout, L.cout)
+                # ReluGrad in place on the upper half of dcat
+                call("bsl_relu_bwd", C.c_longlong(L.a.pixels), C.c_int(L.cout), L.a.p, C.c_int(L.a.ld), dup.p,
+                     C.c_int(dup.ld), dup.p, C.c_int(dup.ld), s)
+                d = self._convT_desc(L)
+                d.y_ld = dup.ld
+                call("bsl_convT2d_bwd_filter", C.byref(d), L.x.p, dup.p, self._pp(self.G, f"{L.scope}/weights"),
+                     self._pp(self.G, f"{L.scope}/biases"), self.wgrad_ws.p, C.c_size_t(self.wgrad_ws_bytes), s)
+                d.x_ld = L.cin
+                call("bsl_convT2d_bwd_data", C.byref(d), dup.p, self._pp(self.Wbf, f"{L.scope}/weights", BF16), cur.p, s)
+                self._after_grad(L)
+
+    def _after_grad(self, L: ConvL):
+        """Hook for the bucketed all-reduce: called when layer L's parameter gradients are enqueued."""
+
+    # ------------------------------------------------------------------ optimizer
+    def optimizer_step(self, lr: float):
+        ctx, s, cfg = self.ctx, self.stream, self.cfg
+        self.step_count += 1
+        l2 = cfg.weight_decay_rate if cfg.weight_decay_rate > 0 else 0.0
+        regions = [(0, self.n_reg, l2, self.sumsq.p), (self.n_reg, self.n_train - self.n_reg, 0.0, None)]
+        for off, n, rate, sq in regions:
+            if n <= 0:
+                continue
+            w = C.c_void_p(self.W.ptr + off * F32)
+            g = C.c_void_p(self.G.ptr + off * F32)
+            m = C.c_void_p(self.M.ptr + off * F32)
+            wb = C.c_void_p(self.Wbf.ptr + off * BF16)
+            if cfg.optimizer == "adam":
+                v = C.c_void_p(self.V.ptr + off * F32)
+                d = _lib.AdamDesc(lr, 0.9, 0.99, 1e-8, rate, 1.0, self.step_count)   # solver.py:206
+                ctx.call("bsl_adam_step", C.byref(d), w, g, m, v, wb, C.c_size_t(n), sq, s)
+            elif cfg.optimizer == "momentum":
+                ctx.call("bsl_momentum_step", C.c_float(lr), C.c_float(0.9), C.c_float(rate), C.c_float(1.0), w, g, m,
+                         wb, C.c_size_t(n), sq, s)
+            else:
+                raise ValueError("Not supported optimizer: " + cfg.optimizer)
+
+    # ------------------------------------------------------------------ results
+    def read_loss(self):
+        """(data loss, L2 regularisation loss) of the step just run; the only D2H read of a train step."""
+        data = self.loss_dev.download(np.float32, (1,))[0]
+        sq = self.sumsq.download(np.float64, (1,))[0]
+        return float(data), float(self.cfg.weight_decay_rate * 0.5 * sq) if self.cfg.weight_decay_rate > 0 else 0.0
+
+    def read_counts(self):
+        k = self.cfg.num_classes - 1
+        return self.ilr.download(np.uint32, (self.cfg.batch, k, 3))
+
+    def train_step(self, lr: float, with_metrics: bool = False):
+        self.forward(True)
+        if with_metrics:
+            self.predict_outputs(True)
+        self.loss_backward()
+        self.optimizer_step(lr)
+
+    def close(self):
+        for b in self._bufs:
+            b.free()
+        self._bufs = []
