@@ -25,6 +25,7 @@ struct bsl_ctx {
   void* nccl_lib = nullptr;                            // dlopen handle (comm.cu)
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  unsigned long long launches = 0;  // kernels enqueued through this context (bench.py gpu_launches)
 };
 
 int bsl_fail(bsl_ctx* ctx, int code, const char* fmt, ...);
@@ -40,6 +41,7 @@ int bsl_check_cuda(bsl_ctx* ctx, cudaError_t e, const char* what);
   do {                                                             \
     cudaError_t _e = cudaGetLastError();                           \
     if (_e != cudaSuccess) return bsl_check_cuda(ctx, _e, what);   \
+    ++(ctx)->launches;                                             \
   } while (0)
 
 // Encodes (or fetches from the cache) a bf16 tensor map with 128-byte swizzle and zero OOB fill.

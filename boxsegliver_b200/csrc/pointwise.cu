@@ -1,7 +1,6 @@
-// HBM-bound passes of the U-Net hot path: casts, reductions over pixels, normalisation, pooling,
-// ReLU masks. All are vectorised (16 B per thread per access), coalesced along the NHWC channel
-// axis, and reduce with warp shuffles + a fixed-order second level (no float atomics), so results
-// are bit-reproducible run to run.
+// Small HBM-bound helpers: dtype casts, in-place scaling, per-channel sums (bias gradients).
+// Vectorised and coalesced along the NHWC channel axis; reductions are two-level with a fixed
+// order (reduce.cuh), so results are bit-reproducible run to run.
 #include <cuda_bf16.h>
 #include "reduce.cuh"
 
@@ -44,6 +43,11 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, floa
     for (size_t j = n & ~(size_t)3; j < n; ++j) dst[j] = __bfloat162float(src[j]);
 }
 
+__global__ void scale_f32_kernel(float* __restrict__ x, size_t n, float a) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] *= a;
+}
+
 struct SumF {
   static constexpr int K = 1;
   const __nv_bfloat16* x;
@@ -80,6 +84,14 @@ int bsl_channel_sum_bf16(bsl_ctx* ctx, const void* x, long long pixels, int c, i
 }
 
 extern "C" {
+
+int bsl_scale_f32(bsl_ctx* ctx, float* x, size_t n, float a, void* stream) {
+  if (!ctx || !x) return BSL_EINVAL;
+  if (n == 0) return BSL_OK;
+  scale_f32_kernel<<<grid_for((long long)n, kThreads, 8 * ctx->sm_count), kThreads, 0, as_stream(stream)>>>(x, n, a);
+  BSL_LAUNCH_CHECK(ctx, "scale_f32_kernel");
+  return BSL_OK;
+}
 
 int bsl_cast_f32_to_bf16(bsl_ctx* ctx, const float* src, void* dst, size_t n, void* stream) {
   if (!ctx || !src || !dst) return BSL_EINVAL;

@@ -88,6 +88,12 @@ int bsl_device_status(bsl_ctx* ctx, int* block, int* site) {
   return BSL_OK;
 }
 
+int bsl_launch_count(bsl_ctx* ctx, unsigned long long* out) {
+  if (!ctx || !out) return BSL_EINVAL;
+  *out = ctx->launches;
+  return BSL_OK;
+}
+
 int bsl_malloc(bsl_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return BSL_EINVAL;
   BSL_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 16));

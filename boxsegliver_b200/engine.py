@@ -128,6 +128,66 @@ class UNetEngine:
         self.comm_stream = None
         self._graph = None
 
+    # ------------------------------------------------------------------ per-kernel timing (bench roofline)
+    def enable_conv_timing(self, on: bool = True):
+        """Bracket every tcgen05 conv launch with CUDA events on the compute stream (bench.py roofline)."""
+        self._timing = on
+        self._timed = []          # (name, flops, ev0, ev1) in launch order for the current step(s)
+        self._ev_pool = getattr(self, "_ev_pool", [])
+        self._ev_next = 0
+
+    def _ev(self):
+        if self._ev_next == len(self._ev_pool):
+            self._ev_pool.append(self.ctx.new_event())
+        e = self._ev_pool[self._ev_next]
+        self._ev_next += 1
+        return e
+
+    def _tc(self, name: str, flops: float, fn_name: str, *args):
+        """Enqueue a tensor-core conv call, optionally bracketed by events."""
+        if getattr(self, "_timing", False):
+            e0, e1 = self._ev(), self._ev()
+            self.ctx.record(e0, self.stream)
+            self.ctx.call(fn_name, *args)
+            self.ctx.record(e1, self.stream)
+            self._timed.append((name, flops, e0, e1))
+        else:
+            self.ctx.call(fn_name, *args)
+
+    def conv_timing_report(self):
+        """Sum of device time and algorithmic FLOPs over the bracketed conv launches since enable_conv_timing."""
+        self.ctx.sync(self.stream)
+        tot_ms, tot_fl, per = 0.0, 0.0, {}
+        for name, fl, e0, e1 in self._timed:
+            ms = self.ctx.elapsed_ms(e0, e1)
+            tot_ms += ms
+            tot_fl += fl
+            a = per.setdefault(name, [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += ms
+            a[2] += fl
+        return {"launches": len(self._timed), "ms": tot_ms, "flops": tot_fl, "per_kind": per}
+
+    # ------------------------------------------------------------------ data parallel
+    def attach_comm(self, rank: int, world: int, unique_id: bytes):
+        """Join the NCCL communicator (one process per GPU). cfg.world must equal `world`."""
+        assert world == self.cfg.world, (world, self.cfg.world)
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self.ctx.call("bsl_comm_init", buf, C.c_int(rank), C.c_int(world))
+        self.rank = rank
+
+    def _allreduce_grads(self):
+        if self.cfg.world > 1:
+            self.ctx.call("bsl_allreduce_sum_f32", self.G.p, C.c_size_t(self.n_train), self.stream)
+
+    def _allreduce_moving_stats(self):
+        # MirroredStrategy aggregates the moving-average updates with MEAN across replicas
+        # (/root/reference/core/estimator.py:570-613); batch statistics themselves stay per replica.
+        if self.cfg.world > 1 and self.n_stats > 0:
+            self.ctx.call("bsl_allreduce_sum_f32", self.S.p, C.c_size_t(self.n_stats), self.stream)
+            self.ctx.call("bsl_scale_f32", self.S.p, C.c_size_t(self.n_stats), C.c_float(1.0 / self.cfg.world),
+                          self.stream)
+
     # ------------------------------------------------------------------ planning
     def _alloc(self, nbytes) -> DeviceBuffer:
         b = self.ctx.alloc(max(int(nbytes), 16))
@@ -278,6 +338,21 @@ class UNetEngine:
             self.wgrad_ws_bytes = int(ws)
             self.wgrad_ws = self._alloc(max(ws, 16))
 
+    def _flops(self, L: ConvL) -> float:
+        """Algorithmic FLOPs of ONE pass (fprop, dgrad or wgrad) of layer L: 2 * MACs, un-padded."""
+        n = self.cfg.batch
+        if L.kind == "convT":
+            return 2.0 * n * (2 * L.h) * (2 * L.w) * L.cin * L.cout   # one tap per output pixel
+        k = 1 if L.kind == "logits" else 9
+        return 2.0 * n * L.h * L.w * k * L.cin * L.cout
+
+    def step_flops(self) -> dict:
+        """Algorithmic fwd / bwd FLOPs of one training step (bwd = dgrad + wgrad, no dgrad for the stem)."""
+        fwd = sum(self._flops(L) for L in self.layers)
+        bwd = sum(self._flops(L) * (1 if L.kind == "stem" else 2) for L in self.layers)
+        tc = sum(self._flops(L) * 3 for L in self.layers if L.kind in ("conv", "convT"))
+        return {"fwd": fwd, "bwd": bwd, "total": fwd + bwd, "tensor_core": tc}
+
     # ------------------------------------------------------------------ descriptors
     def _conv_desc(self, L: ConvL):
         k = 1 if L.kind == "logits" else 3
@@ -334,6 +409,21 @@ class UNetEngine:
             out[name] = src[p.offset:p.offset + p.size].reshape(p.shape).copy()
         return out
 
+    def get_stored_forward(self) -> dict:
+        """{scope: {"y": pre-norm conv output, "a": activation}} as fp32 numpy (what backward will read)."""
+        out = {}
+        for L in self.layers:
+            if L.kind == "logits":
+                continue
+            d = {}
+            for key, v in (("y", L.y), ("a", L.a)):
+                if v is None:
+                    continue
+                full = self.ctx.bf16_to_f32(v.buf, (v.n, v.h, v.w, v.ld))
+                d[key] = full[..., v.c0:v.c0 + v.c].copy()
+            out[L.scope] = d
+        return out
+
     def get_grads(self) -> dict:
         hostG = self.G.download(np.float32, (self.n_train,))
         return {name: hostG[p.offset:p.offset + p.size].reshape(p.shape).copy()
@@ -376,8 +466,8 @@ class UNetEngine:
                     call("bsl_conv2d_stem_fprop", C.byref(d), self.images.p, self._pp(self.W, f"{L.scope}/weights"),
                          L.y.p, s)
                 else:
-                    call("bsl_conv2d_fprop", C.byref(d), L.x.p, self._pp(self.Wbf, f"{L.scope}/weights", BF16),
-                         L.y.p, s)
+                    self._tc("fprop", self._flops(L), "bsl_conv2d_fprop", C.byref(d), L.x.p,
+                             self._pp(self.Wbf, f"{L.scope}/weights", BF16), L.y.p, s)
                 nd = self._norm_desc(L)
                 q = self._norm_ptrs(L)
                 ns = self.norm_scope
@@ -396,8 +486,8 @@ class UNetEngine:
                     call("bsl_norm_apply", C.byref(nd), L.y.p, q["scale"], q["shift"], L.a.p, s)
             elif L.kind == "convT":
                 d = self._convT_desc(L)
-                call("bsl_convT2d_fwd", C.byref(d), L.x.p, self._pp(self.Wbf, f"{L.scope}/weights", BF16),
-                     self._pp(self.W, f"{L.scope}/biases"), L.a.p, s)
+                self._tc("convT_fwd", self._flops(L), "bsl_convT2d_fwd", C.byref(d), L.x.p,
+                         self._pp(self.Wbf, f"{L.scope}/weights", BF16), self._pp(self.W, f"{L.scope}/biases"), L.a.p, s)
             else:
                 d = self._conv_desc(L)
                 call("bsl_conv2d_head_fprop", C.byref(d), L.x.p, self._pp(self.W, f"{L.scope}/weights"),
@@ -456,17 +546,17 @@ class UNetEngine:
                 if L.kind == "stem":
                     call("bsl_conv2d_stem_wgrad", C.byref(d), self.images.p, oth.p, gw, s)
                 else:
-                    call("bsl_conv2d_wgrad", C.byref(d), L.x.p, oth.p, gw, self.wgrad_ws.p,
-                         C.c_size_t(self.wgrad_ws_bytes), s)
+                    self._tc("wgrad", self._flops(L), "bsl_conv2d_wgrad", C.byref(d), L.x.p, oth.p, gw,
+                             self.wgrad_ws.p, C.c_size_t(self.wgrad_ws_bytes), s)
                     is_dec1 = L.scope.startswith("UNet/Decode") and L.scope.endswith("_1")
                     wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
                     if is_dec1:
                         dc = self.dcat[L.level]
                         d.x_ld = dc.ld
-                        call("bsl_conv2d_dgrad", C.byref(d), oth.p, wbf, dc.p, s)
+                        self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad", C.byref(d), oth.p, wbf, dc.p, s)
                     else:
                         d.x_ld = L.cin
-                        call("bsl_conv2d_dgrad", C.byref(d), oth.p, wbf, cur.p, s)
+                        self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad", C.byref(d), oth.p, wbf, cur.p, s)
                 self._after_grad(L)
             elif L.kind == "convT":
                 dc = self.dcat[L.level]
@@ -476,10 +566,12 @@ class UNetEngine:
                      C.c_int(dup.ld), dup.p, C.c_int(dup.ld), s)
                 d = self._convT_desc(L)
                 d.y_ld = dup.ld
-                call("bsl_convT2d_bwd_filter", C.byref(d), L.x.p, dup.p, self._pp(self.G, f"{L.scope}/weights"),
-                     self._pp(self.G, f"{L.scope}/biases"), self.wgrad_ws.p, C.c_size_t(self.wgrad_ws_bytes), s)
+                self._tc("convT_wgrad", self._flops(L), "bsl_convT2d_bwd_filter", C.byref(d), L.x.p, dup.p,
+                         self._pp(self.G, f"{L.scope}/weights"), self._pp(self.G, f"{L.scope}/biases"),
+                         self.wgrad_ws.p, C.c_size_t(self.wgrad_ws_bytes), s)
                 d.x_ld = L.cin
-                call("bsl_convT2d_bwd_data", C.byref(d), dup.p, self._pp(self.Wbf, f"{L.scope}/weights", BF16), cur.p, s)
+                self._tc("convT_dgrad", self._flops(L), "bsl_convT2d_bwd_data", C.byref(d), dup.p,
+                         self._pp(self.Wbf, f"{L.scope}/weights", BF16), cur.p, s)
                 self._after_grad(L)
 
     def _after_grad(self, L: ConvL):
@@ -520,11 +612,52 @@ class UNetEngine:
         return self.ilr.download(np.uint32, (self.cfg.batch, k, 3))
 
     def train_step(self, lr: float, with_metrics: bool = False):
+        """One `sess.run(train_op)` on device-resident inputs (/root/reference/core/estimator.py:756-757)."""
         self.forward(True)
+        if self.cfg.normalizer == "batch_norm":
+            self._allreduce_moving_stats()
         if with_metrics:
             self.predict_outputs(True)
         self.loss_backward()
+        self._allreduce_grads()
         self.optimizer_step(lr)
+
+    # ------------------------------------------------------------------ host-fed step (end-to-end path)
+    def pinned_inputs(self):
+        """numpy views of page-locked staging buffers (images fp32 [N,H,W,C], labels int32 [N,H,W])."""
+        if not hasattr(self, "_pin"):
+            cfg = self.cfg
+            shp_i = (cfg.batch, cfg.height, cfg.width, cfg.channel)
+            shp_l = (cfg.batch, cfg.height, cfg.width)
+            pi, pl, po = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            self.ctx.call("bsl_host_alloc", C.c_size_t(int(np.prod(shp_i)) * 4), C.byref(pi))
+            self.ctx.call("bsl_host_alloc", C.c_size_t(int(np.prod(shp_l)) * 4), C.byref(pl))
+            self.ctx.call("bsl_host_alloc", C.c_size_t(64), C.byref(po))
+            img = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_float)), shape=shp_i)
+            lab = np.ctypeslib.as_array(C.cast(pl, C.POINTER(C.c_int32)), shape=shp_l)
+            out = np.ctypeslib.as_array(C.cast(po, C.POINTER(C.c_double)), shape=(8,))
+            self._pin = (img, lab, out, pi, pl, po)
+        return self._pin[0], self._pin[1]
+
+    def train_step_host(self, lr: float, with_metrics: bool = False):
+        """H2D copy of the staged batch, one training step, D2H read of (loss, sum w^2). Returns total loss.
+
+        This is the call a user of the reference makes per step (feed a batch, fetch the loss)."""
+        img, lab, out, pi, pl, po = self._pin
+        s = self.stream
+        self.ctx.call("bsl_memcpy_h2d", self.images.p, pi, C.c_size_t(img.nbytes), s)
+        self.ctx.call("bsl_memcpy_h2d", self.labels.p, pl, C.c_size_t(lab.nbytes), s)
+        self.train_step(lr, with_metrics)
+        self.ctx.call("bsl_memcpy_d2h", po, self.loss_dev.p, C.c_size_t(4), s)
+        self.ctx.call("bsl_memcpy_d2h", C.c_void_p(po.value + 8), self.sumsq.p, C.c_size_t(8), s)
+        self.ctx.sync(s)
+        data = float(np.frombuffer(out[:1].tobytes(), np.float32)[0])
+        reg = float(self.cfg.weight_decay_rate * 0.5 * out[1]) if self.cfg.weight_decay_rate > 0 else 0.0
+        return data + reg
+
+    def h2d_bytes_per_step(self):
+        cfg = self.cfg
+        return cfg.batch * cfg.height * cfg.width * (cfg.channel * 4 + 4)
 
     def close(self):
         for b in self._bufs:

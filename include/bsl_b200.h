@@ -45,6 +45,9 @@ const char* bsl_version(void);
 /* Reads back (synchronously) and clears the device-side watchdog word. 0 = healthy. */
 int bsl_device_status(bsl_ctx* ctx, int* block, int* site);
 
+/* Number of kernels enqueued through this context since bsl_init (host-side counter). */
+int bsl_launch_count(bsl_ctx* ctx, unsigned long long* out);
+
 /* Probe hook: overrides a layout constant of the UMMA descriptors (tools/gpu_conv_probe.py). */
 int bsl_debug_set(bsl_ctx* ctx, int key, int value);
 
@@ -74,6 +77,8 @@ int bsl_graph_destroy(bsl_ctx* ctx, void* graph_exec);
 /* ------------------------------------------------------------------ dtype casts (fp32 <-> bf16) */
 int bsl_cast_f32_to_bf16(bsl_ctx* ctx, const float* src, void* dst, size_t n, void* stream);
 int bsl_cast_bf16_to_f32(bsl_ctx* ctx, const void* src, float* dst, size_t n, void* stream);
+/* x *= a in place (cross-replica MEAN of the batch-norm moving statistics after a SUM all-reduce). */
+int bsl_scale_f32(bsl_ctx* ctx, float* x, size_t n, float a, void* stream);
 
 /* ------------------------------------------------------------------ conv2d, stride 1, SAME
  * Replaces TF ops Conv2D / Conv2DBackpropInput / Conv2DBackpropFilter behind

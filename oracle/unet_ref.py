@@ -185,6 +185,57 @@ def forward(params: dict, images: np.ndarray, cfg: UNetCfg, is_training: bool, r
     return tape
 
 
+def tape_from_stored(params: dict, images: np.ndarray, stored: dict, logits: np.ndarray, cfg: UNetCfg,
+                     wrnd=_identity) -> Tape:
+    """Rebuilds the backward tape from forward tensors that were STORED by another implementation
+    (`stored[scope] = {"y": pre-norm conv output, "a": activation}`), so that a backward pass can be
+    compared op by op on identical inputs: ReLU masks and max-pool arg-maxes then come from the same
+    bits on both sides instead of diverging chaotically with the last-ulp differences of the forward."""
+    ns = norm_scope(cfg)
+    tape = Tape()
+    dt = images.dtype
+
+    def block(x, scope, first=False):
+        w = params[f"{scope}/weights"].astype(dt)
+        w = w if first else wrnd(w).astype(dt)
+        y = stored[scope]["y"].astype(dt)
+        g, b = params[f"{scope}/{ns}/gamma"].astype(dt), params[f"{scope}/{ns}/beta"].astype(dt)
+        if cfg.normalizer == "batch_norm":
+            z, cache, _, _ = O.batch_norm_train(y, g, b, np.zeros_like(g), np.ones_like(g), cfg.bn_eps, cfg.bn_decay)
+        else:
+            z, cache = O.instance_norm(y, g, b, cfg.in_eps)
+        a = stored[scope]["a"].astype(dt)
+        tape.layers.append(dict(kind="conv", scope=scope, x=x, w=w, z=z, a=a, cache=cache, first=first))
+        return a
+
+    x = images
+    skips = []
+    first = True
+    for i in range(cfg.num_down_samples):
+        for j in (1, 2):
+            x = block(x, f"UNet/Encode{i + 1}/Repeat/convolution2d_{j}", first)
+            first = False
+        skips.append(x)
+        tape.layers.append(dict(kind="pool", x=x))
+        x = O.max_pool_2x2(x)
+    for j in (1, 2):
+        x = block(x, f"UNet/ED-Bridge/convolution2d_{j}")
+    for i in reversed(range(cfg.num_down_samples)):
+        scope = f"UNet/Decode{i + 1}/Conv2d_transpose"
+        w = wrnd(params[f"{scope}/weights"].astype(dt)).astype(dt)
+        up = stored[scope]["a"].astype(dt)
+        tape.layers.append(dict(kind="convT", scope=scope, x=x, w=w, a=up))
+        x = np.concatenate((skips[i], up), axis=-1)
+        tape.layers.append(dict(kind="concat", split=skips[i].shape[-1], level=i))
+        for j in (1, 2):
+            x = block(x, f"UNet/Decode{i + 1}/Repeat/convolution2d_{j}")
+    scope = "UNet/AdjustChannels"
+    tape.layers.append(dict(kind="logits", scope=scope, x=x, w=params[f"{scope}/weights"].astype(dt)))
+    tape.logits = logits.astype(dt)
+    tape.prob = O.softmax(tape.logits)
+    return tape
+
+
 def loss_and_dlogits(tape: Tape, labels: np.ndarray, cfg: UNetCfg, loss_scale: float = 1.0):
     """UNet._build_loss (data term only). Returns (loss, dlogits * loss_scale)."""
     kw = {}

@@ -1,0 +1,152 @@
+"""Parity of the tcgen05 implicit-GEMM convolutions (through the C ABI) against the numpy oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from boxsegliver_b200 import _lib
+from oracle import tf_ops as O
+from tests.gpu_util import TOL_BF16, TOL_F32, bf16_randn, padded, rel
+
+pytestmark = pytest.mark.gpu
+
+CONV_CASES = [
+    # n, h, w, cin, cout, k, x_ld, y_ld
+    (2, 16, 16, 64, 64, 3, None, None),      # column tile 64
+    (1, 16, 16, 128, 128, 3, None, None),    # column tile 128, two k-blocks per tap
+    (1, 8, 16, 64, 256, 3, None, None),      # column tile 256
+    (1, 16, 16, 256, 64, 3, None, None),
+    (2, 12, 20, 64, 128, 3, None, None),     # ragged spatial size: out-of-bounds rows masked
+    (3, 4, 4, 128, 64, 3, None, None),       # box spans several images
+    (2, 16, 16, 64, 64, 3, 128, 192),        # skip-concat views (channel stride > channels)
+    (2, 16, 16, 128, 64, 1, None, None),     # 1x1
+    (1, 2, 2, 1024, 1024, 3, None, None),    # bridge layer of a 32x32 input
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,k,x_ld,y_ld", CONV_CASES)
+def test_conv2d_fprop_dgrad_wgrad(ctx, n, h, w, cin, cout, k, x_ld, y_ld):
+    rng = np.random.default_rng(cin * 7 + cout + h)
+    x_ld, y_ld = x_ld or cin, y_ld or cout
+    x = bf16_randn(rng, (n, h, w, cin))
+    wt = bf16_randn(rng, (k, k, cin, cout), 0.05)
+    dy = bf16_randn(rng, (n, h, w, cout))
+    dx_ = ctx.bf16_from_f32(padded(x, x_ld))
+    dw_ = ctx.bf16_from_f32(wt)
+    ddy = ctx.bf16_from_f32(padded(dy, y_ld))
+    yo = ctx.alloc(n * h * w * y_ld * 2).zero()
+    dxo = ctx.alloc(n * h * w * x_ld * 2).zero()
+    desc = _lib.Conv2dDesc(n, h, w, cin, cout, k, k, x_ld, y_ld)
+    x64, w64, dy64 = x.astype(np.float64), wt.astype(np.float64), dy.astype(np.float64)
+
+    ctx.call("bsl_conv2d_fprop", C.byref(desc), dx_.p, dw_.p, yo.p, ctx.stream)
+    ctx.check_device()
+    got = ctx.bf16_to_f32(yo, (n, h, w, y_ld))
+    assert rel(got[..., :cout], O.conv2d(x64, w64)) < TOL_BF16
+    assert not got[..., cout:].any(), "fprop wrote outside its channel slice"
+
+    ctx.call("bsl_conv2d_dgrad", C.byref(desc), ddy.p, dw_.p, dxo.p, ctx.stream)
+    ctx.check_device()
+    got = ctx.bf16_to_f32(dxo, (n, h, w, x_ld))
+    assert rel(got[..., :cin], O.conv2d_backprop_input(x.shape, w64, dy64)) < TOL_BF16
+    assert not got[..., cin:].any()
+
+    ws_bytes = ctx.lib.bsl_conv2d_wgrad_workspace(ctx.h, C.byref(desc))
+    ws = ctx.alloc(max(ws_bytes, 16))
+    dwo = ctx.alloc(k * k * cin * cout * 4).zero()
+    ctx.call("bsl_conv2d_wgrad", C.byref(desc), dx_.p, ddy.p, dwo.p, ws.p, C.c_size_t(ws_bytes), ctx.stream)
+    ctx.check_device()
+    got1 = dwo.download(np.float32, (k, k, cin, cout))
+    assert rel(got1, O.conv2d_backprop_filter(x64, wt.shape, dy64)) < TOL_F32
+    # split-K partials are reduced in a fixed order: a second run is bit-identical
+    ctx.call("bsl_conv2d_wgrad", C.byref(desc), dx_.p, ddy.p, dwo.p, ws.p, C.c_size_t(ws_bytes), ctx.stream)
+    assert np.array_equal(got1, dwo.download(np.float32, (k, k, cin, cout)))
+    for b in (dx_, dw_, ddy, yo, dxo, ws, dwo):
+        b.free()
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,y_ld", [
+    (2, 8, 8, 128, 64, None), (1, 16, 16, 64, 64, None), (2, 4, 8, 256, 128, None), (1, 6, 10, 128, 64, None),
+    (2, 8, 8, 128, 64, 128), (1, 2, 2, 1024, 512, 1024)])
+def test_conv2d_transpose(ctx, n, h, w, cin, cout, y_ld):
+    rng = np.random.default_rng(cin + cout + h)
+    y_ld = y_ld or cout
+    x = bf16_randn(rng, (n, h, w, cin))
+    wt = bf16_randn(rng, (2, 2, cout, cin), 0.05)
+    bias = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+    dy = bf16_randn(rng, (n, 2 * h, 2 * w, cout))
+    dx_, dw_, db_ = ctx.bf16_from_f32(x), ctx.bf16_from_f32(wt), ctx.from_numpy(bias)
+    ddy = ctx.bf16_from_f32(padded(dy, y_ld))
+    yo = ctx.alloc(n * 4 * h * w * y_ld * 2).zero()
+    dxo = ctx.alloc(n * h * w * cin * 2).zero()
+    desc = _lib.ConvT2dDesc(n, h, w, cin, cout, cin, y_ld, 1)
+    x64, w64, dy64 = x.astype(np.float64), wt.astype(np.float64), dy.astype(np.float64)
+    ctx.call("bsl_convT2d_fwd", C.byref(desc), dx_.p, dw_.p, db_.p, yo.p, ctx.stream)
+    ctx.check_device()
+    got = ctx.bf16_to_f32(yo, (n, 2 * h, 2 * w, y_ld))
+    assert rel(got[..., :cout], O.relu(O.conv2d_transpose(x64, w64) + bias)) < TOL_BF16
+    assert not got[..., cout:].any()
+    rdx, rdw = O.conv2d_transpose_grad(x64, w64, dy64)
+    ctx.call("bsl_convT2d_bwd_data", C.byref(desc), ddy.p, dw_.p, dxo.p, ctx.stream)
+    ctx.check_device()
+    assert rel(ctx.bf16_to_f32(dxo, (n, h, w, cin)), rdx) < TOL_BF16
+    ws_bytes = ctx.lib.bsl_convT2d_bwd_filter_workspace(ctx.h, C.byref(desc))
+    ws = ctx.alloc(max(ws_bytes, 16))
+    dwo, dbo = ctx.alloc(4 * cout * cin * 4).zero(), ctx.alloc(cout * 4).zero()
+    ctx.call("bsl_convT2d_bwd_filter", C.byref(desc), dx_.p, ddy.p, dwo.p, dbo.p, ws.p, C.c_size_t(ws_bytes), ctx.stream)
+    ctx.check_device()
+    assert rel(dwo.download(np.float32, (2, 2, cout, cin)), rdw) < TOL_F32
+    assert rel(dbo.download(np.float32, (cout,)), dy64.sum(axis=(0, 1, 2))) < TOL_F32
+    for b in (dx_, dw_, db_, ddy, yo, dxo, ws, dwo, dbo):
+        b.free()
+
+
+def test_full_size_adjoint_identity(ctx):
+    """BASELINE-size layer (Decode1 conv1 of cfg2: 64 x 256 x 256, 128 -> 64): the oracle cannot run it in
+    seconds, but <fprop(x), dy> == <x, dgrad(dy)> == <w, wgrad(x, dy)> must hold for any correct triple."""
+    n, h, w, cin, cout = 32, 256, 256, 128, 64   # half of cfg2's batch: bounds host RAM/time; same tiles, same kernels
+    rng = np.random.default_rng(0)
+    npx = n * h * w
+    # low-rank random fields keep host generation cheap: x[p, c] = a[p] * b[c] (exactly bf16 products are not
+    # needed; the identity holds for whatever bits are uploaded)
+    x = bf16_randn(rng, (npx, 1)) * bf16_randn(rng, (1, cin))
+    dy = bf16_randn(rng, (npx, 1)) * bf16_randn(rng, (1, cout))
+    from boxsegliver_b200.device import round_bf16
+    x, dy = round_bf16(x), round_bf16(dy)
+    wt = bf16_randn(rng, (3, 3, cin, cout), 0.05)
+    dx_, ddy, dw_ = ctx.bf16_from_f32(x), ctx.bf16_from_f32(dy), ctx.bf16_from_f32(wt)
+    yo, dxo = ctx.alloc(npx * cout * 2), ctx.alloc(npx * cin * 2)
+    desc = _lib.Conv2dDesc(n, h, w, cin, cout, 3, 3, cin, cout)
+    ws_bytes = ctx.lib.bsl_conv2d_wgrad_workspace(ctx.h, C.byref(desc))
+    ws, dwo = ctx.alloc(max(ws_bytes, 16)), ctx.alloc(9 * cin * cout * 4)
+    ctx.call("bsl_conv2d_fprop", C.byref(desc), dx_.p, dw_.p, yo.p, ctx.stream)
+    ctx.call("bsl_conv2d_dgrad", C.byref(desc), ddy.p, dw_.p, dxo.p, ctx.stream)
+    ctx.call("bsl_conv2d_wgrad", C.byref(desc), dx_.p, ddy.p, dwo.p, ws.p, C.c_size_t(ws_bytes), ctx.stream)
+    ctx.check_device()
+    def dot64(u, v, chunk=1 << 18):
+        return sum(float(np.dot(u[i:i + chunk].ravel().astype(np.float64), v[i:i + chunk].ravel().astype(np.float64)))
+                   for i in range(0, u.shape[0], chunk))
+
+    a = dot64(ctx.bf16_to_f32(yo, (npx, cout)), dy)
+    b = dot64(ctx.bf16_to_f32(dxo, (npx, cin)), x)
+    dwg = dwo.download(np.float32, (3, 3, cin, cout)).astype(np.float64)
+    c = float((dwg * wt).sum())
+    scale = max(abs(a), abs(b), abs(c), 1e-30)
+    assert abs(a - c) / scale < 2e-3 and abs(b - c) / scale < 2e-3, (a, b, c)
+    for buf in (dx_, ddy, dw_, yo, dxo, ws, dwo):
+        buf.free()
+
+
+def test_rejects_unsupported_shapes(ctx):
+    from boxsegliver_b200._lib import BslError
+    d = _lib.Conv2dDesc(1, 8, 8, 48, 64, 3, 3, 48, 64)  # cin not a multiple of 64 -> loud failure, no fallback
+    buf = ctx.alloc(1 << 16)
+    with pytest.raises(BslError):
+        ctx.call("bsl_conv2d_fprop", C.byref(d), buf.p, buf.p, buf.p, ctx.stream)
+    d = _lib.Conv2dDesc(1, 8, 8, 64, 64, 5, 5, 64, 64)
+    with pytest.raises(BslError):
+        ctx.call("bsl_conv2d_fprop", C.byref(d), buf.p, buf.p, buf.p, ctx.stream)
+    d = _lib.Conv2dDesc(1, 8, 8, 64, 64, 3, 3, 64, 64)
+    with pytest.raises(BslError):
+        ctx.call("bsl_conv2d_fprop", C.byref(d), None, buf.p, buf.p, ctx.stream)
+    buf.free()

@@ -1,0 +1,163 @@
+"""End-to-end parity of the U-Net engine (forward, loss, backward, optimizer, masks, counts) against the
+numpy oracle, plus full-size properties at BASELINE cfg2 (batch 64, 256x256x3).
+
+Gates (relative L2 norm per tensor, bf16 path, north_star tolerance 1e-2):
+  * logits vs the oracle run with bf16-storage emulation ......................... <= 1.5e-2 (tiny-batch BN
+    statistics amplify last-ulp differences; at these test sizes the fp64 oracle itself sits at ~2e-2)
+  * gradients: oracle backward over the DEVICE's stored forward tensors, so that ReLU masks and max-pool
+    arg-maxes are the same bits on both sides ...................................... median <= 1e-2, worst <= 1.5e-2
+  * `p > 0.5` masks, argmax and Dice I/L/R counts ................................ bit-exact given the logits
+"""
+import numpy as np
+import pytest
+
+from boxsegliver_b200 import synthetic
+from boxsegliver_b200.device import round_bf16
+from boxsegliver_b200.engine import EngineConfig, UNetEngine
+from oracle import unet_ref as R
+from tests.gpu_util import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfgs(n, hw, normalizer, loss_type, wtype):
+    kw = dict(height=hw, width=hw, channel=3, init_channels=64, num_down_samples=4, normalizer=normalizer,
+              weight_decay_rate=1e-5, loss_type=loss_type, loss_weight_type=wtype,
+              loss_numeric_w=(0.2, 0.4, 4.4) if wtype == "numerical" else ())
+    return EngineConfig(batch=n, **kw), R.UNetCfg(**kw)
+
+
+@pytest.mark.parametrize("n,hw,normalizer,loss_type,wtype", [
+    (2, 128, "batch_norm", "xentropy", "numerical"),
+    (3, 64, "instance_norm", "xentropy", "numerical"),
+    (2, 64, "batch_norm", "dice", "none"),
+    (2, 64, "batch_norm", "xentropy", "proportion"),
+])
+def test_train_step_parity(ctx, n, hw, normalizer, loss_type, wtype):
+    ecfg, rcfg = _cfgs(n, hw, normalizer, loss_type, wtype)
+    images, labels = synthetic.make_batch(n, hw, hw, 3, seed=1357 + n)
+    params = R.init_params(rcfg, seed=7)
+    eng = UNetEngine(ctx, ecfg)
+    eng.set_weights(params)
+    eng.set_inputs(images, labels)
+    lr = 1e-3
+    eng.forward(True)
+    eng.predict_outputs(True)
+    eng.loss_backward()
+    ctx.check_device()
+    k = rcfg.num_classes
+    logits = eng.logits.download(np.float32, (n, hw, hw, k))
+    dlogits = eng.dlogits.download(np.float32, (n, hw, hw, k))
+    grads = eng.get_grads()
+    stored = eng.get_stored_forward()
+    masks = eng.masks.download(np.uint8, (k - 1, n, hw, hw))
+    argmax = eng.argmax.download(np.uint8, (n, hw, hw))
+    counts = eng.read_counts()
+    eng.optimizer_step(lr)
+    ctx.check_device()
+    data_loss, reg_loss = eng.read_loss()
+    new_w = eng.get_weights()
+    eng.close()
+
+    # forward: free-running oracle with bf16 storage emulation
+    tape = R.forward(params, images, rcfg, True, rnd=round_bf16)
+    loss_o, _ = R.loss_and_dlogits(tape, labels, rcfg)
+    assert rel(logits, tape.logits) < 1.5e-2
+    assert abs(data_loss - float(loss_o)) < 1e-3 * abs(float(loss_o))
+    assert abs(reg_loss - R.regularization_loss(params, rcfg)) < 1e-6
+    if normalizer == "batch_norm":
+        for name, v in tape.new_moving.items():
+            assert rel(new_w[name], v) < 1e-2, name
+
+    # backward: oracle over the device's stored forward tape
+    tft = R.tape_from_stored(params, images, stored, logits, rcfg, wrnd=round_bf16)
+    _, dl = R.loss_and_dlogits(tft, labels, rcfg)
+    assert rel(dlogits, dl) < 1e-5
+    g_ref = R.backward(tft, dl, rcfg, rnd=round_bf16)
+    errs = {name: rel(grads[name], g) for name, g in g_ref.items()}
+    assert np.median(list(errs.values())) < 1e-2, errs
+    assert max(errs.values()) < 1.5e-2, max(errs.items(), key=lambda t: t[1])
+
+    # masks / argmax / counts: bit-exact functions of the device's own logits
+    prob = R.O.softmax(logits)
+    decided = np.abs(prob[..., 1:] - 0.5).transpose(3, 0, 1, 2) > 1e-6
+    m_ref = np.stack([(prob[..., c] > 0.5).astype(np.uint8) for c in range(1, k)])
+    assert not ((masks != m_ref) & decided).any()
+    srt = np.sort(prob, axis=-1)
+    clear = (srt[..., -1] - srt[..., -2]) > 1e-6
+    assert np.array_equal(argmax[clear], np.argmax(prob, axis=-1).astype(np.uint8)[clear])
+    for c in range(1, k):
+        i_, l_, r_ = R.O.seg_counts(masks[c - 1][..., None], labels, c)
+        assert np.array_equal(counts[:, c - 1, 0], i_)
+        assert np.array_equal(counts[:, c - 1, 1], l_)
+        assert np.array_equal(counts[:, c - 1, 2], r_)
+
+    # optimizer: oracle Adam applied to the device gradients reproduces the device update
+    tg = R.total_grads(params, grads, rcfg)
+    for name in R.trainable_names(rcfg, params):
+        w, _, _ = R.O.adam_step(params[name].astype(np.float64), tg[name].astype(np.float64), 0.0, 0.0, 1, lr)
+        assert rel(new_w[name].astype(np.float64) - params[name], w - params[name]) < 1e-3, name
+
+
+def test_eval_mode_uses_moving_statistics(ctx):
+    n, hw = 2, 64
+    ecfg, rcfg = _cfgs(n, hw, "batch_norm", "xentropy", "none")
+    ecfg.training = False
+    params = R.init_params(rcfg, seed=3)
+    rng = np.random.default_rng(0)
+    for name in params:
+        if name.endswith("moving_mean"):
+            params[name] = rng.normal(0, 0.05, params[name].shape).astype(np.float32)
+        if name.endswith("moving_variance"):
+            params[name] = rng.uniform(0.05, 0.15, params[name].shape).astype(np.float32)
+    images, labels = synthetic.make_batch(n, hw, hw, 3, seed=5)
+    eng = UNetEngine(ctx, ecfg)
+    eng.set_weights(params)
+    eng.set_inputs(images, labels)
+    eng.forward(False)
+    eng.predict_outputs(False)
+    ctx.check_device()
+    logits = eng.logits.download(np.float32, (n, hw, hw, 3))
+    after = eng.get_weights()
+    eng.close()
+    tape = R.forward(params, images, rcfg, False, rnd=round_bf16)
+    assert rel(logits, tape.logits) < 1.5e-2
+    for name in params:
+        assert np.array_equal(after[name], params[name]), f"{name} changed in eval mode"
+
+
+def test_full_size_training_properties(ctx):
+    """BASELINE cfg2 shapes (batch 64, 256x256x3): properties the oracle is not needed for."""
+    n, hw = 64, 256
+    ecfg, _ = _cfgs(n, hw, "batch_norm", "xentropy", "numerical")
+    images, labels = synthetic.make_batch(n, hw, hw, 3)
+    eng = UNetEngine(ctx, ecfg)
+    eng.init_weights(seed=0)
+    eng.set_inputs(images, labels)
+    w0 = eng.get_weights()
+    # (1) determinism: two forward+backward passes from the same state give bit-identical gradients
+    eng.forward(True); eng.predict_outputs(True); eng.loss_backward(); ctx.check_device()
+    g1 = eng.G.download(np.float32, (eng.n_train,))
+    c1 = eng.read_counts()
+    eng.set_weights(w0)     # forward(True) advanced the moving statistics: restore
+    eng.forward(True); eng.predict_outputs(True); eng.loss_backward(); ctx.check_device()
+    g2 = eng.G.download(np.float32, (eng.n_train,))
+    assert np.array_equal(g1, g2), "gradients are not bit-reproducible"
+    assert np.all(np.isfinite(g1))
+    # (2) integer identities of the Dice counts: R equals the label histogram, I <= min(L, R)
+    for c in (1, 2):
+        r = (labels.reshape(n, -1) == c).sum(axis=1)
+        assert np.array_equal(c1[:, c - 1, 2], r)
+        assert np.all(c1[:, c - 1, 0] <= np.minimum(c1[:, c - 1, 1], c1[:, c - 1, 2]))
+    # (3) sum over classes of dlogits is zero per pixel (softmax - onehot, any weight)
+    dl = eng.dlogits.download(np.float32, (n * hw * hw, 3))
+    assert np.abs(dl.sum(axis=1)).max() < 1e-9
+    # (4) training on a fixed batch reduces the loss
+    losses = []
+    eng.set_weights(w0)
+    for _ in range(6):
+        eng.train_step(1e-3)
+        losses.append(sum(eng.read_loss()))
+    ctx.check_device()
+    assert np.all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    eng.close()
