@@ -130,7 +130,7 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         try:
             with open(self.path) as f:
                 for ln in f:
@@ -138,10 +138,12 @@ class ClockSampler:
                     if len(parts) < 9:
                         continue
                     try:
-                        sm.append(float(parts[1]))
-                        mx.append(float(parts[2]))
+                        a, b, c = float(parts[1]), float(parts[2]), float(parts[3])
                     except ValueError:
                         continue
+                    sm.append(a)
+                    mx.append(b)
+                    pw.append(c)
                     for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
                                        parts[5:9]):
                         if v.lower().startswith("active"):
@@ -150,9 +152,11 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             pass
         if sm:
-            # median over the busiest half of the samples = "under load"
-            top = sorted(sm)[len(sm) // 2:]
-            out.update(sm_mhz=statistics.median(top), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+            # "under load" = samples drawing at least 60 % of the highest power seen in the window
+            lim = 0.6 * max(pw)
+            load = [a for a, c in zip(sm, pw) if c >= lim] or sm
+            out.update(sm_mhz=statistics.median(load), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       samples_under_load=len(load), power_w_max=max(pw))
         return out
 
 
@@ -207,10 +211,10 @@ def run_b200(args):
         return n.value
 
     # ---- device-resident arm
+    sampler = ClockSampler(local) if rank == 0 else None   # started before warm-up: nvidia-smi takes ~1 s to spin up
     for _ in range(max(args.warmup, 3)):
         eng.train_step(lr)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     eng.enable_conv_timing(True)
     l0 = launches()
     e0, e1 = ctx.new_event(), ctx.new_event()

@@ -10,14 +10,21 @@
 using namespace bsl;
 
 namespace bsl {
+// Block = 32 consecutive outputs x 4 partial lanes (128 threads): lane q sums partials q, q+4, ...
+// (coalesced across outputs), then the 4 lane sums are added in a fixed order.
 __global__ void pixel_reduce_final_kernel(const float* __restrict__ part, int blocks, int kc,
                                           double* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= kc) return;
-  const float* p = part + (long long)blockIdx.y * blocks * kc + i;
+  __shared__ double sm[4][32];
+  const int il = threadIdx.x & 31, q = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + il;
   double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += (double)p[(long long)b * kc];
-  out[(long long)blockIdx.y * kc + i] = s;
+  if (i < kc) {
+    const float* p = part + (long long)blockIdx.y * blocks * kc + i;
+    for (int b = q; b < blocks; b += 4) s += (double)p[(long long)b * kc];
+  }
+  sm[q][il] = s;
+  __syncthreads();
+  if (q == 0 && i < kc) out[(long long)blockIdx.y * kc + i] = ((sm[0][il] + sm[1][il]) + sm[2][il]) + sm[3][il];
 }
 
 static float* g_scratch = nullptr;
@@ -39,22 +46,28 @@ int bsl_scratch(bsl_ctx* ctx, size_t bytes, float** out) {
 namespace {
 
 struct StatsF {
-  static constexpr int K = 2;
+  static constexpr int K = 2, NIN = 1, UNROLL = 8;
+  struct State {};
   const __nv_bfloat16* y;
   int ld;
-  __device__ void operator()(long long p, int, int ch0, float (&acc)[2][8]) const {
+  __device__ void init(State&, int, int) const {}
+  __device__ void load(long long p, int ch0, uint4 (&raw)[1]) const { raw[0] = ld16(y + p * ld + ch0); }
+  __device__ void accum(const State&, const uint4 (&raw)[1], float (&acc)[2][8]) const {
     float v[8];
-    unpack8(ld16(y + p * ld + ch0), v);
+    unpack8(raw[0], v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       acc[0][j] += v[j];
-      acc[1][j] += v[j] * v[j];
+      acc[1][j] = fmaf(v[j], v[j], acc[1][j]);
     }
   }
 };
 
 struct BwdF {
-  static constexpr int K = 2;
+  static constexpr int K = 2, NIN = 2, UNROLL = 4;
+  struct State {
+    float scale[8], shift[8], rstd[8], mrstd[8];
+  };
   const __nv_bfloat16* y;
   const __nv_bfloat16* da;
   const float* mean;
@@ -62,18 +75,31 @@ struct BwdF {
   const float* scale;
   const float* shift;
   int y_ld, da_ld, c, relu;
-  __device__ void operator()(long long p, int group, int ch0, float (&acc)[2][8]) const {
-    float v[8], g[8];
-    unpack8(ld16(y + p * y_ld + ch0), v);
-    unpack8(ld16(da + p * da_ld + ch0), g);
+  __device__ void init(State& st, int group, int ch0) const {
     const int o = group * c + ch0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(v[j], scale[o + j], shift[o + j]);
+      st.scale[j] = scale[o + j];
+      st.shift[j] = shift[o + j];
+      st.rstd[j] = rstd[o + j];
+      st.mrstd[j] = mean[o + j] * rstd[o + j];
+    }
+  }
+  __device__ void load(long long p, int ch0, uint4 (&raw)[2]) const {
+    raw[0] = ld16(y + p * y_ld + ch0);
+    raw[1] = ld16(da + p * da_ld + ch0);
+  }
+  __device__ void accum(const State& st, const uint4 (&raw)[2], float (&acc)[2][8]) const {
+    float v[8], g[8];
+    unpack8(raw[0], v);
+    unpack8(raw[1], g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float z = fmaf(v[j], st.scale[j], st.shift[j]);
       const float dz = (!relu || z > 0.f) ? g[j] : 0.f;
-      const float xh = (v[j] - mean[o + j]) * rstd[o + j];
+      const float xh = fmaf(v[j], st.rstd[j], -st.mrstd[j]);
       acc[0][j] += dz;
-      acc[1][j] += dz * xh;
+      acc[1][j] = fmaf(dz, xh, acc[1][j]);
     }
   }
 };
@@ -111,66 +137,100 @@ __global__ void norm_finalize_kernel(int groups, int c, double m, float eps, flo
   shift_o[i] = (center ? beta[ch] : 0.f) - (float)mean * sc;
 }
 
+// Elementwise passes share one thread layout: block = (rows x c/8 channel groups), a thread owns ONE
+// 8-channel group for the whole launch, so its per-channel parameters live in registers, and it
+// keeps 4 independent 16 B loads in flight. grid.y = sample index when parameters are per sample.
+constexpr int EW_UNROLL = 4;
+
 __global__ void norm_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, __nv_bfloat16* __restrict__ a,
-                                  int a_ld, long long pixels, int hw, int c, int per_sample, int relu,
+                                  int a_ld, long long pixels_per_group, int c, int relu,
                                   const float* __restrict__ scale, const float* __restrict__ shift) {
   const int cg = c / 8;
-  const long long total = pixels * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / cg;
-    const int ch0 = (int)(i - p * cg) * 8;
-    const int o = (per_sample ? (int)(p / hw) * c : 0) + ch0;
+  const int rows = blockDim.x / cg;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  if (r >= rows) return;
+  const int ch0 = g * 8;
+  const int o = blockIdx.y * c + ch0;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[o + j]; sh[j] = shift[o + j]; }
+  const long long base = (long long)blockIdx.y * pixels_per_group;
+  const long long stride = (long long)gridDim.x * rows;
+  long long p = (long long)blockIdx.x * rows + r;
+  for (; p + (EW_UNROLL - 1) * stride < pixels_per_group; p += EW_UNROLL * stride) {
+    uint4 raw[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) raw[u] = ld16(y + (base + p + u * stride) * y_ld + ch0);
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      float v[8];
+      unpack8(raw[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(v[j], sc[j], sh[j]);
+        v[j] = relu ? fmaxf(z, 0.f) : z;
+      }
+      st16(a + (base + p + u * stride) * a_ld + ch0, pack8(v));
+    }
+  }
+  for (; p < pixels_per_group; p += stride) {
     float v[8];
-    unpack8(ld16(y + p * y_ld + ch0), v);
+    unpack8(ld16(y + (base + p) * y_ld + ch0), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float z = fmaf(v[j], scale[o + j], shift[o + j]);
+      const float z = fmaf(v[j], sc[j], sh[j]);
       v[j] = relu ? fmaxf(z, 0.f) : z;
     }
-    st16(a + p * a_ld + ch0, pack8(v));
+    st16(a + (base + p) * a_ld + ch0, pack8(v));
   }
 }
 
 // Same as norm_apply_kernel, and also emits the 2x2/s2 max-pooled tensor from the same read.
+// "pixels" here are pooled pixels of one sample (grid.y = sample).
 __global__ void norm_apply_pool_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, __nv_bfloat16* __restrict__ a,
-                                       int a_ld, __nv_bfloat16* __restrict__ pooled, int p_ld, int n, int h, int w,
-                                       int c, int per_sample, int relu, const float* __restrict__ scale,
+                                       int a_ld, __nv_bfloat16* __restrict__ pooled, int p_ld, int h, int w, int c,
+                                       int per_sample, int relu, const float* __restrict__ scale,
                                        const float* __restrict__ shift) {
   const int cg = c / 8, ho = h / 2, wo = w / 2;
-  const long long total = (long long)n * ho * wo * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    long long t = i;
-    const int ch0 = (int)(t % cg) * 8; t /= cg;
-    const int xo = (int)(t % wo); t /= wo;
-    const int yo = (int)(t % ho);
-    const int img = (int)(t / ho);
-    const int o = (per_sample ? img * c : 0) + ch0;
-    float sc[8], sh[8], mx[8];
+  const int rows = blockDim.x / cg;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  if (r >= rows) return;
+  const int ch0 = g * 8;
+  const int img = blockIdx.y;
+  const int o = (per_sample ? img * c : 0) + ch0;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = scale[o + j]; sh[j] = shift[o + j]; mx[j] = -INFINITY; }
+  for (int j = 0; j < 8; ++j) { sc[j] = scale[o + j]; sh[j] = shift[o + j]; }
+  const long long in0 = (long long)img * h * w, out0 = (long long)img * ho * wo;
+  for (int q = blockIdx.x * rows + r; q < ho * wo; q += gridDim.x * rows) {
+    const int yo = q / wo, xo = q - yo * wo;
+    long long pix[4];
+    uint4 raw[4];
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
+    for (int k = 0; k < 4; ++k) {
+      pix[k] = in0 + (long long)(2 * yo + (k >> 1)) * w + (2 * xo + (k & 1));
+      raw[k] = ld16(y + pix[k] * y_ld + ch0);
+    }
+    float mx[8];
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const long long p = ((long long)img * h + (2 * yo + dy)) * w + (2 * xo + dx);
-        float v[8];
-        unpack8(ld16(y + p * y_ld + ch0), v);
+    for (int j = 0; j < 8; ++j) mx[j] = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float z = fmaf(v[j], sc[j], sh[j]);
-          v[j] = relu ? fmaxf(z, 0.f) : z;
-        }
-        const uint4 packed = pack8(v);
-        st16(a + p * a_ld + ch0, packed);
-        float r[8];
-        unpack8(packed, r);  // pool the bf16-rounded values: what the next layer actually sees
+    for (int k = 0; k < 4; ++k) {
+      float v[8];
+      unpack8(raw[k], v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], r[j]);
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(v[j], sc[j], sh[j]);
+        v[j] = relu ? fmaxf(z, 0.f) : z;
       }
-    const long long q = ((long long)img * ho + yo) * wo + xo;
-    st16(pooled + q * p_ld + ch0, pack8(mx));
+      const uint4 packed = pack8(v);
+      st16(a + pix[k] * a_ld + ch0, packed);
+      float rr[8];
+      unpack8(packed, rr);  // pool the bf16-rounded values: what the next layer actually sees
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx[j] = fmaxf(mx[j], rr[j]);
+    }
+    st16(pooled + (out0 + q) * p_ld + ch0, pack8(mx));
   }
 }
 
@@ -196,29 +256,62 @@ __global__ void norm_bwd_finalize_kernel(int groups, int c, double m, const doub
 
 __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld,
                                       const __nv_bfloat16* __restrict__ da, int da_ld,
-                                      __nv_bfloat16* __restrict__ dy, int dy_ld, long long pixels, int hw, int c,
-                                      int per_sample, int relu, const float* __restrict__ mean,
-                                      const float* __restrict__ rstd, const float* __restrict__ scale,
-                                      const float* __restrict__ shift, const float* __restrict__ c1,
-                                      const float* __restrict__ c2) {
+                                      __nv_bfloat16* __restrict__ dy, int dy_ld, long long pixels_per_group, int c,
+                                      int relu, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                      const float* __restrict__ c1, const float* __restrict__ c2) {
   const int cg = c / 8;
-  const long long total = pixels * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / cg;
-    const int ch0 = (int)(i - p * cg) * 8;
-    const int o = (per_sample ? (int)(p / hw) * c : 0) + ch0;
-    float v[8], g[8];
-    unpack8(ld16(y + p * y_ld + ch0), v);
-    unpack8(ld16(da + p * da_ld + ch0), g);
+  const int rows = blockDim.x / cg;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  if (r >= rows) return;
+  const int ch0 = g * 8;
+  const int o = blockIdx.y * c + ch0;
+  // dy = scale*(dz - c1 - xhat*c2), xhat = (v - mean)*rstd  ==  scale*dz + k1*v + k0
+  float sc[8], sh[8], k1[8], k0[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[o + j];
+    sh[j] = shift[o + j];
+    const float t = sc[j] * c2[o + j] * rstd[o + j];
+    k1[j] = -t;
+    k0[j] = fmaf(t, mean[o + j], -sc[j] * c1[o + j]);
+  }
+  const long long base = (long long)blockIdx.y * pixels_per_group;
+  const long long stride = (long long)gridDim.x * rows;
+  long long p = (long long)blockIdx.x * rows + r;
+  constexpr int U = 2;
+  for (; p + (U - 1) * stride < pixels_per_group; p += U * stride) {
+    uint4 ry[U], rg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      ry[u] = ld16(y + (base + p + u * stride) * y_ld + ch0);
+      rg[u] = ld16(da + (base + p + u * stride) * da_ld + ch0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float v[8], gg[8];
+      unpack8(ry[u], v);
+      unpack8(rg[u], gg);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(v[j], sc[j], sh[j]);
+        const float dz = (!relu || z > 0.f) ? gg[j] : 0.f;
+        v[j] = fmaf(sc[j], dz, fmaf(k1[j], v[j], k0[j]));
+      }
+      st16(dy + (base + p + u * stride) * dy_ld + ch0, pack8(v));
+    }
+  }
+  for (; p < pixels_per_group; p += stride) {
+    float v[8], gg[8];
+    unpack8(ld16(y + (base + p) * y_ld + ch0), v);
+    unpack8(ld16(da + (base + p) * da_ld + ch0), gg);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(v[j], scale[o + j], shift[o + j]);
-      const float dz = (!relu || z > 0.f) ? g[j] : 0.f;
-      const float xh = (v[j] - mean[o + j]) * rstd[o + j];
-      v[j] = scale[o + j] * (dz - c1[o + j] - xh * c2[o + j]);
+      const float z = fmaf(v[j], sc[j], sh[j]);
+      const float dz = (!relu || z > 0.f) ? gg[j] : 0.f;
+      v[j] = fmaf(sc[j], dz, fmaf(k1[j], v[j], k0[j]));
     }
-    st16(dy + p * dy_ld + ch0, pack8(v));
+    st16(dy + (base + p) * dy_ld + ch0, pack8(v));
   }
 }
 
@@ -272,18 +365,56 @@ __global__ void maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ act, in
 __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ dy,
                                 int dy_ld, __nv_bfloat16* __restrict__ out, int o_ld, long long pixels, int c) {
   const int cg = c / 8;
-  const long long total = pixels * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / cg;
-    const int ch0 = (int)(i - p * cg) * 8;
-    float v[8], g[8];
-    unpack8(ld16(y + p * y_ld + ch0), v);
-    unpack8(ld16(dy + p * dy_ld + ch0), g);
+  const int rows = blockDim.x / cg;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  if (r >= rows) return;
+  const int ch0 = g * 8;
+  const long long stride = (long long)gridDim.x * rows;
+  long long p = (long long)blockIdx.x * rows + r;
+  for (; p + (EW_UNROLL - 1) * stride < pixels; p += EW_UNROLL * stride) {
+    uint4 ry[EW_UNROLL], rg[EW_UNROLL];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = v[j] > 0.f ? g[j] : 0.f;
-    st16(out + p * o_ld + ch0, pack8(g));
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      ry[u] = ld16(y + (p + u * stride) * y_ld + ch0);
+      rg[u] = ld16(dy + (p + u * stride) * dy_ld + ch0);
+    }
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      float v[8], gg[8];
+      unpack8(ry[u], v);
+      unpack8(rg[u], gg);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gg[j] = v[j] > 0.f ? gg[j] : 0.f;
+      st16(out + (p + u * stride) * o_ld + ch0, pack8(gg));
+    }
   }
+  for (; p < pixels; p += stride) {
+    float v[8], gg[8];
+    unpack8(ld16(y + p * y_ld + ch0), v);
+    unpack8(ld16(dy + p * dy_ld + ch0), gg);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) gg[j] = v[j] > 0.f ? gg[j] : 0.f;
+    st16(out + p * o_ld + ch0, pack8(gg));
+  }
+}
+
+// Launch shape for the (rows x channel-group) elementwise kernels.
+struct EwPlan {
+  int threads, rows;
+  unsigned blocks;
+};
+EwPlan ew_plan(bsl_ctx* ctx, long long pixels_per_group, int groups, int c, int unroll) {
+  EwPlan p;
+  const int cg = c / 8;
+  p.threads = cg > 256 ? cg : 256;
+  p.rows = p.threads / cg;
+  p.threads = p.rows * cg;
+  long long want = (pixels_per_group + (long long)p.rows * unroll - 1) / ((long long)p.rows * unroll);
+  long long cap = (16LL * ctx->sm_count + groups - 1) / groups;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  p.blocks = (unsigned)want;
+  return p;
 }
 
 unsigned ew_grid(bsl_ctx* ctx, long long items) {
@@ -342,10 +473,12 @@ int bsl_norm_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const fl
   int rc = check_norm(ctx, d);
   if (rc) return rc;
   if (!x || !scale || !shift || !y) return bsl_fail(ctx, BSL_EINVAL, "norm_apply: null buffer");
-  const long long pixels = (long long)d->n * d->hw;
-  norm_apply_kernel<<<ew_grid(ctx, pixels * (d->c / 8)), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld, reinterpret_cast<__nv_bfloat16*>(y), d->y_ld, pixels,
-      d->hw, d->c, d->mode, d->relu, scale, shift);
+  const int groups = d->mode ? d->n : 1;
+  const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
+  const EwPlan pl = ew_plan(ctx, ppg, groups, d->c, EW_UNROLL);
+  norm_apply_kernel<<<dim3(pl.blocks, groups), pl.threads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld, reinterpret_cast<__nv_bfloat16*>(y), d->y_ld, ppg, d->c,
+      d->relu, scale, shift);
   BSL_LAUNCH_CHECK(ctx, "norm_apply_kernel");
   return BSL_OK;
 }
@@ -357,10 +490,10 @@ int bsl_norm_apply_pool(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, cons
   if (!x || !scale || !shift || !y || !pooled) return bsl_fail(ctx, BSL_EINVAL, "norm_apply_pool: null buffer");
   if (h * w != d->hw || (h & 1) || (w & 1) || pooled_ld < d->c || pooled_ld % 8)
     return bsl_fail(ctx, BSL_EINVAL, "norm_apply_pool: h=%d w=%d must be even and match hw=%d", h, w, d->hw);
-  const long long items = (long long)d->n * (h / 2) * (w / 2) * (d->c / 8);
-  norm_apply_pool_kernel<<<ew_grid(ctx, items), 256, 0, as_stream(stream)>>>(
+  const EwPlan pl = ew_plan(ctx, (long long)(h / 2) * (w / 2), d->n, d->c, 1);
+  norm_apply_pool_kernel<<<dim3(pl.blocks, d->n), pl.threads, 0, as_stream(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld, reinterpret_cast<__nv_bfloat16*>(y), d->y_ld,
-      reinterpret_cast<__nv_bfloat16*>(pooled), pooled_ld, d->n, h, w, d->c, d->mode, d->relu, scale, shift);
+      reinterpret_cast<__nv_bfloat16*>(pooled), pooled_ld, h, w, d->c, d->mode, d->relu, scale, shift);
   BSL_LAUNCH_CHECK(ctx, "norm_apply_pool_kernel");
   return BSL_OK;
 }
@@ -399,11 +532,12 @@ int bsl_norm_bwd_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, cons
   if (rc) return rc;
   if (!x || !dy || !mean || !rstd || !scale || !shift || !c1 || !c2 || !dx)
     return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_apply: null buffer");
-  const long long pixels = (long long)d->n * d->hw;
-  norm_bwd_apply_kernel<<<ew_grid(ctx, pixels * (d->c / 8)), 256, 0, as_stream(stream)>>>(
+  const int groups = d->mode ? d->n : 1;
+  const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
+  const EwPlan pl = ew_plan(ctx, ppg, groups, d->c, 2);
+  norm_bwd_apply_kernel<<<dim3(pl.blocks, groups), pl.threads, 0, as_stream(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld, reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld,
-      reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, pixels, d->hw, d->c, d->mode, d->relu, mean, rstd, scale, shift,
-      c1, c2);
+      reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, ppg, d->c, d->relu, mean, rstd, scale, shift, c1, c2);
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_apply_kernel");
   return BSL_OK;
 }
@@ -428,7 +562,8 @@ int bsl_relu_bwd(bsl_ctx* ctx, long long pixels, int c, const void* y, int y_ld,
   if (!ctx) return BSL_EINVAL;
   if (!y || !dy || !out) return bsl_fail(ctx, BSL_EINVAL, "relu_bwd: null buffer");
   if (c % 8) return bsl_fail(ctx, BSL_EUNSUPPORTED, "relu_bwd: c%%8");
-  relu_bwd_kernel<<<ew_grid(ctx, pixels * (c / 8)), 256, 0, as_stream(stream)>>>(
+  const EwPlan pl = ew_plan(ctx, pixels, 1, c, EW_UNROLL);
+  relu_bwd_kernel<<<pl.blocks, pl.threads, 0, as_stream(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(y), y_ld, reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld,
       reinterpret_cast<__nv_bfloat16*>(out), out_ld, pixels, c);
   BSL_LAUNCH_CHECK(ctx, "relu_bwd_kernel");

@@ -49,12 +49,15 @@ __global__ void scale_f32_kernel(float* __restrict__ x, size_t n, float a) {
 }
 
 struct SumF {
-  static constexpr int K = 1;
+  static constexpr int K = 1, NIN = 1, UNROLL = 8;
+  struct State {};
   const __nv_bfloat16* x;
   int ld;
-  __device__ void operator()(long long p, int, int ch0, float (&acc)[1][8]) const {
+  __device__ void init(State&, int, int) const {}
+  __device__ void load(long long p, int ch0, uint4 (&raw)[1]) const { raw[0] = bsl::ld16(x + p * ld + ch0); }
+  __device__ void accum(const State&, const uint4 (&raw)[1], float (&acc)[1][8]) const {
     float v[8];
-    bsl::unpack8(bsl::ld16(x + p * ld + ch0), v);
+    bsl::unpack8(raw[0], v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[0][j] += v[j];
   }

@@ -33,13 +33,17 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 __device__ __forceinline__ uint4 ld16(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
 __device__ __forceinline__ void st16(__nv_bfloat16* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
 
-// F must provide: static constexpr int K; __device__ void operator()(long long pixel /*global*/,
-// int group, int ch0, float (&acc)[K][8]) const  -- accumulates the contribution of 8 channels.
-template <class F>
+// F must provide: static constexpr int K; a nested `struct State` of per-thread registers;
+//   __device__ void init(State&, int group, int ch0) const          -- hoists per-channel parameters
+//   __device__ void load(long long pixel, int ch0, uint4 (&raw)[NIN]) const, with static constexpr int NIN
+//   __device__ void accum(const State&, const uint4 (&raw)[NIN], float (&acc)[K][8]) const
+// Loads of UNROLL pixels are issued before any is consumed (memory-level parallelism).
+template <class F, int UNROLL>
 __global__ void pixel_reduce_kernel(F f, long long pixels_per_group, long long ppb, int c,
                                     float* __restrict__ part) {
   extern __shared__ float sm[];  // [rows][K][c]
   constexpr int K = F::K;
+  constexpr int NIN = F::NIN;
   const int cg = c / 8;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg;
@@ -51,10 +55,24 @@ __global__ void pixel_reduce_kernel(F f, long long pixels_per_group, long long p
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[k][j] = 0.f;
   if (r < rows) {
+    typename F::State st;
+    f.init(st, group, g * 8);
     const long long p0 = blockIdx.x * ppb;
     const long long p1 = min(pixels_per_group, p0 + ppb);
     const long long base = (long long)group * pixels_per_group;
-    for (long long p = p0 + r; p < p1; p += rows) f(base + p, group, g * 8, acc);
+    long long p = p0 + r;
+    for (; p + (long long)(UNROLL - 1) * rows < p1; p += (long long)UNROLL * rows) {
+      uint4 raw[UNROLL][NIN];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) f.load(base + p + (long long)u * rows, g * 8, raw[u]);
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) f.accum(st, raw[u], acc);
+    }
+    for (; p < p1; p += rows) {
+      uint4 raw[NIN];
+      f.load(base + p, g * 8, raw);
+      f.accum(st, raw, acc);
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
@@ -87,8 +105,8 @@ inline ReducePlan plan_reduce(bsl_ctx* ctx, long long pixels_per_group, int grou
   // keep K*c*rows*4 bytes of smem under 48 KB
   while ((size_t)p.rows * K * c * 4 > 48 * 1024 && p.rows > 1) p.rows /= 2;
   p.threads = p.rows * cg;
-  long long want = (pixels_per_group + 1023) / 1024;
-  long long cap = (4LL * ctx->sm_count + groups - 1) / groups;
+  long long want = (pixels_per_group + 511) / 512;
+  long long cap = (8LL * ctx->sm_count + groups - 1) / groups;
   if (cap < 1) cap = 1;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
@@ -109,8 +127,8 @@ int run_pixel_reduce(bsl_ctx* ctx, const F& f, long long pixels_per_group, int g
   float* part = nullptr;
   int rc = bsl_scratch(ctx, p.scratch_bytes, &part);
   if (rc) return rc;
-  pixel_reduce_kernel<F><<<dim3(p.blocks, groups), p.threads, p.smem, stream>>>(f, pixels_per_group, p.ppb, c,
-                                                                               part);
+  pixel_reduce_kernel<F, F::UNROLL><<<dim3(p.blocks, groups), p.threads, p.smem, stream>>>(f, pixels_per_group,
+                                                                                          p.ppb, c, part);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_kernel");
   const int kc = F::K * c;
   pixel_reduce_final_kernel<<<dim3((kc + 127) / 128, groups), 128, 0, stream>>>(part, p.blocks, kc, out);

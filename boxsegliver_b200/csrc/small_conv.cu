@@ -57,6 +57,38 @@ __global__ void stem_fprop_kernel(const float* __restrict__ x, const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------ stem im2col
+// col[p][t*CIN + ci] = x[p + tap t][ci] (zero outside the image, zero for columns >= taps*CIN), bf16,
+// 64 columns per pixel. With this matrix the stem becomes a 1x1 conv with cin = 64 on the tcgen05
+// path (fprop and wgrad), instead of a CUDA-core kernel. Thread = (pixel, 8-column group).
+__global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int n, int h, int wd,
+                                   int cin, int kh, int kw) {
+  const long long total = (long long)n * h * wd * 8;
+  const int ph = (kh - 1) / 2, pw = (kw - 1) / 2;
+  const int kcols = kh * kw * cin;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i & 7);
+    const long long p = i >> 3;
+    const int xw = (int)(p % wd);
+    const int yh = (int)((p / wd) % h);
+    const long long img = p / ((long long)wd * h);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col_i = g * 8 + j;
+      float val = 0.f;
+      if (col_i < kcols) {
+        const int t = col_i / cin, ci = col_i - t * cin;
+        const int yy = yh + t / kw - ph, xx = xw + t % kw - pw;
+        if (yy >= 0 && yy < h && xx >= 0 && xx < wd) val = __ldg(x + ((img * h + yy) * wd + xx) * cin + ci);
+      }
+      v[j] = val;
+    }
+    st16(col + p * 64 + g * 8, pack8(v));
+  }
+}
+
 // ------------------------------------------------------------------------------------ stem wgrad
 // grid = (pixel chunks, kh). Warp = one 8-channel group of dy, lane = pixel lane; each thread keeps
 // kw*CIN*8 accumulators for filter row r, reduced across the warp with shuffles, then one fp32
@@ -191,19 +223,29 @@ __global__ void head_dgrad_kernel(const float* __restrict__ dl, const float* __r
 
 template <int COUT>
 struct HeadWgradF {
-  static constexpr int K = COUT;
+  static constexpr int K = COUT, NIN = 2, UNROLL = 4;
+  struct State {};
   const __nv_bfloat16* x;
   const float* dl;
   int ld;
-  __device__ void operator()(long long p, int, int ch0, float (&acc)[COUT][8]) const {
+  __device__ void init(State&, int, int) const {}
+  // raw[1] carries the COUT (<= 4) fp32 dlogits of the pixel
+  __device__ void load(long long p, int ch0, uint4 (&raw)[2]) const {
+    raw[0] = ld16(x + p * ld + ch0);
+    float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < COUT; ++k) d[k] = __ldg(dl + p * COUT + k);
+    raw[1] = make_uint4(__float_as_uint(d[0]), __float_as_uint(d[1]), __float_as_uint(d[2]), __float_as_uint(d[3]));
+  }
+  __device__ void accum(const State&, const uint4 (&raw)[2], float (&acc)[COUT][8]) const {
     float v[8];
-    unpack8(ld16(x + p * ld + ch0), v);
+    unpack8(raw[0], v);
+    const float d[4] = {__uint_as_float(raw[1].x), __uint_as_float(raw[1].y), __uint_as_float(raw[1].z),
+                        __uint_as_float(raw[1].w)};
 #pragma unroll
-    for (int k = 0; k < COUT; ++k) {
-      const float d = __ldg(dl + p * COUT + k);
+    for (int k = 0; k < COUT; ++k)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(v[j], d, acc[k][j]);
-    }
+      for (int j = 0; j < 8; ++j) acc[k][j] = fmaf(v[j], d[k], acc[k][j]);
   }
 };
 
@@ -275,6 +317,19 @@ int bsl_conv2d_stem_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x
     default: return bsl_fail(ctx, BSL_EUNSUPPORTED, "stem_fprop: cin=%d (1..5)", d->cin);
   }
   BSL_LAUNCH_CHECK(ctx, "stem_fprop_kernel");
+  return BSL_OK;
+}
+
+int bsl_stem_im2col(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x, void* col, void* stream) {
+  int rc = check_small(ctx, d);
+  if (rc) return rc;
+  if (!x || !col) return bsl_fail(ctx, BSL_EINVAL, "stem_im2col: null buffer");
+  if (d->kh * d->kw * d->cin > 64 || d->cin < 1)
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "stem_im2col: kh*kw*cin = %d must be <= 64", d->kh * d->kw * d->cin);
+  const long long items = (long long)d->n * d->h * d->w * 8;
+  stem_im2col_kernel<<<ew_grid(ctx, items), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(col),
+                                                                         d->n, d->h, d->w, d->cin, d->kh, d->kw);
+  BSL_LAUNCH_CHECK(ctx, "stem_im2col_kernel");
   return BSL_OK;
 }
 

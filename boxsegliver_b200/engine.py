@@ -82,6 +82,7 @@ class Param:
     shape: tuple
     offset: int = 0          # element offset in the arena
     size: int = 0
+    alloc: int = 0           # elements reserved in the arena (>= size; the stem filter is padded to 64 x 64)
     region: str = "A"        # "A" regularised, "B" not, "S" moving statistics (not trained)
 
 
@@ -109,6 +110,8 @@ def _align(n, a=64):
 class UNetEngine:
     def __init__(self, ctx: Context, cfg: EngineConfig):
         self.ctx, self.cfg = ctx, cfg
+        if 9 * cfg.channel > 64:
+            raise ValueError("im_channel must be <= 7 (the stem's im2col row holds 9 * channels <= 64 columns)")
         if cfg.init_channels % 64:
             raise ValueError("init_channels must be a multiple of 64 for the tcgen05 conv path")
         ds = 2 ** cfg.num_down_samples
@@ -230,7 +233,8 @@ class UNetEngine:
         plist = []
         for L in self.layers:
             if L.kind in ("stem", "conv"):
-                plist.append(Param(f"{L.scope}/weights", (3, 3, L.cin, L.cout)))
+                plist.append(Param(f"{L.scope}/weights", (3, 3, L.cin, L.cout),
+                                   alloc=64 * L.cout if L.kind == "stem" else 0))
                 plist.append(Param(f"{L.scope}/{ns}/gamma", (L.cout,), region="B"))
                 plist.append(Param(f"{L.scope}/{ns}/beta", (L.cout,), region="B"))
                 if cfg.normalizer == "batch_norm":
@@ -248,7 +252,7 @@ class UNetEngine:
                 if p.region == region:
                     p.size = int(np.prod(p.shape))
                     p.offset = off
-                    off += _align(p.size)
+                    off += _align(max(p.size, p.alloc))
             if region == "A":
                 self.n_reg = off
         self.n_train = off
@@ -309,6 +313,7 @@ class UNetEngine:
                 L.x = prev_a
         self.cat = cat
         self.images = self._alloc(n * cfg.height * cfg.width * cfg.channel * F32)
+        self.stem_col = View(self._alloc(n * cfg.height * cfg.width * 64 * BF16), n, cfg.height, cfg.width, 64)
         self.labels = self._alloc(n * cfg.height * cfg.width * 4)
         npx = n * cfg.height * cfg.width
         self.logits = self._alloc(npx * cfg.num_classes * F32)
@@ -329,7 +334,10 @@ class UNetEngine:
             self.dcat = {i: View(self._alloc(v.pixels * v.c * BF16), n, v.h, v.w, v.c) for i, v in cat.items()}
             ws = 0
             for L in self.layers:
-                if L.kind == "conv":
+                if L.kind == "stem":
+                    d = _lib.Conv2dDesc(n, L.h, L.w, 64, L.cout, 1, 1, 64, L.cout)
+                    ws = max(ws, self.ctx.lib.bsl_conv2d_wgrad_workspace(self.ctx.h, C.byref(d)))
+                elif L.kind == "conv":
                     d = self._conv_desc(L)
                     ws = max(ws, self.ctx.lib.bsl_conv2d_wgrad_workspace(self.ctx.h, C.byref(d)))
                 elif L.kind == "convT":
@@ -350,7 +358,7 @@ class UNetEngine:
         """Algorithmic fwd / bwd FLOPs of one training step (bwd = dgrad + wgrad, no dgrad for the stem)."""
         fwd = sum(self._flops(L) for L in self.layers)
         bwd = sum(self._flops(L) * (1 if L.kind == "stem" else 2) for L in self.layers)
-        tc = sum(self._flops(L) * 3 for L in self.layers if L.kind in ("conv", "convT"))
+        tc = sum(self._flops(L) * (2 if L.kind == "stem" else 3) for L in self.layers if L.kind != "logits")
         return {"fwd": fwd, "bwd": bwd, "total": fwd + bwd, "tensor_core": tc}
 
     # ------------------------------------------------------------------ descriptors
@@ -463,8 +471,11 @@ class UNetEngine:
             if L.kind in ("stem", "conv"):
                 d = self._conv_desc(L)
                 if L.kind == "stem":
-                    call("bsl_conv2d_stem_fprop", C.byref(d), self.images.p, self._pp(self.W, f"{L.scope}/weights"),
-                         L.y.p, s)
+                    # im2col (27 -> 64 columns, bf16) + 1x1 conv on the tensor cores
+                    call("bsl_stem_im2col", C.byref(d), self.images.p, self.stem_col.p, s)
+                    d1 = _lib.Conv2dDesc(self.cfg.batch, L.h, L.w, 64, L.cout, 1, 1, 64, L.y.ld)
+                    self._tc("fprop", self._flops(L), "bsl_conv2d_fprop", C.byref(d1), self.stem_col.p,
+                             self._pp(self.Wbf, f"{L.scope}/weights", BF16), L.y.p, s)
                 else:
                     self._tc("fprop", self._flops(L), "bsl_conv2d_fprop", C.byref(d), L.x.p,
                              self._pp(self.Wbf, f"{L.scope}/weights", BF16), L.y.p, s)
@@ -544,7 +555,9 @@ class UNetEngine:
                 d.y_ld = L.cout
                 gw = self._pp(self.G, f"{L.scope}/weights")
                 if L.kind == "stem":
-                    call("bsl_conv2d_stem_wgrad", C.byref(d), self.images.p, oth.p, gw, s)
+                    d1 = _lib.Conv2dDesc(n, L.h, L.w, 64, L.cout, 1, 1, 64, L.cout)
+                    self._tc("wgrad", self._flops(L), "bsl_conv2d_wgrad", C.byref(d1), self.stem_col.p, oth.p, gw,
+                             self.wgrad_ws.p, C.c_size_t(self.wgrad_ws_bytes), s)
                 else:
                     self._tc("wgrad", self._flops(L), "bsl_conv2d_wgrad", C.byref(d), L.x.p, oth.p, gw,
                              self.wgrad_ws.p, C.c_size_t(self.wgrad_ws_bytes), s)

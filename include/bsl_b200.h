@@ -131,6 +131,10 @@ int bsl_convT2d_bwd_filter(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* 
  *         x fp32 [n,h,w,cin], w fp32 HWIO, y bf16 (pre-norm), dw fp32. No dgrad (inputs have none).
  * Logits: slim.conv2d(x, num_classes, 1, activation_fn=None) + bias -- NetworksV2/UNet.py:100;
  *         x bf16, w fp32 [cin][classes], logits / dlogits fp32 [n,h,w,classes] dense. */
+/* col[n,h,w,64] (bf16) = im2col of the fp32 images: column t*cin+ci holds tap t, channel ci; columns
+ * >= kh*kw*cin are zero. The stem then runs as bsl_conv2d_fprop / bsl_conv2d_wgrad with k = 1,
+ * cin = 64 on the tensor cores (filter rows >= kh*kw*cin are zero padding). */
+int bsl_stem_im2col(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x_f32, void* col_bf16, void* stream);
 int bsl_conv2d_stem_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x_f32, const float* w_hwio_f32,
                           void* y_bf16, void* stream);
 int bsl_conv2d_stem_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x_f32, const void* dy_bf16,

@@ -109,11 +109,13 @@ def test_full_size_adjoint_identity(ctx):
     npx = n * h * w
     # low-rank random fields keep host generation cheap: x[p, c] = a[p] * b[c] (exactly bf16 products are not
     # needed; the identity holds for whatever bits are uploaded)
-    x = bf16_randn(rng, (npx, 1)) * bf16_randn(rng, (1, cin))
-    dy = bf16_randn(rng, (npx, 1)) * bf16_randn(rng, (1, cout))
+    # All fields are non-negative so the three inner products accumulate coherently: with random signs the sums
+    # are residuals of cancelling terms and the bf16 output rounding (2^-9 per element) alone moves them by ~1e-3.
+    x = np.abs(bf16_randn(rng, (npx, 1))) * np.abs(bf16_randn(rng, (1, cin)))
+    dy = np.abs(bf16_randn(rng, (npx, 1))) * np.abs(bf16_randn(rng, (1, cout)))
     from boxsegliver_b200.device import round_bf16
     x, dy = round_bf16(x), round_bf16(dy)
-    wt = bf16_randn(rng, (3, 3, cin, cout), 0.05)
+    wt = np.abs(bf16_randn(rng, (3, 3, cin, cout), 0.05))
     dx_, ddy, dw_ = ctx.bf16_from_f32(x), ctx.bf16_from_f32(dy), ctx.bf16_from_f32(wt)
     yo, dxo = ctx.alloc(npx * cout * 2), ctx.alloc(npx * cin * 2)
     desc = _lib.Conv2dDesc(n, h, w, cin, cout, 3, 3, cin, cout)
@@ -132,7 +134,7 @@ def test_full_size_adjoint_identity(ctx):
     dwg = dwo.download(np.float32, (3, 3, cin, cout)).astype(np.float64)
     c = float((dwg * wt).sum())
     scale = max(abs(a), abs(b), abs(c), 1e-30)
-    assert abs(a - c) / scale < 2e-3 and abs(b - c) / scale < 2e-3, (a, b, c)
+    assert abs(a - c) / scale < 5e-4 and abs(b - c) / scale < 5e-4, (a, b, c)
     for buf in (dx_, ddy, dw_, yo, dxo, ws, dwo):
         buf.free()
 

@@ -60,7 +60,7 @@ def test_train_step_parity(ctx, n, hw, normalizer, loss_type, wtype):
     eng.close()
 
     # forward: free-running oracle with bf16 storage emulation
-    tape = R.forward(params, images, rcfg, True, rnd=round_bf16)
+    tape = R.forward(params, round_bf16(images), rcfg, True, rnd=round_bf16, stem_fp32=False)
     loss_o, _ = R.loss_and_dlogits(tape, labels, rcfg)
     assert rel(logits, tape.logits) < 1.5e-2
     assert abs(data_loss - float(loss_o)) < 1e-3 * abs(float(loss_o))
@@ -70,7 +70,7 @@ def test_train_step_parity(ctx, n, hw, normalizer, loss_type, wtype):
             assert rel(new_w[name], v) < 1e-2, name
 
     # backward: oracle over the device's stored forward tape
-    tft = R.tape_from_stored(params, images, stored, logits, rcfg, wrnd=round_bf16)
+    tft = R.tape_from_stored(params, round_bf16(images), stored, logits, rcfg, wrnd=round_bf16)
     _, dl = R.loss_and_dlogits(tft, labels, rcfg)
     assert rel(dlogits, dl) < 1e-5
     g_ref = R.backward(tft, dl, rcfg, rnd=round_bf16)
@@ -120,7 +120,7 @@ def test_eval_mode_uses_moving_statistics(ctx):
     logits = eng.logits.download(np.float32, (n, hw, hw, 3))
     after = eng.get_weights()
     eng.close()
-    tape = R.forward(params, images, rcfg, False, rnd=round_bf16)
+    tape = R.forward(params, round_bf16(images), rcfg, False, rnd=round_bf16, stem_fp32=False)
     assert rel(logits, tape.logits) < 1.5e-2
     for name in params:
         assert np.array_equal(after[name], params[name]), f"{name} changed in eval mode"

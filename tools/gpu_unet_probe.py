@@ -56,7 +56,7 @@ def parity_case(ctx, n, hw, normalizer, loss_type="xentropy", wtype="numerical",
     out = {"case": f"n={n} hw={hw} {normalizer} {loss_type}/{wtype}"}
     # ---- oracle with bf16 storage emulation (isolates implementation errors)
     p32 = {k: v.copy() for k, v in params.items()}
-    tape = R.forward(p32, images, rcfg, True, rnd=round_bf16)
+    tape = R.forward(p32, round_bf16(images), rcfg, True, rnd=round_bf16, stem_fp32=False)
     loss_o, dl = R.loss_and_dlogits(tape, labels, rcfg)
     g_o = R.backward(tape, dl, rcfg, rnd=round_bf16)
     out["logits_rel_emul"] = rel(logits, tape.logits)
@@ -72,7 +72,7 @@ def parity_case(ctx, n, hw, normalizer, loss_type="xentropy", wtype="numerical",
     out["grad_rel_freerun_emul_worst"] = worst
     out["grad_rel_freerun_emul_median"] = float(np.median(list(gr.values())))
     # ---- backward on identical forward tensors: oracle backward over the DEVICE's stored tape
-    tf_tape = R.tape_from_stored(p32, images, stored, logits, rcfg, wrnd=round_bf16)
+    tf_tape = R.tape_from_stored(p32, round_bf16(images), stored, logits, rcfg, wrnd=round_bf16)
     loss_tf, dl_tf = R.loss_and_dlogits(tf_tape, labels, rcfg)
     out["dlogits_rel"] = rel(dlogits_dev, dl_tf)
     g_tf = R.backward(tf_tape, dl_tf, rcfg, rnd=round_bf16)
@@ -80,7 +80,7 @@ def parity_case(ctx, n, hw, normalizer, loss_type="xentropy", wtype="numerical",
     worst = max(gr.items(), key=lambda t: t[1])
     out["grad_rel_worst"] = worst
     out["grad_rel_median"] = float(np.median(list(gr.values())))
-    t64s = R.tape_from_stored(p64s, images.astype(np.float64), stored, logits, rcfg, wrnd=round_bf16)
+    t64s = R.tape_from_stored(p64s, round_bf16(images).astype(np.float64), stored, logits, rcfg, wrnd=round_bf16)
     _, dl64s = R.loss_and_dlogits(t64s, labels, rcfg)
     g64s = R.backward(t64s, dl64s, rcfg)
     gr64 = {k: rel(grads[k], g) for k, g in g64s.items()}
