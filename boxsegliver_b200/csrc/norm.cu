@@ -10,21 +10,36 @@
 using namespace bsl;
 
 namespace bsl {
-// Block = 32 consecutive outputs x 4 partial lanes (128 threads): lane q sums partials q, q+4, ...
-// (coalesced across outputs), then the 4 lane sums are added in a fixed order.
+// Block = 32 consecutive outputs x 8 partial lanes (256 threads): lane q sums partials q, q+8, ...
+// (coalesced across outputs, 4 independent loads in flight), then the 8 lane sums are added in a
+// fixed order.
 __global__ void pixel_reduce_final_kernel(const float* __restrict__ part, int blocks, int kc,
                                           double* __restrict__ out) {
-  __shared__ double sm[4][32];
+  __shared__ double sm[8][32];
   const int il = threadIdx.x & 31, q = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + il;
   double s = 0.0;
   if (i < kc) {
     const float* p = part + (long long)blockIdx.y * blocks * kc + i;
-    for (int b = q; b < blocks; b += 4) s += (double)p[(long long)b * kc];
+    int b = q;
+    for (; b + 24 < blocks; b += 32) {
+      const float v0 = p[(long long)b * kc], v1 = p[(long long)(b + 8) * kc], v2 = p[(long long)(b + 16) * kc],
+                  v3 = p[(long long)(b + 24) * kc];
+      s += (double)v0;
+      s += (double)v1;
+      s += (double)v2;
+      s += (double)v3;
+    }
+    for (; b < blocks; b += 8) s += (double)p[(long long)b * kc];
   }
   sm[q][il] = s;
   __syncthreads();
-  if (q == 0 && i < kc) out[(long long)blockIdx.y * kc + i] = ((sm[0][il] + sm[1][il]) + sm[2][il]) + sm[3][il];
+  if (q == 0 && i < kc) {
+    double t = sm[0][il];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += sm[k][il];
+    out[(long long)blockIdx.y * kc + i] = t;
+  }
 }
 
 static float* g_scratch = nullptr;

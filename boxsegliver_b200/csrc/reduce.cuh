@@ -106,7 +106,7 @@ inline ReducePlan plan_reduce(bsl_ctx* ctx, long long pixels_per_group, int grou
   while ((size_t)p.rows * K * c * 4 > 48 * 1024 && p.rows > 1) p.rows /= 2;
   p.threads = p.rows * cg;
   long long want = (pixels_per_group + 511) / 512;
-  long long cap = (8LL * ctx->sm_count + groups - 1) / groups;
+  long long cap = (4LL * ctx->sm_count + groups - 1) / groups;
   if (cap < 1) cap = 1;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
@@ -131,7 +131,7 @@ int run_pixel_reduce(bsl_ctx* ctx, const F& f, long long pixels_per_group, int g
                                                                                           p.ppb, c, part);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_kernel");
   const int kc = F::K * c;
-  pixel_reduce_final_kernel<<<dim3((kc + 127) / 128, groups), 128, 0, stream>>>(part, p.blocks, kc, out);
+  pixel_reduce_final_kernel<<<dim3((kc + 31) / 32, groups), 256, 0, stream>>>(part, p.blocks, kc, out);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel");
   return BSL_OK;
 }

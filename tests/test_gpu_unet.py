@@ -109,7 +109,7 @@ def test_eval_mode_uses_moving_statistics(ctx):
         if name.endswith("moving_mean"):
             params[name] = rng.normal(0, 0.05, params[name].shape).astype(np.float32)
         if name.endswith("moving_variance"):
-            params[name] = rng.uniform(0.05, 0.15, params[name].shape).astype(np.float32)
+            params[name] = rng.uniform(0.5, 1.5, params[name].shape).astype(np.float32)
     images, labels = synthetic.make_batch(n, hw, hw, 3, seed=5)
     eng = UNetEngine(ctx, ecfg)
     eng.set_weights(params)
