@@ -86,16 +86,47 @@ class Context:
             raise BslError(rc, "bsl_init failed (is an sm_100 GPU visible?)")
         self.h = h
         self.device = device
+        self.tag = ""            # label attached to profiled calls (the engine sets it per layer)
+        self._prof = None
         s = C.c_void_p()
         self.call("bsl_stream_create", C.byref(s))
         self.stream = s
 
     # -- plumbing
+    _NO_PROF = ("bsl_malloc", "bsl_free", "bsl_stream_", "bsl_event_", "bsl_host_", "bsl_device_status",
+                "bsl_launch_count", "bsl_graph_", "bsl_comm_", "bsl_debug_set")
+
     def call(self, name: str, *args) -> int:
+        prof = self._prof is not None and not name.startswith(self._NO_PROF)
+        if prof:
+            e0, e1 = self._prof_event(), self._prof_event()
+            self.lib.bsl_event_record(self.h, e0, self.stream)
         rc = getattr(self.lib, name)(self.h, *args)
         if rc != 0:
             raise BslError(rc, (self.lib.bsl_last_error(self.h) or b"").decode())
+        if prof:
+            self.lib.bsl_event_record(self.h, e1, self.stream)
+            self._prof.append((name, self.tag, e0, e1))
         return rc
+
+    # -- per-call device timing (tools/step_breakdown.py): brackets every enqueue on the compute stream
+    def _prof_event(self):
+        if self._prof_next == len(self._prof_pool):
+            self._prof_pool.append(self.new_event())
+        e = self._prof_pool[self._prof_next]
+        self._prof_next += 1
+        return e
+
+    def profile_begin(self):
+        self._prof_pool = getattr(self, "_prof_pool", [])
+        self._prof_next = 0
+        self._prof = []
+
+    def profile_end(self):
+        """[(function, tag, ms)] for every call since profile_begin, in enqueue order."""
+        rec, self._prof = self._prof, None
+        self.sync()
+        return [(n, t, self.elapsed_ms(a, b)) for n, t, a, b in rec]
 
     def stream_arg(self, stream=None) -> C.c_void_p:
         return self.stream if stream is None else stream

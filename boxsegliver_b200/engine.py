@@ -468,6 +468,7 @@ class UNetEngine:
         ctx, s = self.ctx, self.stream
         call = ctx.call
         for L in self.layers:
+            ctx.tag = L.scope
             if L.kind in ("stem", "conv"):
                 d = self._conv_desc(L)
                 if L.kind == "stem":
@@ -527,6 +528,7 @@ class UNetEngine:
         ns = self.norm_scope
         for idx in range(len(self.layers) - 1, -1, -1):
             L = self.layers[idx]
+            ctx.tag = L.scope
             if L.kind == "logits":
                 d = self._conv_desc(L)
                 call("bsl_conv2d_head_wgrad", C.byref(d), L.x.p, self.dlogits.p, self._pp(self.G, f"{L.scope}/weights"),

@@ -236,6 +236,65 @@ def tape_from_stored(params: dict, images: np.ndarray, stored: dict, logits: np.
     return tape
 
 
+def layerwise_forward_errors(params: dict, images: np.ndarray, stored: dict, logits: np.ndarray, cfg: UNetCfg,
+                             is_training: bool, wrnd=_identity) -> dict:
+    """Op-by-op forward parity on identical inputs: every layer of UNet._build_network is evaluated by the
+    oracle on the INPUT TENSOR THE OTHER IMPLEMENTATION STORED, and its result is compared with what that
+    implementation stored as the output. Returns {"<scope>:y" | "<scope>:a" | "logits": relative L2 error}.
+    (A free-running comparison of the final logits measures the chaos of 23 stacked bf16 roundings, not the
+    kernels; this is the per-op statement the bf16 tolerance of 1e-2 applies to.)"""
+    ns = norm_scope(cfg)
+    dt = np.float64
+    errs = {}
+
+    def rel(a, b):
+        a, b = np.asarray(a, dt), np.asarray(b, dt)
+        return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+    def block(x, scope, first=False):
+        w = params[f"{scope}/weights"].astype(dt)
+        w = w if first else wrnd(w).astype(dt)
+        y_ref = O.conv2d(x.astype(dt), w)
+        y = stored[scope]["y"].astype(dt)
+        errs[f"{scope}:y"] = rel(y, y_ref)
+        g, b = params[f"{scope}/{ns}/gamma"].astype(dt), params[f"{scope}/{ns}/beta"].astype(dt)
+        if cfg.normalizer == "batch_norm":
+            mm, mv = params[f"{scope}/{ns}/moving_mean"].astype(dt), params[f"{scope}/{ns}/moving_variance"].astype(dt)
+            if is_training:
+                z = O.batch_norm_train(y, g, b, mm, mv, cfg.bn_eps, cfg.bn_decay)[0]
+            else:
+                z = O.batch_norm_infer(y, g, b, mm, mv, cfg.bn_eps)
+        else:
+            z = O.instance_norm(y, g, b, cfg.in_eps)[0]
+        a = stored[scope]["a"].astype(dt)
+        errs[f"{scope}:a"] = rel(a, O.relu(z))
+        return a
+
+    x = images.astype(dt)
+    skips = []
+    first = True
+    for i in range(cfg.num_down_samples):
+        for j in (1, 2):
+            x = block(x, f"UNet/Encode{i + 1}/Repeat/convolution2d_{j}", first)
+            first = False
+        skips.append(x)
+        x = O.max_pool_2x2(x)
+    for j in (1, 2):
+        x = block(x, f"UNet/ED-Bridge/convolution2d_{j}")
+    for i in reversed(range(cfg.num_down_samples)):
+        scope = f"UNet/Decode{i + 1}/Conv2d_transpose"
+        w = wrnd(params[f"{scope}/weights"].astype(dt)).astype(dt)
+        up = stored[scope]["a"].astype(dt)
+        errs[f"{scope}:a"] = rel(up, O.relu(O.conv2d_transpose(x, w) + params[f"{scope}/biases"].astype(dt)))
+        x = np.concatenate((skips[i], up), axis=-1)
+        for j in (1, 2):
+            x = block(x, f"UNet/Decode{i + 1}/Repeat/convolution2d_{j}")
+    scope = "UNet/AdjustChannels"
+    ref = O.conv2d(x, params[f"{scope}/weights"].astype(dt)) + params[f"{scope}/biases"].astype(dt)
+    errs["logits"] = rel(logits, ref)
+    return errs
+
+
 def loss_and_dlogits(tape: Tape, labels: np.ndarray, cfg: UNetCfg, loss_scale: float = 1.0):
     """UNet._build_loss (data term only). Returns (loss, dlogits * loss_scale)."""
     kw = {}

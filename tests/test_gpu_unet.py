@@ -69,6 +69,10 @@ def test_train_step_parity(ctx, n, hw, normalizer, loss_type, wtype):
         for name, v in tape.new_moving.items():
             assert rel(new_w[name], v) < 1e-2, name
 
+    # forward, op by op on identical inputs (fp64 oracle op vs the stored device output): the 1e-2 bf16 gate
+    lw = R.layerwise_forward_errors(params, round_bf16(images), stored, logits, rcfg, True, wrnd=round_bf16)
+    assert max(lw.values()) < 1e-2, max(lw.items(), key=lambda t: t[1])
+
     # backward: oracle over the device's stored forward tape
     tft = R.tape_from_stored(params, round_bf16(images), stored, logits, rcfg, wrnd=round_bf16)
     _, dl = R.loss_and_dlogits(tft, labels, rcfg)
@@ -119,9 +123,12 @@ def test_eval_mode_uses_moving_statistics(ctx):
     ctx.check_device()
     logits = eng.logits.download(np.float32, (n, hw, hw, 3))
     after = eng.get_weights()
+    stored = eng.get_stored_forward()
     eng.close()
     tape = R.forward(params, round_bf16(images), rcfg, False, rnd=round_bf16, stem_fp32=False)
     assert rel(logits, tape.logits) < 1.5e-2
+    lw = R.layerwise_forward_errors(params, round_bf16(images), stored, logits, rcfg, False, wrnd=round_bf16)
+    assert max(lw.values()) < 1e-2, max(lw.items(), key=lambda t: t[1])
     for name in params:
         assert np.array_equal(after[name], params[name]), f"{name} changed in eval mode"
 
