@@ -3,8 +3,11 @@
 //   conv2d fprop / dgrad / wgrad  <- slim.conv2d, NetworksV2/UNet.py:79,85,94 (+ tf.gradients)
 //   convT2d fwd / bwd             <- slim.conv2d_transpose, NetworksV2/UNet.py:91
 #include <algorithm>
+#include <cstdlib>
 #include "igemm.cuh"
+#include "igemm_halo.cuh"
 #include "internal.h"
+#include "reduce.cuh"
 
 using namespace bsl;
 
@@ -165,6 +168,90 @@ int reduce_splits(bsl_ctx* ctx, const float* part, float* out, long long n, int 
   return BSL_OK;
 }
 
+
+// ------------------------------------------------------------------ second-generation (halo-tile) kernels
+// BSL_IGEMM_V1=1 forces the first-generation kernels everywhere (A/B timing, bisecting).
+bool force_v1() {
+  static const int v = [] {
+    const char* e = getenv("BSL_IGEMM_V1");
+    return e ? atoi(e) : 0;
+  }();
+  return v != 0;
+}
+
+template <int BN, int NSUB, bool B_MN, bool STATS>
+int launch_halo_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args, int grid,
+                    cudaStream_t stream) {
+  auto kern = conv_halo_kernel<BN, NSUB, B_MN, STATS>;
+  constexpr int smem = ConvHaloCfg<BN, NSUB>::SMEM_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    BSL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  kern<<<grid, CH_THREADS, smem, stream>>>(a, b, args);
+  BSL_LAUNCH_CHECK(ctx, "conv_halo_kernel launch");
+  return BSL_OK;
+}
+
+template <bool B_MN, bool STATS>
+int launch_halo(bsl_ctx* ctx, int bn, int nsub, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args,
+                int grid, cudaStream_t stream) {
+  if (bn == 64 && nsub == 2) return launch_halo_one<64, 2, B_MN, STATS>(ctx, a, b, args, grid, stream);
+  if (bn == 64 && nsub == 1) return launch_halo_one<64, 1, B_MN, STATS>(ctx, a, b, args, grid, stream);
+  if (bn == 128 && nsub == 2) return launch_halo_one<128, 2, B_MN, STATS>(ctx, a, b, args, grid, stream);
+  if (bn == 128 && nsub == 1) return launch_halo_one<128, 1, B_MN, STATS>(ctx, a, b, args, grid, stream);
+  return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv_halo: tile %d x %d", bn, nsub);
+}
+
+struct HaloPlan {
+  int bn, nsub, n_ntiles, n_sub_total, n_units, grid, slots;
+};
+
+// Pixel sub-tiles are 8 (w) x 16 (h); `ncols` is the GEMM N extent (a multiple of 64).
+bool halo_eligible(int w, int h) { return !force_v1() && w % 8 == 0 && h % 16 == 0; }
+
+HaloPlan plan_halo(bsl_ctx* ctx, int w, int h, int n, int ncols) {
+  HaloPlan p;
+  p.n_sub_total = (w / 8) * (h / 16) * n;
+  p.bn = ncols % 128 == 0 ? 128 : 64;
+  p.nsub = p.n_sub_total % 2 == 0 ? 2 : 1;
+  p.n_ntiles = ncols / p.bn;
+  p.n_units = cdiv(p.n_sub_total, p.nsub) * p.n_ntiles;
+  int g = std::min(p.n_units, ctx->sm_count);
+  if (g >= p.n_ntiles) g -= g % p.n_ntiles;  // a CTA then always owns the same column tile (statistics)
+  p.grid = std::max(g, 1);
+  p.slots = cdiv(p.grid, p.n_ntiles);
+  return p;
+}
+
+void halo_common(ConvHaloArgs& a, const HaloPlan& p, int w, int h, int n) {
+  a.ntile_w = w / 8;
+  a.ntile_h = h / 16;
+  a.n = n;
+  a.n_sub_total = p.n_sub_total;
+  a.n_units = p.n_units;
+  a.n_ntiles = p.n_ntiles;
+}
+
+struct WgradPlan {
+  int k_tiles, per, splits;
+};
+
+bool wgrad_halo_eligible(const bsl_conv2d_desc* d) {
+  return !force_v1() && d->kh == 3 && d->kw == 3 && d->w % WG_TW == 0 && d->h % WG_TH == 0;
+}
+
+WgradPlan plan_wgrad_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
+  WgradPlan p;
+  p.k_tiles = (d->w / WG_TW) * (d->h / WG_TH) * d->n;
+  const int mn = (d->cin / 64) * (d->cout / 64);
+  int splits = std::max(1, ctx->sm_count / mn);
+  splits = std::max(1, std::min(splits, p.k_tiles / 4));
+  p.per = cdiv(p.k_tiles, splits);
+  p.splits = cdiv(p.k_tiles, p.per);
+  return p;
+}
 }  // namespace
 
 extern "C" {
@@ -178,11 +265,56 @@ int bsl_debug_set(bsl_ctx* ctx, int key, int value) {
   return bsl_fail(ctx, BSL_EINVAL, "debug_set: unknown key %d", key);
 }
 
+// fprop on the halo-tile kernel; `sums` (fp64 [2][cout], nullable) receives the per-channel sum and
+// sum of squares of the bf16 outputs, reduced deterministically from per-CTA partials.
+static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
+                             double* sums, cudaStream_t stream) {
+  const int halo = d->kh == 3 ? 1 : 0;
+  const HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, d->cout);
+  const int box[4] = {8 + 2 * halo, 16 + 2 * halo, 1, 1};
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, box, &ta))) return rc;
+  if ((rc = matrix_map(ctx, w, d->cout, d->kh * d->kw * d->cin, 64, 64, &tb))) return rc;
+  ConvHaloArgs a = {};
+  halo_common(a, pl, d->w, d->h, d->n);
+  a.ntaps = d->kh * d->kw;
+  a.halo = halo;
+  a.cblocks = d->cin / 64;
+  a.out = y;
+  a.ostride_x = d->y_ld;
+  a.ostride_y = (long long)d->w * d->y_ld;
+  a.ostride_n = (long long)d->h * d->w * d->y_ld;
+  a.n_group = d->cout;
+  a.n_total = d->cout;
+  a.status = ctx->d_status;
+  if (!sums) return launch_halo<true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+  float* part = nullptr;
+  if ((rc = bsl_scratch(ctx, (size_t)pl.slots * 2 * d->cout * sizeof(float), &part))) return rc;
+  a.stats_part = part;
+  if ((rc = launch_halo<true, true>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream))) return rc;
+  const int kc = 2 * d->cout;
+  pixel_reduce_final_kernel<<<dim3((kc + 31) / 32, 1), 256, 0, stream>>>(part, pl.slots, kc, sums);
+  BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel (conv statistics)");
+  return BSL_OK;
+}
+
+int bsl_conv2d_fprop_stats(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
+                           double* sums, void* stream) {
+  int rc = check_conv(ctx, d);
+  if (rc) return rc;
+  if (!x || !w || !y || !sums) return bsl_fail(ctx, BSL_EINVAL, "conv2d_fprop_stats: null buffer");
+  if (halo_eligible(d->w, d->h)) return conv2d_fprop_halo(ctx, d, x, w, y, sums, as_stream(stream));
+  if ((rc = bsl_conv2d_fprop(ctx, d, x, w, y, stream))) return rc;
+  return bsl_stats_bf16(ctx, y, (long long)d->n * d->h * d->w, 1, d->cout, d->y_ld, sums, as_stream(stream));
+}
+
 int bsl_conv2d_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
                      void* stream) {
   int rc = check_conv(ctx, d);
   if (rc) return rc;
   if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "conv2d_fprop: null buffer");
+  if (halo_eligible(d->w, d->h)) return conv2d_fprop_halo(ctx, d, x, w, y, nullptr, as_stream(stream));
   int box[4] = {0, 0, 0, 1};
   pick_box(128, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
   const int bn = pick_bn(d->cout);
@@ -210,6 +342,29 @@ int bsl_conv2d_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, con
   int rc = check_conv(ctx, d);
   if (rc) return rc;
   if (!dy || !w || !dx) return bsl_fail(ctx, BSL_EINVAL, "conv2d_dgrad: null buffer");
+  if (halo_eligible(d->w, d->h)) {
+    const int halo = d->kh == 3 ? 1 : 0;
+    const HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, d->cin);
+    const int hbox[4] = {8 + 2 * halo, 16 + 2 * halo, 1, 1};
+    CUtensorMap ta, tb;
+    if ((rc = nhwc_map(ctx, dy, d->cout, d->w, d->h, d->n, d->y_ld, hbox, &ta))) return rc;
+    if ((rc = matrix_map(ctx, w, d->cout, d->kh * d->kw * d->cin, 64, pl.bn, &tb))) return rc;
+    ConvHaloArgs a = {};
+    halo_common(a, pl, d->w, d->h, d->n);
+    a.ntaps = d->kh * d->kw;
+    a.halo = halo;
+    a.cblocks = d->cout / 64;
+    a.b_flip = 1;
+    a.b_rows_per_tap = d->cin;
+    a.out = dx;
+    a.ostride_x = d->x_ld;
+    a.ostride_y = (long long)d->w * d->x_ld;
+    a.ostride_n = (long long)d->h * d->w * d->x_ld;
+    a.n_group = d->cin;
+    a.n_total = d->cin;
+    a.status = ctx->d_status;
+    return launch_halo<false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
+  }
   int box[4] = {0, 0, 0, 1};
   pick_box(128, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
   const int bn = pick_bn(d->cin);
@@ -237,6 +392,10 @@ int bsl_conv2d_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, con
 
 size_t bsl_conv2d_wgrad_workspace(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
   if (!ctx || !d || check_conv(ctx, d)) return 0;
+  if (wgrad_halo_eligible(d)) {
+    const WgradPlan p = plan_wgrad_halo(ctx, d);
+    return p.splits > 1 ? (size_t)p.splits * 9 * d->cin * d->cout * sizeof(float) : 0;
+  }
   int box[4] = {0, 0, 0, 1};
   pick_box(64, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
   const int k_tiles = cdiv(d->w, box[0]) * cdiv(d->h, box[1]) * cdiv(d->n, box[2]);
@@ -252,6 +411,39 @@ int bsl_conv2d_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, cons
   int rc = check_conv(ctx, d);
   if (rc) return rc;
   if (!x || !dy || !dw) return bsl_fail(ctx, BSL_EINVAL, "conv2d_wgrad: null buffer");
+  if (wgrad_halo_eligible(d)) {
+    const WgradPlan p = plan_wgrad_halo(ctx, d);
+    const size_t need = p.splits > 1 ? (size_t)p.splits * 9 * d->cin * d->cout * sizeof(float) : 0;
+    if (need > workspace_bytes || (need && !workspace))
+      return bsl_fail(ctx, BSL_EWORKSPACE, "conv2d_wgrad: workspace %zu < %zu", workspace_bytes, need);
+    const int xbox[4] = {WG_TW + 2, WG_TH + 2, 1, 1}, ybox[4] = {WG_TW, WG_TH, 1, 1};
+    CUtensorMap tx, ty;
+    if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, xbox, &tx))) return rc;
+    if ((rc = nhwc_map(ctx, dy, d->cout, d->w, d->h, d->n, d->y_ld, ybox, &ty))) return rc;
+    WgradHaloArgs a = {};
+    a.ntile_w = d->w / WG_TW;
+    a.ntile_h = d->h / WG_TH;
+    a.n = d->n;
+    a.k_tiles_total = p.k_tiles;
+    a.k_tiles_per_split = p.per;
+    a.cin = d->cin;
+    a.cout = d->cout;
+    a.out = p.splits > 1 ? reinterpret_cast<float*>(workspace) : dw;
+    a.status = ctx->d_status;
+    static bool configured = false;
+    if (!configured) {
+      BSL_CUDA(ctx, cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         WG_SMEM_BYTES));
+      configured = true;
+    }
+    wgrad_halo_kernel<<<dim3(d->cin / 64, d->cout / 64, p.splits), WG_THREADS, WG_SMEM_BYTES, as_stream(stream)>>>(
+        tx, ty, a);
+    BSL_LAUNCH_CHECK(ctx, "wgrad_halo_kernel launch");
+    if (p.splits > 1)
+      return reduce_splits(ctx, reinterpret_cast<const float*>(workspace), dw, (long long)9 * d->cin * d->cout,
+                           p.splits, as_stream(stream));
+    return BSL_OK;
+  }
   int box[4] = {0, 0, 0, 1};
   pick_box(64, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
   const int taps = d->kh * d->kw;
@@ -303,6 +495,32 @@ int bsl_convT2d_fwd(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, cons
   int rc = check_convT(ctx, d);
   if (rc) return rc;
   if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "convT2d_fwd: null buffer");
+  if (halo_eligible(d->w, d->h)) {
+    const HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, 4 * d->cout);
+    const int hbox[4] = {8, 16, 1, 1};
+    CUtensorMap ta, tb;
+    if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, hbox, &ta))) return rc;
+    if ((rc = matrix_map(ctx, w, d->cin, 4 * d->cout, 64, pl.bn, &tb))) return rc;
+    ConvHaloArgs a = {};
+    halo_common(a, pl, d->w, d->h, d->n);
+    a.ntaps = 1;
+    a.halo = 0;
+    a.cblocks = d->cin / 64;
+    a.b_rows_per_tap = 0;
+    a.out = y;
+    const long long row = (long long)2 * d->w * d->y_ld;
+    a.ostride_x = 2 * d->y_ld;
+    a.ostride_y = 2 * row;
+    a.ostride_n = (long long)2 * d->h * row;
+    a.n_group = d->cout;
+    for (int ta_ = 0; ta_ < 2; ++ta_)
+      for (int tb_ = 0; tb_ < 2; ++tb_) a.group_off[ta_ * 2 + tb_] = ta_ * row + (long long)tb_ * d->y_ld;
+    a.bias = bias;
+    a.relu = d->relu;
+    a.n_total = 4 * d->cout;
+    a.status = ctx->d_status;
+    return launch_halo<false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
+  }
   int box[4] = {0, 0, 0, 1};
   pick_box(128, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
   const int bn = pick_bn(d->cout);

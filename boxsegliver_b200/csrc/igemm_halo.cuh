@@ -1,0 +1,493 @@
+// Halo-tile implicit GEMM for 3x3 / stride-1 / SAME convolutions on sm_100a (tcgen05 + TMEM + TMA).
+//
+// Measured on B200 (tools/umma_probe.cu, profiles/r01_umma_shifted_descriptor_probe.log): a SWIZZLE_128B
+// UMMA shared-memory descriptor may start at any 128-byte aligned address, with any 128-byte multiple
+// as the stride between 8-row groups / 64-element blocks, because the swizzle is a function of the
+// absolute shared-memory address on both sides (TMA writes, UMMA reads). So the 9 filter taps need not
+// be 9 TMA loads of shifted pixel boxes: ONE box with a 1-pixel halo is loaded per 64-channel block and
+// tap (r, s) is the same tile read through a descriptor whose start address is moved by
+// (r * pitch + s) pixels. That cuts the L2 -> shared-memory traffic of the activation operand ~6x, which
+// is what bounded the first-generation kernel (igemm.cuh) on the 64/128-channel layers.
+//
+//   conv_halo_kernel   fprop / dgrad (and 1x1 / transposed-conv forward as the 1-tap case): persistent CTAs,
+//                      static tile schedule, TMEM double-buffered accumulators so the epilogue of tile i
+//                      overlaps the MMAs of tile i+1, optional per-channel sum / sum-of-squares of the
+//                      bf16-rounded outputs (batch-norm statistics, NetworksV2/base.py:154-162) fused into
+//                      the epilogue.   Reference ops: slim.conv2d, NetworksV2/UNet.py:79,85,94.
+//   wgrad_halo_kernel  filter gradient: one CTA owns (64 input channels) x (64 output channels) x ALL 9 taps
+//                      for a range of pixel tiles; 5 TMEM accumulators hold tap pairs (M = 2 x 64 channels).
+//                      Reference op: Conv2DBackpropFilter created by optimizer.minimize, core/solver.py:239.
+#pragma once
+#include "ptx.cuh"
+#include <cuda_bf16.h>
+
+namespace bsl {
+
+// ------------------------------------------------------------------------------------------------ wgrad
+struct WgradHaloArgs {
+  int ntile_w, ntile_h, n;       // pixel tiles of 16 (w) x 4 (h)
+  int k_tiles_total;
+  int k_tiles_per_split;
+  int cin, cout;                 // padded-to-64 extents of dW
+  float* out;                    // [split][9][cin][cout] fp32 (or dW itself when splits == 1)
+  DeviceStatus* status;
+};
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_TW = 16, WG_TH = 4;
+constexpr int WG_PITCH = WG_TW + 2;                     // halo tile row pitch in pixels
+constexpr int WG_X_ROWS = WG_PITCH * (WG_TH + 2);       // 108 pixels of 128 B
+constexpr int WG_X_BYTES = 14336;                       // 108 * 128 = 13824, padded to 1024
+constexpr int WG_DY_BYTES = WG_TW * WG_TH * 128;        // 8192
+constexpr int WG_STAGE_BYTES = WG_X_BYTES + WG_DY_BYTES;
+constexpr int WG_STAGES = 8;
+constexpr int WG_SMEM_BYTES = WG_STAGES * WG_STAGE_BYTES + 1024;
+
+// grid = (cin / 64, cout / 64, splits)
+__global__ void __launch_bounds__(WG_THREADS)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                  const WgradHaloArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * WG_STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int dead;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t full0 = smem_u32(&bars[0]);
+  const uint32_t empty0 = smem_u32(&bars[WG_STAGES]);
+  const uint32_t tfull = smem_u32(&bars[2 * WG_STAGES]);
+  DeviceStatus* st = p.status;
+
+  if (threadIdx.x == 0) dead = *reinterpret_cast<volatile int*>(&st->error);
+  __syncthreads();
+  if (dead) return;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmX);
+    prefetch_tensormap(&tmDY);
+    for (int s = 0; s < WG_STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc<512>(smem_u32(&tmem_slot));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+
+  const int cb = blockIdx.x, nb = blockIdx.y;
+  const int k_begin = blockIdx.z * p.k_tiles_per_split;
+  const int k_end = min(p.k_tiles_total, k_begin + p.k_tiles_per_split);
+  const int num_k = k_end - k_begin;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kk = 0; kk < num_k; ++kk) {
+        if (!mbar_wait(empty0 + 8 * stage, phase ^ 1, st, 11)) break;
+        int t = k_begin + kk;
+        const int tx = t % p.ntile_w;
+        t /= p.ntile_w;
+        const int ty = t % p.ntile_h;
+        const int img = t / p.ntile_h;
+        const uint32_t fb = full0 + 8 * stage;
+        const uint32_t sx = smem_base + stage * WG_STAGE_BYTES;
+        mbar_arrive_expect_tx(fb, WG_X_ROWS * 128 + WG_DY_BYTES);
+        tma_load_5d(sx, &tmX, fb, cb * 64, tx * WG_TW - 1, ty * WG_TH - 1, img, 0);
+        tma_load_5d(sx + WG_X_BYTES, &tmDY, fb, nb * 64, tx * WG_TW, ty * WG_TH, img, 0);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, true);
+      // tap pairs (0,1) (2,3) (4,5) (6,7) (8,-): start row of the first tap and distance to the second
+      // inside the halo tile, tap t = (r, s) = (t / 3, t % 3) at pixel offset r * PITCH + s.
+      int off0[5], lbo[5];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int t0 = 2 * q, t1 = (2 * q + 1 < 9) ? 2 * q + 1 : 2 * q;
+        const int o0 = (t0 / 3) * WG_PITCH + t0 % 3, o1 = (t1 / 3) * WG_PITCH + t1 % 3;
+        off0[q] = o0 * 128;
+        lbo[q] = (o1 > o0 ? o1 - o0 : 1) * 128;  // lone tap 8: second block = garbage rows, never read back
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int kk = 0; kk < num_k; ++kk) {
+        if (!mbar_wait(full0 + 8 * stage, phase, st, 12)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t sx = smem_base + stage * WG_STAGE_BYTES;
+        const uint32_t sdy = sx + WG_X_BYTES;
+#pragma unroll
+        for (int y = 0; y < WG_TH; ++y) {
+          const uint64_t db = make_smem_desc_sw128(sdy + y * (WG_TW * 128), 8192, 1024);
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            const uint64_t da = make_smem_desc_sw128(sx + off0[q] + y * (WG_PITCH * 128), lbo[q], 1024);
+            umma_bf16(tmem_base + q * 64, da, db, idesc, (kk | y) != 0);
+          }
+        }
+        umma_commit(empty0 + 8 * stage);
+        if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (ok) umma_commit(tfull);
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int r = q4 * 32 + lane;  // accumulator row: tap-in-pair = r / 64, input channel = r % 64
+    const bool alive = mbar_wait(tfull, 0, st, 13);
+    tc_fence_after();
+    if (alive) {
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+#pragma unroll 1
+      for (int q = 0; q < 5; ++q) {
+        const int tap = 2 * q + (r >> 6);
+        const bool valid = tap < 9 && !(q == 4 && r >= 64);
+        float* o = p.out + (((long long)blockIdx.z * 9 + tap) * p.cin + cb * 64 + (r & 63)) * p.cout + nb * 64;
+#pragma unroll
+        for (int c = 0; c < 64; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + q * 64 + c, v);
+          tmem_ld_wait();
+          if (valid) {
+            float4* dst = reinterpret_cast<float4*>(o + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              dst[j] = make_float4(num_k ? __uint_as_float(v[4 * j]) : 0.f, num_k ? __uint_as_float(v[4 * j + 1]) : 0.f,
+                                   num_k ? __uint_as_float(v[4 * j + 2]) : 0.f, num_k ? __uint_as_float(v[4 * j + 3]) : 0.f);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ fprop / dgrad
+struct ConvHaloArgs {
+  int ntile_w, ntile_h, n;       // sub-tiles of 8 (w) x 16 (h) pixels
+  int n_sub_total;               // ntile_w * ntile_h * n
+  int n_units;                   // ceil(n_sub_total / NSUB) * n_ntiles
+  int n_ntiles;                  // column tiles (N / BN)
+  int ntaps;                     // 9 (halo = 1) or 1 (halo = 0)
+  int halo;                      // 1: box (10 x 18), 0: box (8 x 16)
+  int cblocks;                   // 64-channel blocks of the reduction
+  int b_flip;                    // dgrad: B tap = ntaps - 1 - tap
+  int b_rows_per_tap;            // K-major B: rows per tap
+  // ---- epilogue
+  void* out;                     // bf16
+  long long ostride_x, ostride_y, ostride_n;  // element strides of the output pixel grid
+  int n_group;                   // columns per output group (== N unless transposed-conv scatter)
+  long long group_off[8];
+  const float* bias;
+  int relu;
+  int n_total;
+  float* stats_part;             // [slot][2][n_total] per-CTA partial sums (nullptr: no statistics)
+  DeviceStatus* status;
+};
+
+constexpr int CH_SUB_BYTES = 23552;   // (10 x 18) x 128 B = 23040, padded to a multiple of 1024
+constexpr int CH_A_STAGES = 2;
+
+template <int BN, int NSUB>
+struct ConvHaloCfg {
+  static constexpr int ACC_BUFS = (512 / (BN * NSUB)) >= 2 ? 2 : 1;
+  static constexpr int TMEM_COLS = BN * NSUB * ACC_BUFS;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int A_BYTES = NSUB * CH_SUB_BYTES;
+  // fill what is left of ~200 KB after the A ring with B stages (at least 3, at most 8)
+  static constexpr int B_FIT = (200 * 1024 - CH_A_STAGES * A_BYTES) / B_BYTES;
+  static constexpr int B_STAGES = B_FIT > 8 ? 8 : (B_FIT < 3 ? 3 : B_FIT);
+  static constexpr int SMEM_BYTES = CH_A_STAGES * A_BYTES + B_STAGES * B_BYTES + 1024;
+};
+
+constexpr int CH_THREADS = 224;  // warp 0: A producer, 1: MMA, 2-5: epilogue, 6: B producer
+
+template <int BN, int NSUB, bool B_MN, bool STATS>
+__global__ void __launch_bounds__(CH_THREADS)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const ConvHaloArgs p) {
+  using Cfg = ConvHaloCfg<BN, NSUB>;
+  constexpr int ACC_BUFS = Cfg::ACC_BUFS;
+  constexpr int B_STAGES = Cfg::B_STAGES;
+  constexpr int A_BYTES = Cfg::A_BYTES;
+  constexpr int B_BYTES = Cfg::B_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * CH_A_STAGES + 2 * B_STAGES + 2 * ACC_BUFS];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int dead;
+  __shared__ float s_stats[STATS ? 4 * 2 * BN : 1];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA0 = smem_base;
+  const uint32_t sB0 = smem_base + CH_A_STAGES * A_BYTES;
+  const uint32_t a_full = smem_u32(&bars[0]);
+  const uint32_t a_empty = smem_u32(&bars[CH_A_STAGES]);
+  const uint32_t b_full = smem_u32(&bars[2 * CH_A_STAGES]);
+  const uint32_t b_empty = smem_u32(&bars[2 * CH_A_STAGES + B_STAGES]);
+  const uint32_t acc_full = smem_u32(&bars[2 * CH_A_STAGES + 2 * B_STAGES]);
+  const uint32_t acc_empty = smem_u32(&bars[2 * CH_A_STAGES + 2 * B_STAGES + ACC_BUFS]);
+  DeviceStatus* st = p.status;
+
+  if (threadIdx.x == 0) dead = *reinterpret_cast<volatile int*>(&st->error);
+  if (STATS) {
+    for (int i = threadIdx.x; i < 4 * 2 * BN; i += CH_THREADS) s_stats[i] = 0.f;
+  }
+  __syncthreads();
+  if (dead) return;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+    for (int s = 0; s < CH_A_STAGES; ++s) {
+      mbar_init(a_full + 8 * s, 1);
+      mbar_init(a_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < B_STAGES; ++s) {
+      mbar_init(b_full + 8 * s, 1);
+      mbar_init(b_empty + 8 * s, 1);
+    }
+    for (int s = 0; s < ACC_BUFS; ++s) {
+      mbar_init(acc_full + 8 * s, 1);
+      mbar_init(acc_empty + 8 * s, 4);  // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc<Cfg::TMEM_COLS>(smem_u32(&tmem_slot));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+
+  const int box_w = p.halo ? 10 : 8;
+  const int sub_rows = p.halo ? 180 : 128;
+
+  if (warp == 0) {
+    // ============================== A producer: one halo'd tile per (sub-tile, 64-channel block)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int u = blockIdx.x; u < p.n_units && ok; u += gridDim.x) {
+        const int pu = u / p.n_ntiles;
+        for (int cb = 0; cb < p.cblocks && ok; ++cb) {
+          if (!mbar_wait(a_empty + 8 * stage, phase ^ 1, st, 21)) { ok = false; break; }
+          const uint32_t fb = a_full + 8 * stage;
+          int nsub = p.n_sub_total - pu * NSUB;
+          nsub = nsub > NSUB ? NSUB : nsub;
+          mbar_arrive_expect_tx(fb, nsub * sub_rows * 128);
+#pragma unroll
+          for (int j = 0; j < NSUB; ++j) {
+            if (j < nsub) {
+              int s = pu * NSUB + j;
+              const int tx = s % p.ntile_w;
+              s /= p.ntile_w;
+              const int ty = s % p.ntile_h;
+              const int img = s / p.ntile_h;
+              tma_load_5d(sA0 + stage * A_BYTES + j * CH_SUB_BYTES, &tmA, fb, cb * 64, tx * 8 - p.halo,
+                          ty * 16 - p.halo, img, 0);
+            }
+          }
+          if (++stage == CH_A_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ============================== B producer: one (tap, 64-channel block) filter slice per stage
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int u = blockIdx.x; u < p.n_units && ok; u += gridDim.x) {
+        const int n0 = (u % p.n_ntiles) * BN;
+        for (int cb = 0; cb < p.cblocks && ok; ++cb) {
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            if (!mbar_wait(b_empty + 8 * stage, phase ^ 1, st, 22)) { ok = false; break; }
+            const uint32_t fb = b_full + 8 * stage;
+            const uint32_t sb = sB0 + stage * B_BYTES;
+            mbar_arrive_expect_tx(fb, B_BYTES);
+            const int tapb = p.b_flip ? (p.ntaps - 1 - tap) : tap;
+            if (B_MN) {
+              const int krow = (tapb * p.cblocks + cb) * 64;
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, fb, n0 + 64 * j, krow);
+            } else {
+              tma_load_2d(sb, &tmB, fb, cb * 64, tapb * p.b_rows_per_tap + n0);
+            }
+            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== UMMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, B_MN);
+      const uint32_t a_sbo = box_w * 128;
+      int sa = 0, sb = 0, buf = 0;
+      uint32_t pa = 0, pb = 0, pacc = 0;
+      bool ok = true;
+      for (int u = blockIdx.x; u < p.n_units && ok; u += gridDim.x) {
+        const int pu = u / p.n_ntiles;
+        int nsub = p.n_sub_total - pu * NSUB;
+        nsub = nsub > NSUB ? NSUB : nsub;
+        if (!mbar_wait(acc_empty + 8 * buf, pacc ^ 1, st, 23)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t acc = tmem_base + buf * (NSUB * BN);
+        for (int cb = 0; cb < p.cblocks && ok; ++cb) {
+          if (!mbar_wait(a_full + 8 * sa, pa, st, 24)) { ok = false; break; }
+          const uint32_t a_stage = sA0 + sa * A_BYTES;
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            if (!mbar_wait(b_full + 8 * sb, pb, st, 25)) { ok = false; break; }
+            tc_fence_after();
+            const uint32_t b_stage = sB0 + sb * B_BYTES;
+            const int toff = p.halo ? ((tap / 3) * box_w + tap % 3) * 128 : 0;
+#pragma unroll
+            for (int j = 0; j < NSUB; ++j) {
+              if (j < nsub) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t da = make_smem_desc_sw128(a_stage + j * CH_SUB_BYTES + toff + k * 32, 16, a_sbo);
+                  const uint64_t db = B_MN ? make_smem_desc_sw128(b_stage + k * 2048, 8192, 1024)
+                                           : make_smem_desc_sw128(b_stage + k * 32, 16, 1024);
+                  umma_bf16(acc + j * BN, da, db, idesc, (cb | tap | k) != 0);
+                }
+              }
+            }
+            umma_commit(b_empty + 8 * sb);
+            if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+          }
+          umma_commit(a_empty + 8 * sa);
+          if (++sa == CH_A_STAGES) { sa = 0; pa ^= 1; }
+        }
+        if (ok) umma_commit(acc_full + 8 * buf);
+        if (++buf == ACC_BUFS) { buf = 0; pacc ^= 1; }
+      }
+    }
+  } else {
+    // ============================== epilogue (warps 2..5): TMEM -> registers -> bf16 global (+ statistics)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;        // accumulator row = pixel (x = r % 8, y = r / 8) of the sub-tile
+    int buf = 0;
+    uint32_t pacc = 0;
+    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      const int pu = u / p.n_ntiles;
+      const int n0 = (u % p.n_ntiles) * BN;
+      int nsub = p.n_sub_total - pu * NSUB;
+      nsub = nsub > NSUB ? NSUB : nsub;
+      if (!mbar_wait(acc_full + 8 * buf, pacc, st, 26)) break;
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < nsub; ++j) {
+        int s = pu * NSUB + j;
+        const int tx = s % p.ntile_w;
+        s /= p.ntile_w;
+        const int ty = s % p.ntile_h;
+        const int img = s / p.ntile_h;
+        const long long off = (long long)(tx * 8 + (r & 7)) * p.ostride_x + (long long)(ty * 16 + (r >> 3)) * p.ostride_y +
+                              (long long)img * p.ostride_n;
+        __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (NSUB * BN) + j * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          const int g = (n0 + c) / p.n_group;          // transposed-conv scatter: column group = filter tap
+          const int ngc = (n0 + c) - g * p.n_group;
+          __nv_bfloat16* o = obase + p.group_off[g] + ngc;
+          uint32_t v[32];
+          tmem_ld_32x32(trow + c, v);
+          tmem_ld_wait();
+          uint32_t packed[16];
+          float s1[32], s2[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = __uint_as_float(v[2 * i]);
+            float b = __uint_as_float(v[2 * i + 1]);
+            if (p.bias) {
+              a += __ldg(p.bias + ngc + 2 * i);
+              b += __ldg(p.bias + ngc + 2 * i + 1);
+            }
+            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+            packed[i] = *reinterpret_cast<uint32_t*>(&h);
+            if (STATS) {
+              const float2 f = __bfloat1622float2(h);   // statistics of what the next pass will read back
+              s1[2 * i] = f.x;
+              s1[2 * i + 1] = f.y;
+              s2[2 * i] = f.x * f.x;
+              s2[2 * i + 1] = f.y * f.y;
+            }
+          }
+          if (n0 + c < p.n_total) {
+            uint4* dst = reinterpret_cast<uint4*>(o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+          }
+          if (STATS) {
+            // transpose-reduce over the 32 rows of this warp: after 5 halving steps lane l holds column c + l
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) {
+              const bool hi = (lane & w) != 0;
+#pragma unroll
+              for (int i = 0; i < w; ++i) {
+                const float keep1 = hi ? s1[i + w] : s1[i];
+                const float send1 = hi ? s1[i] : s1[i + w];
+                const float keep2 = hi ? s2[i + w] : s2[i];
+                const float send2 = hi ? s2[i] : s2[i + w];
+                s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, w);
+                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
+              }
+            }
+            // lane l now owns column c + bitrev-free index: by construction the surviving element is
+            // column (lane & 16 ? 16 : 0) + (lane & 8 ? 8 : 0) + ... = lane
+            s_stats[(q * 2 + 0) * BN + c + lane] += s1[0];
+            s_stats[(q * 2 + 1) * BN + c + lane] += s2[0];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+      if (++buf == ACC_BUFS) { buf = 0; pacc ^= 1; }
+    }
+  }
+
+  __syncthreads();
+  if (STATS && p.stats_part != nullptr) {
+    // this CTA always works on column tile blockIdx.x % n_ntiles (the host makes gridDim.x a multiple of it)
+    const int n0 = (blockIdx.x % p.n_ntiles) * BN;
+    const int slot = blockIdx.x / p.n_ntiles;
+    for (int i = threadIdx.x; i < 2 * BN; i += CH_THREADS) {
+      const int k = i / BN, c = i - k * BN;
+      const float t = (s_stats[(0 * 2 + k) * BN + c] + s_stats[(1 * 2 + k) * BN + c]) +
+                      (s_stats[(2 * 2 + k) * BN + c] + s_stats[(3 * 2 + k) * BN + c]);
+      if (n0 + c < p.n_total) p.stats_part[((long long)slot * 2 + k) * p.n_total + n0 + c] = t;
+    }
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+}  // namespace bsl

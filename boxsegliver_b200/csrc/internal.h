@@ -53,4 +53,8 @@ int bsl_get_tmap(bsl_ctx* ctx, const void* base, int rank, const uint64_t* dims,
 int bsl_channel_sum_bf16(bsl_ctx* ctx, const void* x, long long pixels, int c, int ld, float* out,
                          cudaStream_t stream);
 
+// sums[group][2][c] (fp64) = per-channel sum and sum of squares of a bf16 NHWC tensor (norm.cu).
+int bsl_stats_bf16(bsl_ctx* ctx, const void* x, long long pixels_per_group, int groups, int c, int ld, double* sums,
+                   cudaStream_t stream);
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

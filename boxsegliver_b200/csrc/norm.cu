@@ -451,6 +451,12 @@ int check_norm(bsl_ctx* ctx, const bsl_norm_desc* d) {
 
 }  // namespace
 
+int bsl_stats_bf16(bsl_ctx* ctx, const void* x, long long pixels_per_group, int groups, int c, int ld, double* sums,
+                   cudaStream_t stream) {
+  StatsF f{reinterpret_cast<const __nv_bfloat16*>(x), ld};
+  return run_pixel_reduce(ctx, f, pixels_per_group, groups, c, sums, stream);
+}
+
 extern "C" {
 
 int bsl_norm_stats(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, double* sums, void* stream) {

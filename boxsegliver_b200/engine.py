@@ -471,20 +471,23 @@ class UNetEngine:
             ctx.tag = L.scope
             if L.kind in ("stem", "conv"):
                 d = self._conv_desc(L)
-                if L.kind == "stem":
-                    # im2col (27 -> 64 columns, bf16) + 1x1 conv on the tensor cores
-                    call("bsl_stem_im2col", C.byref(d), self.images.p, self.stem_col.p, s)
-                    d1 = _lib.Conv2dDesc(self.cfg.batch, L.h, L.w, 64, L.cout, 1, 1, 64, L.y.ld)
-                    self._tc("fprop", self._flops(L), "bsl_conv2d_fprop", C.byref(d1), self.stem_col.p,
-                             self._pp(self.Wbf, f"{L.scope}/weights", BF16), L.y.p, s)
-                else:
-                    self._tc("fprop", self._flops(L), "bsl_conv2d_fprop", C.byref(d), L.x.p,
-                             self._pp(self.Wbf, f"{L.scope}/weights", BF16), L.y.p, s)
                 nd = self._norm_desc(L)
                 q = self._norm_ptrs(L)
                 ns = self.norm_scope
                 bn = self.cfg.normalizer == "batch_norm"
-                if not bn or is_training:
+                # batch-norm training: the per-channel sums come out of the conv epilogue (no pass over y)
+                fused = bn and is_training
+                fn = "bsl_conv2d_fprop_stats" if fused else "bsl_conv2d_fprop"
+                extra = (q["sums"],) if fused else ()
+                wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
+                if L.kind == "stem":
+                    # im2col (27 -> 64 columns, bf16) + 1x1 conv on the tensor cores
+                    call("bsl_stem_im2col", C.byref(d), self.images.p, self.stem_col.p, s)
+                    d1 = _lib.Conv2dDesc(self.cfg.batch, L.h, L.w, 64, L.cout, 1, 1, 64, L.y.ld)
+                    self._tc("fprop", self._flops(L), fn, C.byref(d1), self.stem_col.p, wbf, L.y.p, *extra, s)
+                else:
+                    self._tc("fprop", self._flops(L), fn, C.byref(d), L.x.p, wbf, L.y.p, *extra, s)
+                if not fused and (not bn or is_training):
                     call("bsl_norm_stats", C.byref(nd), L.y.p, q["sums"], s)
                 mm = C.c_void_p(self.S.ptr + self.params[f"{L.scope}/{ns}/moving_mean"].offset * F32) if bn else None
                 mv = C.c_void_p(self.S.ptr + self.params[f"{L.scope}/{ns}/moving_variance"].offset * F32) if bn else None

@@ -95,6 +95,11 @@ typedef struct {
 
 int bsl_conv2d_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x_bf16,
                      const void* w_hwio_bf16, void* y_bf16, void* stream);
+/* Conv2D fused with the reduction half of FusedBatchNorm (NetworksV2/base.py:154-162): also returns
+ * sums[0][c] = sum over (n,h,w) of y, sums[1][c] = sum of y^2 (of the bf16-rounded outputs, fp64), which is
+ * exactly what bsl_norm_stats(mode = batch) computes from y in a separate pass. */
+int bsl_conv2d_fprop_stats(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x_bf16,
+                           const void* w_hwio_bf16, void* y_bf16, double* sums, void* stream);
 /* dx = dgrad(dy, w); dy has stride y_ld, dx has stride x_ld. */
 int bsl_conv2d_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy_bf16,
                      const void* w_hwio_bf16, void* dx_bf16, void* stream);

@@ -21,6 +21,14 @@ CONV_CASES = [
     (2, 16, 16, 64, 64, 3, 128, 192),        # skip-concat views (channel stride > channels)
     (2, 16, 16, 128, 64, 1, None, None),     # 1x1
     (1, 2, 2, 1024, 1024, 3, None, None),    # bridge layer of a 32x32 input
+    # halo-tile kernels (w % 8 == 0, h % 16 == 0): one TMA box + 9 shifted UMMA descriptors
+    (2, 32, 32, 128, 64, 3, None, None),     # Decode1/conv1 shape class: 2 k-blocks, column tile 64, sub-tile pairs
+    (3, 16, 24, 64, 192, 3, None, None),     # odd number of sub-tiles (single sub-tile units), 3 column tiles of 64
+    (2, 32, 16, 64, 256, 3, None, None),     # column tile 128 x 2
+    (1, 48, 40, 192, 128, 3, 256, 192),      # concat views, 3 k-blocks, wgrad tiles of 16 x 4
+    (4, 16, 16, 512, 64, 3, None, None),     # long reduction (8 k-blocks): ring wrap-around of both pipelines
+    (5, 16, 32, 64, 64, 1, None, None),      # 1x1 through the 1-tap path (stem after im2col)
+    (2, 64, 64, 64, 64, 3, None, None),      # many tiles per CTA? no: 64 sub-tiles; wgrad split over pixel tiles
 ]
 
 
@@ -65,9 +73,41 @@ def test_conv2d_fprop_dgrad_wgrad(ctx, n, h, w, cin, cout, k, x_ld, y_ld):
         b.free()
 
 
+def test_conv2d_fprop_fused_statistics(ctx):
+    """bsl_conv2d_fprop_stats == bsl_conv2d_fprop followed by bsl_norm_stats (batch mode), on both kernel paths."""
+    for (n, h, w, cin, cout, y_ld) in [(2, 32, 32, 64, 64, 64), (3, 16, 24, 128, 192, 256), (2, 12, 20, 64, 128, 128),
+                                       (6, 32, 32, 64, 256, 256)]:
+        rng = np.random.default_rng(h + cout)
+        x = bf16_randn(rng, (n, h, w, cin))
+        wt = bf16_randn(rng, (3, 3, cin, cout), 0.05)
+        dx_, dw_ = ctx.bf16_from_f32(x), ctx.bf16_from_f32(wt)
+        y1 = ctx.alloc(n * h * w * y_ld * 2).zero()
+        y2 = ctx.alloc(n * h * w * y_ld * 2).zero()
+        s1, s2 = ctx.alloc(2 * cout * 8).zero(), ctx.alloc(2 * cout * 8).zero()
+        desc = _lib.Conv2dDesc(n, h, w, cin, cout, 3, 3, cin, y_ld)
+        ctx.call("bsl_conv2d_fprop_stats", C.byref(desc), dx_.p, dw_.p, y1.p, s1.p, ctx.stream)
+        ctx.call("bsl_conv2d_fprop", C.byref(desc), dx_.p, dw_.p, y2.p, ctx.stream)
+        nd = _lib.NormDesc(0, n, h * w, cout, y_ld, y_ld, 1e-3, 0.999, 1, 1, 1)
+        ctx.call("bsl_norm_stats", C.byref(nd), y2.p, s2.p, ctx.stream)
+        ctx.check_device()
+        a = y1.download(np.uint16, (n, h, w, y_ld))
+        assert np.array_equal(a, y2.download(np.uint16, (n, h, w, y_ld)))
+        yv = ctx.bf16_to_f32(y1, (n, h, w, y_ld))[..., :cout].astype(np.float64)
+        got = s1.download(np.float64, (2, cout))
+        assert rel(got[0], yv.sum(axis=(0, 1, 2))) < 1e-5
+        assert rel(got[1], (yv * yv).sum(axis=(0, 1, 2))) < 1e-5
+        assert rel(got, s2.download(np.float64, (2, cout))) < 1e-5
+        # static tile schedule + fixed-order reductions: bit-reproducible
+        ctx.call("bsl_conv2d_fprop_stats", C.byref(desc), dx_.p, dw_.p, y1.p, s2.p, ctx.stream)
+        assert np.array_equal(got, s2.download(np.float64, (2, cout)))
+        for b in (dx_, dw_, y1, y2, s1, s2):
+            b.free()
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,y_ld", [
     (2, 8, 8, 128, 64, None), (1, 16, 16, 64, 64, None), (2, 4, 8, 256, 128, None), (1, 6, 10, 128, 64, None),
-    (2, 8, 8, 128, 64, 128), (1, 2, 2, 1024, 512, 1024)])
+    (2, 8, 8, 128, 64, 128), (1, 2, 2, 1024, 512, 1024),
+    (2, 16, 16, 128, 64, 128), (3, 32, 8, 256, 128, None), (1, 16, 24, 64, 64, 192)])   # 1-tap halo-kernel path
 def test_conv2d_transpose(ctx, n, h, w, cin, cout, y_ld):
     rng = np.random.default_rng(cin + cout + h)
     y_ld = y_ld or cout

@@ -56,7 +56,7 @@ print(f"sum of bracketed calls: {tot:.3f} ms/step")
 for fn, (cnt, ms) in sorted(by_fn.items(), key=lambda kv: -kv[1][1]):
     print(f"  {ms / a.steps:8.3f} ms  {cnt // a.steps:4d}x  {100 * ms / a.steps / tot:5.1f}%  {fn}")
 print("tensor-core convs per layer:")
-TC = ("bsl_conv2d_fprop", "bsl_conv2d_dgrad", "bsl_conv2d_wgrad", "bsl_convT2d_fwd", "bsl_convT2d_bwd_data",
+TC = ("bsl_conv2d_fprop", "bsl_conv2d_fprop_stats", "bsl_conv2d_dgrad", "bsl_conv2d_wgrad", "bsl_convT2d_fwd", "bsl_convT2d_bwd_data",
       "bsl_convT2d_bwd_filter")
 rows = []
 for (tag, fn), (cnt, ms) in by_layer.items():
