@@ -179,10 +179,10 @@ bool force_v1() {
   return v != 0;
 }
 
-template <int BN, int NSUB, bool B_MN, bool STATS>
+template <int BN, int NSUB, bool B_MN, bool STATS, bool SCATTER>
 int launch_halo_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args, int grid,
                     cudaStream_t stream) {
-  auto kern = conv_halo_kernel<BN, NSUB, B_MN, STATS>;
+  auto kern = conv_halo_kernel<BN, NSUB, B_MN, STATS, SCATTER>;
   constexpr int smem = ConvHaloCfg<BN, NSUB>::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
@@ -194,13 +194,17 @@ int launch_halo_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, co
   return BSL_OK;
 }
 
-template <bool B_MN, bool STATS>
+template <bool B_MN, bool STATS, bool SCATTER>
 int launch_halo(bsl_ctx* ctx, int bn, int nsub, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args,
                 int grid, cudaStream_t stream) {
-  if (bn == 64 && nsub == 2) return launch_halo_one<64, 2, B_MN, STATS>(ctx, a, b, args, grid, stream);
-  if (bn == 64 && nsub == 1) return launch_halo_one<64, 1, B_MN, STATS>(ctx, a, b, args, grid, stream);
-  if (bn == 128 && nsub == 2) return launch_halo_one<128, 2, B_MN, STATS>(ctx, a, b, args, grid, stream);
-  if (bn == 128 && nsub == 1) return launch_halo_one<128, 1, B_MN, STATS>(ctx, a, b, args, grid, stream);
+  if (bn == 64 && nsub == 2) return launch_halo_one<64, 2, B_MN, STATS, SCATTER>(ctx, a, b, args, grid, stream);
+  if (bn == 64 && nsub == 1) return launch_halo_one<64, 1, B_MN, STATS, SCATTER>(ctx, a, b, args, grid, stream);
+  if (bn == 128 && nsub == 2) return launch_halo_one<128, 2, B_MN, STATS, SCATTER>(ctx, a, b, args, grid, stream);
+  if (bn == 128 && nsub == 1) return launch_halo_one<128, 1, B_MN, STATS, SCATTER>(ctx, a, b, args, grid, stream);
+  if (!STATS) {  // the widest tile has no spare TMEM for an overlapped epilogue: statistics stay a separate pass
+    if (bn == 256 && nsub == 2) return launch_halo_one<256, 2, B_MN, false, SCATTER>(ctx, a, b, args, grid, stream);
+    if (bn == 256 && nsub == 1) return launch_halo_one<256, 1, B_MN, false, SCATTER>(ctx, a, b, args, grid, stream);
+  }
   return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv_halo: tile %d x %d", bn, nsub);
 }
 
@@ -214,8 +218,12 @@ bool halo_eligible(int w, int h) { return !force_v1() && w % 8 == 0 && h % 16 ==
 HaloPlan plan_halo(bsl_ctx* ctx, int w, int h, int n, int ncols) {
   HaloPlan p;
   p.n_sub_total = (w / 8) * (h / 16) * n;
-  p.bn = ncols % 128 == 0 ? 128 : 64;
+  p.bn = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64);
   p.nsub = p.n_sub_total % 2 == 0 ? 2 : 1;
+  static const int env_bn = getenv("BSL_HALO_BN") ? atoi(getenv("BSL_HALO_BN")) : 0;      // tuning overrides
+  static const int env_nsub = getenv("BSL_HALO_NSUB") ? atoi(getenv("BSL_HALO_NSUB")) : 0;
+  if (env_bn && ncols % env_bn == 0) p.bn = env_bn;
+  if (env_nsub == 1) p.nsub = 1;
   p.n_ntiles = ncols / p.bn;
   p.n_units = cdiv(p.n_sub_total, p.nsub) * p.n_ntiles;
   int g = std::min(p.n_units, ctx->sm_count);
@@ -288,11 +296,17 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
   a.n_group = d->cout;
   a.n_total = d->cout;
   a.status = ctx->d_status;
-  if (!sums) return launch_halo<true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+  if (!sums) return launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+  if (pl.bn == 256) {
+    // long-reduction layers: small, L2-resident outputs; a separate statistics pass is cheaper than an
+    // un-overlapped epilogue butterfly
+    if ((rc = launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream))) return rc;
+    return bsl_stats_bf16(ctx, y, (long long)d->n * d->h * d->w, 1, d->cout, d->y_ld, sums, stream);
+  }
   float* part = nullptr;
   if ((rc = bsl_scratch(ctx, (size_t)pl.slots * 2 * d->cout * sizeof(float), &part))) return rc;
   a.stats_part = part;
-  if ((rc = launch_halo<true, true>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream))) return rc;
+  if ((rc = launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream))) return rc;
   const int kc = 2 * d->cout;
   pixel_reduce_final_kernel<<<dim3((kc + 31) / 32, 1), 256, 0, stream>>>(part, pl.slots, kc, sums);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel (conv statistics)");
@@ -363,7 +377,7 @@ int bsl_conv2d_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, con
     a.n_group = d->cin;
     a.n_total = d->cin;
     a.status = ctx->d_status;
-    return launch_halo<false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
+    return launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
   }
   int box[4] = {0, 0, 0, 1};
   pick_box(128, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
@@ -519,7 +533,7 @@ int bsl_convT2d_fwd(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, cons
     a.relu = d->relu;
     a.n_total = 4 * d->cout;
     a.status = ctx->d_status;
-    return launch_halo<false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
+    return launch_halo<false, false, true>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
   }
   int box[4] = {0, 0, 0, 1};
   pick_box(128, d->w, d->h, d->n, &box[0], &box[1], &box[2]);

@@ -125,7 +125,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int kk = 0; kk < num_k; ++kk) {
@@ -173,7 +173,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   } else if (warp == 1) {
     // ============================== UMMA issuer ===============================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, A_MN, B_MN);
       int stage = 0;
       uint32_t phase = 0;

@@ -88,7 +88,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int num_k = k_end - k_begin;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int kk = 0; kk < num_k; ++kk) {
@@ -107,7 +107,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, 64, true, true);
       // tap pairs (0,1) (2,3) (4,5) (6,7) (8,-): start row of the first tap and distance to the second
       // inside the halo tile, tap t = (r, s) = (t / 3, t % 3) at pixel offset r * PITCH + s.
@@ -127,14 +127,17 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         tc_fence_after();
         const uint32_t sx = smem_base + stage * WG_STAGE_BYTES;
         const uint32_t sdy = sx + WG_X_BYTES;
+        const uint64_t db0 = make_smem_desc_sw128(sdy, 8192, 1024);
+        uint64_t da0[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) da0[q] = make_smem_desc_sw128(sx + off0[q], lbo[q], 1024);
+        const uint32_t first = kk != 0;
 #pragma unroll
         for (int y = 0; y < WG_TH; ++y) {
-          const uint64_t db = make_smem_desc_sw128(sdy + y * (WG_TW * 128), 8192, 1024);
 #pragma unroll
-          for (int q = 0; q < 5; ++q) {
-            const uint64_t da = make_smem_desc_sw128(sx + off0[q] + y * (WG_PITCH * 128), lbo[q], 1024);
-            umma_bf16(tmem_base + q * 64, da, db, idesc, (kk | y) != 0);
-          }
+          for (int q = 0; q < 5; ++q)
+            umma_bf16(tmem_base + q * 64, da0[q] + (uint64_t)((y * WG_PITCH * 128) >> 4),
+                      db0 + (uint64_t)((y * WG_TW * 128) >> 4), idesc, first | (uint32_t)(y != 0));
         }
         umma_commit(empty0 + 8 * stage);
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
@@ -202,7 +205,6 @@ struct ConvHaloArgs {
 };
 
 constexpr int CH_SUB_BYTES = 23552;   // (10 x 18) x 128 B = 23040, padded to a multiple of 1024
-constexpr int CH_A_STAGES = 2;
 
 template <int BN, int NSUB>
 struct ConvHaloCfg {
@@ -210,46 +212,75 @@ struct ConvHaloCfg {
   static constexpr int TMEM_COLS = BN * NSUB * ACC_BUFS;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int A_BYTES = NSUB * CH_SUB_BYTES;
-  // fill what is left of ~200 KB after the A ring with B stages (at least 3, at most 8)
-  static constexpr int B_FIT = (200 * 1024 - CH_A_STAGES * A_BYTES) / B_BYTES;
+  // three activation stages hide the HBM latency of the one-block-deep reductions (Cin = 64: a unit is
+  // ~1.5 us of MMAs); the widest column tile only occurs with long reductions and keeps two.
+  static constexpr int A_STAGES = BN == 256 ? 2 : 3;
+  static constexpr int B_FIT = (212 * 1024 - A_STAGES * A_BYTES) / B_BYTES;
   static constexpr int B_STAGES = B_FIT > 8 ? 8 : (B_FIT < 3 ? 3 : B_FIT);
-  static constexpr int SMEM_BYTES = CH_A_STAGES * A_BYTES + B_STAGES * B_BYTES + 1024;
+  static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_BYTES + 1024;
 };
 
-constexpr int CH_THREADS = 224;  // warp 0: A producer, 1: MMA, 2-5: epilogue, 6: B producer
+// warp 0: A producer, 1: UMMA issuer, 2..9: epilogue (two warps per TMEM lane quarter), 10: B producer
+constexpr int CH_EPI_WARPS = 8;
+constexpr int CH_THREADS = (3 + CH_EPI_WARPS) * 32;
 
-template <int BN, int NSUB, bool B_MN, bool STATS>
+// 32 fp32 accumulator columns of one pixel row -> 32 bf16 (64 B) in global memory.
+template <bool SCATTER>
+__device__ __forceinline__ void ch_store_chunk(const uint32_t (&v)[32], __nv_bfloat16* o, const float* bias,
+                                               int relu, uint32_t (&packed)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float a = __uint_as_float(v[2 * i]);
+    float b = __uint_as_float(v[2 * i + 1]);
+    if (SCATTER) {
+      if (bias) {
+        a += __ldg(bias + 2 * i);
+        b += __ldg(bias + 2 * i + 1);
+      }
+      if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    packed[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+}
+
+template <int BN, int NSUB, bool B_MN, bool STATS, bool SCATTER>
 __global__ void __launch_bounds__(CH_THREADS)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvHaloArgs p) {
   using Cfg = ConvHaloCfg<BN, NSUB>;
   constexpr int ACC_BUFS = Cfg::ACC_BUFS;
+  constexpr int A_STAGES = Cfg::A_STAGES;
   constexpr int B_STAGES = Cfg::B_STAGES;
   constexpr int A_BYTES = Cfg::A_BYTES;
   constexpr int B_BYTES = Cfg::B_BYTES;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * CH_A_STAGES + 2 * B_STAGES + 2 * ACC_BUFS];
+  __shared__ __align__(8) uint64_t bars[2 * A_STAGES + 2 * B_STAGES + 2 * ACC_BUFS];
   __shared__ uint32_t tmem_slot;
   __shared__ int dead;
-  __shared__ float s_stats[STATS ? 4 * 2 * BN : 1];
+  __shared__ float s_stats[STATS ? CH_EPI_WARPS * 2 * BN : 1];
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA0 = smem_base;
-  const uint32_t sB0 = smem_base + CH_A_STAGES * A_BYTES;
+  const uint32_t sB0 = smem_base + A_STAGES * A_BYTES;
   const uint32_t a_full = smem_u32(&bars[0]);
-  const uint32_t a_empty = smem_u32(&bars[CH_A_STAGES]);
-  const uint32_t b_full = smem_u32(&bars[2 * CH_A_STAGES]);
-  const uint32_t b_empty = smem_u32(&bars[2 * CH_A_STAGES + B_STAGES]);
-  const uint32_t acc_full = smem_u32(&bars[2 * CH_A_STAGES + 2 * B_STAGES]);
-  const uint32_t acc_empty = smem_u32(&bars[2 * CH_A_STAGES + 2 * B_STAGES + ACC_BUFS]);
+  const uint32_t a_empty = smem_u32(&bars[A_STAGES]);
+  const uint32_t b_full = smem_u32(&bars[2 * A_STAGES]);
+  const uint32_t b_empty = smem_u32(&bars[2 * A_STAGES + B_STAGES]);
+  const uint32_t acc_full = smem_u32(&bars[2 * A_STAGES + 2 * B_STAGES]);
+  const uint32_t acc_empty = smem_u32(&bars[2 * A_STAGES + 2 * B_STAGES + ACC_BUFS]);
   DeviceStatus* st = p.status;
 
   if (threadIdx.x == 0) dead = *reinterpret_cast<volatile int*>(&st->error);
   if (STATS) {
-    for (int i = threadIdx.x; i < 4 * 2 * BN; i += CH_THREADS) s_stats[i] = 0.f;
+    for (int i = threadIdx.x; i < CH_EPI_WARPS * 2 * BN; i += CH_THREADS) s_stats[i] = 0.f;
   }
   __syncthreads();
   if (dead) return;
@@ -257,7 +288,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
     prefetch_tensormap(&tmB);
-    for (int s = 0; s < CH_A_STAGES; ++s) {
+    for (int s = 0; s < A_STAGES; ++s) {
       mbar_init(a_full + 8 * s, 1);
       mbar_init(a_empty + 8 * s, 1);
     }
@@ -267,7 +298,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < ACC_BUFS; ++s) {
       mbar_init(acc_full + 8 * s, 1);
-      mbar_init(acc_empty + 8 * s, 4);  // one arrival per epilogue warp
+      mbar_init(acc_empty + 8 * s, CH_EPI_WARPS);  // one arrival per epilogue warp
     }
     fence_barrier_init();
   } else if (warp == 1) {
@@ -284,37 +315,39 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     // ============================== A producer: one halo'd tile per (sub-tile, 64-channel block)
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
       for (int u = blockIdx.x; u < p.n_units && ok; u += gridDim.x) {
         const int pu = u / p.n_ntiles;
+        int nsub = p.n_sub_total - pu * NSUB;
+        nsub = nsub > NSUB ? NSUB : nsub;
+        int tx[NSUB], ty[NSUB], img[NSUB];
+#pragma unroll
+        for (int j = 0; j < NSUB; ++j) {
+          int s = pu * NSUB + j;
+          tx[j] = s % p.ntile_w;
+          s /= p.ntile_w;
+          ty[j] = s % p.ntile_h;
+          img[j] = s / p.ntile_h;
+        }
         for (int cb = 0; cb < p.cblocks && ok; ++cb) {
           if (!mbar_wait(a_empty + 8 * stage, phase ^ 1, st, 21)) { ok = false; break; }
           const uint32_t fb = a_full + 8 * stage;
-          int nsub = p.n_sub_total - pu * NSUB;
-          nsub = nsub > NSUB ? NSUB : nsub;
           mbar_arrive_expect_tx(fb, nsub * sub_rows * 128);
 #pragma unroll
-          for (int j = 0; j < NSUB; ++j) {
-            if (j < nsub) {
-              int s = pu * NSUB + j;
-              const int tx = s % p.ntile_w;
-              s /= p.ntile_w;
-              const int ty = s % p.ntile_h;
-              const int img = s / p.ntile_h;
-              tma_load_5d(sA0 + stage * A_BYTES + j * CH_SUB_BYTES, &tmA, fb, cb * 64, tx * 8 - p.halo,
-                          ty * 16 - p.halo, img, 0);
-            }
-          }
-          if (++stage == CH_A_STAGES) { stage = 0; phase ^= 1; }
+          for (int j = 0; j < NSUB; ++j)
+            if (j < nsub)
+              tma_load_5d(sA0 + stage * A_BYTES + j * CH_SUB_BYTES, &tmA, fb, cb * 64, tx[j] * 8 - p.halo,
+                          ty[j] * 16 - p.halo, img[j], 0);
+          if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 2 + CH_EPI_WARPS) {
     // ============================== B producer: one (tap, 64-channel block) filter slice per stage
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
@@ -341,7 +374,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ============================== UMMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, B_MN);
       const uint32_t a_sbo = box_w * 128;
       int sa = 0, sb = 0, buf = 0;
@@ -362,32 +395,39 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
             const uint32_t b_stage = sB0 + sb * B_BYTES;
             const int toff = p.halo ? ((tap / 3) * box_w + tap % 3) * 128 : 0;
+            // descriptors differ only in the 14-bit start-address field: one add per operand per UMMA
+            const uint64_t da0 = make_smem_desc_sw128(a_stage + toff, 16, a_sbo);
+            const uint64_t db0 = B_MN ? make_smem_desc_sw128(b_stage, 8192, 1024) : make_smem_desc_sw128(b_stage, 16, 1024);
+            const uint32_t first = (cb | tap) != 0;
 #pragma unroll
             for (int j = 0; j < NSUB; ++j) {
               if (j < nsub) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t da = make_smem_desc_sw128(a_stage + j * CH_SUB_BYTES + toff + k * 32, 16, a_sbo);
-                  const uint64_t db = B_MN ? make_smem_desc_sw128(b_stage + k * 2048, 8192, 1024)
-                                           : make_smem_desc_sw128(b_stage + k * 32, 16, 1024);
-                  umma_bf16(acc + j * BN, da, db, idesc, (cb | tap | k) != 0);
-                }
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(acc + j * BN, da0 + (uint64_t)((j * CH_SUB_BYTES + k * 32) >> 4),
+                            db0 + (uint64_t)((B_MN ? k * 2048 : k * 32) >> 4), idesc, first | (uint32_t)(k != 0));
               }
             }
             umma_commit(b_empty + 8 * sb);
             if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
           }
           umma_commit(a_empty + 8 * sa);
-          if (++sa == CH_A_STAGES) { sa = 0; pa ^= 1; }
+          if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
         }
         if (ok) umma_commit(acc_full + 8 * buf);
         if (++buf == ACC_BUFS) { buf = 0; pacc ^= 1; }
       }
     }
   } else {
-    // ============================== epilogue (warps 2..5): TMEM -> registers -> bf16 global (+ statistics)
+    // ============================== epilogue (warps 2..9): TMEM -> registers -> bf16 global (+ statistics)
+    // Warp e handles TMEM lane quarter (warp & 3); the two warps of a quarter split the work of a unit:
+    // NSUB == 2: one sub-tile each; NSUB == 1: half of the columns each.
+    const int e = warp - 2;
     const int q = warp & 3;
+    const int half = e >> 2;
     const int r = q * 32 + lane;        // accumulator row = pixel (x = r % 8, y = r / 8) of the sub-tile
+    constexpr int COLS = NSUB == 2 ? BN : BN / 2;   // columns this warp handles per unit
+    const int c_begin = NSUB == 2 ? 0 : half * COLS;
     int buf = 0;
     uint32_t pacc = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
@@ -397,8 +437,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       nsub = nsub > NSUB ? NSUB : nsub;
       if (!mbar_wait(acc_full + 8 * buf, pacc, st, 26)) break;
       tc_fence_after();
-#pragma unroll 1
-      for (int j = 0; j < nsub; ++j) {
+      const int j = NSUB == 2 ? half : 0;
+      if (j < nsub) {
         int s = pu * NSUB + j;
         const int tx = s % p.ntile_w;
         s /= p.ntile_w;
@@ -408,43 +448,48 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                               (long long)img * p.ostride_n;
         __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (NSUB * BN) + j * BN;
+        if (!STATS) {
+          // two chunks in flight: both TMEM loads are issued before the first is consumed
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          const int g = (n0 + c) / p.n_group;          // transposed-conv scatter: column group = filter tap
-          const int ngc = (n0 + c) - g * p.n_group;
-          __nv_bfloat16* o = obase + p.group_off[g] + ngc;
-          uint32_t v[32];
-          tmem_ld_32x32(trow + c, v);
-          tmem_ld_wait();
-          uint32_t packed[16];
-          float s1[32], s2[32];
+          for (int c = c_begin; c < c_begin + COLS; c += 64) {
+            uint32_t v0[32], v1[32], packed[16];
+            tmem_ld_32x32(trow + c, v0);
+            if (COLS >= 64) tmem_ld_32x32(trow + c + 32, v1);
+            tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            float a = __uint_as_float(v[2 * i]);
-            float b = __uint_as_float(v[2 * i + 1]);
-            if (p.bias) {
-              a += __ldg(p.bias + ngc + 2 * i);
-              b += __ldg(p.bias + ngc + 2 * i + 1);
+            for (int hc = 0; hc < (COLS >= 64 ? 2 : 1); ++hc) {
+              const int col = n0 + c + 32 * hc;
+              __nv_bfloat16* o;
+              const float* bias = nullptr;
+              if (SCATTER) {
+                const int g = col / p.n_group;          // transposed-conv scatter: column group = filter tap
+                const int ngc = col - g * p.n_group;
+                o = obase + p.group_off[g] + ngc;
+                bias = p.bias ? p.bias + ngc : nullptr;
+              } else {
+                o = obase + col;
+              }
+              ch_store_chunk<SCATTER>(hc ? v1 : v0, o, bias, p.relu, packed);
             }
-            if (p.relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-            __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-            packed[i] = *reinterpret_cast<uint32_t*>(&h);
-            if (STATS) {
-              const float2 f = __bfloat1622float2(h);   // statistics of what the next pass will read back
+          }
+        } else {
+#pragma unroll 1
+          for (int c = c_begin; c < c_begin + COLS; c += 32) {
+            uint32_t v[32], packed[16];
+            tmem_ld_32x32(trow + c, v);
+            tmem_ld_wait();
+            ch_store_chunk<false>(v, obase + n0 + c, nullptr, 0, packed);
+            // statistics of the bf16 values just stored (what the normalisation pass reads back):
+            // transpose-reduce over the 32 rows of this warp; after 5 halving steps lane l holds column c + l
+            float s1[32], s2[32];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[i]));
               s1[2 * i] = f.x;
               s1[2 * i + 1] = f.y;
               s2[2 * i] = f.x * f.x;
               s2[2 * i + 1] = f.y * f.y;
             }
-          }
-          if (n0 + c < p.n_total) {
-            uint4* dst = reinterpret_cast<uint4*>(o);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
-          }
-          if (STATS) {
-            // transpose-reduce over the 32 rows of this warp: after 5 halving steps lane l holds column c + l
 #pragma unroll
             for (int w = 16; w >= 1; w >>= 1) {
               const bool hi = (lane & w) != 0;
@@ -458,10 +503,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
               }
             }
-            // lane l now owns column c + bitrev-free index: by construction the surviving element is
-            // column (lane & 16 ? 16 : 0) + (lane & 8 ? 8 : 0) + ... = lane
-            s_stats[(q * 2 + 0) * BN + c + lane] += s1[0];
-            s_stats[(q * 2 + 1) * BN + c + lane] += s2[0];
+            s_stats[(e * 2 + 0) * BN + c + lane] += s1[0];
+            s_stats[(e * 2 + 1) * BN + c + lane] += s2[0];
           }
         }
       }
@@ -479,8 +522,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int slot = blockIdx.x / p.n_ntiles;
     for (int i = threadIdx.x; i < 2 * BN; i += CH_THREADS) {
       const int k = i / BN, c = i - k * BN;
-      const float t = (s_stats[(0 * 2 + k) * BN + c] + s_stats[(1 * 2 + k) * BN + c]) +
-                      (s_stats[(2 * 2 + k) * BN + c] + s_stats[(3 * 2 + k) * BN + c]);
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < CH_EPI_WARPS; ++w) t += s_stats[(w * 2 + k) * BN + c];  // fixed order
       if (n0 + c < p.n_total) p.stats_part[((long long)slot * 2 + k) * p.n_total + n0 + c] = t;
     }
   }
