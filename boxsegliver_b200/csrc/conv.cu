@@ -510,7 +510,14 @@ int bsl_convT2d_fwd(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, cons
   if (rc) return rc;
   if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "convT2d_fwd: null buffer");
   if (halo_eligible(d->w, d->h)) {
-    const HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, 4 * d->cout);
+    HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, 4 * d->cout);
+    if (pl.bn == 256 && d->cin <= 256) {
+      // short reductions: the un-overlapped epilogue of the 256-wide tile would cost as much as its MMAs
+      pl.bn = 128;
+      pl.n_ntiles = 4 * d->cout / 128;
+      pl.n_units = cdiv(pl.n_sub_total, pl.nsub) * pl.n_ntiles;
+      pl.grid = std::max(1, std::min(pl.n_units, ctx->sm_count));
+    }
     const int hbox[4] = {8, 16, 1, 1};
     CUtensorMap ta, tb;
     if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, hbox, &ta))) return rc;

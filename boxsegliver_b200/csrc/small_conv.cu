@@ -61,31 +61,43 @@ __global__ void stem_fprop_kernel(const float* __restrict__ x, const float* __re
 // col[p][t*CIN + ci] = x[p + tap t][ci] (zero outside the image, zero for columns >= taps*CIN), bf16,
 // 64 columns per pixel. With this matrix the stem becomes a 1x1 conv with cin = 64 on the tcgen05
 // path (fprop and wgrad), instead of a CUDA-core kernel. Thread = (pixel, 8-column group).
+// Block = one strip of IM2COL_STRIP pixels of one image row. The (kh x (strip + kw - 1) x cin) input patch is
+// staged in shared memory with coalesced loads (zero outside the image = SAME padding); thread
+// (pixel lane, 8-column group g) then gathers its 8 columns through offsets that depend only on g
+// (held in registers) and writes one 16-byte chunk: a warp writes 512 contiguous bytes.
+constexpr int IM2COL_STRIP = 128;
 __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int n, int h, int wd,
                                    int cin, int kh, int kw) {
-  const long long total = (long long)n * h * wd * 8;
+  extern __shared__ float patch[];  // [kh][strip + kw - 1][cin]
+  const int strips = (wd + IM2COL_STRIP - 1) / IM2COL_STRIP;
   const int ph = (kh - 1) / 2, pw = (kw - 1) / 2;
   const int kcols = kh * kw * cin;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(i & 7);
-    const long long p = i >> 3;
-    const int xw = (int)(p % wd);
-    const int yh = (int)((p / wd) % h);
-    const long long img = p / ((long long)wd * h);
-    float v[8];
+  const int pitch = (IM2COL_STRIP + kw - 1) * cin;
+  const int g = threadIdx.x & 7;
+  int off[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int col_i = g * 8 + j;
-      float val = 0.f;
-      if (col_i < kcols) {
-        const int t = col_i / cin, ci = col_i - t * cin;
-        const int yy = yh + t / kw - ph, xx = xw + t % kw - pw;
-        if (yy >= 0 && yy < h && xx >= 0 && xx < wd) val = __ldg(x + ((img * h + yy) * wd + xx) * cin + ci);
-      }
-      v[j] = val;
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    const int t = c / cin, ci = c - t * cin;
+    off[j] = c < kcols ? (t / kw) * pitch + (t % kw) * cin + ci : -1;
+  }
+  for (long long b = blockIdx.x; b < (long long)n * h * strips; b += gridDim.x) {
+    const int sx = (int)(b % strips) * IM2COL_STRIP;
+    const int yh = (int)((b / strips) % h);
+    const long long img = b / ((long long)strips * h);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kh * pitch; i += blockDim.x) {
+      const int r = i / pitch, rem = i - r * pitch;
+      const int xx = sx - pw + rem / cin, yy = yh - ph + r;
+      patch[i] = (yy >= 0 && yy < h && xx >= 0 && xx < wd) ? __ldg(x + ((img * h + yy) * wd + xx) * cin + rem % cin) : 0.f;
     }
-    st16(col + p * 64 + g * 8, pack8(v));
+    __syncthreads();
+    for (int px = threadIdx.x >> 3; px < IM2COL_STRIP && sx + px < wd; px += blockDim.x >> 3) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? patch[off[j] + px * cin] : 0.f;
+      st16(col + ((img * h + yh) * wd + sx + px) * 64 + g * 8, pack8(v));
+    }
   }
 }
 
@@ -326,9 +338,11 @@ int bsl_stem_im2col(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x, void
   if (!x || !col) return bsl_fail(ctx, BSL_EINVAL, "stem_im2col: null buffer");
   if (d->kh * d->kw * d->cin > 64 || d->cin < 1)
     return bsl_fail(ctx, BSL_EUNSUPPORTED, "stem_im2col: kh*kw*cin = %d must be <= 64", d->kh * d->kw * d->cin);
-  const long long items = (long long)d->n * d->h * d->w * 8;
-  stem_im2col_kernel<<<ew_grid(ctx, items), 256, 0, as_stream(stream)>>>(x, reinterpret_cast<__nv_bfloat16*>(col),
-                                                                         d->n, d->h, d->w, d->cin, d->kh, d->kw);
+  const long long blocks = (long long)d->n * d->h * ((d->w + IM2COL_STRIP - 1) / IM2COL_STRIP);
+  const size_t smem = (size_t)d->kh * (IM2COL_STRIP + d->kw - 1) * d->cin * sizeof(float);
+  const long long cap = 16LL * ctx->sm_count;
+  stem_im2col_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, smem, as_stream(stream)>>>(
+      x, reinterpret_cast<__nv_bfloat16*>(col), d->n, d->h, d->w, d->cin, d->kh, d->kw);
   BSL_LAUNCH_CHECK(ctx, "stem_im2col_kernel");
   return BSL_OK;
 }

@@ -1,0 +1,71 @@
+"""Generates tests/golden/unet2d_step.npz -- golden vectors for one U-Net training step.
+
+The reference (Jarvis73/BoxSegLiver) cannot be imported here: it is TensorFlow 1.13 code and TF cannot be
+installed in this image, and it ships no tests or golden vectors of its own (section 4).
+These vectors are therefore minted by this repo's CPU oracle (oracle/unet_ref.py, a restatement of
+NetworksV2/UNet.py:58-155 + loss_metrics.py:115-339 + core/solver.py:204-243 with TF-1.13/slim semantics) in
+fp64, after that oracle has been cross-checked against an independent torch-CPU implementation
+(tests/test_oracle_vs_torch.py) and central finite differences (tests/test_oracle_gradcheck.py).
+PARITY UNPINNED by the reference itself; pinned by two independent implementations.
+
+    python tests/golden/make_golden.py          # rewrites the .npz next to this file
+
+The fixture stores the INPUTS (images, labels) verbatim and the weights by seed + per-tensor checksums (the
+31 M parameters do not belong in git); outputs are logits, loss, masks, argmax, integer Dice counts and, per
+trainable tensor, the gradient's L2 norm, sum and leading entries.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from boxsegliver_b200 import synthetic  # noqa: E402
+from oracle import unet_ref as R  # noqa: E402
+
+CFG = dict(height=32, width=32, channel=3, init_channels=64, num_down_samples=4, normalizer="batch_norm",
+           weight_decay_rate=1e-5, loss_type="xentropy", loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4))
+N, WEIGHT_SEED, DATA_SEED, LR = 3, 11, 1357, 1e-3
+
+
+def build(dtype=np.float64):
+    cfg = R.UNetCfg(**CFG)
+    params = R.init_params(cfg, seed=WEIGHT_SEED)
+    images, labels = synthetic.make_batch(N, CFG["height"], CFG["width"], 3, seed=DATA_SEED)
+    p = {k: v.astype(dtype) for k, v in params.items()}
+    tape = R.forward(p, images.astype(dtype), cfg, True)
+    loss, dl = R.loss_and_dlogits(tape, labels, cfg)
+    grads = R.backward(tape, dl, cfg)
+    preds = R.predictions(tape, cfg)
+    mets = R.metrics(tape, labels, cfg, ("Dice", "VOE", "VD"))
+    out = {
+        "images": images, "labels": labels,
+        "logits": tape.logits.astype(np.float32), "loss": np.float64(loss),
+        "reg_loss": np.float64(R.regularization_loss(params, cfg)),
+        "argmax": np.argmax(tape.prob, axis=-1).astype(np.uint8),
+    }
+    for k, v in preds.items():
+        out["pred/" + k] = np.asarray(v)
+    for k, v in mets.items():
+        out["metric/" + k] = np.float32(v)
+    for c in range(1, cfg.num_classes):
+        i_, l_, r_ = R.O.seg_counts(np.asarray(preds[cfg.classes[c] + "Pred"]), labels, c)
+        out[f"counts/{c}"] = np.stack([i_, l_, r_], axis=1).astype(np.uint32)
+    names = sorted(grads)
+    out["grad_names"] = np.array(names)
+    out["grad_norm"] = np.array([np.linalg.norm(grads[k].astype(np.float64)) for k in names])
+    out["grad_sum"] = np.array([grads[k].astype(np.float64).sum() for k in names])
+    out["grad_head"] = np.stack([np.resize(grads[k].astype(np.float64).ravel()[:8], 8) for k in names])
+    wn = sorted(params)
+    out["weight_names"] = np.array(wn)
+    out["weight_sumsq"] = np.array([float((params[k].astype(np.float64) ** 2).sum()) for k in wn])
+    for k, v in tape.new_moving.items():
+        out["moving/" + k] = np.asarray(v, np.float32)
+    return out
+
+
+if __name__ == "__main__":
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "unet2d_step.npz")
+    np.savez_compressed(path, **build())
+    print("wrote", path, os.path.getsize(path), "bytes")
