@@ -391,6 +391,41 @@ def train_step(params: dict, slots: dict, step: int, images, labels, cfg: UNetCf
     return total, tape, grads
 
 
+def replica_grads(params: dict, images, labels, cfg: UNetCfg, replicas: int, rnd=_identity, wrnd=None):
+    """What ONE replica contributes under MirroredStrategy (/root/reference/core/estimator.py:570-613,
+    utils/distribution_utils.py:85-98): gradients of (data loss / R) on its own per-device batch -- batch-norm
+    statistics are per replica, there is no sync-BN -- plus its new moving statistics and its data loss."""
+    tape = forward(params, images, cfg, True, rnd, wrnd)
+    data_loss, dl = loss_and_dlogits(tape, labels, cfg, loss_scale=1.0 / replicas)
+    return backward(tape, dl, cfg, rnd), tape.new_moving, float(data_loss)
+
+
+def mirrored_apply(params: dict, slots: dict, step: int, grad_sum: dict, moving_mean: dict, cfg: UNetCfg, lr: float):
+    """The identical update every mirror applies after the all-reduce: SUM of the replica gradients (= gradient of
+    the mean loss) + the L2 term, Adam; moving statistics are the cross-replica MEAN of the replica updates."""
+    grads = total_grads(params, grad_sum, cfg)
+    for k, g in grads.items():
+        w = params[k].astype(np.float64)
+        m, v = slots.setdefault(k, (np.zeros_like(w), np.zeros_like(w)))
+        w, m, v = O.adam_step(w, g.astype(np.float64), m, v, step, lr)
+        slots[k] = (m, v)
+        params[k] = w.astype(params[k].dtype)
+    for k, v in moving_mean.items():
+        params[k] = np.asarray(v).astype(params[k].dtype)
+
+
+def mirrored_train_step(params: dict, slots: dict, step: int, shards, cfg: UNetCfg, lr: float):
+    """R virtual replicas in one process, gradients summed in rank order. `shards` = [(images, labels)] per replica.
+    Returns the MEAN of the replica data losses + the regularisation loss (estimator.py:576-577)."""
+    r = len(shards)
+    reg = regularization_loss(params, cfg)
+    outs = [replica_grads(params, im, lb, cfg, r) for im, lb in shards]
+    gsum = {k: sum(o[0][k].astype(np.float64) for o in outs) for k in outs[0][0]}
+    mmean = {k: sum(np.asarray(o[1][k], np.float64) for o in outs) / r for k in outs[0][1]}
+    mirrored_apply(params, slots, step, gsum, mmean, cfg, lr)
+    return sum(o[2] for o in outs) / r + reg
+
+
 def predictions(tape: Tape, cfg: UNetCfg):
     """`<Cls>Pred` uint8 masks (UNet.py:112-117)."""
     masks = O.threshold_masks(tape.prob)
