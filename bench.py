@@ -260,6 +260,16 @@ def run_b200(args):
         achieved = conv["flops"] / (conv["ms"] / 1e3) / 1e12 if conv["ms"] > 0 else 0.0
         peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0)))
         fl = eng.step_flops()
+        traffic, traffic_note = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+        if os.path.exists(tp):   # dram__bytes_read+write of one ncu --set full capture (never measured under this run)
+            with open(tp) as f:
+                tj = json.load(f)
+            traffic = tj.get("dram_bytes_per_launch")
+            traffic_note = {"kernel": tj.get("dominant"), "algorithmic_bytes_per_launch": tj.get("algorithmic_bytes_per_launch"),
+                            "source": tj.get("source")}
+        per_kind = {k: {"launches_per_step": v[0] // args.steps, "ms_per_step": v[1] / args.steps,
+                        "tflops": v[2] / (v[1] / 1e3) / 1e12 if v[1] > 0 else 0.0} for k, v in conv["per_kind"].items()}
         line = {
             "metric": "unet2d_256_train_slices_per_s", "value": value, "unit": "slices/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
@@ -273,8 +283,9 @@ def run_b200(args):
             "model_tflops_per_s": FLOP_PER_SLICE * value / 1e12,
             "step_tflop_algorithmic": fl["total"] / 1e12,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
-                         "kernel": "bsl::igemm_kernel (all tcgen05 conv / convT fprop, dgrad, wgrad launches)",
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_note": traffic_note, "per_kind": per_kind,
+                         "kernel": "bsl::conv_halo_kernel + bsl::wgrad_halo_kernel + bsl::igemm_kernel (every tcgen05 conv / convT fprop, dgrad, wgrad launch of the timed steps)",
                          "launches_timed": conv["launches"], "ms_per_step_in_kernel": conv["ms"] / args.steps,
                          "peak_source": f"{peak_src} MEASURED_PEAKS.json bf16_tflops_sustained",
                          "whole_step_frac_of_peak": FLOP_PER_SLICE * value / 1e12 / world / peak},
