@@ -37,6 +37,19 @@ class NormDesc(C.Structure):
     ]
 
 
+class Guide(C.Structure):
+    _fields_ = [("map", C.c_void_p), ("channels", C.c_int), ("w", C.c_void_p), ("w_ld", C.c_int)]
+
+
+class DropoutDesc(C.Structure):
+    _fields_ = [("keep_prob", C.c_float), ("seed", C.c_ulonglong), ("offset", C.c_ulonglong)]
+
+
+class FcDesc(C.Structure):
+    _fields_ = [("n", C.c_int), ("cin", C.c_int), ("cout", C.c_int), ("relu", C.c_int), ("use_dropout", C.c_int),
+                ("dropout", DropoutDesc)]
+
+
 class SmallConvDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("n", "h", "w", "cin", "cout", "kh", "kw", "x_ld", "y_ld")]
 

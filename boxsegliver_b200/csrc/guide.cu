@@ -1,0 +1,188 @@
+// GUNet guide sub-networks (small, fp32, CUDA-core): the context MLP that produces the per-(sample, channel)
+// modulation vector and the average-pooled pyramid of the spatial guide.
+//   slim_nets.fc / mlp (fully_connected + dropout)   <- NetworksV2/Backbone/slim_nets.py:34-57, GUNet.py:31-59
+//   slim.avg_pool2d(gs, 2) pyramid                   <- NetworksV2/GUNet.py:136-159
+// The 1x1 guide convolutions themselves are never materialised: norm.cu evaluates guide[p] . w[:, c] inside the
+// normalisation passes of the layer they modulate.
+#include "internal.h"
+
+namespace {
+
+// Philox4x32-10 (Salmon et al. 2011), the counter-based generator TF's random ops are built on. The stream here is
+// keyed by (seed, offset) from the descriptor; element i uses counter i / 4, lane i % 4.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+__device__ __forceinline__ float dropout_scale(const bsl_dropout_desc& dd, unsigned long long idx) {
+  // tf.nn.dropout: binary = floor(keep_prob + uniform[0,1)); y = x / keep_prob * binary
+  const uint4 r = philox4x32_10(make_uint4((unsigned)(idx >> 2), (unsigned)(idx >> 34), (unsigned)dd.offset,
+                                           (unsigned)(dd.offset >> 32)),
+                                make_uint2((unsigned)dd.seed, (unsigned)(dd.seed >> 32)));
+  const unsigned lane = (unsigned)(idx & 3);
+  const unsigned bits = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
+  const float u = __uint_as_float((bits & 0x7fffffu) | 0x3f800000u) - 1.0f;
+  return floorf(dd.keep_prob + u) >= 1.0f ? 1.0f / dd.keep_prob : 0.0f;
+}
+
+__global__ void fc_fwd_kernel(int n, int cin, int cout, const float* __restrict__ x, const float* __restrict__ w,
+                              const float* __restrict__ b, int relu, bsl_dropout_desc dd, int use_dropout,
+                              float* __restrict__ y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * cout) return;
+  const int s = i / cout, co = i - s * cout;
+  float acc = b ? b[co] : 0.f;
+  const float* xr = x + (long long)s * cin;
+  for (int ci = 0; ci < cin; ++ci) acc = fmaf(xr[ci], w[(long long)ci * cout + co], acc);
+  if (relu) acc = fmaxf(acc, 0.f);
+  if (use_dropout) acc *= dropout_scale(dd, (unsigned long long)i);
+  y[i] = acc;
+}
+
+// dpre = dy * d(out)/d(pre): out = relu(pre) * mask / keep, so out > 0 <=> (pre > 0 and kept).
+__global__ void fc_dpre_kernel(int total, const float* __restrict__ y, const float* __restrict__ dy, int relu,
+                               float inv_keep, float* __restrict__ dpre) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  float g = dy[i];
+  if (relu) g = y[i] > 0.f ? g * inv_keep : 0.f;
+  dpre[i] = g;
+}
+
+__global__ void fc_dw_kernel(int n, int cin, int cout, const float* __restrict__ x, const float* __restrict__ dpre,
+                             float* __restrict__ dw, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (cin + 1) * cout) return;
+  const int ci = i / cout, co = i - ci * cout;
+  float acc = 0.f;
+  if (ci < cin) {
+    for (int s = 0; s < n; ++s) acc = fmaf(x[(long long)s * cin + ci], dpre[(long long)s * cout + co], acc);
+    dw[i] = acc;
+  } else if (db) {
+    for (int s = 0; s < n; ++s) acc += dpre[(long long)s * cout + co];
+    db[co] = acc;
+  }
+}
+
+// one warp per (sample, input feature): lanes stride over cout (coalesced rows of w), shuffle tree at the end
+__global__ void fc_dx_kernel(int n, int cin, int cout, const float* __restrict__ dpre, const float* __restrict__ w,
+                             float* __restrict__ dx) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= n * cin) return;
+  const int s = warp / cin, ci = warp - s * cin;
+  float acc = 0.f;
+  for (int co = lane; co < cout; co += 32) acc = fmaf(dpre[(long long)s * cout + co], w[(long long)ci * cout + co], acc);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) dx[warp] = acc;
+}
+
+__global__ void avgpool2x2_f32_kernel(int n, int h, int w, int c, const float* __restrict__ x, float* __restrict__ y) {
+  const int ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * ho * wo * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int ch = (int)(t % c); t /= c;
+    const int xo = (int)(t % wo); t /= wo;
+    const int yo = (int)(t % ho);
+    const int s = (int)(t / ho);
+    const float* p = x + (((long long)s * h + 2 * yo) * w + 2 * xo) * c + ch;
+    y[i] = ((p[0] + p[c]) + (p[(long long)w * c] + p[(long long)w * c + c])) * 0.25f;
+  }
+}
+
+__global__ void dropout_mask_kernel(int total, bsl_dropout_desc dd, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) out[i] = dropout_scale(dd, (unsigned long long)i);
+}
+
+int check_fc(bsl_ctx* ctx, const bsl_fc_desc* d) {
+  if (!ctx) return BSL_EINVAL;
+  if (!d) return bsl_fail(ctx, BSL_EINVAL, "fc: null descriptor");
+  if (d->n <= 0 || d->cin <= 0 || d->cout <= 0) return bsl_fail(ctx, BSL_EINVAL, "fc: non-positive size");
+  if (d->use_dropout && !(d->dropout.keep_prob > 0.f && d->dropout.keep_prob <= 1.f))
+    return bsl_fail(ctx, BSL_EINVAL, "fc: keep_prob %f outside (0, 1]", d->dropout.keep_prob);
+  if (d->use_dropout && !d->relu)
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "fc: dropout is only defined after the ReLU layers of slim_nets.mlp");
+  return BSL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bsl_fc_fwd(bsl_ctx* ctx, const bsl_fc_desc* d, const float* x, const float* w, const float* bias, float* y,
+               void* stream) {
+  int rc = check_fc(ctx, d);
+  if (rc) return rc;
+  if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "fc_fwd: null buffer");
+  const int total = d->n * d->cout;
+  fc_fwd_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(d->n, d->cin, d->cout, x, w, bias, d->relu,
+                                                                   d->dropout, d->use_dropout, y);
+  BSL_LAUNCH_CHECK(ctx, "fc_fwd_kernel");
+  return BSL_OK;
+}
+
+size_t bsl_fc_bwd_workspace(bsl_ctx* ctx, const bsl_fc_desc* d) {
+  if (!ctx || !d || check_fc(ctx, d)) return 0;
+  return (size_t)d->n * d->cout * sizeof(float);
+}
+
+int bsl_fc_bwd(bsl_ctx* ctx, const bsl_fc_desc* d, const float* x, const float* w, const float* y, const float* dy,
+               float* dx, float* dw, float* dbias, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_fc(ctx, d);
+  if (rc) return rc;
+  if (!x || !w || !y || !dy || !dw) return bsl_fail(ctx, BSL_EINVAL, "fc_bwd: null buffer");
+  const size_t need = (size_t)d->n * d->cout * sizeof(float);
+  if (!workspace || workspace_bytes < need)
+    return bsl_fail(ctx, BSL_EWORKSPACE, "fc_bwd: workspace %zu < %zu", workspace_bytes, need);
+  float* dpre = reinterpret_cast<float*>(workspace);
+  cudaStream_t s = as_stream(stream);
+  const int total = d->n * d->cout;
+  fc_dpre_kernel<<<(total + 255) / 256, 256, 0, s>>>(total, y, dy, d->relu,
+                                                     d->use_dropout ? 1.0f / d->dropout.keep_prob : 1.0f, dpre);
+  BSL_LAUNCH_CHECK(ctx, "fc_dpre_kernel");
+  const int nw = (d->cin + 1) * d->cout;
+  fc_dw_kernel<<<(nw + 127) / 128, 128, 0, s>>>(d->n, d->cin, d->cout, x, dpre, dw, dbias);
+  BSL_LAUNCH_CHECK(ctx, "fc_dw_kernel");
+  if (dx) {
+    const long long threads = (long long)d->n * d->cin * 32;
+    fc_dx_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(d->n, d->cin, d->cout, dpre, w, dx);
+    BSL_LAUNCH_CHECK(ctx, "fc_dx_kernel");
+  }
+  return BSL_OK;
+}
+
+int bsl_dropout_mask(bsl_ctx* ctx, const bsl_dropout_desc* d, size_t n, float* out, void* stream) {
+  if (!ctx) return BSL_EINVAL;
+  if (!d || !out || !(d->keep_prob > 0.f && d->keep_prob <= 1.f) || n > 0x7fffffffu)
+    return bsl_fail(ctx, BSL_EINVAL, "dropout_mask: bad argument");
+  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>((int)n, *d, out);
+  BSL_LAUNCH_CHECK(ctx, "dropout_mask_kernel");
+  return BSL_OK;
+}
+
+int bsl_avgpool2x2_f32(bsl_ctx* ctx, int n, int h, int w, int c, const float* x, float* y, void* stream) {
+  if (!ctx) return BSL_EINVAL;
+  if (!x || !y) return bsl_fail(ctx, BSL_EINVAL, "avgpool2x2: null buffer");
+  if (n <= 0 || c <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1))
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "avgpool2x2: h=%d w=%d must be even (SAME == VALID then)", h, w);
+  const long long total = (long long)n * (h / 2) * (w / 2) * c;
+  long long blocks = (total + 255) / 256;
+  const long long cap = 16LL * ctx->sm_count;
+  if (blocks > cap) blocks = cap;
+  avgpool2x2_f32_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(n, h, w, c, x, y);
+  BSL_LAUNCH_CHECK(ctx, "avgpool2x2_f32_kernel");
+  return BSL_OK;
+}
+
+}  // extern "C"

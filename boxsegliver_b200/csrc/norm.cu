@@ -67,7 +67,7 @@ struct StatsF {
   int ld;
   __device__ void init(State&, int, int) const {}
   __device__ void load(long long p, int ch0, uint4 (&raw)[1]) const { raw[0] = ld16(y + p * ld + ch0); }
-  __device__ void accum(const State&, const uint4 (&raw)[1], float (&acc)[2][8]) const {
+  __device__ void accum(const State&, long long, const uint4 (&raw)[1], float (&acc)[2][8]) const {
     float v[8];
     unpack8(raw[0], v);
 #pragma unroll
@@ -78,11 +78,18 @@ struct StatsF {
   }
 };
 
-struct BwdF {
-  static constexpr int K = 2, NIN = 2, UNROLL = 4;
+// G = channels of the additive spatial-guide map (GUNet modulated_conv_block, NetworksV2/GUNet.py:205-210):
+// z += sum_g guide[p][g] * wsp[g][c]; the extra K rows are sum(dz * guide_g) (gradient of the 1x1 guide conv).
+template <int G>
+struct BwdFG {
+  static constexpr int K = 2 + G, NIN = 2, UNROLL = 4;
   struct State {
     float scale[8], shift[8], rstd[8], mrstd[8];
+    float wsp[G ? G : 1][8];
   };
+  const float* guide;
+  const float* wsp;
+  int wsp_ld;
   const __nv_bfloat16* y;
   const __nv_bfloat16* da;
   const float* mean;
@@ -98,26 +105,35 @@ struct BwdF {
       st.shift[j] = shift[o + j];
       st.rstd[j] = rstd[o + j];
       st.mrstd[j] = mean[o + j] * rstd[o + j];
+#pragma unroll
+      for (int q = 0; q < G; ++q) st.wsp[q][j] = wsp[q * wsp_ld + ch0 + j];
     }
   }
   __device__ void load(long long p, int ch0, uint4 (&raw)[2]) const {
     raw[0] = ld16(y + p * y_ld + ch0);
     raw[1] = ld16(da + p * da_ld + ch0);
   }
-  __device__ void accum(const State& st, const uint4 (&raw)[2], float (&acc)[2][8]) const {
-    float v[8], g[8];
+  __device__ void accum(const State& st, long long p, const uint4 (&raw)[2], float (&acc)[2 + G][8]) const {
+    float v[8], g[8], gm[G ? G : 1];
     unpack8(raw[0], v);
     unpack8(raw[1], g);
 #pragma unroll
+    for (int q = 0; q < G; ++q) gm[q] = __ldg(guide + p * G + q);
+#pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(v[j], st.scale[j], st.shift[j]);
+      float z = fmaf(v[j], st.scale[j], st.shift[j]);
+#pragma unroll
+      for (int q = 0; q < G; ++q) z = fmaf(gm[q], st.wsp[q][j], z);
       const float dz = (!relu || z > 0.f) ? g[j] : 0.f;
       const float xh = fmaf(v[j], st.rstd[j], -st.mrstd[j]);
       acc[0][j] += dz;
       acc[1][j] = fmaf(dz, xh, acc[1][j]);
+#pragma unroll
+      for (int q = 0; q < G; ++q) acc[2 + q][j] = fmaf(dz, gm[q], acc[2 + q][j]);
     }
   }
 };
+using BwdF = BwdFG<0>;
 
 __global__ void norm_finalize_kernel(int groups, int c, double m, float eps, float decay, int bn_training,
                                      int use_moving, int center, int scale_flag, const double* __restrict__ sums,
@@ -157,32 +173,46 @@ __global__ void norm_finalize_kernel(int groups, int c, double m, float eps, flo
 // keeps 4 independent 16 B loads in flight. grid.y = sample index when parameters are per sample.
 constexpr int EW_UNROLL = 4;
 
+template <int G>
 __global__ void norm_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, __nv_bfloat16* __restrict__ a,
                                   int a_ld, long long pixels_per_group, int c, int relu,
-                                  const float* __restrict__ scale, const float* __restrict__ shift) {
+                                  const float* __restrict__ scale, const float* __restrict__ shift,
+                                  const float* __restrict__ guide, const float* __restrict__ wsp, int wsp_ld) {
   const int cg = c / 8;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
   if (r >= rows) return;
   const int ch0 = g * 8;
   const int o = blockIdx.y * c + ch0;
-  float sc[8], sh[8];
+  float sc[8], sh[8], ws[G ? G : 1][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { sc[j] = scale[o + j]; sh[j] = shift[o + j]; }
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[o + j];
+    sh[j] = shift[o + j];
+#pragma unroll
+    for (int q = 0; q < G; ++q) ws[q][j] = wsp[q * wsp_ld + ch0 + j];
+  }
   const long long base = (long long)blockIdx.y * pixels_per_group;
   const long long stride = (long long)gridDim.x * rows;
   long long p = (long long)blockIdx.x * rows + r;
   for (; p + (EW_UNROLL - 1) * stride < pixels_per_group; p += EW_UNROLL * stride) {
     uint4 raw[EW_UNROLL];
+    float gm[EW_UNROLL][G ? G : 1];
 #pragma unroll
-    for (int u = 0; u < EW_UNROLL; ++u) raw[u] = ld16(y + (base + p + u * stride) * y_ld + ch0);
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      raw[u] = ld16(y + (base + p + u * stride) * y_ld + ch0);
+#pragma unroll
+      for (int q = 0; q < G; ++q) gm[u][q] = __ldg(guide + (base + p + u * stride) * G + q);
+    }
 #pragma unroll
     for (int u = 0; u < EW_UNROLL; ++u) {
       float v[8];
       unpack8(raw[u], v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(v[j], sc[j], sh[j]);
+        float z = fmaf(v[j], sc[j], sh[j]);
+#pragma unroll
+        for (int q = 0; q < G; ++q) z = fmaf(gm[u][q], ws[q][j], z);
         v[j] = relu ? fmaxf(z, 0.f) : z;
       }
       st16(a + (base + p + u * stride) * a_ld + ch0, pack8(v));
@@ -193,7 +223,9 @@ __global__ void norm_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld,
     unpack8(ld16(y + (base + p) * y_ld + ch0), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(v[j], sc[j], sh[j]);
+      float z = fmaf(v[j], sc[j], sh[j]);
+#pragma unroll
+      for (int q = 0; q < G; ++q) z = fmaf(__ldg(guide + (base + p) * G + q), ws[q][j], z);
       v[j] = relu ? fmaxf(z, 0.f) : z;
     }
     st16(a + (base + p) * a_ld + ch0, pack8(v));
@@ -202,10 +234,12 @@ __global__ void norm_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld,
 
 // Same as norm_apply_kernel, and also emits the 2x2/s2 max-pooled tensor from the same read.
 // "pixels" here are pooled pixels of one sample (grid.y = sample).
+template <int G>
 __global__ void norm_apply_pool_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, __nv_bfloat16* __restrict__ a,
                                        int a_ld, __nv_bfloat16* __restrict__ pooled, int p_ld, int h, int w, int c,
                                        int per_sample, int relu, const float* __restrict__ scale,
-                                       const float* __restrict__ shift) {
+                                       const float* __restrict__ shift, const float* __restrict__ guide,
+                                       const float* __restrict__ wsp, int wsp_ld) {
   const int cg = c / 8, ho = h / 2, wo = w / 2;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -213,18 +247,26 @@ __global__ void norm_apply_pool_kernel(const __nv_bfloat16* __restrict__ y, int 
   const int ch0 = g * 8;
   const int img = blockIdx.y;
   const int o = (per_sample ? img * c : 0) + ch0;
-  float sc[8], sh[8];
+  float sc[8], sh[8], ws[G ? G : 1][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { sc[j] = scale[o + j]; sh[j] = shift[o + j]; }
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[o + j];
+    sh[j] = shift[o + j];
+#pragma unroll
+    for (int q = 0; q < G; ++q) ws[q][j] = wsp[q * wsp_ld + ch0 + j];
+  }
   const long long in0 = (long long)img * h * w, out0 = (long long)img * ho * wo;
   for (int q = blockIdx.x * rows + r; q < ho * wo; q += gridDim.x * rows) {
     const int yo = q / wo, xo = q - yo * wo;
     long long pix[4];
     uint4 raw[4];
+    float gm[4][G ? G : 1];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       pix[k] = in0 + (long long)(2 * yo + (k >> 1)) * w + (2 * xo + (k & 1));
       raw[k] = ld16(y + pix[k] * y_ld + ch0);
+#pragma unroll
+      for (int q = 0; q < G; ++q) gm[k][q] = __ldg(guide + pix[k] * G + q);
     }
     float mx[8];
 #pragma unroll
@@ -235,7 +277,9 @@ __global__ void norm_apply_pool_kernel(const __nv_bfloat16* __restrict__ y, int 
       unpack8(raw[k], v);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(v[j], sc[j], sh[j]);
+        float z = fmaf(v[j], sc[j], sh[j]);
+#pragma unroll
+        for (int q = 0; q < G; ++q) z = fmaf(gm[k][q], ws[q][j], z);
         v[j] = relu ? fmaxf(z, 0.f) : z;
       }
       const uint4 packed = pack8(v);
@@ -269,12 +313,14 @@ __global__ void norm_bwd_finalize_kernel(int groups, int c, double m, const doub
   (void)rstd_unused;
 }
 
+template <int G>
 __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld,
                                       const __nv_bfloat16* __restrict__ da, int da_ld,
                                       __nv_bfloat16* __restrict__ dy, int dy_ld, long long pixels_per_group, int c,
                                       int relu, const float* __restrict__ mean, const float* __restrict__ rstd,
                                       const float* __restrict__ scale, const float* __restrict__ shift,
-                                      const float* __restrict__ c1, const float* __restrict__ c2) {
+                                      const float* __restrict__ c1, const float* __restrict__ c2,
+                                      const float* __restrict__ guide, const float* __restrict__ wsp, int wsp_ld) {
   const int cg = c / 8;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -282,11 +328,13 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y
   const int ch0 = g * 8;
   const int o = blockIdx.y * c + ch0;
   // dy = scale*(dz - c1 - xhat*c2), xhat = (v - mean)*rstd  ==  scale*dz + k1*v + k0
-  float sc[8], sh[8], k1[8], k0[8];
+  float sc[8], sh[8], k1[8], k0[8], ws[G ? G : 1][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     sc[j] = scale[o + j];
     sh[j] = shift[o + j];
+#pragma unroll
+    for (int q = 0; q < G; ++q) ws[q][j] = wsp[q * wsp_ld + ch0 + j];
     const float t = sc[j] * c2[o + j] * rstd[o + j];
     k1[j] = -t;
     k0[j] = fmaf(t, mean[o + j], -sc[j] * c1[o + j]);
@@ -297,10 +345,13 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y
   constexpr int U = 2;
   for (; p + (U - 1) * stride < pixels_per_group; p += U * stride) {
     uint4 ry[U], rg[U];
+    float gm[U][G ? G : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       ry[u] = ld16(y + (base + p + u * stride) * y_ld + ch0);
       rg[u] = ld16(da + (base + p + u * stride) * da_ld + ch0);
+#pragma unroll
+      for (int q = 0; q < G; ++q) gm[u][q] = __ldg(guide + (base + p + u * stride) * G + q);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -309,7 +360,9 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y
       unpack8(rg[u], gg);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float z = fmaf(v[j], sc[j], sh[j]);
+        float z = fmaf(v[j], sc[j], sh[j]);
+#pragma unroll
+        for (int q = 0; q < G; ++q) z = fmaf(gm[u][q], ws[q][j], z);
         const float dz = (!relu || z > 0.f) ? gg[j] : 0.f;
         v[j] = fmaf(sc[j], dz, fmaf(k1[j], v[j], k0[j]));
       }
@@ -322,12 +375,56 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y
     unpack8(ld16(da + (base + p) * da_ld + ch0), gg);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float z = fmaf(v[j], sc[j], sh[j]);
+      float z = fmaf(v[j], sc[j], sh[j]);
+#pragma unroll
+      for (int q = 0; q < G; ++q) z = fmaf(__ldg(guide + (base + p) * G + q), ws[q][j], z);
       const float dz = (!relu || z > 0.f) ? gg[j] : 0.f;
       v[j] = fmaf(sc[j], dz, fmaf(k1[j], v[j], k0[j]));
     }
     st16(dy + (base + p) * dy_ld + ch0, pack8(v));
   }
+}
+
+// GUNet density modulation folded into the per-(sample, channel) affine of an instance-norm layer
+// (conditional_normalization, NetworksV2/GUNet.py:119-133,193-204): z*gm + bias_sp == y*(sc*gm) + (sh*gm + bias_sp).
+__global__ void norm_modulate_kernel(int n, int c, const float* __restrict__ gamma_mod, int gm_ld,
+                                     const float* __restrict__ sp_bias, float* __restrict__ scale,
+                                     float* __restrict__ shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * c) return;
+  const int s = i / c, ch = i - s * c;
+  const float gm = gamma_mod ? gamma_mod[(long long)s * gm_ld + ch] : 1.f;
+  scale[i] *= gm;
+  shift[i] = fmaf(shift[i], gm, sp_bias ? sp_bias[ch] : 0.f);
+}
+
+// Backward scalars of a modulated instance-norm layer. sums[n][K][c]: S0 = sum dz, S1 = sum dz*xhat, T_g = sum dz*guide_g.
+__global__ void norm_bwd_finalize_mod_kernel(int n, int c, int K, double m, const double* __restrict__ sums,
+                                             const float* __restrict__ gamma_mod, int gm_ld,
+                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                             float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
+                                             float* __restrict__ dbeta, float* __restrict__ dgamma_mod,
+                                             float* __restrict__ dw_guide, int dw_ld, float* __restrict__ dbias_guide) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double ga = gamma ? (double)gamma[ch] : 1.0, be = beta ? (double)beta[ch] : 0.0;
+  double sg = 0.0, sb = 0.0, s0all = 0.0, t[2] = {0.0, 0.0};
+  for (int s = 0; s < n; ++s) {  // fixed order
+    const double* q = sums + (long long)s * K * c + ch;
+    const double s0 = q[0], s1 = q[c];
+    c1[s * c + ch] = (float)(s0 / m);
+    c2[s * c + ch] = (float)(s1 / m);
+    const double gm = gamma_mod ? (double)gamma_mod[(long long)s * gm_ld + ch] : 1.0;
+    if (dgamma_mod) dgamma_mod[(long long)s * gm_ld + ch] = (float)(ga * s1 + be * s0);
+    sg += gm * s1;
+    sb += gm * s0;
+    s0all += s0;
+    for (int g = 0; g < K - 2; ++g) t[g] += q[(long long)(2 + g) * c];
+  }
+  if (dgamma) dgamma[ch] = (float)sg;
+  if (dbeta) dbeta[ch] = (float)sb;
+  for (int g = 0; g < K - 2; ++g) dw_guide[g * dw_ld + ch] = (float)t[g];
+  if (dbias_guide) dbias_guide[ch] = (float)s0all;
 }
 
 // da[n,2i+a,2j+b,:] = dskip (optional) + (first max of the window in scan order ? dpool[n,i,j,:] : 0)
@@ -489,48 +586,111 @@ int bsl_norm_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, int is_training, con
   return BSL_OK;
 }
 
-int bsl_norm_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const float* scale, const float* shift,
-                   void* y, void* stream) {
+static int check_guide(bsl_ctx* ctx, const bsl_norm_desc* d, const bsl_guide* g, int* G) {
+  *G = 0;
+  if (!g || !g->map) return BSL_OK;
+  if (d->mode != 1) return bsl_fail(ctx, BSL_EUNSUPPORTED, "guide modulation is implemented for instance_norm layers");
+  if (g->channels < 1 || g->channels > 2 || !g->w || g->w_ld < d->c)
+    return bsl_fail(ctx, BSL_EINVAL, "guide: channels=%d (1 or 2), w_ld=%d >= c", g->channels, g->w_ld);
+  *G = g->channels;
+  return BSL_OK;
+}
+
+int bsl_norm_apply_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const float* scale, const float* shift,
+                       const bsl_guide* guide, void* y, void* stream) {
   int rc = check_norm(ctx, d);
   if (rc) return rc;
   if (!x || !scale || !shift || !y) return bsl_fail(ctx, BSL_EINVAL, "norm_apply: null buffer");
+  int G;
+  if ((rc = check_guide(ctx, d, guide, &G))) return rc;
   const int groups = d->mode ? d->n : 1;
   const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
   const EwPlan pl = ew_plan(ctx, ppg, groups, d->c, EW_UNROLL);
-  norm_apply_kernel<<<dim3(pl.blocks, groups), pl.threads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld, reinterpret_cast<__nv_bfloat16*>(y), d->y_ld, ppg, d->c,
-      d->relu, scale, shift);
+  const dim3 grid(pl.blocks, groups);
+  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto yb = reinterpret_cast<__nv_bfloat16*>(y);
+  cudaStream_t s = as_stream(stream);
+  if (G == 0)
+    norm_apply_kernel<0><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
+                                                     nullptr, nullptr, 0);
+  else if (G == 1)
+    norm_apply_kernel<1><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
+                                                     guide->map, guide->w, guide->w_ld);
+  else
+    norm_apply_kernel<2><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
+                                                     guide->map, guide->w, guide->w_ld);
   BSL_LAUNCH_CHECK(ctx, "norm_apply_kernel");
   return BSL_OK;
 }
 
-int bsl_norm_apply_pool(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, const void* x, const float* scale,
-                        const float* shift, void* y, void* pooled, int pooled_ld, void* stream) {
+int bsl_norm_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const float* scale, const float* shift,
+                   void* y, void* stream) {
+  return bsl_norm_apply_mod(ctx, d, x, scale, shift, nullptr, y, stream);
+}
+
+int bsl_norm_apply_pool_mod(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, const void* x, const float* scale,
+                            const float* shift, const bsl_guide* guide, void* y, void* pooled, int pooled_ld,
+                            void* stream) {
   int rc = check_norm(ctx, d);
   if (rc) return rc;
   if (!x || !scale || !shift || !y || !pooled) return bsl_fail(ctx, BSL_EINVAL, "norm_apply_pool: null buffer");
   if (h * w != d->hw || (h & 1) || (w & 1) || pooled_ld < d->c || pooled_ld % 8)
     return bsl_fail(ctx, BSL_EINVAL, "norm_apply_pool: h=%d w=%d must be even and match hw=%d", h, w, d->hw);
+  int G;
+  if ((rc = check_guide(ctx, d, guide, &G))) return rc;
   const EwPlan pl = ew_plan(ctx, (long long)(h / 2) * (w / 2), d->n, d->c, 1);
-  norm_apply_pool_kernel<<<dim3(pl.blocks, d->n), pl.threads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld, reinterpret_cast<__nv_bfloat16*>(y), d->y_ld,
-      reinterpret_cast<__nv_bfloat16*>(pooled), pooled_ld, h, w, d->c, d->mode, d->relu, scale, shift);
+  const dim3 grid(pl.blocks, d->n);
+  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto yb = reinterpret_cast<__nv_bfloat16*>(y);
+  auto pb = reinterpret_cast<__nv_bfloat16*>(pooled);
+  cudaStream_t s = as_stream(stream);
+  if (G == 0)
+    norm_apply_pool_kernel<0><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, pb, pooled_ld, h, w, d->c, d->mode,
+                                                          d->relu, scale, shift, nullptr, nullptr, 0);
+  else if (G == 1)
+    norm_apply_pool_kernel<1><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, pb, pooled_ld, h, w, d->c, d->mode,
+                                                          d->relu, scale, shift, guide->map, guide->w, guide->w_ld);
+  else
+    norm_apply_pool_kernel<2><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, pb, pooled_ld, h, w, d->c, d->mode,
+                                                          d->relu, scale, shift, guide->map, guide->w, guide->w_ld);
   BSL_LAUNCH_CHECK(ctx, "norm_apply_pool_kernel");
   return BSL_OK;
+}
+
+int bsl_norm_apply_pool(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, const void* x, const float* scale,
+                        const float* shift, void* y, void* pooled, int pooled_ld, void* stream) {
+  return bsl_norm_apply_pool_mod(ctx, d, h, w, x, scale, shift, nullptr, y, pooled, pooled_ld, stream);
+}
+
+int bsl_norm_bwd_reduce_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
+                            const float* mean, const float* rstd, const float* scale, const float* shift,
+                            const bsl_guide* guide, double* sums, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (!x || !dy || !mean || !rstd || !scale || !shift || !sums)
+    return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_reduce: null buffer");
+  int G;
+  if ((rc = check_guide(ctx, d, guide, &G))) return rc;
+  const int groups = d->mode ? d->n : 1;
+  const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
+  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto db = reinterpret_cast<const __nv_bfloat16*>(dy);
+  if (G == 0) {
+    BwdFG<0> f{nullptr, nullptr, 0, xb, db, mean, rstd, scale, shift, d->x_ld, dy_ld, d->c, d->relu};
+    return run_pixel_reduce(ctx, f, ppg, groups, d->c, sums, as_stream(stream));
+  }
+  if (G == 1) {
+    BwdFG<1> f{guide->map, guide->w, guide->w_ld, xb, db, mean, rstd, scale, shift, d->x_ld, dy_ld, d->c, d->relu};
+    return run_pixel_reduce(ctx, f, ppg, groups, d->c, sums, as_stream(stream));
+  }
+  BwdFG<2> f{guide->map, guide->w, guide->w_ld, xb, db, mean, rstd, scale, shift, d->x_ld, dy_ld, d->c, d->relu};
+  return run_pixel_reduce(ctx, f, ppg, groups, d->c, sums, as_stream(stream));
 }
 
 int bsl_norm_bwd_reduce(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
                         const float* mean, const float* rstd, const float* scale, const float* shift,
                         double* sums, void* stream) {
-  int rc = check_norm(ctx, d);
-  if (rc) return rc;
-  if (!x || !dy || !mean || !rstd || !scale || !shift || !sums)
-    return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_reduce: null buffer");
-  BwdF f{reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(dy), mean, rstd, scale,
-         shift, d->x_ld, dy_ld, d->c, d->relu};
-  const int groups = d->mode ? d->n : 1;
-  const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
-  return run_pixel_reduce(ctx, f, ppg, groups, d->c, sums, as_stream(stream));
+  return bsl_norm_bwd_reduce_mod(ctx, d, x, dy, dy_ld, mean, rstd, scale, shift, nullptr, sums, stream);
 }
 
 int bsl_norm_bwd_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, const double* sums, float* c1, float* c2,
@@ -546,21 +706,71 @@ int bsl_norm_bwd_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, const double* su
   return BSL_OK;
 }
 
-int bsl_norm_bwd_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
-                       const float* mean, const float* rstd, const float* scale, const float* shift,
-                       const float* c1, const float* c2, void* dx, int dx_ld, void* stream) {
+int bsl_norm_modulate(bsl_ctx* ctx, const bsl_norm_desc* d, const float* gamma_mod, int gm_ld, const float* sp_bias,
+                      float* scale, float* shift, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (d->mode != 1) return bsl_fail(ctx, BSL_EUNSUPPORTED, "norm_modulate: instance_norm layers only");
+  if (!scale || !shift || (gamma_mod && gm_ld < d->c)) return bsl_fail(ctx, BSL_EINVAL, "norm_modulate: bad argument");
+  const int total = d->n * d->c;
+  norm_modulate_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(d->n, d->c, gamma_mod, gm_ld, sp_bias, scale,
+                                                                         shift);
+  BSL_LAUNCH_CHECK(ctx, "norm_modulate_kernel");
+  return BSL_OK;
+}
+
+int bsl_norm_bwd_finalize_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const double* sums, int guide_channels,
+                              const float* gamma_mod, int gm_ld, const float* gamma, const float* beta, float* c1,
+                              float* c2, float* dgamma, float* dbeta, float* dgamma_mod, float* dw_guide, int dw_ld,
+                              float* dbias_guide, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (d->mode != 1) return bsl_fail(ctx, BSL_EUNSUPPORTED, "norm_bwd_finalize_mod: instance_norm layers only");
+  if (!sums || !c1 || !c2 || guide_channels < 0 || guide_channels > 2 || (gamma_mod && !dgamma_mod) ||
+      (guide_channels && (!dw_guide || dw_ld < d->c)))
+    return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_finalize_mod: bad argument");
+  norm_bwd_finalize_mod_kernel<<<(d->c + 127) / 128, 128, 0, as_stream(stream)>>>(
+      d->n, d->c, 2 + guide_channels, (double)d->hw, sums, gamma_mod, gm_ld, d->scale ? gamma : nullptr,
+      d->center ? beta : nullptr, c1, c2, dgamma, dbeta, dgamma_mod, dw_guide, dw_ld, dbias_guide);
+  BSL_LAUNCH_CHECK(ctx, "norm_bwd_finalize_mod_kernel");
+  return BSL_OK;
+}
+
+int bsl_norm_bwd_apply_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
+                           const float* mean, const float* rstd, const float* scale, const float* shift,
+                           const float* c1, const float* c2, const bsl_guide* guide, void* dx, int dx_ld,
+                           void* stream) {
   int rc = check_norm(ctx, d);
   if (rc) return rc;
   if (!x || !dy || !mean || !rstd || !scale || !shift || !c1 || !c2 || !dx)
     return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_apply: null buffer");
+  int G;
+  if ((rc = check_guide(ctx, d, guide, &G))) return rc;
   const int groups = d->mode ? d->n : 1;
   const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
   const EwPlan pl = ew_plan(ctx, ppg, groups, d->c, 2);
-  norm_bwd_apply_kernel<<<dim3(pl.blocks, groups), pl.threads, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld, reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld,
-      reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, ppg, d->c, d->relu, mean, rstd, scale, shift, c1, c2);
+  const dim3 grid(pl.blocks, groups);
+  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto db = reinterpret_cast<const __nv_bfloat16*>(dy);
+  auto ob = reinterpret_cast<__nv_bfloat16*>(dx);
+  cudaStream_t s = as_stream(stream);
+  if (G == 0)
+    norm_bwd_apply_kernel<0><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
+                                                         rstd, scale, shift, c1, c2, nullptr, nullptr, 0);
+  else if (G == 1)
+    norm_bwd_apply_kernel<1><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
+                                                         rstd, scale, shift, c1, c2, guide->map, guide->w, guide->w_ld);
+  else
+    norm_bwd_apply_kernel<2><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
+                                                         rstd, scale, shift, c1, c2, guide->map, guide->w, guide->w_ld);
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_apply_kernel");
   return BSL_OK;
+}
+
+int bsl_norm_bwd_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
+                       const float* mean, const float* rstd, const float* scale, const float* shift,
+                       const float* c1, const float* c2, void* dx, int dx_ld, void* stream) {
+  return bsl_norm_bwd_apply_mod(ctx, d, x, dy, dy_ld, mean, rstd, scale, shift, c1, c2, nullptr, dx, dx_ld, stream);
 }
 
 int bsl_maxpool2x2_bwd_add(bsl_ctx* ctx, int n, int h, int w, int c, const void* act, int act_ld,

@@ -55,7 +55,7 @@ struct SumF {
   int ld;
   __device__ void init(State&, int, int) const {}
   __device__ void load(long long p, int ch0, uint4 (&raw)[1]) const { raw[0] = bsl::ld16(x + p * ld + ch0); }
-  __device__ void accum(const State&, const uint4 (&raw)[1], float (&acc)[1][8]) const {
+  __device__ void accum(const State&, long long, const uint4 (&raw)[1], float (&acc)[1][8]) const {
     float v[8];
     bsl::unpack8(raw[0], v);
 #pragma unroll

@@ -36,7 +36,7 @@ __device__ __forceinline__ void st16(__nv_bfloat16* p, const uint4& v) { *reinte
 // F must provide: static constexpr int K; a nested `struct State` of per-thread registers;
 //   __device__ void init(State&, int group, int ch0) const          -- hoists per-channel parameters
 //   __device__ void load(long long pixel, int ch0, uint4 (&raw)[NIN]) const, with static constexpr int NIN
-//   __device__ void accum(const State&, const uint4 (&raw)[NIN], float (&acc)[K][8]) const
+//   __device__ void accum(const State&, long long pixel, const uint4 (&raw)[NIN], float (&acc)[K][8]) const
 // Loads of UNROLL pixels are issued before any is consumed (memory-level parallelism).
 template <class F, int UNROLL>
 __global__ void pixel_reduce_kernel(F f, long long pixels_per_group, long long ppb, int c,
@@ -66,12 +66,12 @@ __global__ void pixel_reduce_kernel(F f, long long pixels_per_group, long long p
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u) f.load(base + p + (long long)u * rows, g * 8, raw[u]);
 #pragma unroll
-      for (int u = 0; u < UNROLL; ++u) f.accum(st, raw[u], acc);
+      for (int u = 0; u < UNROLL; ++u) f.accum(st, base + p + (long long)u * rows, raw[u], acc);
     }
     for (; p < p1; p += rows) {
       uint4 raw[NIN];
       f.load(base + p, g * 8, raw);
-      f.accum(st, raw, acc);
+      f.accum(st, base + p, raw, acc);
     }
 #pragma unroll
     for (int k = 0; k < K; ++k)

@@ -249,7 +249,7 @@ struct HeadWgradF {
     for (int k = 0; k < COUT; ++k) d[k] = __ldg(dl + p * COUT + k);
     raw[1] = make_uint4(__float_as_uint(d[0]), __float_as_uint(d[1]), __float_as_uint(d[2]), __float_as_uint(d[3]));
   }
-  __device__ void accum(const State&, const uint4 (&raw)[2], float (&acc)[COUT][8]) const {
+  __device__ void accum(const State&, long long, const uint4 (&raw)[2], float (&acc)[COUT][8]) const {
     float v[8];
     unpack8(raw[0], v);
     const float d[4] = {__uint_as_float(raw[1].x), __uint_as_float(raw[1].y), __uint_as_float(raw[1].z),

@@ -95,6 +95,11 @@ class ConvL:
     h: int
     w: int                   # INPUT spatial size
     level: int
+    role: str = ""           # enc1 | enc2 (pooled afterwards) | bridge1 | bridge2 | dec1 (reads the concat) | dec2
+    center: bool = True      # normaliser has beta / gamma (GUNet's modulated blocks take them from the YAML)
+    scale: bool = True
+    mod_off: int = None      # GUNet: first column of this layer's slice of the context-MLP output
+    sp_off: int = None       # GUNet: first column of this layer's slice of the level's 1x1 guide conv
     x: View = None
     y: View = None           # pre-norm conv output (conv/stem), or output (convT)
     a: View = None           # post-activation
@@ -117,7 +122,7 @@ class UNetEngine:
         ds = 2 ** cfg.num_down_samples
         if cfg.height % ds or cfg.width % ds:
             raise ValueError(f"height/width must be multiples of {ds}")
-        if cfg.loss_type not in ("xentropy", "dice"):
+        if not self._loss_terms():
             raise ValueError("Not supported loss_type: {}".format(cfg.loss_type))  # UNet.py:132
         if cfg.loss_weight_type not in ("none", "numerical", "proportion"):
             raise ValueError("Not supported weight type: " + cfg.loss_weight_type)
@@ -205,13 +210,14 @@ class UNetEngine:
         for i in range(cfg.num_down_samples):
             for j in (1, 2):
                 kind = "stem" if (i == 0 and j == 1) else "conv"
-                specs.append(ConvL(kind, f"UNet/Encode{i + 1}/Repeat/convolution2d_{j}", cin, c, h, w, i))
+                specs.append(ConvL(kind, f"UNet/Encode{i + 1}/Repeat/convolution2d_{j}", cin, c, h, w, i, role=f"enc{j}"))
                 cin = c
             c *= 2
             h //= 2
             w //= 2
         for j in (1, 2):
-            specs.append(ConvL("conv", f"UNet/ED-Bridge/convolution2d_{j}", cin, c, h, w, cfg.num_down_samples))
+            specs.append(ConvL("conv", f"UNet/ED-Bridge/convolution2d_{j}", cin, c, h, w, cfg.num_down_samples,
+                               role=f"bridge{j}"))
             cin = c
         for i in reversed(range(cfg.num_down_samples)):
             c //= 2
@@ -220,7 +226,7 @@ class UNetEngine:
             w *= 2
             for j in (1, 2):
                 specs.append(ConvL("conv", f"UNet/Decode{i + 1}/Repeat/convolution2d_{j}",
-                                   c + cin // 2 if j == 1 else c, c, h, w, i))
+                                   c + cin // 2 if j == 1 else c, c, h, w, i, role=f"dec{j}"))
             cin = c
         specs.append(ConvL("logits", "UNet/AdjustChannels", cin, cfg.num_classes, h, w, 0))
         return specs
@@ -235,8 +241,10 @@ class UNetEngine:
             if L.kind in ("stem", "conv"):
                 plist.append(Param(f"{L.scope}/weights", (3, 3, L.cin, L.cout),
                                    alloc=64 * L.cout if L.kind == "stem" else 0))
-                plist.append(Param(f"{L.scope}/{ns}/gamma", (L.cout,), region="B"))
-                plist.append(Param(f"{L.scope}/{ns}/beta", (L.cout,), region="B"))
+                if L.scale:
+                    plist.append(Param(f"{L.scope}/{ns}/gamma", (L.cout,), region="B"))
+                if L.center:
+                    plist.append(Param(f"{L.scope}/{ns}/beta", (L.cout,), region="B"))
                 if cfg.normalizer == "batch_norm":
                     plist.append(Param(f"{L.scope}/{ns}/moving_mean", (L.cout,), region="S"))
                     plist.append(Param(f"{L.scope}/{ns}/moving_variance", (L.cout,), region="S"))
@@ -246,6 +254,7 @@ class UNetEngine:
             else:
                 plist.append(Param(f"{L.scope}/weights", (1, 1, L.cin, L.cout)))
                 plist.append(Param(f"{L.scope}/biases", (L.cout,), region="B" if cfg.bias_decay else "A"))
+        plist += self._extra_params()
         off = 0
         for region in ("A", "B"):
             for p in plist:
@@ -273,8 +282,17 @@ class UNetEngine:
             self.V = self._alloc(self.n_train * F32).zero() if cfg.optimizer == "adam" else None
         self.sumsq = self._alloc(16)
 
-    def _pp(self, arena: DeviceBuffer, name: str, esize=F32) -> C.c_void_p:
-        return C.c_void_p(arena.ptr + self.params[name].offset * esize)
+    def _extra_params(self):
+        """Parameters outside the conv trunk (GUNet: context MLP, guide convs)."""
+        return []
+
+    def _pp(self, arena: DeviceBuffer, name: str, esize=F32, off: int = 0) -> C.c_void_p:
+        if name not in self.params:
+            return None
+        return C.c_void_p(arena.ptr + (self.params[name].offset + off) * esize)
+
+    def _guide_channels(self, L: ConvL) -> int:
+        return 0
 
     def _plan_activations(self):
         cfg = self.cfg
@@ -287,7 +305,7 @@ class UNetEngine:
         for L in self.layers:
             if L.kind in ("stem", "conv"):
                 L.y = View(self._alloc(n * L.h * L.w * L.cout * BF16), n, L.h, L.w, L.cout)
-                is_enc2 = L.scope.startswith("UNet/Encode") and L.scope.endswith("_2")
+                is_enc2 = L.role == "enc2"
                 if is_enc2:
                     cbuf = View(self._alloc(n * L.h * L.w * 2 * L.cout * BF16), n, L.h, L.w, 2 * L.cout)
                     cat[L.level] = cbuf
@@ -297,12 +315,12 @@ class UNetEngine:
                 else:
                     L.a = View(self._alloc(n * L.h * L.w * L.cout * BF16), n, L.h, L.w, L.cout)
                 if L.kind == "conv":
-                    is_dec1 = L.scope.startswith("UNet/Decode") and L.scope.endswith("_1")
-                    L.x = cat[L.level] if is_dec1 else prev_a
+                    L.x = cat[L.level] if L.role == "dec1" else prev_a
                 prev_a = L.pooled if is_enc2 else L.a
                 g = groups_max
-                L.norm = dict(groups=g, off=small)
-                small += 10 * _align(g * L.cout, 16)  # sums (2 x f64 = 4 float slots), mean, rstd, scale, shift, c1, c2
+                k = 2 + self._guide_channels(L)
+                L.norm = dict(groups=g, off=small, k=k)
+                small += (2 * k + 6) * _align(g * L.cout, 16)  # sums (k x f64), mean, rstd, scale, shift, c1, c2
                 max_act = max(max_act, L.h * L.w * L.cout)
             elif L.kind == "convT":
                 L.x = prev_a
@@ -354,6 +372,10 @@ class UNetEngine:
         k = 1 if L.kind == "logits" else 9
         return 2.0 * n * L.h * L.w * k * L.cin * L.cout
 
+    def _loss_terms(self):
+        """UNet accepts exactly "xentropy" or "dice" (UNet.py:123-132); GUNet overrides with substring matching."""
+        return [self.cfg.loss_type] if self.cfg.loss_type in ("xentropy", "dice") else []
+
     def step_flops(self) -> dict:
         """Algorithmic fwd / bwd FLOPs of one training step (bwd = dgrad + wgrad, no dgrad for the stem)."""
         fwd = sum(self._flops(L) for L in self.layers)
@@ -375,7 +397,7 @@ class UNetEngine:
         cfg = self.cfg
         bn = cfg.normalizer == "batch_norm"
         return _lib.NormDesc(0 if bn else 1, cfg.batch, L.h * L.w, L.cout, L.y.ld, L.a.ld,
-                             cfg.bn_eps if bn else cfg.in_eps, cfg.bn_decay, 1, 1, 1)
+                             cfg.bn_eps if bn else cfg.in_eps, cfg.bn_decay, 1, int(L.center), int(L.scale))
 
     def _loss_desc(self):
         cfg = self.cfg
@@ -389,8 +411,11 @@ class UNetEngine:
         g = L.norm["groups"]
         n = _align(g * L.cout, 16)
         base = self.small.ptr + L.norm["off"] * F32
-        names = ["sums", "_s1", "_s2", "_s3", "mean", "rstd", "scale", "shift", "c1", "c2"]
-        return {nm: C.c_void_p(base + i * n * F32) for i, nm in enumerate(names)}
+        k2 = 2 * L.norm["k"]
+        names = ["mean", "rstd", "scale", "shift", "c1", "c2"]
+        out = {nm: C.c_void_p(base + (k2 + i) * n * F32) for i, nm in enumerate(names)}
+        out["sums"] = C.c_void_p(base)
+        return out
 
     # ------------------------------------------------------------------ weights
     def set_weights(self, weights: dict):
@@ -494,11 +519,13 @@ class UNetEngine:
                 call("bsl_norm_finalize", C.byref(nd), C.c_int(1 if is_training else 0), q["sums"],
                      self._pp(self.W, f"{L.scope}/{ns}/gamma"), self._pp(self.W, f"{L.scope}/{ns}/beta"), mm, mv,
                      q["mean"], q["rstd"], q["scale"], q["shift"], s)
+                guide = self._modulate(L, nd, q)   # GUNet: folds gamma_mod / guide bias into scale, shift
+                gp = C.byref(guide) if guide is not None else None
                 if L.pooled is not None:
-                    call("bsl_norm_apply_pool", C.byref(nd), C.c_int(L.h), C.c_int(L.w), L.y.p, q["scale"], q["shift"],
-                         L.a.p, L.pooled.p, C.c_int(L.pooled.ld), s)
+                    call("bsl_norm_apply_pool_mod", C.byref(nd), C.c_int(L.h), C.c_int(L.w), L.y.p, q["scale"],
+                         q["shift"], gp, L.a.p, L.pooled.p, C.c_int(L.pooled.ld), s)
                 else:
-                    call("bsl_norm_apply", C.byref(nd), L.y.p, q["scale"], q["shift"], L.a.p, s)
+                    call("bsl_norm_apply_mod", C.byref(nd), L.y.p, q["scale"], q["shift"], gp, L.a.p, s)
             elif L.kind == "convT":
                 d = self._convT_desc(L)
                 self._tc("convT_fwd", self._flops(L), "bsl_convT2d_fwd", C.byref(d), L.x.p,
@@ -507,6 +534,21 @@ class UNetEngine:
                 d = self._conv_desc(L)
                 call("bsl_conv2d_head_fprop", C.byref(d), L.x.p, self._pp(self.W, f"{L.scope}/weights"),
                      self._pp(self.W, f"{L.scope}/biases"), self.logits.p, s)
+
+    def _modulate(self, L: ConvL, nd, q):
+        """Hook between norm_finalize and norm_apply; returns the bsl_guide of the layer (or None)."""
+        return None
+
+    def _norm_backward(self, L: ConvL, nd, q, cur, oth):
+        """Gradient through ReLU + normalisation of layer L: `cur` (w.r.t. the activation) -> `oth` (w.r.t. the conv
+        output); leaves the gradients of the normaliser's own parameters in G."""
+        call, s, ns = self.ctx.call, self.stream, self.norm_scope
+        call("bsl_norm_bwd_reduce", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"],
+             q["scale"], q["shift"], q["sums"], s)
+        call("bsl_norm_bwd_finalize", C.byref(nd), q["sums"], q["c1"], q["c2"],
+             self._pp(self.G, f"{L.scope}/{ns}/gamma"), self._pp(self.G, f"{L.scope}/{ns}/beta"), s)
+        call("bsl_norm_bwd_apply", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"], q["scale"],
+             q["shift"], q["c1"], q["c2"], oth.p, C.c_int(L.cout), s)
 
     def predict_outputs(self, with_counts: bool):
         """softmax, `<Cls>Pred` masks, argmax and (optionally) the integer Dice sums, one pass over the logits."""
@@ -519,13 +561,15 @@ class UNetEngine:
         ctx, s, cfg = self.ctx, self.stream, self.cfg
         call = ctx.call
         ld = self._loss_desc()
-        if cfg.loss_type == "xentropy":
+        terms = self._loss_terms()
+        if "xentropy" in terms:
             call("bsl_label_counts", C.byref(ld), self.labels.p, self.counts.p, s)
             call("bsl_wxent_fwd_bwd", C.byref(ld), self.logits.p, self.labels.p, self.counts.p, self.loss_dev.p,
                  self.dlogits.p, self.loss_ws.p, C.c_size_t(self.loss_ws_bytes), s)
-        else:
-            call("bsl_dice_fwd_bwd", C.byref(ld), self.logits.p, self.labels.p, self.loss_dev.p, self.dlogits.p,
-                 C.c_int(0), self.loss_ws.p, C.c_size_t(self.loss_ws_bytes), s)
+        if "dice" in terms:   # second scalar slot; dlogits accumulate when both terms are present (GUNet.py:399-408)
+            call("bsl_dice_fwd_bwd", C.byref(ld), self.logits.p, self.labels.p,
+                 self.loss_dev.at(4 * terms.index("dice")), self.dlogits.p, C.c_int(1 if len(terms) > 1 else 0),
+                 self.loss_ws.p, C.c_size_t(self.loss_ws_bytes), s)
         n = cfg.batch
         cur, oth = self.g1, self.g2     # `cur` holds the gradient w.r.t. the current activation
         ns = self.norm_scope
@@ -549,12 +593,7 @@ class UNetEngine:
                     cur, oth = oth, cur
                 nd = self._norm_desc(L)
                 q = self._norm_ptrs(L)
-                call("bsl_norm_bwd_reduce", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"],
-                     q["scale"], q["shift"], q["sums"], s)
-                call("bsl_norm_bwd_finalize", C.byref(nd), q["sums"], q["c1"], q["c2"],
-                     self._pp(self.G, f"{L.scope}/{ns}/gamma"), self._pp(self.G, f"{L.scope}/{ns}/beta"), s)
-                call("bsl_norm_bwd_apply", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"], q["scale"],
-                     q["shift"], q["c1"], q["c2"], oth.p, C.c_int(L.cout), s)
+                self._norm_backward(L, nd, q, cur, oth)
                 # oth = dY (gradient w.r.t. the conv output), dense with ld = cout
                 d = self._conv_desc(L)
                 d.y_ld = L.cout
@@ -566,9 +605,8 @@ class UNetEngine:
                 else:
                     self._tc("wgrad", self._flops(L), "bsl_conv2d_wgrad", C.byref(d), L.x.p, oth.p, gw,
                              self.wgrad_ws.p, C.c_size_t(self.wgrad_ws_bytes), s)
-                    is_dec1 = L.scope.startswith("UNet/Decode") and L.scope.endswith("_1")
                     wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
-                    if is_dec1:
+                    if L.role == "dec1":
                         dc = self.dcat[L.level]
                         d.x_ld = dc.ld
                         self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad", C.byref(d), oth.p, wbf, dc.p, s)
@@ -621,7 +659,7 @@ class UNetEngine:
     # ------------------------------------------------------------------ results
     def read_loss(self):
         """(data loss, L2 regularisation loss) of the step just run; the only D2H read of a train step."""
-        data = self.loss_dev.download(np.float32, (1,))[0]
+        data = float(self.loss_dev.download(np.float32, (len(self._loss_terms()),)).sum())
         sq = self.sumsq.download(np.float64, (1,))[0]
         return float(data), float(self.cfg.weight_decay_rate * 0.5 * sq) if self.cfg.weight_decay_rate > 0 else 0.0
 
@@ -666,10 +704,11 @@ class UNetEngine:
         self.ctx.call("bsl_memcpy_h2d", self.images.p, pi, C.c_size_t(img.nbytes), s)
         self.ctx.call("bsl_memcpy_h2d", self.labels.p, pl, C.c_size_t(lab.nbytes), s)
         self.train_step(lr, with_metrics)
-        self.ctx.call("bsl_memcpy_d2h", po, self.loss_dev.p, C.c_size_t(4), s)
+        nt = len(self._loss_terms())
+        self.ctx.call("bsl_memcpy_d2h", po, self.loss_dev.p, C.c_size_t(4 * nt), s)
         self.ctx.call("bsl_memcpy_d2h", C.c_void_p(po.value + 8), self.sumsq.p, C.c_size_t(8), s)
         self.ctx.sync(s)
-        data = float(np.frombuffer(out[:1].tobytes(), np.float32)[0])
+        data = float(np.frombuffer(out[:1].tobytes(), np.float32)[:nt].sum())
         reg = float(self.cfg.weight_decay_rate * 0.5 * out[1]) if self.cfg.weight_decay_rate > 0 else 0.0
         return data + reg
 

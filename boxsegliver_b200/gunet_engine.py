@@ -1,0 +1,277 @@
+"""Guided U-Net (GUNet) training / inference engine on the sm_100a kernels.
+
+Mirrors /root/reference/NetworksV2/GUNet.py:259-413 the way engine.UNetEngine mirrors UNet.py: the trunk is the
+same conv / norm / pool / transposed-conv sequence (same tcgen05 kernels, same zero-copy concat), and the blocks
+listed in `mod_layers` are modulated (modulated_conv_block, GUNet.py:162-217):
+
+    conv -> instance_norm(center, scale per YAML) -> * gamma_mod[n, c] -> + (sp_guide . w_sp[:, c] + b_sp[c]) -> ReLU
+
+gamma_mod is a slice of the context MLP output (GUNet.py:31-59: fc(200 -> 256 -> 256 -> 3840), dropout after the
+hidden layers); the additive map is the level's 1x1 guide convolution (GUNet.py:136-159) evaluated on the fly inside
+the normalisation kernels, so modulation adds no pass over the activations. Scope: instance_norm (what every
+shipped GUNet script uses), context_model "fc"; --use_se, --fix, --without_norm, --dropout, after_affine, --img_grad
+and ct_conv raise NotImplementedError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .engine import BF16, F32, ConvL, EngineConfig, Param, UNetEngine, _align
+
+
+@dataclass
+class GUNetConfig(EngineConfig):
+    height: int = 512
+    width: int = 512
+    normalizer: str = "instance_norm"
+    mod_layers: tuple = (1, 2, 3, 4)               # NetworksV2/GUNet.yml
+    context_fc_channels: tuple = (256, 256)
+    norm_with_center: bool = True
+    norm_with_scale: bool = False
+    after_affine: bool = False
+    context_model: str = "fc"
+    use_context: bool = True                       # --use_context
+    use_spatial: bool = True                       # --use_spatial
+    guide_channel: int = 1                         # --guide_channel
+    context_dim: int = 200
+    side_dropout: float = 0.5                      # --side_dropout
+    dropout_seed: int = 0
+    use_se: bool = False
+    fix: bool = False
+    without_norm: bool = False
+    dropout: float = None
+
+    @property
+    def n_modulator_param(self):
+        return self.init_channels * sum(2 ** i for i in range(self.num_down_samples + 1) if i in self.mod_layers) * 2
+
+
+class GUNetEngine(UNetEngine):
+    def __init__(self, ctx, cfg: GUNetConfig):
+        if cfg.normalizer != "instance_norm":
+            raise NotImplementedError("GUNet engine: guide modulation is implemented for --normalizer instance_norm")
+        for flag in ("use_se", "fix", "without_norm", "dropout", "after_affine"):
+            if getattr(cfg, flag):
+                raise NotImplementedError(f"GUNet engine: --{flag} is not supported")
+        if cfg.context_model != "fc":
+            raise ValueError("Not supported context model")          # GUNet.py:79
+        if cfg.use_spatial and cfg.guide_channel not in (1, 2):
+            raise ValueError("guide_channel must be 1 or 2")
+        super().__init__(ctx, cfg)
+        self._plan_guides()
+
+    # ------------------------------------------------------------------ graph
+    def _loss_terms(self):
+        return [t for t in ("xentropy", "dice") if t in self.cfg.loss_type]   # GUNet.py:399-408
+
+    def _layer_specs(self):
+        cfg = self.cfg
+        specs = []
+        c, cin = cfg.init_channels, cfg.channel
+        h, w = cfg.height, cfg.width
+        nd = cfg.num_down_samples
+        off = 0
+        for i in range(nd + 1):
+            mod = i in cfg.mod_layers and (cfg.use_context or cfg.use_spatial)
+            for j in (1, 2):
+                kind = "stem" if (i == 0 and j == 1) else "conv"
+                role = f"enc{j}" if i < nd else f"bridge{j}"
+                L = ConvL(kind, f"GUNet/Encode/down_conv{i + 1}/mod_conv{j}/Conv", cin, c, h, w, i, role=role,
+                          center=cfg.norm_with_center if mod else True, scale=cfg.norm_with_scale if mod else True)
+                if mod and cfg.use_context:
+                    L.mod_off = off
+                    off += c
+                if mod and cfg.use_spatial:
+                    L.sp_off = (j - 1) * c
+                specs.append(L)
+                cin = c
+            if i < nd:
+                c *= 2
+                h //= 2
+                w //= 2
+        for i in reversed(range(nd)):
+            c //= 2
+            specs.append(ConvL("convT", f"GUNet/Decode/up{i + 1}", cin, cin // 2, h, w, i))
+            h *= 2
+            w *= 2
+            for j in (1, 2):
+                specs.append(ConvL("conv", f"GUNet/Decode/up_conv{i + 1}/up_conv{i + 1}_{j}",
+                                   c + cin // 2 if j == 1 else c, c, h, w, i, role=f"dec{j}"))
+            cin = c
+        specs.append(ConvL("logits", "GUNet/AdjustChannels", cin, cfg.num_classes, h, w, 0))
+        return specs
+
+    def _fc_specs(self):
+        cfg = self.cfg
+        chans = list(cfg.context_fc_channels) + [cfg.n_modulator_param]
+        out, cin = [], cfg.context_dim
+        for k, co in enumerate(chans):
+            out.append((f"GUNet/context/fc{k + 1}", cin, co, k < len(chans) - 1))
+            cin = co
+        return out
+
+    def _extra_params(self):
+        cfg = self.cfg
+        plist = []
+        if cfg.use_context:
+            for sc, cin, cout, _ in self._fc_specs():      # slim.fully_connected: no regulariser in GUNet's arg scope
+                plist.append(Param(f"{sc}/weights", (cin, cout), region="B"))
+                plist.append(Param(f"{sc}/biases", (cout,), region="B"))
+        if cfg.use_spatial:
+            for i in range(cfg.num_down_samples + 1):
+                if i in cfg.mod_layers:
+                    co = cfg.init_channels * 2 ** (i + 1)
+                    sc = f"GUNet/spatial/conv{i + 1}"
+                    plist.append(Param(f"{sc}/weights", (1, 1, cfg.guide_channel, co)))
+                    plist.append(Param(f"{sc}/biases", (co,), region="B" if cfg.bias_decay else "A"))
+        return plist
+
+    def _guide_channels(self, L: ConvL) -> int:
+        return self.cfg.guide_channel if L.sp_off is not None else 0
+
+    def _plan_guides(self):
+        cfg, n = self.cfg, self.cfg.batch
+        self.guides = []
+        if cfg.use_spatial:
+            h, w = cfg.height, cfg.width
+            for _ in range(cfg.num_down_samples + 1):
+                self.guides.append((self._alloc(n * h * w * cfg.guide_channel * F32), h, w))
+                h //= 2
+                w //= 2
+        self.fc_bufs = []
+        if cfg.use_context:
+            self.context = self._alloc(n * cfg.context_dim * F32)
+            ws = 0
+            for sc, cin, cout, hidden in self._fc_specs():
+                y = self._alloc(n * cout * F32)
+                dy = self._alloc(n * cout * F32) if cfg.training else None
+                self.fc_bufs.append((y, dy))
+                d = self._fc_desc(cin, cout, hidden, 0, True)
+                ws = max(ws, self.ctx.lib.bsl_fc_bwd_workspace(self.ctx.h, C.byref(d)))
+            self.fc_ws_bytes = int(ws)
+            self.fc_ws = self._alloc(max(ws, 16))
+
+    def _fc_desc(self, cin, cout, hidden, layer, is_training):
+        cfg = self.cfg
+        drop = bool(hidden and is_training and cfg.side_dropout)
+        dd = _lib.DropoutDesc(1.0 - cfg.side_dropout if drop else 1.0, cfg.dropout_seed,
+                              (self.step_count + 1) * 16 + layer)
+        return _lib.FcDesc(cfg.batch, cin, cout, int(hidden), int(drop), dd)
+
+    # ------------------------------------------------------------------ weights / inputs
+    def init_weights(self, seed: int = 0):
+        """xavier for convs and hidden FC layers, he_normal for the final FC (GUNet.py:56), zeros / ones elsewhere."""
+        rng = np.random.default_rng(seed)
+        w = {}
+        for name, p in self.params.items():
+            shp = p.shape
+            if name.endswith("/weights") and len(shp) == 4:
+                rf = shp[0] * shp[1]
+                lim = np.sqrt(6.0 / (rf * shp[2] + rf * shp[3]))
+                w[name] = rng.uniform(-lim, lim, size=shp).astype(np.float32)
+            elif name.endswith("/weights"):
+                last = name.startswith(f"GUNet/context/fc{len(self._fc_specs())}/")
+                if last:
+                    w[name] = np.clip(rng.standard_normal(shp), -2, 2).astype(np.float32) * np.float32(
+                        np.sqrt(2.0 / shp[0]) / 0.87962566103423978)
+                else:
+                    lim = np.sqrt(6.0 / (shp[0] + shp[1]))
+                    w[name] = rng.uniform(-lim, lim, size=shp).astype(np.float32)
+            elif name.endswith("gamma"):
+                w[name] = np.ones(shp, np.float32)
+            else:
+                w[name] = np.zeros(shp, np.float32)
+        self.set_weights(w)
+        return w
+
+    def set_guides(self, context: np.ndarray | None = None, sp_guide: np.ndarray | None = None):
+        cfg = self.cfg
+        if cfg.use_context:
+            assert context is not None and context.shape == (cfg.batch, cfg.context_dim), "context [N, context_dim]"
+            self.context.upload(np.ascontiguousarray(context, np.float32))
+        if cfg.use_spatial:
+            shp = (cfg.batch, cfg.height, cfg.width, cfg.guide_channel)
+            assert sp_guide is not None and sp_guide.shape == shp, f"sp_guide {shp}"
+            self.guides[0][0].upload(np.ascontiguousarray(sp_guide, np.float32))
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, is_training: bool):
+        cfg, call, s = self.cfg, self.ctx.call, self.stream
+        self.ctx.tag = "GUNet/context"
+        if cfg.use_context:
+            x = self.context
+            for k, (sc, cin, cout, hidden) in enumerate(self._fc_specs()):
+                d = self._fc_desc(cin, cout, hidden, k, is_training)
+                call("bsl_fc_fwd", C.byref(d), x.p, self._pp(self.W, f"{sc}/weights"), self._pp(self.W, f"{sc}/biases"),
+                     self.fc_bufs[k][0].p, s)
+                x = self.fc_bufs[k][0]
+            self.ctx_params = x
+        self.ctx.tag = "GUNet/spatial"
+        if cfg.use_spatial:
+            for i in range(cfg.num_down_samples):
+                (src, h, w), (dst, _, _) = self.guides[i], self.guides[i + 1]
+                call("bsl_avgpool2x2_f32", C.c_int(cfg.batch), C.c_int(h), C.c_int(w), C.c_int(cfg.guide_channel), src.p,
+                     dst.p, s)
+        self._fwd_training = is_training
+        super().forward(is_training)
+
+    def _guide_struct(self, L: ConvL):
+        if L.sp_off is None:
+            return None
+        sc = f"GUNet/spatial/conv{L.level + 1}"
+        return _lib.Guide(self.guides[L.level][0].ptr, self.cfg.guide_channel,
+                          self._pp(self.W, f"{sc}/weights", off=L.sp_off).value, 2 * L.cout)
+
+    def _modulate(self, L: ConvL, nd, q):
+        if L.mod_off is None and L.sp_off is None:
+            return None
+        gm = C.c_void_p(self.ctx_params.ptr + L.mod_off * F32) if L.mod_off is not None else None
+        bsp = self._pp(self.W, f"GUNet/spatial/conv{L.level + 1}/biases", off=L.sp_off) if L.sp_off is not None else None
+        self.ctx.call("bsl_norm_modulate", C.byref(nd), gm, C.c_int(self.cfg.n_modulator_param), bsp, q["scale"],
+                      q["shift"], self.stream)
+        return self._guide_struct(L)
+
+    # ------------------------------------------------------------------ backward
+    def _norm_backward(self, L: ConvL, nd, q, cur, oth):
+        if L.mod_off is None and L.sp_off is None:
+            return super()._norm_backward(L, nd, q, cur, oth)
+        call, s, ns = self.ctx.call, self.stream, self.norm_scope
+        guide = self._guide_struct(L)
+        gp = C.byref(guide) if guide is not None else None
+        nmod = self.cfg.n_modulator_param
+        gm = C.c_void_p(self.ctx_params.ptr + L.mod_off * F32) if L.mod_off is not None else None
+        dgm = C.c_void_p(self.fc_bufs[-1][1].ptr + L.mod_off * F32) if L.mod_off is not None else None
+        ssc = f"GUNet/spatial/conv{L.level + 1}"
+        dwg = self._pp(self.G, f"{ssc}/weights", off=L.sp_off) if L.sp_off is not None else None
+        dbg = self._pp(self.G, f"{ssc}/biases", off=L.sp_off) if L.sp_off is not None else None
+        call("bsl_norm_bwd_reduce_mod", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"], q["scale"],
+             q["shift"], gp, q["sums"], s)
+        call("bsl_norm_bwd_finalize_mod", C.byref(nd), q["sums"], C.c_int(self._guide_channels(L)), gm, C.c_int(nmod),
+             self._pp(self.W, f"{L.scope}/{ns}/gamma"), self._pp(self.W, f"{L.scope}/{ns}/beta"), q["c1"], q["c2"],
+             self._pp(self.G, f"{L.scope}/{ns}/gamma"), self._pp(self.G, f"{L.scope}/{ns}/beta"), dgm, dwg,
+             C.c_int(2 * L.cout), dbg, s)
+        call("bsl_norm_bwd_apply_mod", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"], q["scale"],
+             q["shift"], q["c1"], q["c2"], gp, oth.p, C.c_int(L.cout), s)
+
+    def loss_backward(self):
+        super().loss_backward()
+        cfg, call, s = self.cfg, self.ctx.call, self.stream
+        if not cfg.use_context:
+            return
+        self.ctx.tag = "GUNet/context"
+        specs = self._fc_specs()
+        for k in range(len(specs) - 1, -1, -1):
+            sc, cin, cout, hidden = specs[k]
+            d = self._fc_desc(cin, cout, hidden, k, True)
+            x = self.context if k == 0 else self.fc_bufs[k - 1][0]
+            dx = self.fc_bufs[k - 1][1].p if k > 0 else None
+            call("bsl_fc_bwd", C.byref(d), x.p, self._pp(self.W, f"{sc}/weights"), self.fc_bufs[k][0].p,
+                 self.fc_bufs[k][1].p, dx, self._pp(self.G, f"{sc}/weights"), self._pp(self.G, f"{sc}/biases"),
+                 self.fc_ws.p, C.c_size_t(self.fc_ws_bytes), s)
+
+    def get_context_params(self):
+        return self.ctx_params.download(np.float32, (self.cfg.batch, self.cfg.n_modulator_param))

@@ -80,3 +80,23 @@ def make_sp_guide(labels: np.ndarray, sigma: float = 6.0):
             g = np.exp(-((yy - ys.mean()) ** 2 + (xx - xs.mean()) ** 2) / (2 * sigma * sigma))
             out[i, :, :, 0] = 0.5 + 0.5 * g
     return out
+
+
+def make_guides(images: np.ndarray, labels: np.ndarray, context_dim: int = 200, guide_channel: int = 1, seed: int = 0):
+    """(context [n, context_dim], sp_guide [n,h,w,guide_channel]) as the reference's pipeline feeds GUNet
+    (/root/reference/DataLoader/Liver/input_pipeline_g.py:374-394,549-567): histograms + N(0, 0.002) noise, the second
+    guide channel (when present) is a Gaussian at the liver centre."""
+    rng = np.random.default_rng(seed)
+    ctx = make_context(labels, images, bins=context_dim // 2)
+    ctx = (ctx + rng.normal(0, 0.002, ctx.shape) * (ctx.sum(axis=1, keepdims=True) > 0)).astype(np.float32)
+    g = make_sp_guide(labels)
+    if guide_channel == 2:
+        n, h, w = labels.shape
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        g2 = np.full((n, h, w, 1), 0.5, np.float32)
+        for i in range(n):
+            ys, xs = np.nonzero(labels[i] == 1)
+            if ys.size:
+                g2[i, :, :, 0] = 0.5 + 0.5 * np.exp(-((yy - ys.mean()) ** 2 + (xx - xs.mean()) ** 2) / (2 * 12.0 ** 2))
+        g = np.concatenate((g, g2), axis=-1)
+    return ctx, np.ascontiguousarray(g, np.float32)

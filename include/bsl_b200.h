@@ -186,6 +186,68 @@ int bsl_norm_bwd_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, const double* su
 int bsl_norm_bwd_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const void* dy_bf16, int dy_ld,
                        const float* mean, const float* rstd, const float* scale, const float* shift,
                        const float* c1, const float* c2, void* dx_bf16, int dx_ld, void* stream);
+/* ---- GUNet guide modulation of an instance-norm layer (NetworksV2/GUNet.py:162-217, modulated_conv_block):
+ *   conv -> norm(center, scale per YAML) -> * gamma_mod[n, c] -> + (sp_guide[n, p, :] . w[:, c] + b[c]) -> ReLU
+ * gamma_mod is this layer's slice of the context MLP output (conditional_normalization, GUNet.py:119-133); the
+ * additive map is the 1x1 guide convolution of _spatial_subnets (GUNet.py:136-159), evaluated on the fly from the
+ * 1- or 2-channel guide at this layer's resolution and never materialised. bsl_norm_modulate folds gamma_mod and the
+ * guide-conv bias into the per-(sample, channel) scale / shift that bsl_norm_finalize produced; the *_mod passes are
+ * the plain passes plus the guide term (guide == NULL or guide->map == NULL: identical to the plain pass). */
+typedef struct {
+  const float* map; /* fp32 [n][hw][channels]; NULL = no spatial guide */
+  int channels;     /* 1 or 2 (--guide_channel) */
+  const float* w;   /* this layer's columns of the guide conv filter: w[g * w_ld + c] */
+  int w_ld;
+} bsl_guide;
+
+int bsl_norm_modulate(bsl_ctx* ctx, const bsl_norm_desc* d, const float* gamma_mod /*[n][gm_ld], nullable*/, int gm_ld,
+                      const float* sp_bias /*[c], nullable*/, float* scale, float* shift, void* stream);
+int bsl_norm_apply_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const float* scale,
+                       const float* shift, const bsl_guide* guide, void* y_bf16, void* stream);
+int bsl_norm_apply_pool_mod(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, const void* x_bf16,
+                            const float* scale, const float* shift, const bsl_guide* guide, void* y_bf16,
+                            void* pooled_bf16, int pooled_ld, void* stream);
+/* sums: fp64 [n][2 + guide channels][c] = sum dz, sum dz * xhat, sum dz * guide_g. */
+int bsl_norm_bwd_reduce_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const void* dy_bf16, int dy_ld,
+                            const float* mean, const float* rstd, const float* scale, const float* shift,
+                            const bsl_guide* guide, double* sums, void* stream);
+/* c1, c2 as bsl_norm_bwd_finalize; dgamma / dbeta (nullable) of the norm's own affine; dgamma_mod [n][gm_ld] is the
+ * gradient w.r.t. the context MLP output slice; dw_guide [g * dw_ld + c] and dbias_guide [c] the guide conv's. */
+int bsl_norm_bwd_finalize_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const double* sums, int guide_channels,
+                              const float* gamma_mod, int gm_ld, const float* gamma, const float* beta, float* c1,
+                              float* c2, float* dgamma, float* dbeta, float* dgamma_mod, float* dw_guide, int dw_ld,
+                              float* dbias_guide, void* stream);
+int bsl_norm_bwd_apply_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const void* dy_bf16, int dy_ld,
+                           const float* mean, const float* rstd, const float* scale, const float* shift,
+                           const float* c1, const float* c2, const bsl_guide* guide, void* dx_bf16, int dx_ld,
+                           void* stream);
+
+/* ---- GUNet context MLP and guide pyramid (fp32, tiny): slim_nets.fc = fully_connected (+ ReLU) (+ dropout) --
+ * NetworksV2/Backbone/slim_nets.py:34-57 called from GUNet._context_subnets (GUNet.py:31-59); slim.avg_pool2d(gs, 2)
+ * -- GUNet.py:155-156. Dropout follows tf.nn.dropout (x / keep_prob * floor(keep_prob + u)) with u drawn from
+ * Philox4x32-10 keyed by (seed, offset): element i uses counter i / 4, lane i % 4, so the oracle reproduces the mask
+ * bit for bit. */
+typedef struct {
+  float keep_prob;
+  unsigned long long seed, offset;
+} bsl_dropout_desc;
+typedef struct {
+  int n, cin, cout;
+  int relu;        /* slim.fully_connected default activation_fn */
+  int use_dropout; /* only when is_training and side_dropout > 0 */
+  bsl_dropout_desc dropout;
+} bsl_fc_desc;
+
+int bsl_fc_fwd(bsl_ctx* ctx, const bsl_fc_desc* d, const float* x, const float* w /*[cin][cout]*/, const float* bias,
+               float* y, void* stream);
+size_t bsl_fc_bwd_workspace(bsl_ctx* ctx, const bsl_fc_desc* d);
+/* y is the forward OUTPUT (post ReLU / dropout); dx nullable (first layer). */
+int bsl_fc_bwd(bsl_ctx* ctx, const bsl_fc_desc* d, const float* x, const float* w, const float* y, const float* dy,
+               float* dx, float* dw, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
+/* out[i] = 1 / keep_prob or 0: the dropout multipliers themselves (tests, and backbone --dropout). */
+int bsl_dropout_mask(bsl_ctx* ctx, const bsl_dropout_desc* d, size_t n, float* out, void* stream);
+int bsl_avgpool2x2_f32(bsl_ctx* ctx, int n, int h, int w, int c, const float* x, float* y, void* stream);
+
 /* MaxPoolGrad (first maximum in scan order wins ties) fused with the skip-connection add:
  * dact = dskip (nullable) + unpool(dpool). */
 int bsl_maxpool2x2_bwd_add(bsl_ctx* ctx, int n, int h, int w, int c, const void* act_bf16, int act_ld,

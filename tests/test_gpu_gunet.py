@@ -1,0 +1,133 @@
+"""Parity of the guided U-Net engine (context MLP + dropout, guide pyramid, modulated instance-norm blocks, trunk,
+loss, backward) against oracle/gunet_ref.py, through the C ABI.
+
+Gates (relative L2 per tensor; bf16 path, north_star tolerance 1e-2):
+  * every layer evaluated by the fp64 oracle on the tensor the device stored as its input ........ <= 1e-2
+  * gradients: oracle backward over the device's stored forward tape (same ReLU masks) ........... median <= 1e-2,
+    worst <= 1.5e-2; fp32-only paths (context MLP, guide convs) ................................... <= 1e-3
+  * dropout multipliers (Philox4x32-10) ........................................................... bit-exact
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from boxsegliver_b200 import _lib, synthetic
+from boxsegliver_b200.device import round_bf16
+from boxsegliver_b200.gunet_engine import GUNetConfig, GUNetEngine
+from oracle import gunet_ref as G
+from oracle import tf_ops as O
+from tests.gpu_util import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def test_dropout_mask_bit_exact(ctx):
+    n = 12345
+    for keep, seed, off in ((0.5, 0, 17), (0.8, 0xDEADBEEFCAFE, 1 << 33), (1.0, 3, 3)):
+        buf = ctx.alloc(n * 4)
+        d = _lib.DropoutDesc(keep, seed, off)
+        ctx.call("bsl_dropout_mask", C.byref(d), C.c_size_t(n), buf.p, ctx.stream)
+        got = buf.download(np.float32, (n,))
+        buf.free()
+        assert np.array_equal(got, O.dropout_multipliers(n, keep, seed, off))
+
+
+def test_fc_and_avgpool_ops(ctx):
+    rng = np.random.default_rng(0)
+    n, cin, cout = 5, 37, 50
+    x = rng.standard_normal((n, cin), dtype=np.float32)
+    w = rng.standard_normal((cin, cout), dtype=np.float32) * 0.2
+    b = rng.standard_normal(cout, dtype=np.float32)
+    dy = rng.standard_normal((n, cout), dtype=np.float32)
+    d = _lib.FcDesc(n, cin, cout, 1, 1, _lib.DropoutDesc(0.5, 9, 4))
+    bx, bw, bb, bdy = (ctx.from_numpy(a) for a in (x, w, b, dy))
+    by, bdx, bdw, bdb = ctx.alloc(n * cout * 4), ctx.alloc(n * cin * 4), ctx.alloc(cin * cout * 4), ctx.alloc(cout * 4)
+    ws_bytes = ctx.lib.bsl_fc_bwd_workspace(ctx.h, C.byref(d))
+    ws = ctx.alloc(ws_bytes)
+    ctx.call("bsl_fc_fwd", C.byref(d), bx.p, bw.p, bb.p, by.p, ctx.stream)
+    ctx.call("bsl_fc_bwd", C.byref(d), bx.p, bw.p, by.p, bdy.p, bdx.p, bdw.p, bdb.p, ws.p, C.c_size_t(ws_bytes), ctx.stream)
+    y = by.download(np.float32, (n, cout))
+    mult = O.dropout_multipliers(n * cout, 0.5, 9, 4).reshape(n, cout)
+    pre = x.astype(np.float64) @ w + b
+    assert rel(y, np.maximum(pre, 0) * mult) < 1e-6
+    dpre = dy * mult * (pre > 0)
+    dx, dw, db = O.fully_connected_grad(x.astype(np.float64), w.astype(np.float64), dpre.astype(np.float64))
+    assert rel(bdx.download(np.float32, (n, cin)), dx) < 1e-5
+    assert rel(bdw.download(np.float32, (cin, cout)), dw) < 1e-5
+    assert rel(bdb.download(np.float32, (cout,)), db) < 1e-5
+    g = rng.uniform(0.5, 1, (3, 8, 12, 2)).astype(np.float32)
+    bg, bo = ctx.from_numpy(g), ctx.alloc(3 * 4 * 6 * 2 * 4)
+    ctx.call("bsl_avgpool2x2_f32", C.c_int(3), C.c_int(8), C.c_int(12), C.c_int(2), bg.p, bo.p, ctx.stream)
+    assert rel(bo.download(np.float32, (3, 4, 6, 2)), O.avg_pool_2x2(g)) < 1e-7
+    for buf in (bx, bw, bb, bdy, by, bdx, bdw, bdb, ws, bg, bo):
+        buf.free()
+
+
+def _make(n, hw, **kw):
+    base = dict(height=hw, width=hw, channel=3, init_channels=64, num_down_samples=4, weight_decay_rate=1e-5,
+                loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4), dropout_seed=21)
+    base.update(kw)
+    ecfg = GUNetConfig(batch=n, **base)
+    rcfg = G.GUNetCfg(**base)
+    images, labels = synthetic.make_batch(n, hw, hw, 3, seed=1360 + n)
+    context, guide = synthetic.make_guides(images, labels, rcfg.context_dim, rcfg.guide_channel, seed=5)
+    return ecfg, rcfg, dict(images=images, context=context, sp_guide=guide), labels
+
+
+@pytest.mark.parametrize("n,hw,kw", [
+    (2, 64, dict(use_context=True, use_spatial=True, guide_channel=1, loss_type="xentropy+dice")),      # GUNet.yml
+    (3, 64, dict(use_context=True, use_spatial=True, guide_channel=2, norm_with_center=False,
+                 context_fc_channels=(200, 200), loss_type="xentropy")),                                # GUNet_BOTH.yml
+    (2, 64, dict(use_context=False, use_spatial=True, guide_channel=2, norm_with_scale=True, mod_layers=(0, 2, 4),
+                 loss_type="dice")),
+    (2, 64, dict(use_context=True, use_spatial=False, side_dropout=0.0, loss_type="xentropy")),
+])
+def test_gunet_train_step_parity(ctx, n, hw, kw):
+    ecfg, rcfg, inputs, labels = _make(n, hw, **kw)
+    params = G.init_params(rcfg, seed=4)
+    rng = np.random.default_rng(2)
+    for k in params:                      # non-trivial affine / bias values so every term is exercised
+        if k.endswith(("beta", "biases")):
+            params[k] = (0.1 * rng.standard_normal(params[k].shape)).astype(np.float32)
+        if k.endswith("gamma"):
+            params[k] = (1 + 0.1 * rng.standard_normal(params[k].shape)).astype(np.float32)
+    eng = GUNetEngine(ctx, ecfg)
+    assert set(eng.params) == set(params)
+    eng.set_weights(params)
+    eng.set_inputs(inputs["images"], labels)
+    eng.set_guides(inputs.get("context"), inputs.get("sp_guide"))
+    eng.forward(True)
+    eng.predict_outputs(True)
+    eng.loss_backward()
+    ctx.check_device()
+    k = rcfg.num_classes
+    logits = eng.logits.download(np.float32, (n, hw, hw, k))
+    dlogits = eng.dlogits.download(np.float32, (n, hw, hw, k))
+    grads = eng.get_grads()
+    stored = eng.get_stored_forward()
+    stored["logits"] = logits
+    ctxp = eng.get_context_params() if rcfg.use_context else None
+    eng.optimizer_step(1e-3)
+    ctx.check_device()
+    data_loss, reg_loss = eng.read_loss()
+    eng.close()
+
+    rin = dict(inputs, images=round_bf16(inputs["images"]))
+    # layer by layer on the device's stored inputs (fp64 oracle ops), and the tape for the backward check
+    tft = G.forward({k_: v.astype(np.float64) for k_, v in params.items()},
+                    {k_: v.astype(np.float64) for k_, v in rin.items()}, rcfg, True, wrnd=round_bf16, stored=stored, step=1)
+    assert max(tft.errs.values()) < 1e-2, max(tft.errs.items(), key=lambda t: t[1])
+    if rcfg.use_context:
+        assert rel(ctxp, tft.ctx_params) < 1e-5
+        if rcfg.side_dropout:
+            assert any((f["mult"] == 0).any() for f in tft.fc if f["mult"] is not None)
+    loss_o, dl = G.loss_and_dlogits(tft, labels, rcfg)
+    assert abs(data_loss - loss_o) < 1e-4 * abs(loss_o)
+    assert abs(reg_loss - G.regularization_loss(params, rcfg)) < 1e-6
+    assert rel(dlogits, dl) < 1e-5
+    g_ref = G.backward(tft, dl, rcfg, rnd=round_bf16)
+    assert set(g_ref) == set(grads)
+    errs = {name: rel(grads[name], g) for name, g in g_ref.items()}
+    assert np.median(list(errs.values())) < 1e-2, errs
+    assert max(errs.values()) < 1.5e-2, max(errs.items(), key=lambda t: t[1])
