@@ -28,6 +28,15 @@ class ConvT2dDesc(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("n", "h", "w", "cin", "cout", "x_ld", "y_ld", "relu")]
 
 
+class Conv3dDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n", "d", "h", "w", "cin", "cout", "kd", "kh", "kw", "sd", "sh", "sw", "x_ld",
+                                       "y_ld")]
+
+
+class ConvT3dDesc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("n", "d", "h", "w", "cin", "cout", "sd", "x_ld", "y_ld", "relu")]
+
+
 class NormDesc(C.Structure):
     _fields_ = [
         ("mode", C.c_int), ("n", C.c_int), ("hw", C.c_int), ("c", C.c_int),

@@ -68,6 +68,7 @@ void set_tiles(IgemmArgs& a, const int tdim[4], const int tbox[4]) {
     a.tdim[d] = tdim[d];
     a.tbox[d] = tbox[d];
     a.ntile[d] = cdiv(tdim[d], tbox[d]);
+    a.istride[d] = 1;
   }
 }
 

@@ -29,9 +29,12 @@ struct IgemmArgs {
   int ntile[4];          // ceil(tdim / tbox)
   int ntaps;             // filter taps
   int cblocks;           // 64-channel blocks per tap on the A side
-  int b_flip;            // MODE_PIX_M, K-major B: visit B taps in reverse (dgrad)
+  int b_flip;            // MODE_PIX_M: 1 = visit B taps in reverse (stride-1 dgrad), 2 = B tap index from tapb[]
   int b_rows_per_tap;    // MODE_PIX_M, K-major B: B rows per tap
   signed char tapoff[27][4];  // per tap: offsets added to A-map coordinates 1..4
+  signed char tapb[27];  // b_flip == 2: filter tap read for loop tap t (phase decomposition of strided dgrad)
+  int istride[4];        // A-map coordinate = pixel coordinate * istride + tapoff (strided convs: the A map
+                         // carries the same traversal stride, so a box still holds tbox consecutive OUTPUT pixels)
   // ---- epilogue
   void* out;             // bf16 (MODE_PIX_M) or fp32 partials (MODE_PIX_K)
   long long ostride[4];  // MODE_PIX_M: output element stride per pixel-grid dim
@@ -137,9 +140,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (MODE == MODE_PIX_M) {
           const int tap = kk / p.cblocks;
           const int cb = kk - tap * p.cblocks;
-          tma_load_5d(sa, &tmA, fb, cb * 64, x[0] + p.tapoff[tap][0], x[1] + p.tapoff[tap][1],
-                      x[2] + p.tapoff[tap][2], x[3] + p.tapoff[tap][3]);
-          const int tapb = p.b_flip ? (p.ntaps - 1 - tap) : tap;
+          tma_load_5d(sa, &tmA, fb, cb * 64, x[0] * p.istride[0] + p.tapoff[tap][0],
+                      x[1] * p.istride[1] + p.tapoff[tap][1], x[2] * p.istride[2] + p.tapoff[tap][2],
+                      x[3] * p.istride[3] + p.tapoff[tap][3]);
+          const int tapb = p.b_flip == 2 ? p.tapb[tap] : (p.b_flip ? (p.ntaps - 1 - tap) : tap);
           if (B_MN) {
             const int krow = (tapb * p.cblocks + cb) * 64;
 #pragma unroll
@@ -161,8 +165,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (mblk >= p.ntaps * p.cblocks) mblk = p.ntaps * p.cblocks - 1;  // rows ignored later
             const int tap = mblk / p.cblocks;
             const int cb = mblk - tap * p.cblocks;
-            tma_load_5d(sa + blk * 8192, &tmA, fb, cb * 64, px[0] + p.tapoff[tap][0],
-                        px[1] + p.tapoff[tap][1], px[2] + p.tapoff[tap][2], px[3] + p.tapoff[tap][3]);
+            tma_load_5d(sa + blk * 8192, &tmA, fb, cb * 64, px[0] * p.istride[0] + p.tapoff[tap][0],
+                        px[1] * p.istride[1] + p.tapoff[tap][1], px[2] * p.istride[2] + p.tapoff[tap][2],
+                        px[3] * p.istride[3] + p.tapoff[tap][3]);
           }
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j)

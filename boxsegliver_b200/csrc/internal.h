@@ -49,6 +49,11 @@ int bsl_check_cuda(bsl_ctx* ctx, cudaError_t e, const char* what);
 int bsl_get_tmap(bsl_ctx* ctx, const void* base, int rank, const uint64_t* dims,
                  const uint64_t* strides_bytes, const uint32_t* box, CUtensorMap* out);
 
+// Same, with a traversal stride per dimension (TMA elementStrides): a box of box[i] elements then holds
+// ceil(box[i] / elem_strides[i]) loaded elements, taken every elem_strides[i]-th from the start coordinate.
+int bsl_get_tmap_es(bsl_ctx* ctx, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const uint32_t* elem_strides, CUtensorMap* out);
+
 // out[c] = sum over pixels of x[p*ld + c] (bf16 in, fp32 out), deterministic two-level reduction.
 int bsl_channel_sum_bf16(bsl_ctx* ctx, const void* x, long long pixels, int c, int ld, float* out,
                          cudaStream_t stream);

@@ -510,6 +510,24 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, c
   }
 }
 
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, const __nv_bfloat16* __restrict__ b,
+                                int b_ld, __nv_bfloat16* __restrict__ out, int o_ld, long long pixels, int c) {
+  const int cg = c / 8;
+  const int rows = blockDim.x / cg;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  if (r >= rows) return;
+  const int ch0 = g * 8;
+  const long long stride = (long long)gridDim.x * rows;
+  for (long long p = (long long)blockIdx.x * rows + r; p < pixels; p += stride) {
+    float u[8], v[8];
+    unpack8(ld16(a + p * a_ld + ch0), u);
+    unpack8(ld16(b + p * b_ld + ch0), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) u[j] += v[j];
+    st16(out + p * o_ld + ch0, pack8(u));
+  }
+}
+
 // Launch shape for the (rows x channel-group) elementwise kernels.
 struct EwPlan {
   int threads, rows;
@@ -785,6 +803,19 @@ int bsl_maxpool2x2_bwd_add(bsl_ctx* ctx, int n, int h, int w, int c, const void*
       reinterpret_cast<const __nv_bfloat16*>(dskip), dskip_ld, reinterpret_cast<__nv_bfloat16*>(dact), dact_ld, n, h,
       w, c);
   BSL_LAUNCH_CHECK(ctx, "maxpool_bwd_add_kernel");
+  return BSL_OK;
+}
+
+int bsl_add_bf16(bsl_ctx* ctx, long long pixels, int c, const void* a, int a_ld, const void* b, int b_ld, void* out,
+                 int out_ld, void* stream) {
+  if (!ctx) return BSL_EINVAL;
+  if (!a || !b || !out) return bsl_fail(ctx, BSL_EINVAL, "add_bf16: null buffer");
+  if (c % 8 || a_ld % 8 || b_ld % 8 || out_ld % 8) return bsl_fail(ctx, BSL_EUNSUPPORTED, "add_bf16: c, ld %% 8");
+  const EwPlan pl = ew_plan(ctx, pixels, 1, c, 2);
+  add_bf16_kernel<<<pl.blocks, pl.threads, 0, as_stream(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(a), a_ld, reinterpret_cast<const __nv_bfloat16*>(b), b_ld,
+      reinterpret_cast<__nv_bfloat16*>(out), out_ld, pixels, c);
+  BSL_LAUNCH_CHECK(ctx, "add_bf16_kernel");
   return BSL_OK;
 }
 

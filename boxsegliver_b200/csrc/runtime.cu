@@ -199,11 +199,16 @@ int bsl_graph_destroy(bsl_ctx* ctx, void* graph_exec) {
 
 int bsl_get_tmap(bsl_ctx* ctx, const void* base, int rank, const uint64_t* dims,
                  const uint64_t* strides_bytes, const uint32_t* box, CUtensorMap* out) {
-  char key[512];
+  return bsl_get_tmap_es(ctx, base, rank, dims, strides_bytes, box, nullptr, out);
+}
+
+int bsl_get_tmap_es(bsl_ctx* ctx, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, const uint32_t* elem_strides, CUtensorMap* out) {
+  char key[640];
   int n = snprintf(key, sizeof(key), "%p:%d", base, rank);
   for (int i = 0; i < rank; ++i)
-    n += snprintf(key + n, sizeof(key) - n, ":%llu,%llu,%u", (unsigned long long)dims[i],
-                  (unsigned long long)(i ? strides_bytes[i] : 2), box[i]);
+    n += snprintf(key + n, sizeof(key) - n, ":%llu,%llu,%u,%u", (unsigned long long)dims[i],
+                  (unsigned long long)(i ? strides_bytes[i] : 2), box[i], elem_strides ? elem_strides[i] : 1u);
   {
     std::lock_guard<std::mutex> g(ctx->mu);
     auto it = ctx->tmaps.find(key);
@@ -217,7 +222,7 @@ int bsl_get_tmap(bsl_ctx* ctx, const void* base, int rank, const uint64_t* dims,
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bx[i] = box[i];
-    es[i] = 1;
+    es[i] = elem_strides ? elem_strides[i] : 1;
     if (i) gstr[i - 1] = strides_bytes[i];
   }
   alignas(64) CUtensorMap m;

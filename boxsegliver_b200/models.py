@@ -5,10 +5,10 @@ from pathlib import Path
 
 import yaml
 
-from .networks import UNet
+from .networks import GUNet, UNet
 from .networks.base import ModeKeys
 
-MODEL_ZOO = [UNet]
+MODEL_ZOO = [UNet, GUNet]
 
 
 def add_arguments(parser):

@@ -1,1 +1,2 @@
 from .unet import UNet  # noqa: F401
+from .gunet import GUNet  # noqa: F401

@@ -130,6 +130,49 @@ int bsl_convT2d_bwd_filter(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* 
                            const void* dyr_bf16, float* dw_kkoi_f32, float* dbias_f32, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------ conv3d / conv3d_transpose (UNet3D)
+ * Replaces Conv3D / Conv3DBackpropInputV2 / Conv3DBackpropFilterV2 behind slim.conv3d(x, c, kernel, stride) and
+ * slim.conv3d_transpose(x, c, kernel == stride, biases_initializer=None) -- NetworksV2/UNet3D.py:31-91,151-168.
+ * Tensors are NDHWC bf16; filters DHWIO ([kd,kh,kw,Cin,Cout]) and [kd,kh,kw,Cout,Cin] for the transposed conv.
+ * SAME padding as TF: out = ceil(in / stride), pad_before = max((out-1)*stride + k - in, 0) / 2.
+ * Kernel extents 1 or 3, strides 1 or 2 per axis. (1,3,3)/stride-1 layers can equally be run as bsl_conv2d_* over
+ * n*d images. cin and cout must be multiples of 64: the engine stores UNet3D's 30/60/120/240 channels zero-padded. */
+typedef struct {
+  int n, d, h, w; /* INPUT spatial size */
+  int cin, cout;
+  int kd, kh, kw;
+  int sd, sh, sw;
+  int x_ld, y_ld;
+} bsl_conv3d_desc;
+
+int bsl_conv3d_fprop(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x_bf16, const void* w_dhwio_bf16,
+                     void* y_bf16, void* stream);
+int bsl_conv3d_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy_bf16, const void* w_dhwio_bf16,
+                     void* dx_bf16, void* stream);
+size_t bsl_conv3d_wgrad_workspace(bsl_ctx* ctx, const bsl_conv3d_desc* d);
+int bsl_conv3d_wgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x_bf16, const void* dy_bf16,
+                     float* dw_dhwio_f32, void* workspace, size_t workspace_bytes, void* stream);
+
+typedef struct {
+  int n, d, h, w; /* INPUT spatial size; output is [n, sd*d, 2h, 2w, cout] */
+  int cin, cout;
+  int sd;         /* kernel == stride == (sd, 2, 2), sd in {1, 2} */
+  int x_ld, y_ld;
+  int relu;
+} bsl_convT3d_desc;
+
+int bsl_convT3d_fwd(bsl_ctx* ctx, const bsl_convT3d_desc* d, const void* x_bf16, const void* w_bf16,
+                    const float* bias_f32 /*nullable: UNet3D has none*/, void* y_bf16, void* stream);
+int bsl_convT3d_bwd_data(bsl_ctx* ctx, const bsl_convT3d_desc* d, const void* dyr_bf16, const void* w_bf16,
+                         void* dx_bf16, void* stream);
+size_t bsl_convT3d_bwd_filter_workspace(bsl_ctx* ctx, const bsl_convT3d_desc* d);
+int bsl_convT3d_bwd_filter(bsl_ctx* ctx, const bsl_convT3d_desc* d, const void* x_bf16, const void* dyr_bf16,
+                           float* dw_f32, float* dbias_f32 /*nullable*/, void* workspace, size_t workspace_bytes,
+                           void* stream);
+/* out = a + b (bf16, channel-strided views): AddN of the skip gradient and the strided-conv gradient in UNet3D. */
+int bsl_add_bf16(bsl_ctx* ctx, long long pixels, int c, const void* a_bf16, int a_ld, const void* b_bf16, int b_ld,
+                 void* out_bf16, int out_ld, void* stream);
+
 /* ------------------------------------------------------------------ stem + logits convolutions
  * CUDA-core kernels for the two HBM-bound layers (0.26 % of the FLOPs).
  * Stem:   slim.conv2d(images, 64, 3) on the fp32 input images -- NetworksV2/UNet.py:79 (first call);
