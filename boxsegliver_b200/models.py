@@ -5,10 +5,10 @@ from pathlib import Path
 
 import yaml
 
-from .networks import GUNet, UNet
+from .networks import GUNet, UNet, UNet3D
 from .networks.base import ModeKeys
 
-MODEL_ZOO = [UNet, GUNet]
+MODEL_ZOO = [UNet, GUNet, UNet3D]
 
 
 def add_arguments(parser):

@@ -1,2 +1,3 @@
 from .unet import UNet  # noqa: F401
 from .gunet import GUNet  # noqa: F401
+from .unet3d import UNet3D  # noqa: F401

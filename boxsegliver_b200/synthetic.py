@@ -100,3 +100,32 @@ def make_guides(images: np.ndarray, labels: np.ndarray, context_dim: int = 200, 
                 g2[i, :, :, 0] = 0.5 + 0.5 * np.exp(-((yy - ys.mean()) ** 2 + (xx - xs.mean()) ** 2) / (2 * 12.0 ** 2))
         g = np.concatenate((g, g2), axis=-1)
     return ctx, np.ascontiguousarray(g, np.float32)
+
+
+def make_volume_batch(n: int, d: int, h: int, w: int, seed: int = FOLD_SEED, guide_channel: int = 0):
+    """UNet3D inputs as /root/reference/DataLoader/NF/input_pipeline_3d.py:352-408 feeds them: z-scored volume
+    [n,d,h,w,1] (statistics over non-zero voxels), labels {0,1} [n,d,h,w], optional Gaussian click guides."""
+    rng = np.random.default_rng(seed)
+    zz, yy, xx = np.mgrid[0:d, 0:h, 0:w].astype(np.float32)
+    images = np.zeros((n, d, h, w, 1), np.float32)
+    labels = np.zeros((n, d, h, w), np.int32)
+    guide = np.zeros((n, d, h, w, max(guide_channel, 1)), np.float32)
+    for i in range(n):
+        body = ((yy - h / 2) / (0.45 * h)) ** 2 + ((xx - w / 2) / (0.42 * w)) ** 2 < 1
+        vol = np.where(body, 0.35, 0.0).astype(np.float32)
+        lab = np.zeros((d, h, w), np.int32)
+        for _ in range(rng.integers(0, 4) if i else 0, 4):          # sample 0 has no lesion (all-background edge case)
+            cz, cy, cx = rng.uniform(0.2, 0.8) * d, rng.uniform(0.25, 0.75) * h, rng.uniform(0.25, 0.75) * w
+            rz, ry, rx = rng.uniform(0.1, 0.3) * d + 1, rng.uniform(0.05, 0.15) * h, rng.uniform(0.05, 0.15) * w
+            blob = ((zz - cz) / rz) ** 2 + ((yy - cy) / ry) ** 2 + ((xx - cx) / rx) ** 2 < 1
+            vol[blob & body] = 0.7
+            lab[blob & body] = 1
+            if guide_channel:
+                g = np.exp(-(((zz - cz) / 1.0) ** 2 + ((yy - cy) / 5.0) ** 2 + ((xx - cx) / 5.0) ** 2) / 2)
+                guide[i, ..., 0] = np.maximum(guide[i, ..., 0], g)
+        vol += rng.normal(0, 0.03, vol.shape).astype(np.float32) * body
+        nz = vol[vol != 0]
+        vol = np.where(vol != 0, (vol - nz.mean()) / (nz.std() + 1e-8), 0.0)
+        images[i, ..., 0] = vol
+        labels[i] = lab
+    return (images, labels, guide) if guide_channel else (images, labels)

@@ -1,0 +1,618 @@
+"""3-D U-Net (UNet3D) training / inference engine on the sm_100a kernels.
+
+Mirrors /root/reference/NetworksV2/UNet3D.py:31-202: conv3d + instance-norm + ReLU blocks with kernels (1,3,3) /
+(3,3,3), strided-conv down-sampling ((1,2,2), bridge (2,2,2)), bias-free conv3d_transpose + ReLU up-sampling, skip
+concat [encoder, up], 1x1x1 logits, weighted cross-entropy. What differs from the 2-D engine:
+
+  * activations are NDHWC bf16; (1,3,3)/stride-1 layers run as 2-D convolutions over n*d images on the halo-tile
+    kernels, everything else goes through bsl_conv3d_* / bsl_convT3d_* (csrc/conv3d.cu);
+  * UNet3D's channel counts (30, 60, 120, 240, 320) are stored zero-padded to multiples of 64 (64, 64, 128, 256, 320)
+    because the tcgen05 kernels reduce over 64-channel blocks. Pad lanes are exactly zero everywhere and stay zero
+    through instance-norm (y = 0 -> z = beta_pad = 0), ReLU, the backward pass (dz = 0 where z = 0) and Adam
+    (g = 0 -> no update), so numerics are those of the un-padded network; FLOP accounting uses the un-padded counts;
+  * parameter arenas hold the PADDED layouts; set_weights / get_weights / get_grads pack and unpack TF-shaped
+    variables ([kd,kh,kw,Cin,Cout], concat inputs split as [encoder | up]);
+  * there is no pooling: an encoder block's output feeds the skip and the next strided conv, so its gradient is an
+    explicit add (bsl_add_bf16) of the two branches.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .device import Context, DeviceBuffer, f32_to_bf16_bits
+from .engine import BF16, F32, _align
+
+CPAD = 64
+
+
+@dataclass
+class UNet3DConfig:
+    batch: int
+    depth: int = 64
+    height: int = 128
+    width: int = 128
+    channel: int = 1
+    classes: tuple = ("Background", "NF")
+    init_channels: int = 30           # NetworksV2/UNet3D.yml
+    max_channels: int = 320
+    num_pool_layers: int = 4
+    use_spatial: bool = False
+    guide_channel: int = 2
+    normalizer: str = "instance_norm"
+    weight_decay_rate: float = 3e-5
+    bias_decay: bool = False
+    loss_type: str = "xentropy"
+    loss_weight_type: str = "numerical"
+    loss_numeric_w: tuple = (1.0, 1.0)
+    loss_proportion_decay: float = 1000.0
+    optimizer: str = "adam"
+    in_eps: float = 1e-6
+    training: bool = True
+    world: int = 1
+
+    @property
+    def num_classes(self):
+        return len(self.classes)
+
+    @property
+    def in_channels(self):
+        return self.channel + (self.guide_channel if self.use_spatial else 0)
+
+
+class View3:
+    """Channels [c0, c0 + c) of an NDHWC bf16 tensor with channel stride ld."""
+
+    def __init__(self, buf: DeviceBuffer, n, dhw, c, ld=None, c0=0):
+        self.buf, self.n, self.dhw, self.c = buf, n, tuple(dhw), c
+        self.ld = ld or c
+        self.c0 = c0
+
+    @property
+    def p(self):
+        return C.c_void_p(self.buf.ptr + self.c0 * BF16)
+
+    @property
+    def voxels(self):
+        return self.n * self.dhw[0] * self.dhw[1] * self.dhw[2]
+
+    def slice(self, c0, c):
+        return View3(self.buf, self.n, self.dhw, c, self.ld, self.c0 + c0)
+
+
+@dataclass
+class Layer3:
+    kind: str                 # stem | conv | convT | logits
+    scope: str
+    block: str
+    layer: str
+    cin: int                  # real channels
+    cout: int
+    k: tuple
+    s: tuple
+    dhw: tuple                # input spatial size
+    odhw: tuple = None
+    cinp: int = 0             # stored (padded) channels of the input view
+    coutp: int = 0
+    cin_map: np.ndarray = None   # real input channel -> stored input channel
+    fork: bool = False        # encoder conv2: output also feeds the skip connection
+    x: View3 = None
+    y: View3 = None
+    a: View3 = None
+    norm_off: int = 0
+    params: dict = field(default_factory=dict)
+
+
+@dataclass
+class Param3:
+    name: str
+    shape: tuple              # TF variable shape
+    pshape: tuple             # stored (padded) shape
+    layer: Layer3 = None
+    offset: int = 0
+    size: int = 0             # stored elements
+    region: str = "A"
+
+
+def _cp(c):
+    return _align(c, CPAD)
+
+
+def _model_config(pools: int):
+    """UNet3D._ModelConfig.config[pools] (UNet3D.py:31-91) as (block, layer, kernel, stride)."""
+    if pools not in (4, 5):
+        raise KeyError(f"num_pool_layers {pools}: the reference defines configs for 4 and 5")
+    out = []
+    for i in range(pools):
+        k = (1, 3, 3) if i < 2 else (3, 3, 3)
+        out.append((f"conv_e{i}", "conv1", k, (1, 1, 1) if i == 0 else (1, 2, 2)))
+        out.append((f"conv_e{i}", "conv2", k, (1, 1, 1)))
+    out += [("bridge", "conv1", (3, 3, 3), (2, 2, 2)), ("bridge", "conv2", (3, 3, 3), (1, 1, 1))]
+    for i in reversed(range(pools)):
+        up = (2, 2, 2) if i == pools - 1 else (1, 2, 2)
+        k = (1, 3, 3) if i < 2 else (3, 3, 3)
+        out += [(f"conv_d{i}", "up", up, up), (f"conv_d{i}", "conv1", k, (1, 1, 1)), (f"conv_d{i}", "conv2", k, (1, 1, 1))]
+    return out
+
+
+class UNet3DEngine:
+    def __init__(self, ctx: Context, cfg: UNet3DConfig):
+        self.ctx, self.cfg = ctx, cfg
+        if cfg.normalizer != "instance_norm":
+            raise NotImplementedError("UNet3D engine: --normalizer instance_norm (what the shipped 3-D scripts use)")
+        if "xentropy" not in cfg.loss_type:
+            raise ValueError("Not supported loss_type: {}".format(cfg.loss_type))   # UNet3D.py:198-199
+        if cfg.loss_weight_type not in ("none", "numerical", "proportion"):
+            raise ValueError("Not supported weight type: " + cfg.loss_weight_type)
+        if cfg.loss_weight_type == "numerical" and len(cfg.loss_numeric_w) != cfg.num_classes:
+            raise KeyError("w_type `numerical` need keyword argument `numeric_w` (one value per class)")
+        if 9 * cfg.in_channels > 64:
+            raise ValueError("input channels must be <= 7 (the stem's im2col row holds 9 * channels <= 64 columns)")
+        ds = 2 ** cfg.num_pool_layers
+        if cfg.height % ds or cfg.width % ds or cfg.depth % 2:
+            raise ValueError(f"height/width must be multiples of {ds} and depth even")
+        self.step_count = 0
+        self._bufs = []
+        self.stream = ctx.stream
+        self._plan_layers()
+        self._plan_params()
+        self._plan_activations()
+
+    def _alloc(self, nbytes) -> DeviceBuffer:
+        b = self.ctx.alloc(max(int(nbytes), 16))
+        self._bufs.append(b)
+        return b
+
+    # ------------------------------------------------------------------ planning
+    def _plan_layers(self):
+        cfg = self.cfg
+        layers = []
+        c, cin = cfg.init_channels, cfg.in_channels
+        dhw = (cfg.depth, cfg.height, cfg.width)
+        enc = {}
+        first = True
+        for block, layer, k, s in _model_config(cfg.num_pool_layers):
+            scope = f"UNet3D/{block}/{layer}"
+            if layer == "up":
+                e = enc[block.replace("d", "e")]
+                c = e["c"]
+                L = Layer3("convT", scope, block, layer, cin, c, k, s, dhw, cinp=_cp(cin), coutp=_cp(c))
+                L.odhw = tuple(dhw[i] * s[i] for i in range(3))
+                assert L.odhw == e["dhw"]
+                dhw = L.odhw
+                layers.append(L)
+                cin = 2 * c
+                continue
+            L = Layer3("stem" if first else "conv", scope, block, layer, cin, c, k, s, dhw, coutp=_cp(c))
+            L.odhw = tuple(-(-dhw[i] // s[i]) for i in range(3))
+            if first:
+                L.cinp = 64
+            elif block.startswith("conv_d") and layer == "conv1":
+                L.cinp = 2 * _cp(c)
+                L.cin_map = np.r_[0:c, _cp(c):_cp(c) + c]
+            else:
+                L.cinp = _cp(cin)
+            if L.cin_map is None:
+                L.cin_map = np.arange(cin)
+            first = False
+            dhw = L.odhw
+            layers.append(L)
+            cin = c
+            if layer == "conv2" and (block.startswith("conv_e") or block == "bridge"):
+                if block != "bridge":
+                    L.fork = True
+                    enc[block] = dict(c=c, dhw=dhw)
+                c = min(c * 2, cfg.max_channels)
+        L = Layer3("logits", "UNet3D/logits", "logits", "logits", cin, cfg.num_classes, (1, 1, 1), (1, 1, 1), dhw,
+                   cinp=_cp(cin), coutp=cfg.num_classes)
+        L.odhw = dhw
+        L.cin_map = np.arange(cin)
+        layers.append(L)
+        self.layers = layers
+
+    def _plan_params(self):
+        cfg = self.cfg
+        plist = []
+        for L in self.layers:
+            if L.kind in ("stem", "conv"):
+                ps = (64, L.coutp) if L.kind == "stem" else L.k + (L.cinp, L.coutp)
+                plist.append(Param3(f"{L.scope}/weights", L.k + (L.cin, L.cout), ps, L))
+                plist.append(Param3(f"{L.scope}/InstanceNorm/gamma", (L.cout,), (L.coutp,), L, region="B"))
+                plist.append(Param3(f"{L.scope}/InstanceNorm/beta", (L.cout,), (L.coutp,), L, region="B"))
+            elif L.kind == "convT":
+                plist.append(Param3(f"{L.scope}/weights", L.k + (L.cout, L.cin), L.k + (L.coutp, L.cinp), L))
+            else:
+                plist.append(Param3(f"{L.scope}/weights", (1, 1, 1, L.cin, L.cout), (L.cinp, L.cout), L))
+                plist.append(Param3(f"{L.scope}/biases", (L.cout,), (L.cout,), L, region="B" if cfg.bias_decay else "A"))
+        off = 0
+        for region in ("A", "B"):
+            for p in plist:
+                if p.region == region:
+                    p.size = int(np.prod(p.pshape))
+                    p.offset = off
+                    off += _align(p.size)
+            if region == "A":
+                self.n_reg = off
+        self.n_train = off
+        self.params = {p.name: p for p in plist}
+        self.W = self._alloc(self.n_train * F32)
+        self.Wbf = self._alloc(self.n_train * BF16)
+        if cfg.training:
+            self.G = self._alloc(self.n_train * F32).zero()
+            self.M = self._alloc(self.n_train * F32).zero()
+            self.V = self._alloc(self.n_train * F32).zero() if cfg.optimizer == "adam" else None
+        self.sumsq = self._alloc(16)
+
+    def _pp(self, arena, name, esize=F32):
+        return C.c_void_p(arena.ptr + self.params[name].offset * esize)
+
+    def _plan_activations(self):
+        cfg, n = self.cfg, self.cfg.batch
+        cat, max_act, small = {}, 0, 0
+        prev = None
+        for L in self.layers:
+            vox = int(np.prod(L.odhw))
+            if L.kind in ("stem", "conv"):
+                L.y = View3(self._alloc(n * vox * L.coutp * BF16), n, L.odhw, L.coutp)
+                if L.fork:
+                    cb = View3(self._alloc(n * vox * 2 * L.coutp * BF16).zero(), n, L.odhw, 2 * L.coutp)
+                    cat[L.block] = cb
+                    L.a = cb.slice(0, L.coutp)
+                else:
+                    L.a = View3(self._alloc(n * vox * L.coutp * BF16), n, L.odhw, L.coutp)
+                is_dec1 = L.block.startswith("conv_d") and L.layer == "conv1"
+                L.x = cat[L.block.replace("d", "e")] if is_dec1 else prev
+                prev = L.a
+                L.norm_off = small
+                small += 10 * _align(n * L.coutp, 16)
+                max_act = max(max_act, vox * L.coutp)
+            elif L.kind == "convT":
+                L.x = prev
+                cb = cat[L.block.replace("d", "e")]
+                L.a = cb.slice(L.coutp, L.coutp)
+                L.y = L.a
+                prev = cb
+            else:
+                L.x = prev
+        self.cat = cat
+        d, h, w = cfg.depth, cfg.height, cfg.width
+        nvox = n * d * h * w
+        self.images = self._alloc(nvox * cfg.in_channels * F32)
+        self.stem_col = self._alloc(nvox * 64 * BF16)
+        self.labels = self._alloc(nvox * 4)
+        k = cfg.num_classes
+        self.logits = self._alloc(nvox * k * F32)
+        self.prob = self._alloc(nvox * k * F32)
+        self.masks = self._alloc(nvox * (k - 1))
+        self.argmax = self._alloc(nvox)
+        self.ilr = self._alloc(n * (k - 1) * 3 * 4)
+        self.counts = self._alloc(n * k * 4)
+        self.loss_dev = self._alloc(16)
+        self.small = self._alloc(max(small, 16) * F32)
+        ld = self._loss_desc()
+        self.loss_ws_bytes = self.ctx.lib.bsl_loss_workspace(self.ctx.h, C.byref(ld))
+        self.loss_ws = self._alloc(self.loss_ws_bytes)
+        if cfg.training:
+            self.dlogits = self._alloc(nvox * k * F32)
+            self.g1 = self._alloc(n * max_act * BF16)
+            self.g2 = self._alloc(n * max_act * BF16)
+            self.dcat = {b: View3(self._alloc(v.voxels * v.c * BF16), n, v.dhw, v.c) for b, v in cat.items()}
+            ws = 0
+            for L in self.layers:
+                if L.kind == "stem":
+                    dd = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], 64, L.coutp, 1, 1, 64, L.coutp)
+                    ws = max(ws, self.ctx.lib.bsl_conv2d_wgrad_workspace(self.ctx.h, C.byref(dd)))
+                elif L.kind == "conv":
+                    if self._is2d(L):
+                        ws = max(ws, self.ctx.lib.bsl_conv2d_wgrad_workspace(self.ctx.h, C.byref(self._desc2(L))))
+                    else:
+                        ws = max(ws, self.ctx.lib.bsl_conv3d_wgrad_workspace(self.ctx.h, C.byref(self._desc3(L))))
+                elif L.kind == "convT":
+                    if L.s[0] == 1:
+                        ws = max(ws, self.ctx.lib.bsl_convT2d_bwd_filter_workspace(self.ctx.h, C.byref(self._descT2(L))))
+                    else:
+                        ws = max(ws, self.ctx.lib.bsl_convT3d_bwd_filter_workspace(self.ctx.h, C.byref(self._descT3(L))))
+            self.wgrad_ws_bytes = int(ws)
+            self.wgrad_ws = self._alloc(max(ws, 16))
+
+    # ------------------------------------------------------------------ descriptors
+    @staticmethod
+    def _is2d(L: Layer3):
+        return L.k[0] == 1 and L.s == (1, 1, 1)
+
+    def _desc2(self, L: Layer3):
+        n = self.cfg.batch
+        return _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.coutp, L.k[1], L.k[2], L.x.ld, L.y.ld)
+
+    def _desc3(self, L: Layer3):
+        return _lib.Conv3dDesc(self.cfg.batch, L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.coutp, L.k[0], L.k[1], L.k[2],
+                               L.s[0], L.s[1], L.s[2], L.x.ld, L.y.ld)
+
+    def _descT2(self, L: Layer3):
+        return _lib.ConvT2dDesc(self.cfg.batch * L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.coutp, L.x.ld, L.a.ld, 1)
+
+    def _descT3(self, L: Layer3):
+        return _lib.ConvT3dDesc(self.cfg.batch, L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.coutp, L.s[0], L.x.ld, L.a.ld, 1)
+
+    def _norm_desc(self, L: Layer3):
+        return _lib.NormDesc(1, self.cfg.batch, int(np.prod(L.odhw)), L.coutp, L.y.ld, L.a.ld, self.cfg.in_eps, 0.0,
+                             1, 1, 1)
+
+    def _norm_ptrs(self, L: Layer3):
+        n = _align(self.cfg.batch * L.coutp, 16)
+        base = self.small.ptr + L.norm_off * F32
+        names = ["sums", "_s1", "_s2", "_s3", "mean", "rstd", "scale", "shift", "c1", "c2"]
+        return {nm: C.c_void_p(base + i * n * F32) for i, nm in enumerate(names)}
+
+    def _loss_desc(self):
+        cfg = self.cfg
+        wt = {"none": 0, "numerical": 1, "proportion": 2}[cfg.loss_weight_type]
+        nw = (C.c_float * 8)(*([float(x) for x in cfg.loss_numeric_w] + [0.0] * (8 - len(cfg.loss_numeric_w))))
+        return _lib.LossDesc(cfg.batch, cfg.depth * cfg.height * cfg.width, cfg.num_classes, wt, nw,
+                             float(cfg.loss_proportion_decay), 1.0 / cfg.world)
+
+    def _flops(self, L: Layer3) -> float:
+        n = self.cfg.batch
+        taps = 1 if L.kind == "convT" else int(np.prod(L.k))
+        return 2.0 * n * float(np.prod(L.odhw)) * taps * L.cin * L.cout
+
+    def step_flops(self) -> dict:
+        fwd = sum(self._flops(L) for L in self.layers)
+        bwd = sum(self._flops(L) * (1 if L.kind == "stem" else 2) for L in self.layers)
+        return {"fwd": fwd, "bwd": bwd, "total": fwd + bwd}
+
+    # ------------------------------------------------------------------ weights (pack / unpack)
+    def _pack(self, p: Param3, a: np.ndarray) -> np.ndarray:
+        L = p.layer
+        out = np.zeros(p.pshape, np.float32)
+        if p.name.endswith("/weights"):
+            if L.kind == "stem":
+                out[:a.shape[1] * a.shape[2] * a.shape[3], :L.cout] = a.reshape(-1, L.cout)
+            elif L.kind == "conv":
+                out[:, :, :, L.cin_map, :L.cout] = a
+            elif L.kind == "convT":
+                out[:, :, :, :L.cout, :L.cin] = a
+            else:
+                out[L.cin_map, :] = a.reshape(L.cin, L.cout)
+        else:
+            out[:a.shape[0]] = a
+        return out
+
+    def _unpack(self, p: Param3, flat: np.ndarray) -> np.ndarray:
+        L = p.layer
+        a = flat[p.offset:p.offset + p.size].reshape(p.pshape)
+        if p.name.endswith("/weights"):
+            if L.kind == "stem":
+                return a[:int(np.prod(p.shape[:4])), :L.cout].reshape(p.shape).copy()
+            if L.kind == "conv":
+                return a[:, :, :, L.cin_map, :L.cout].copy()
+            if L.kind == "convT":
+                return a[:, :, :, :L.cout, :L.cin].copy()
+            return a[L.cin_map, :].reshape(p.shape).copy()
+        return a[:p.shape[0]].copy()
+
+    def set_weights(self, weights: dict):
+        host = np.zeros(self.n_train, np.float32)
+        for name, p in self.params.items():
+            if name not in weights:
+                raise KeyError(f"missing variable {name}")
+            a = np.asarray(weights[name], np.float32)
+            if tuple(a.shape) != tuple(p.shape):
+                raise ValueError(f"{name}: shape {a.shape} != {p.shape}")
+            host[p.offset:p.offset + p.size] = self._pack(p, a).ravel()
+        self.W.upload(host)
+        self.Wbf.upload(f32_to_bf16_bits(host))
+
+    def get_weights(self) -> dict:
+        host = self.W.download(np.float32, (self.n_train,))
+        return {name: self._unpack(p, host) for name, p in self.params.items()}
+
+    def get_grads(self) -> dict:
+        host = self.G.download(np.float32, (self.n_train,))
+        return {name: self._unpack(p, host) for name, p in self.params.items()}
+
+    def init_weights(self, seed: int = 0):
+        rng = np.random.default_rng(seed)
+        w = {}
+        for name, p in self.params.items():
+            shp = p.shape
+            if name.endswith("/weights"):
+                rf = int(np.prod(shp[:3]))
+                lim = np.sqrt(6.0 / (rf * shp[3] + rf * shp[4]))
+                w[name] = rng.uniform(-lim, lim, size=shp).astype(np.float32)
+            elif name.endswith("gamma"):
+                w[name] = np.ones(shp, np.float32)
+            else:
+                w[name] = np.zeros(shp, np.float32)
+        self.set_weights(w)
+        return w
+
+    def set_inputs(self, images: np.ndarray, labels: np.ndarray | None = None, sp_guide: np.ndarray | None = None):
+        cfg = self.cfg
+        shp = (cfg.batch, cfg.depth, cfg.height, cfg.width)
+        assert images.shape == shp + (cfg.channel,), images.shape
+        if cfg.use_spatial:
+            assert sp_guide is not None and sp_guide.shape == shp + (cfg.guide_channel,)
+            images = np.concatenate((images, sp_guide), axis=-1)      # UNet3D.py:142-144
+        self.images.upload(np.ascontiguousarray(images, np.float32))
+        if labels is not None:
+            assert labels.shape == shp, labels.shape
+            self.labels.upload(np.ascontiguousarray(labels, np.int32))
+
+    def get_stored_forward(self) -> dict:
+        out = {}
+        for L in self.layers:
+            if L.kind == "logits":
+                continue
+            dct = {}
+            for key, v in (("y", L.y), ("a", L.a)):
+                full = self.ctx.bf16_to_f32(v.buf, (v.n,) + v.dhw + (v.ld,))
+                dct[key] = full[..., v.c0:v.c0 + L.cout].copy()
+                pad = full[..., v.c0 + L.cout:v.c0 + v.c]
+                assert not pad.any(), f"{L.scope}: pad lanes of {key} are not zero"
+            out[L.scope] = dct
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, is_training: bool = True):
+        ctx, s, cfg = self.ctx, self.stream, self.cfg
+        call = ctx.call
+        n = cfg.batch
+        for L in self.layers:
+            ctx.tag = L.scope
+            if L.kind in ("stem", "conv"):
+                wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
+                if L.kind == "stem":
+                    d0 = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], L.cin, 64, 3, 3, L.cin, 64)
+                    call("bsl_stem_im2col", C.byref(d0), self.images.p, self.stem_col.p, s)
+                    d1 = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], 64, L.coutp, 1, 1, 64, L.y.ld)
+                    call("bsl_conv2d_fprop", C.byref(d1), self.stem_col.p, wbf, L.y.p, s)
+                elif self._is2d(L):
+                    call("bsl_conv2d_fprop", C.byref(self._desc2(L)), L.x.p, wbf, L.y.p, s)
+                else:
+                    call("bsl_conv3d_fprop", C.byref(self._desc3(L)), L.x.p, wbf, L.y.p, s)
+                nd, q = self._norm_desc(L), self._norm_ptrs(L)
+                call("bsl_norm_stats", C.byref(nd), L.y.p, q["sums"], s)
+                call("bsl_norm_finalize", C.byref(nd), C.c_int(1 if is_training else 0), q["sums"],
+                     self._pp(self.W, f"{L.scope}/InstanceNorm/gamma"), self._pp(self.W, f"{L.scope}/InstanceNorm/beta"),
+                     None, None, q["mean"], q["rstd"], q["scale"], q["shift"], s)
+                call("bsl_norm_apply", C.byref(nd), L.y.p, q["scale"], q["shift"], L.a.p, s)
+            elif L.kind == "convT":
+                wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
+                if L.s[0] == 1:
+                    call("bsl_convT2d_fwd", C.byref(self._descT2(L)), L.x.p, wbf, None, L.a.p, s)
+                else:
+                    call("bsl_convT3d_fwd", C.byref(self._descT3(L)), L.x.p, wbf, None, L.a.p, s)
+            else:
+                dh = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.cout, 1, 1, L.x.ld, L.cout)
+                call("bsl_conv2d_head_fprop", C.byref(dh), L.x.p, self._pp(self.W, f"{L.scope}/weights"),
+                     self._pp(self.W, f"{L.scope}/biases"), self.logits.p, s)
+
+    def predict_outputs(self, with_counts: bool):
+        ld = self._loss_desc()
+        self.ctx.call("bsl_softmax_threshold", C.byref(ld), self.logits.p, self.labels.p if with_counts else None,
+                      self.prob.p, self.masks.p, self.argmax.p, self.ilr.p if with_counts else None, self.stream)
+
+    # ------------------------------------------------------------------ loss + backward
+    def loss_backward(self):
+        ctx, s, cfg = self.ctx, self.stream, self.cfg
+        call = ctx.call
+        n = cfg.batch
+        ld = self._loss_desc()
+        call("bsl_label_counts", C.byref(ld), self.labels.p, self.counts.p, s)
+        call("bsl_wxent_fwd_bwd", C.byref(ld), self.logits.p, self.labels.p, self.counts.p, self.loss_dev.p,
+             self.dlogits.p, self.loss_ws.p, C.c_size_t(self.loss_ws_bytes), s)
+        cur, oth = self.g1, self.g2
+        wsb = C.c_size_t(self.wgrad_ws_bytes)
+        for L in reversed(self.layers):
+            ctx.tag = L.scope
+            if L.kind == "logits":
+                dh = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.cout, 1, 1, L.x.ld, L.cout)
+                call("bsl_conv2d_head_wgrad", C.byref(dh), L.x.p, self.dlogits.p, self._pp(self.G, f"{L.scope}/weights"),
+                     self._pp(self.G, f"{L.scope}/biases"), s)
+                dh.x_ld = L.cinp
+                call("bsl_conv2d_head_dgrad", C.byref(dh), self.dlogits.p, self._pp(self.W, f"{L.scope}/weights"), cur.p, s)
+            elif L.kind in ("stem", "conv"):
+                vox = n * int(np.prod(L.odhw))
+                if L.fork:   # AddN: gradient through the next block's strided conv + gradient through the skip
+                    dc = self.dcat[L.block]
+                    call("bsl_add_bf16", C.c_longlong(vox), C.c_int(L.coutp), cur.p, C.c_int(L.coutp), dc.p,
+                         C.c_int(dc.ld), oth.p, C.c_int(L.coutp), s)
+                    cur, oth = oth, cur
+                nd, q = self._norm_desc(L), self._norm_ptrs(L)
+                call("bsl_norm_bwd_reduce", C.byref(nd), L.y.p, cur.p, C.c_int(L.coutp), q["mean"], q["rstd"], q["scale"],
+                     q["shift"], q["sums"], s)
+                call("bsl_norm_bwd_finalize", C.byref(nd), q["sums"], q["c1"], q["c2"],
+                     self._pp(self.G, f"{L.scope}/InstanceNorm/gamma"), self._pp(self.G, f"{L.scope}/InstanceNorm/beta"), s)
+                call("bsl_norm_bwd_apply", C.byref(nd), L.y.p, cur.p, C.c_int(L.coutp), q["mean"], q["rstd"], q["scale"],
+                     q["shift"], q["c1"], q["c2"], oth.p, C.c_int(L.coutp), s)
+                gw = self._pp(self.G, f"{L.scope}/weights")
+                wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
+                if L.kind == "stem":
+                    d1 = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], 64, L.coutp, 1, 1, 64, L.coutp)
+                    call("bsl_conv2d_wgrad", C.byref(d1), self.stem_col.p, oth.p, gw, self.wgrad_ws.p, wsb, s)
+                    continue
+                is_dec1 = L.block.startswith("conv_d") and L.layer == "conv1"
+                dx = self.dcat[L.block.replace("d", "e")] if is_dec1 else None
+                if self._is2d(L):
+                    d = self._desc2(L)
+                    d.y_ld = L.coutp
+                    call("bsl_conv2d_wgrad", C.byref(d), L.x.p, oth.p, gw, self.wgrad_ws.p, wsb, s)
+                    d.x_ld = dx.ld if dx is not None else L.cinp
+                    call("bsl_conv2d_dgrad", C.byref(d), oth.p, wbf, dx.p if dx is not None else cur.p, s)
+                else:
+                    d = self._desc3(L)
+                    d.y_ld = L.coutp
+                    call("bsl_conv3d_wgrad", C.byref(d), L.x.p, oth.p, gw, self.wgrad_ws.p, wsb, s)
+                    d.x_ld = dx.ld if dx is not None else L.cinp
+                    call("bsl_conv3d_dgrad", C.byref(d), oth.p, wbf, dx.p if dx is not None else cur.p, s)
+            else:  # convT
+                dc = self.dcat[L.block.replace("d", "e")]
+                dup = dc.slice(L.coutp, L.coutp)
+                vox = n * int(np.prod(L.odhw))
+                call("bsl_relu_bwd", C.c_longlong(vox), C.c_int(L.coutp), L.a.p, C.c_int(L.a.ld), dup.p, C.c_int(dup.ld),
+                     dup.p, C.c_int(dup.ld), s)
+                gw = self._pp(self.G, f"{L.scope}/weights")
+                wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
+                if L.s[0] == 1:
+                    d = self._descT2(L)
+                    d.y_ld = dup.ld
+                    call("bsl_convT2d_bwd_filter", C.byref(d), L.x.p, dup.p, gw, None, self.wgrad_ws.p, wsb, s)
+                    d.x_ld = L.cinp
+                    call("bsl_convT2d_bwd_data", C.byref(d), dup.p, wbf, cur.p, s)
+                else:
+                    d = self._descT3(L)
+                    d.y_ld = dup.ld
+                    call("bsl_convT3d_bwd_filter", C.byref(d), L.x.p, dup.p, gw, None, self.wgrad_ws.p, wsb, s)
+                    d.x_ld = L.cinp
+                    call("bsl_convT3d_bwd_data", C.byref(d), dup.p, wbf, cur.p, s)
+
+    # ------------------------------------------------------------------ optimizer / step
+    def attach_comm(self, rank: int, world: int, unique_id: bytes):
+        assert world == self.cfg.world
+        buf = (C.c_char * 128).from_buffer_copy(unique_id)
+        self.ctx.call("bsl_comm_init", buf, C.c_int(rank), C.c_int(world))
+
+    def optimizer_step(self, lr: float):
+        ctx, s, cfg = self.ctx, self.stream, self.cfg
+        self.step_count += 1
+        l2 = cfg.weight_decay_rate if cfg.weight_decay_rate > 0 else 0.0
+        for off, cnt, rate, sq in ((0, self.n_reg, l2, self.sumsq.p), (self.n_reg, self.n_train - self.n_reg, 0.0, None)):
+            if cnt <= 0:
+                continue
+            w, g, m = (C.c_void_p(a.ptr + off * F32) for a in (self.W, self.G, self.M))
+            wb = C.c_void_p(self.Wbf.ptr + off * BF16)
+            if cfg.optimizer == "adam":
+                v = C.c_void_p(self.V.ptr + off * F32)
+                d = _lib.AdamDesc(lr, 0.9, 0.99, 1e-8, rate, 1.0, self.step_count)
+                ctx.call("bsl_adam_step", C.byref(d), w, g, m, v, wb, C.c_size_t(cnt), sq, s)
+            elif cfg.optimizer == "momentum":
+                ctx.call("bsl_momentum_step", C.c_float(lr), C.c_float(0.9), C.c_float(rate), C.c_float(1.0), w, g, m, wb,
+                         C.c_size_t(cnt), sq, s)
+            else:
+                raise ValueError("Not supported optimizer: " + cfg.optimizer)
+
+    def train_step(self, lr: float, with_metrics: bool = False):
+        self.forward(True)
+        if with_metrics:
+            self.predict_outputs(True)
+        self.loss_backward()
+        if self.cfg.world > 1:
+            self.ctx.call("bsl_allreduce_sum_f32", self.G.p, C.c_size_t(self.n_train), self.stream)
+        self.optimizer_step(lr)
+
+    def read_loss(self):
+        data = self.loss_dev.download(np.float32, (1,))[0]
+        sq = self.sumsq.download(np.float64, (1,))[0]
+        return float(data), float(self.cfg.weight_decay_rate * 0.5 * sq) if self.cfg.weight_decay_rate > 0 else 0.0
+
+    def read_counts(self):
+        return self.ilr.download(np.uint32, (self.cfg.batch, self.cfg.num_classes - 1, 3))
+
+    def close(self):
+        for b in self._bufs:
+            b.free()
+        self._bufs = []
