@@ -183,10 +183,60 @@ class UNetEngine:
         buf = (C.c_char * 128).from_buffer_copy(unique_id)
         self.ctx.call("bsl_comm_init", buf, C.c_int(rank), C.c_int(world))
         self.rank = rank
+        self._plan_buckets()
+
+    # Gradient exchange overlapped with backward (replaces AllReduceCrossDeviceOps("nccl", num_packs=2),
+    # /root/reference/utils/distribution_utils.py:91-98): the regularised region of the gradient arena is laid out in
+    # forward layer order and backward fills it from the end, so a bucket is a suffix range that is complete as soon
+    # as its first layer's wgrad has been enqueued. Each bucket is all-reduced on a side stream behind an event.
+    BUCKET_ELEMS = 6 << 20
+
+    def _plan_buckets(self):
+        self.comm_stream = self.ctx.new_stream()
+        self._ev_ready = [self.ctx.new_event() for _ in range(16)]
+        self._ev_done = self.ctx.new_event()
+        self._bucket_at = {}          # scope of the layer that closes a bucket -> (offset, count)
+        # parameters outside the conv trunk (GUNet guide convs) sit after the last layer in region A and get their
+        # gradients late in backward: they travel with the tail
+        lastp = [p for p in self.params.values() if p.region == "A" and p.name.startswith(self.layers[-1].scope + "/")]
+        self._trunk_end = max(p.offset + _align(max(p.size, p.alloc)) for p in lastp)
+        end, acc, last = self._trunk_end, 0, None
+        for L in reversed(self.layers):
+            p = self.params[f"{L.scope}/weights"]
+            acc = end - p.offset
+            last = L
+            if acc >= self.BUCKET_ELEMS and len(self._bucket_at) < len(self._ev_ready) - 1:
+                self._bucket_at[L.scope] = (p.offset, acc)
+                end, acc = p.offset, 0
+        if end > 0:
+            self._bucket_at[last.scope] = (0, end)
+        self._bucket_i = 0
+
+    def _after_grad(self, L: ConvL):
+        """Called when layer L's parameter gradients have been enqueued (backward order)."""
+        if self.cfg.world <= 1 or L.scope not in getattr(self, "_bucket_at", {}):
+            return
+        off, cnt = self._bucket_at[L.scope]
+        ev = self._ev_ready[self._bucket_i]
+        self._bucket_i += 1
+        self.ctx.record(ev, self.stream)
+        self.ctx.call("bsl_stream_wait_event", self.comm_stream, ev)
+        self.ctx.call("bsl_allreduce_sum_f32", C.c_void_p(self.G.ptr + off * F32), C.c_size_t(cnt), self.comm_stream)
 
     def _allreduce_grads(self):
-        if self.cfg.world > 1:
+        """Tail of the exchange: the un-regularised region (gamma / beta / FC, tiny), then join the side stream."""
+        if self.cfg.world <= 1:
+            return
+        if self.comm_stream is None:       # attach_comm not called: single all-reduce on the compute stream
             self.ctx.call("bsl_allreduce_sum_f32", self.G.p, C.c_size_t(self.n_train), self.stream)
+            return
+        nb = self.n_train - self._trunk_end
+        if nb > 0:
+            self.ctx.call("bsl_allreduce_sum_f32", C.c_void_p(self.G.ptr + self._trunk_end * F32), C.c_size_t(nb),
+                          self.stream)
+        self.ctx.record(self._ev_done, self.comm_stream)
+        self.ctx.call("bsl_stream_wait_event", self.stream, self._ev_done)
+        self._bucket_i = 0
 
     def _allreduce_moving_stats(self):
         # MirroredStrategy aggregates the moving-average updates with MEAN across replicas
@@ -629,9 +679,6 @@ class UNetEngine:
                 self._tc("convT_dgrad", self._flops(L), "bsl_convT2d_bwd_data", C.byref(d), dup.p,
                          self._pp(self.Wbf, f"{L.scope}/weights", BF16), cur.p, s)
                 self._after_grad(L)
-
-    def _after_grad(self, L: ConvL):
-        """Hook for the bucketed all-reduce: called when layer L's parameter gradients are enqueued."""
 
     # ------------------------------------------------------------------ optimizer
     def optimizer_step(self, lr: float):

@@ -327,6 +327,20 @@ int bsl_dice_fwd_bwd(bsl_ctx* ctx, const bsl_loss_desc* d, const float* logits, 
 int bsl_softmax_threshold(bsl_ctx* ctx, const bsl_loss_desc* d, const float* logits, const int* labels,
                           float* prob, uint8_t* masks, uint8_t* argmax, unsigned int* ilr, void* stream);
 
+/* ------------------------------------------------------------------ forward-only consumers (inference / evaluation)
+ * Test-time mirroring as run_TTA does it on the host (/root/reference/entry/main_eval_3d.py:246-287,
+ * entry/infer_2d.py:60-78): probs += np.flip(prob of the flipped input); avg = probs / count; np.argmax -> uint8;
+ * and ConfusionMatrix.compute (/root/reference/loss_metrics.py:542-556) as exact integer counts.
+ * Tensors are dense fp32 [n][d][h][w][c] (d = 1 for 2-D); `axes` is a bit mask: 1 = W, 2 = H, 4 = D. */
+int bsl_flip_f32(bsl_ctx* ctx, long long n, int d, int h, int w, int c, int axes, int accumulate, const float* src,
+                 float* dst, void* stream); /* dst = (accumulate ? dst : 0) + flip(src); src != dst */
+int bsl_tta_finalize(bsl_ctx* ctx, long long pixels, int classes, int count, const float* acc,
+                     float* avg_prob /*nullable*/, uint8_t* pred, void* stream);
+/* counts4 += {tp, fp, tn, fn}; test = (test_u8 == test_value), or (test_u8 != 0) when test_value < 0;
+ * reference = (labels == ref_value). The caller zeroes counts4 (accumulation over batches is the point). */
+int bsl_confusion_counts(bsl_ctx* ctx, long long n, const uint8_t* test_u8, int test_value, const int* labels,
+                         int ref_value, unsigned long long* counts4, void* stream);
+
 /* ------------------------------------------------------------------ fused optimizer step
  * tf.train.AdamOptimizer(lr, 0.9, 0.99) / MomentumOptimizer(lr, 0.9) -- /root/reference/core/solver.py:204-219,
  * with slim.l2_regularizer folded in (grad += l2_rate * w) -- NetworksV2/base.py:128-135.
