@@ -4,6 +4,9 @@
 //   convT2d fwd / bwd             <- slim.conv2d_transpose, NetworksV2/UNet.py:91
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
 #include "igemm.cuh"
 #include "igemm_halo.cuh"
 #include "internal.h"
@@ -251,6 +254,107 @@ bool wgrad_halo_eligible(const bsl_conv2d_desc* d) {
   return !force_v1() && d->kh == 3 && d->kw == 3 && d->w % WG_TW == 0 && d->h % WG_TH == 0;
 }
 
+// ---- wide wgrad (wgrad_halo2_kernel): split counts for the two CTA classes, chosen by simulating the hardware's
+// in-order block dispatch onto the SMs (one CTA per SM: 216 KB of shared memory each).
+struct Wgrad2Plan {
+  int k_tiles, splits_a, per_a, splits_b, per_b;
+  size_t ws_floats;
+};
+
+bool wgrad2_eligible(const bsl_conv2d_desc* d) {
+  static const int off = getenv("BSL_WGRAD_V2") ? atoi(getenv("BSL_WGRAD_V2")) == 0 : 0;
+  return !off && !force_v1() && d->kh == 3 && d->kw == 3 && d->w % WG_TW == 0 && d->h % WG_TH == 0 && d->cout % 128 == 0;
+}
+
+Wgrad2Plan plan_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
+  Wgrad2Plan best = {};
+  const int k = (d->w / WG_TW) * (d->h / WG_TH) * d->n;
+  const int mn = (d->cin / 64) * (d->cout / 128);
+  const int sms = ctx->sm_count;
+  const double fixed = 6.0;  // prologue + epilogue of a CTA, in units of one (tile, accumulator) step
+  double best_t = 1e300;
+  const int max_a = std::max(1, std::min(k / 2, (2 * sms) / mn + 2));
+  std::vector<double> free_at(sms);
+  for (int na = 1; na <= max_a; ++na) {
+    const int per_a = cdiv(k, na), sa = cdiv(k, per_a);
+    if (sa != na) continue;
+    for (int nb2 = std::max(1, na / 2 - 1); nb2 <= std::min(na, na / 2 + 2); ++nb2) {   // class b has half the work
+      const int per_b = cdiv(k, nb2), sb = cdiv(k, per_b);
+      if (sb != nb2) continue;
+      const double ta = 2.0 * per_a + fixed, tb = 1.0 * per_b + fixed;
+      // in-order dispatch: all class-a CTAs, then class-b, each to the SM that frees up first
+      std::fill(free_at.begin(), free_at.end(), 0.0);
+      const long long ja = (long long)mn * sa, jb = (long long)mn * sb;
+      double makespan = 0;
+      for (long long j = 0; j < ja + jb; ++j) {
+        int arg = 0;
+        for (int m = 1; m < sms; ++m)
+          if (free_at[m] < free_at[arg]) arg = m;
+        free_at[arg] += j < ja ? ta : tb;
+        makespan = std::max(makespan, free_at[arg]);
+      }
+      makespan += 0.02 * (sa + sb);  // a little pressure towards fewer partials to reduce afterwards
+      if (makespan < best_t) {
+        best_t = makespan;
+        best = {k, sa, per_a, sb, per_b, 0};
+      }
+    }
+  }
+  best.ws_floats = ((size_t)(best.splits_a > 1 ? best.splits_a * 6 : 0) + (size_t)(best.splits_b > 1 ? best.splits_b * 3 : 0)) *
+                   d->cin * d->cout;
+  return best;
+}
+
+const Wgrad2Plan& cached_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
+  static std::mutex mu;
+  static std::unordered_map<unsigned long long, Wgrad2Plan> cache;
+  const unsigned long long key = ((unsigned long long)d->n << 48) ^ ((unsigned long long)d->h << 36) ^
+                                 ((unsigned long long)d->w << 24) ^ ((unsigned long long)d->cin << 12) ^ d->cout;
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) it = cache.emplace(key, plan_wgrad2(ctx, d)).first;
+  return it->second;
+}
+
+int conv2d_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* dy, float* dw, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream) {
+  const Wgrad2Plan& p = cached_wgrad2(ctx, d);
+  if (p.ws_floats * sizeof(float) > workspace_bytes || (p.ws_floats && !workspace))
+    return bsl_fail(ctx, BSL_EWORKSPACE, "conv2d_wgrad: workspace %zu < %zu", workspace_bytes, p.ws_floats * sizeof(float));
+  const int xbox[4] = {WG_TW + 2, WG_TH + 2, 1, 1}, ybox[4] = {WG_TW, WG_TH, 1, 1};
+  CUtensorMap tx, ty;
+  int rc;
+  if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, xbox, &tx))) return rc;
+  if ((rc = nhwc_map(ctx, dy, d->cout, d->w, d->h, d->n, d->y_ld, ybox, &ty))) return rc;
+  const long long per_tap = (long long)d->cin * d->cout;
+  float* ws = reinterpret_cast<float*>(workspace);
+  WgradHalo2Args a = {};
+  a.ntile_w = d->w / WG_TW;
+  a.ntile_h = d->h / WG_TH;
+  a.n = d->n;
+  a.k_tiles_total = p.k_tiles;
+  a.splits_a = p.splits_a;
+  a.per_a = p.per_a;
+  a.splits_b = p.splits_b;
+  a.per_b = p.per_b;
+  a.cin = d->cin;
+  a.cout = d->cout;
+  a.out_a = p.splits_a > 1 ? ws : dw;
+  a.out_b = p.splits_b > 1 ? ws + (p.splits_a > 1 ? (long long)p.splits_a * 6 * per_tap : 0) : dw + 6 * per_tap;
+  a.status = ctx->d_status;
+  static bool configured = false;
+  if (!configured) {
+    BSL_CUDA(ctx, cudaFuncSetAttribute(wgrad_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_BYTES));
+    configured = true;
+  }
+  wgrad_halo2_kernel<<<dim3(d->cin / 64, d->cout / 128, p.splits_a + p.splits_b), WG_THREADS, WG2_SMEM_BYTES, stream>>>(
+      tx, ty, a);
+  BSL_LAUNCH_CHECK(ctx, "wgrad_halo2_kernel launch");
+  if (p.splits_a > 1 && (rc = reduce_splits(ctx, a.out_a, dw, 6 * per_tap, p.splits_a, stream))) return rc;
+  if (p.splits_b > 1 && (rc = reduce_splits(ctx, a.out_b, dw + 6 * per_tap, 3 * per_tap, p.splits_b, stream))) return rc;
+  return BSL_OK;
+}
+
 WgradPlan plan_wgrad_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
   WgradPlan p;
   p.k_tiles = (d->w / WG_TW) * (d->h / WG_TH) * d->n;
@@ -407,6 +511,7 @@ int bsl_conv2d_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, con
 
 size_t bsl_conv2d_wgrad_workspace(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
   if (!ctx || !d || check_conv(ctx, d)) return 0;
+  if (wgrad2_eligible(d)) return cached_wgrad2(ctx, d).ws_floats * sizeof(float);
   if (wgrad_halo_eligible(d)) {
     const WgradPlan p = plan_wgrad_halo(ctx, d);
     return p.splits > 1 ? (size_t)p.splits * 9 * d->cin * d->cout * sizeof(float) : 0;
@@ -426,6 +531,7 @@ int bsl_conv2d_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, cons
   int rc = check_conv(ctx, d);
   if (rc) return rc;
   if (!x || !dy || !dw) return bsl_fail(ctx, BSL_EINVAL, "conv2d_wgrad: null buffer");
+  if (wgrad2_eligible(d)) return conv2d_wgrad2(ctx, d, x, dy, dw, workspace, workspace_bytes, as_stream(stream));
   if (wgrad_halo_eligible(d)) {
     const WgradPlan p = plan_wgrad_halo(ctx, d);
     const size_t need = p.splits > 1 ? (size_t)p.splits * 9 * d->cin * d->cout * sizeof(float) : 0;

@@ -181,6 +181,158 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------ wgrad, wide
+// Second filter-gradient kernel for layers with cout % 128 == 0. wgrad_halo_kernel issues 128 x 64 x 16 UMMAs, whose
+// operand fetch (6 KB per 32 tensor-pipe cycles) saturates the shared-memory read path at ~55 % tensor utilisation
+// (profiles/r01_ncu_full_conv_kernels.txt: l1tex tc wavefronts 82 %). Here the roles are swapped: A = dy tile
+// (M = 128 output channels), B = THREE taps of one filter row read from the halo tile as a 192-wide MN-major operand
+// (the 64-element blocks of the descriptor are 128 B = one pixel apart), so one UMMA is 128 x 192 x 16: 10 KB of
+// operands per 96 cycles. A CTA owns 64 input x 128 output channels and either filter rows r = 0, 1 (two 192-column
+// accumulators) or row r = 2 (one accumulator, given twice the pixel range), split-K over pixel tiles.
+struct WgradHalo2Args {
+  int ntile_w, ntile_h, n;       // pixel tiles of 16 (w) x 4 (h)
+  int k_tiles_total;
+  int splits_a, per_a;           // blockIdx.z <  splits_a: rows 0, 1 over tiles [z * per_a, ...)
+  int splits_b, per_b;           // blockIdx.z >= splits_a: row 2 over tiles [(z - splits_a) * per_b, ...)
+  int cin, cout;
+  float* out_a;                  // [splits_a][6][cin][cout]
+  float* out_b;                  // [splits_b][3][cin][cout]
+  DeviceStatus* status;
+};
+
+constexpr int WG2_DY_BYTES = 2 * WG_DY_BYTES;           // 128 output channels = two 64-channel blocks
+constexpr int WG2_STAGE_BYTES = WG_X_BYTES + WG2_DY_BYTES;
+constexpr int WG2_STAGES = 7;
+constexpr int WG2_SMEM_BYTES = WG2_STAGES * WG2_STAGE_BYTES + 1024;
+
+// grid = (cin / 64, cout / 128, splits_a + splits_b)
+__global__ void __launch_bounds__(WG_THREADS)
+wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                   const WgradHalo2Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * WG2_STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int dead;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t full0 = smem_u32(&bars[0]);
+  const uint32_t empty0 = smem_u32(&bars[WG2_STAGES]);
+  const uint32_t tfull = smem_u32(&bars[2 * WG2_STAGES]);
+  DeviceStatus* st = p.status;
+
+  if (threadIdx.x == 0) dead = *reinterpret_cast<volatile int*>(&st->error);
+  __syncthreads();
+  if (dead) return;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmX);
+    prefetch_tensormap(&tmDY);
+    for (int s = 0; s < WG2_STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc<512>(smem_u32(&tmem_slot));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+
+  const int cb = blockIdx.x, nb = blockIdx.y;
+  const bool type_a = (int)blockIdx.z < p.splits_a;
+  const int zi = type_a ? blockIdx.z : blockIdx.z - p.splits_a;
+  const int per = type_a ? p.per_a : p.per_b;
+  const int k_begin = zi * per;
+  const int k_end = min(p.k_tiles_total, k_begin + per);
+  const int num_k = max(k_end - k_begin, 0);
+  const int nacc = type_a ? 2 : 1;
+  const int r0 = type_a ? 0 : 2;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kk = 0; kk < num_k; ++kk) {
+        if (!mbar_wait(empty0 + 8 * stage, phase ^ 1, st, 14)) break;
+        int t = k_begin + kk;
+        const int tx = t % p.ntile_w;
+        t /= p.ntile_w;
+        const int ty = t % p.ntile_h;
+        const int img = t / p.ntile_h;
+        const uint32_t fb = full0 + 8 * stage;
+        const uint32_t sx = smem_base + stage * WG2_STAGE_BYTES;
+        mbar_arrive_expect_tx(fb, WG_X_ROWS * 128 + WG2_DY_BYTES);
+        tma_load_5d(sx, &tmX, fb, cb * 64, tx * WG_TW - 1, ty * WG_TH - 1, img, 0);
+        tma_load_5d(sx + WG_X_BYTES, &tmDY, fb, nb * 128, tx * WG_TW, ty * WG_TH, img, 0);
+        tma_load_5d(sx + WG_X_BYTES + WG_DY_BYTES, &tmDY, fb, nb * 128 + 64, tx * WG_TW, ty * WG_TH, img, 0);
+        if (++stage == WG2_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 192, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int kk = 0; kk < num_k; ++kk) {
+        if (!mbar_wait(full0 + 8 * stage, phase, st, 15)) { ok = false; break; }
+        tc_fence_after();
+        const uint32_t sx = smem_base + stage * WG2_STAGE_BYTES;
+        const uint64_t da0 = make_smem_desc_sw128(sx + WG_X_BYTES, WG_DY_BYTES, 1024);
+        const uint32_t first = kk != 0;
+#pragma unroll
+        for (int y = 0; y < WG_TH; ++y) {
+          for (int a = 0; a < nacc; ++a) {
+            // taps (r0 + a, 0..2): three 64-channel blocks one pixel (128 B) apart, 16 pixels of row y as K
+            const uint64_t db = make_smem_desc_sw128(sx + ((r0 + a + y) * WG_PITCH) * 128, 128, 1024);
+            umma_bf16(tmem_base + a * 192, da0 + (uint64_t)((y * WG_TW * 128) >> 4), db, idesc,
+                      first | (uint32_t)(y != 0));
+          }
+        }
+        umma_commit(empty0 + 8 * stage);
+        if (++stage == WG2_STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (ok) umma_commit(tfull);
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;  // accumulator row = output channel within the 128-block
+    const bool alive = mbar_wait(tfull, 0, st, 16);
+    tc_fence_after();
+    if (alive) {
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+      const int ntap = type_a ? 6 : 3;
+      float* obase = (type_a ? p.out_a : p.out_b) + (long long)zi * ntap * p.cin * p.cout + nb * 128 + row;
+#pragma unroll 1
+      for (int a = 0; a < nacc; ++a) {
+#pragma unroll 1
+        for (int c = 0; c < 192; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + a * 192 + c, v);
+          tmem_ld_wait();
+          const int tap = a * 3 + c / 64;             // local tap index within this CTA's rows
+          float* o = obase + ((long long)tap * p.cin + cb * 64 + (c & 63)) * p.cout;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[(long long)j * p.cout] = num_k ? __uint_as_float(v[j]) : 0.f;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ fprop / dgrad
 struct ConvHaloArgs {
   int ntile_w, ntile_h, n;       // sub-tiles of 8 (w) x 16 (h) pixels
