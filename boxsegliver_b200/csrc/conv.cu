@@ -198,6 +198,64 @@ int launch_halo_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, co
   return BSL_OK;
 }
 
+struct HaloPlan {
+  int bn, nsub, n_ntiles, n_sub_total, n_units, grid, slots;
+};
+
+template <int BN, int NSUB, bool B_MN, bool STATS, bool SCATTER>
+int launch_halo_res_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args, int grid,
+                        int smem, cudaStream_t stream) {
+  auto kern = conv_halo_kernel<BN, NSUB, B_MN, STATS, SCATTER, true>;
+  static int configured = 0;
+  if (configured < smem) {
+    BSL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  kern<<<grid, CH_THREADS, smem, stream>>>(a, b, args);
+  BSL_LAUNCH_CHECK(ctx, "conv_halo_kernel (resident filter) launch");
+  return BSL_OK;
+}
+
+// Resident-filter plan: returns false when the filter slice of one column tile does not fit beside >= 2
+// activation stages. May lower nsub to 1 (the filter is no longer re-read per unit, so sharing it matters less).
+constexpr int CH_DYN_BUDGET = 232448 - 10 * 1024;   // 227 KB minus static shared memory (barriers, statistics)
+bool plan_resident(int bn, int ntaps, int cblocks, int* nsub, int* a_stages, int* smem) {
+  static const int off = getenv("BSL_B_RES") ? atoi(getenv("BSL_B_RES")) == 0 : 0;
+  if (off || bn > 128) return false;
+  const int res = ntaps * cblocks * bn * 128;
+  const int left = CH_DYN_BUDGET - 1024 - res;
+  if (left <= 0) return false;
+  const int s2 = std::min(CH_MAX_A_STAGES, left / (2 * CH_SUB_BYTES)), s1 = std::min(CH_MAX_A_STAGES, left / CH_SUB_BYTES);
+  int ns, st;
+  if (*nsub == 2 && s2 >= 3) { ns = 2; st = s2; }
+  else if (s1 >= 3) { ns = 1; st = s1; }
+  else if (*nsub == 2 && s2 >= 2) { ns = 2; st = s2; }
+  else return false;
+  *nsub = ns;
+  *a_stages = st;
+  *smem = st * ns * CH_SUB_BYTES + res + 1024;
+  return true;
+}
+
+template <bool B_MN, bool STATS, bool SCATTER>
+int launch_halo_res(bsl_ctx* ctx, int bn, int nsub, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args,
+                    int grid, int smem, cudaStream_t stream) {
+  if (bn == 64 && nsub == 2) return launch_halo_res_one<64, 2, B_MN, STATS, SCATTER>(ctx, a, b, args, grid, smem, stream);
+  if (bn == 64 && nsub == 1) return launch_halo_res_one<64, 1, B_MN, STATS, SCATTER>(ctx, a, b, args, grid, smem, stream);
+  if (bn == 128 && nsub == 2) return launch_halo_res_one<128, 2, B_MN, STATS, SCATTER>(ctx, a, b, args, grid, smem, stream);
+  if (bn == 128 && nsub == 1) return launch_halo_res_one<128, 1, B_MN, STATS, SCATTER>(ctx, a, b, args, grid, smem, stream);
+  return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv_halo (resident): tile %d x %d", bn, nsub);
+}
+
+// Re-derives the unit count / grid of a plan after nsub or bn changed.
+void replan_units(bsl_ctx* ctx, HaloPlan& p) {
+  p.n_units = cdiv(p.n_sub_total, p.nsub) * p.n_ntiles;
+  int g = std::min(p.n_units, ctx->sm_count);
+  if (g >= p.n_ntiles) g -= g % p.n_ntiles;
+  p.grid = std::max(g, 1);
+  p.slots = cdiv(p.grid, p.n_ntiles);
+}
+
 template <bool B_MN, bool STATS, bool SCATTER>
 int launch_halo(bsl_ctx* ctx, int bn, int nsub, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args,
                 int grid, cudaStream_t stream) {
@@ -211,10 +269,6 @@ int launch_halo(bsl_ctx* ctx, int bn, int nsub, const CUtensorMap& a, const CUte
   }
   return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv_halo: tile %d x %d", bn, nsub);
 }
-
-struct HaloPlan {
-  int bn, nsub, n_ntiles, n_sub_total, n_units, grid, slots;
-};
 
 // Pixel sub-tiles are 8 (w) x 16 (h); `ncols` is the GEMM N extent (a multiple of 64).
 bool halo_eligible(int w, int h) { return !force_v1() && w % 8 == 0 && h % 16 == 0; }
@@ -383,7 +437,10 @@ int bsl_debug_set(bsl_ctx* ctx, int key, int value) {
 static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
                              double* sums, cudaStream_t stream) {
   const int halo = d->kh == 3 ? 1 : 0;
-  const HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, d->cout);
+  HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, d->cout);
+  int res_stages = 0, res_smem = 0;
+  const bool res = plan_resident(pl.bn, d->kh * d->kw, d->cin / 64, &pl.nsub, &res_stages, &res_smem);
+  if (res) replan_units(ctx, pl);
   const int box[4] = {8 + 2 * halo, 16 + 2 * halo, 1, 1};
   CUtensorMap ta, tb;
   int rc;
@@ -400,8 +457,11 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
   a.ostride_n = (long long)d->h * d->w * d->y_ld;
   a.n_group = d->cout;
   a.n_total = d->cout;
+  a.a_stages = res_stages;
   a.status = ctx->d_status;
-  if (!sums) return launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+  if (!sums)
+    return res ? launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
+               : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
   if (pl.bn == 256) {
     // long-reduction layers: small, L2-resident outputs; a separate statistics pass is cheaper than an
     // un-overlapped epilogue butterfly
@@ -411,7 +471,9 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
   float* part = nullptr;
   if ((rc = bsl_scratch(ctx, (size_t)pl.slots * 2 * d->cout * sizeof(float), &part))) return rc;
   a.stats_part = part;
-  if ((rc = launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream))) return rc;
+  rc = res ? launch_halo_res<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
+           : launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+  if (rc) return rc;
   const int kc = 2 * d->cout;
   pixel_reduce_final_kernel<<<dim3((kc + 31) / 32, 1), 256, 0, stream>>>(part, pl.slots, kc, sums);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel (conv statistics)");
@@ -463,7 +525,10 @@ int bsl_conv2d_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, con
   if (!dy || !w || !dx) return bsl_fail(ctx, BSL_EINVAL, "conv2d_dgrad: null buffer");
   if (halo_eligible(d->w, d->h)) {
     const int halo = d->kh == 3 ? 1 : 0;
-    const HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, d->cin);
+    HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, d->cin);
+    int res_stages = 0, res_smem = 0;
+    const bool res = plan_resident(pl.bn, d->kh * d->kw, d->cout / 64, &pl.nsub, &res_stages, &res_smem);
+    if (res) replan_units(ctx, pl);
     const int hbox[4] = {8 + 2 * halo, 16 + 2 * halo, 1, 1};
     CUtensorMap ta, tb;
     if ((rc = nhwc_map(ctx, dy, d->cout, d->w, d->h, d->n, d->y_ld, hbox, &ta))) return rc;
@@ -481,8 +546,10 @@ int bsl_conv2d_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, con
     a.ostride_n = (long long)d->h * d->w * d->x_ld;
     a.n_group = d->cin;
     a.n_total = d->cin;
+    a.a_stages = res_stages;
     a.status = ctx->d_status;
-    return launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
+    return res ? launch_halo_res<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream))
+               : launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
   }
   int box[4] = {0, 0, 0, 1};
   pick_box(128, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
@@ -625,6 +692,9 @@ int bsl_convT2d_fwd(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, cons
       pl.n_units = cdiv(pl.n_sub_total, pl.nsub) * pl.n_ntiles;
       pl.grid = std::max(1, std::min(pl.n_units, ctx->sm_count));
     }
+    int res_stages = 0, res_smem = 0;
+    const bool res = plan_resident(pl.bn, 1, d->cin / 64, &pl.nsub, &res_stages, &res_smem);
+    if (res) replan_units(ctx, pl);   // also makes the grid a multiple of the column-tile count
     const int hbox[4] = {8, 16, 1, 1};
     CUtensorMap ta, tb;
     if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, hbox, &ta))) return rc;
@@ -646,8 +716,10 @@ int bsl_convT2d_fwd(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, cons
     a.bias = bias;
     a.relu = d->relu;
     a.n_total = 4 * d->cout;
+    a.a_stages = res_stages;
     a.status = ctx->d_status;
-    return launch_halo<false, false, true>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
+    return res ? launch_halo_res<false, false, true>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream))
+               : launch_halo<false, false, true>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
   }
   int box[4] = {0, 0, 0, 1};
   pick_box(128, d->w, d->h, d->n, &box[0], &box[1], &box[2]);

@@ -353,6 +353,7 @@ struct ConvHaloArgs {
   int relu;
   int n_total;
   float* stats_part;             // [slot][2][n_total] per-CTA partial sums (nullptr: no statistics)
+  int a_stages;                  // B_RES kernels: activation stages that fit beside the resident filter
   DeviceStatus* status;
 };
 
@@ -400,19 +401,27 @@ __device__ __forceinline__ void ch_store_chunk(const uint32_t (&v)[32], __nv_bfl
     dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
 }
 
-template <int BN, int NSUB, bool B_MN, bool STATS, bool SCATTER>
+// B_RES: the whole filter slice of this CTA's column tile (ntaps x cblocks x BN x 64 channels) is loaded ONCE and
+// stays in shared memory; a CTA always owns column tile blockIdx.x % n_ntiles. Chosen by the host when it fits
+// (short reductions: the 64- and 128-channel layers, 1x1 and transposed convs), where re-streaming the filter from
+// L2 for every unit was 60 % of the TMA bytes and its latency left the tensor pipe idle two thirds of the time
+// (profiles/r01_ncu_full_conv_kernels.txt, enc1_2 dgrad). a_stages = p.a_stages activation stages share the rest.
+constexpr int CH_MAX_A_STAGES = 4;
+
+template <int BN, int NSUB, bool B_MN, bool STATS, bool SCATTER, bool B_RES = false>
 __global__ void __launch_bounds__(CH_THREADS)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvHaloArgs p) {
   using Cfg = ConvHaloCfg<BN, NSUB>;
   constexpr int ACC_BUFS = Cfg::ACC_BUFS;
-  constexpr int A_STAGES = Cfg::A_STAGES;
   constexpr int B_STAGES = Cfg::B_STAGES;
   constexpr int A_BYTES = Cfg::A_BYTES;
   constexpr int B_BYTES = Cfg::B_BYTES;
+  constexpr int A_BARS = B_RES ? CH_MAX_A_STAGES : Cfg::A_STAGES;
+  const int A_STAGES = B_RES ? p.a_stages : Cfg::A_STAGES;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * A_STAGES + 2 * B_STAGES + 2 * ACC_BUFS];
+  __shared__ __align__(8) uint64_t bars[2 * A_BARS + 2 * B_STAGES + 2 * ACC_BUFS];
   __shared__ uint32_t tmem_slot;
   __shared__ int dead;
   __shared__ float s_stats[STATS ? CH_EPI_WARPS * 2 * BN : 1];
@@ -423,11 +432,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t sA0 = smem_base;
   const uint32_t sB0 = smem_base + A_STAGES * A_BYTES;
   const uint32_t a_full = smem_u32(&bars[0]);
-  const uint32_t a_empty = smem_u32(&bars[A_STAGES]);
-  const uint32_t b_full = smem_u32(&bars[2 * A_STAGES]);
-  const uint32_t b_empty = smem_u32(&bars[2 * A_STAGES + B_STAGES]);
-  const uint32_t acc_full = smem_u32(&bars[2 * A_STAGES + 2 * B_STAGES]);
-  const uint32_t acc_empty = smem_u32(&bars[2 * A_STAGES + 2 * B_STAGES + ACC_BUFS]);
+  const uint32_t a_empty = smem_u32(&bars[A_BARS]);
+  const uint32_t b_full = smem_u32(&bars[2 * A_BARS]);
+  const uint32_t b_empty = smem_u32(&bars[2 * A_BARS + B_STAGES]);
+  const uint32_t acc_full = smem_u32(&bars[2 * A_BARS + 2 * B_STAGES]);
+  const uint32_t acc_empty = smem_u32(&bars[2 * A_BARS + 2 * B_STAGES + ACC_BUFS]);
   DeviceStatus* st = p.status;
 
   if (threadIdx.x == 0) dead = *reinterpret_cast<volatile int*>(&st->error);
@@ -499,7 +508,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 2 + CH_EPI_WARPS) {
     // ============================== B producer: one (tap, 64-channel block) filter slice per stage
-    if (elect_one_sync()) {
+    if (B_RES) {
+      if (elect_one_sync() && (int)blockIdx.x < p.n_units) {
+        const int n0 = (blockIdx.x % p.n_ntiles) * BN;
+        mbar_arrive_expect_tx(b_full, p.cblocks * p.ntaps * B_BYTES);
+        for (int cb = 0; cb < p.cblocks; ++cb)
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            const uint32_t sb = sB0 + (cb * p.ntaps + tap) * B_BYTES;
+            const int tapb = p.b_flip ? (p.ntaps - 1 - tap) : tap;
+            if (B_MN) {
+              const int krow = (tapb * p.cblocks + cb) * 64;
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j) tma_load_2d(sb + j * 8192, &tmB, b_full, n0 + 64 * j, krow);
+            } else {
+              tma_load_2d(sb, &tmB, b_full, cb * 64, tapb * p.b_rows_per_tap + n0);
+            }
+          }
+      }
+    } else if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
@@ -532,6 +558,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int sa = 0, sb = 0, buf = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
       bool ok = true;
+      if (B_RES && (int)blockIdx.x < p.n_units) ok = mbar_wait(b_full, 0, st, 27);
       for (int u = blockIdx.x; u < p.n_units && ok; u += gridDim.x) {
         const int pu = u / p.n_ntiles;
         int nsub = p.n_sub_total - pu * NSUB;
@@ -542,10 +569,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int cb = 0; cb < p.cblocks && ok; ++cb) {
           if (!mbar_wait(a_full + 8 * sa, pa, st, 24)) { ok = false; break; }
           const uint32_t a_stage = sA0 + sa * A_BYTES;
+          if (B_RES) tc_fence_after();
           for (int tap = 0; tap < p.ntaps; ++tap) {
-            if (!mbar_wait(b_full + 8 * sb, pb, st, 25)) { ok = false; break; }
-            tc_fence_after();
-            const uint32_t b_stage = sB0 + sb * B_BYTES;
+            if (!B_RES) {
+              if (!mbar_wait(b_full + 8 * sb, pb, st, 25)) { ok = false; break; }
+              tc_fence_after();
+            }
+            const uint32_t b_stage = B_RES ? sB0 + (cb * p.ntaps + tap) * B_BYTES : sB0 + sb * B_BYTES;
             const int toff = p.halo ? ((tap / 3) * box_w + tap % 3) * 128 : 0;
             // descriptors differ only in the 14-bit start-address field: one add per operand per UMMA
             const uint64_t da0 = make_smem_desc_sw128(a_stage + toff, 16, a_sbo);
@@ -560,8 +590,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             db0 + (uint64_t)((B_MN ? k * 2048 : k * 32) >> 4), idesc, first | (uint32_t)(k != 0));
               }
             }
-            umma_commit(b_empty + 8 * sb);
-            if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+            if (!B_RES) {
+              umma_commit(b_empty + 8 * sb);
+              if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+            }
           }
           umma_commit(a_empty + 8 * sa);
           if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
