@@ -401,6 +401,24 @@ __device__ __forceinline__ void ch_store_chunk(const uint32_t (&v)[32], __nv_bfl
     dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
 }
 
+// Sums s1[i], s2[i] (i = column) over the 32 lanes (= rows) of a warp: 5 halving steps, after which lane l holds
+// the totals of column l in s1[0], s2[0].
+__device__ __forceinline__ void ch_transpose_reduce(float (&s1)[32], float (&s2)[32], int lane) {
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const bool hi = (lane & w) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float keep1 = hi ? s1[i + w] : s1[i];
+      const float send1 = hi ? s1[i] : s1[i + w];
+      const float keep2 = hi ? s2[i + w] : s2[i];
+      const float send2 = hi ? s2[i] : s2[i + w];
+      s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, w);
+      s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
+    }
+  }
+}
+
 // B_RES: the whole filter slice of this CTA's column tile (ntaps x cblocks x BN x 64 channels) is loaded ONCE and
 // stays in shared memory; a CTA always owns column tile blockIdx.x % n_ntiles. Chosen by the host when it fits
 // (short reductions: the 64- and 128-channel layers, 1x1 and transposed convs), where re-streaming the filter from
@@ -612,6 +630,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int r = q * 32 + lane;        // accumulator row = pixel (x = r % 8, y = r / 8) of the sub-tile
     constexpr int COLS = NSUB == 2 ? BN : BN / 2;   // columns this warp handles per unit
     const int c_begin = NSUB == 2 ? 0 : half * COLS;
+    constexpr int SC = BN / 2;                      // STATS: columns per warp
+    constexpr bool PERSIST = STATS && BN == 64;
+    const int sc0 = half * SC;
+    float acc1[PERSIST ? SC : 1], acc2[PERSIST ? SC : 1];
+    if (PERSIST) {
+#pragma unroll
+      for (int i = 0; i < SC; ++i) acc1[i] = acc2[i] = 0.f;
+    }
     int buf = 0;
     uint32_t pacc = 0;
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
@@ -622,7 +648,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!mbar_wait(acc_full + 8 * buf, pacc, st, 26)) break;
       tc_fence_after();
       const int j = NSUB == 2 ? half : 0;
-      if (j < nsub) {
+      if (!STATS && j < nsub) {
         int s = pu * NSUB + j;
         const int tx = s % p.ntile_w;
         s /= p.ntile_w;
@@ -632,7 +658,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                               (long long)img * p.ostride_n;
         __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (NSUB * BN) + j * BN;
-        if (!STATS) {
+        {
           // two chunks in flight: both TMEM loads are issued before the first is consumed
 #pragma unroll 1
           for (int c = c_begin; c < c_begin + COLS; c += 64) {
@@ -656,39 +682,60 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               ch_store_chunk<SCATTER>(hc ? v1 : v0, o, bias, p.relu, packed);
             }
           }
-        } else {
-#pragma unroll 1
-          for (int c = c_begin; c < c_begin + COLS; c += 32) {
-            uint32_t v[32], packed[16];
-            tmem_ld_32x32(trow + c, v);
-            tmem_ld_wait();
-            ch_store_chunk<false>(v, obase + n0 + c, nullptr, 0, packed);
-            // statistics of the bf16 values just stored (what the normalisation pass reads back):
-            // transpose-reduce over the 32 rows of this warp; after 5 halving steps lane l holds column c + l
-            float s1[32], s2[32];
+        }
+      }
+      if (STATS) {
+        // Statistics variant: the two warps of a lane quarter split the COLUMNS (SC each) and walk every sub-tile,
+        // so a thread always sees the same SC channels. BN == 64: per-thread running sums over all units of this
+        // CTA (fixed order), transposed across the 32 rows once at the end. BN == 128: the sub-tiles' values are
+        // added first, then one transpose-reduce per 32-column strip and unit.
+        const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (NSUB * BN) + sc0;
+        __nv_bfloat16* ob[NSUB];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[i]));
-              s1[2 * i] = f.x;
-              s1[2 * i + 1] = f.y;
-              s2[2 * i] = f.x * f.x;
-              s2[2 * i + 1] = f.y * f.y;
-            }
+        for (int jj = 0; jj < NSUB; ++jj) {
+          int s = pu * NSUB + jj;
+          const int tx = s % p.ntile_w;
+          s /= p.ntile_w;
+          const int ty = s % p.ntile_h;
+          const int img = s / p.ntile_h;
+          ob[jj] = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)(tx * 8 + (r & 7)) * p.ostride_x +
+                   (long long)(ty * 16 + (r >> 3)) * p.ostride_y + (long long)img * p.ostride_n + n0 + sc0;
+        }
 #pragma unroll
-            for (int w = 16; w >= 1; w >>= 1) {
-              const bool hi = (lane & w) != 0;
+        for (int c = 0; c < SC; c += 32) {
+          float s1[32], s2[32];
+          if (!PERSIST) {
 #pragma unroll
-              for (int i = 0; i < w; ++i) {
-                const float keep1 = hi ? s1[i + w] : s1[i];
-                const float send1 = hi ? s1[i] : s1[i + w];
-                const float keep2 = hi ? s2[i + w] : s2[i];
-                const float send2 = hi ? s2[i] : s2[i + w];
-                s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, w);
-                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, w);
+            for (int i = 0; i < 32; ++i) s1[i] = s2[i] = 0.f;
+          }
+#pragma unroll
+          for (int jj = 0; jj < NSUB; ++jj) {
+            if (jj < nsub) {
+              uint32_t v[32], packed[16];
+              tmem_ld_32x32(tq + jj * BN + c, v);
+              tmem_ld_wait();
+              ch_store_chunk<false>(v, ob[jj] + c, nullptr, 0, packed);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {   // the bf16 values just stored: what the normalisation pass reads back
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[i]));
+                if (PERSIST) {
+                  acc1[c + 2 * i] += f.x;
+                  acc1[c + 2 * i + 1] += f.y;
+                  acc2[c + 2 * i] = fmaf(f.x, f.x, acc2[c + 2 * i]);
+                  acc2[c + 2 * i + 1] = fmaf(f.y, f.y, acc2[c + 2 * i + 1]);
+                } else {
+                  s1[2 * i] += f.x;
+                  s1[2 * i + 1] += f.y;
+                  s2[2 * i] = fmaf(f.x, f.x, s2[2 * i]);
+                  s2[2 * i + 1] = fmaf(f.y, f.y, s2[2 * i + 1]);
+                }
               }
             }
-            s_stats[(e * 2 + 0) * BN + c + lane] += s1[0];
-            s_stats[(e * 2 + 1) * BN + c + lane] += s2[0];
+          }
+          if (!PERSIST) {
+            ch_transpose_reduce(s1, s2, lane);
+            s_stats[(e * 2 + 0) * BN + sc0 + c + lane] += s1[0];
+            s_stats[(e * 2 + 1) * BN + sc0 + c + lane] += s2[0];
           }
         }
       }
@@ -696,6 +743,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
       if (++buf == ACC_BUFS) { buf = 0; pacc ^= 1; }
+    }
+    if (PERSIST) {
+#pragma unroll
+      for (int c = 0; c < SC; c += 32) {
+        float s1[32], s2[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { s1[i] = acc1[c + i]; s2[i] = acc2[c + i]; }
+        ch_transpose_reduce(s1, s2, lane);
+        s_stats[(e * 2 + 0) * BN + sc0 + c + lane] = s1[0];
+        s_stats[(e * 2 + 1) * BN + sc0 + c + lane] = s2[0];
+      }
     }
   }
 
