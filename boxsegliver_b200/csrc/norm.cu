@@ -342,7 +342,7 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y
   const long long base = (long long)blockIdx.y * pixels_per_group;
   const long long stride = (long long)gridDim.x * rows;
   long long p = (long long)blockIdx.x * rows + r;
-  constexpr int U = 2;
+  constexpr int U = 4;
   for (; p + (U - 1) * stride < pixels_per_group; p += U * stride) {
     uint4 ry[U], rg[U];
     float gm[U][G ? G : 1];
@@ -766,7 +766,7 @@ int bsl_norm_bwd_apply_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, 
   if ((rc = check_guide(ctx, d, guide, &G))) return rc;
   const int groups = d->mode ? d->n : 1;
   const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
-  const EwPlan pl = ew_plan(ctx, ppg, groups, d->c, 2);
+  const EwPlan pl = ew_plan(ctx, ppg, groups, d->c, 4);
   const dim3 grid(pl.blocks, groups);
   auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
   auto db = reinterpret_cast<const __nv_bfloat16*>(dy);

@@ -6,6 +6,7 @@
 // No float atomics anywhere: results are bit-reproducible.
 #pragma once
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "internal.h"
 
 namespace bsl {
@@ -100,12 +101,13 @@ struct ReducePlan {
 inline ReducePlan plan_reduce(bsl_ctx* ctx, long long pixels_per_group, int groups, int c, int K) {
   ReducePlan p;
   const int cg = c / 8;
-  p.threads = kReduceThreads < cg ? cg : kReduceThreads;
+  p.threads = kReduceThreads;   // c <= 2048 (checked by run_pixel_reduce): cg <= 256 channel groups
   p.rows = p.threads / cg;
   // keep K*c*rows*4 bytes of smem under 48 KB
   while ((size_t)p.rows * K * c * 4 > 48 * 1024 && p.rows > 1) p.rows /= 2;
   p.threads = p.rows * cg;
-  long long want = (pixels_per_group + 511) / 512;
+  // ~32 KB of every input per block (512 pixels at 64 channels), so wide layers with few pixels still fill the GPU
+  long long want = (pixels_per_group * c + 32767) / 32768;
   long long cap = (4LL * ctx->sm_count + groups - 1) / groups;
   if (cap < 1) cap = 1;
   if (want > cap) want = cap;
@@ -122,7 +124,7 @@ int bsl_scratch(bsl_ctx* ctx, size_t bytes, float** out);
 template <class F>
 int run_pixel_reduce(bsl_ctx* ctx, const F& f, long long pixels_per_group, int groups, int c, double* out,
                      cudaStream_t stream) {
-  if (c % 8 || c <= 0 || c > 4096) return bsl_fail(ctx, BSL_EUNSUPPORTED, "pixel reduce: c=%d", c);
+  if (c % 8 || c <= 0 || c > 2048) return bsl_fail(ctx, BSL_EUNSUPPORTED, "pixel reduce: c=%d (multiple of 8, <= 2048)", c);
   ReducePlan p = plan_reduce(ctx, pixels_per_group, groups, c, F::K);
   float* part = nullptr;
   int rc = bsl_scratch(ctx, p.scratch_bytes, &part);

@@ -178,30 +178,40 @@ __global__ void head_fprop_kernel(const __nv_bfloat16* __restrict__ x, int x_ld,
   for (int i = threadIdx.x; i < cin * COUT; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
   const int cg = cin / 8;  // power of two <= 32
-  const long long total = pixels * cg;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i0 = blockIdx.x * (long long)blockDim.x; i0 < total; i0 += stride) {
-    const long long i = i0 + threadIdx.x;
-    const bool live = i < total;
-    const long long p = live ? i / cg : 0;
-    const int g = live ? (int)(i - p * cg) : 0;
-    float acc[COUT];
+  const int g = threadIdx.x % cg;
+  float wr[8][COUT];       // this lane's 8 input channels: constant for the whole launch (blockDim % cg == 0)
 #pragma unroll
-    for (int k = 0; k < COUT; ++k) acc[k] = 0.f;
-    if (live) {
-      float v[8];
-      unpack8(ld16(x + p * x_ld + g * 8), v);
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int k = 0; k < COUT; ++k) wr[j][k] = sw[(g * 8 + j) * COUT + k];
+  const long long ppb = blockDim.x / cg;                  // pixels per block per iteration
+  const long long stride = (long long)gridDim.x * ppb;
+  constexpr int U = 4;                                    // independent 16 B loads in flight per thread
+  for (long long p0 = blockIdx.x * ppb + threadIdx.x / cg; p0 < pixels; p0 += U * stride) {
+    uint4 raw[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * stride;
+      raw[u] = p < pixels ? ld16(x + p * x_ld + g * 8) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * stride;
+      float v[8], acc[COUT];
+      unpack8(raw[u], v);
+#pragma unroll
+      for (int k = 0; k < COUT; ++k) acc[k] = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int k = 0; k < COUT; ++k) acc[k] = fmaf(v[j], sw[(g * 8 + j) * COUT + k], acc[k]);
-    }
+        for (int k = 0; k < COUT; ++k) acc[k] = fmaf(v[j], wr[j][k], acc[k]);
 #pragma unroll
-    for (int k = 0; k < COUT; ++k)
-      for (int o = cg >> 1; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
-    if (live && g == 0) {
+      for (int k = 0; k < COUT; ++k)
+        for (int o = cg >> 1; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+      if (p < pixels && g == 0) {
 #pragma unroll
-      for (int k = 0; k < COUT; ++k) y[p * COUT + k] = acc[k] + (bias ? bias[k] : 0.f);
+        for (int k = 0; k < COUT; ++k) y[p * COUT + k] = acc[k] + (bias ? bias[k] : 0.f);
+      }
     }
   }
 }
@@ -213,23 +223,36 @@ __global__ void head_dgrad_kernel(const float* __restrict__ dl, const float* __r
   for (int i = threadIdx.x; i < cin * COUT; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
   const int cg = cin / 8;
-  const long long total = pixels * cg;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / cg;
-    const int g = (int)(i - p * cg);
-    float d[COUT];
+  const int g = threadIdx.x % cg;
+  float wr[8][COUT];
 #pragma unroll
-    for (int k = 0; k < COUT; ++k) d[k] = __ldg(dl + p * COUT + k);
-    float o[8];
+  for (int j = 0; j < 8; ++j)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float s = 0.f;
+    for (int k = 0; k < COUT; ++k) wr[j][k] = sw[(g * 8 + j) * COUT + k];
+  const long long ppb = blockDim.x / cg;
+  const long long stride = (long long)gridDim.x * ppb;
+  constexpr int U = 4;
+  for (long long p0 = blockIdx.x * ppb + threadIdx.x / cg; p0 < pixels; p0 += U * stride) {
+    float d[U][COUT];
 #pragma unroll
-      for (int k = 0; k < COUT; ++k) s = fmaf(d[k], sw[(g * 8 + j) * COUT + k], s);
-      o[j] = s;
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * stride;
+#pragma unroll
+      for (int k = 0; k < COUT; ++k) d[u][k] = p < pixels ? __ldg(dl + p * COUT + k) : 0.f;
     }
-    st16(dx + p * dx_ld + g * 8, pack8(o));
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long p = p0 + u * stride;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < COUT; ++k) s = fmaf(d[u][k], wr[j][k], s);
+        o[j] = s;
+      }
+      if (p < pixels) st16(dx + p * dx_ld + g * 8, pack8(o));
+    }
   }
 }
 

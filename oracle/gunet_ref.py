@@ -319,7 +319,7 @@ def backward(tape: Tape, dlogits: np.ndarray, cfg: GUNetCfg, rnd=_identity) -> d
         elif k == "conv":
             s = L["spec"]
             sc, cout = s["scope"], s["cout"]
-            dz = O.relu_grad(d, L["z"])
+            dz = O.relu_grad(d, L["a"])   # a > 0 <=> z > 0; with a stored tape the mask is the other side's bits
             if L["sp"] is not None:
                 ssc, off = L["sp"]["scope"], s["sp_off"]
                 gw = np.einsum("nhwg,nhwc->gc", L["sp"]["guide"], dz)

@@ -227,7 +227,7 @@ def backward(tape: Tape, dlogits: np.ndarray, cfg: UNet3DCfg, rnd=_identity) -> 
         elif k == "conv":
             s = L["spec"]
             sc = s["scope"]
-            dz = O.relu_grad(d, L["z"])
+            dz = O.relu_grad(d, L["a"])   # a > 0 <=> z > 0; with a stored tape the mask is the other side's bits
             dy, dg, db = O.instance_norm_grad(dz, L["cache"])
             dy = rnd(dy).astype(dt)
             grads[f"{sc}/InstanceNorm/gamma"] = dg

@@ -332,7 +332,7 @@ def backward(tape: Tape, dlogits: np.ndarray, cfg: UNetCfg, rnd=_identity) -> di
             grads[f"{L['scope']}/biases"] = d.sum(axis=(0, 1, 2))
             d = rnd(O.conv2d_backprop_input(L["x"].shape, L["w"], d)).astype(dt)
         elif k == "conv":
-            dz = O.relu_grad(d, L["z"])
+            dz = O.relu_grad(d, L["a"])   # a > 0 <=> z > 0; with a stored tape the mask is the other side's bits
             if cfg.normalizer == "batch_norm":
                 dy, dg, db = O.batch_norm_grad(dz, L["cache"])
             else:

@@ -65,7 +65,42 @@ for (tag, fn), (cnt, ms) in by_layer.items():
         tf = flops[tag] / (t * 1e-3) / 1e12
         rows.append({"layer": tag, "fn": fn, "ms": t, "tflops": tf})
         print(f"  {t:7.3f} ms {tf:7.1f} TF/s  {fn:24s} {tag}")
+# HBM-bound passes: algorithmic bytes / time, against the measured copy bandwidth
+L_by_scope = {L.scope: L for L in eng.layers}
+n = a.batch
+
+
+def alg_bytes(fn, L):
+    px_out = n * L.h * L.w * (4 if L.kind == "convT" else 1)
+    c = L.cout
+    full = px_out * c * 2
+    return {"bsl_norm_apply_mod": 2 * full, "bsl_norm_apply": 2 * full, "bsl_norm_apply_pool_mod": 2.25 * full,
+            "bsl_norm_apply_pool": 2.25 * full, "bsl_norm_stats": full, "bsl_norm_bwd_reduce": 2 * full,
+            "bsl_norm_bwd_apply": 3 * full, "bsl_maxpool2x2_bwd_add": 3.25 * full, "bsl_relu_bwd": 3 * full,
+            "bsl_stem_im2col": n * L.h * L.w * (L.cin * 4 + 128), "bsl_conv2d_head_fprop": n * L.h * L.w * (L.cin * 2 + 4 * L.cout),
+            "bsl_conv2d_head_dgrad": n * L.h * L.w * (L.cin * 2 + 4 * L.cout),
+            "bsl_conv2d_head_wgrad": n * L.h * L.w * (L.cin * 2 + 4 * L.cout)}.get(fn)
+
+
+print("HBM-bound passes per layer (algorithmic GB/s; measured copy peak 6541.8 GB/s):")
+mem_rows = []
+agg = collections.OrderedDict()
+for (tag, fn), (cnt, ms) in by_layer.items():
+    L = L_by_scope.get(tag)
+    b = alg_bytes(fn, L) if L is not None else None
+    if b is None:
+        continue
+    t = ms / cnt
+    gbs = b / (t * 1e-3) / 1e9
+    mem_rows.append({"layer": tag, "fn": fn, "ms": t, "gbs": gbs})
+    g = agg.setdefault(fn, [0.0, 0.0])
+    g[0] += b
+    g[1] += t
+    print(f"  {t:7.3f} ms {gbs:7.0f} GB/s  {fn:26s} {tag}")
+print("HBM-bound passes, whole step:")
+for fn, (b, t) in agg.items():
+    print(f"  {t:7.3f} ms {b / (t * 1e-3) / 1e9:7.0f} GB/s ({100 * b / (t * 1e-3) / 1e9 / 6541.8:4.1f}% of peak)  {fn}")
 if a.json:
     with open(a.json, "w") as f:
         json.dump({"ms_per_step_bracketed": tot, "by_fn": {k: [v[0] // a.steps, v[1] / a.steps] for k, v in by_fn.items()},
-                   "tc_layers": rows}, f, indent=1)
+                   "tc_layers": rows, "mem_layers": mem_rows}, f, indent=1)
