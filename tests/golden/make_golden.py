@@ -1,4 +1,4 @@
-"""Generates tests/golden/unet2d_step.npz -- golden vectors for one U-Net training step.
+"""Generates tests/golden/{unet2d,gunet,unet3d}_step.npz -- golden vectors for one training step of each model.
 
 The reference (Jarvis73/BoxSegLiver) cannot be imported here: it is TensorFlow 1.13 code and TF cannot be
 installed in this image, and it ships no tests or golden vectors of its own (section 4).
@@ -65,7 +65,72 @@ def build(dtype=np.float64):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------- GUNet / UNet3D
+GCFG = dict(height=32, width=32, channel=3, init_channels=64, num_down_samples=4, mod_layers=(1, 2, 3, 4),
+            context_fc_channels=(256, 256), norm_with_center=True, norm_with_scale=False, use_context=True,
+            use_spatial=True, guide_channel=1, context_dim=200, side_dropout=0.5, dropout_seed=3,
+            weight_decay_rate=1e-5, loss_type="xentropy+dice", loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4))
+GN = 2
+VCFG = dict(depth=2, height=32, width=32, channel=1, init_channels=30, max_channels=320, num_pool_layers=4,
+            weight_decay_rate=3e-5, loss_weight_type="numerical", loss_numeric_w=(1.0, 10.0))
+VN = 2
+
+
+def _grad_summary(out, grads, params):
+    names = sorted(grads)
+    out["grad_names"] = np.array(names)
+    out["grad_norm"] = np.array([np.linalg.norm(grads[k].astype(np.float64)) for k in names])
+    out["grad_sum"] = np.array([grads[k].astype(np.float64).sum() for k in names])
+    wn = sorted(params)
+    out["weight_names"] = np.array(wn)
+    out["weight_sumsq"] = np.array([float((params[k].astype(np.float64) ** 2).sum()) for k in wn])
+
+
+def gunet_inputs():
+    images, labels = synthetic.make_batch(GN, GCFG["height"], GCFG["width"], 3, seed=DATA_SEED + 1)
+    context, guide = synthetic.make_guides(images, labels, GCFG["context_dim"], GCFG["guide_channel"], seed=2)
+    return dict(images=images, context=context, sp_guide=guide), labels
+
+
+def build_gunet(dtype=np.float64):
+    """One GUNet training step (GUNet.yml, --use_context --use_spatial, instance_norm, dropout 0.5): oracle/gunet_ref.py,
+    pinned by the torch-autograd cross-check in tests/test_oracle_gunet.py."""
+    from oracle import gunet_ref as GU
+    cfg = GU.GUNetCfg(**GCFG)
+    params = GU.init_params(cfg, seed=WEIGHT_SEED)
+    inputs, labels = gunet_inputs()
+    tape = GU.forward({k: v.astype(dtype) for k, v in params.items()}, {k: v.astype(dtype) for k, v in inputs.items()},
+                      cfg, True, step=1)
+    loss, dl = GU.loss_and_dlogits(tape, labels, cfg)
+    grads = GU.backward(tape, dl, cfg)
+    out = {"labels": labels, "logits": tape.logits.astype(np.float32), "loss": np.float64(loss),
+           "reg_loss": np.float64(GU.regularization_loss(params, cfg)), "ctx_params": tape.ctx_params.astype(np.float32),
+           "dropout_kept": np.array([int((f["mult"] > 0).sum()) for f in tape.fc if f["mult"] is not None])}
+    out.update({"in/" + k: v for k, v in inputs.items()})
+    _grad_summary(out, grads, params)
+    return out
+
+
+def build_unet3d(dtype=np.float64):
+    """One UNet3D training step (UNet3D.yml channels 30..320, instance_norm): oracle/unet3d_ref.py, pinned by the
+    torch-autograd cross-check in tests/test_oracle_unet3d.py."""
+    from oracle import unet3d_ref as U3
+    cfg = U3.UNet3DCfg(**VCFG)
+    params = U3.init_params(cfg, seed=WEIGHT_SEED)
+    images, labels = synthetic.make_volume_batch(VN, VCFG["depth"], VCFG["height"], VCFG["width"], seed=DATA_SEED + 2)
+    tape = U3.forward({k: v.astype(dtype) for k, v in params.items()}, dict(images=images.astype(dtype)), cfg)
+    loss, dl = U3.loss_and_dlogits(tape, labels, cfg)
+    grads = U3.backward(tape, dl, cfg)
+    out = {"images": images, "labels": labels, "logits": tape.logits.astype(np.float32), "loss": np.float64(loss),
+           "reg_loss": np.float64(U3.regularization_loss(params, cfg)),
+           "argmax": np.argmax(tape.prob, axis=-1).astype(np.uint8)}
+    _grad_summary(out, grads, params)
+    return out
+
+
 if __name__ == "__main__":
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "unet2d_step.npz")
-    np.savez_compressed(path, **build())
-    print("wrote", path, os.path.getsize(path), "bytes")
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name, fn in (("unet2d_step.npz", build), ("gunet_step.npz", build_gunet), ("unet3d_step.npz", build_unet3d)):
+        path = os.path.join(here, name)
+        np.savez_compressed(path, **fn())
+        print("wrote", path, os.path.getsize(path), "bytes")

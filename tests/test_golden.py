@@ -84,3 +84,88 @@ def test_engine_against_golden_vectors(ctx, gold):
     # right-hand (label) counts do not depend on the network at all: bit-exact
     for c in (1, 2):
         assert np.array_equal(counts[:, c - 1, 2], gold[f"counts/{c}"][:, 2])
+
+
+# ------------------------------------------------------------------------------------------------ GUNet / UNet3D
+GDIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _check_oracle_against(gold, now):
+    assert list(now["weight_names"]) == list(gold["weight_names"])
+    assert np.allclose(now["weight_sumsq"], gold["weight_sumsq"], rtol=1e-12)
+    assert rel(now["logits"], gold["logits"]) < 1e-6
+    assert abs(float(now["loss"]) - float(gold["loss"])) < 1e-10
+    assert abs(float(now["reg_loss"]) - float(gold["reg_loss"])) < 1e-12
+    assert list(now["grad_names"]) == list(gold["grad_names"])
+    assert np.allclose(now["grad_norm"], gold["grad_norm"], rtol=1e-8)
+    assert np.allclose(now["grad_sum"], gold["grad_sum"], rtol=1e-6, atol=1e-10)
+
+
+def test_gunet_oracle_reproduces_golden_vectors():
+    gold = dict(np.load(os.path.join(GDIR, "gunet_step.npz"), allow_pickle=False))
+    now = G.build_gunet()
+    for k in ("in/images", "in/context", "in/sp_guide", "labels", "dropout_kept"):
+        assert np.array_equal(now[k], gold[k]), k
+    assert rel(now["ctx_params"], gold["ctx_params"]) < 1e-6
+    _check_oracle_against(gold, now)
+
+
+def test_unet3d_oracle_reproduces_golden_vectors():
+    gold = dict(np.load(os.path.join(GDIR, "unet3d_step.npz"), allow_pickle=False))
+    now = G.build_unet3d()
+    assert np.array_equal(now["images"], gold["images"]) and np.array_equal(now["labels"], gold["labels"])
+    assert np.array_equal(now["argmax"], gold["argmax"])
+    _check_oracle_against(gold, now)
+
+
+def _check_engine_against(gold, logits, data_loss, reg, grads):
+    assert rel(logits, gold["logits"]) < 5e-2
+    assert abs(data_loss - float(gold["loss"])) < 2e-2 * abs(float(gold["loss"]))
+    assert abs(reg - float(gold["reg_loss"])) < 1e-6
+    names = list(gold["grad_names"])
+    ratio = np.array([np.linalg.norm(grads[nm].astype(np.float64)) for nm in names]) / gold["grad_norm"]
+    assert np.all(np.abs(ratio - 1) < 0.3), dict(zip(names, ratio))
+    assert abs(np.median(ratio) - 1) < 0.05
+
+
+@pytest.mark.gpu
+def test_gunet_engine_against_golden_vectors(ctx):
+    from boxsegliver_b200.gunet_engine import GUNetConfig, GUNetEngine
+    from oracle import gunet_ref as GU
+    gold = dict(np.load(os.path.join(GDIR, "gunet_step.npz"), allow_pickle=False))
+    params = GU.init_params(GU.GUNetCfg(**G.GCFG), seed=G.WEIGHT_SEED)
+    eng = GUNetEngine(ctx, GUNetConfig(batch=G.GN, **G.GCFG))
+    eng.set_weights(params)
+    eng.set_inputs(gold["in/images"], gold["labels"])
+    eng.set_guides(gold["in/context"], gold["in/sp_guide"])
+    eng.forward(True)
+    eng.loss_backward()
+    ctx.check_device()
+    logits = eng.logits.download(np.float32, gold["logits"].shape)
+    ctxp = eng.get_context_params()
+    grads = eng.get_grads()
+    eng.optimizer_step(G.LR)
+    data_loss, reg = eng.read_loss()
+    eng.close()
+    assert rel(ctxp, gold["ctx_params"]) < 1e-5          # fp32 MLP with the bit-exact dropout masks
+    _check_engine_against(gold, logits, data_loss, reg, grads)
+
+
+@pytest.mark.gpu
+def test_unet3d_engine_against_golden_vectors(ctx):
+    from boxsegliver_b200.unet3d_engine import UNet3DConfig, UNet3DEngine
+    from oracle import unet3d_ref as U3
+    gold = dict(np.load(os.path.join(GDIR, "unet3d_step.npz"), allow_pickle=False))
+    params = U3.init_params(U3.UNet3DCfg(**G.VCFG), seed=G.WEIGHT_SEED)
+    eng = UNet3DEngine(ctx, UNet3DConfig(batch=G.VN, **G.VCFG))
+    eng.set_weights(params)
+    eng.set_inputs(gold["images"], gold["labels"])
+    eng.forward(True)
+    eng.loss_backward()
+    ctx.check_device()
+    logits = eng.logits.download(np.float32, gold["logits"].shape)
+    grads = eng.get_grads()
+    eng.optimizer_step(G.LR)
+    data_loss, reg = eng.read_loss()
+    eng.close()
+    _check_engine_against(gold, logits, data_loss, reg, grads)
