@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <string>
 #include <unordered_map>
 #include <vector>
 #include "igemm.cuh"
@@ -164,6 +165,27 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, float* __re
   *reinterpret_cast<float4*>(out + i) = acc;
 }
 
+__global__ void reduce_splits_strided_kernel(const float* __restrict__ part, float* __restrict__ out, long long n,
+                                             int splits, long long stride) {
+  long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 acc = *reinterpret_cast<const float4*>(part + i);
+  for (int s = 1; s < splits; ++s) {  // fixed order => bit-reproducible
+    float4 v = *reinterpret_cast<const float4*>(part + s * stride + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + i) = acc;
+}
+
+int reduce_splits_strided(bsl_ctx* ctx, const float* part, float* out, long long n, int splits, long long stride,
+                          cudaStream_t s) {
+  const int threads = 256;
+  const long long blocks = (n / 4 + threads - 1) / threads;
+  reduce_splits_strided_kernel<<<(unsigned)blocks, threads, 0, s>>>(part, out, n, splits, stride);
+  BSL_LAUNCH_CHECK(ctx, "reduce_splits_strided_kernel");
+  return BSL_OK;
+}
+
 int reduce_splits(bsl_ctx* ctx, const float* part, float* out, long long n, int splits, cudaStream_t s) {
   int threads = 256;
   long long blocks = (n / 4 + threads - 1) / threads;
@@ -298,6 +320,8 @@ void halo_common(ConvHaloArgs& a, const HaloPlan& p, int w, int h, int n) {
   a.n_sub_total = p.n_sub_total;
   a.n_units = p.n_units;
   a.n_ntiles = p.n_ntiles;
+  a.kd = 1;        // 2-D: every image is its own one-slice "volume" (tensor map dims (c, w, h, n, 1))
+  a.depth = n;
 }
 
 struct WgradPlan {
@@ -320,10 +344,8 @@ bool wgrad2_eligible(const bsl_conv2d_desc* d) {
   return !off && !force_v1() && d->kh == 3 && d->kw == 3 && d->w % WG_TW == 0 && d->h % WG_TH == 0 && d->cout % 128 == 0;
 }
 
-Wgrad2Plan plan_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
+Wgrad2Plan plan_wgrad2_core(bsl_ctx* ctx, int k, int mn, size_t per_tap) {
   Wgrad2Plan best = {};
-  const int k = (d->w / WG_TW) * (d->h / WG_TH) * d->n;
-  const int mn = (d->cin / 64) * (d->cout / 128);
   const int sms = ctx->sm_count;
   const double fixed = 6.0;  // prologue + epilogue of a CTA, in units of one (tile, accumulator) step
   double best_t = 1e300;
@@ -355,8 +377,13 @@ Wgrad2Plan plan_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
     }
   }
   best.ws_floats = ((size_t)(best.splits_a > 1 ? best.splits_a * 6 : 0) + (size_t)(best.splits_b > 1 ? best.splits_b * 3 : 0)) *
-                   d->cin * d->cout;
+                   per_tap;
   return best;
+}
+
+Wgrad2Plan plan_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
+  return plan_wgrad2_core(ctx, (d->w / WG_TW) * (d->h / WG_TH) * d->n, (d->cin / 64) * (d->cout / 128),
+                          (size_t)d->cin * d->cout);
 }
 
 const Wgrad2Plan& cached_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
@@ -395,6 +422,8 @@ int conv2d_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const v
   a.cout = d->cout;
   a.out_a = p.splits_a > 1 ? ws : dw;
   a.out_b = p.splits_b > 1 ? ws + (p.splits_a > 1 ? (long long)p.splits_a * 6 * per_tap : 0) : dw + 6 * per_tap;
+  a.kd = 1;
+  a.depth = d->n;
   a.status = ctx->d_status;
   static bool configured = false;
   if (!configured) {
@@ -617,6 +646,9 @@ int bsl_conv2d_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, cons
     a.cin = d->cin;
     a.cout = d->cout;
     a.out = p.splits > 1 ? reinterpret_cast<float*>(workspace) : dw;
+    a.kd = 1;
+    a.depth = d->n;
+    a.splits = p.splits;
     a.status = ctx->d_status;
     static bool configured = false;
     if (!configured) {
@@ -853,3 +885,210 @@ int bsl_convT2d_bwd_filter(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* 
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ 3-D layers on the halo-tile kernels
+// (3,3,3) and (1,3,3) stride-1 convolutions of UNet3D (NetworksV2/UNet3D.py:31-91): the reduction of the 2-D kernels
+// gains an outer loop over the filter depth, each step reading the slice z + kd - 1 through a 5-D (c, w, h, d, n)
+// tensor map (out-of-volume slices are zero-filled = SAME padding). Called from conv3d.cu.
+namespace {
+int ndhwc_halo_map(bsl_ctx* ctx, const void* base, int c, int w, int h, int dd, int n, int ld, int bw, int bh,
+                   CUtensorMap* out) {
+  uint64_t dims[5] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)dd, (uint64_t)n};
+  uint64_t str[5] = {2, (uint64_t)ld * 2, (uint64_t)w * ld * 2, (uint64_t)h * w * ld * 2, (uint64_t)dd * h * w * ld * 2};
+  uint32_t bx[5] = {64, (uint32_t)bw, (uint32_t)bh, 1, 1};
+  return bsl_get_tmap(ctx, base, 5, dims, str, bx, out);
+}
+bool d3_stride1(const bsl_conv3d_desc* d) {
+  return d->kh == 3 && d->kw == 3 && (d->kd == 1 || d->kd == 3) && d->sd == 1 && d->sh == 1 && d->sw == 1;
+}
+}  // namespace
+
+bool bsl_conv3d_halo_ok(const bsl_conv3d_desc* d) { return d3_stride1(d) && halo_eligible(d->w, d->h); }
+
+int bsl_conv3d_halo_fprop(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x, const void* w, void* y,
+                          cudaStream_t stream) {
+  HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n * d->d, d->cout);
+  int res_stages = 0, res_smem = 0;
+  const bool res = plan_resident(pl.bn, 9 * d->kd, d->cin / 64, &pl.nsub, &res_stages, &res_smem);
+  if (res) replan_units(ctx, pl);
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = ndhwc_halo_map(ctx, x, d->cin, d->w, d->h, d->d, d->n, d->x_ld, 10, 18, &ta))) return rc;
+  if ((rc = matrix_map(ctx, w, d->cout, d->kd * 9 * d->cin, 64, 64, &tb))) return rc;
+  ConvHaloArgs a = {};
+  halo_common(a, pl, d->w, d->h, d->n * d->d);
+  a.ntaps = 9;
+  a.halo = 1;
+  a.cblocks = d->cin / 64;
+  a.kd = d->kd;
+  a.depth = d->d;
+  a.out = y;
+  a.ostride_x = d->y_ld;
+  a.ostride_y = (long long)d->w * d->y_ld;
+  a.ostride_n = (long long)d->h * d->w * d->y_ld;
+  a.n_group = d->cout;
+  a.n_total = d->cout;
+  a.a_stages = res_stages;
+  a.status = ctx->d_status;
+  return res ? launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
+             : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+}
+
+int bsl_conv3d_halo_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy, const void* w, void* dx,
+                          cudaStream_t stream) {
+  HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n * d->d, d->cin);
+  int res_stages = 0, res_smem = 0;
+  const bool res = plan_resident(pl.bn, 9 * d->kd, d->cout / 64, &pl.nsub, &res_stages, &res_smem);
+  if (res) replan_units(ctx, pl);
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = ndhwc_halo_map(ctx, dy, d->cout, d->w, d->h, d->d, d->n, d->y_ld, 10, 18, &ta))) return rc;
+  if ((rc = matrix_map(ctx, w, d->cout, d->kd * 9 * d->cin, 64, pl.bn, &tb))) return rc;
+  ConvHaloArgs a = {};
+  halo_common(a, pl, d->w, d->h, d->n * d->d);
+  a.ntaps = 9;
+  a.halo = 1;
+  a.cblocks = d->cout / 64;
+  a.kd = d->kd;
+  a.depth = d->d;
+  a.b_flip = 1;
+  a.b_rows_per_tap = d->cin;
+  a.out = dx;
+  a.ostride_x = d->x_ld;
+  a.ostride_y = (long long)d->w * d->x_ld;
+  a.ostride_n = (long long)d->h * d->w * d->x_ld;
+  a.n_group = d->cin;
+  a.n_total = d->cin;
+  a.a_stages = res_stages;
+  a.status = ctx->d_status;
+  return res ? launch_halo_res<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
+             : launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+}
+
+bool bsl_conv3d_halo_wgrad_ok(const bsl_conv3d_desc* d) {
+  return !force_v1() && d3_stride1(d) && d->w % WG_TW == 0 && d->h % WG_TH == 0;
+}
+
+namespace {
+struct Wgrad3Plan {
+  bool wide;
+  Wgrad2Plan w2;
+  int k_tiles, per, splits;
+  size_t ws_bytes;
+};
+Wgrad3Plan plan_wgrad3_halo_uncached(bsl_ctx* ctx, const bsl_conv3d_desc* d);
+
+// The split search simulates block dispatch (~1 ms on the host): once per shape.
+Wgrad3Plan plan_wgrad3_halo(bsl_ctx* ctx, const bsl_conv3d_desc* d) {
+  static std::mutex mu;
+  static std::unordered_map<std::string, Wgrad3Plan> cache;
+  char key[96];
+  snprintf(key, sizeof(key), "%d.%d.%d.%d.%d.%d.%d", d->n, d->d, d->h, d->w, d->cin, d->cout, d->kd);
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) it = cache.emplace(key, plan_wgrad3_halo_uncached(ctx, d)).first;
+  return it->second;
+}
+
+Wgrad3Plan plan_wgrad3_halo_uncached(bsl_ctx* ctx, const bsl_conv3d_desc* d) {
+  Wgrad3Plan p = {};
+  p.k_tiles = (d->w / WG_TW) * (d->h / WG_TH) * d->n * d->d;
+  const size_t per_tap = (size_t)d->cin * d->cout;
+  static const int v2off = getenv("BSL_WGRAD_V2") ? atoi(getenv("BSL_WGRAD_V2")) == 0 : 0;
+  p.wide = !v2off && d->cout % 128 == 0;
+  if (p.wide) {
+    p.w2 = plan_wgrad2_core(ctx, p.k_tiles, (d->cin / 64) * (d->cout / 128) * d->kd, per_tap);
+    const bool direct_a = p.w2.splits_a == 1 && d->kd == 1, direct_b = p.w2.splits_b == 1 && d->kd == 1;
+    p.ws_bytes = ((direct_a ? 0 : (size_t)p.w2.splits_a * 6) + (direct_b ? 0 : (size_t)p.w2.splits_b * 3)) * d->kd * per_tap *
+                 sizeof(float);
+  } else {
+    const int mn = (d->cin / 64) * (d->cout / 64) * d->kd;
+    int splits = std::max(1, ctx->sm_count / mn);
+    splits = std::max(1, std::min(splits, p.k_tiles / 4));
+    p.per = cdiv(p.k_tiles, splits);
+    p.splits = cdiv(p.k_tiles, p.per);
+    p.ws_bytes = p.splits > 1 ? (size_t)p.splits * d->kd * 9 * per_tap * sizeof(float) : 0;
+  }
+  return p;
+}
+}  // namespace
+
+size_t bsl_conv3d_halo_wgrad_ws(bsl_ctx* ctx, const bsl_conv3d_desc* d) { return plan_wgrad3_halo(ctx, d).ws_bytes; }
+
+int bsl_conv3d_halo_wgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x, const void* dy, float* dw,
+                          void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  const Wgrad3Plan p = plan_wgrad3_halo(ctx, d);
+  if (p.ws_bytes > workspace_bytes || (p.ws_bytes && !workspace))
+    return bsl_fail(ctx, BSL_EWORKSPACE, "conv3d_wgrad: workspace %zu < %zu", workspace_bytes, p.ws_bytes);
+  CUtensorMap tx, ty;
+  int rc;
+  if ((rc = ndhwc_halo_map(ctx, x, d->cin, d->w, d->h, d->d, d->n, d->x_ld, WG_TW + 2, WG_TH + 2, &tx))) return rc;
+  if ((rc = ndhwc_halo_map(ctx, dy, d->cout, d->w, d->h, d->d, d->n, d->y_ld, WG_TW, WG_TH, &ty))) return rc;
+  const long long per_tap = (long long)d->cin * d->cout;
+  float* ws = reinterpret_cast<float*>(workspace);
+  if (p.wide) {
+    const Wgrad2Plan& q = p.w2;
+    WgradHalo2Args a = {};
+    a.ntile_w = d->w / WG_TW;
+    a.ntile_h = d->h / WG_TH;
+    a.n = d->n * d->d;
+    a.k_tiles_total = q.k_tiles;
+    a.splits_a = q.splits_a;
+    a.per_a = q.per_a;
+    a.splits_b = q.splits_b;
+    a.per_b = q.per_b;
+    a.cin = d->cin;
+    a.cout = d->cout;
+    a.kd = d->kd;
+    a.depth = d->d;
+    // partial layouts [split][kd][taps]; with a single split the kernel writes dW rows directly, which needs the
+    // per-depth stride of dW (9 taps) instead of 6 / 3: only taken when kd == 1, otherwise always through partials
+    const bool direct_a = q.splits_a == 1 && d->kd == 1, direct_b = q.splits_b == 1 && d->kd == 1;
+    const size_t need = ((direct_a ? 0 : (size_t)q.splits_a * 6) + (direct_b ? 0 : (size_t)q.splits_b * 3)) * d->kd * per_tap *
+                        sizeof(float);
+    if (need > workspace_bytes) return bsl_fail(ctx, BSL_EWORKSPACE, "conv3d_wgrad: workspace %zu < %zu", workspace_bytes, need);
+    a.out_a = direct_a ? dw : ws;
+    a.out_b = direct_b ? dw + 6 * per_tap : ws + (direct_a ? 0 : (long long)q.splits_a * d->kd * 6 * per_tap);
+    a.status = ctx->d_status;
+    static bool configured = false;
+    if (!configured) {
+      BSL_CUDA(ctx, cudaFuncSetAttribute(wgrad_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_BYTES));
+      configured = true;
+    }
+    wgrad_halo2_kernel<<<dim3(d->cin / 64, d->cout / 128, d->kd * (q.splits_a + q.splits_b)), WG_THREADS, WG2_SMEM_BYTES,
+                         stream>>>(tx, ty, a);
+    BSL_LAUNCH_CHECK(ctx, "wgrad_halo2_kernel launch (3-D)");
+    for (int k = 0; k < d->kd; ++k) {   // partial[split][kd][taps] -> dW[kd][9]: split stride = kd * taps * per_tap
+      if (!direct_a && (rc = reduce_splits_strided(ctx, a.out_a + (long long)k * 6 * per_tap, dw + (long long)k * 9 * per_tap,
+                                                   6 * per_tap, q.splits_a, (long long)d->kd * 6 * per_tap, stream)))
+        return rc;
+      if (!direct_b && (rc = reduce_splits_strided(ctx, a.out_b + (long long)k * 3 * per_tap,
+                                                   dw + ((long long)k * 9 + 6) * per_tap, 3 * per_tap, q.splits_b,
+                                                   (long long)d->kd * 3 * per_tap, stream)))
+        return rc;
+    }
+    return BSL_OK;
+  }
+  WgradHaloArgs a = {};
+  a.ntile_w = d->w / WG_TW;
+  a.ntile_h = d->h / WG_TH;
+  a.n = d->n * d->d;
+  a.k_tiles_total = p.k_tiles;
+  a.k_tiles_per_split = p.per;
+  a.cin = d->cin;
+  a.cout = d->cout;
+  a.out = p.splits > 1 ? ws : dw;
+  a.kd = d->kd;
+  a.depth = d->d;
+  a.splits = p.splits;
+  a.status = ctx->d_status;
+  static bool configured1 = false;
+  if (!configured1) {
+    BSL_CUDA(ctx, cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
+    configured1 = true;
+  }
+  wgrad_halo_kernel<<<dim3(d->cin / 64, d->cout / 64, d->kd * p.splits), WG_THREADS, WG_SMEM_BYTES, stream>>>(tx, ty, a);
+  BSL_LAUNCH_CHECK(ctx, "wgrad_halo_kernel launch (3-D)");
+  if (p.splits > 1) return reduce_splits(ctx, ws, dw, (long long)d->kd * 9 * per_tap, p.splits, stream);
+  return BSL_OK;
+}

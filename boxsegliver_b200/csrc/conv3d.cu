@@ -207,6 +207,7 @@ int bsl_conv3d_fprop(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x, cons
   int rc = geometry(ctx, d, &g);
   if (rc) return rc;
   if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "conv3d_fprop: null buffer");
+  if (bsl_conv3d_halo_ok(d)) return bsl_conv3d_halo_fprop(ctx, d, x, w, y, as_stream(stream));
   const int odim[4] = {g.out[0], g.out[1], g.out[2], d->n};
   int box[4];
   pick_box4(128, odim, box);
@@ -246,6 +247,7 @@ int bsl_conv3d_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy, con
   int rc = geometry(ctx, d, &g);
   if (rc) return rc;
   if (!dy || !w || !dx) return bsl_fail(ctx, BSL_EINVAL, "conv3d_dgrad: null buffer");
+  if (bsl_conv3d_halo_ok(d)) return bsl_conv3d_halo_dgrad(ctx, d, dy, w, dx, as_stream(stream));
   for (int i = 0; i < 3; ++i)
     if (g.in[i] % g.s[i]) return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv3d_dgrad: extents must be multiples of the stride");
   const int bn = pick_bn(d->cin);
@@ -314,6 +316,7 @@ int bsl_conv3d_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy, con
 size_t bsl_conv3d_wgrad_workspace(bsl_ctx* ctx, const bsl_conv3d_desc* d) {
   Geo g;
   if (!ctx || !d || geometry(ctx, d, &g)) return 0;
+  if (bsl_conv3d_halo_wgrad_ok(d)) return bsl_conv3d_halo_wgrad_ws(ctx, d);
   const WgradPlan3 p = plan_wgrad3(ctx, d, g);
   return p.sp.splits > 1 ? (size_t)p.sp.splits * p.taps * d->cin * d->cout * sizeof(float) : 0;
 }
@@ -324,6 +327,8 @@ int bsl_conv3d_wgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x, cons
   int rc = geometry(ctx, d, &g);
   if (rc) return rc;
   if (!x || !dy || !dw) return bsl_fail(ctx, BSL_EINVAL, "conv3d_wgrad: null buffer");
+  if (bsl_conv3d_halo_wgrad_ok(d))
+    return bsl_conv3d_halo_wgrad(ctx, d, x, dy, dw, workspace, workspace_bytes, as_stream(stream));
   const WgradPlan3 p = plan_wgrad3(ctx, d, g);
   const int odim[4] = {g.out[0], g.out[1], g.out[2], d->n};
   const int es1[3] = {1, 1, 1};

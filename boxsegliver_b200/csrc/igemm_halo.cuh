@@ -29,7 +29,8 @@ struct WgradHaloArgs {
   int k_tiles_total;
   int k_tiles_per_split;
   int cin, cout;                 // padded-to-64 extents of dW
-  float* out;                    // [split][9][cin][cout] fp32 (or dW itself when splits == 1)
+  float* out;                    // [split][kd * 9][cin][cout] fp32 (or dW itself when splits == 1)
+  int kd, depth, splits;         // filter depth (blockIdx.z = kdi * splits + split); slices per volume
   DeviceStatus* status;
 };
 
@@ -83,7 +84,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
 
   const int cb = blockIdx.x, nb = blockIdx.y;
-  const int k_begin = blockIdx.z * p.k_tiles_per_split;
+  const int kdi = blockIdx.z / p.splits, split = blockIdx.z - kdi * p.splits;
+  const int k_begin = split * p.k_tiles_per_split;
   const int k_end = min(p.k_tiles_total, k_begin + p.k_tiles_per_split);
   const int num_k = k_end - k_begin;
 
@@ -101,8 +103,9 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const uint32_t fb = full0 + 8 * stage;
         const uint32_t sx = smem_base + stage * WG_STAGE_BYTES;
         mbar_arrive_expect_tx(fb, WG_X_ROWS * 128 + WG_DY_BYTES);
-        tma_load_5d(sx, &tmX, fb, cb * 64, tx * WG_TW - 1, ty * WG_TH - 1, img, 0);
-        tma_load_5d(sx + WG_X_BYTES, &tmDY, fb, nb * 64, tx * WG_TW, ty * WG_TH, img, 0);
+        const int z = img % p.depth, vol = img / p.depth;
+        tma_load_5d(sx, &tmX, fb, cb * 64, tx * WG_TW - 1, ty * WG_TH - 1, z + kdi - (p.kd >> 1), vol);
+        tma_load_5d(sx + WG_X_BYTES, &tmDY, fb, nb * 64, tx * WG_TW, ty * WG_TH, z, vol);
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -155,7 +158,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int q = 0; q < 5; ++q) {
         const int tap = 2 * q + (r >> 6);
         const bool valid = tap < 9 && !(q == 4 && r >= 64);
-        float* o = p.out + (((long long)blockIdx.z * 9 + tap) * p.cin + cb * 64 + (r & 63)) * p.cout + nb * 64;
+        float* o = p.out + ((((long long)split * p.kd + kdi) * 9 + tap) * p.cin + cb * 64 + (r & 63)) * p.cout + nb * 64;
 #pragma unroll
         for (int c = 0; c < 64; c += 32) {
           uint32_t v[32];
@@ -195,8 +198,9 @@ struct WgradHalo2Args {
   int splits_a, per_a;           // blockIdx.z <  splits_a: rows 0, 1 over tiles [z * per_a, ...)
   int splits_b, per_b;           // blockIdx.z >= splits_a: row 2 over tiles [(z - splits_a) * per_b, ...)
   int cin, cout;
-  float* out_a;                  // [splits_a][6][cin][cout]
-  float* out_b;                  // [splits_b][3][cin][cout]
+  float* out_a;                  // [splits_a][kd][6][cin][cout]
+  float* out_b;                  // [splits_b][kd][3][cin][cout]
+  int kd, depth;                 // filter depth: blockIdx.z = class offset + kdi * splits + split
   DeviceStatus* status;
 };
 
@@ -245,8 +249,10 @@ wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
 
   const int cb = blockIdx.x, nb = blockIdx.y;
-  const bool type_a = (int)blockIdx.z < p.splits_a;
-  const int zi = type_a ? blockIdx.z : blockIdx.z - p.splits_a;
+  const bool type_a = (int)blockIdx.z < p.kd * p.splits_a;
+  const int zz = type_a ? blockIdx.z : blockIdx.z - p.kd * p.splits_a;
+  const int nsplit = type_a ? p.splits_a : p.splits_b;
+  const int kdi = zz / nsplit, zi = zz - kdi * nsplit;
   const int per = type_a ? p.per_a : p.per_b;
   const int k_begin = zi * per;
   const int k_end = min(p.k_tiles_total, k_begin + per);
@@ -268,9 +274,10 @@ wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const uint32_t fb = full0 + 8 * stage;
         const uint32_t sx = smem_base + stage * WG2_STAGE_BYTES;
         mbar_arrive_expect_tx(fb, WG_X_ROWS * 128 + WG2_DY_BYTES);
-        tma_load_5d(sx, &tmX, fb, cb * 64, tx * WG_TW - 1, ty * WG_TH - 1, img, 0);
-        tma_load_5d(sx + WG_X_BYTES, &tmDY, fb, nb * 128, tx * WG_TW, ty * WG_TH, img, 0);
-        tma_load_5d(sx + WG_X_BYTES + WG_DY_BYTES, &tmDY, fb, nb * 128 + 64, tx * WG_TW, ty * WG_TH, img, 0);
+        const int z = img % p.depth, vol = img / p.depth;
+        tma_load_5d(sx, &tmX, fb, cb * 64, tx * WG_TW - 1, ty * WG_TH - 1, z + kdi - (p.kd >> 1), vol);
+        tma_load_5d(sx + WG_X_BYTES, &tmDY, fb, nb * 128, tx * WG_TW, ty * WG_TH, z, vol);
+        tma_load_5d(sx + WG_X_BYTES + WG_DY_BYTES, &tmDY, fb, nb * 128 + 64, tx * WG_TW, ty * WG_TH, z, vol);
         if (++stage == WG2_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -308,7 +315,7 @@ wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     if (alive) {
       const uint32_t trow = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
       const int ntap = type_a ? 6 : 3;
-      float* obase = (type_a ? p.out_a : p.out_b) + (long long)zi * ntap * p.cin * p.cout + nb * 128 + row;
+      float* obase = (type_a ? p.out_a : p.out_b) + ((long long)zi * p.kd + kdi) * ntap * p.cin * p.cout + nb * 128 + row;
 #pragma unroll 1
       for (int a = 0; a < nacc; ++a) {
 #pragma unroll 1
@@ -354,6 +361,8 @@ struct ConvHaloArgs {
   int n_total;
   float* stats_part;             // [slot][2][n_total] per-CTA partial sums (nullptr: no statistics)
   int a_stages;                  // B_RES kernels: activation stages that fit beside the resident filter
+  int kd;                        // filter depth (1, or 3 for the (3,3,3) layers of UNet3D): the reduction runs over
+  int depth;                     //   (kd, 64-channel block, tap); an "image" is slice z = img % depth of volume img / depth
   DeviceStatus* status;
 };
 
@@ -491,6 +500,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int box_w = p.halo ? 10 : 8;
   const int sub_rows = p.halo ? 180 : 128;
+  const int kblocks = p.kd * p.cblocks;
 
   if (warp == 0) {
     // ============================== A producer: one halo'd tile per (sub-tile, 64-channel block)
@@ -511,15 +521,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ty[j] = s % p.ntile_h;
           img[j] = s / p.ntile_h;
         }
-        for (int cb = 0; cb < p.cblocks && ok; ++cb) {
+        for (int cbx = 0; cbx < kblocks && ok; ++cbx) {
           if (!mbar_wait(a_empty + 8 * stage, phase ^ 1, st, 21)) { ok = false; break; }
           const uint32_t fb = a_full + 8 * stage;
           mbar_arrive_expect_tx(fb, nsub * sub_rows * 128);
+          const int kdi = cbx / p.cblocks, cb = cbx - kdi * p.cblocks;
 #pragma unroll
           for (int j = 0; j < NSUB; ++j)
-            if (j < nsub)
+            if (j < nsub)   // slices outside the volume are zero-filled by TMA: SAME padding along depth
               tma_load_5d(sA0 + stage * A_BYTES + j * CH_SUB_BYTES, &tmA, fb, cb * 64, tx[j] * 8 - p.halo,
-                          ty[j] * 16 - p.halo, img[j], 0);
+                          ty[j] * 16 - p.halo, img[j] % p.depth + kdi - (p.kd >> 1), img[j] / p.depth);
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -529,11 +540,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (B_RES) {
       if (elect_one_sync() && (int)blockIdx.x < p.n_units) {
         const int n0 = (blockIdx.x % p.n_ntiles) * BN;
-        mbar_arrive_expect_tx(b_full, p.cblocks * p.ntaps * B_BYTES);
-        for (int cb = 0; cb < p.cblocks; ++cb)
+        mbar_arrive_expect_tx(b_full, kblocks * p.ntaps * B_BYTES);
+        for (int cbx = 0; cbx < kblocks; ++cbx)
           for (int tap = 0; tap < p.ntaps; ++tap) {
-            const uint32_t sb = sB0 + (cb * p.ntaps + tap) * B_BYTES;
-            const int tapb = p.b_flip ? (p.ntaps - 1 - tap) : tap;
+            const uint32_t sb = sB0 + (cbx * p.ntaps + tap) * B_BYTES;
+            const int kdi = cbx / p.cblocks, cb = cbx - kdi * p.cblocks;
+            const int tapb = p.b_flip ? (p.kd * p.ntaps - 1 - (kdi * p.ntaps + tap)) : kdi * p.ntaps + tap;
             if (B_MN) {
               const int krow = (tapb * p.cblocks + cb) * 64;
 #pragma unroll
@@ -549,13 +561,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       bool ok = true;
       for (int u = blockIdx.x; u < p.n_units && ok; u += gridDim.x) {
         const int n0 = (u % p.n_ntiles) * BN;
-        for (int cb = 0; cb < p.cblocks && ok; ++cb) {
+        for (int cbx = 0; cbx < kblocks && ok; ++cbx) {
+          const int kdi = cbx / p.cblocks, cb = cbx - kdi * p.cblocks;
           for (int tap = 0; tap < p.ntaps; ++tap) {
             if (!mbar_wait(b_empty + 8 * stage, phase ^ 1, st, 22)) { ok = false; break; }
             const uint32_t fb = b_full + 8 * stage;
             const uint32_t sb = sB0 + stage * B_BYTES;
             mbar_arrive_expect_tx(fb, B_BYTES);
-            const int tapb = p.b_flip ? (p.ntaps - 1 - tap) : tap;
+            const int tapb = p.b_flip ? (p.kd * p.ntaps - 1 - (kdi * p.ntaps + tap)) : kdi * p.ntaps + tap;
             if (B_MN) {
               const int krow = (tapb * p.cblocks + cb) * 64;
 #pragma unroll
@@ -584,7 +597,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (!mbar_wait(acc_empty + 8 * buf, pacc ^ 1, st, 23)) { ok = false; break; }
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * (NSUB * BN);
-        for (int cb = 0; cb < p.cblocks && ok; ++cb) {
+        for (int cb = 0; cb < kblocks && ok; ++cb) {   // cb runs over (kd, 64-channel block) here
           if (!mbar_wait(a_full + 8 * sa, pa, st, 24)) { ok = false; break; }
           const uint32_t a_stage = sA0 + sa * A_BYTES;
           if (B_RES) tc_fence_after();

@@ -62,4 +62,13 @@ int bsl_channel_sum_bf16(bsl_ctx* ctx, const void* x, long long pixels, int c, i
 int bsl_stats_bf16(bsl_ctx* ctx, const void* x, long long pixels_per_group, int groups, int c, int ld, double* sums,
                    cudaStream_t stream);
 
+// (3,3,3) / (1,3,3) stride-1 layers on the halo-tile kernels (conv.cu), used by conv3d.cu when the shape allows.
+bool bsl_conv3d_halo_ok(const bsl_conv3d_desc* d);
+int bsl_conv3d_halo_fprop(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x, const void* w, void* y, cudaStream_t s);
+int bsl_conv3d_halo_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy, const void* w, void* dx, cudaStream_t s);
+bool bsl_conv3d_halo_wgrad_ok(const bsl_conv3d_desc* d);
+size_t bsl_conv3d_halo_wgrad_ws(bsl_ctx* ctx, const bsl_conv3d_desc* d);
+int bsl_conv3d_halo_wgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x, const void* dy, float* dw, void* workspace,
+                          size_t workspace_bytes, cudaStream_t s);
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -20,6 +20,11 @@ CASES = [  # (n, d, h, w, cin, cout, kernel, stride)
     (1, 8, 8, 8, 128, 64, (3, 3, 3), (2, 2, 2)),       # bridge/conv1
     (1, 4, 8, 8, 64, 64, (1, 3, 3), (1, 1, 1)),        # (1,3,3) through the 3-D entry point
     (1, 4, 8, 8, 64, 64, (1, 1, 1), (1, 1, 1)),
+    # stride-1 layers whose slices tile into 8x16 / 16x4 boxes: halo-tile kernels with the depth loop
+    (2, 3, 16, 16, 128, 128, (3, 3, 3), (1, 1, 1)),    # conv_e2/conv2: wide wgrad (cout % 128 == 0)
+    (1, 4, 16, 32, 128, 64, (3, 3, 3), (1, 1, 1)),     # cout 64: first wgrad kernel, resident filter in dgrad
+    (1, 2, 32, 16, 64, 320, (3, 3, 3), (1, 1, 1)),     # cout 320 (bridge width): not a multiple of 128
+    (2, 2, 16, 16, 256, 128, (1, 3, 3), (1, 1, 1)),
 ]
 
 

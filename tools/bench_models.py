@@ -59,6 +59,14 @@ def breakdown(fn, steps=2):
     print(f"  sum of bracketed calls {tot:.3f} ms/step", file=sys.stderr)
     for f, (c, ms) in sorted(by.items(), key=lambda kv: -kv[1][1])[:14]:
         print(f"  {ms / steps:8.3f} ms {c // steps:4d}x {f}", file=sys.stderr)
+    lay = collections.OrderedDict()
+    for f, tag, ms in rec:
+        if "conv" in f and "head" not in f:
+            lay.setdefault((tag, f), [0, 0.0])
+            lay[(tag, f)][0] += 1
+            lay[(tag, f)][1] += ms
+    for (tag, f), (c, ms) in lay.items():
+        print(f"    {ms / c:7.3f} ms  {f:26s} {tag}", file=sys.stderr)
     return rec
 
 
