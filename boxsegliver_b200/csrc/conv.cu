@@ -498,7 +498,7 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
     return bsl_stats_bf16(ctx, y, (long long)d->n * d->h * d->w, 1, d->cout, d->y_ld, sums, stream);
   }
   float* part = nullptr;
-  if ((rc = bsl_scratch(ctx, (size_t)pl.slots * 2 * d->cout * sizeof(float), &part))) return rc;
+  if ((rc = bsl_scratch(ctx, (size_t)pl.slots * 2 * d->cout * sizeof(float), &part, stream))) return rc;
   a.stats_part = part;
   rc = res ? launch_halo_res<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
            : launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);

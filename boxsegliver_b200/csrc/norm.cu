@@ -6,6 +6,8 @@
 // Statistics are two-level deterministic reductions (reduce.cuh); the apply passes move 16 B per
 // thread per access along the NHWC channel axis.
 #include "reduce.cuh"
+#include <mutex>
+#include <unordered_map>
 
 using namespace bsl;
 
@@ -42,18 +44,27 @@ __global__ void pixel_reduce_final_kernel(const float* __restrict__ part, int bl
   }
 }
 
-static float* g_scratch = nullptr;
-static size_t g_scratch_bytes = 0;
-int bsl_scratch(bsl_ctx* ctx, size_t bytes, float** out) {
-  if (bytes > g_scratch_bytes) {
-    if (g_scratch) cudaFree(g_scratch);
+// Scratch arena for the two-level reductions: one per stream, so reductions enqueued on the side streams (filter
+// gradients, all-reduce tails) never share partials with the ones on the compute stream. Grows on demand; growth
+// frees the old arena with cudaFree, which synchronises the device first.
+struct ScratchArena {
+  float* ptr = nullptr;
+  size_t bytes = 0;
+};
+static std::mutex g_scratch_mu;
+static std::unordered_map<cudaStream_t, ScratchArena> g_scratch;
+int bsl_scratch(bsl_ctx* ctx, size_t bytes, float** out, cudaStream_t stream) {
+  std::lock_guard<std::mutex> g(g_scratch_mu);
+  ScratchArena& a = g_scratch[stream];
+  if (bytes > a.bytes) {
+    if (a.ptr) cudaFree(a.ptr);
     size_t want = bytes < (16u << 20) ? (16u << 20) : bytes;
-    g_scratch = nullptr;
-    g_scratch_bytes = 0;
-    BSL_CUDA(ctx, cudaMalloc(&g_scratch, want));
-    g_scratch_bytes = want;
+    a.ptr = nullptr;
+    a.bytes = 0;
+    BSL_CUDA(ctx, cudaMalloc(&a.ptr, want));
+    a.bytes = want;
   }
-  *out = g_scratch;
+  *out = a.ptr;
   return BSL_OK;
 }
 }  // namespace bsl

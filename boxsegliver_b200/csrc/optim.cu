@@ -96,7 +96,7 @@ int bsl_adam_step(bsl_ctx* ctx, const bsl_adam_desc* d, float* w, const float* g
   double* part = nullptr;
   if (sumsq_out) {
     float* base = nullptr;
-    int rc = bsl_scratch(ctx, (size_t)blocks * sizeof(double), &base);
+    int rc = bsl_scratch(ctx, (size_t)blocks * sizeof(double), &base, as_stream(stream));
     if (rc) return rc;
     part = reinterpret_cast<double*>(base);
   }
@@ -120,7 +120,7 @@ int bsl_momentum_step(bsl_ctx* ctx, float lr, float momentum, float l2_rate, flo
   double* part = nullptr;
   if (sumsq_out) {
     float* base = nullptr;
-    int rc = bsl_scratch(ctx, (size_t)blocks * sizeof(double), &base);
+    int rc = bsl_scratch(ctx, (size_t)blocks * sizeof(double), &base, as_stream(stream));
     if (rc) return rc;
     part = reinterpret_cast<double*>(base);
   }

@@ -76,7 +76,7 @@ int bsl_channel_sum_bf16(bsl_ctx* ctx, const void* x, long long pixels, int c, i
   SumF f{reinterpret_cast<const __nv_bfloat16*>(x), ld};
   bsl::ReducePlan p = bsl::plan_reduce(ctx, pixels, 1, c, 1);
   float* base = nullptr;
-  int rc = bsl::bsl_scratch(ctx, p.scratch_bytes + (size_t)c * sizeof(double) + 16, &base);
+  int rc = bsl::bsl_scratch(ctx, p.scratch_bytes + (size_t)c * sizeof(double) + 16, &base, stream);
   if (rc) return rc;
   double* tmp = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + ((p.scratch_bytes + 15) & ~(size_t)15));
   rc = bsl::run_pixel_reduce(ctx, f, pixels, 1, c, tmp, stream);

@@ -119,7 +119,7 @@ inline ReducePlan plan_reduce(bsl_ctx* ctx, long long pixels_per_group, int grou
   return p;
 }
 
-int bsl_scratch(bsl_ctx* ctx, size_t bytes, float** out);
+int bsl_scratch(bsl_ctx* ctx, size_t bytes, float** out, cudaStream_t stream);
 
 template <class F>
 int run_pixel_reduce(bsl_ctx* ctx, const F& f, long long pixels_per_group, int groups, int c, double* out,
@@ -127,7 +127,7 @@ int run_pixel_reduce(bsl_ctx* ctx, const F& f, long long pixels_per_group, int g
   if (c % 8 || c <= 0 || c > 2048) return bsl_fail(ctx, BSL_EUNSUPPORTED, "pixel reduce: c=%d (multiple of 8, <= 2048)", c);
   ReducePlan p = plan_reduce(ctx, pixels_per_group, groups, c, F::K);
   float* part = nullptr;
-  int rc = bsl_scratch(ctx, p.scratch_bytes, &part);
+  int rc = bsl_scratch(ctx, p.scratch_bytes, &part, stream);
   if (rc) return rc;
   pixel_reduce_kernel<F, F::UNROLL><<<dim3(p.blocks, groups), p.threads, p.smem, stream>>>(f, pixels_per_group,
                                                                                           p.ppb, c, part);

@@ -384,7 +384,7 @@ int bsl_conv2d_stem_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x
   const long long ppb = (pixels + chunks - 1) / chunks;
   const int nout = d->kh * d->kw * d->cin * d->cout;
   float* part = nullptr;
-  rc = bsl_scratch(ctx, (size_t)chunks * nout * sizeof(float), &part);
+  rc = bsl_scratch(ctx, (size_t)chunks * nout * sizeof(float), &part, as_stream(stream));
   if (rc) return rc;
   const int threads = 32 * (d->cout / 8);
   auto go = [&](auto kern) {
@@ -462,7 +462,7 @@ int bsl_conv2d_head_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x,
   const size_t off_cols = off_sums + (size_t)d->cin * d->cout * sizeof(double);
   const int cblocks = 2 * ctx->sm_count;
   float* base = nullptr;
-  rc = bsl_scratch(ctx, off_cols + (size_t)cblocks * d->cout * sizeof(float), &base);
+  rc = bsl_scratch(ctx, off_cols + (size_t)cblocks * d->cout * sizeof(float), &base, s);
   if (rc) return rc;
   double* sums = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + off_sums);
   float* cpart = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + off_cols);

@@ -16,6 +16,7 @@ Memory plan (all NHWC, bf16 unless noted):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -135,6 +136,14 @@ class UNetEngine:
         self.stream = ctx.stream
         self.comm_stream = None
         self._graph = None
+        self._grad_stream = self.stream
+        self._overlap_wgrad = cfg.training and os.environ.get("BSL_WGRAD_OVERLAP", "1") != "0"
+        self._fork_pre = os.environ.get("BSL_WGRAD_FORK", "pre") == "pre"
+        if cfg.training:
+            self.wg_stream = ctx.new_stream()
+            self._dy_events = [ctx.new_event(), ctx.new_event()]
+            self._dy_busy = [None, None]
+            self._ev_ring, self._ev_ring_i = [ctx.new_event() for _ in range(96)], 0
 
     # ------------------------------------------------------------------ per-kernel timing (bench roofline)
     def enable_conv_timing(self, on: bool = True):
@@ -144,6 +153,12 @@ class UNetEngine:
         self._ev_pool = getattr(self, "_ev_pool", [])
         self._ev_next = 0
 
+    def _next_event(self):
+        """Round-robin pool for fork / join events (a step records far fewer than the ring holds)."""
+        e = self._ev_ring[self._ev_ring_i]
+        self._ev_ring_i = (self._ev_ring_i + 1) % len(self._ev_ring)
+        return e
+
     def _ev(self):
         if self._ev_next == len(self._ev_pool):
             self._ev_pool.append(self.ctx.new_event())
@@ -151,13 +166,14 @@ class UNetEngine:
         self._ev_next += 1
         return e
 
-    def _tc(self, name: str, flops: float, fn_name: str, *args):
-        """Enqueue a tensor-core conv call, optionally bracketed by events."""
+    def _tc(self, name: str, flops: float, fn_name: str, *args, stream=None):
+        """Enqueue a tensor-core conv call, optionally bracketed by events on the stream it is launched on."""
         if getattr(self, "_timing", False):
             e0, e1 = self._ev(), self._ev()
-            self.ctx.record(e0, self.stream)
+            st = stream if stream is not None else self.stream
+            self.ctx.record(e0, st)
             self.ctx.call(fn_name, *args)
-            self.ctx.record(e1, self.stream)
+            self.ctx.record(e1, st)
             self._timed.append((name, flops, e0, e1))
         else:
             self.ctx.call(fn_name, *args)
@@ -219,7 +235,7 @@ class UNetEngine:
         off, cnt = self._bucket_at[L.scope]
         ev = self._ev_ready[self._bucket_i]
         self._bucket_i += 1
-        self.ctx.record(ev, self.stream)
+        self.ctx.record(ev, self._grad_stream)
         self.ctx.call("bsl_stream_wait_event", self.comm_stream, ev)
         self.ctx.call("bsl_allreduce_sum_f32", C.c_void_p(self.G.ptr + off * F32), C.c_size_t(cnt), self.comm_stream)
 
@@ -399,6 +415,7 @@ class UNetEngine:
             self.dlogits = self._alloc(npx * cfg.num_classes * F32)
             self.g1 = self._alloc(n * max_act * BF16)
             self.g2 = self._alloc(n * max_act * BF16)
+            self.dyb = [self._alloc(n * max_act * BF16), self._alloc(n * max_act * BF16)]
             self.dcat = {i: View(self._alloc(v.pixels * v.c * BF16), n, v.h, v.w, v.c) for i, v in cat.items()}
             ws = 0
             for L in self.layers:
@@ -621,15 +638,32 @@ class UNetEngine:
                  self.loss_dev.at(4 * terms.index("dice")), self.dlogits.p, C.c_int(1 if len(terms) > 1 else 0),
                  self.loss_ws.p, C.c_size_t(self.loss_ws_bytes), s)
         n = cfg.batch
-        cur, oth = self.g1, self.g2     # `cur` holds the gradient w.r.t. the current activation
-        ns = self.norm_scope
+        # `cur` holds the gradient w.r.t. the current activation; dY (w.r.t. the conv output) alternates between two
+        # buffers so that the filter gradient of layer L can run on the side stream while the main stream goes on
+        # with dgrad(L) and the HBM-bound normalisation backward of layer L-1 (tensor-bound and memory-bound work
+        # overlap); a dY buffer is reused two conv layers later, behind an event.
+        cur, alt = self.g1, self.g2
+        overlap = self._overlap_wgrad and ctx._prof is None
+        ws = self.wg_stream if overlap else s
+        self._grad_stream = ws
+        k = 0
+        wsb = C.c_size_t(self.wgrad_ws_bytes)
+
+        def fork():
+            """side stream waits for everything enqueued on the main stream so far"""
+            if overlap:
+                ev = self._next_event()
+                ctx.record(ev, s)
+                call("bsl_stream_wait_event", ws, ev)
+
         for idx in range(len(self.layers) - 1, -1, -1):
             L = self.layers[idx]
             ctx.tag = L.scope
             if L.kind == "logits":
                 d = self._conv_desc(L)
+                fork()
                 call("bsl_conv2d_head_wgrad", C.byref(d), L.x.p, self.dlogits.p, self._pp(self.G, f"{L.scope}/weights"),
-                     self._pp(self.G, f"{L.scope}/biases"), s)
+                     self._pp(self.G, f"{L.scope}/biases"), ws)
                 call("bsl_conv2d_head_dgrad", C.byref(d), self.dlogits.p, self._pp(self.W, f"{L.scope}/weights"),
                      cur.p, s)
                 self._after_grad(L)
@@ -639,30 +673,46 @@ class UNetEngine:
                     # `cur` is the gradient w.r.t. the POOLED tensor; merge MaxPoolGrad with the skip gradient
                     dc = self.dcat[L.level]
                     call("bsl_maxpool2x2_bwd_add", C.c_int(n), C.c_int(L.h), C.c_int(L.w), C.c_int(L.cout), L.a.p,
-                         C.c_int(L.a.ld), cur.p, C.c_int(L.cout), dc.p, C.c_int(dc.ld), oth.p, C.c_int(L.cout), s)
-                    cur, oth = oth, cur
+                         C.c_int(L.a.ld), cur.p, C.c_int(L.cout), dc.p, C.c_int(dc.ld), alt.p, C.c_int(L.cout), s)
+                    cur, alt = alt, cur
+                dyb = self.dyb[k]
+                if overlap and self._dy_busy[k] is not None:       # the wgrad that read this buffer two layers ago
+                    call("bsl_stream_wait_event", s, self._dy_busy[k])
                 nd = self._norm_desc(L)
                 q = self._norm_ptrs(L)
-                self._norm_backward(L, nd, q, cur, oth)
-                # oth = dY (gradient w.r.t. the conv output), dense with ld = cout
+                self._norm_backward(L, nd, q, cur, dyb)
+                # dyb = dY (gradient w.r.t. the conv output), dense with ld = cout
                 d = self._conv_desc(L)
                 d.y_ld = L.cout
                 gw = self._pp(self.G, f"{L.scope}/weights")
-                if L.kind == "stem":
-                    d1 = _lib.Conv2dDesc(n, L.h, L.w, 64, L.cout, 1, 1, 64, L.cout)
-                    self._tc("wgrad", self._flops(L), "bsl_conv2d_wgrad", C.byref(d1), self.stem_col.p, oth.p, gw,
-                             self.wgrad_ws.p, C.c_size_t(self.wgrad_ws_bytes), s)
-                else:
-                    self._tc("wgrad", self._flops(L), "bsl_conv2d_wgrad", C.byref(d), L.x.p, oth.p, gw,
-                             self.wgrad_ws.p, C.c_size_t(self.wgrad_ws_bytes), s)
+                # dgrad first, on the main stream; the side stream forks AFTER it, so that the filter gradient of this
+                # layer runs beside the HBM-bound normalisation backward of the next one instead of beside dgrad
+                if self._fork_pre:
+                    fork()
+                if L.kind != "stem":
                     wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
+                    dd = self._conv_desc(L)
+                    dd.y_ld = L.cout
                     if L.role == "dec1":
                         dc = self.dcat[L.level]
-                        d.x_ld = dc.ld
-                        self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad", C.byref(d), oth.p, wbf, dc.p, s)
+                        dd.x_ld = dc.ld
+                        self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad", C.byref(dd), dyb.p, wbf, dc.p, s)
                     else:
-                        d.x_ld = L.cin
-                        self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad", C.byref(d), oth.p, wbf, cur.p, s)
+                        dd.x_ld = L.cin
+                        self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad", C.byref(dd), dyb.p, wbf, cur.p, s)
+                if not self._fork_pre:
+                    fork()
+                if L.kind == "stem":
+                    d1 = _lib.Conv2dDesc(n, L.h, L.w, 64, L.cout, 1, 1, 64, L.cout)
+                    self._tc("wgrad", self._flops(L), "bsl_conv2d_wgrad", C.byref(d1), self.stem_col.p, dyb.p, gw,
+                             self.wgrad_ws.p, wsb, ws, stream=ws)
+                else:
+                    self._tc("wgrad", self._flops(L), "bsl_conv2d_wgrad", C.byref(d), L.x.p, dyb.p, gw,
+                             self.wgrad_ws.p, wsb, ws, stream=ws)
+                if overlap:
+                    self._dy_busy[k] = self._dy_events[k]
+                    ctx.record(self._dy_busy[k], ws)
+                k ^= 1
                 self._after_grad(L)
             elif L.kind == "convT":
                 dc = self.dcat[L.level]
@@ -672,13 +722,20 @@ class UNetEngine:
                      C.c_int(dup.ld), dup.p, C.c_int(dup.ld), s)
                 d = self._convT_desc(L)
                 d.y_ld = dup.ld
-                self._tc("convT_wgrad", self._flops(L), "bsl_convT2d_bwd_filter", C.byref(d), L.x.p, dup.p,
-                         self._pp(self.G, f"{L.scope}/weights"), self._pp(self.G, f"{L.scope}/biases"),
-                         self.wgrad_ws.p, C.c_size_t(self.wgrad_ws_bytes), s)
                 d.x_ld = L.cin
                 self._tc("convT_dgrad", self._flops(L), "bsl_convT2d_bwd_data", C.byref(d), dup.p,
                          self._pp(self.Wbf, f"{L.scope}/weights", BF16), cur.p, s)
+                fork()
+                d.x_ld = L.x.ld
+                self._tc("convT_wgrad", self._flops(L), "bsl_convT2d_bwd_filter", C.byref(d), L.x.p, dup.p,
+                         self._pp(self.G, f"{L.scope}/weights"), self._pp(self.G, f"{L.scope}/biases"),
+                         self.wgrad_ws.p, wsb, ws, stream=ws)
                 self._after_grad(L)
+        if overlap:     # join: everything downstream (optimizer, host reads of G) is ordered after the filter gradients
+            ev = self._next_event()
+            ctx.record(ev, ws)
+            call("bsl_stream_wait_event", s, ev)
+            self._dy_busy = [None, None]
 
     # ------------------------------------------------------------------ optimizer
     def optimizer_step(self, lr: float):

@@ -18,6 +18,7 @@ concat [encoder, up], 1x1x1 logits, weighted cross-entropy. What differs from th
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -157,6 +158,12 @@ class UNet3DEngine:
         self.step_count = 0
         self._bufs = []
         self.stream = ctx.stream
+        # filter gradients on a side stream, as in engine.UNetEngine.loss_backward
+        self._overlap_wgrad = cfg.training and os.environ.get("BSL_WGRAD_OVERLAP", "1") != "0"
+        if cfg.training:
+            self.wg_stream = ctx.new_stream()
+            self._dy_events = [ctx.new_event(), ctx.new_event()]
+            self._ev_ring, self._ev_ring_i = [ctx.new_event() for _ in range(96)], 0
         self._plan_layers()
         self._plan_params()
         self._plan_activations()
@@ -299,6 +306,7 @@ class UNet3DEngine:
             self.dlogits = self._alloc(nvox * k * F32)
             self.g1 = self._alloc(n * max_act * BF16)
             self.g2 = self._alloc(n * max_act * BF16)
+            self.dyb = [self._alloc(n * max_act * BF16), self._alloc(n * max_act * BF16)]
             self.dcat = {b: View3(self._alloc(v.voxels * v.c * BF16), n, v.dhw, v.c) for b, v in cat.items()}
             ws = 0
             for L in self.layers:
@@ -505,50 +513,69 @@ class UNet3DEngine:
         call("bsl_label_counts", C.byref(ld), self.labels.p, self.counts.p, s)
         call("bsl_wxent_fwd_bwd", C.byref(ld), self.logits.p, self.labels.p, self.counts.p, self.loss_dev.p,
              self.dlogits.p, self.loss_ws.p, C.c_size_t(self.loss_ws_bytes), s)
-        cur, oth = self.g1, self.g2
+        cur, alt = self.g1, self.g2
         wsb = C.c_size_t(self.wgrad_ws_bytes)
+        overlap = self._overlap_wgrad and ctx._prof is None
+        ws = self.wg_stream if overlap else s
+        busy = [None, None]
+        k = 0
+
+        def fork():
+            if overlap:
+                ev = self._ev_ring[self._ev_ring_i]
+                self._ev_ring_i = (self._ev_ring_i + 1) % len(self._ev_ring)
+                ctx.record(ev, s)
+                call("bsl_stream_wait_event", ws, ev)
+
         for L in reversed(self.layers):
             ctx.tag = L.scope
             if L.kind == "logits":
                 dh = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.cout, 1, 1, L.x.ld, L.cout)
+                fork()
                 call("bsl_conv2d_head_wgrad", C.byref(dh), L.x.p, self.dlogits.p, self._pp(self.G, f"{L.scope}/weights"),
-                     self._pp(self.G, f"{L.scope}/biases"), s)
-                dh.x_ld = L.cinp
-                call("bsl_conv2d_head_dgrad", C.byref(dh), self.dlogits.p, self._pp(self.W, f"{L.scope}/weights"), cur.p, s)
+                     self._pp(self.G, f"{L.scope}/biases"), ws)
+                dh2 = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.cout, 1, 1, L.cinp, L.cout)
+                call("bsl_conv2d_head_dgrad", C.byref(dh2), self.dlogits.p, self._pp(self.W, f"{L.scope}/weights"), cur.p, s)
             elif L.kind in ("stem", "conv"):
                 vox = n * int(np.prod(L.odhw))
                 if L.fork:   # AddN: gradient through the next block's strided conv + gradient through the skip
                     dc = self.dcat[L.block]
                     call("bsl_add_bf16", C.c_longlong(vox), C.c_int(L.coutp), cur.p, C.c_int(L.coutp), dc.p,
-                         C.c_int(dc.ld), oth.p, C.c_int(L.coutp), s)
-                    cur, oth = oth, cur
+                         C.c_int(dc.ld), alt.p, C.c_int(L.coutp), s)
+                    cur, alt = alt, cur
+                dyb = self.dyb[k]
+                if overlap and busy[k] is not None:
+                    call("bsl_stream_wait_event", s, busy[k])
                 nd, q = self._norm_desc(L), self._norm_ptrs(L)
                 call("bsl_norm_bwd_reduce", C.byref(nd), L.y.p, cur.p, C.c_int(L.coutp), q["mean"], q["rstd"], q["scale"],
                      q["shift"], q["sums"], s)
                 call("bsl_norm_bwd_finalize", C.byref(nd), q["sums"], q["c1"], q["c2"],
                      self._pp(self.G, f"{L.scope}/InstanceNorm/gamma"), self._pp(self.G, f"{L.scope}/InstanceNorm/beta"), s)
                 call("bsl_norm_bwd_apply", C.byref(nd), L.y.p, cur.p, C.c_int(L.coutp), q["mean"], q["rstd"], q["scale"],
-                     q["shift"], q["c1"], q["c2"], oth.p, C.c_int(L.coutp), s)
+                     q["shift"], q["c1"], q["c2"], dyb.p, C.c_int(L.coutp), s)
                 gw = self._pp(self.G, f"{L.scope}/weights")
                 wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
+                fork()
                 if L.kind == "stem":
                     d1 = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], 64, L.coutp, 1, 1, 64, L.coutp)
-                    call("bsl_conv2d_wgrad", C.byref(d1), self.stem_col.p, oth.p, gw, self.wgrad_ws.p, wsb, s)
-                    continue
-                is_dec1 = L.block.startswith("conv_d") and L.layer == "conv1"
-                dx = self.dcat[L.block.replace("d", "e")] if is_dec1 else None
-                if self._is2d(L):
-                    d = self._desc2(L)
-                    d.y_ld = L.coutp
-                    call("bsl_conv2d_wgrad", C.byref(d), L.x.p, oth.p, gw, self.wgrad_ws.p, wsb, s)
-                    d.x_ld = dx.ld if dx is not None else L.cinp
-                    call("bsl_conv2d_dgrad", C.byref(d), oth.p, wbf, dx.p if dx is not None else cur.p, s)
+                    call("bsl_conv2d_wgrad", C.byref(d1), self.stem_col.p, dyb.p, gw, self.wgrad_ws.p, wsb, ws)
                 else:
-                    d = self._desc3(L)
+                    is_dec1 = L.block.startswith("conv_d") and L.layer == "conv1"
+                    dx = self.dcat[L.block.replace("d", "e")] if is_dec1 else None
+                    two_d = self._is2d(L)
+                    d = self._desc2(L) if two_d else self._desc3(L)
                     d.y_ld = L.coutp
-                    call("bsl_conv3d_wgrad", C.byref(d), L.x.p, oth.p, gw, self.wgrad_ws.p, wsb, s)
-                    d.x_ld = dx.ld if dx is not None else L.cinp
-                    call("bsl_conv3d_dgrad", C.byref(d), oth.p, wbf, dx.p if dx is not None else cur.p, s)
+                    call("bsl_conv2d_wgrad" if two_d else "bsl_conv3d_wgrad", C.byref(d), L.x.p, dyb.p, gw,
+                         self.wgrad_ws.p, wsb, ws)
+                    dd = self._desc2(L) if two_d else self._desc3(L)
+                    dd.y_ld = L.coutp
+                    dd.x_ld = dx.ld if dx is not None else L.cinp
+                    call("bsl_conv2d_dgrad" if two_d else "bsl_conv3d_dgrad", C.byref(dd), dyb.p, wbf,
+                         dx.p if dx is not None else cur.p, s)
+                if overlap:
+                    busy[k] = self._dy_events[k]
+                    ctx.record(busy[k], ws)
+                k ^= 1
             else:  # convT
                 dc = self.dcat[L.block.replace("d", "e")]
                 dup = dc.slice(L.coutp, L.coutp)
@@ -557,18 +584,21 @@ class UNet3DEngine:
                      dup.p, C.c_int(dup.ld), s)
                 gw = self._pp(self.G, f"{L.scope}/weights")
                 wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
-                if L.s[0] == 1:
-                    d = self._descT2(L)
-                    d.y_ld = dup.ld
-                    call("bsl_convT2d_bwd_filter", C.byref(d), L.x.p, dup.p, gw, None, self.wgrad_ws.p, wsb, s)
-                    d.x_ld = L.cinp
-                    call("bsl_convT2d_bwd_data", C.byref(d), dup.p, wbf, cur.p, s)
-                else:
-                    d = self._descT3(L)
-                    d.y_ld = dup.ld
-                    call("bsl_convT3d_bwd_filter", C.byref(d), L.x.p, dup.p, gw, None, self.wgrad_ws.p, wsb, s)
-                    d.x_ld = L.cinp
-                    call("bsl_convT3d_bwd_data", C.byref(d), dup.p, wbf, cur.p, s)
+                two_d = L.s[0] == 1
+                d = self._descT2(L) if two_d else self._descT3(L)
+                d.y_ld = dup.ld
+                fork()
+                call("bsl_convT2d_bwd_filter" if two_d else "bsl_convT3d_bwd_filter", C.byref(d), L.x.p, dup.p, gw, None,
+                     self.wgrad_ws.p, wsb, ws)
+                dd = self._descT2(L) if two_d else self._descT3(L)
+                dd.y_ld = dup.ld
+                dd.x_ld = L.cinp
+                call("bsl_convT2d_bwd_data" if two_d else "bsl_convT3d_bwd_data", C.byref(dd), dup.p, wbf, cur.p, s)
+        if overlap:
+            ev = self._ev_ring[self._ev_ring_i]
+            self._ev_ring_i = (self._ev_ring_i + 1) % len(self._ev_ring)
+            ctx.record(ev, ws)
+            call("bsl_stream_wait_event", s, ev)
 
     # ------------------------------------------------------------------ optimizer / step
     def attach_comm(self, rank: int, world: int, unique_id: bytes):
