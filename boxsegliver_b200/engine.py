@@ -816,6 +816,57 @@ class UNetEngine:
         reg = float(self.cfg.weight_decay_rate * 0.5 * out[1]) if self.cfg.weight_decay_rate > 0 else 0.0
         return data + reg
 
+    # ---- prefetching variant: a 2-deep ring of pinned staging slots + device input buffers. The H2D copy of batch
+    # i + 1 runs on a copy stream while step i computes (what tf.data prefetch / StagingArea does for the reference's
+    # feed path); every step still pays one H2D of its own inputs and one D2H of its loss.
+    def staging_slot(self, j: int):
+        """numpy views (images, labels) of pinned slot j in {0, 1}. Do not refill a slot between submit_staged(j) and
+        the train_step_prefetched() that consumes it."""
+        if not hasattr(self, "_ring"):
+            cfg = self.cfg
+            shp_i = (cfg.batch, cfg.height, cfg.width, cfg.channel)
+            shp_l = (cfg.batch, cfg.height, cfg.width)
+            self._ring = []
+            for k in range(2):
+                pi, pl = C.c_void_p(), C.c_void_p()
+                self.ctx.call("bsl_host_alloc", C.c_size_t(int(np.prod(shp_i)) * 4), C.byref(pi))
+                self.ctx.call("bsl_host_alloc", C.c_size_t(int(np.prod(shp_l)) * 4), C.byref(pl))
+                img = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_float)), shape=shp_i)
+                lab = np.ctypeslib.as_array(C.cast(pl, C.POINTER(C.c_int32)), shape=shp_l)
+                dimg = self.images if k == 0 else self._alloc(img.nbytes)
+                dlab = self.labels if k == 0 else self._alloc(lab.nbytes)
+                self._ring.append(dict(img=img, lab=lab, pi=pi, pl=pl, dimg=dimg, dlab=dlab, ev=self.ctx.new_event()))
+            self.copy_stream = self.ctx.new_stream()
+            self._submitted = []
+            self.pinned_inputs()   # the D2H slot for the loss
+        return self._ring[j]["img"], self._ring[j]["lab"]
+
+    def submit_staged(self, j: int):
+        """Enqueue the H2D copy of pinned slot j into device input buffer j on the copy stream."""
+        r = self._ring[j]
+        cs = self.copy_stream
+        self.ctx.call("bsl_memcpy_h2d", r["dimg"].p, r["pi"], C.c_size_t(r["img"].nbytes), cs)
+        self.ctx.call("bsl_memcpy_h2d", r["dlab"].p, r["pl"], C.c_size_t(r["lab"].nbytes), cs)
+        self.ctx.record(r["ev"], cs)
+        self._submitted.append(j)
+
+    def train_step_prefetched(self, lr: float, with_metrics: bool = False):
+        """One training step on the oldest submitted slot; returns the total loss (D2H read, host sync)."""
+        j = self._submitted.pop(0)
+        r = self._ring[j]
+        s = self.stream
+        self.ctx.call("bsl_stream_wait_event", s, r["ev"])
+        self.images, self.labels = r["dimg"], r["dlab"]
+        self.train_step(lr, with_metrics)
+        out, po = self._pin[2], self._pin[5]
+        nt = len(self._loss_terms())
+        self.ctx.call("bsl_memcpy_d2h", po, self.loss_dev.p, C.c_size_t(4 * nt), s)
+        self.ctx.call("bsl_memcpy_d2h", C.c_void_p(po.value + 8), self.sumsq.p, C.c_size_t(8), s)
+        self.ctx.sync(s)
+        data = float(np.frombuffer(out[:1].tobytes(), np.float32)[:nt].sum())
+        reg = float(self.cfg.weight_decay_rate * 0.5 * out[1]) if self.cfg.weight_decay_rate > 0 else 0.0
+        return data + reg
+
     def h2d_bytes_per_step(self):
         cfg = self.cfg
         return cfg.batch * cfg.height * cfg.width * (cfg.channel * 4 + 4)

@@ -168,3 +168,49 @@ def test_full_size_training_properties(ctx):
     ctx.check_device()
     assert np.all(np.isfinite(losses)) and losses[-1] < losses[0], losses
     eng.close()
+
+
+def test_host_fed_steps_match_device_resident_steps(ctx):
+    """The e2e entry points (pinned batch -> H2D -> step -> D2H loss; with and without prefetch) run the same
+    arithmetic as the device-resident step: identical loss sequences and bit-identical weights."""
+    n, hw = 2, 64
+    ecfg, _ = _cfgs(n, hw, "batch_norm", "xentropy", "numerical")
+    batches = [synthetic.make_batch(n, hw, hw, 3, seed=40 + i) for i in range(3)]
+
+    def run(mode):
+        eng = UNetEngine(ctx, ecfg)
+        eng.init_weights(seed=2)
+        losses = []
+        if mode == "resident":
+            for im, lb in batches:
+                eng.set_inputs(im, lb)
+                eng.train_step(1e-3)
+                losses.append(sum(eng.read_loss()))
+        elif mode == "host":
+            pi, pl = eng.pinned_inputs()
+            for im, lb in batches:
+                pi[...] = im
+                pl[...] = lb
+                losses.append(eng.train_step_host(1e-3))
+        else:
+            for j in (0, 1):
+                eng.staging_slot(j)
+            si, sl = eng.staging_slot(0)
+            si[...], sl[...] = batches[0]
+            eng.submit_staged(0)
+            for i in range(len(batches)):
+                if i + 1 < len(batches):
+                    si, sl = eng.staging_slot((i + 1) % 2)
+                    si[...], sl[...] = batches[i + 1]
+                    eng.submit_staged((i + 1) % 2)
+                losses.append(eng.train_step_prefetched(1e-3))
+        ctx.check_device()
+        w = eng.W.download(np.float32, (eng.n_train,))
+        eng.close()
+        return np.array(losses), w
+
+    l0, w0 = run("resident")
+    for mode in ("host", "prefetch"):
+        l, w = run(mode)
+        assert np.allclose(l, l0, rtol=1e-6), (mode, l, l0)
+        assert np.array_equal(w, w0), mode
