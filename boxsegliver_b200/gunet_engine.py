@@ -15,6 +15,7 @@ and ct_conv raise NotImplementedError.
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 from dataclasses import dataclass
 
 import numpy as np
@@ -51,6 +52,8 @@ class GUNetConfig(EngineConfig):
 
 
 class GUNetEngine(UNetEngine):
+    prefix = "GUNet"      # variable-scope root (UNetInterEngine reuses the graph under "UNetInter")
+
     def __init__(self, ctx, cfg: GUNetConfig):
         if cfg.normalizer != "instance_norm":
             raise NotImplementedError("GUNet engine: guide modulation is implemented for --normalizer instance_norm")
@@ -80,7 +83,7 @@ class GUNetEngine(UNetEngine):
             for j in (1, 2):
                 kind = "stem" if (i == 0 and j == 1) else "conv"
                 role = f"enc{j}" if i < nd else f"bridge{j}"
-                L = ConvL(kind, f"GUNet/Encode/down_conv{i + 1}/mod_conv{j}/Conv", cin, c, h, w, i, role=role,
+                L = ConvL(kind, f"{self.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/Conv", cin, c, h, w, i, role=role,
                           center=cfg.norm_with_center if mod else True, scale=cfg.norm_with_scale if mod else True)
                 if mod and cfg.use_context:
                     L.mod_off = off
@@ -95,14 +98,14 @@ class GUNetEngine(UNetEngine):
                 w //= 2
         for i in reversed(range(nd)):
             c //= 2
-            specs.append(ConvL("convT", f"GUNet/Decode/up{i + 1}", cin, cin // 2, h, w, i))
+            specs.append(ConvL("convT", f"{self.prefix}/Decode/up{i + 1}", cin, cin // 2, h, w, i))
             h *= 2
             w *= 2
             for j in (1, 2):
-                specs.append(ConvL("conv", f"GUNet/Decode/up_conv{i + 1}/up_conv{i + 1}_{j}",
+                specs.append(ConvL("conv", f"{self.prefix}/Decode/up_conv{i + 1}/up_conv{i + 1}_{j}",
                                    c + cin // 2 if j == 1 else c, c, h, w, i, role=f"dec{j}"))
             cin = c
-        specs.append(ConvL("logits", "GUNet/AdjustChannels", cin, cfg.num_classes, h, w, 0))
+        specs.append(ConvL("logits", f"{self.prefix}/AdjustChannels", cin, cfg.num_classes, h, w, 0))
         return specs
 
     def _fc_specs(self):
@@ -275,3 +278,41 @@ class GUNetEngine(UNetEngine):
 
     def get_context_params(self):
         return self.ctx_params.download(np.float32, (self.cfg.batch, self.cfg.n_modulator_param))
+
+
+@dataclass
+class UNetInterConfig(GUNetConfig):
+    """UNetInter (/root/reference/NetworksV2/UNetInter.py:44-160): the interactive-segmentation U-Net. `channel` is the
+    image channel count; the `guide_channel`-channel click guide is concatenated to the images at the input."""
+    height: int = 256
+    width: int = 256
+    use_context: bool = False
+    use_spatial: bool = False
+    mod_layers: tuple = ()
+    guide_channel: int = 2
+    mid_cat: bool = False
+
+
+class UNetInterEngine(GUNetEngine):
+    """UNetInter = GUNet's variable layout (Encode/down_conv*/mod_conv*/Conv, Decode/up*, up_conv*) without modulation:
+    every conv is conv -> norm(center, scale) -> ReLU, and the network input is concat(images, sp_guide)
+    (UNetInter.py:89-92). --mid_cat (guide re-concatenated after the first block: 66 input channels to the next
+    conv) is not a multiple of the tensor-core channel block and raises NotImplementedError."""
+    prefix = "UNetInter"
+
+    def __init__(self, ctx, cfg: UNetInterConfig):
+        if cfg.mid_cat:
+            raise NotImplementedError("UNetInter --mid_cat is outside the accelerated path")
+        if cfg.use_context or cfg.use_spatial or cfg.mod_layers:
+            raise ValueError("UNetInter has no guide modulation: the guide is an input channel")
+        self.image_channels = cfg.channel
+        self.user_cfg = cfg
+        super().__init__(ctx, dataclasses.replace(cfg, channel=cfg.channel + cfg.guide_channel))
+
+    def set_inputs(self, images: np.ndarray, labels: np.ndarray | None = None, sp_guide: np.ndarray | None = None,
+                   stream=None):
+        cfg = self.cfg
+        if images.shape[-1] == self.image_channels:
+            assert sp_guide is not None and sp_guide.shape == images.shape[:3] + (cfg.guide_channel,), "sp_guide"
+            images = np.concatenate((images, sp_guide), axis=-1)          # UNetInter.py:90
+        super().set_inputs(images, labels, stream)

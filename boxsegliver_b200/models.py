@@ -5,10 +5,10 @@ from pathlib import Path
 
 import yaml
 
-from .networks import GUNet, UNet, UNet3D
+from .networks import GUNet, UNet, UNet3D, UNetInter
 from .networks.base import ModeKeys
 
-MODEL_ZOO = [UNet, GUNet, UNet3D]
+MODEL_ZOO = [UNet, GUNet, UNet3D, UNetInter]
 
 
 def add_arguments(parser):

@@ -47,6 +47,8 @@ class GUNetCfg:
     loss_numeric_w: tuple = ()
     loss_proportion_decay: float = 1000.0
     in_eps: float = 1e-6
+    prefix: str = "GUNet"                # "UNetInter": same variable layout, no modulation, guide concatenated to the
+                                         # images at the input (/root/reference/NetworksV2/UNetInter.py:89-92,118-146)
 
     @property
     def num_classes(self):
@@ -55,6 +57,19 @@ class GUNetCfg:
     @property
     def n_modulator_param(self):
         return self.init_channels * sum(2 ** i for i in range(self.num_down_samples + 1) if i in self.mod_layers) * 2
+
+
+def unetinter_cfg(channel: int = 3, guide_channel: int = 2, **kw) -> GUNetCfg:
+    """UNetInter (/root/reference/NetworksV2/UNetInter.py:73-146) expressed on the GUNet restatement: scope root
+    "UNetInter", no modulated block, every conv followed by norm(center, scale) + ReLU (encoder_arg_scope, :100-117),
+    and `channel + guide_channel` network input channels (the guide is concatenated to the images, :89-90)."""
+    return GUNetCfg(channel=channel + guide_channel, guide_channel=guide_channel, prefix="UNetInter", use_context=False,
+                    use_spatial=False, mod_layers=(), **kw)
+
+
+def unetinter_inputs(images: np.ndarray, sp_guide: np.ndarray) -> dict:
+    """tf.concat((images, sp_guide), axis=-1) -- UNetInter.py:90."""
+    return dict(images=np.concatenate((images, sp_guide), axis=-1))
 
 
 def layer_specs(cfg: GUNetCfg):
@@ -68,7 +83,7 @@ def layer_specs(cfg: GUNetCfg):
     for i in range(cfg.num_down_samples + 1):
         mod = i in cfg.mod_layers and (cfg.use_context or cfg.use_spatial)
         for j in (1, 2):
-            s = dict(kind="conv", scope=f"GUNet/Encode/down_conv{i + 1}/mod_conv{j}/Conv", cin=cin, cout=c, level=i,
+            s = dict(kind="conv", scope=f"{cfg.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/Conv", cin=cin, cout=c, level=i,
                      role=f"enc{j}", mod=mod, center=cfg.norm_with_center if mod else True,
                      scale=cfg.norm_with_scale if mod else True, mod_off=None, sp_off=None)
             if mod and cfg.use_context:
@@ -82,13 +97,13 @@ def layer_specs(cfg: GUNetCfg):
             c *= 2
     for i in reversed(range(cfg.num_down_samples)):
         c //= 2
-        specs.append(dict(kind="convT", scope=f"GUNet/Decode/up{i + 1}", cin=cin, cout=cin // 2, level=i))
+        specs.append(dict(kind="convT", scope=f"{cfg.prefix}/Decode/up{i + 1}", cin=cin, cout=cin // 2, level=i))
         for j in (1, 2):
-            specs.append(dict(kind="conv", scope=f"GUNet/Decode/up_conv{i + 1}/up_conv{i + 1}_{j}",
+            specs.append(dict(kind="conv", scope=f"{cfg.prefix}/Decode/up_conv{i + 1}/up_conv{i + 1}_{j}",
                               cin=c + cin // 2 if j == 1 else c, cout=c, level=i, role=f"dec{j}", mod=False, center=True,
                               scale=True, mod_off=None, sp_off=None))
         cin = c
-    specs.append(dict(kind="logits", scope="GUNet/AdjustChannels", cin=cin, cout=cfg.num_classes, level=0))
+    specs.append(dict(kind="logits", scope=f"{cfg.prefix}/AdjustChannels", cin=cin, cout=cfg.num_classes, level=0))
     return specs
 
 

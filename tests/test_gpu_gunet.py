@@ -131,3 +131,53 @@ def test_gunet_train_step_parity(ctx, n, hw, kw):
     errs = {name: rel(grads[name], g) for name, g in g_ref.items()}
     assert np.median(list(errs.values())) < 1e-2, errs
     assert max(errs.values()) < 1.5e-2, max(errs.items(), key=lambda t: t[1])
+
+
+def test_unetinter_train_step_parity(ctx):
+    """UNetInter (/root/reference/NetworksV2/UNetInter.py:73-146): image + 2-channel click guide as a 5-channel
+    input, variables under "UNetInter/", no modulation; same gates as the GUNet parity test."""
+    from boxsegliver_b200.gunet_engine import UNetInterConfig, UNetInterEngine
+    n, hw = 2, 64
+    base = dict(height=hw, width=hw, init_channels=64, num_down_samples=4, weight_decay_rate=1e-5,
+                loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4), loss_type="xentropy+dice")
+    ecfg = UNetInterConfig(batch=n, channel=3, guide_channel=2, **base)
+    rcfg = G.unetinter_cfg(channel=3, guide_channel=2, **base)
+    images, labels = synthetic.make_batch(n, hw, hw, 3, seed=1377)
+    _, guide = synthetic.make_guides(images, labels, 200, 2, seed=6)
+    params = G.init_params(rcfg, seed=9)
+    rng = np.random.default_rng(4)
+    for k in params:
+        if k.endswith(("beta", "biases")):
+            params[k] = (0.1 * rng.standard_normal(params[k].shape)).astype(np.float32)
+        if k.endswith("gamma"):
+            params[k] = (1 + 0.1 * rng.standard_normal(params[k].shape)).astype(np.float32)
+    eng = UNetInterEngine(ctx, ecfg)
+    assert set(eng.params) == set(params)
+    eng.set_weights(params)
+    eng.set_inputs(images, labels, guide)
+    eng.forward(True)
+    eng.predict_outputs(True)
+    eng.loss_backward()
+    ctx.check_device()
+    logits = eng.logits.download(np.float32, (n, hw, hw, 3))
+    dlogits = eng.dlogits.download(np.float32, (n, hw, hw, 3))
+    grads = eng.get_grads()
+    stored = eng.get_stored_forward()
+    stored["logits"] = logits
+    eng.optimizer_step(1e-3)          # sum(w^2) of the step's weights is accumulated by the optimizer kernel
+    ctx.check_device()
+    data_loss, reg_loss = eng.read_loss()
+    eng.close()
+    rin = {k_: round_bf16(v).astype(np.float64) for k_, v in G.unetinter_inputs(images, guide).items()}
+    tft = G.forward({k_: v.astype(np.float64) for k_, v in params.items()}, rin, rcfg, True, wrnd=round_bf16,
+                    stored=stored)
+    assert max(tft.errs.values()) < 1e-2, max(tft.errs.items(), key=lambda t: t[1])
+    loss_o, dl = G.loss_and_dlogits(tft, labels, rcfg)
+    assert abs(data_loss - loss_o) < 1e-4 * abs(loss_o)
+    assert abs(reg_loss - G.regularization_loss(params, rcfg)) < 1e-6
+    assert rel(dlogits, dl) < 1e-5
+    g_ref = G.backward(tft, dl, rcfg, rnd=round_bf16)
+    errs = {name: rel(grads[name], g) for name, g in g_ref.items()}
+    assert set(g_ref) == set(grads)
+    assert np.median(list(errs.values())) < 1e-2, errs
+    assert max(errs.values()) < 1.5e-2, max(errs.items(), key=lambda t: t[1])

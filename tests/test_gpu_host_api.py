@@ -1,0 +1,100 @@
+"""The drop-in call sequence of the reference (core/models.py:224-281 model_fn -> core/solver.py:204-243 Solver ->
+core/estimator.py:756-757 `sess.run([train_op, loss])`) driven through the host mirror, for every model class of
+MODEL_ZOO that a shipped script trains. The step it runs must be the step the engine tests gate: same loss as the
+engine driven directly with the same seed, loss decreasing over a few steps, predictions / metrics populated."""
+import argparse
+
+import numpy as np
+import pytest
+
+from boxsegliver_b200 import models, solver, synthetic
+from boxsegliver_b200.networks.base import ModeKeys
+
+pytestmark = pytest.mark.gpu
+
+
+def _args(model, **kw):
+    p = argparse.ArgumentParser()
+    models.add_arguments(p)
+    solver.add_arguments(p)
+    a = p.parse_args(["--model", model, "--classes", "Liver", "Tumor", "--batch_size", "2",
+                      "--normalizer", kw.pop("normalizer", "batch_norm"), "--learning_rate", "1e-3"])
+    base = dict(im_height=64, im_width=64, im_channel=3, num_gpus=1, seed=3, weight_decay_rate=1e-5, bias_decay=False,
+                loss_type="xentropy", loss_weight_type="numerical", loss_numeric_w=[0.2, 0.4, 4.4],
+                loss_proportion_decay=1000.0, metrics_train=["Dice"], use_spatial=False, use_context=False)
+    base.update(kw)
+    for k, v in base.items():
+        setattr(a, k, v)
+    return a
+
+
+def _drive(ctx, model_name, feed_kw, **kw):
+    args = _args(model_name, **kw)
+    params = models.get_model_params(args, build_metrics=True)
+    params.update(args=args, solver=solver.Solver, ctx=ctx, world=1)
+    images, labels = synthetic.make_batch(2, 64, 64, 3, seed=1400)
+    feats = dict(images=images, **feed_kw(images, labels))
+    spec = models.model_fn(feats, labels, ModeKeys.TRAIN, params)
+    model = spec.model
+    assert spec.train_op is not None and spec.loss is not None
+    model.feed(images, labels, **feed_kw(images, labels))
+    losses = []
+    for _ in range(4):
+        spec.train_op.run(with_metrics=True)
+        losses.append(spec.train_op.fetch_loss())
+    ctx.check_device()
+    assert params["solver_instance"].global_step == 4
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0], losses
+    md = model.collect_metrics()
+    assert set(md) == {"Liver/Dice", "Tumor/Dice"} and all(0.0 <= v <= 1.0 for v in md.values())
+    # forward-only in EVAL mode through the same object (core/models.py:262-281)
+    model.mode = ModeKeys.EVAL
+    prob = model.run_forward()
+    assert prob.shape == (2, 64, 64, 3) and np.allclose(prob.sum(-1), 1.0, atol=1e-5)
+    for cls in ("Liver", "Tumor"):
+        m = model.predictions[cls + "Pred"]
+        assert m.dtype == np.uint8 and m.shape == (2, 64, 64, 1)
+        assert np.array_equal(m[..., 0], (prob[..., ("Liver", "Tumor").index(cls) + 1] > 0.5).astype(np.uint8))
+    eng = model.engine
+    first = losses[0]
+    model.engine = None
+    eng.close()
+    return first, args
+
+
+def test_unet_through_model_fn_matches_engine(ctx):
+    from boxsegliver_b200.engine import EngineConfig, UNetEngine
+    first, args = _drive(ctx, "UNet", lambda im, lb: {})
+    cfg = EngineConfig(batch=2, height=64, width=64, channel=3, classes=("Background", "Liver", "Tumor"),
+                       weight_decay_rate=1e-5, loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4))
+    eng = UNetEngine(ctx, cfg)
+    eng.init_weights(seed=3)
+    images, labels = synthetic.make_batch(2, 64, 64, 3, seed=1400)
+    eng.set_inputs(images, labels)
+    eng.train_step(1e-3)
+    direct = sum(eng.read_loss())
+    eng.close()
+    assert first == pytest.approx(direct, rel=1e-6)
+
+
+def test_unetinter_through_model_fn(ctx):
+    def feed(images, labels):
+        return dict(sp_guide=synthetic.make_guides(images, labels, 200, 2, seed=1)[1])
+    _drive(ctx, "UNetInter", feed, normalizer="instance_norm", use_spatial=True, guide_channel=2,
+           loss_type="xentropy+dice", mid_cat=False)
+
+
+def test_gunet_through_model_fn(ctx):
+    def feed(images, labels):
+        c, g = synthetic.make_guides(images, labels, 200, 1, seed=1)
+        return dict(context=c, sp_guide=g)
+    _drive(ctx, "GUNet", feed, normalizer="instance_norm", use_spatial=True, use_context=True, guide_channel=1,
+           side_dropout=0.5)
+
+
+def test_unsupported_flags_raise(ctx):
+    args = _args("UNetInter", normalizer="instance_norm", mid_cat=True)
+    params = models.get_model_params(args)
+    params.update(args=args, solver=solver.Solver, ctx=ctx, world=1)
+    with pytest.raises(NotImplementedError, match="mid_cat"):
+        models.model_fn(dict(images=None), None, ModeKeys.TRAIN, params)

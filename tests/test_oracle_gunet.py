@@ -137,6 +137,36 @@ def test_oracle_matches_torch_autograd(kw):
         assert np.allclose(g, t_grads[k], rtol=1e-7, atol=1e-10), k
 
 
+def test_unetinter_oracle_matches_torch_autograd():
+    """UNetInter (/root/reference/NetworksV2/UNetInter.py:73-146): guide concatenated to the images, every conv
+    normalised with centre + scale, variables under "UNetInter/"."""
+    cfg = G.unetinter_cfg(channel=3, guide_channel=2, height=16, width=16, init_channels=4, num_down_samples=2,
+                          loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4), weight_decay_rate=0.0,
+                          loss_type="xentropy+dice")
+    rng = np.random.default_rng(8)
+    n = 2
+    images = rng.uniform(0, 1, (n, 16, 16, 3))
+    guide = rng.uniform(0, 1, (n, 16, 16, 2))
+    labels = rng.integers(0, 3, (n, 16, 16)).astype(np.int32)
+    inputs = G.unetinter_inputs(images, guide)
+    assert inputs["images"].shape == (n, 16, 16, 5) and np.array_equal(inputs["images"][..., 3:], guide)
+    params = {k: v.astype(np.float64) + (0.1 * rng.standard_normal(v.shape) if k.endswith(("beta", "gamma", "biases")) else 0)
+              for k, v in G.init_params(cfg, seed=1, dtype=np.float64).items()}
+    assert params["UNetInter/Encode/down_conv1/mod_conv1/Conv/weights"].shape == (3, 3, 5, 4)
+    assert "UNetInter/Encode/down_conv3/mod_conv2/Conv/InstanceNorm/gamma" in params
+    assert "UNetInter/Decode/up2/biases" in params and "UNetInter/AdjustChannels/biases" in params
+    assert not any("context" in k or "spatial" in k for k in params)
+    tape = G.forward(params, inputs, cfg, True)
+    loss, dl = G.loss_and_dlogits(tape, labels, cfg)
+    grads = G.backward(tape, dl, cfg)
+    t_logits, t_loss, t_grads = _torch_gunet(params, inputs, labels, cfg, None)
+    assert np.allclose(tape.logits, t_logits, rtol=1e-9, atol=1e-10)
+    assert abs(loss - t_loss) < 1e-10
+    assert set(grads) == set(params)
+    for k, g in grads.items():
+        assert np.allclose(g, t_grads[k], rtol=1e-7, atol=1e-10), k
+
+
 def test_parameter_inventory_matches_reference_naming():
     cfg = G.GUNetCfg(height=32, width=32)
     p = G.init_params(cfg)
