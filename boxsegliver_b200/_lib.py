@@ -46,6 +46,11 @@ class NormDesc(C.Structure):
     ]
 
 
+class Pipe(C.Structure):
+    """bsl_pipe: image-slice flags between an HBM-bound pass and the tensor-core kernel that reads its output."""
+    _fields_ = [("flags", C.c_void_p), ("counters", C.c_void_p), ("slices", C.c_int), ("epoch", C.c_int)]
+
+
 class Guide(C.Structure):
     _fields_ = [("map", C.c_void_p), ("channels", C.c_int), ("w", C.c_void_p), ("w_ld", C.c_int)]
 

@@ -313,6 +313,17 @@ HaloPlan plan_halo(bsl_ctx* ctx, int w, int h, int n, int ncols) {
   return p;
 }
 
+// Attaches the image-slice flags a tensor-core kernel waits on (bsl_pipe, include/bsl_b200.h) to the kernel arguments.
+int attach_wait(bsl_ctx* ctx, ConvHaloArgs& a, const bsl_pipe* wait, int n) {
+  if (!wait) return BSL_OK;
+  if (!wait->flags || wait->slices < 1 || wait->slices > 64 || n % wait->slices)
+    return bsl_fail(ctx, BSL_EINVAL, "pipe: slices=%d must divide n=%d and be <= 64", wait->slices, n);
+  a.wait_flags = wait->flags;
+  a.wait_epoch = wait->epoch;
+  a.wait_imgs = n / wait->slices;
+  return BSL_OK;
+}
+
 void halo_common(ConvHaloArgs& a, const HaloPlan& p, int w, int h, int n) {
   a.ntile_w = w / 8;
   a.ntile_h = h / 16;
@@ -320,6 +331,8 @@ void halo_common(ConvHaloArgs& a, const HaloPlan& p, int w, int h, int n) {
   a.n_sub_total = p.n_sub_total;
   a.n_units = p.n_units;
   a.n_ntiles = p.n_ntiles;
+  static const int narrow = getenv("BSL_NARROW_STORE") ? atoi(getenv("BSL_NARROW_STORE")) : 0;
+  a.narrow_store = narrow;
   a.kd = 1;        // 2-D: every image is its own one-slice "volume" (tensor map dims (c, w, h, n, 1))
   a.depth = n;
 }
@@ -464,7 +477,7 @@ int bsl_debug_set(bsl_ctx* ctx, int key, int value) {
 // fprop on the halo-tile kernel; `sums` (fp64 [2][cout], nullable) receives the per-channel sum and
 // sum of squares of the bf16 outputs, reduced deterministically from per-CTA partials.
 static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
-                             double* sums, cudaStream_t stream) {
+                             double* sums, cudaStream_t stream, const bsl_pipe* wait = nullptr) {
   const int halo = d->kh == 3 ? 1 : 0;
   HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, d->cout);
   int res_stages = 0, res_smem = 0;
@@ -488,6 +501,7 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
   a.n_total = d->cout;
   a.a_stages = res_stages;
   a.status = ctx->d_status;
+  if ((rc = attach_wait(ctx, a, wait, d->n))) return rc;
   if (!sums)
     return res ? launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
                : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
@@ -517,6 +531,21 @@ int bsl_conv2d_fprop_stats(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x
   if (halo_eligible(d->w, d->h)) return conv2d_fprop_halo(ctx, d, x, w, y, sums, as_stream(stream));
   if ((rc = bsl_conv2d_fprop(ctx, d, x, w, y, stream))) return rc;
   return bsl_stats_bf16(ctx, y, (long long)d->n * d->h * d->w, 1, d->cout, d->y_ld, sums, as_stream(stream));
+}
+
+int bsl_conv2d_fprop_pipe(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
+                          double* sums, const bsl_pipe* wait, void* stream) {
+  int rc = check_conv(ctx, d);
+  if (rc) return rc;
+  if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "conv2d_fprop_pipe: null buffer");
+  if (!halo_eligible(d->w, d->h))
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv2d_fprop_pipe: %dx%d is not on the halo-tile kernel", d->h, d->w);
+  return conv2d_fprop_halo(ctx, d, x, w, y, sums, as_stream(stream), wait);
+}
+
+int bsl_conv2d_pipe_ok(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
+  (void)ctx;
+  return d && halo_eligible(d->w, d->h) ? 1 : 0;
 }
 
 int bsl_conv2d_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
@@ -549,9 +578,16 @@ int bsl_conv2d_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, cons
 
 int bsl_conv2d_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, const void* w, void* dx,
                      void* stream) {
+  return bsl_conv2d_dgrad_pipe(ctx, d, dy, w, dx, nullptr, stream);
+}
+
+int bsl_conv2d_dgrad_pipe(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, const void* w, void* dx,
+                          const bsl_pipe* wait, void* stream) {
   int rc = check_conv(ctx, d);
   if (rc) return rc;
   if (!dy || !w || !dx) return bsl_fail(ctx, BSL_EINVAL, "conv2d_dgrad: null buffer");
+  if (wait && !halo_eligible(d->w, d->h))
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv2d_dgrad_pipe: %dx%d is not on the halo-tile kernel", d->h, d->w);
   if (halo_eligible(d->w, d->h)) {
     const int halo = d->kh == 3 ? 1 : 0;
     HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, d->cin);
@@ -577,6 +613,7 @@ int bsl_conv2d_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, con
     a.n_total = d->cin;
     a.a_stages = res_stages;
     a.status = ctx->d_status;
+    if ((rc = attach_wait(ctx, a, wait, d->n))) return rc;
     return res ? launch_halo_res<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream))
                : launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
   }
@@ -712,9 +749,16 @@ static int check_convT(bsl_ctx* ctx, const bsl_convT2d_desc* d) {
 
 int bsl_convT2d_fwd(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, const void* w,
                     const float* bias, void* y, void* stream) {
+  return bsl_convT2d_fwd_pipe(ctx, d, x, w, bias, y, nullptr, stream);
+}
+
+int bsl_convT2d_fwd_pipe(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, const void* w,
+                         const float* bias, void* y, const bsl_pipe* wait, void* stream) {
   int rc = check_convT(ctx, d);
   if (rc) return rc;
   if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "convT2d_fwd: null buffer");
+  if (wait && !halo_eligible(d->w, d->h))
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "convT2d_fwd_pipe: %dx%d is not on the halo-tile kernel", d->h, d->w);
   if (halo_eligible(d->w, d->h)) {
     HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, 4 * d->cout);
     if (pl.bn == 256 && d->cin <= 256) {
@@ -750,6 +794,7 @@ int bsl_convT2d_fwd(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, cons
     a.n_total = 4 * d->cout;
     a.a_stages = res_stages;
     a.status = ctx->d_status;
+    if ((rc = attach_wait(ctx, a, wait, d->n))) return rc;
     return res ? launch_halo_res<false, false, true>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream))
                : launch_halo<false, false, true>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
   }

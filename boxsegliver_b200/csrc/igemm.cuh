@@ -242,10 +242,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
               packed[j] = *reinterpret_cast<uint32_t*>(&h);
             }
-            uint4* dst = reinterpret_cast<uint4*>(o + c);
+            if ((reinterpret_cast<uintptr_t>(o + c) & 31) == 0) {   // whole 32-byte sectors per lane
+              st_global_v8(o + c, packed[0], packed[1], packed[2], packed[3], packed[4], packed[5], packed[6], packed[7]);
+              st_global_v8(o + c + 16, packed[8], packed[9], packed[10], packed[11], packed[12], packed[13], packed[14],
+                           packed[15]);
+            } else {
+              uint4* dst = reinterpret_cast<uint4*>(o + c);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+              for (int j = 0; j < 4; ++j)
+                dst[j] = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+            }
           }
         }
       } else {
@@ -259,11 +265,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tmem_ld_32x32(trow + c, v);
           tmem_ld_wait();
           if (valid && n0 + c < p.n_total) {
-            float4* dst = reinterpret_cast<float4*>(o + c);
+            if ((reinterpret_cast<uintptr_t>(o + c) & 31) == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+              for (int j = 0; j < 4; ++j)
+                st_global_v8(o + c + 8 * j, v[8 * j], v[8 * j + 1], v[8 * j + 2], v[8 * j + 3], v[8 * j + 4], v[8 * j + 5],
+                             v[8 * j + 6], v[8 * j + 7]);
+            } else {
+              float4* dst = reinterpret_cast<float4*>(o + c);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
           }
         }
       }

@@ -363,6 +363,11 @@ struct ConvHaloArgs {
   int a_stages;                  // B_RES kernels: activation stages that fit beside the resident filter
   int kd;                        // filter depth (1, or 3 for the (3,3,3) layers of UNet3D): the reduction runs over
   int depth;                     //   (kd, 64-channel block, tap); an "image" is slice z = img % depth of volume img / depth
+  // ---- optional image-slice flags (2-D only): the A producer loads a tile of image i only after
+  //      wait_flags[i / wait_imgs] >= wait_epoch (the pass that writes the A tensor runs beside this kernel)
+  const int* wait_flags;
+  int wait_epoch, wait_imgs;
+  int narrow_store;              // tuning: 128-bit epilogue stores instead of 256-bit (BSL_NARROW_STORE=1)
   DeviceStatus* status;
 };
 
@@ -389,7 +394,7 @@ constexpr int CH_THREADS = (3 + CH_EPI_WARPS) * 32;
 // 32 fp32 accumulator columns of one pixel row -> 32 bf16 (64 B) in global memory.
 template <bool SCATTER>
 __device__ __forceinline__ void ch_store_chunk(const uint32_t (&v)[32], __nv_bfloat16* o, const float* bias,
-                                               int relu, uint32_t (&packed)[16]) {
+                                               int relu, uint32_t (&packed)[16], int narrow = 0) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float a = __uint_as_float(v[2 * i]);
@@ -404,10 +409,17 @@ __device__ __forceinline__ void ch_store_chunk(const uint32_t (&v)[32], __nv_bfl
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     packed[i] = *reinterpret_cast<uint32_t*>(&h);
   }
-  uint4* dst = reinterpret_cast<uint4*>(o);
+  if (!narrow && (reinterpret_cast<uintptr_t>(o) & 31) == 0) {
+    // two 256-bit stores: every lane fills whole 32-byte sectors (lanes of a warp are different pixels, so a
+    // 128-bit store would touch 32 sectors and fill half of each)
+    st_global_v8(o, packed[0], packed[1], packed[2], packed[3], packed[4], packed[5], packed[6], packed[7]);
+    st_global_v8(o + 16, packed[8], packed[9], packed[10], packed[11], packed[12], packed[13], packed[14], packed[15]);
+  } else {
+    uint4* dst = reinterpret_cast<uint4*>(o);
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+    for (int i = 0; i < 4; ++i)
+      dst[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+  }
 }
 
 // Sums s1[i], s2[i] (i = column) over the 32 lanes (= rows) of a warp: 5 halving steps, after which lane l holds
@@ -508,6 +520,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
+      unsigned long long ready = 0;   // image slices already seen complete (wait_flags)
       for (int u = blockIdx.x; u < p.n_units && ok; u += gridDim.x) {
         const int pu = u / p.n_ntiles;
         int nsub = p.n_sub_total - pu * NSUB;
@@ -520,6 +533,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           s /= p.ntile_w;
           ty[j] = s % p.ntile_h;
           img[j] = s / p.ntile_h;
+        }
+        if (p.wait_flags != nullptr) {
+          bool fresh = false;
+#pragma unroll
+          for (int j = 0; j < NSUB; ++j) {
+            if (j < nsub && ok) {
+              const int f = img[j] / p.wait_imgs;
+              if (!((ready >> f) & 1ull)) {
+                ok = pipe_wait(p.wait_flags + f, p.wait_epoch, st, 28);
+                ready |= 1ull << f;
+                fresh = true;
+              }
+            }
+          }
+          if (fresh) fence_proxy_async_global();
         }
         for (int cbx = 0; cbx < kblocks && ok; ++cbx) {
           if (!mbar_wait(a_empty + 8 * stage, phase ^ 1, st, 21)) { ok = false; break; }
@@ -692,7 +720,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               } else {
                 o = obase + col;
               }
-              ch_store_chunk<SCATTER>(hc ? v1 : v0, o, bias, p.relu, packed);
+              ch_store_chunk<SCATTER>(hc ? v1 : v0, o, bias, p.relu, packed, p.narrow_store);
             }
           }
         }
@@ -727,7 +755,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               uint32_t v[32], packed[16];
               tmem_ld_32x32(tq + jj * BN + c, v);
               tmem_ld_wait();
-              ch_store_chunk<false>(v, ob[jj] + c, nullptr, 0, packed);
+              ch_store_chunk<false>(v, ob[jj] + c, nullptr, 0, packed, p.narrow_store);
 #pragma unroll
               for (int i = 0; i < 16; ++i) {   // the bf16 values just stored: what the normalisation pass reads back
                 const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[i]));

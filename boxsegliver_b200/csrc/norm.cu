@@ -188,13 +188,14 @@ template <int G>
 __global__ void norm_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, __nv_bfloat16* __restrict__ a,
                                   int a_ld, long long pixels_per_group, int c, int relu,
                                   const float* __restrict__ scale, const float* __restrict__ shift,
-                                  const float* __restrict__ guide, const float* __restrict__ wsp, int wsp_ld) {
+                                  const float* __restrict__ guide, const float* __restrict__ wsp, int wsp_ld,
+                                  int gstride, PipeSignal sig) {
+  // blockIdx.y = group (instance norm: gstride = c) or image slice of the batch (batch norm, gstride = 0)
   const int cg = c / 8;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
-  if (r >= rows) return;
   const int ch0 = g * 8;
-  const int o = blockIdx.y * c + ch0;
+  const int o = blockIdx.y * gstride + ch0;
   float sc[8], sh[8], ws[G ? G : 1][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -241,6 +242,7 @@ __global__ void norm_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld,
     }
     st16(a + (base + p) * a_ld + ch0, pack8(v));
   }
+  if (sig.flags != nullptr) pipe_signal_block(sig, blockIdx.y / sig.imgs_per_slice);
 }
 
 // Same as norm_apply_kernel, and also emits the 2x2/s2 max-pooled tensor from the same read.
@@ -250,11 +252,10 @@ __global__ void norm_apply_pool_kernel(const __nv_bfloat16* __restrict__ y, int 
                                        int a_ld, __nv_bfloat16* __restrict__ pooled, int p_ld, int h, int w, int c,
                                        int per_sample, int relu, const float* __restrict__ scale,
                                        const float* __restrict__ shift, const float* __restrict__ guide,
-                                       const float* __restrict__ wsp, int wsp_ld) {
+                                       const float* __restrict__ wsp, int wsp_ld, PipeSignal sig) {
   const int cg = c / 8, ho = h / 2, wo = w / 2;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
-  if (r >= rows) return;
   const int ch0 = g * 8;
   const int img = blockIdx.y;
   const int o = (per_sample ? img * c : 0) + ch0;
@@ -302,6 +303,7 @@ __global__ void norm_apply_pool_kernel(const __nv_bfloat16* __restrict__ y, int 
     }
     st16(pooled + (out0 + q) * p_ld + ch0, pack8(mx));
   }
+  if (sig.flags != nullptr) pipe_signal_block(sig, img / sig.imgs_per_slice);
 }
 
 __global__ void norm_bwd_finalize_kernel(int groups, int c, double m, const double* __restrict__ sums,
@@ -331,13 +333,13 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y
                                       int relu, const float* __restrict__ mean, const float* __restrict__ rstd,
                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                       const float* __restrict__ c1, const float* __restrict__ c2,
-                                      const float* __restrict__ guide, const float* __restrict__ wsp, int wsp_ld) {
+                                      const float* __restrict__ guide, const float* __restrict__ wsp, int wsp_ld,
+                                      int gstride, PipeSignal sig) {
   const int cg = c / 8;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
-  if (r >= rows) return;
   const int ch0 = g * 8;
-  const int o = blockIdx.y * c + ch0;
+  const int o = blockIdx.y * gstride + ch0;
   // dy = scale*(dz - c1 - xhat*c2), xhat = (v - mean)*rstd  ==  scale*dz + k1*v + k0
   float sc[8], sh[8], k1[8], k0[8], ws[G ? G : 1][8];
 #pragma unroll
@@ -394,6 +396,7 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y
     }
     st16(dy + (base + p) * dy_ld + ch0, pack8(v));
   }
+  if (sig.flags != nullptr) pipe_signal_block(sig, blockIdx.y / sig.imgs_per_slice);
 }
 
 // GUNet density modulation folded into the per-(sample, channel) affine of an instance-norm layer
@@ -575,6 +578,31 @@ int check_norm(bsl_ctx* ctx, const bsl_norm_desc* d) {
   return BSL_OK;
 }
 
+// Launch geometry of an apply pass that publishes image slices: grid.y = `gy` entries, `per` of them per slice, and
+// enough blocks per entry that the blocks of one slice fill the GPU (slices then complete one after the other).
+int plan_signal(bsl_ctx* ctx, const bsl_pipe* sg, int n, int gy, unsigned blocks_x, PipeSignal* out) {
+  *out = PipeSignal{nullptr, nullptr, 0, 0, 1};
+  if (!sg) return BSL_OK;
+  if (!sg->flags || !sg->counters || sg->slices < 1 || sg->slices > 64 || n % sg->slices || gy % sg->slices)
+    return bsl_fail(ctx, BSL_EINVAL, "pipe: slices=%d must divide n=%d and be <= 64", sg->slices, n);
+  out->flags = sg->flags;
+  out->counters = sg->counters;
+  out->imgs_per_slice = gy / sg->slices;
+  out->expected = (int)blocks_x * out->imgs_per_slice;
+  out->epoch = sg->epoch;
+  return BSL_OK;
+}
+
+EwPlan ew_plan_sliced(bsl_ctx* ctx, long long pixels_per_entry, int entries_per_slice, int c, int unroll) {
+  EwPlan p = ew_plan(ctx, pixels_per_entry, 1, c, unroll);
+  long long want = (pixels_per_entry + (long long)p.rows * unroll - 1) / ((long long)p.rows * unroll);
+  long long cap = (8LL * ctx->sm_count + entries_per_slice - 1) / entries_per_slice;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  p.blocks = (unsigned)want;
+  return p;
+}
+
 }  // namespace
 
 int bsl_stats_bf16(bsl_ctx* ctx, const void* x, long long pixels_per_group, int groups, int c, int ld, double* sums,
@@ -627,27 +655,44 @@ static int check_guide(bsl_ctx* ctx, const bsl_norm_desc* d, const bsl_guide* g,
 
 int bsl_norm_apply_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const float* scale, const float* shift,
                        const bsl_guide* guide, void* y, void* stream) {
+  return bsl_norm_apply_mod_pipe(ctx, d, x, scale, shift, guide, y, nullptr, stream);
+}
+
+int bsl_norm_apply_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const float* scale,
+                            const float* shift, const bsl_guide* guide, void* y, const bsl_pipe* signal,
+                            void* stream) {
   int rc = check_norm(ctx, d);
   if (rc) return rc;
   if (!x || !scale || !shift || !y) return bsl_fail(ctx, BSL_EINVAL, "norm_apply: null buffer");
   int G;
   if ((rc = check_guide(ctx, d, guide, &G))) return rc;
-  const int groups = d->mode ? d->n : 1;
-  const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
-  const EwPlan pl = ew_plan(ctx, ppg, groups, d->c, EW_UNROLL);
+  int groups = d->mode ? d->n : 1;
+  long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
+  EwPlan pl = ew_plan(ctx, ppg, groups, d->c, EW_UNROLL);
+  if (signal) {
+    if (signal->slices < 1 || d->n % signal->slices) return bsl_fail(ctx, BSL_EINVAL, "pipe: bad slice count");
+    if (!d->mode) {            // batch norm: one grid row per image slice, all rows use the batch statistics
+      groups = signal->slices;
+      ppg = (long long)(d->n / signal->slices) * d->hw;
+    }
+    pl = ew_plan_sliced(ctx, ppg, groups / signal->slices, d->c, EW_UNROLL);
+  }
+  PipeSignal sg;
+  if ((rc = plan_signal(ctx, signal, d->n, groups, pl.blocks, &sg))) return rc;
+  const int gstride = d->mode ? d->c : 0;
   const dim3 grid(pl.blocks, groups);
   auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
   auto yb = reinterpret_cast<__nv_bfloat16*>(y);
   cudaStream_t s = as_stream(stream);
   if (G == 0)
     norm_apply_kernel<0><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
-                                                     nullptr, nullptr, 0);
+                                                     nullptr, nullptr, 0, gstride, sg);
   else if (G == 1)
     norm_apply_kernel<1><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
-                                                     guide->map, guide->w, guide->w_ld);
+                                                     guide->map, guide->w, guide->w_ld, gstride, sg);
   else
     norm_apply_kernel<2><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
-                                                     guide->map, guide->w, guide->w_ld);
+                                                     guide->map, guide->w, guide->w_ld, gstride, sg);
   BSL_LAUNCH_CHECK(ctx, "norm_apply_kernel");
   return BSL_OK;
 }
@@ -660,6 +705,12 @@ int bsl_norm_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const fl
 int bsl_norm_apply_pool_mod(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, const void* x, const float* scale,
                             const float* shift, const bsl_guide* guide, void* y, void* pooled, int pooled_ld,
                             void* stream) {
+  return bsl_norm_apply_pool_mod_pipe(ctx, d, h, w, x, scale, shift, guide, y, pooled, pooled_ld, nullptr, stream);
+}
+
+int bsl_norm_apply_pool_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, const void* x,
+                                 const float* scale, const float* shift, const bsl_guide* guide, void* y,
+                                 void* pooled, int pooled_ld, const bsl_pipe* signal, void* stream) {
   int rc = check_norm(ctx, d);
   if (rc) return rc;
   if (!x || !scale || !shift || !y || !pooled) return bsl_fail(ctx, BSL_EINVAL, "norm_apply_pool: null buffer");
@@ -667,7 +718,13 @@ int bsl_norm_apply_pool_mod(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, 
     return bsl_fail(ctx, BSL_EINVAL, "norm_apply_pool: h=%d w=%d must be even and match hw=%d", h, w, d->hw);
   int G;
   if ((rc = check_guide(ctx, d, guide, &G))) return rc;
-  const EwPlan pl = ew_plan(ctx, (long long)(h / 2) * (w / 2), d->n, d->c, 1);
+  EwPlan pl = ew_plan(ctx, (long long)(h / 2) * (w / 2), d->n, d->c, 1);
+  if (signal) {
+    if (signal->slices < 1 || d->n % signal->slices) return bsl_fail(ctx, BSL_EINVAL, "pipe: bad slice count");
+    pl = ew_plan_sliced(ctx, (long long)(h / 2) * (w / 2), d->n / signal->slices, d->c, 1);
+  }
+  PipeSignal sg;
+  if ((rc = plan_signal(ctx, signal, d->n, d->n, pl.blocks, &sg))) return rc;
   const dim3 grid(pl.blocks, d->n);
   auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
   auto yb = reinterpret_cast<__nv_bfloat16*>(y);
@@ -675,13 +732,13 @@ int bsl_norm_apply_pool_mod(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, 
   cudaStream_t s = as_stream(stream);
   if (G == 0)
     norm_apply_pool_kernel<0><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, pb, pooled_ld, h, w, d->c, d->mode,
-                                                          d->relu, scale, shift, nullptr, nullptr, 0);
+                                                          d->relu, scale, shift, nullptr, nullptr, 0, sg);
   else if (G == 1)
     norm_apply_pool_kernel<1><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, pb, pooled_ld, h, w, d->c, d->mode,
-                                                          d->relu, scale, shift, guide->map, guide->w, guide->w_ld);
+                                                          d->relu, scale, shift, guide->map, guide->w, guide->w_ld, sg);
   else
     norm_apply_pool_kernel<2><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, pb, pooled_ld, h, w, d->c, d->mode,
-                                                          d->relu, scale, shift, guide->map, guide->w, guide->w_ld);
+                                                          d->relu, scale, shift, guide->map, guide->w, guide->w_ld, sg);
   BSL_LAUNCH_CHECK(ctx, "norm_apply_pool_kernel");
   return BSL_OK;
 }
@@ -769,15 +826,34 @@ int bsl_norm_bwd_apply_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, 
                            const float* mean, const float* rstd, const float* scale, const float* shift,
                            const float* c1, const float* c2, const bsl_guide* guide, void* dx, int dx_ld,
                            void* stream) {
+  return bsl_norm_bwd_apply_mod_pipe(ctx, d, x, dy, dy_ld, mean, rstd, scale, shift, c1, c2, guide, dx, dx_ld, nullptr,
+                                     stream);
+}
+
+int bsl_norm_bwd_apply_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
+                                const float* mean, const float* rstd, const float* scale, const float* shift,
+                                const float* c1, const float* c2, const bsl_guide* guide, void* dx, int dx_ld,
+                                const bsl_pipe* signal, void* stream) {
   int rc = check_norm(ctx, d);
   if (rc) return rc;
   if (!x || !dy || !mean || !rstd || !scale || !shift || !c1 || !c2 || !dx)
     return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_apply: null buffer");
   int G;
   if ((rc = check_guide(ctx, d, guide, &G))) return rc;
-  const int groups = d->mode ? d->n : 1;
-  const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
-  const EwPlan pl = ew_plan(ctx, ppg, groups, d->c, 4);
+  int groups = d->mode ? d->n : 1;
+  long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
+  EwPlan pl = ew_plan(ctx, ppg, groups, d->c, 4);
+  if (signal) {
+    if (signal->slices < 1 || d->n % signal->slices) return bsl_fail(ctx, BSL_EINVAL, "pipe: bad slice count");
+    if (!d->mode) {
+      groups = signal->slices;
+      ppg = (long long)(d->n / signal->slices) * d->hw;
+    }
+    pl = ew_plan_sliced(ctx, ppg, groups / signal->slices, d->c, 4);
+  }
+  PipeSignal sg;
+  if ((rc = plan_signal(ctx, signal, d->n, groups, pl.blocks, &sg))) return rc;
+  const int gstride = d->mode ? d->c : 0;
   const dim3 grid(pl.blocks, groups);
   auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
   auto db = reinterpret_cast<const __nv_bfloat16*>(dy);
@@ -785,13 +861,15 @@ int bsl_norm_bwd_apply_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, 
   cudaStream_t s = as_stream(stream);
   if (G == 0)
     norm_bwd_apply_kernel<0><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
-                                                         rstd, scale, shift, c1, c2, nullptr, nullptr, 0);
+                                                         rstd, scale, shift, c1, c2, nullptr, nullptr, 0, gstride, sg);
   else if (G == 1)
     norm_bwd_apply_kernel<1><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
-                                                         rstd, scale, shift, c1, c2, guide->map, guide->w, guide->w_ld);
+                                                         rstd, scale, shift, c1, c2, guide->map, guide->w, guide->w_ld,
+                                                         gstride, sg);
   else
     norm_bwd_apply_kernel<2><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
-                                                         rstd, scale, shift, c1, c2, guide->map, guide->w, guide->w_ld);
+                                                         rstd, scale, shift, c1, c2, guide->map, guide->w, guide->w_ld,
+                                                         gstride, sg);
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_apply_kernel");
   return BSL_OK;
 }

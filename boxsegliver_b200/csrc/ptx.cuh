@@ -98,6 +98,72 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, DeviceS
   }
 }
 
+// ----------------------------------------------------------------------------------------- image-slice flags
+// Producer / consumer flags between two kernels that run side by side on different streams: an
+// HBM-bound pass publishes "images [s * k, (s + 1) * k) are written" by storing the step's epoch into flags[s];
+// the TMA producer thread of a tensor-core kernel waits for the slice of the tile it is about to load.
+struct PipeSignal {
+  int* flags;       // [slices] last epoch completed
+  int* counters;    // [slices] arrivals of the current epoch; the last arriver resets it to 0
+  int expected;     // arrivals (thread blocks) per slice
+  int epoch;
+  int imgs_per_slice;
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// generic-proxy writes of other SMs (made visible by the acquire above) -> this thread's TMA (async proxy) reads
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// Called by every thread of a block after its last global store of the slice.
+__device__ __forceinline__ void pipe_signal_block(const PipeSignal& sg, int slice) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(&sg.counters[slice], 1);
+    if (prev == sg.expected - 1) {
+      sg.counters[slice] = 0;
+      __threadfence();
+      st_release_gpu(&sg.flags[slice], sg.epoch);
+    }
+  }
+}
+
+// Bounded wait for flags[slice] >= epoch (epochs only grow). Returns false if the pipeline is dead.
+__device__ __forceinline__ bool pipe_wait(const int* flag, int epoch, DeviceStatus* st, int site) {
+  if (ld_acquire_gpu(flag) - epoch >= 0) return true;
+  uint64_t t0 = globaltimer_ns();
+  uint32_t spins = 0;
+  while (true) {
+    if (ld_acquire_gpu(flag) - epoch >= 0) return true;
+    __nanosleep(spins < 8 ? 500 : 2000);   // one poller per CTA; keep the flag's L2 line quiet for the writer
+    if ((++spins & 0x3f) == 0) {
+      if (*reinterpret_cast<volatile int*>(&st->error) != 0) return false;
+      if (globaltimer_ns() - t0 > BSL_WAIT_TIMEOUT_NS) {
+        if (atomicCAS(&st->error, 0, 1) == 0) {
+          st->block = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+          st->site = site;
+        }
+        return false;
+      }
+    }
+  }
+}
+
+// 256-bit global store (sm_100: STG.E.256), 32-byte aligned address.
+__device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e,
+                                             uint32_t f, uint32_t g, uint32_t h) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+               "r"(f), "r"(g), "r"(h)
+               : "memory");
+}
+
 // ----------------------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -88,6 +88,7 @@ class Context:
         self.device = device
         self.tag = ""            # label attached to profiled calls (the engine sets it per layer)
         self._prof = None
+        self._timeline = None
         s = C.c_void_p()
         self.call("bsl_stream_create", C.byref(s))
         self.stream = s
@@ -101,13 +102,39 @@ class Context:
         if prof:
             e0, e1 = self._prof_event(), self._prof_event()
             self.lib.bsl_event_record(self.h, e0, self.stream)
+        tl = self._timeline is not None and not name.startswith(self._NO_PROF)
+        if tl:   # every enqueue-only entry point takes its stream as the last argument
+            st = args[-1] if args and isinstance(args[-1], C.c_void_p) and args[-1].value else self.stream
+            e0, e1 = self._prof_event(), self._prof_event()
+            self.lib.bsl_event_record(self.h, e0, st)
         rc = getattr(self.lib, name)(self.h, *args)
         if rc != 0:
             raise BslError(rc, (self.lib.bsl_last_error(self.h) or b"").decode())
         if prof:
             self.lib.bsl_event_record(self.h, e1, self.stream)
             self._prof.append((name, self.tag, e0, e1))
+        if tl:
+            self.lib.bsl_event_record(self.h, e1, st)
+            self._timeline.append((name, self.tag, st.value, e0, e1))
         return rc
+
+    # -- multi-stream timeline (tools/timeline.py): events on the stream each call is enqueued on, no serialisation
+    def timeline_begin(self):
+        self._prof_pool = getattr(self, "_prof_pool", [])
+        self._prof_next = 0
+        self._timeline = []
+        self._t0 = self.new_event()
+        self.record(self._t0, self.stream)
+
+    def timeline_end(self):
+        """[(function, tag, stream, start_ms, end_ms)] relative to timeline_begin."""
+        rec, self._timeline = self._timeline, None
+        self.sync()
+        out = []
+        for n, t, st, a, b in rec:
+            self.call("bsl_event_sync", b)
+            out.append((n, t, st, self.elapsed_ms(self._t0, a), self.elapsed_ms(self._t0, b)))
+        return out
 
     # -- per-call device timing (tools/step_breakdown.py): brackets every enqueue on the compute stream
     def _prof_event(self):

@@ -139,11 +139,25 @@ class UNetEngine:
         self._grad_stream = self.stream
         self._overlap_wgrad = cfg.training and os.environ.get("BSL_WGRAD_OVERLAP", "1") != "0"
         self._fork_pre = os.environ.get("BSL_WGRAD_FORK", "pre") == "pre"
+        self._ev_ring, self._ev_ring_i = [ctx.new_event() for _ in range(160)], 0
         if cfg.training:
             self.wg_stream = ctx.new_stream()
             self._dy_events = [ctx.new_event(), ctx.new_event()]
             self._dy_busy = [None, None]
-            self._ev_ring, self._ev_ring_i = [ctx.new_event() for _ in range(96)], 0
+        # Image-slice pipelining (bsl_pipe, include/bsl_b200.h): the HBM-bound normalisation apply of layer L runs on
+        # `aux_stream` beside the tensor-core kernel that consumes its output (fprop of layer L + 1 / dgrad of layer L),
+        # which loads the tiles of an image only after the apply pass has published that image's slice.
+        # Measured on B200 (profiles/r01_pipe_experiment.md): beside a tcgen05 kernel the apply passes run 2-4x slower
+        # (the UMMA operand fetch saturates the SM's L1 / shared-memory data path that their loads share), so the
+        # step gets SLOWER (23.8 -> 25.1 ms at cfg2); the schedule stays available for experiments, off by default.
+        self._pipe_on = os.environ.get("BSL_PIPE", "0") != "0"
+        self.aux_stream = ctx.new_stream()
+        self._pipe_rows = 2 * len(self.layers)
+        self.pipe_buf = self._alloc(2 * self._pipe_rows * 64 * 4).zero()
+        self._pipe_epoch = 0
+        cap = int(os.environ.get("BSL_PIPE_SLICES", "8")) if cfg.normalizer == "batch_norm" else 64
+        self._pipe_slices = max(d for d in range(1, min(cfg.batch, cap) + 1) if cfg.batch % d == 0)
+        self._pending = None
 
     # ------------------------------------------------------------------ per-kernel timing (bench roofline)
     def enable_conv_timing(self, on: bool = True):
@@ -556,10 +570,34 @@ class UNetEngine:
             self.labels.upload(np.ascontiguousarray(labels, np.int32), stream)
 
     # ------------------------------------------------------------------ forward
+    # ------------------------------------------------------------------ image-slice pipelining
+    def _pipe(self, row: int) -> _lib.Pipe:
+        return _lib.Pipe(self.pipe_buf.ptr + row * 256, self.pipe_buf.ptr + (self._pipe_rows + row) * 256,
+                         self._pipe_slices, self._pipe_epoch)
+
+    def _pipe_active(self) -> bool:
+        return self._pipe_on and self.ctx._prof is None and not getattr(self, "_timing", False)
+
+    @staticmethod
+    def _pipe_shape_ok(L: ConvL) -> bool:
+        """The layer's tensor-core kernel is the halo-tile one (the only kernel that can wait on slices)."""
+        return L.kind in ("conv", "convT") and L.h % 16 == 0 and L.w % 8 == 0
+
+    def _take_pending(self, s):
+        """(pipe to wait on or None, completion callback): the previous layer's apply pass still running on the
+        auxiliary stream. The callback orders the main stream after that pass once the consumer is enqueued."""
+        pend, self._pending = self._pending, None
+        if pend is None:
+            return None, lambda: None
+        pipe, ev = pend
+        return pipe, lambda: self.ctx.call("bsl_stream_wait_event", s, ev)
+
     def forward(self, is_training: bool):
         ctx, s = self.ctx, self.stream
         call = ctx.call
-        for L in self.layers:
+        self._pipe_epoch += 1
+        piping = self._pipe_active()
+        for idx, L in enumerate(self.layers):
             ctx.tag = L.scope
             if L.kind in ("stem", "conv"):
                 d = self._conv_desc(L)
@@ -578,7 +616,13 @@ class UNetEngine:
                     d1 = _lib.Conv2dDesc(self.cfg.batch, L.h, L.w, 64, L.cout, 1, 1, 64, L.y.ld)
                     self._tc("fprop", self._flops(L), fn, C.byref(d1), self.stem_col.p, wbf, L.y.p, *extra, s)
                 else:
-                    self._tc("fprop", self._flops(L), fn, C.byref(d), L.x.p, wbf, L.y.p, *extra, s)
+                    pw, done = self._take_pending(s)
+                    if pw is not None:
+                        self._tc("fprop", self._flops(L), "bsl_conv2d_fprop_pipe", C.byref(d), L.x.p, wbf, L.y.p,
+                                 q["sums"] if fused else None, C.byref(pw), s)
+                        done()
+                    else:
+                        self._tc("fprop", self._flops(L), fn, C.byref(d), L.x.p, wbf, L.y.p, *extra, s)
                 if not fused and (not bn or is_training):
                     call("bsl_norm_stats", C.byref(nd), L.y.p, q["sums"], s)
                 mm = C.c_void_p(self.S.ptr + self.params[f"{L.scope}/{ns}/moving_mean"].offset * F32) if bn else None
@@ -588,15 +632,32 @@ class UNetEngine:
                      q["mean"], q["rstd"], q["scale"], q["shift"], s)
                 guide = self._modulate(L, nd, q)   # GUNet: folds gamma_mod / guide bias into scale, shift
                 gp = C.byref(guide) if guide is not None else None
+                nxt = self.layers[idx + 1] if idx + 1 < len(self.layers) else None
+                sig, st = None, s
+                if piping and nxt is not None and self._pipe_shape_ok(nxt):
+                    # the apply pass goes to the auxiliary stream and publishes image slices; the next layer's
+                    # tensor-core kernel starts right away on the main stream and follows it slice by slice
+                    sig, st = self._pipe(idx), self.aux_stream
+                    ev = self._next_event()
+                    ctx.record(ev, s)
+                    call("bsl_stream_wait_event", st, ev)
+                sp = C.byref(sig) if sig is not None else None
                 if L.pooled is not None:
-                    call("bsl_norm_apply_pool_mod", C.byref(nd), C.c_int(L.h), C.c_int(L.w), L.y.p, q["scale"],
-                         q["shift"], gp, L.a.p, L.pooled.p, C.c_int(L.pooled.ld), s)
+                    call("bsl_norm_apply_pool_mod_pipe", C.byref(nd), C.c_int(L.h), C.c_int(L.w), L.y.p, q["scale"],
+                         q["shift"], gp, L.a.p, L.pooled.p, C.c_int(L.pooled.ld), sp, st)
                 else:
-                    call("bsl_norm_apply_mod", C.byref(nd), L.y.p, q["scale"], q["shift"], gp, L.a.p, s)
+                    call("bsl_norm_apply_mod_pipe", C.byref(nd), L.y.p, q["scale"], q["shift"], gp, L.a.p, sp, st)
+                if sig is not None:
+                    ev = self._next_event()
+                    ctx.record(ev, st)
+                    self._pending = (sig, ev)
             elif L.kind == "convT":
                 d = self._convT_desc(L)
-                self._tc("convT_fwd", self._flops(L), "bsl_convT2d_fwd", C.byref(d), L.x.p,
-                         self._pp(self.Wbf, f"{L.scope}/weights", BF16), self._pp(self.W, f"{L.scope}/biases"), L.a.p, s)
+                pw, done = self._take_pending(s)
+                self._tc("convT_fwd", self._flops(L), "bsl_convT2d_fwd_pipe", C.byref(d), L.x.p,
+                         self._pp(self.Wbf, f"{L.scope}/weights", BF16), self._pp(self.W, f"{L.scope}/biases"), L.a.p,
+                         C.byref(pw) if pw is not None else None, s)
+                done()
             else:
                 d = self._conv_desc(L)
                 call("bsl_conv2d_head_fprop", C.byref(d), L.x.p, self._pp(self.W, f"{L.scope}/weights"),
@@ -606,16 +667,24 @@ class UNetEngine:
         """Hook between norm_finalize and norm_apply; returns the bsl_guide of the layer (or None)."""
         return None
 
-    def _norm_backward(self, L: ConvL, nd, q, cur, oth):
-        """Gradient through ReLU + normalisation of layer L: `cur` (w.r.t. the activation) -> `oth` (w.r.t. the conv
-        output); leaves the gradients of the normaliser's own parameters in G."""
+    def _norm_backward_reduce(self, L: ConvL, nd, q, cur):
+        """First half of the gradient through ReLU + normalisation of layer L: the per-channel sums over `cur` (the
+        gradient w.r.t. the activation) and the gradients of the normaliser's own parameters (into G)."""
         call, s, ns = self.ctx.call, self.stream, self.norm_scope
         call("bsl_norm_bwd_reduce", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"],
              q["scale"], q["shift"], q["sums"], s)
         call("bsl_norm_bwd_finalize", C.byref(nd), q["sums"], q["c1"], q["c2"],
              self._pp(self.G, f"{L.scope}/{ns}/gamma"), self._pp(self.G, f"{L.scope}/{ns}/beta"), s)
-        call("bsl_norm_bwd_apply", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"], q["scale"],
-             q["shift"], q["c1"], q["c2"], oth.p, C.c_int(L.cout), s)
+
+    def _norm_backward_apply(self, L: ConvL, nd, q, cur, oth, stream, sig=None):
+        """Second half: `cur` -> `oth` (gradient w.r.t. the conv output), optionally publishing image slices."""
+        self.ctx.call("bsl_norm_bwd_apply_mod_pipe", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"],
+                      q["scale"], q["shift"], q["c1"], q["c2"], None, oth.p, C.c_int(L.cout),
+                      C.byref(sig) if sig is not None else None, stream)
+
+    def _norm_backward(self, L: ConvL, nd, q, cur, oth):
+        self._norm_backward_reduce(L, nd, q, cur)
+        self._norm_backward_apply(L, nd, q, cur, oth, self.stream)
 
     def predict_outputs(self, with_counts: bool):
         """softmax, `<Cls>Pred` masks, argmax and (optionally) the integer Dice sums, one pass over the logits."""
@@ -644,6 +713,8 @@ class UNetEngine:
         # overlap); a dY buffer is reused two conv layers later, behind an event.
         cur, alt = self.g1, self.g2
         overlap = self._overlap_wgrad and ctx._prof is None
+        piping = self._pipe_active()
+        self._pipe_epoch += 1
         ws = self.wg_stream if overlap else s
         self._grad_stream = ws
         k = 0
@@ -676,11 +747,30 @@ class UNetEngine:
                          C.c_int(L.a.ld), cur.p, C.c_int(L.cout), dc.p, C.c_int(dc.ld), alt.p, C.c_int(L.cout), s)
                     cur, alt = alt, cur
                 dyb = self.dyb[k]
-                if overlap and self._dy_busy[k] is not None:       # the wgrad that read this buffer two layers ago
-                    call("bsl_stream_wait_event", s, self._dy_busy[k])
                 nd = self._norm_desc(L)
                 q = self._norm_ptrs(L)
-                self._norm_backward(L, nd, q, cur, dyb)
+                # pipelined: the apply half runs on the auxiliary stream beside dgrad(L), which follows it image slice
+                # by image slice and writes into `alt` (its output must not overwrite the gradient apply still reads)
+                pipe_b = overlap and piping and L.kind == "conv" and self._pipe_shape_ok(L)
+                self._norm_backward_reduce(L, nd, q, cur)
+                sig, ev_apply = None, None
+                if pipe_b:
+                    sig, aux = self._pipe(len(self.layers) + idx), self.aux_stream
+                    ev = self._next_event()
+                    ctx.record(ev, s)
+                    call("bsl_stream_wait_event", aux, ev)
+                    if self._dy_busy[k] is not None:
+                        # on the MAIN stream too: dgrad(L) must not occupy the SMs (spinning on slices) while the
+                        # filter-gradient kernel that still reads this dY buffer waits for shared memory
+                        call("bsl_stream_wait_event", aux, self._dy_busy[k])
+                        call("bsl_stream_wait_event", s, self._dy_busy[k])
+                    self._norm_backward_apply(L, nd, q, cur, dyb, aux, sig)
+                    ev_apply = self._next_event()
+                    ctx.record(ev_apply, aux)
+                else:
+                    if overlap and self._dy_busy[k] is not None:   # the wgrad that read this buffer two layers ago
+                        call("bsl_stream_wait_event", s, self._dy_busy[k])
+                    self._norm_backward_apply(L, nd, q, cur, dyb, s)
                 # dyb = dY (gradient w.r.t. the conv output), dense with ld = cout
                 d = self._conv_desc(L)
                 d.y_ld = L.cout
@@ -693,13 +783,20 @@ class UNetEngine:
                     wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
                     dd = self._conv_desc(L)
                     dd.y_ld = L.cout
+                    wp = C.byref(sig) if sig is not None else None
                     if L.role == "dec1":
                         dc = self.dcat[L.level]
                         dd.x_ld = dc.ld
-                        self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad", C.byref(dd), dyb.p, wbf, dc.p, s)
+                        self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad_pipe", C.byref(dd), dyb.p, wbf, dc.p, wp, s)
                     else:
                         dd.x_ld = L.cin
-                        self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad", C.byref(dd), dyb.p, wbf, cur.p, s)
+                        dst = alt if pipe_b else cur
+                        self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad_pipe", C.byref(dd), dyb.p, wbf, dst.p, wp, s)
+                        if pipe_b:
+                            cur, alt = alt, cur
+                if ev_apply is not None:
+                    call("bsl_stream_wait_event", s, ev_apply)
+                    call("bsl_stream_wait_event", ws, ev_apply)
                 if not self._fork_pre:
                     fork()
                 if L.kind == "stem":

@@ -239,9 +239,9 @@ class GUNetEngine(UNetEngine):
         return self._guide_struct(L)
 
     # ------------------------------------------------------------------ backward
-    def _norm_backward(self, L: ConvL, nd, q, cur, oth):
+    def _norm_backward_reduce(self, L: ConvL, nd, q, cur):
         if L.mod_off is None and L.sp_off is None:
-            return super()._norm_backward(L, nd, q, cur, oth)
+            return super()._norm_backward_reduce(L, nd, q, cur)
         call, s, ns = self.ctx.call, self.stream, self.norm_scope
         guide = self._guide_struct(L)
         gp = C.byref(guide) if guide is not None else None
@@ -257,8 +257,12 @@ class GUNetEngine(UNetEngine):
              self._pp(self.W, f"{L.scope}/{ns}/gamma"), self._pp(self.W, f"{L.scope}/{ns}/beta"), q["c1"], q["c2"],
              self._pp(self.G, f"{L.scope}/{ns}/gamma"), self._pp(self.G, f"{L.scope}/{ns}/beta"), dgm, dwg,
              C.c_int(2 * L.cout), dbg, s)
-        call("bsl_norm_bwd_apply_mod", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"], q["scale"],
-             q["shift"], q["c1"], q["c2"], gp, oth.p, C.c_int(L.cout), s)
+
+    def _norm_backward_apply(self, L: ConvL, nd, q, cur, oth, stream, sig=None):
+        guide = self._guide_struct(L)
+        self.ctx.call("bsl_norm_bwd_apply_mod_pipe", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"],
+                      q["scale"], q["shift"], q["c1"], q["c2"], C.byref(guide) if guide is not None else None, oth.p,
+                      C.c_int(L.cout), C.byref(sig) if sig is not None else None, stream)
 
     def loss_backward(self):
         super().loss_backward()

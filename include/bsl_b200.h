@@ -93,8 +93,29 @@ typedef struct {
   int y_ld;        /* channel stride of the output buffer (elements), >= cout */
 } bsl_conv2d_desc;
 
+/* Image-slice flags between two kernels that run side by side on different streams. TF's executor starts an op when
+ * its whole input tensor is ready (core/estimator.py:756-757 runs one graph); here the HBM-bound normalisation pass
+ * that WRITES a tensor and the tensor-core convolution that READS it overlap: the batch is cut into `slices` groups of
+ * n / slices consecutive images, the writer stores `epoch` into flags[s] when slice s is complete, and the reader's
+ * TMA producer loads a tile of image i only once flags[i / (n / slices)] >= epoch. Results are bit-identical to the
+ * un-pipelined calls. `counters` is scratch of the writer ([slices] ints, zero before first use, self-resetting);
+ * epochs must grow from one use of the same flags to the next. slices <= 64 and n % slices == 0. */
+typedef struct {
+  int* flags;
+  int* counters;
+  int slices;
+  int epoch;
+} bsl_pipe;
+
 int bsl_conv2d_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x_bf16,
                      const void* w_hwio_bf16, void* y_bf16, void* stream);
+/* 1 when the shape runs on the halo-tile kernel (h % 16 == 0, w % 8 == 0), the only one that can wait on a pipe. */
+int bsl_conv2d_pipe_ok(bsl_ctx* ctx, const bsl_conv2d_desc* d);
+/* bsl_conv2d_fprop[_stats] (sums nullable) whose input x is being written by a *_pipe normalisation pass. */
+int bsl_conv2d_fprop_pipe(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x_bf16, const void* w_hwio_bf16,
+                          void* y_bf16, double* sums, const bsl_pipe* wait, void* stream);
+int bsl_conv2d_dgrad_pipe(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy_bf16, const void* w_hwio_bf16,
+                          void* dx_bf16, const bsl_pipe* wait, void* stream);
 /* Conv2D fused with the reduction half of FusedBatchNorm (NetworksV2/base.py:154-162): also returns
  * sums[0][c] = sum over (n,h,w) of y, sums[1][c] = sum of y^2 (of the bf16-rounded outputs, fp64), which is
  * exactly what bsl_norm_stats(mode = batch) computes from y in a separate pass. */
@@ -122,6 +143,8 @@ typedef struct {
 
 int bsl_convT2d_fwd(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x_bf16,
                     const void* w_kkoi_bf16, const float* bias_f32, void* y_bf16, void* stream);
+int bsl_convT2d_fwd_pipe(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x_bf16, const void* w_kkoi_bf16,
+                         const float* bias_f32, void* y_bf16, const bsl_pipe* wait, void* stream);
 /* dyr must already carry the ReLU mask (dy * (y > 0)); see bsl_relu_bwd. */
 int bsl_convT2d_bwd_data(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* dyr_bf16,
                          const void* w_kkoi_bf16, void* dx_bf16, void* stream);
@@ -250,6 +273,18 @@ int bsl_norm_apply_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16,
 int bsl_norm_apply_pool_mod(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, const void* x_bf16,
                             const float* scale, const float* shift, const bsl_guide* guide, void* y_bf16,
                             void* pooled_bf16, int pooled_ld, void* stream);
+/* The same passes publishing image slices of their output through `signal` (bsl_pipe above), for a tensor-core
+ * kernel that reads the output while the pass is still running. */
+int bsl_norm_apply_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const float* scale,
+                            const float* shift, const bsl_guide* guide, void* y_bf16, const bsl_pipe* signal,
+                            void* stream);
+int bsl_norm_apply_pool_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, const void* x_bf16,
+                                 const float* scale, const float* shift, const bsl_guide* guide, void* y_bf16,
+                                 void* pooled_bf16, int pooled_ld, const bsl_pipe* signal, void* stream);
+int bsl_norm_bwd_apply_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const void* dy_bf16,
+                                int dy_ld, const float* mean, const float* rstd, const float* scale,
+                                const float* shift, const float* c1, const float* c2, const bsl_guide* guide,
+                                void* dx_bf16, int dx_ld, const bsl_pipe* signal, void* stream);
 /* sums: fp64 [n][2 + guide channels][c] = sum dz, sum dz * xhat, sum dz * guide_g. */
 int bsl_norm_bwd_reduce_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const void* dy_bf16, int dy_ld,
                             const float* mean, const float* rstd, const float* scale, const float* shift,

@@ -214,3 +214,27 @@ def test_host_fed_steps_match_device_resident_steps(ctx):
         l, w = run(mode)
         assert np.allclose(l, l0, rtol=1e-6), (mode, l, l0)
         assert np.array_equal(w, w0), mode
+
+
+def test_image_slice_pipelining_is_bit_identical(ctx):
+    """The optional schedule that runs the normalisation apply passes beside the tensor-core kernels (bsl_pipe,
+    BSL_PIPE=1) changes WHEN tiles are computed, never WHAT: logits, loss and every gradient are bit-identical."""
+    from boxsegliver_b200.engine import EngineConfig, UNetEngine
+    n, hw = 8, 64
+    images, labels = synthetic.make_batch(n, hw, hw, 3, seed=1401)
+    out = []
+    for pipe in (False, True):
+        eng = UNetEngine(ctx, EngineConfig(batch=n, height=hw, width=hw, weight_decay_rate=1e-5,
+                                           loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4)))
+        eng._pipe_on = pipe
+        eng.init_weights(seed=5)
+        eng.set_inputs(images, labels)
+        for _ in range(2):
+            eng.train_step(1e-3)
+        ctx.check_device()
+        out.append((eng.logits.download(np.float32, (n, hw, hw, 3)), eng.read_loss(), eng.get_grads()))
+        eng.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    assert out[0][1] == out[1][1]
+    for k, g in out[0][2].items():
+        assert np.array_equal(g, out[1][2][k]), k
