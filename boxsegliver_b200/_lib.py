@@ -51,6 +51,17 @@ class Pipe(C.Structure):
     _fields_ = [("flags", C.c_void_p), ("counters", C.c_void_p), ("slices", C.c_int), ("epoch", C.c_int)]
 
 
+class InputDesc(C.Structure):
+    _fields_ = [("n", C.c_int), ("channels", C.c_int), ("src_h", C.c_int), ("src_w", C.c_int), ("out_h", C.c_int),
+                ("out_w", C.c_int), ("max_centers", C.c_int), ("noise_scale", C.c_float), ("min_std", C.c_float),
+                ("seed", C.c_ulonglong), ("offset", C.c_ulonglong)]
+
+
+class InputParams(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("bbox", "clip", "lab_scale", "present", "flips", "centers", "stddevs",
+                                          "n_centers")]
+
+
 class Guide(C.Structure):
     _fields_ = [("map", C.c_void_p), ("channels", C.c_int), ("w", C.c_void_p), ("w_ld", C.c_int)]
 

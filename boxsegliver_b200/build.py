@@ -18,7 +18,7 @@ CSRC = PKG_DIR / "csrc"
 OBJ_DIR = PKG_DIR / "_build"
 LIB_PATH = PKG_DIR / "libbsl_b200.so"
 
-SOURCES = ["runtime.cu", "conv.cu", "conv3d.cu", "pointwise.cu", "small_conv.cu", "norm.cu", "guide.cu", "loss.cu", "infer.cu", "optim.cu", "comm.cu"]
+SOURCES = ["runtime.cu", "conv.cu", "conv3d.cu", "pointwise.cu", "small_conv.cu", "norm.cu", "guide.cu", "augment.cu", "loss.cu", "infer.cu", "optim.cu", "comm.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -5,23 +5,10 @@
 // The 1x1 guide convolutions themselves are never materialised: norm.cu evaluates guide[p] . w[:, c] inside the
 // normalisation passes of the layer they modulate.
 #include "internal.h"
+#include "philox.cuh"
 
 namespace {
-
-// Philox4x32-10 (Salmon et al. 2011), the counter-based generator TF's random ops are built on. The stream here is
-// keyed by (seed, offset) from the descriptor; element i uses counter i / 4, lane i % 4.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  constexpr unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const unsigned hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const unsigned hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
+using bsl::philox4x32_10;
 
 __device__ __forceinline__ float dropout_scale(const bsl_dropout_desc& dd, unsigned long long idx) {
   // tf.nn.dropout: binary = floor(keep_prob + uniform[0,1)); y = x / keep_prob * binary

@@ -401,6 +401,41 @@ int bsl_comm_init(bsl_ctx* ctx, const void* id128, int rank, int world);
 int bsl_allreduce_sum_f32(bsl_ctx* ctx, float* buf, size_t n, void* stream);
 int bsl_comm_destroy(bsl_ctx* ctx);
 
+/* ------------------------------------------------------------------ device-side input stage
+ * One pass over the decoded PNG slices of a batch that does what the reference's tf.data map function does per
+ * sample on the host: crop_to_bounding_box -> resize_bilinear(align_corners=True) -> [H,W,C] -> window clip and
+ * normalise -> uniform noise (not in empty slices) -> random left/right and up/down flips of image, label and guide
+ * (DataLoader/Liver/input_pipeline.py:243-284, utils/image_ops.py:209-238,245-320); labels go through
+ * resize_nearest_neighbor(align_corners=True) and trunc(seg / lab_scale); the optional sp_guide is
+ * create_spatial_guide_2d on the crop grid, resized, / 2 + 0.5 (input_pipeline_g.py:380-391, image_ops.py:396-434).
+ * The random DECISIONS (bbox, flips) are inputs, drawn by the caller as the reference's generator does; the noise
+ * stream is Philox4x32-10 keyed by (seed, offset), element ((i*H + y)*W + x)*C + c of the UN-flipped image.
+ * Outputs are the engines' input buffers: images fp32 [n,H,W,C], labels int32 [n,H,W], sp_guide fp32 [n,H,W,1]. */
+typedef struct {
+  int n, channels;   /* samples, adjacent slices per sample (--im_channel) */
+  int src_h, src_w;  /* decoded slice size (512 x 512) */
+  int out_h, out_w;  /* --im_height, --im_width */
+  int max_centers;   /* padded centre count per sample (sp_guide only) */
+  float noise_scale; /* --noise_scale; 0 = no noise */
+  float min_std;     /* lower bound of the guide stddevs (kwargs min_std, default 1) */
+  unsigned long long seed, offset;
+} bsl_input_desc;
+
+typedef struct {          /* device pointers, one row per sample */
+  const int* bbox;        /* [n][4] offset_row, offset_col, height, width (crop_to_bounding_box order) */
+  const float* clip;      /* [n][2] window min, max */
+  const int* lab_scale;   /* [n] */
+  const unsigned char* present; /* [n][channels] 0 for a missing neighbour slice (nullable: all present) */
+  const int* flips;       /* [n] bit 0: left/right, bit 1: up/down (nullable) */
+  const float* centers;   /* [n][max_centers][2] (y, x) on the crop grid */
+  const float* stddevs;   /* [n][max_centers][2] */
+  const int* n_centers;   /* [n]; 0 = constant 0.5 guide */
+} bsl_input_params;
+
+int bsl_input_stage(bsl_ctx* ctx, const bsl_input_desc* d, const bsl_input_params* p, const void* slices_u16,
+                    const void* seg_u8 /*nullable*/, float* images, int* labels /*nullable*/,
+                    float* sp_guide /*nullable*/, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
