@@ -119,6 +119,8 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)  # AttributeError here == header/library mismatch
         if name.endswith("_workspace"):
             fn.restype = C.c_size_t
+        elif name == "bsl_crc32c":
+            fn.restype, fn.argtypes = C.c_uint32, (C.c_uint32, C.c_void_p, C.c_size_t)
         elif name not in ("bsl_last_error", "bsl_version", "bsl_destroy"):
             fn.restype = C.c_int
     lib.bsl_destroy.restype = None

@@ -27,6 +27,37 @@ extern "C" {
 
 const char* bsl_version(void) { return "bsl_b200 0.1 (sm_100a)"; }
 
+// CRC-32C (Castagnoli, reflected polynomial 0x82F63B78), slicing-by-8, host only: the checksum of the TF Saver V2
+// bundle format (boxsegliver_b200/checkpoint.py). `crc` is the running value (0 to start); no context needed.
+unsigned bsl_crc32c(unsigned crc, const void* data, size_t n) {
+  static uint32_t T[8][256];
+  static bool ready = [] {
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c >> 1) ^ (0x82F63B78u & (0u - (c & 1u)));
+      T[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) T[t][i] = (T[t - 1][i] >> 8) ^ T[0][T[t - 1][i] & 0xff];
+    return true;
+  }();
+  (void)ready;
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint32_t c = ~crc;
+  while (n >= 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, p, 4);
+    memcpy(&hi, p + 4, 4);
+    lo ^= c;
+    c = T[7][lo & 0xff] ^ T[6][(lo >> 8) & 0xff] ^ T[5][(lo >> 16) & 0xff] ^ T[4][lo >> 24] ^ T[3][hi & 0xff] ^
+        T[2][(hi >> 8) & 0xff] ^ T[1][(hi >> 16) & 0xff] ^ T[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = (c >> 8) ^ T[0][(c ^ *p++) & 0xff];
+  return ~c;
+}
+
 int bsl_init(int device, bsl_ctx** out) {
   if (!out) return BSL_EINVAL;
   *out = nullptr;

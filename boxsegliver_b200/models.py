@@ -77,3 +77,17 @@ def model_fn(features, labels, mode, params, config=None):
             params["solver_instance"] = solver
         train_op = solver(loss)
     return EstimatorSpec(mode, loss, train_op, model.predictions, model)
+
+
+def init_model(model, args):
+    """core/models.py:161-185: restore `--load_weights` (a checkpoint prefix, or a directory next to model_dir read
+    through its `--load_weights_version` CheckpointState file) into the built model, renaming the model's root scope
+    to `--weights_scope` (or the scope found in the checkpoint). Returns the checkpoint's global_step, or None when
+    --load_weights is not set."""
+    if not getattr(args, "load_weights", None):
+        return None
+    from . import checkpoint
+    weights_dir = Path(getattr(args, "model_dir", ".")).parent / args.load_weights
+    target = weights_dir if weights_dir.is_dir() else Path(args.load_weights)
+    return checkpoint.restore_engine(model.engine, target, weights_scope=getattr(args, "weights_scope", None),
+                                     latest_filename=getattr(args, "load_weights_version", "checkpoint"))

@@ -42,6 +42,9 @@ int bsl_init(int device, bsl_ctx** out);
 void bsl_destroy(bsl_ctx* ctx);
 const char* bsl_last_error(bsl_ctx* ctx);
 const char* bsl_version(void);
+/* Host-only helper: running CRC-32C (Castagnoli) as used by TF's Saver V2 bundles (core/estimator.py:694-703 saves
+ * and restores through tf.train.Saver; boxsegliver_b200/checkpoint.py reads / writes that wire format). */
+unsigned bsl_crc32c(unsigned crc, const void* data, size_t n);
 /* Reads back (synchronously) and clears the device-side watchdog word. 0 = healthy. */
 int bsl_device_status(bsl_ctx* ctx, int* block, int* site);
 
