@@ -576,13 +576,32 @@ int bsl_conv2d_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, cons
   return launch_igemm<MODE_PIX_M, true>(ctx, bn, ta, tb, a, grid, as_stream(stream));
 }
 
+static int conv2d_dgrad_impl(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, const void* w, void* dx,
+                             const bsl_pipe* wait, const void* relu_act, int mask_col0, void* stream);
+
 int bsl_conv2d_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, const void* w, void* dx,
                      void* stream) {
-  return bsl_conv2d_dgrad_pipe(ctx, d, dy, w, dx, nullptr, stream);
+  return conv2d_dgrad_impl(ctx, d, dy, w, dx, nullptr, nullptr, 0, stream);
 }
 
 int bsl_conv2d_dgrad_pipe(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, const void* w, void* dx,
                           const bsl_pipe* wait, void* stream) {
+  return conv2d_dgrad_impl(ctx, d, dy, w, dx, wait, nullptr, 0, stream);
+}
+
+int bsl_conv2d_dgrad_relu(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, const void* w, void* dx,
+                          const void* act, int col0, const bsl_pipe* wait, void* stream) {
+  if (!act || col0 < 0 || col0 % 32 || (d && col0 > d->cin))
+    return bsl_fail(ctx, BSL_EINVAL, "conv2d_dgrad_relu: act required, col0 a multiple of 32 within cin");
+  if (d && !halo_eligible(d->w, d->h))
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv2d_dgrad_relu: %dx%d is not on the halo-tile kernel", d->h, d->w);
+  if (d && (d->x_ld % 16 || (reinterpret_cast<uintptr_t>(act) & 31) || (reinterpret_cast<uintptr_t>(dx) & 31)))
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv2d_dgrad_relu: dx / act need 32-byte aligned pixels (x_ld %% 16 == 0)");
+  return conv2d_dgrad_impl(ctx, d, dy, w, dx, wait, act, col0, stream);
+}
+
+static int conv2d_dgrad_impl(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy, const void* w, void* dx,
+                             const bsl_pipe* wait, const void* relu_act, int mask_col0, void* stream) {
   int rc = check_conv(ctx, d);
   if (rc) return rc;
   if (!dy || !w || !dx) return bsl_fail(ctx, BSL_EINVAL, "conv2d_dgrad: null buffer");
@@ -614,6 +633,8 @@ int bsl_conv2d_dgrad_pipe(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy
     a.a_stages = res_stages;
     a.status = ctx->d_status;
     if ((rc = attach_wait(ctx, a, wait, d->n))) return rc;
+    a.relu_mask = relu_act;
+    a.mask_col0 = mask_col0;
     return res ? launch_halo_res<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream))
                : launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
   }

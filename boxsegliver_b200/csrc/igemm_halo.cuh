@@ -368,6 +368,10 @@ struct ConvHaloArgs {
   const int* wait_flags;
   int wait_epoch, wait_imgs;
   int narrow_store;              // tuning: 128-bit epilogue stores instead of 256-bit (BSL_NARROW_STORE=1)
+  // ---- optional fused ReluGrad (dgrad into a concat buffer): output columns >= mask_col0 are zeroed where the
+  //      activation stored at the same (pixel, column) of `relu_mask` (same strides as `out`) is not positive
+  const void* relu_mask;
+  int mask_col0;
   DeviceStatus* status;
 };
 
@@ -394,7 +398,19 @@ constexpr int CH_THREADS = (3 + CH_EPI_WARPS) * 32;
 // 32 fp32 accumulator columns of one pixel row -> 32 bf16 (64 B) in global memory.
 template <bool SCATTER>
 __device__ __forceinline__ void ch_store_chunk(const uint32_t (&v)[32], __nv_bfloat16* o, const float* bias,
-                                               int relu, uint32_t (&packed)[16], int narrow = 0) {
+                                               int relu, uint32_t (&packed)[16], int narrow = 0,
+                                               const __nv_bfloat16* mask = nullptr) {
+  uint32_t keep[16];
+  if (mask != nullptr) {   // ReluGrad: keep a gradient only where the stored activation is > 0
+    uint32_t w[16];
+    ld_global_nc_v8(mask, w);          // 2 x 256-bit: whole sectors per lane, as for the stores
+    ld_global_nc_v8(mask + 16, w + 8);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const uint32_t lo = w[i] & 0xffffu, hi = w[i] >> 16;
+      keep[i] = ((lo != 0 && lo < 0x8000u) ? 0xffffu : 0u) | ((hi != 0 && hi < 0x8000u) ? 0xffff0000u : 0u);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float a = __uint_as_float(v[2 * i]);
@@ -408,6 +424,7 @@ __device__ __forceinline__ void ch_store_chunk(const uint32_t (&v)[32], __nv_bfl
     }
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     packed[i] = *reinterpret_cast<uint32_t*>(&h);
+    if (mask != nullptr) packed[i] &= keep[i];
   }
   if (!narrow && (reinterpret_cast<uintptr_t>(o) & 31) == 0) {
     // two 256-bit stores: every lane fills whole 32-byte sectors (lanes of a warp are different pixels, so a
@@ -720,7 +737,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               } else {
                 o = obase + col;
               }
-              ch_store_chunk<SCATTER>(hc ? v1 : v0, o, bias, p.relu, packed, p.narrow_store);
+              const __nv_bfloat16* mk = nullptr;
+              if (!SCATTER && p.relu_mask != nullptr && col >= p.mask_col0)
+                mk = reinterpret_cast<const __nv_bfloat16*>(p.relu_mask) + (o - reinterpret_cast<__nv_bfloat16*>(p.out));
+              ch_store_chunk<SCATTER>(hc ? v1 : v0, o, bias, p.relu, packed, p.narrow_store, mk);
             }
           }
         }

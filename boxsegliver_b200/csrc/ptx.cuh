@@ -164,6 +164,13 @@ __device__ __forceinline__ void st_global_v8(void* p, uint32_t a, uint32_t b, ui
                : "memory");
 }
 
+// 256-bit read-only global load, 32-byte aligned address.
+__device__ __forceinline__ void ld_global_nc_v8(const void* p, uint32_t* v) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(p));
+}
+
 // ----------------------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

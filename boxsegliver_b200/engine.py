@@ -151,6 +151,8 @@ class UNetEngine:
         # (the UMMA operand fetch saturates the SM's L1 / shared-memory data path that their loads share), so the
         # step gets SLOWER (23.8 -> 25.1 ms at cfg2); the schedule stays available for experiments, off by default.
         self._pipe_on = os.environ.get("BSL_PIPE", "0") != "0"
+        # measured: the mask loads in the epilogue cost dgrad +0.45 ms, more than the 0.49 ms relu_bwd pass they replace
+        self._fuse_relu_bwd = os.environ.get("BSL_FUSE_RELU_BWD", "0") != "0"
         self.aux_stream = ctx.new_stream()
         self._pipe_rows = 2 * len(self.layers)
         self.pipe_buf = self._alloc(2 * self._pipe_rows * 64 * 4).zero()
@@ -715,6 +717,7 @@ class UNetEngine:
         overlap = self._overlap_wgrad and ctx._prof is None
         piping = self._pipe_active()
         self._pipe_epoch += 1
+        relu_fused = set()      # levels whose transposed-conv ReluGrad was applied by the decoder dgrad's epilogue
         ws = self.wg_stream if overlap else s
         self._grad_stream = ws
         k = 0
@@ -787,7 +790,15 @@ class UNetEngine:
                     if L.role == "dec1":
                         dc = self.dcat[L.level]
                         dd.x_ld = dc.ld
-                        self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad_pipe", C.byref(dd), dyb.p, wbf, dc.p, wp, s)
+                        if self._fuse_relu_bwd and self._pipe_shape_ok(L):
+                            # ReluGrad of the transposed conv (upper channel half of the concat) in the epilogue
+                            up = self.layers[idx - 1]
+                            assert up.kind == "convT" and up.level == L.level
+                            self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad_relu", C.byref(dd), dyb.p, wbf, dc.p,
+                                     self.cat[L.level].p, C.c_int(L.cin - up.cout), wp, s)
+                            relu_fused.add(L.level)
+                        else:
+                            self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad_pipe", C.byref(dd), dyb.p, wbf, dc.p, wp, s)
                     else:
                         dd.x_ld = L.cin
                         dst = alt if pipe_b else cur
@@ -814,9 +825,10 @@ class UNetEngine:
             elif L.kind == "convT":
                 dc = self.dcat[L.level]
                 dup = dc.slice(L.cout, L.cout)
-                # ReluGrad in place on the upper half of dcat
-                call("bsl_relu_bwd", C.c_longlong(L.a.pixels), C.c_int(L.cout), L.a.p, C.c_int(L.a.ld), dup.p,
-                     C.c_int(dup.ld), dup.p, C.c_int(dup.ld), s)
+                # ReluGrad in place on the upper half of dcat (unless dgrad's epilogue already applied it)
+                if L.level not in relu_fused:
+                    call("bsl_relu_bwd", C.c_longlong(L.a.pixels), C.c_int(L.cout), L.a.p, C.c_int(L.a.ld), dup.p,
+                         C.c_int(dup.ld), dup.p, C.c_int(dup.ld), s)
                 d = self._convT_desc(L)
                 d.y_ld = dup.ld
                 d.x_ld = L.cin

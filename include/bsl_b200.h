@@ -119,6 +119,13 @@ int bsl_conv2d_fprop_pipe(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x_
                           void* y_bf16, double* sums, const bsl_pipe* wait, void* stream);
 int bsl_conv2d_dgrad_pipe(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy_bf16, const void* w_hwio_bf16,
                           void* dx_bf16, const bsl_pipe* wait, void* stream);
+/* dgrad fused with the ReluGrad of the producer of part of its input (decoder conv1 reads concat(skip, up) --
+ * NetworksV2/UNet.py:92-94 -- and `up` is the ReLU output of slim.conv2d_transpose): columns >= col0 of dx are
+ * zeroed where act (same shape and channel stride as dx, the concat buffer itself) is not > 0, which is
+ * bsl_relu_bwd applied in place afterwards, without the extra pass. Halo-tile shapes only (bsl_conv2d_pipe_ok);
+ * col0 % 32 == 0; `wait` nullable. */
+int bsl_conv2d_dgrad_relu(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy_bf16, const void* w_hwio_bf16,
+                          void* dx_bf16, const void* act_bf16, int col0, const bsl_pipe* wait, void* stream);
 /* Conv2D fused with the reduction half of FusedBatchNorm (NetworksV2/base.py:154-162): also returns
  * sums[0][c] = sum over (n,h,w) of y, sums[1][c] = sum of y^2 (of the bf16-rounded outputs, fp64), which is
  * exactly what bsl_norm_stats(mode = batch) computes from y in a separate pass. */

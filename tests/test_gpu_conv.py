@@ -192,3 +192,31 @@ def test_rejects_unsupported_shapes(ctx):
     with pytest.raises(BslError):
         ctx.call("bsl_conv2d_fprop", C.byref(d), None, buf.p, buf.p, ctx.stream)
     buf.free()
+
+
+def test_dgrad_with_fused_relu_grad_matches_two_passes(ctx):
+    """bsl_conv2d_dgrad_relu == bsl_conv2d_dgrad followed by bsl_relu_bwd on the upper channel window, bit for bit
+    (decoder conv1 of the U-Net: dx goes to the concat gradient buffer, columns >= col0 belong to the ReLU output of
+    the transposed conv -- /root/reference/NetworksV2/UNet.py:90-94)."""
+    import ctypes as C
+    from boxsegliver_b200 import _lib
+    from boxsegliver_b200.device import f32_to_bf16_bits
+    rng = np.random.default_rng(21)
+    for n, hw, cin, cout, col0 in ((2, 32, 128, 64, 64), (1, 16, 256, 128, 128), (2, 16, 512, 256, 256)):
+        dy = ctx.from_numpy(f32_to_bf16_bits(rng.standard_normal((n, hw, hw, cout)).astype(np.float32)))
+        w = ctx.from_numpy(f32_to_bf16_bits((0.05 * rng.standard_normal((3, 3, cin, cout))).astype(np.float32)))
+        act_h = np.maximum(rng.standard_normal((n, hw, hw, cin)), 0).astype(np.float32)     # ~half zeros, like a ReLU output
+        act = ctx.from_numpy(f32_to_bf16_bits(act_h))
+        a, b = ctx.alloc(n * hw * hw * cin * 2), ctx.alloc(n * hw * hw * cin * 2)
+        d = _lib.Conv2dDesc(n, hw, hw, cin, cout, 3, 3, cin, cout)
+        ctx.call("bsl_conv2d_dgrad", C.byref(d), dy.p, w.p, a.p, ctx.stream)
+        up = C.c_void_p(a.ptr + col0 * 2)
+        ctx.call("bsl_relu_bwd", C.c_longlong(n * hw * hw), C.c_int(cin - col0), C.c_void_p(act.ptr + col0 * 2), C.c_int(cin),
+                 up, C.c_int(cin), up, C.c_int(cin), ctx.stream)
+        ctx.call("bsl_conv2d_dgrad_relu", C.byref(d), dy.p, w.p, b.p, act.p, C.c_int(col0), None, ctx.stream)
+        ctx.check_device()
+        ra, rb = a.download(np.uint16, (n, hw, hw, cin)), b.download(np.uint16, (n, hw, hw, cin))
+        assert np.array_equal(ra, rb)
+        assert (rb[..., col0:][act_h[..., col0:] == 0] == 0).all() and (rb[..., :col0] != 0).mean() > 0.9
+        for buf in (dy, w, act, a, b):
+            buf.free()
