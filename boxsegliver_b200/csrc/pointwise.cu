@@ -63,6 +63,35 @@ struct SumF {
   }
 };
 
+// ReluGrad fused with the BiasAddGrad that follows it (transposed conv: y = relu(convT(x) + b)): one pass writes
+// dy * (y > 0) and accumulates its per-channel sum; same reduction plan and order as SumF over the written tensor.
+struct ReluBiasF {
+  static constexpr int K = 1, NIN = 2, UNROLL = 4;
+  struct State {};
+  const __nv_bfloat16* y;
+  const __nv_bfloat16* dy;
+  __nv_bfloat16* out;
+  int y_ld, dy_ld, o_ld;
+  __device__ void init(State&, int, int) const {}
+  __device__ void load(long long p, int ch0, uint4 (&raw)[2]) const {
+    raw[0] = bsl::ld16(y + p * y_ld + ch0);
+    raw[1] = bsl::ld16(dy + p * dy_ld + ch0);
+  }
+  __device__ void accum(const State&, long long p, const uint4 (&raw)[2], float (&acc)[1][8]) const {
+    float v[8], g[8];
+    bsl::unpack8(raw[0], v);
+    bsl::unpack8(raw[1], g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      g[j] = v[j] > 0.f ? g[j] : 0.f;
+      acc[0][j] += g[j];
+    }
+    // this thread's channel group, as pixel_reduce_kernel assigns it (threadIdx.x % (c / 8))
+    bsl::st16(out + p * o_ld + (threadIdx.x % cg) * 8, bsl::pack8(g));
+  }
+  int cg;
+};
+
 __global__ void f64_to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = (float)src[i];
@@ -82,6 +111,26 @@ int bsl_channel_sum_bf16(bsl_ctx* ctx, const void* x, long long pixels, int c, i
   rc = bsl::run_pixel_reduce(ctx, f, pixels, 1, c, tmp, stream);
   if (rc) return rc;
   f64_to_f32_kernel<<<(c + 127) / 128, 128, 0, stream>>>(tmp, out, c);
+  BSL_LAUNCH_CHECK(ctx, "f64_to_f32_kernel");
+  return BSL_OK;
+}
+
+extern "C" int bsl_relu_bwd_bias(bsl_ctx* ctx, long long pixels, int c, const void* y, int y_ld, const void* dy,
+                                 int dy_ld, void* out, int out_ld, float* dbias, void* stream) {
+  if (!ctx) return BSL_EINVAL;
+  if (!y || !dy || !out || !dbias) return bsl_fail(ctx, BSL_EINVAL, "relu_bwd_bias: null buffer");
+  if (c % 8 || y_ld % 8 || dy_ld % 8 || out_ld % 8) return bsl_fail(ctx, BSL_EUNSUPPORTED, "relu_bwd_bias: c%%8");
+  cudaStream_t s = as_stream(stream);
+  ReluBiasF f{reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dy),
+              reinterpret_cast<__nv_bfloat16*>(out), y_ld, dy_ld, out_ld, c / 8};
+  bsl::ReducePlan p = bsl::plan_reduce(ctx, pixels, 1, c, 1);
+  float* base = nullptr;
+  int rc = bsl::bsl_scratch(ctx, p.scratch_bytes + (size_t)c * sizeof(double) + 16, &base, s);
+  if (rc) return rc;
+  double* tmp = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + ((p.scratch_bytes + 15) & ~(size_t)15));
+  rc = bsl::run_pixel_reduce(ctx, f, pixels, 1, c, tmp, s);
+  if (rc) return rc;
+  f64_to_f32_kernel<<<(c + 127) / 128, 128, 0, s>>>(tmp, dbias, c);
   BSL_LAUNCH_CHECK(ctx, "f64_to_f32_kernel");
   return BSL_OK;
 }

@@ -826,9 +826,12 @@ class UNetEngine:
                 dc = self.dcat[L.level]
                 dup = dc.slice(L.cout, L.cout)
                 # ReluGrad in place on the upper half of dcat (unless dgrad's epilogue already applied it)
+                gb = self._pp(self.G, f"{L.scope}/biases")
                 if L.level not in relu_fused:
-                    call("bsl_relu_bwd", C.c_longlong(L.a.pixels), C.c_int(L.cout), L.a.p, C.c_int(L.a.ld), dup.p,
-                         C.c_int(dup.ld), dup.p, C.c_int(dup.ld), s)
+                    # ... and the bias gradient (sum over pixels of the masked gradient) from the same pass
+                    call("bsl_relu_bwd_bias", C.c_longlong(L.a.pixels), C.c_int(L.cout), L.a.p, C.c_int(L.a.ld), dup.p,
+                         C.c_int(dup.ld), dup.p, C.c_int(dup.ld), gb, s)
+                    gb = None
                 d = self._convT_desc(L)
                 d.y_ld = dup.ld
                 d.x_ld = L.cin
@@ -837,7 +840,7 @@ class UNetEngine:
                 fork()
                 d.x_ld = L.x.ld
                 self._tc("convT_wgrad", self._flops(L), "bsl_convT2d_bwd_filter", C.byref(d), L.x.p, dup.p,
-                         self._pp(self.G, f"{L.scope}/weights"), self._pp(self.G, f"{L.scope}/biases"),
+                         self._pp(self.G, f"{L.scope}/weights"), gb,
                          self.wgrad_ws.p, wsb, ws, stream=ws)
                 self._after_grad(L)
         if overlap:     # join: everything downstream (optimizer, host reads of G) is ordered after the filter gradients

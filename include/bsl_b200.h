@@ -344,6 +344,11 @@ int bsl_maxpool2x2_bwd_add(bsl_ctx* ctx, int n, int h, int w, int c, const void*
 /* ReluGrad: out = dy * (y > 0). */
 int bsl_relu_bwd(bsl_ctx* ctx, long long pixels, int c, const void* y_bf16, int y_ld, const void* dy_bf16,
                  int dy_ld, void* out_bf16, int out_ld, void* stream);
+/* ReluGrad + BiasAddGrad of slim.conv2d_transpose (UNet.py:91) in one pass: out = dy * (y > 0) and
+ * dbias[c] = sum over pixels of out (the same fixed-order reduction bsl_convT2d_bwd_filter runs when it is given
+ * dbias; pass dbias = NULL there afterwards). */
+int bsl_relu_bwd_bias(bsl_ctx* ctx, long long pixels, int c, const void* y_bf16, int y_ld, const void* dy_bf16,
+                      int dy_ld, void* out_bf16, int out_ld, float* dbias_f32, void* stream);
 
 /* ------------------------------------------------------------------ losses, masks, Dice counts
  * loss_metrics._compute_weights / weighted_sparse_softmax_cross_entropy / sparse_dice_loss

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from boxsegliver_b200 import _lib
-from boxsegliver_b200.device import round_bf16
+from boxsegliver_b200.device import bf16_bits_to_f32, f32_to_bf16_bits, round_bf16
 from oracle import tf_ops as O
 from tests.gpu_util import TOL_BF16, bf16_randn, padded, rel
 
@@ -408,3 +408,33 @@ def test_pipelined_apply_and_conv_match_serial(ctx):
         bad = _lib.Pipe(flags.ptr, flags.ptr + 256, 3, 6)      # 3 does not divide n = 8
         ctx.call("bsl_conv2d_dgrad_pipe", C.byref(cd3), ba[1].p, wd.p, bdx[1].p, C.byref(bad), ctx.stream)
     ctx.sync()
+
+
+def test_relu_bwd_bias_matches_two_passes(ctx):
+    """bsl_relu_bwd_bias == bsl_relu_bwd followed by the bias-gradient reduction of bsl_convT2d_bwd_filter: the masked
+    gradient bit for bit (also in place, with channel windows of a wider buffer), the bias gradient to fp32 rounding
+    of the same fixed-order sums."""
+    rng = np.random.default_rng(31)
+    for pixels, c, ld in ((2 * 32 * 32, 64, 128), (5 * 16 * 16, 256, 256), (1000, 8, 24)):
+        yh = np.maximum(rng.standard_normal((pixels, ld)), 0).astype(np.float32)
+        dyh = rng.standard_normal((pixels, ld)).astype(np.float32)
+        y, dy = ctx.from_numpy(f32_to_bf16_bits(yh)), ctx.from_numpy(f32_to_bf16_bits(dyh))
+        a, b = ctx.alloc(pixels * ld * 2).zero(), ctx.from_numpy(f32_to_bf16_bits(dyh))
+        db = ctx.alloc(c * 4)
+        c0 = ld - c                                            # upper channel window, like the concat buffer
+        win = lambda buf: C.c_void_p(buf.ptr + c0 * 2)         # noqa: E731
+        ctx.call("bsl_relu_bwd", C.c_longlong(pixels), C.c_int(c), win(y), C.c_int(ld), win(dy), C.c_int(ld), win(a),
+                 C.c_int(ld), ctx.stream)
+        ctx.call("bsl_relu_bwd_bias", C.c_longlong(pixels), C.c_int(c), win(y), C.c_int(ld), win(b), C.c_int(ld), win(b),
+                 C.c_int(ld), db.p, ctx.stream)               # in place
+        ctx.check_device()
+        ra = a.download(np.uint16, (pixels, ld))[:, c0:]
+        rb = b.download(np.uint16, (pixels, ld))[:, c0:]
+        assert np.array_equal(ra, rb)
+        if c0:
+            assert np.array_equal(b.download(np.uint16, (pixels, ld))[:, :c0], f32_to_bf16_bits(dyh)[:, :c0])  # untouched
+        ref = bf16_bits_to_f32(ra).astype(np.float64).sum(axis=0)
+        got = db.download(np.float32, (c,))
+        assert np.allclose(got, ref, rtol=2e-6, atol=1e-4), np.abs(got - ref).max()
+        for buf in (y, dy, a, b, db):
+            buf.free()
