@@ -852,6 +852,40 @@ int bsl_convT2d_bwd_data(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* dy
   int rc = check_convT(ctx, d);
   if (rc) return rc;
   if (!dyr || !w || !dx) return bsl_fail(ctx, BSL_EINVAL, "convT2d_bwd_data: null buffer");
+  static const int up_off = getenv("BSL_CONVT_DGRAD_V1") ? atoi(getenv("BSL_CONVT_DGRAD_V1")) : 0;
+  if (!up_off && halo_eligible(d->w, d->n * d->h)) {
+    // Persistent halo-tile kernel as a 1-tap GEMM: dx[p, ci] = sum over (a, b, co) of dy[2y+a, 2x+b, co] w[a,b,co,ci].
+    // For a fixed row parity a the pair (b, co) is the channel axis of a row-strided view of dy, so the reduction is
+    // 2 "depth" steps (a) x 2 (b) x co/64 dense TMA boxes, no element-strided gather; the rows of all images form one
+    // tall image (a 1x1 conv has no halo, tiles may straddle images).
+    const int rows = d->n * d->h;
+    HaloPlan pl = plan_halo(ctx, d->w, rows, 1, d->cin);
+    const int kblocks = 4 * d->cout / 64;
+    int res_stages = 0, res_smem = 0;
+    const bool res = plan_resident(pl.bn, 1, kblocks, &pl.nsub, &res_stages, &res_smem);
+    if (res) replan_units(ctx, pl);
+    CUtensorMap ta, tb;
+    if ((rc = upsampled_map(ctx, dyr, d->cout, d->w, d->h, d->n, d->y_ld, 8, 16, &ta))) return rc;
+    if ((rc = matrix_map(ctx, w, d->cin, 4 * d->cout, 64, 64, &tb))) return rc;
+    ConvHaloArgs a = {};
+    halo_common(a, pl, d->w, rows, 1);
+    a.ntaps = 1;
+    a.halo = 0;
+    a.kd = 2;
+    a.depth = 1;
+    a.cblocks = 2 * d->cout / 64;
+    a.up_cpb = d->cout / 64;
+    a.out = dx;
+    a.ostride_x = d->x_ld;
+    a.ostride_y = (long long)d->w * d->x_ld;
+    a.ostride_n = 0;
+    a.n_group = d->cin;
+    a.n_total = d->cin;
+    a.a_stages = res_stages;
+    a.status = ctx->d_status;
+    return res ? launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream))
+               : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
+  }
   int tw, th, tn;
   pick_box(128, d->w, d->n * d->h, 1, &tw, &th, &tn);
   if (tn != 1) th *= tn;  // rows absorb the remainder (boxes may overhang; OOB rows are masked)

@@ -368,6 +368,9 @@ struct ConvHaloArgs {
   const int* wait_flags;
   int wait_epoch, wait_imgs;
   int narrow_store;              // tuning: 128-bit epilogue stores instead of 256-bit (BSL_NARROW_STORE=1)
+  // ---- transposed-conv backward-data: the A tensor map is upsampled_map (c, b, w, a, n*h); the reduction runs over
+  //      (a = kd index, b, 64-channel block): K block cbx -> a = cbx / cblocks, b = cb / up_cpb, channel (cb % up_cpb) * 64
+  int up_cpb;                    // 0 = ordinary (c, x, y, z, vol) coordinates
   // ---- optional fused ReluGrad (dgrad into a concat buffer): output columns >= mask_col0 are zeroed where the
   //      activation stored at the same (pixel, column) of `relu_mask` (same strides as `out`) is not positive
   const void* relu_mask;
@@ -416,9 +419,10 @@ __device__ __forceinline__ void ch_store_chunk(const uint32_t (&v)[32], __nv_bfl
     float a = __uint_as_float(v[2 * i]);
     float b = __uint_as_float(v[2 * i + 1]);
     if (SCATTER) {
-      if (bias) {
-        a += __ldg(bias + 2 * i);
-        b += __ldg(bias + 2 * i + 1);
+      if (bias) {   // the warp's slice of the bias vector, staged in shared memory by the epilogue loop
+        const float2 bb = reinterpret_cast<const float2*>(bias)[i];
+        a += bb.x;
+        b += bb.y;
       }
       if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
     }
@@ -481,6 +485,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __shared__ uint32_t tmem_slot;
   __shared__ int dead;
   __shared__ float s_stats[STATS ? CH_EPI_WARPS * 2 * BN : 1];
+  __shared__ __align__(16) float s_bias[SCATTER ? CH_EPI_WARPS * 256 : 1];   // per epilogue warp: bias of its columns
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -573,9 +578,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int kdi = cbx / p.cblocks, cb = cbx - kdi * p.cblocks;
 #pragma unroll
           for (int j = 0; j < NSUB; ++j)
-            if (j < nsub)   // slices outside the volume are zero-filled by TMA: SAME padding along depth
-              tma_load_5d(sA0 + stage * A_BYTES + j * CH_SUB_BYTES, &tmA, fb, cb * 64, tx[j] * 8 - p.halo,
-                          ty[j] * 16 - p.halo, img[j] % p.depth + kdi - (p.kd >> 1), img[j] / p.depth);
+            if (j < nsub) {
+              if (p.up_cpb != 0)   // (c, b, x, a, row) of the upsampled gradient; rows of all images form one column
+                tma_load_5d(sA0 + stage * A_BYTES + j * CH_SUB_BYTES, &tmA, fb, (cb % p.up_cpb) * 64, cb / p.up_cpb,
+                            tx[j] * 8, kdi, ty[j] * 16);
+              else                 // slices outside the volume are zero-filled by TMA: SAME padding along depth
+                tma_load_5d(sA0 + stage * A_BYTES + j * CH_SUB_BYTES, &tmA, fb, cb * 64, tx[j] * 8 - p.halo,
+                            ty[j] * 16 - p.halo, img[j] % p.depth + kdi - (p.kd >> 1), img[j] / p.depth);
+            }
           if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -698,11 +708,21 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     int buf = 0;
     uint32_t pacc = 0;
+    int bias_n0 = -1;
+    float* sb = s_bias + (SCATTER ? e * 256 : 0);
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int pu = u / p.n_ntiles;
       const int n0 = (u % p.n_ntiles) * BN;
       int nsub = p.n_sub_total - pu * NSUB;
       nsub = nsub > NSUB ? NSUB : nsub;
+      if (SCATTER && p.bias != nullptr && n0 != bias_n0) {
+        // (re)stage the bias of this warp's columns: 32 scalar global loads per chunk in the store loop left the
+        // epilogue waiting on the long scoreboard (ncu: 4.7 stalled warps per issue, tensor pipe 11 % active)
+        __syncwarp();
+        for (int i = lane; i < COLS; i += 32) sb[i] = __ldg(p.bias + (n0 + c_begin + i) % p.n_group);
+        __syncwarp();
+        bias_n0 = n0;
+      }
       if (!mbar_wait(acc_full + 8 * buf, pacc, st, 26)) break;
       tc_fence_after();
       const int j = NSUB == 2 ? half : 0;
@@ -733,7 +753,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int g = col / p.n_group;          // transposed-conv scatter: column group = filter tap
                 const int ngc = col - g * p.n_group;
                 o = obase + p.group_off[g] + ngc;
-                bias = p.bias ? p.bias + ngc : nullptr;
+                bias = p.bias ? sb + (c - c_begin) + 32 * hc : nullptr;
               } else {
                 o = obase + col;
               }
