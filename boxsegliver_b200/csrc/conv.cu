@@ -18,6 +18,7 @@ using namespace bsl;
 namespace {
 
 int g_mn_lbo = 8192, g_mn_sbo = 1024, g_mn_kadv = 2048;
+long long* g_dbg_waits = nullptr;   // device [256][4], allocated by bsl_debug_set(ctx, 3, 1)
 
 template <int MODE, bool B_MN, int BN, int STAGES>
 int launch_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const IgemmArgs& args_in, dim3 grid,
@@ -333,6 +334,7 @@ void halo_common(ConvHaloArgs& a, const HaloPlan& p, int w, int h, int n) {
   a.n_ntiles = p.n_ntiles;
   static const int narrow = getenv("BSL_NARROW_STORE") ? atoi(getenv("BSL_NARROW_STORE")) : 0;
   a.narrow_store = narrow;
+  a.dbg = g_dbg_waits;
   a.kd = 1;        // 2-D: every image is its own one-slice "volume" (tensor map dims (c, w, h, n, 1))
   a.depth = n;
 }
@@ -470,8 +472,24 @@ int bsl_debug_set(bsl_ctx* ctx, int key, int value) {
     case 0: g_mn_lbo = value; return BSL_OK;
     case 1: g_mn_sbo = value; return BSL_OK;
     case 2: g_mn_kadv = value; return BSL_OK;
+    case 3:
+      if (value && !g_dbg_waits) {
+        BSL_CUDA(ctx, cudaMalloc(&g_dbg_waits, 256 * 4 * sizeof(long long)));
+        BSL_CUDA(ctx, cudaMemset(g_dbg_waits, 0, 256 * 4 * sizeof(long long)));
+      } else if (!value && g_dbg_waits) {
+        cudaFree(g_dbg_waits);
+        g_dbg_waits = nullptr;
+      }
+      return BSL_OK;
   }
   return bsl_fail(ctx, BSL_EINVAL, "debug_set: unknown key %d", key);
+}
+
+int bsl_debug_read_waits(bsl_ctx* ctx, long long* out, int ctas) {
+  if (!ctx || !out || ctas < 1 || ctas > 256) return BSL_EINVAL;
+  if (!g_dbg_waits) return bsl_fail(ctx, BSL_EINVAL, "debug waits are off (bsl_debug_set(ctx, 3, 1))");
+  BSL_CUDA(ctx, cudaMemcpy(out, g_dbg_waits, (size_t)ctas * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return BSL_OK;
 }
 
 // fprop on the halo-tile kernel; `sums` (fp64 [2][cout], nullable) receives the per-channel sum and

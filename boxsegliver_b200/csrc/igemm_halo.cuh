@@ -371,6 +371,8 @@ struct ConvHaloArgs {
   // ---- transposed-conv backward-data: the A tensor map is upsampled_map (c, b, w, a, n*h); the reduction runs over
   //      (a = kd index, b, 64-channel block): K block cbx -> a = cbx / cblocks, b = cb / up_cpb, channel (cb % up_cpb) * 64
   int up_cpb;                    // 0 = ordinary (c, x, y, z, vol) coordinates
+  long long* dbg;                // tuning (bsl_debug_set key 3): per CTA {total, wait acc_empty, wait a_full, wait b_full}
+                                 // cycles of the UMMA issuer thread
   // ---- optional fused ReluGrad (dgrad into a concat buffer): output columns >= mask_col0 are zeroed where the
   //      activation stored at the same (pixel, column) of `relu_mask` (same strides as `out`) is not positive
   const void* relu_mask;
@@ -644,21 +646,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int sa = 0, sb = 0, buf = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
       bool ok = true;
+      long long t_all = clock64(), w_acc = 0, w_a = 0, w_b = 0, t0;
       if (B_RES && (int)blockIdx.x < p.n_units) ok = mbar_wait(b_full, 0, st, 27);
       for (int u = blockIdx.x; u < p.n_units && ok; u += gridDim.x) {
         const int pu = u / p.n_ntiles;
         int nsub = p.n_sub_total - pu * NSUB;
         nsub = nsub > NSUB ? NSUB : nsub;
+        t0 = clock64();
         if (!mbar_wait(acc_empty + 8 * buf, pacc ^ 1, st, 23)) { ok = false; break; }
+        w_acc += clock64() - t0;
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * (NSUB * BN);
         for (int cb = 0; cb < kblocks && ok; ++cb) {   // cb runs over (kd, 64-channel block) here
+          t0 = clock64();
           if (!mbar_wait(a_full + 8 * sa, pa, st, 24)) { ok = false; break; }
+          w_a += clock64() - t0;
           const uint32_t a_stage = sA0 + sa * A_BYTES;
           if (B_RES) tc_fence_after();
           for (int tap = 0; tap < p.ntaps; ++tap) {
             if (!B_RES) {
+              t0 = clock64();
               if (!mbar_wait(b_full + 8 * sb, pb, st, 25)) { ok = false; break; }
+              w_b += clock64() - t0;
               tc_fence_after();
             }
             const uint32_t b_stage = B_RES ? sB0 + (cb * p.ntaps + tap) * B_BYTES : sB0 + sb * B_BYTES;
@@ -686,6 +695,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (ok) umma_commit(acc_full + 8 * buf);
         if (++buf == ACC_BUFS) { buf = 0; pacc ^= 1; }
+      }
+      if (p.dbg != nullptr) {
+        p.dbg[blockIdx.x * 4 + 0] = clock64() - t_all;
+        p.dbg[blockIdx.x * 4 + 1] = w_acc;
+        p.dbg[blockIdx.x * 4 + 2] = w_a;
+        p.dbg[blockIdx.x * 4 + 3] = w_b;
       }
     }
   } else {

@@ -53,6 +53,9 @@ int bsl_launch_count(bsl_ctx* ctx, unsigned long long* out);
 
 /* Probe hook: overrides a layout constant of the UMMA descriptors (tools/gpu_conv_probe.py). */
 int bsl_debug_set(bsl_ctx* ctx, int key, int value);
+/* Tuning aid: with bsl_debug_set(ctx, 3, 1) the UMMA issuer thread of every conv_halo CTA records {total cycles,
+ * cycles waiting for a free accumulator, for an activation stage, for a filter stage} of its last launch. */
+int bsl_debug_read_waits(bsl_ctx* ctx, long long* out /*[ctas][4]*/, int ctas);
 
 int bsl_malloc(bsl_ctx* ctx, size_t bytes, void** out);
 int bsl_free(bsl_ctx* ctx, void* ptr);

@@ -32,9 +32,12 @@ ap.add_argument("--ops", default="fprop,dgrad,wgrad")
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--stats", action="store_true", help="time bsl_conv2d_fprop_stats instead of bsl_conv2d_fprop")
+ap.add_argument("--waits", action="store_true", help="print where the UMMA issuer thread waits (bsl_debug_set key 3)")
 a = ap.parse_args()
 
 ctx = Context(0)
+if a.waits:
+    ctx.call("bsl_debug_set", C.c_int(3), C.c_int(1))
 rng = np.random.default_rng(0)
 seed_block = (rng.standard_normal(1 << 20).astype(np.float32) * 0.5)
 from boxsegliver_b200.device import f32_to_bf16_bits  # noqa: E402
@@ -91,6 +94,14 @@ for name in a.layers.split(","):
         ctx.check_device()
         tot[op] = tot.get(op, 0.0) + ms
         print(f"{name:8s} {op:6s} hw={hw:3d} cin={cin:4d} cout={cout:4d}  {ms:7.3f} ms  {flops / ms / 1e9:7.1f} TF/s", flush=True)
+        if a.waits and op != "wgrad":
+            wt = np.zeros((148, 4), np.int64)
+            ctx.call("bsl_debug_read_waits", wt.ctypes.data_as(C.c_void_p), C.c_int(148))
+            cyc = wt[:, 0].astype(np.float64)
+            ok = cyc > 0
+            f = lambda k: 100.0 * (wt[ok, k] / cyc[ok]).mean()   # noqa: E731
+            print(f"         issuer: {cyc[ok].mean():.0f} cycles; waiting acc_empty {f(1):.1f}%  a_full {f(2):.1f}%  "
+                  f"b_full {f(3):.1f}%  issuing {100 - f(1) - f(2) - f(3):.1f}%", flush=True)
     for b in (x, dy, w, y, dx, dw, sums, ws):
         b.free()
 print("totals (ms):", {k: round(v, 3) for k, v in tot.items()})

@@ -21,6 +21,75 @@ using namespace bsl;
 constexpr int KB = 4;            // 64-element K blocks resident in shared memory (K = 256)
 constexpr uint64_t TIMEOUT_NS = 500000000ull;
 
+// Timing-only variant of the cta_group::1 stream with the operand geometry of the conv kernels: A is a halo tile
+// (10 x 18 pixels of 128 B), 8-row groups SBO = 1280 B apart, start address shifted by the tap offset
+// (r * 10 + s) * 128 B; B as before. halo = 0 reproduces the aligned stream (SBO 1024, no shift).
+struct HaloArgs {
+  int halo;
+  int reps;
+  long long* cycles;
+};
+
+template <int N>
+__global__ void __launch_bounds__(128) halo_stream_kernel(const HaloArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = base;                      // two sub-tiles of 23552 B
+  uint8_t* sB = base + 2 * 23552;          // 9 taps x (N x 128 B)
+  for (int i = threadIdx.x; i < (2 * 23552 + 9 * N * 128) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(base)[i] = make_uint4(0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+  const uint32_t done = smem_u32(&bar_done);
+  if (threadIdx.x == 0) { mbar_init(done, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc<(N < 32 ? 32 : N) * 2>(smem_u32(&tmem_slot)); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+  if (warp == 1 && elect_one_sync()) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, N, false, false);
+    const uint32_t sbo = p.halo ? 1280 : 1024;
+    const long long t0 = clock64();
+    for (int rep = 0; rep < p.reps; ++rep) {
+      for (int tap = 0; tap < 9; ++tap) {
+        const int toff = p.halo ? ((tap / 3) * 10 + tap % 3) * 128 : 0;
+        const uint64_t db = make_smem_desc_sw128(smem_u32(sB + tap * N * 128), 16, 1024);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const uint64_t da = make_smem_desc_sw128(smem_u32(sA + j * 23552) + toff, 16, sbo);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_bf16(tmem + j * N, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, 1u);
+        }
+      }
+    }
+    umma_commit(done);
+    const uint64_t t1 = globaltimer_ns();
+    while (!mbar_try_wait(done, 0)) if (globaltimer_ns() - t1 > TIMEOUT_NS) break;
+    p.cycles[blockIdx.x] = clock64() - t0;
+  }
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc<(N < 32 ? 32 : N) * 2>(tmem); }
+}
+
+template <int N>
+static void run_halo(int halo, int reps, long long* d_cycles, int grid) {
+  auto kern = halo_stream_kernel<N>;
+  const int smem = 2 * 23552 + 9 * N * 128 + 1024;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  HaloArgs a{halo, reps, d_cycles};
+  kern<<<grid, 128, smem>>>(a);
+  cudaError_t e = cudaDeviceSynchronize();
+  std::vector<long long> cyc(grid);
+  cudaMemcpy(cyc.data(), d_cycles, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
+  long long cmax = 0;
+  for (long long c : cyc) cmax = c > cmax ? c : cmax;
+  printf("stream 128x%dx16, %s operand geometry: %.1f cycles/MMA  (%s)\n", N,
+         halo ? "halo-tile (SBO 1280, tap-shifted start)" : "aligned (SBO 1024)", cmax / (reps * 72.0), cudaGetErrorString(e));
+}
+
 struct Args {
   const __nv_bfloat16* a;   // [256][K]   (cta_group::1: rows [0,128) are used by every CTA)
   const __nv_bfloat16* b;   // [N][K]
@@ -260,6 +329,11 @@ int main(int argc, char** argv) {
   { a.n = 64;  auto r = ref_for(64);  fails += run<false, 64>("cta_group::1 128x64x16", a, r, g1, 0);  fails += run<true, 64>("cta_group::2 256x64x16", a, r, g2, 0); }
   { a.n = 128; auto r = ref_for(128); fails += run<false, 128>("cta_group::1 128x128x16", a, r, g1, 0); fails += run<true, 128>("cta_group::2 256x128x16", a, r, g2, 0); }
   { a.n = 256; auto r = ref_for(256); fails += run<false, 256>("cta_group::1 128x256x16", a, r, g1, 0); fails += run<true, 256>("cta_group::2 256x256x16", a, r, g2, 0); }
+  for (int halo = 0; halo < 2; ++halo) {
+    run_halo<64>(halo, reps / 4, a.cycles, g1);
+    run_halo<128>(halo, reps / 4, a.cycles, g1);
+    run_halo<256>(halo, reps / 4, a.cycles, g1);
+  }
   printf("%s\n", fails ? "SOME CASES FAILED" : "ALL PASS");
   return fails ? 1 : 0;
 }
