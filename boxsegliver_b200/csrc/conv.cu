@@ -206,17 +206,17 @@ bool force_v1() {
   return v != 0;
 }
 
-template <int BN, int NSUB, bool B_MN, bool STATS, bool SCATTER>
+template <int BN, int NSUB, bool B_MN, bool STATS, bool SCATTER, bool TMA_ST = false>
 int launch_halo_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args, int grid,
-                    cudaStream_t stream) {
-  auto kern = conv_halo_kernel<BN, NSUB, B_MN, STATS, SCATTER>;
-  constexpr int smem = ConvHaloCfg<BN, NSUB>::SMEM_BYTES;
+                    cudaStream_t stream, const CUtensorMap* o = nullptr) {
+  auto kern = conv_halo_kernel<BN, NSUB, B_MN, STATS, SCATTER, false, TMA_ST>;
+  constexpr int smem = ConvHaloCfg<BN, NSUB, TMA_ST>::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
     BSL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, CH_THREADS, smem, stream>>>(a, b, args);
+  kern<<<grid, CH_THREADS, smem, stream>>>(a, b, o ? *o : a, args);
   BSL_LAUNCH_CHECK(ctx, "conv_halo_kernel launch");
   return BSL_OK;
 }
@@ -234,7 +234,7 @@ int launch_halo_res_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b
     BSL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  kern<<<grid, CH_THREADS, smem, stream>>>(a, b, args);
+  kern<<<grid, CH_THREADS, smem, stream>>>(a, b, a, args);
   BSL_LAUNCH_CHECK(ctx, "conv_halo_kernel (resident filter) launch");
   return BSL_OK;
 }
@@ -279,9 +279,39 @@ void replan_units(bsl_ctx* ctx, HaloPlan& p) {
   p.slots = cdiv(p.grid, p.n_ntiles);
 }
 
+// Which column-tile widths use the TMA-store epilogue (BSL_TMA_STORE: 0 none, 1 = 256-wide tiles, 2 = also 128).
+int tma_store_level() {
+  static const int v = getenv("BSL_TMA_STORE") ? atoi(getenv("BSL_TMA_STORE")) : 1;
+  return v;
+}
+
+// Output tensor map of the TMA-store epilogue: (c, x, y, image) with a 64-channel x 8 x 16 pixel box.
+int out_map(bsl_ctx* ctx, const ConvHaloArgs& a, int w, int h, CUtensorMap* out) {
+  if (a.ostride_y != (long long)w * a.ostride_x || (a.n > 1 && a.ostride_n != (long long)h * a.ostride_y) ||
+      (reinterpret_cast<uintptr_t>(a.out) & 15) || a.ostride_x % 8)
+    return 1;   // not a plain NHWC window: keep the direct stores
+  uint64_t dims[4] = {(uint64_t)a.n_total, (uint64_t)w, (uint64_t)h, (uint64_t)a.n};
+  uint64_t str[4] = {2, (uint64_t)a.ostride_x * 2, (uint64_t)a.ostride_y * 2,
+                     (uint64_t)(a.n > 1 ? a.ostride_n : (long long)h * a.ostride_y) * 2};
+  uint32_t bx[4] = {64, 8, 16, 1};
+  return bsl_get_tmap(ctx, a.out, 4, dims, str, bx, out);
+}
+
 template <bool B_MN, bool STATS, bool SCATTER>
 int launch_halo(bsl_ctx* ctx, int bn, int nsub, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args,
                 int grid, cudaStream_t stream) {
+  if constexpr (!STATS && !SCATTER) {
+    const int lvl = tma_store_level();
+    if (args.relu_mask == nullptr && ((bn == 256 && lvl >= 1) || (bn == 128 && lvl >= 2))) {
+      CUtensorMap o;
+      if (out_map(ctx, args, args.ntile_w * 8, args.ntile_h * 16, &o) == 0) {
+        if (bn == 256 && nsub == 2) return launch_halo_one<256, 2, B_MN, false, false, true>(ctx, a, b, args, grid, stream, &o);
+        if (bn == 256 && nsub == 1) return launch_halo_one<256, 1, B_MN, false, false, true>(ctx, a, b, args, grid, stream, &o);
+        if (bn == 128 && nsub == 2) return launch_halo_one<128, 2, B_MN, false, false, true>(ctx, a, b, args, grid, stream, &o);
+        if (bn == 128 && nsub == 1) return launch_halo_one<128, 1, B_MN, false, false, true>(ctx, a, b, args, grid, stream, &o);
+      }
+    }
+  }
   if (bn == 64 && nsub == 2) return launch_halo_one<64, 2, B_MN, STATS, SCATTER>(ctx, a, b, args, grid, stream);
   if (bn == 64 && nsub == 1) return launch_halo_one<64, 1, B_MN, STATS, SCATTER>(ctx, a, b, args, grid, stream);
   if (bn == 128 && nsub == 2) return launch_halo_one<128, 2, B_MN, STATS, SCATTER>(ctx, a, b, args, grid, stream);

@@ -382,7 +382,9 @@ struct ConvHaloArgs {
 
 constexpr int CH_SUB_BYTES = 23552;   // (10 x 18) x 128 B = 23040, padded to a multiple of 1024
 
-template <int BN, int NSUB>
+constexpr int CH_STAGING_BYTES = 2 * 16384;   // TMA-store epilogue: one 128-pixel x 64-channel tile per warp group
+
+template <int BN, int NSUB, bool TMA_ST = false>
 struct ConvHaloCfg {
   static constexpr int ACC_BUFS = (512 / (BN * NSUB)) >= 2 ? 2 : 1;
   static constexpr int TMEM_COLS = BN * NSUB * ACC_BUFS;
@@ -391,9 +393,9 @@ struct ConvHaloCfg {
   // three activation stages hide the HBM latency of the one-block-deep reductions (Cin = 64: a unit is
   // ~1.5 us of MMAs); the widest column tile only occurs with long reductions and keeps two.
   static constexpr int A_STAGES = BN == 256 ? 2 : 3;
-  static constexpr int B_FIT = (212 * 1024 - A_STAGES * A_BYTES) / B_BYTES;
+  static constexpr int B_FIT = (212 * 1024 - (TMA_ST ? CH_STAGING_BYTES : 0) - A_STAGES * A_BYTES) / B_BYTES;
   static constexpr int B_STAGES = B_FIT > 8 ? 8 : (B_FIT < 3 ? 3 : B_FIT);
-  static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_BYTES + 1024;
+  static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_BYTES + 1024 + (TMA_ST ? CH_STAGING_BYTES : 0);
 };
 
 // warp 0: A producer, 1: UMMA issuer, 2..9: epilogue (two warps per TMEM lane quarter), 10: B producer
@@ -470,11 +472,17 @@ __device__ __forceinline__ void ch_transpose_reduce(float (&s1)[32], float (&s2)
 // (profiles/r01_ncu_full_conv_kernels.txt, enc1_2 dgrad). a_stages = p.a_stages activation stages share the rest.
 constexpr int CH_MAX_A_STAGES = 4;
 
-template <int BN, int NSUB, bool B_MN, bool STATS, bool SCATTER, bool B_RES = false>
+// TMA_ST (plain epilogue only: no statistics, no scatter, streamed filter): the bf16 tile goes registers -> swizzled
+// shared-memory staging -> one TMA store per 128-pixel x 64-channel block instead of one 32-byte sector per lane and
+// store instruction. A lane-per-pixel global store costs one L1 wavefront per 32 bytes on the data path the UMMA
+// operand fetch also uses, and left the issuer waiting 16-30 % of the time for the un-overlapped epilogue of the
+// 256-wide tiles (gpu_conv_bench --waits); the staged store needs a quarter of the wavefronts and is asynchronous.
+template <int BN, int NSUB, bool B_MN, bool STATS, bool SCATTER, bool B_RES = false, bool TMA_ST = false>
 __global__ void __launch_bounds__(CH_THREADS)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvHaloArgs p) {
-  using Cfg = ConvHaloCfg<BN, NSUB>;
+                 const __grid_constant__ CUtensorMap tmO, const ConvHaloArgs p) {
+  static_assert(!TMA_ST || (!STATS && !SCATTER && !B_RES), "TMA-store epilogue: plain streamed-filter variant only");
+  using Cfg = ConvHaloCfg<BN, NSUB, TMA_ST>;
   constexpr int ACC_BUFS = Cfg::ACC_BUFS;
   constexpr int B_STAGES = Cfg::B_STAGES;
   constexpr int A_BYTES = Cfg::A_BYTES;
@@ -483,7 +491,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int A_STAGES = B_RES ? p.a_stages : Cfg::A_STAGES;
 
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * A_BARS + 2 * B_STAGES + 2 * ACC_BUFS];
+  __shared__ __align__(8) uint64_t bars[2 * A_BARS + 2 * B_STAGES + 2 * ACC_BUFS + 2];
   __shared__ uint32_t tmem_slot;
   __shared__ int dead;
   __shared__ float s_stats[STATS ? CH_EPI_WARPS * 2 * BN : 1];
@@ -500,6 +508,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t b_empty = smem_u32(&bars[2 * A_BARS + B_STAGES]);
   const uint32_t acc_full = smem_u32(&bars[2 * A_BARS + 2 * B_STAGES]);
   const uint32_t acc_empty = smem_u32(&bars[2 * A_BARS + 2 * B_STAGES + ACC_BUFS]);
+  const uint32_t grp_bar = smem_u32(&bars[2 * A_BARS + 2 * B_STAGES + 2 * ACC_BUFS]);   // TMA_ST: one per warp group
+  const uint32_t sStage = sB0 + B_STAGES * B_BYTES;                                     // TMA_ST: 2 x 16 KB
   DeviceStatus* st = p.status;
 
   if (threadIdx.x == 0) dead = *reinterpret_cast<volatile int*>(&st->error);
@@ -524,6 +534,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(acc_full + 8 * s, 1);
       mbar_init(acc_empty + 8 * s, CH_EPI_WARPS);  // one arrival per epilogue warp
     }
+    mbar_init(grp_bar, 4);       // the four lane-quarter warps of a staging group
+    mbar_init(grp_bar + 8, 4);
+    if (TMA_ST) prefetch_tensormap(&tmO);
     fence_barrier_init();
   } else if (warp == 1) {
     tmem_alloc<Cfg::TMEM_COLS>(smem_u32(&tmem_slot));
@@ -724,6 +737,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int buf = 0;
     uint32_t pacc = 0;
     int bias_n0 = -1;
+    uint32_t gphase = 0;
     float* sb = s_bias + (SCATTER ? e * 256 : 0);
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int pu = u / p.n_ntiles;
@@ -741,7 +755,54 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!mbar_wait(acc_full + 8 * buf, pacc, st, 26)) break;
       tc_fence_after();
       const int j = NSUB == 2 ? half : 0;
-      if (!STATS && j < nsub) {
+      if (TMA_ST && j < nsub) {
+        // group = the four warps (lane quarters 0..3) with the same `half`: one staging tile, one barrier
+        int s = pu * NSUB + j;
+        const int tx = s % p.ntile_w;
+        s /= p.ntile_w;
+        const int ty = s % p.ntile_h;
+        const int img = s / p.ntile_h;
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (NSUB * BN) + j * BN;
+        const uint32_t stg = sStage + half * 16384;
+        const uint32_t gb = grp_bar + 8 * half;
+        const bool leader = q == 0 && lane == 0;
+        const uint32_t rowaddr = stg + r * 128;
+#pragma unroll 1
+        for (int c = c_begin; c < c_begin + COLS; c += 64) {
+          uint32_t v0[32], v1[32], pk[32];
+          tmem_ld_32x32(trow + c, v0);
+          tmem_ld_32x32(trow + c + 32, v1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
+            pk[i] = *reinterpret_cast<uint32_t*>(&h0);
+            pk[16 + i] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+          // (1) the previous store of this group has finished reading the staging tile
+          if (leader) bulk_wait_read_all();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(gb);
+          if (!mbar_wait(gb, gphase, st, 29)) break;
+          gphase ^= 1;
+          // (2) row r -> 8 chunks of 16 B at chunk position (i ^ (r & 7)): the tensor map's 128-byte swizzle
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            st_shared_v4(rowaddr + (static_cast<uint32_t>(i ^ (r & 7)) << 4), pk[4 * i], pk[4 * i + 1], pk[4 * i + 2],
+                         pk[4 * i + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(gb);
+          if (!mbar_wait(gb, gphase, st, 30)) break;
+          gphase ^= 1;
+          if (leader) {
+            tma_store_4d(&tmO, stg, n0 + c, tx * 8, ty * 16, img);
+            bulk_commit_group();
+          }
+        }
+      }
+      if (!TMA_ST && !STATS && j < nsub) {
         int s = pu * NSUB + j;
         const int tx = s % p.ntile_w;
         s /= p.ntile_w;
@@ -840,6 +901,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
       if (++buf == ACC_BUFS) { buf = 0; pacc ^= 1; }
     }
+    if (TMA_ST && q == 0 && lane == 0) bulk_wait_all();   // the staging tiles stay valid until the last store is done
     if (PERSIST) {
 #pragma unroll
       for (int c = 0; c < SC; c += 32) {
