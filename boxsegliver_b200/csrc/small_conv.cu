@@ -65,7 +65,7 @@ __global__ void stem_fprop_kernel(const float* __restrict__ x, const float* __re
 // staged in shared memory with coalesced loads (zero outside the image = SAME padding); thread
 // (pixel lane, 8-column group g) then gathers its 8 columns through offsets that depend only on g
 // (held in registers) and writes one 16-byte chunk: a warp writes 512 contiguous bytes.
-constexpr int IM2COL_STRIP = 128;
+constexpr int IM2COL_STRIP = 256;
 __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int n, int h, int wd,
                                    int cin, int kh, int kw) {
   extern __shared__ float patch[];  // [kh][strip + kw - 1][cin]
