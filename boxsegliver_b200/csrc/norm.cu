@@ -245,6 +245,71 @@ __global__ void norm_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld,
   if (sig.flags != nullptr) pipe_signal_block(sig, blockIdx.y / sig.imgs_per_slice);
 }
 
+// norm_apply_kernel (no guide) that also evaluates the 1x1 logits convolution on the activation it has just produced
+// (slim.conv2d(net, num_classes, 1, activation_fn=None), NetworksV2/UNet.py:100): the last normalised layer feeds
+// only that conv, so its 128 bytes per pixel need not be read back. Same arithmetic and summation order as
+// head_fprop_kernel (small_conv.cu): bf16-rounded activations, 8 channels per lane in ascending order, xor-shuffle
+// over the lanes of a pixel, + bias -- the logits are bit-identical to the two-pass path.
+template <int COUT>
+__global__ void norm_apply_head_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, __nv_bfloat16* __restrict__ a,
+                                       int a_ld, long long pixels_per_group, int c, int relu,
+                                       const float* __restrict__ scale, const float* __restrict__ shift, int gstride,
+                                       const float* __restrict__ wh, const float* __restrict__ bh,
+                                       float* __restrict__ logits) {
+  const int cg = c / 8;                    // power of two <= 32: the lanes of a pixel sit in one warp
+  const int rows = blockDim.x / cg;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  const int ch0 = g * 8;
+  const int o = blockIdx.y * gstride + ch0;
+  float sc[8], sh[8], wr[8][COUT];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[o + j];
+    sh[j] = shift[o + j];
+#pragma unroll
+    for (int k = 0; k < COUT; ++k) wr[j][k] = wh[(ch0 + j) * COUT + k];
+  }
+  const long long base = (long long)blockIdx.y * pixels_per_group;
+  const long long stride = (long long)gridDim.x * rows;
+  // block-uniform loop (every lane takes part in the shuffles); lanes past the end are masked
+  for (long long pb = (long long)blockIdx.x * rows; pb < pixels_per_group; pb += EW_UNROLL * stride) {
+    uint4 raw[EW_UNROLL];
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const long long p = pb + u * stride + r;
+      raw[u] = p < pixels_per_group ? ld16(y + (base + p) * y_ld + ch0) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < EW_UNROLL; ++u) {
+      const long long p = pb + u * stride + r;
+      const bool valid = p < pixels_per_group;
+      float v[8], acc[COUT];
+      unpack8(raw[u], v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z = fmaf(v[j], sc[j], sh[j]);
+        v[j] = relu ? fmaxf(z, 0.f) : z;
+      }
+      const uint4 packed = pack8(v);
+      if (valid) st16(a + (base + p) * a_ld + ch0, packed);
+      unpack8(packed, v);              // what the logits layer would read back
+#pragma unroll
+      for (int k = 0; k < COUT; ++k) acc[k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int k = 0; k < COUT; ++k) acc[k] = fmaf(v[j], wr[j][k], acc[k]);
+#pragma unroll
+      for (int k = 0; k < COUT; ++k)
+        for (int s = cg >> 1; s > 0; s >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], s);
+      if (valid && g == 0) {
+#pragma unroll
+        for (int k = 0; k < COUT; ++k) logits[(base + p) * COUT + k] = acc[k] + (bh ? bh[k] : 0.f);
+      }
+    }
+  }
+}
+
 // Same as norm_apply_kernel, and also emits the 2x2/s2 max-pooled tensor from the same read.
 // "pixels" here are pooled pixels of one sample (grid.y = sample).
 template <int G>
@@ -694,6 +759,31 @@ int bsl_norm_apply_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x,
     norm_apply_kernel<2><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
                                                      guide->map, guide->w, guide->w_ld, gstride, sg);
   BSL_LAUNCH_CHECK(ctx, "norm_apply_kernel");
+  return BSL_OK;
+}
+
+int bsl_norm_apply_head(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const float* scale, const float* shift,
+                        void* y, const float* w_head, const float* b_head, int classes, float* logits, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (!x || !scale || !shift || !y || !w_head || !logits) return bsl_fail(ctx, BSL_EINVAL, "norm_apply_head: null buffer");
+  const int cg = d->c / 8;
+  if (cg > 32 || (cg & (cg - 1)) || classes < 2 || classes > 4)
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "norm_apply_head: c=%d in {8,..,256}, classes=%d in 2..4", d->c, classes);
+  const int groups = d->mode ? d->n : 1;
+  const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
+  const EwPlan pl = ew_plan(ctx, ppg, groups, d->c, EW_UNROLL);
+  const dim3 grid(pl.blocks, groups);
+  auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
+  auto yb = reinterpret_cast<__nv_bfloat16*>(y);
+  cudaStream_t s = as_stream(stream);
+  const int gstride = d->mode ? d->c : 0;
+  switch (classes) {
+    case 2: norm_apply_head_kernel<2><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift, gstride, w_head, b_head, logits); break;
+    case 3: norm_apply_head_kernel<3><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift, gstride, w_head, b_head, logits); break;
+    default: norm_apply_head_kernel<4><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift, gstride, w_head, b_head, logits); break;
+  }
+  BSL_LAUNCH_CHECK(ctx, "norm_apply_head_kernel");
   return BSL_OK;
 }
 

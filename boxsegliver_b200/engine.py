@@ -153,6 +153,7 @@ class UNetEngine:
         self._pipe_on = os.environ.get("BSL_PIPE", "0") != "0"
         # measured: the mask loads in the epilogue cost dgrad +0.45 ms, more than the 0.49 ms relu_bwd pass they replace
         self._fuse_relu_bwd = os.environ.get("BSL_FUSE_RELU_BWD", "0") != "0"
+        self._fuse_head = os.environ.get("BSL_FUSE_HEAD", "1") != "0"
         self.aux_stream = ctx.new_stream()
         self._pipe_rows = 2 * len(self.layers)
         self.pipe_buf = self._alloc(2 * self._pipe_rows * 64 * 4).zero()
@@ -599,6 +600,7 @@ class UNetEngine:
         call = ctx.call
         self._pipe_epoch += 1
         piping = self._pipe_active()
+        self._head_done = False
         for idx, L in enumerate(self.layers):
             ctx.tag = L.scope
             if L.kind in ("stem", "conv"):
@@ -644,7 +646,15 @@ class UNetEngine:
                     ctx.record(ev, s)
                     call("bsl_stream_wait_event", st, ev)
                 sp = C.byref(sig) if sig is not None else None
-                if L.pooled is not None:
+                cg = L.cout // 8
+                if (self._fuse_head and nxt is not None and nxt.kind == "logits" and gp is None and L.pooled is None
+                        and cg <= 32 and cg & (cg - 1) == 0 and 2 <= self.cfg.num_classes <= 4):
+                    # last normalised layer: the logits come out of the same pass (no second read of the activation)
+                    call("bsl_norm_apply_head", C.byref(nd), L.y.p, q["scale"], q["shift"], L.a.p,
+                         self._pp(self.W, f"{nxt.scope}/weights"), self._pp(self.W, f"{nxt.scope}/biases"),
+                         C.c_int(self.cfg.num_classes), self.logits.p, s)
+                    self._head_done = True
+                elif L.pooled is not None:
                     call("bsl_norm_apply_pool_mod_pipe", C.byref(nd), C.c_int(L.h), C.c_int(L.w), L.y.p, q["scale"],
                          q["shift"], gp, L.a.p, L.pooled.p, C.c_int(L.pooled.ld), sp, st)
                 else:
@@ -660,7 +670,7 @@ class UNetEngine:
                          self._pp(self.Wbf, f"{L.scope}/weights", BF16), self._pp(self.W, f"{L.scope}/biases"), L.a.p,
                          C.byref(pw) if pw is not None else None, s)
                 done()
-            else:
+            elif not self._head_done:
                 d = self._conv_desc(L)
                 call("bsl_conv2d_head_fprop", C.byref(d), L.x.p, self._pp(self.W, f"{L.scope}/weights"),
                      self._pp(self.W, f"{L.scope}/biases"), self.logits.p, s)

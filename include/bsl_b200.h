@@ -286,6 +286,12 @@ int bsl_norm_apply_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16,
 int bsl_norm_apply_pool_mod(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, const void* x_bf16,
                             const float* scale, const float* shift, const bsl_guide* guide, void* y_bf16,
                             void* pooled_bf16, int pooled_ld, void* stream);
+/* bsl_norm_apply (no guide) that also produces the logits of the 1x1 class convolution that follows the last
+ * normalised layer (NetworksV2/UNet.py:100): logits[p][k] = sum_c act[p][c] * w_head[c][k] + b_head[k], fp32
+ * [n,h,w,classes], bit-identical to bsl_conv2d_head_fprop on the stored activation. c in {8,16,..,256}. */
+int bsl_norm_apply_head(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const float* scale,
+                        const float* shift, void* y_bf16, const float* w_head_f32, const float* b_head_f32,
+                        int classes, float* logits_f32, void* stream);
 /* The same passes publishing image slices of their output through `signal` (bsl_pipe above), for a tensor-core
  * kernel that reads the output while the pass is still running. */
 int bsl_norm_apply_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const float* scale,

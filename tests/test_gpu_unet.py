@@ -232,10 +232,12 @@ def test_image_slice_pipelining_is_bit_identical(ctx):
     n, hw = 8, 64
     images, labels = synthetic.make_batch(n, hw, hw, 3, seed=1401)
     out = []
-    for pipe in (False, True):
+    # also: the logits conv fused into the last normalisation pass (bsl_norm_apply_head) against the two-pass path,
+    # and the transposed-conv ReluGrad fused into the decoder dgrad's epilogue
+    for pipe, head, relu in ((False, False, False), (True, True, False), (False, True, True)):
         eng = UNetEngine(ctx, EngineConfig(batch=n, height=hw, width=hw, weight_decay_rate=1e-5,
                                            loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4)))
-        eng._pipe_on = pipe
+        eng._pipe_on, eng._fuse_head, eng._fuse_relu_bwd = pipe, head, relu
         eng.init_weights(seed=5)
         eng.set_inputs(images, labels)
         for _ in range(2):
@@ -243,7 +245,8 @@ def test_image_slice_pipelining_is_bit_identical(ctx):
         ctx.check_device()
         out.append((eng.logits.download(np.float32, (n, hw, hw, 3)), eng.read_loss(), eng.get_grads()))
         eng.close()
-    assert np.array_equal(out[0][0], out[1][0])
-    assert out[0][1] == out[1][1]
-    for k, g in out[0][2].items():
-        assert np.array_equal(g, out[1][2][k]), k
+    for other in out[1:]:
+        assert np.array_equal(out[0][0], other[0])
+        assert out[0][1] == other[1]
+        for k, g in out[0][2].items():
+            assert np.array_equal(g, other[2][k]), k
