@@ -5,11 +5,13 @@ set -u
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit=$?" | tee -a gpurun_out/pytest_gpu.log
 tail -3 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit=$?"; tail -2 gpurun_out/smoke.log
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit=$?"
 cat gpurun_out/bench.log
 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.log 2>&1; echo "ref exit=$?"
 cat gpurun_out/bench_ref.log
 python tools/step_breakdown.py --json gpurun_out/breakdown.json > gpurun_out/breakdown.log 2>&1; echo "breakdown exit=$?"
+python tools/timeline.py --out gpurun_out/timeline.txt > /dev/null 2>&1; echo "timeline exit=$?"
 head -24 gpurun_out/breakdown.log
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv \
