@@ -128,9 +128,64 @@ def build_unet3d(dtype=np.float64):
     return out
 
 
+ICFG = dict(height=32, width=32, init_channels=64, num_down_samples=4, weight_decay_rate=1e-5,
+            loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4), loss_type="xentropy+dice")
+IN_ = 2
+
+
+def build_unetinter(dtype=np.float64):
+    """One UNetInter training step (image + 2-channel click guide as 5 input channels, instance_norm, xentropy + dice):
+    oracle/gunet_ref.py with prefix "UNetInter", pinned by tests/test_oracle_gunet.py."""
+    from oracle import gunet_ref as GU
+    cfg = GU.unetinter_cfg(channel=3, guide_channel=2, **ICFG)
+    params = GU.init_params(cfg, seed=WEIGHT_SEED)
+    images, labels = synthetic.make_batch(IN_, ICFG["height"], ICFG["width"], 3, seed=DATA_SEED + 3)
+    _, guide = synthetic.make_guides(images, labels, 200, 2, seed=4)
+    inputs = GU.unetinter_inputs(images, guide)
+    tape = GU.forward({k: v.astype(dtype) for k, v in params.items()}, {k: v.astype(dtype) for k, v in inputs.items()},
+                      cfg, True)
+    loss, dl = GU.loss_and_dlogits(tape, labels, cfg)
+    grads = GU.backward(tape, dl, cfg)
+    out = {"images": images, "sp_guide": guide, "labels": labels, "logits": tape.logits.astype(np.float32),
+           "loss": np.float64(loss), "reg_loss": np.float64(GU.regularization_loss(params, cfg))}
+    _grad_summary(out, grads, params)
+    return out
+
+
+def build_input_stage():
+    """The per-sample input map function (crop, align-corners resize, window, noise, flips, Gaussian guide) on a
+    seeded batch of synthetic 16-bit slices: oracle/input_ref.py, pinned by tests/test_oracle_input.py."""
+    from oracle import input_ref as IR
+    rng = np.random.default_rng(DATA_SEED + 4)
+    n, c, src, out = 3, 3, 96, (48, 64)
+    yy, xx = np.mgrid[0:src, 0:src]
+    slices = (rng.integers(0, 1500, (n, c, src, src)) + 600 + 300 * np.sin(yy / 11.0) * np.cos(xx / 7.0)).astype(np.uint16)
+    seg = (rng.integers(0, 3, (n, src, src)) * 64).astype(np.uint8)
+    bbox = np.array([[3, 5, 70, 60], [10, 0, 50, 96], [0, 20, 96, 40]], np.int32)
+    clip = np.array([[700, 1900], [650, 2100], [800, 1800]], np.float32)
+    present = np.array([[1, 1, 1], [0, 1, 1], [1, 1, 0]], np.uint8)
+    slices[1, 0] = 0
+    slices[2, 2] = 0
+    flips = np.array([0, 1, 3], np.int32)
+    centers = [np.array([[20.0, 30.0]], np.float32), np.zeros((0, 2), np.float32),
+               np.array([[10.0, 5.0], [60.0, 30.0]], np.float32)]
+    stddevs = [np.array([[4.0, 6.0]], np.float32), np.zeros((0, 2), np.float32),
+               np.array([[0.5, 3.0], [8.0, 2.0]], np.float32)]
+    res = [IR.data_processing_train(slices[i], seg[i], bbox[i], clip[i], 64, out, present=present[i], noise_scale=0.05,
+                                    seed=77, offset=5, sample=i, flip=int(flips[i]), centers=centers[i],
+                                    stddevs=stddevs[i], with_guide=True) for i in range(n)]
+    return {"slices": slices, "seg": seg, "bbox": bbox, "clip": clip, "present": present, "flips": flips,
+            "centers": np.stack([np.pad(ci, ((0, 2 - len(ci)), (0, 0)), constant_values=-1) for ci in centers]),
+            "stddevs": np.stack([np.pad(si, ((0, 2 - len(si)), (0, 0)), constant_values=1) for si in stddevs]),
+            "n_centers": np.array([len(ci) for ci in centers], np.int32),
+            "images": np.stack([r[0] for r in res]), "labels": np.stack([r[1] for r in res]),
+            "guide": np.stack([r[2] for r in res])}
+
+
 if __name__ == "__main__":
     here = os.path.dirname(os.path.abspath(__file__))
-    for name, fn in (("unet2d_step.npz", build), ("gunet_step.npz", build_gunet), ("unet3d_step.npz", build_unet3d)):
+    for name, fn in (("unet2d_step.npz", build), ("gunet_step.npz", build_gunet), ("unet3d_step.npz", build_unet3d),
+                     ("unetinter_step.npz", build_unetinter), ("input_stage.npz", build_input_stage)):
         path = os.path.join(here, name)
         np.savez_compressed(path, **fn())
         print("wrote", path, os.path.getsize(path), "bytes")

@@ -118,6 +118,65 @@ def test_unet3d_oracle_reproduces_golden_vectors():
     _check_oracle_against(gold, now)
 
 
+def test_unetinter_oracle_reproduces_golden_vectors():
+    gold = dict(np.load(os.path.join(GDIR, "unetinter_step.npz"), allow_pickle=False))
+    now = G.build_unetinter()
+    for k in ("images", "sp_guide", "labels"):
+        assert np.array_equal(now[k], gold[k]), k
+    _check_oracle_against(gold, now)
+
+
+def test_input_stage_oracle_reproduces_golden_vectors():
+    gold = dict(np.load(os.path.join(GDIR, "input_stage.npz"), allow_pickle=False))
+    now = G.build_input_stage()
+    for k in ("slices", "seg", "bbox", "flips", "images", "labels"):        # fp32 single-rounded ops: bit-exact
+        assert np.array_equal(now[k], gold[k]), k
+    assert np.allclose(now["guide"], gold["guide"], rtol=0, atol=1e-6)       # np.exp may differ in the last ulp
+    assert gold["images"].shape == (3, 48, 64, 3) and np.all(gold["images"][1, ..., 0] == 0)
+
+
+@pytest.mark.gpu
+def test_input_stage_against_golden_vectors(ctx):
+    from boxsegliver_b200.input_pipeline import DeviceInputStage
+    gold = dict(np.load(os.path.join(GDIR, "input_stage.npz"), allow_pickle=False))
+    n, c, src = gold["slices"].shape[:3]
+    H, W = gold["images"].shape[1:3]
+    st = DeviceInputStage(ctx, n, c, (src, src), (H, W), noise_scale=0.05, seed=77, max_centers=2, with_guide=True)
+    st.step = 5
+    k = gold["n_centers"]
+    st.stage(gold["slices"], gold["seg"], gold["bbox"], gold["clip"], 64, gold["present"], gold["flips"],
+             [gold["centers"][i, :k[i]] for i in range(n)], [gold["stddevs"][i, :k[i]] for i in range(n)])
+    bi, bl, bg = ctx.alloc(n * H * W * c * 4), ctx.alloc(n * H * W * 4), ctx.alloc(n * H * W * 4)
+    st.run(bi, bl, bg)
+    ctx.check_device()
+    assert np.array_equal(bi.download(np.float32, (n, H, W, c)), gold["images"])
+    assert np.array_equal(bl.download(np.int32, (n, H, W)), gold["labels"])
+    assert np.allclose(bg.download(np.float32, (n, H, W, 1)), gold["guide"], rtol=0, atol=1e-6)
+    for b in (bi, bl, bg):
+        b.free()
+    st.close()
+
+
+@pytest.mark.gpu
+def test_unetinter_engine_against_golden_vectors(ctx):
+    from boxsegliver_b200.gunet_engine import UNetInterConfig, UNetInterEngine
+    from oracle import gunet_ref as GU
+    gold = dict(np.load(os.path.join(GDIR, "unetinter_step.npz"), allow_pickle=False))
+    params = GU.init_params(GU.unetinter_cfg(channel=3, guide_channel=2, **G.ICFG), seed=G.WEIGHT_SEED)
+    eng = UNetInterEngine(ctx, UNetInterConfig(batch=G.IN_, channel=3, guide_channel=2, **G.ICFG))
+    eng.set_weights(params)
+    eng.set_inputs(gold["images"], gold["labels"], gold["sp_guide"])
+    eng.forward(True)
+    eng.loss_backward()
+    ctx.check_device()
+    logits = eng.logits.download(np.float32, gold["logits"].shape)
+    grads = eng.get_grads()
+    eng.optimizer_step(G.LR)
+    data_loss, reg = eng.read_loss()
+    eng.close()
+    _check_engine_against(gold, logits, data_loss, reg, grads)
+
+
 def _check_engine_against(gold, logits, data_loss, reg, grads):
     assert rel(logits, gold["logits"]) < 5e-2
     assert abs(data_loss - float(gold["loss"])) < 2e-2 * abs(float(gold["loss"]))
