@@ -838,6 +838,112 @@ int bsl_norm_apply_pool(bsl_ctx* ctx, const bsl_norm_desc* d, int h, int w, cons
   return bsl_norm_apply_pool_mod(ctx, d, h, w, x, scale, shift, nullptr, y, pooled, pooled_ld, stream);
 }
 
+}  // extern "C"
+
+namespace {
+// The un-guided backward sums with 4 channels (8 bytes per tensor) per thread instead of 8: the 16-byte version
+// needs 126 registers (512 threads per SM) and reads at 4.1-4.8 TB/s; a read-only stream reaches 7.1 TB/s
+// (profiles/r01_hbm_read_probe.log). Same partial layout as pixel_reduce_kernel with K = 2 ([group][block][2][c]),
+// finished by pixel_reduce_final_kernel in block order: deterministic, no atomics.
+template <int U>
+__global__ void __launch_bounds__(256, 4)
+norm_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ da, int da_ld,
+                        const float* __restrict__ mean, const float* __restrict__ rstd,
+                        const float* __restrict__ scale, const float* __restrict__ shift, int c, int relu,
+                        long long pixels_per_group, long long ppb, float* __restrict__ part) {
+  extern __shared__ float sm[];   // [rows][2][c]
+  const int cg = c / 4;
+  const int rows = blockDim.x / cg;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  const int group = blockIdx.y;
+  const int ch0 = g * 4;
+  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (r < rows) {
+    float sc[4], sh[4], rs[4], mr[4];
+    const int o = group * c + ch0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sc[j] = scale[o + j];
+      sh[j] = shift[o + j];
+      rs[j] = rstd[o + j];
+      mr[j] = mean[o + j] * rstd[o + j];
+    }
+    const long long p0 = blockIdx.x * ppb, p1 = min(pixels_per_group, p0 + ppb);
+    const long long base = (long long)group * pixels_per_group;
+    auto one = [&](const uint2& ry, const uint2& rd) {
+      const __nv_bfloat162* hy = reinterpret_cast<const __nv_bfloat162*>(&ry);
+      const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&rd);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 v = __bfloat1622float2(hy[h]), d2 = __bfloat1622float2(hd[h]);
+        const float vv[2] = {v.x, v.y}, dd[2] = {d2.x, d2.y};
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int j = 2 * h + t;
+          const float z = fmaf(vv[t], sc[j], sh[j]);
+          const float dz = (!relu || z > 0.f) ? dd[t] : 0.f;
+          const float xh = fmaf(vv[t], rs[j], -mr[j]);
+          a0[j] += dz;
+          a1[j] = fmaf(dz, xh, a1[j]);
+        }
+      }
+    };
+    long long p = p0 + r;
+    for (; p + (long long)(U - 1) * rows < p1; p += (long long)U * rows) {
+      uint2 ry[U], rd[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ry[u] = *reinterpret_cast<const uint2*>(y + (base + p + (long long)u * rows) * y_ld + ch0);
+        rd[u] = *reinterpret_cast<const uint2*>(da + (base + p + (long long)u * rows) * da_ld + ch0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) one(ry[u], rd[u]);
+    }
+    for (; p < p1; p += rows)
+      one(*reinterpret_cast<const uint2*>(y + (base + p) * y_ld + ch0),
+          *reinterpret_cast<const uint2*>(da + (base + p) * da_ld + ch0));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sm[(r * 2 + 0) * c + ch0 + j] = a0[j];
+      sm[(r * 2 + 1) * c + ch0 + j] = a1[j];
+    }
+  }
+  __syncthreads();
+  float* out = part + ((long long)group * gridDim.x + blockIdx.x) * 2 * c;
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) {
+    float s = 0.f;
+    for (int rr = 0; rr < rows; ++rr) s += sm[rr * 2 * c + i];
+    out[i] = s;
+  }
+}
+
+int run_bwd_reduce4(bsl_ctx* ctx, const bsl_norm_desc* d, const __nv_bfloat16* xb, const __nv_bfloat16* db, int dy_ld,
+                    const float* mean, const float* rstd, const float* scale, const float* shift, long long ppg,
+                    int groups, double* sums, cudaStream_t stream) {
+  const int c = d->c, cg = c / 4;
+  const int rows = 256 / cg;
+  const int threads = rows * cg;
+  long long want = (ppg * c + 32767) / 32768;
+  long long cap = (8LL * ctx->sm_count + groups - 1) / groups;   // two waves of four resident blocks
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  const int blocks = (int)want;
+  const long long ppb = (ppg + blocks - 1) / blocks;
+  float* part = nullptr;
+  int rc = bsl_scratch(ctx, (size_t)groups * blocks * 2 * c * sizeof(float), &part, stream);
+  if (rc) return rc;
+  const size_t smem = (size_t)rows * 2 * c * sizeof(float);
+  norm_bwd_reduce4_kernel<4><<<dim3(blocks, groups), threads, smem, stream>>>(xb, d->x_ld, db, dy_ld, mean, rstd, scale,
+                                                                            shift, c, d->relu, ppg, ppb, part);
+  BSL_LAUNCH_CHECK(ctx, "norm_bwd_reduce4_kernel");
+  pixel_reduce_final_kernel<<<dim3((2 * c + 31) / 32, groups), 256, 0, stream>>>(part, blocks, 2 * c, sums);
+  BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel");
+  return BSL_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int bsl_norm_bwd_reduce_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
                             const float* mean, const float* rstd, const float* scale, const float* shift,
                             const bsl_guide* guide, double* sums, void* stream) {
@@ -852,6 +958,9 @@ int bsl_norm_bwd_reduce_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x,
   auto xb = reinterpret_cast<const __nv_bfloat16*>(x);
   auto db = reinterpret_cast<const __nv_bfloat16*>(dy);
   if (G == 0) {
+    static const int slim = getenv("BSL_BWD_REDUCE4") ? atoi(getenv("BSL_BWD_REDUCE4")) : 1;
+    if (slim && d->c % 4 == 0 && d->c <= 1024 && 256 % (d->c / 4) == 0 && d->x_ld % 4 == 0 && dy_ld % 4 == 0)
+      return run_bwd_reduce4(ctx, d, xb, db, dy_ld, mean, rstd, scale, shift, ppg, groups, sums, as_stream(stream));
     BwdFG<0> f{nullptr, nullptr, 0, xb, db, mean, rstd, scale, shift, d->x_ld, dy_ld, d->c, d->relu};
     return run_pixel_reduce(ctx, f, ppg, groups, d->c, sums, as_stream(stream));
   }
