@@ -71,4 +71,7 @@ size_t bsl_conv3d_halo_wgrad_ws(bsl_ctx* ctx, const bsl_conv3d_desc* d);
 int bsl_conv3d_halo_wgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x, const void* dy, float* dw, void* workspace,
                           size_t workspace_bytes, cudaStream_t s);
 
+// Forces the lazily loaded slice-publishing kernels of norm.cu into the context (see the definition).
+void bsl_preload_pipe_kernels();
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }

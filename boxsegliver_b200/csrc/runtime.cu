@@ -93,6 +93,7 @@ int bsl_init(int device, bsl_ctx** out) {
     delete ctx;
     return BSL_ECUDA;
   }
+  bsl_preload_pipe_kernels();
   *out = ctx;
   return BSL_OK;
 }
