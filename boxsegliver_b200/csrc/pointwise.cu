@@ -115,12 +115,98 @@ int bsl_channel_sum_bf16(bsl_ctx* ctx, const void* x, long long pixels, int c, i
   return BSL_OK;
 }
 
+namespace {
+// ReluBiasF with 4 channels (8 bytes) per thread: 3 streams need the extra resident threads (norm.cu, the
+// normalisation-backward kernels). Partials [block][c] -> pixel_reduce_final_kernel (fixed order) -> fp32.
+template <int U>
+__global__ void __launch_bounds__(256, 4)
+relu_bwd_bias4_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ dy, int dy_ld,
+                      __nv_bfloat16* __restrict__ out, int o_ld, int c, long long pixels, long long ppb,
+                      float* __restrict__ part) {
+  extern __shared__ float sm[];   // [rows][c]
+  const int cg = c / 4;
+  const int rows = blockDim.x / cg;
+  const int g = threadIdx.x % cg, r = threadIdx.x / cg;
+  const int ch0 = g * 4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  auto one = [&](const uint2& ry, const uint2& rd, long long p) {
+    const __nv_bfloat162* hy = reinterpret_cast<const __nv_bfloat162*>(&ry);
+    const __nv_bfloat162* hd = reinterpret_cast<const __nv_bfloat162*>(&rd);
+    uint2 o2;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o2);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float2 v = __bfloat1622float2(hy[h]);
+      float2 d = __bfloat1622float2(hd[h]);
+      d.x = v.x > 0.f ? d.x : 0.f;
+      d.y = v.y > 0.f ? d.y : 0.f;
+      acc[2 * h] += d.x;
+      acc[2 * h + 1] += d.y;
+      ho[h] = __floats2bfloat162_rn(d.x, d.y);
+    }
+    *reinterpret_cast<uint2*>(out + p * o_ld + ch0) = o2;
+  };
+  if (r < rows) {
+    const long long p0 = blockIdx.x * ppb, p1 = min(pixels, p0 + ppb);
+    long long p = p0 + r;
+    for (; p + (long long)(U - 1) * rows < p1; p += (long long)U * rows) {
+      uint2 ry[U], rd[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ry[u] = *reinterpret_cast<const uint2*>(y + (p + (long long)u * rows) * y_ld + ch0);
+        rd[u] = *reinterpret_cast<const uint2*>(dy + (p + (long long)u * rows) * dy_ld + ch0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) one(ry[u], rd[u], p + (long long)u * rows);
+    }
+    for (; p < p1; p += rows)
+      one(*reinterpret_cast<const uint2*>(y + p * y_ld + ch0), *reinterpret_cast<const uint2*>(dy + p * dy_ld + ch0), p);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sm[r * c + ch0 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    float t = 0.f;
+    for (int rr = 0; rr < rows; ++rr) t += sm[rr * c + i];
+    part[(long long)blockIdx.x * c + i] = t;
+  }
+}
+}  // namespace
+
+namespace bsl {
+__global__ void pixel_reduce_final_kernel(const float* __restrict__ part, int blocks, int kc, double* __restrict__ out);
+}
+
 extern "C" int bsl_relu_bwd_bias(bsl_ctx* ctx, long long pixels, int c, const void* y, int y_ld, const void* dy,
                                  int dy_ld, void* out, int out_ld, float* dbias, void* stream) {
   if (!ctx) return BSL_EINVAL;
   if (!y || !dy || !out || !dbias) return bsl_fail(ctx, BSL_EINVAL, "relu_bwd_bias: null buffer");
   if (c % 8 || y_ld % 8 || dy_ld % 8 || out_ld % 8) return bsl_fail(ctx, BSL_EUNSUPPORTED, "relu_bwd_bias: c%%8");
   cudaStream_t s = as_stream(stream);
+  static const int slim = getenv("BSL_RELU_BIAS4") ? atoi(getenv("BSL_RELU_BIAS4")) : 1;
+  if (slim && c <= 1024 && 256 % (c / 4) == 0) {
+    const int cg = c / 4, rows = 256 / cg;
+    long long want = (pixels * c + 32767) / 32768;
+    const long long cap = 8LL * ctx->sm_count;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    const int blocks = (int)want;
+    const long long ppb = (pixels + blocks - 1) / blocks;
+    float* base = nullptr;
+    const size_t pbytes = ((size_t)blocks * c * sizeof(float) + 15) & ~(size_t)15;
+    int rc = bsl::bsl_scratch(ctx, pbytes + (size_t)c * sizeof(double) + 16, &base, s);
+    if (rc) return rc;
+    double* tmp = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + pbytes);
+    relu_bwd_bias4_kernel<4><<<blocks, rows * cg, (size_t)rows * c * sizeof(float), s>>>(
+        reinterpret_cast<const __nv_bfloat16*>(y), y_ld, reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld,
+        reinterpret_cast<__nv_bfloat16*>(out), out_ld, c, pixels, ppb, base);
+    BSL_LAUNCH_CHECK(ctx, "relu_bwd_bias4_kernel");
+    bsl::pixel_reduce_final_kernel<<<dim3((c + 31) / 32, 1), 256, 0, s>>>(base, blocks, c, tmp);
+    BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel");
+    f64_to_f32_kernel<<<(c + 127) / 128, 128, 0, s>>>(tmp, dbias, c);
+    BSL_LAUNCH_CHECK(ctx, "f64_to_f32_kernel");
+    return BSL_OK;
+  }
   ReluBiasF f{reinterpret_cast<const __nv_bfloat16*>(y), reinterpret_cast<const __nv_bfloat16*>(dy),
               reinterpret_cast<__nv_bfloat16*>(out), y_ld, dy_ld, out_ld, c / 8};
   bsl::ReducePlan p = bsl::plan_reduce(ctx, pixels, 1, c, 1);

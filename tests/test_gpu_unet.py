@@ -249,4 +249,9 @@ def test_image_slice_pipelining_is_bit_identical(ctx):
         assert np.array_equal(out[0][0], other[0])
         assert out[0][1] == other[1]
         for k, g in out[0][2].items():
-            assert np.array_equal(g, other[2][k]), k
+            if k.endswith("Conv2d_transpose/biases"):
+                # the bias gradient is a sum over pixels: the fused-ReluGrad schedule takes it from the filter-gradient
+                # call's reduction, the default one from the ReluGrad pass (different fixed summation order)
+                assert np.allclose(g, other[2][k], rtol=1e-4, atol=1e-7), k
+            else:
+                assert np.array_equal(g, other[2][k]), k
