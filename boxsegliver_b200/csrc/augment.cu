@@ -57,6 +57,7 @@ __device__ __forceinline__ float guide_at(int yy, int xx, const float* ctr, cons
 __global__ void input_stage_kernel(bsl_input_desc d, bsl_input_params p, const unsigned short* __restrict__ slices,
                                    const unsigned char* __restrict__ seg, float* __restrict__ images,
                                    int* __restrict__ labels, float* __restrict__ sp_guide) {
+  bsl::pdl_enter();
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long per = (long long)d.out_h * d.out_w;
   if (t >= per * d.n) return;
@@ -122,7 +123,7 @@ extern "C" int bsl_input_stage(bsl_ctx* ctx, const bsl_input_desc* d, const bsl_
     return bsl_fail(ctx, BSL_EINVAL, "input_stage: sp_guide needs centers, stddevs, n_centers");
   const long long total = (long long)d->n * d->out_h * d->out_w;
   const unsigned blocks = (unsigned)((total + 255) / 256);
-  input_stage_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*d, *p, reinterpret_cast<const unsigned short*>(slices_u16),
+  bsl_launch(input_stage_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), *d, *p, reinterpret_cast<const unsigned short*>(slices_u16),
                                                             reinterpret_cast<const unsigned char*>(seg_u8), images, labels,
                                                             sp_guide);
   BSL_LAUNCH_CHECK(ctx, "input_stage_kernel");

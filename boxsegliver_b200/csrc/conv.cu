@@ -34,7 +34,7 @@ int launch_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const I
     BSL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, IGEMM_THREADS, smem, stream>>>(a, b, args);
+  bsl_launch(kern, dim3(grid), dim3(IGEMM_THREADS), smem, stream, a, b, args);
   BSL_LAUNCH_CHECK(ctx, "igemm_kernel launch");
   return BSL_OK;
 }
@@ -156,6 +156,7 @@ SplitPlan plan_split(bsl_ctx* ctx, int mn_tiles, int k_tiles) {
 
 __global__ void reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, long long n,
                                      int splits) {
+  bsl::pdl_enter();
   long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float4 acc = *reinterpret_cast<const float4*>(part + i);
@@ -168,6 +169,7 @@ __global__ void reduce_splits_kernel(const float* __restrict__ part, float* __re
 
 __global__ void reduce_splits_strided_kernel(const float* __restrict__ part, float* __restrict__ out, long long n,
                                              int splits, long long stride) {
+  bsl::pdl_enter();
   long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float4 acc = *reinterpret_cast<const float4*>(part + i);
@@ -182,7 +184,7 @@ int reduce_splits_strided(bsl_ctx* ctx, const float* part, float* out, long long
                           cudaStream_t s) {
   const int threads = 256;
   const long long blocks = (n / 4 + threads - 1) / threads;
-  reduce_splits_strided_kernel<<<(unsigned)blocks, threads, 0, s>>>(part, out, n, splits, stride);
+  bsl_launch(reduce_splits_strided_kernel, dim3((unsigned)blocks), dim3(threads), 0, s, part, out, n, splits, stride);
   BSL_LAUNCH_CHECK(ctx, "reduce_splits_strided_kernel");
   return BSL_OK;
 }
@@ -190,7 +192,7 @@ int reduce_splits_strided(bsl_ctx* ctx, const float* part, float* out, long long
 int reduce_splits(bsl_ctx* ctx, const float* part, float* out, long long n, int splits, cudaStream_t s) {
   int threads = 256;
   long long blocks = (n / 4 + threads - 1) / threads;
-  reduce_splits_kernel<<<(unsigned)blocks, threads, 0, s>>>(part, out, n, splits);
+  bsl_launch(reduce_splits_kernel, dim3((unsigned)blocks), dim3(threads), 0, s, part, out, n, splits);
   BSL_LAUNCH_CHECK(ctx, "reduce_splits_kernel");
   return BSL_OK;
 }
@@ -216,7 +218,7 @@ int launch_halo_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, co
     BSL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, CH_THREADS, smem, stream>>>(a, b, o ? *o : a, args);
+  bsl_launch(kern, dim3(grid), dim3(CH_THREADS), smem, stream, a, b, o ? *o : a, args);
   BSL_LAUNCH_CHECK(ctx, "conv_halo_kernel launch");
   return BSL_OK;
 }
@@ -234,7 +236,7 @@ int launch_halo_res_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b
     BSL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = smem;
   }
-  kern<<<grid, CH_THREADS, smem, stream>>>(a, b, a, args);
+  bsl_launch(kern, dim3(grid), dim3(CH_THREADS), smem, stream, a, b, a, args);
   BSL_LAUNCH_CHECK(ctx, "conv_halo_kernel (resident filter) launch");
   return BSL_OK;
 }
@@ -475,7 +477,7 @@ int conv2d_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const v
     BSL_CUDA(ctx, cudaFuncSetAttribute(wgrad_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_BYTES));
     configured = true;
   }
-  wgrad_halo2_kernel<<<dim3(d->cin / 64, d->cout / 128, p.splits_a + p.splits_b), WG_THREADS, WG2_SMEM_BYTES, stream>>>(
+  bsl_launch(wgrad_halo2_kernel, dim3(dim3(d->cin / 64, d->cout / 128, p.splits_a + p.splits_b)), dim3(WG_THREADS), WG2_SMEM_BYTES, stream, 
       tx, ty, a);
   BSL_LAUNCH_CHECK(ctx, "wgrad_halo2_kernel launch");
   if (p.splits_a > 1 && (rc = reduce_splits(ctx, a.out_a, dw, 6 * per_tap, p.splits_a, stream))) return rc;
@@ -511,6 +513,7 @@ int bsl_debug_set(bsl_ctx* ctx, int key, int value) {
         g_dbg_waits = nullptr;
       }
       return BSL_OK;
+    case 4: bsl_pdl_set(value); return BSL_OK;   // programmatic dependent launch on / off (internal.h)
   }
   return bsl_fail(ctx, BSL_EINVAL, "debug_set: unknown key %d", key);
 }
@@ -566,7 +569,7 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
            : launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
   if (rc) return rc;
   const int kc = 2 * d->cout;
-  pixel_reduce_final_kernel<<<dim3((kc + 31) / 32, 1), 256, 0, stream>>>(part, pl.slots, kc, sums);
+  bsl_launch(pixel_reduce_final_kernel, dim3(dim3((kc + 31) / 32, 1)), dim3(256), 0, stream, part, pl.slots, kc, sums);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel (conv statistics)");
   return BSL_OK;
 }
@@ -762,7 +765,7 @@ int bsl_conv2d_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, cons
                                          WG_SMEM_BYTES));
       configured = true;
     }
-    wgrad_halo_kernel<<<dim3(d->cin / 64, d->cout / 64, p.splits), WG_THREADS, WG_SMEM_BYTES, as_stream(stream)>>>(
+    bsl_launch(wgrad_halo_kernel, dim3(dim3(d->cin / 64, d->cout / 64, p.splits)), dim3(WG_THREADS), WG_SMEM_BYTES, as_stream(stream), 
         tx, ty, a);
     BSL_LAUNCH_CHECK(ctx, "wgrad_halo_kernel launch");
     if (p.splits > 1)
@@ -1203,8 +1206,7 @@ int bsl_conv3d_halo_wgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x,
       BSL_CUDA(ctx, cudaFuncSetAttribute(wgrad_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_BYTES));
       configured = true;
     }
-    wgrad_halo2_kernel<<<dim3(d->cin / 64, d->cout / 128, d->kd * (q.splits_a + q.splits_b)), WG_THREADS, WG2_SMEM_BYTES,
-                         stream>>>(tx, ty, a);
+    bsl_launch(wgrad_halo2_kernel, dim3(dim3(d->cin / 64, d->cout / 128, d->kd * (q.splits_a + q.splits_b))), dim3(WG_THREADS), WG2_SMEM_BYTES, stream, tx, ty, a);
     BSL_LAUNCH_CHECK(ctx, "wgrad_halo2_kernel launch (3-D)");
     for (int k = 0; k < d->kd; ++k) {   // partial[split][kd][taps] -> dW[kd][9]: split stride = kd * taps * per_tap
       if (!direct_a && (rc = reduce_splits_strided(ctx, a.out_a + (long long)k * 6 * per_tap, dw + (long long)k * 9 * per_tap,
@@ -1235,7 +1237,7 @@ int bsl_conv3d_halo_wgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x,
     BSL_CUDA(ctx, cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM_BYTES));
     configured1 = true;
   }
-  wgrad_halo_kernel<<<dim3(d->cin / 64, d->cout / 64, d->kd * p.splits), WG_THREADS, WG_SMEM_BYTES, stream>>>(tx, ty, a);
+  bsl_launch(wgrad_halo_kernel, dim3(dim3(d->cin / 64, d->cout / 64, d->kd * p.splits)), dim3(WG_THREADS), WG_SMEM_BYTES, stream, tx, ty, a);
   BSL_LAUNCH_CHECK(ctx, "wgrad_halo_kernel launch (3-D)");
   if (p.splits > 1) return reduce_splits(ctx, ws, dw, (long long)d->kd * 9 * per_tap, p.splits, stream);
   return BSL_OK;

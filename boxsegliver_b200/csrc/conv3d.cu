@@ -31,7 +31,7 @@ int launch3_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const 
     BSL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  kern<<<grid, IGEMM_THREADS, smem, stream>>>(a, b, args);
+  bsl_launch(kern, dim3(grid), dim3(IGEMM_THREADS), smem, stream, a, b, args);
   BSL_LAUNCH_CHECK(ctx, "igemm_kernel launch (3-D)");
   return BSL_OK;
 }
@@ -138,6 +138,7 @@ SplitPlan plan_split(bsl_ctx* ctx, int mn_tiles, int k_tiles) {
 }
 
 __global__ void reduce_splits3_kernel(const float* __restrict__ part, float* __restrict__ out, long long n, int splits) {
+  bsl::pdl_enter();
   long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float4 acc = *reinterpret_cast<const float4*>(part + i);
@@ -151,7 +152,7 @@ __global__ void reduce_splits3_kernel(const float* __restrict__ part, float* __r
 int reduce_splits3(bsl_ctx* ctx, const float* part, float* out, long long n, int splits, cudaStream_t s) {
   const int threads = 256;
   const long long blocks = (n / 4 + threads - 1) / threads;
-  reduce_splits3_kernel<<<(unsigned)blocks, threads, 0, s>>>(part, out, n, splits);
+  bsl_launch(reduce_splits3_kernel, dim3((unsigned)blocks), dim3(threads), 0, s, part, out, n, splits);
   BSL_LAUNCH_CHECK(ctx, "reduce_splits3_kernel");
   return BSL_OK;
 }

@@ -24,6 +24,7 @@ __device__ __forceinline__ float dropout_scale(const bsl_dropout_desc& dd, unsig
 __global__ void fc_fwd_kernel(int n, int cin, int cout, const float* __restrict__ x, const float* __restrict__ w,
                               const float* __restrict__ b, int relu, bsl_dropout_desc dd, int use_dropout,
                               float* __restrict__ y) {
+  bsl::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * cout) return;
   const int s = i / cout, co = i - s * cout;
@@ -38,6 +39,7 @@ __global__ void fc_fwd_kernel(int n, int cin, int cout, const float* __restrict_
 // dpre = dy * d(out)/d(pre): out = relu(pre) * mask / keep, so out > 0 <=> (pre > 0 and kept).
 __global__ void fc_dpre_kernel(int total, const float* __restrict__ y, const float* __restrict__ dy, int relu,
                                float inv_keep, float* __restrict__ dpre) {
+  bsl::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   float g = dy[i];
@@ -47,6 +49,7 @@ __global__ void fc_dpre_kernel(int total, const float* __restrict__ y, const flo
 
 __global__ void fc_dw_kernel(int n, int cin, int cout, const float* __restrict__ x, const float* __restrict__ dpre,
                              float* __restrict__ dw, float* __restrict__ db) {
+  bsl::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (cin + 1) * cout) return;
   const int ci = i / cout, co = i - ci * cout;
@@ -63,6 +66,7 @@ __global__ void fc_dw_kernel(int n, int cin, int cout, const float* __restrict__
 // one warp per (sample, input feature): lanes stride over cout (coalesced rows of w), shuffle tree at the end
 __global__ void fc_dx_kernel(int n, int cin, int cout, const float* __restrict__ dpre, const float* __restrict__ w,
                              float* __restrict__ dx) {
+  bsl::pdl_enter();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= n * cin) return;
   const int s = warp / cin, ci = warp - s * cin;
@@ -74,6 +78,7 @@ __global__ void fc_dx_kernel(int n, int cin, int cout, const float* __restrict__
 }
 
 __global__ void avgpool2x2_f32_kernel(int n, int h, int w, int c, const float* __restrict__ x, float* __restrict__ y) {
+  bsl::pdl_enter();
   const int ho = h / 2, wo = w / 2;
   const long long total = (long long)n * ho * wo * c;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -88,6 +93,7 @@ __global__ void avgpool2x2_f32_kernel(int n, int h, int w, int c, const float* _
 }
 
 __global__ void dropout_mask_kernel(int total, bsl_dropout_desc dd, float* __restrict__ out) {
+  bsl::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < total) out[i] = dropout_scale(dd, (unsigned long long)i);
 }
@@ -113,7 +119,7 @@ int bsl_fc_fwd(bsl_ctx* ctx, const bsl_fc_desc* d, const float* x, const float* 
   if (rc) return rc;
   if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "fc_fwd: null buffer");
   const int total = d->n * d->cout;
-  fc_fwd_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(d->n, d->cin, d->cout, x, w, bias, d->relu,
+  bsl_launch(fc_fwd_kernel, dim3((total + 127) / 128), dim3(128), 0, as_stream(stream), d->n, d->cin, d->cout, x, w, bias, d->relu,
                                                                    d->dropout, d->use_dropout, y);
   BSL_LAUNCH_CHECK(ctx, "fc_fwd_kernel");
   return BSL_OK;
@@ -135,15 +141,15 @@ int bsl_fc_bwd(bsl_ctx* ctx, const bsl_fc_desc* d, const float* x, const float* 
   float* dpre = reinterpret_cast<float*>(workspace);
   cudaStream_t s = as_stream(stream);
   const int total = d->n * d->cout;
-  fc_dpre_kernel<<<(total + 255) / 256, 256, 0, s>>>(total, y, dy, d->relu,
+  bsl_launch(fc_dpre_kernel, dim3((total + 255) / 256), dim3(256), 0, s, total, y, dy, d->relu,
                                                      d->use_dropout ? 1.0f / d->dropout.keep_prob : 1.0f, dpre);
   BSL_LAUNCH_CHECK(ctx, "fc_dpre_kernel");
   const int nw = (d->cin + 1) * d->cout;
-  fc_dw_kernel<<<(nw + 127) / 128, 128, 0, s>>>(d->n, d->cin, d->cout, x, dpre, dw, dbias);
+  bsl_launch(fc_dw_kernel, dim3((nw + 127) / 128), dim3(128), 0, s, d->n, d->cin, d->cout, x, dpre, dw, dbias);
   BSL_LAUNCH_CHECK(ctx, "fc_dw_kernel");
   if (dx) {
     const long long threads = (long long)d->n * d->cin * 32;
-    fc_dx_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(d->n, d->cin, d->cout, dpre, w, dx);
+    bsl_launch(fc_dx_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, s, d->n, d->cin, d->cout, dpre, w, dx);
     BSL_LAUNCH_CHECK(ctx, "fc_dx_kernel");
   }
   return BSL_OK;
@@ -153,7 +159,7 @@ int bsl_dropout_mask(bsl_ctx* ctx, const bsl_dropout_desc* d, size_t n, float* o
   if (!ctx) return BSL_EINVAL;
   if (!d || !out || !(d->keep_prob > 0.f && d->keep_prob <= 1.f) || n > 0x7fffffffu)
     return bsl_fail(ctx, BSL_EINVAL, "dropout_mask: bad argument");
-  dropout_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>((int)n, *d, out);
+  bsl_launch(dropout_mask_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, as_stream(stream), (int)n, *d, out);
   BSL_LAUNCH_CHECK(ctx, "dropout_mask_kernel");
   return BSL_OK;
 }
@@ -167,7 +173,7 @@ int bsl_avgpool2x2_f32(bsl_ctx* ctx, int n, int h, int w, int c, const float* x,
   long long blocks = (total + 255) / 256;
   const long long cap = 16LL * ctx->sm_count;
   if (blocks > cap) blocks = cap;
-  avgpool2x2_f32_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(n, h, w, c, x, y);
+  bsl_launch(avgpool2x2_f32_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), n, h, w, c, x, y);
   BSL_LAUNCH_CHECK(ctx, "avgpool2x2_f32_kernel");
   return BSL_OK;
 }

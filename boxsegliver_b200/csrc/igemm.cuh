@@ -86,6 +86,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tfull = smem_u32(&bars[2 * STAGES]);
   DeviceStatus* st = p.status;
 
+  pdl_trigger();
   if (threadIdx.x == 0) dead = *reinterpret_cast<volatile int*>(&st->error);
   __syncthreads();
   if (dead) return;
@@ -106,6 +107,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // the prologue above touches no data of the previous kernel in the stream
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
 
   // ---- tile coordinates

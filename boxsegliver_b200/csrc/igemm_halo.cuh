@@ -61,6 +61,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const uint32_t tfull = smem_u32(&bars[2 * WG_STAGES]);
   DeviceStatus* st = p.status;
 
+  pdl_trigger();
   if (threadIdx.x == 0) dead = *reinterpret_cast<volatile int*>(&st->error);
   __syncthreads();
   if (dead) return;
@@ -81,6 +82,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // the prologue above touches no data of the previous kernel in the stream
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
 
   const int cb = blockIdx.x, nb = blockIdx.y;
@@ -226,6 +228,7 @@ wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const uint32_t tfull = smem_u32(&bars[2 * WG2_STAGES]);
   DeviceStatus* st = p.status;
 
+  pdl_trigger();
   if (threadIdx.x == 0) dead = *reinterpret_cast<volatile int*>(&st->error);
   __syncthreads();
   if (dead) return;
@@ -246,6 +249,7 @@ wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // the prologue above touches no data of the previous kernel in the stream
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
 
   const int cb = blockIdx.x, nb = blockIdx.y;
@@ -512,6 +516,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t sStage = sB0 + B_STAGES * B_BYTES;                                     // TMA_ST: 2 x 16 KB
   DeviceStatus* st = p.status;
 
+  pdl_trigger();
   if (threadIdx.x == 0) dead = *reinterpret_cast<volatile int*>(&st->error);
   if (STATS) {
     for (int i = threadIdx.x; i < CH_EPI_WARPS * 2 * BN; i += CH_THREADS) s_stats[i] = 0.f;
@@ -545,6 +550,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // the prologue above touches no data of the previous kernel in the stream
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
 
   const int box_w = p.halo ? 10 : 8;

@@ -29,6 +29,7 @@ __device__ __forceinline__ long long flipped_index(const Dims& s, long long i, i
 
 // dst[i] = (accumulate ? dst[i] : 0) + src[flip(i)]
 __global__ void flip_f32_kernel(Dims s, int axes, int accumulate, const float* __restrict__ src, float* __restrict__ dst) {
+  bsl::pdl_enter();
   const long long total = s.n * s.d * s.h * s.w * s.c;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const float v = src[flipped_index(s, i, axes)];
@@ -39,6 +40,7 @@ __global__ void flip_f32_kernel(Dims s, int axes, int accumulate, const float* _
 template <int C>
 __global__ void tta_finalize_kernel(long long pixels, float count, const float* __restrict__ acc, float* __restrict__ avg,
                                     uint8_t* __restrict__ pred) {
+  bsl::pdl_enter();
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < pixels; p += (long long)gridDim.x * blockDim.x) {
     float best = 0.f;
     int arg = 0;
@@ -55,6 +57,7 @@ __global__ void tta_finalize_kernel(long long pixels, float count, const float* 
 // out[0..3] += tp, fp, tn, fn of test = (t == test_value, or t != 0 when test_value < 0) vs ref = (label == ref_value)
 __global__ void confusion_kernel(long long n, const uint8_t* __restrict__ t, int test_value, const int* __restrict__ labels,
                                  int ref_value, unsigned long long* __restrict__ out) {
+  bsl::pdl_enter();
   unsigned long long tp = 0, fp = 0, tn = 0, fn = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const bool a = test_value < 0 ? t[i] != 0 : t[i] == test_value;
@@ -96,7 +99,7 @@ int bsl_flip_f32(bsl_ctx* ctx, long long n, int d, int h, int w, int c, int axes
   if (n <= 0 || d <= 0 || h <= 0 || w <= 0 || c <= 0 || axes < 0 || axes > 7)
     return bsl_fail(ctx, BSL_EINVAL, "flip_f32: bad shape or axes mask %d", axes);
   const Dims s{n, d, h, w, c};
-  flip_f32_kernel<<<grid_for(ctx, n * d * h * w * c), 256, 0, as_stream(stream)>>>(s, axes, accumulate, src, dst);
+  bsl_launch(flip_f32_kernel, dim3(grid_for(ctx, n * d * h * w * c)), dim3(256), 0, as_stream(stream), s, axes, accumulate, src, dst);
   BSL_LAUNCH_CHECK(ctx, "flip_f32_kernel");
   return BSL_OK;
 }
@@ -108,9 +111,9 @@ int bsl_tta_finalize(bsl_ctx* ctx, long long pixels, int classes, int count, con
   const unsigned g = grid_for(ctx, pixels);
   cudaStream_t s = as_stream(stream);
   switch (classes) {
-    case 2: tta_finalize_kernel<2><<<g, 256, 0, s>>>(pixels, (float)count, acc, avg_prob, pred); break;
-    case 3: tta_finalize_kernel<3><<<g, 256, 0, s>>>(pixels, (float)count, acc, avg_prob, pred); break;
-    case 4: tta_finalize_kernel<4><<<g, 256, 0, s>>>(pixels, (float)count, acc, avg_prob, pred); break;
+    case 2: bsl_launch(tta_finalize_kernel<2>, dim3(g), dim3(256), 0, s, pixels, (float)count, acc, avg_prob, pred); break;
+    case 3: bsl_launch(tta_finalize_kernel<3>, dim3(g), dim3(256), 0, s, pixels, (float)count, acc, avg_prob, pred); break;
+    case 4: bsl_launch(tta_finalize_kernel<4>, dim3(g), dim3(256), 0, s, pixels, (float)count, acc, avg_prob, pred); break;
     default: return bsl_fail(ctx, BSL_EUNSUPPORTED, "tta_finalize: classes=%d (2..4)", classes);
   }
   BSL_LAUNCH_CHECK(ctx, "tta_finalize_kernel");
@@ -121,7 +124,7 @@ int bsl_confusion_counts(bsl_ctx* ctx, long long n, const uint8_t* test, int tes
                          unsigned long long* counts4, void* stream) {
   if (!ctx) return BSL_EINVAL;
   if (!test || !labels || !counts4 || n <= 0) return bsl_fail(ctx, BSL_EINVAL, "confusion_counts: bad argument");
-  confusion_kernel<<<grid_for(ctx, n), 256, 0, as_stream(stream)>>>(n, test, test_value, labels, ref_value, counts4);
+  bsl_launch(confusion_kernel, dim3(grid_for(ctx, n)), dim3(256), 0, as_stream(stream), n, test, test_value, labels, ref_value, counts4);
   BSL_LAUNCH_CHECK(ctx, "confusion_kernel");
   return BSL_OK;
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <unordered_map>
 #include <vector>
 #include "../../include/bsl_b200.h"
@@ -43,6 +44,27 @@ int bsl_check_cuda(bsl_ctx* ctx, cudaError_t e, const char* what);
     if (_e != cudaSuccess) return bsl_check_cuda(ctx, _e, what);   \
     ++(ctx)->launches;                                             \
   } while (0)
+
+// Kernel launch with the programmatic-stream-serialization attribute (on by default, BSL_PDL=0 turns it off): the grid may be
+// scheduled while the previous kernel of the stream drains. Every kernel launched through here calls
+// bsl::pdl_wait() (or pdl_enter()) before its first access to global data (ptx.cuh).
+bool bsl_pdl_enabled();
+void bsl_pdl_set(int on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t bsl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = bsl_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
 
 // Encodes (or fetches from the cache) a bf16 tensor map with 128-byte swizzle and zero OOB fill.
 // dims/strides are innermost-first; strides[0] is implied (2 bytes) and ignored.

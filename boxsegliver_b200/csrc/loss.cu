@@ -27,6 +27,7 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
 
 // counts[n][c] = #pixels of image n with label c (labels outside [0, classes) are ignored)
 __global__ void label_counts_kernel(const int* __restrict__ labels, int hw, int classes, int* __restrict__ counts) {
+  bsl::pdl_enter();
   __shared__ int sc[MAXC];
   if (threadIdx.x < MAXC) sc[threadIdx.x] = 0;
   __syncthreads();
@@ -51,6 +52,7 @@ __global__ void label_counts_kernel(const int* __restrict__ labels, int hw, int 
 // pixels with non-zero weight (denominator of SUM_BY_NONZERO_WEIGHTS). One thread; n*classes is tiny.
 __global__ void weight_table_kernel(bsl_loss_desc d, const int* __restrict__ counts, float* __restrict__ wtab,
                                     double* __restrict__ nz_out) {
+  bsl::pdl_enter();
   if (threadIdx.x || blockIdx.x) return;
   double nz = 0.0;
   for (int img = 0; img < d.n; ++img) {
@@ -104,6 +106,7 @@ template <int C>
 __global__ void wxent_kernel(const float* __restrict__ logits, const int* __restrict__ labels, int hw,
                              long long pixels, const float* __restrict__ wtab, const double* __restrict__ nz_p,
                              float loss_scale, float* __restrict__ dlogits, double* __restrict__ part) {
+  bsl::pdl_enter();
   __shared__ double sm[32];
   const double nz = *nz_p;
   const float inv_nz = nz > 0.0 ? (float)(1.0 / nz) : 0.f;
@@ -133,6 +136,7 @@ __global__ void wxent_kernel(const float* __restrict__ logits, const int* __rest
 
 __global__ void wxent_final_kernel(const double* __restrict__ part, int blocks, const double* __restrict__ nz_p,
                                    float* __restrict__ loss) {
+  bsl::pdl_enter();
   if (threadIdx.x || blockIdx.x) return;
   double s = 0.0;
   for (int b = 0; b < blocks; ++b) s += part[b];
@@ -144,6 +148,7 @@ template <int C>
 __global__ void softmax_threshold_kernel(const float* __restrict__ logits, const int* __restrict__ labels, int hw,
                                          long long pixels, float* __restrict__ prob, uint8_t* __restrict__ masks,
                                          uint8_t* __restrict__ argmax, unsigned int* __restrict__ ilr) {
+  bsl::pdl_enter();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long p0 = blockIdx.x * (long long)blockDim.x; p0 < pixels; p0 += stride) {
     const long long p = p0 + threadIdx.x;
@@ -199,6 +204,7 @@ __global__ void softmax_threshold_kernel(const float* __restrict__ logits, const
 template <int C>
 __global__ void dice_reduce_kernel(const float* __restrict__ logits, const int* __restrict__ labels, int hw,
                                    double* __restrict__ part) {
+  bsl::pdl_enter();
   __shared__ double sm[32];
   const int img = blockIdx.y;
   double ai = 0.0, au = 0.0;
@@ -226,6 +232,7 @@ __global__ void dice_reduce_kernel(const float* __restrict__ logits, const int* 
 
 __global__ void dice_final_kernel(const double* __restrict__ part, int blocks, int n, float eps,
                                   double* __restrict__ iu, float* __restrict__ loss) {
+  bsl::pdl_enter();
   if (threadIdx.x || blockIdx.x) return;
   double mean = 0.0;
   for (int img = 0; img < n; ++img) {
@@ -245,6 +252,7 @@ template <int C>
 __global__ void dice_bwd_kernel(const float* __restrict__ logits, const int* __restrict__ labels, int hw,
                                 long long pixels, int n, float eps, const double* __restrict__ iu, float loss_scale,
                                 int accumulate, float* __restrict__ dlogits) {
+  bsl::pdl_enter();
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < pixels;
        p += (long long)gridDim.x * blockDim.x) {
     float lg[C], pr[C], lse, mx;
@@ -310,7 +318,7 @@ int bsl_label_counts(bsl_ctx* ctx, const bsl_loss_desc* d, const int* labels, in
   BSL_CUDA(ctx, cudaMemsetAsync(counts, 0, sizeof(int) * d->n * d->classes, s));
   int bx = (d->hw + 255) / 256;
   if (bx > 64) bx = 64;
-  label_counts_kernel<<<dim3(bx, d->n), 256, 0, s>>>(labels, d->hw, d->classes, counts);
+  bsl_launch(label_counts_kernel, dim3(dim3(bx, d->n)), dim3(256), 0, s, labels, d->hw, d->classes, counts);
   BSL_LAUNCH_CHECK(ctx, "label_counts_kernel");
   return BSL_OK;
 }
@@ -351,14 +359,14 @@ int bsl_wxent_fwd_bwd(bsl_ctx* ctx, const bsl_loss_desc* d, const float* logits,
   if (workspace_bytes < bsl_loss_workspace(ctx, d)) return bsl_fail(ctx, BSL_EWORKSPACE, "wxent: workspace too small");
   cudaStream_t s = as_stream(stream);
   LossWs w = carve(ctx, d, workspace);
-  weight_table_kernel<<<1, 32, 0, s>>>(*d, counts, w.wtab, w.nz);
+  bsl_launch(weight_table_kernel, dim3(1), dim3(32), 0, s, *d, counts, w.wtab, w.nz);
   BSL_LAUNCH_CHECK(ctx, "weight_table_kernel");
   const long long pixels = (long long)d->n * d->hw;
   const unsigned blocks = px_grid(ctx, pixels);
-  CLASS_SWITCH(d->classes, (wxent_kernel<C><<<blocks, 256, 0, s>>>(logits, labels, d->hw, pixels, w.wtab, w.nz,
+  CLASS_SWITCH(d->classes, (bsl_launch(wxent_kernel<C>, dim3(blocks), dim3(256), 0, s, logits, labels, d->hw, pixels, w.wtab, w.nz,
                                                                     d->loss_scale, dlogits, w.part)));
   BSL_LAUNCH_CHECK(ctx, "wxent_kernel");
-  wxent_final_kernel<<<1, 32, 0, s>>>(w.part, (int)blocks, w.nz, loss);
+  bsl_launch(wxent_final_kernel, dim3(1), dim3(32), 0, s, w.part, (int)blocks, w.nz, loss);
   BSL_LAUNCH_CHECK(ctx, "wxent_final_kernel");
   return BSL_OK;
 }
@@ -374,13 +382,13 @@ int bsl_dice_fwd_bwd(bsl_ctx* ctx, const bsl_loss_desc* d, const float* logits, 
   int bx = (d->hw + 255) / 256;
   if (bx > 64) bx = 64;
   const float eps = 1e-8f;
-  CLASS_SWITCH(d->classes, (dice_reduce_kernel<C><<<dim3(bx, d->n), 256, 0, s>>>(logits, labels, d->hw, w.dpart)));
+  CLASS_SWITCH(d->classes, (bsl_launch(dice_reduce_kernel<C>, dim3(dim3(bx, d->n)), dim3(256), 0, s, logits, labels, d->hw, w.dpart)));
   BSL_LAUNCH_CHECK(ctx, "dice_reduce_kernel");
-  dice_final_kernel<<<1, 32, 0, s>>>(w.dpart, bx, d->n, eps, w.iu, loss);
+  bsl_launch(dice_final_kernel, dim3(1), dim3(32), 0, s, w.dpart, bx, d->n, eps, w.iu, loss);
   BSL_LAUNCH_CHECK(ctx, "dice_final_kernel");
   if (dlogits) {
     const long long pixels = (long long)d->n * d->hw;
-    CLASS_SWITCH(d->classes, (dice_bwd_kernel<C><<<px_grid(ctx, pixels), 256, 0, s>>>(
+    CLASS_SWITCH(d->classes, (bsl_launch(dice_bwd_kernel<C>, dim3(px_grid(ctx, pixels)), dim3(256), 0, s, 
                                  logits, labels, d->hw, pixels, d->n, eps, w.iu, d->loss_scale, accumulate, dlogits)));
     BSL_LAUNCH_CHECK(ctx, "dice_bwd_kernel");
   }
@@ -396,7 +404,7 @@ int bsl_softmax_threshold(bsl_ctx* ctx, const bsl_loss_desc* d, const float* log
   cudaStream_t s = as_stream(stream);
   if (ilr) BSL_CUDA(ctx, cudaMemsetAsync(ilr, 0, sizeof(unsigned int) * d->n * (d->classes - 1) * 3, s));
   const long long pixels = (long long)d->n * d->hw;
-  CLASS_SWITCH(d->classes, (softmax_threshold_kernel<C><<<px_grid(ctx, pixels), 256, 0, s>>>(
+  CLASS_SWITCH(d->classes, (bsl_launch(softmax_threshold_kernel<C>, dim3(px_grid(ctx, pixels)), dim3(256), 0, s, 
                                logits, labels, d->hw, pixels, prob, masks, argmax, ilr)));
   BSL_LAUNCH_CHECK(ctx, "softmax_threshold_kernel");
   return BSL_OK;

@@ -17,6 +17,7 @@ namespace bsl {
 // fixed order.
 __global__ void pixel_reduce_final_kernel(const float* __restrict__ part, int blocks, int kc,
                                           double* __restrict__ out) {
+  bsl::pdl_enter();
   __shared__ double sm[8][32];
   const int il = threadIdx.x & 31, q = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + il;
@@ -152,6 +153,7 @@ __global__ void norm_finalize_kernel(int groups, int c, double m, float eps, flo
                                      float* __restrict__ moving_mean, float* __restrict__ moving_var,
                                      float* __restrict__ mean_o, float* __restrict__ rstd_o,
                                      float* __restrict__ scale_o, float* __restrict__ shift_o) {
+  bsl::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= groups * c) return;
   const int g = i / c, ch = i - g * c;
@@ -190,6 +192,7 @@ __global__ void norm_apply_kernel(const __nv_bfloat16* __restrict__ y, int y_ld,
                                   const float* __restrict__ scale, const float* __restrict__ shift,
                                   const float* __restrict__ guide, const float* __restrict__ wsp, int wsp_ld,
                                   int gstride, PipeSignal sig) {
+  bsl::pdl_enter();
   // blockIdx.y = group (instance norm: gstride = c) or image slice of the batch (batch norm, gstride = 0)
   const int cg = c / 8;
   const int rows = blockDim.x / cg;
@@ -256,6 +259,7 @@ __global__ void norm_apply_head_kernel(const __nv_bfloat16* __restrict__ y, int 
                                        const float* __restrict__ scale, const float* __restrict__ shift, int gstride,
                                        const float* __restrict__ wh, const float* __restrict__ bh,
                                        float* __restrict__ logits) {
+  bsl::pdl_enter();
   const int cg = c / 8;                    // power of two <= 32: the lanes of a pixel sit in one warp
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -318,6 +322,7 @@ __global__ void norm_apply_pool_kernel(const __nv_bfloat16* __restrict__ y, int 
                                        int per_sample, int relu, const float* __restrict__ scale,
                                        const float* __restrict__ shift, const float* __restrict__ guide,
                                        const float* __restrict__ wsp, int wsp_ld, PipeSignal sig) {
+  bsl::pdl_enter();
   const int cg = c / 8, ho = h / 2, wo = w / 2;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -375,6 +380,7 @@ __global__ void norm_bwd_finalize_kernel(int groups, int c, double m, const doub
                                          const float* __restrict__ rstd_unused, float* __restrict__ c1,
                                          float* __restrict__ c2, float* __restrict__ dgamma,
                                          float* __restrict__ dbeta) {
+  bsl::pdl_enter();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   double sg = 0.0, sb = 0.0;
@@ -400,6 +406,7 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y
                                       const float* __restrict__ c1, const float* __restrict__ c2,
                                       const float* __restrict__ guide, const float* __restrict__ wsp, int wsp_ld,
                                       int gstride, PipeSignal sig) {
+  bsl::pdl_enter();
   const int cg = c / 8;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -469,6 +476,7 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y
 __global__ void norm_modulate_kernel(int n, int c, const float* __restrict__ gamma_mod, int gm_ld,
                                      const float* __restrict__ sp_bias, float* __restrict__ scale,
                                      float* __restrict__ shift) {
+  bsl::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * c) return;
   const int s = i / c, ch = i - s * c;
@@ -484,6 +492,7 @@ __global__ void norm_bwd_finalize_mod_kernel(int n, int c, int K, double m, cons
                                              float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
                                              float* __restrict__ dbeta, float* __restrict__ dgamma_mod,
                                              float* __restrict__ dw_guide, int dw_ld, float* __restrict__ dbias_guide) {
+  bsl::pdl_enter();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   const double ga = gamma ? (double)gamma[ch] : 1.0, be = beta ? (double)beta[ch] : 0.0;
@@ -511,6 +520,7 @@ __global__ void maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ act, in
                                        const __nv_bfloat16* __restrict__ dpool, int p_ld,
                                        const __nv_bfloat16* __restrict__ dskip, int s_ld,
                                        __nv_bfloat16* __restrict__ out, int o_ld, int n, int h, int w, int c) {
+  bsl::pdl_enter();
   const int cg = c / 8, ho = h / 2, wo = w / 2;
   const long long total = (long long)n * ho * wo * cg;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -555,6 +565,7 @@ __global__ void maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ act, in
 
 __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ dy,
                                 int dy_ld, __nv_bfloat16* __restrict__ out, int o_ld, long long pixels, int c) {
+  bsl::pdl_enter();
   const int cg = c / 8;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -591,6 +602,7 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, c
 
 __global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, int a_ld, const __nv_bfloat16* __restrict__ b,
                                 int b_ld, __nv_bfloat16* __restrict__ out, int o_ld, long long pixels, int c) {
+  bsl::pdl_enter();
   const int cg = c / 8;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -718,7 +730,7 @@ int bsl_norm_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, int is_training, con
   if (bn && (!moving_mean || !moving_var)) return bsl_fail(ctx, BSL_EINVAL, "norm_finalize: moving stats required");
   const double m = d->mode ? (double)d->hw : (double)d->n * d->hw;
   const int total = groups * d->c;
-  norm_finalize_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(
+  bsl_launch(norm_finalize_kernel, dim3((total + 127) / 128), dim3(128), 0, as_stream(stream), 
       groups, d->c, m, d->eps, d->decay, bn && is_training, use_moving, d->center, d->scale, sums, gamma, beta,
       moving_mean, moving_var, mean, rstd, scale, shift);
   BSL_LAUNCH_CHECK(ctx, "norm_finalize_kernel");
@@ -767,13 +779,13 @@ int bsl_norm_apply_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x,
   auto yb = reinterpret_cast<__nv_bfloat16*>(y);
   cudaStream_t s = as_stream(stream);
   if (G == 0)
-    norm_apply_kernel<0><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
+    bsl_launch(norm_apply_kernel<0>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
                                                      nullptr, nullptr, 0, gstride, sg);
   else if (G == 1)
-    norm_apply_kernel<1><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
+    bsl_launch(norm_apply_kernel<1>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
                                                      guide->map, guide->w, guide->w_ld, gstride, sg);
   else
-    norm_apply_kernel<2><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
+    bsl_launch(norm_apply_kernel<2>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift,
                                                      guide->map, guide->w, guide->w_ld, gstride, sg);
   BSL_LAUNCH_CHECK(ctx, "norm_apply_kernel");
   return BSL_OK;
@@ -796,9 +808,9 @@ int bsl_norm_apply_head(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, con
   cudaStream_t s = as_stream(stream);
   const int gstride = d->mode ? d->c : 0;
   switch (classes) {
-    case 2: norm_apply_head_kernel<2><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift, gstride, w_head, b_head, logits); break;
-    case 3: norm_apply_head_kernel<3><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift, gstride, w_head, b_head, logits); break;
-    default: norm_apply_head_kernel<4><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift, gstride, w_head, b_head, logits); break;
+    case 2: bsl_launch(norm_apply_head_kernel<2>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift, gstride, w_head, b_head, logits); break;
+    case 3: bsl_launch(norm_apply_head_kernel<3>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift, gstride, w_head, b_head, logits); break;
+    default: bsl_launch(norm_apply_head_kernel<4>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, yb, d->y_ld, ppg, d->c, d->relu, scale, shift, gstride, w_head, b_head, logits); break;
   }
   BSL_LAUNCH_CHECK(ctx, "norm_apply_head_kernel");
   return BSL_OK;
@@ -838,13 +850,13 @@ int bsl_norm_apply_pool_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, int h, in
   auto pb = reinterpret_cast<__nv_bfloat16*>(pooled);
   cudaStream_t s = as_stream(stream);
   if (G == 0)
-    norm_apply_pool_kernel<0><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, pb, pooled_ld, h, w, d->c, d->mode,
+    bsl_launch(norm_apply_pool_kernel<0>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, yb, d->y_ld, pb, pooled_ld, h, w, d->c, d->mode,
                                                           d->relu, scale, shift, nullptr, nullptr, 0, sg);
   else if (G == 1)
-    norm_apply_pool_kernel<1><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, pb, pooled_ld, h, w, d->c, d->mode,
+    bsl_launch(norm_apply_pool_kernel<1>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, yb, d->y_ld, pb, pooled_ld, h, w, d->c, d->mode,
                                                           d->relu, scale, shift, guide->map, guide->w, guide->w_ld, sg);
   else
-    norm_apply_pool_kernel<2><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, yb, d->y_ld, pb, pooled_ld, h, w, d->c, d->mode,
+    bsl_launch(norm_apply_pool_kernel<2>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, yb, d->y_ld, pb, pooled_ld, h, w, d->c, d->mode,
                                                           d->relu, scale, shift, guide->map, guide->w, guide->w_ld, sg);
   BSL_LAUNCH_CHECK(ctx, "norm_apply_pool_kernel");
   return BSL_OK;
@@ -868,6 +880,7 @@ norm_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __n
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ scale, const float* __restrict__ shift, int c, int relu,
                         long long pixels_per_group, long long ppb, float* __restrict__ part) {
+  bsl::pdl_enter();
   extern __shared__ float sm[];   // [rows][2][c]
   const int cg = c / 4;
   const int rows = blockDim.x / cg;
@@ -943,6 +956,7 @@ norm_bwd_apply4_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv
                        const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ scale, const float* __restrict__ shift,
                        const float* __restrict__ c1, const float* __restrict__ c2, int gstride) {
+  bsl::pdl_enter();
   const int cg = c / 4;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -1016,10 +1030,10 @@ int run_bwd_reduce4(bsl_ctx* ctx, const bsl_norm_desc* d, const __nv_bfloat16* x
   int rc = bsl_scratch(ctx, (size_t)groups * blocks * 2 * c * sizeof(float), &part, stream);
   if (rc) return rc;
   const size_t smem = (size_t)rows * 2 * c * sizeof(float);
-  norm_bwd_reduce4_kernel<4><<<dim3(blocks, groups), threads, smem, stream>>>(xb, d->x_ld, db, dy_ld, mean, rstd, scale,
+  bsl_launch(norm_bwd_reduce4_kernel<4>, dim3(dim3(blocks, groups)), dim3(threads), smem, stream, xb, d->x_ld, db, dy_ld, mean, rstd, scale,
                                                                             shift, c, d->relu, ppg, ppb, part);
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_reduce4_kernel");
-  pixel_reduce_final_kernel<<<dim3((2 * c + 31) / 32, groups), 256, 0, stream>>>(part, blocks, 2 * c, sums);
+  bsl_launch(pixel_reduce_final_kernel, dim3(dim3((2 * c + 31) / 32, groups)), dim3(256), 0, stream, part, blocks, 2 * c, sums);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel");
   return BSL_OK;
 }
@@ -1068,7 +1082,7 @@ int bsl_norm_bwd_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, const double* su
   if (!sums || !c1 || !c2) return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_finalize: null buffer");
   const int groups = d->mode ? d->n : 1;
   const double m = d->mode ? (double)d->hw : (double)d->n * d->hw;
-  norm_bwd_finalize_kernel<<<(d->c + 127) / 128, 128, 0, as_stream(stream)>>>(groups, d->c, m, sums, nullptr, c1, c2,
+  bsl_launch(norm_bwd_finalize_kernel, dim3((d->c + 127) / 128), dim3(128), 0, as_stream(stream), groups, d->c, m, sums, nullptr, c1, c2,
                                                                              dgamma, dbeta);
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_finalize_kernel");
   return BSL_OK;
@@ -1081,7 +1095,7 @@ int bsl_norm_modulate(bsl_ctx* ctx, const bsl_norm_desc* d, const float* gamma_m
   if (d->mode != 1) return bsl_fail(ctx, BSL_EUNSUPPORTED, "norm_modulate: instance_norm layers only");
   if (!scale || !shift || (gamma_mod && gm_ld < d->c)) return bsl_fail(ctx, BSL_EINVAL, "norm_modulate: bad argument");
   const int total = d->n * d->c;
-  norm_modulate_kernel<<<(total + 127) / 128, 128, 0, as_stream(stream)>>>(d->n, d->c, gamma_mod, gm_ld, sp_bias, scale,
+  bsl_launch(norm_modulate_kernel, dim3((total + 127) / 128), dim3(128), 0, as_stream(stream), d->n, d->c, gamma_mod, gm_ld, sp_bias, scale,
                                                                          shift);
   BSL_LAUNCH_CHECK(ctx, "norm_modulate_kernel");
   return BSL_OK;
@@ -1097,7 +1111,7 @@ int bsl_norm_bwd_finalize_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const double
   if (!sums || !c1 || !c2 || guide_channels < 0 || guide_channels > 2 || (gamma_mod && !dgamma_mod) ||
       (guide_channels && (!dw_guide || dw_ld < d->c)))
     return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_finalize_mod: bad argument");
-  norm_bwd_finalize_mod_kernel<<<(d->c + 127) / 128, 128, 0, as_stream(stream)>>>(
+  bsl_launch(norm_bwd_finalize_mod_kernel, dim3((d->c + 127) / 128), dim3(128), 0, as_stream(stream), 
       d->n, d->c, 2 + guide_channels, (double)d->hw, sums, gamma_mod, gm_ld, d->scale ? gamma : nullptr,
       d->center ? beta : nullptr, c1, c2, dgamma, dbeta, dgamma_mod, dw_guide, dw_ld, dbias_guide);
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_finalize_mod_kernel");
@@ -1149,20 +1163,20 @@ int bsl_norm_bwd_apply_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, const void
     const long long cap = (16LL * ctx->sm_count + groups - 1) / groups;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
-    norm_bwd_apply4_kernel<4><<<dim3((unsigned)want, groups), rows4 * cg4, 0, s>>>(
+    bsl_launch(norm_bwd_apply4_kernel<4>, dim3(dim3((unsigned)want, groups)), dim3(rows4 * cg4), 0, s, 
         xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean, rstd, scale, shift, c1, c2, gstride);
     BSL_LAUNCH_CHECK(ctx, "norm_bwd_apply4_kernel");
     return BSL_OK;
   }
   if (G == 0)
-    norm_bwd_apply_kernel<0><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
+    bsl_launch(norm_bwd_apply_kernel<0>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
                                                          rstd, scale, shift, c1, c2, nullptr, nullptr, 0, gstride, sg);
   else if (G == 1)
-    norm_bwd_apply_kernel<1><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
+    bsl_launch(norm_bwd_apply_kernel<1>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
                                                          rstd, scale, shift, c1, c2, guide->map, guide->w, guide->w_ld,
                                                          gstride, sg);
   else
-    norm_bwd_apply_kernel<2><<<grid, pl.threads, 0, s>>>(xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
+    bsl_launch(norm_bwd_apply_kernel<2>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
                                                          rstd, scale, shift, c1, c2, guide->map, guide->w, guide->w_ld,
                                                          gstride, sg);
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_apply_kernel");
@@ -1182,7 +1196,7 @@ int bsl_maxpool2x2_bwd_add(bsl_ctx* ctx, int n, int h, int w, int c, const void*
   if (!act || !dpool || !dact) return bsl_fail(ctx, BSL_EINVAL, "maxpool_bwd: null buffer");
   if ((h & 1) || (w & 1) || c % 8) return bsl_fail(ctx, BSL_EUNSUPPORTED, "maxpool_bwd: h,w even, c%%8==0");
   const long long items = (long long)n * (h / 2) * (w / 2) * (c / 8);
-  maxpool_bwd_add_kernel<<<ew_grid(ctx, items), 256, 0, as_stream(stream)>>>(
+  bsl_launch(maxpool_bwd_add_kernel, dim3(ew_grid(ctx, items)), dim3(256), 0, as_stream(stream), 
       reinterpret_cast<const __nv_bfloat16*>(act), act_ld, reinterpret_cast<const __nv_bfloat16*>(dpool), dpool_ld,
       reinterpret_cast<const __nv_bfloat16*>(dskip), dskip_ld, reinterpret_cast<__nv_bfloat16*>(dact), dact_ld, n, h,
       w, c);
@@ -1196,7 +1210,7 @@ int bsl_add_bf16(bsl_ctx* ctx, long long pixels, int c, const void* a, int a_ld,
   if (!a || !b || !out) return bsl_fail(ctx, BSL_EINVAL, "add_bf16: null buffer");
   if (c % 8 || a_ld % 8 || b_ld % 8 || out_ld % 8) return bsl_fail(ctx, BSL_EUNSUPPORTED, "add_bf16: c, ld %% 8");
   const EwPlan pl = ew_plan(ctx, pixels, 1, c, 2);
-  add_bf16_kernel<<<pl.blocks, pl.threads, 0, as_stream(stream)>>>(
+  bsl_launch(add_bf16_kernel, dim3(pl.blocks), dim3(pl.threads), 0, as_stream(stream), 
       reinterpret_cast<const __nv_bfloat16*>(a), a_ld, reinterpret_cast<const __nv_bfloat16*>(b), b_ld,
       reinterpret_cast<__nv_bfloat16*>(out), out_ld, pixels, c);
   BSL_LAUNCH_CHECK(ctx, "add_bf16_kernel");
@@ -1209,7 +1223,7 @@ int bsl_relu_bwd(bsl_ctx* ctx, long long pixels, int c, const void* y, int y_ld,
   if (!y || !dy || !out) return bsl_fail(ctx, BSL_EINVAL, "relu_bwd: null buffer");
   if (c % 8) return bsl_fail(ctx, BSL_EUNSUPPORTED, "relu_bwd: c%%8");
   const EwPlan pl = ew_plan(ctx, pixels, 1, c, EW_UNROLL);
-  relu_bwd_kernel<<<pl.blocks, pl.threads, 0, as_stream(stream)>>>(
+  bsl_launch(relu_bwd_kernel, dim3(pl.blocks), dim3(pl.threads), 0, as_stream(stream), 
       reinterpret_cast<const __nv_bfloat16*>(y), y_ld, reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld,
       reinterpret_cast<__nv_bfloat16*>(out), out_ld, pixels, c);
   BSL_LAUNCH_CHECK(ctx, "relu_bwd_kernel");

@@ -15,6 +15,7 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, 
                             float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, size_t n, float lr_t,
                             float beta1, float beta2, float eps, float l2, float gscale,
                             double* __restrict__ sq_part) {
+  bsl::pdl_enter();
   __shared__ double sm[32];
   double sq = 0.0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -44,6 +45,7 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, 
 __global__ void momentum_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ acc,
                                 __nv_bfloat16* __restrict__ shadow, size_t n, float lr, float mom, float l2,
                                 float gscale, double* __restrict__ sq_part) {
+  bsl::pdl_enter();
   __shared__ double sm[32];
   double sq = 0.0;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -69,6 +71,7 @@ __global__ void momentum_kernel(float* __restrict__ w, const float* __restrict__
 }
 
 __global__ void sumsq_final_kernel(const double* __restrict__ part, int blocks, double* __restrict__ out) {
+  bsl::pdl_enter();
   if (threadIdx.x || blockIdx.x) return;
   double s = 0.0;
   for (int b = 0; b < blocks; ++b) s += part[b];
@@ -101,11 +104,11 @@ int bsl_adam_step(bsl_ctx* ctx, const bsl_adam_desc* d, float* w, const float* g
     part = reinterpret_cast<double*>(base);
   }
   cudaStream_t s = as_stream(stream);
-  adam_kernel<<<blocks, 256, 0, s>>>(w, g, m, v, reinterpret_cast<__nv_bfloat16*>(w_bf16), n, (float)lr_t, d->beta1,
+  bsl_launch(adam_kernel, dim3(blocks), dim3(256), 0, s, w, g, m, v, reinterpret_cast<__nv_bfloat16*>(w_bf16), n, (float)lr_t, d->beta1,
                                      d->beta2, d->eps, d->l2_rate, d->grad_scale, part);
   BSL_LAUNCH_CHECK(ctx, "adam_kernel");
   if (sumsq_out) {
-    sumsq_final_kernel<<<1, 32, 0, s>>>(part, blocks, sumsq_out);
+    bsl_launch(sumsq_final_kernel, dim3(1), dim3(32), 0, s, part, blocks, sumsq_out);
     BSL_LAUNCH_CHECK(ctx, "sumsq_final_kernel");
   }
   return BSL_OK;
@@ -125,11 +128,11 @@ int bsl_momentum_step(bsl_ctx* ctx, float lr, float momentum, float l2_rate, flo
     part = reinterpret_cast<double*>(base);
   }
   cudaStream_t s = as_stream(stream);
-  momentum_kernel<<<blocks, 256, 0, s>>>(w, g, acc, reinterpret_cast<__nv_bfloat16*>(w_bf16), n, lr, momentum,
+  bsl_launch(momentum_kernel, dim3(blocks), dim3(256), 0, s, w, g, acc, reinterpret_cast<__nv_bfloat16*>(w_bf16), n, lr, momentum,
                                          l2_rate, grad_scale, part);
   BSL_LAUNCH_CHECK(ctx, "momentum_kernel");
   if (sumsq_out) {
-    sumsq_final_kernel<<<1, 32, 0, s>>>(part, blocks, sumsq_out);
+    bsl_launch(sumsq_final_kernel, dim3(1), dim3(32), 0, s, part, blocks, sumsq_out);
     BSL_LAUNCH_CHECK(ctx, "sumsq_final_kernel");
   }
   return BSL_OK;

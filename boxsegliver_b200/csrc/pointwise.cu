@@ -17,6 +17,7 @@ inline unsigned grid_for(long long work, int per_block, int cap) {
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                      size_t n) {
+  bsl::pdl_enter();
   size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
   for (; i + 3 < n; i += stride) {
@@ -31,6 +32,7 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
                                      size_t n) {
+  bsl::pdl_enter();
   size_t i = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) * 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
   for (; i + 3 < n; i += stride) {
@@ -44,6 +46,7 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, floa
 }
 
 __global__ void scale_f32_kernel(float* __restrict__ x, size_t n, float a) {
+  bsl::pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
     x[i] *= a;
 }
@@ -93,6 +96,7 @@ struct ReluBiasF {
 };
 
 __global__ void f64_to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int n) {
+  bsl::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = (float)src[i];
 }
@@ -110,7 +114,7 @@ int bsl_channel_sum_bf16(bsl_ctx* ctx, const void* x, long long pixels, int c, i
   double* tmp = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + ((p.scratch_bytes + 15) & ~(size_t)15));
   rc = bsl::run_pixel_reduce(ctx, f, pixels, 1, c, tmp, stream);
   if (rc) return rc;
-  f64_to_f32_kernel<<<(c + 127) / 128, 128, 0, stream>>>(tmp, out, c);
+  bsl_launch(f64_to_f32_kernel, dim3((c + 127) / 128), dim3(128), 0, stream, tmp, out, c);
   BSL_LAUNCH_CHECK(ctx, "f64_to_f32_kernel");
   return BSL_OK;
 }
@@ -123,6 +127,7 @@ __global__ void __launch_bounds__(256, 4)
 relu_bwd_bias4_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ dy, int dy_ld,
                       __nv_bfloat16* __restrict__ out, int o_ld, int c, long long pixels, long long ppb,
                       float* __restrict__ part) {
+  bsl::pdl_enter();
   extern __shared__ float sm[];   // [rows][c]
   const int cg = c / 4;
   const int rows = blockDim.x / cg;
@@ -197,13 +202,13 @@ extern "C" int bsl_relu_bwd_bias(bsl_ctx* ctx, long long pixels, int c, const vo
     int rc = bsl::bsl_scratch(ctx, pbytes + (size_t)c * sizeof(double) + 16, &base, s);
     if (rc) return rc;
     double* tmp = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + pbytes);
-    relu_bwd_bias4_kernel<4><<<blocks, rows * cg, (size_t)rows * c * sizeof(float), s>>>(
+    bsl_launch(relu_bwd_bias4_kernel<4>, dim3(blocks), dim3(rows * cg), (size_t)rows * c * sizeof(float), s, 
         reinterpret_cast<const __nv_bfloat16*>(y), y_ld, reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld,
         reinterpret_cast<__nv_bfloat16*>(out), out_ld, c, pixels, ppb, base);
     BSL_LAUNCH_CHECK(ctx, "relu_bwd_bias4_kernel");
-    bsl::pixel_reduce_final_kernel<<<dim3((c + 31) / 32, 1), 256, 0, s>>>(base, blocks, c, tmp);
+    bsl_launch(bsl::pixel_reduce_final_kernel, dim3(dim3((c + 31) / 32, 1)), dim3(256), 0, s, base, blocks, c, tmp);
     BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel");
-    f64_to_f32_kernel<<<(c + 127) / 128, 128, 0, s>>>(tmp, dbias, c);
+    bsl_launch(f64_to_f32_kernel, dim3((c + 127) / 128), dim3(128), 0, s, tmp, dbias, c);
     BSL_LAUNCH_CHECK(ctx, "f64_to_f32_kernel");
     return BSL_OK;
   }
@@ -216,7 +221,7 @@ extern "C" int bsl_relu_bwd_bias(bsl_ctx* ctx, long long pixels, int c, const vo
   double* tmp = reinterpret_cast<double*>(reinterpret_cast<char*>(base) + ((p.scratch_bytes + 15) & ~(size_t)15));
   rc = bsl::run_pixel_reduce(ctx, f, pixels, 1, c, tmp, s);
   if (rc) return rc;
-  f64_to_f32_kernel<<<(c + 127) / 128, 128, 0, s>>>(tmp, dbias, c);
+  bsl_launch(f64_to_f32_kernel, dim3((c + 127) / 128), dim3(128), 0, s, tmp, dbias, c);
   BSL_LAUNCH_CHECK(ctx, "f64_to_f32_kernel");
   return BSL_OK;
 }
@@ -226,23 +231,21 @@ extern "C" {
 int bsl_scale_f32(bsl_ctx* ctx, float* x, size_t n, float a, void* stream) {
   if (!ctx || !x) return BSL_EINVAL;
   if (n == 0) return BSL_OK;
-  scale_f32_kernel<<<grid_for((long long)n, kThreads, 8 * ctx->sm_count), kThreads, 0, as_stream(stream)>>>(x, n, a);
+  bsl_launch(scale_f32_kernel, dim3(grid_for((long long)n, kThreads, 8 * ctx->sm_count)), dim3(kThreads), 0, as_stream(stream), x, n, a);
   BSL_LAUNCH_CHECK(ctx, "scale_f32_kernel");
   return BSL_OK;
 }
 
 int bsl_cast_f32_to_bf16(bsl_ctx* ctx, const float* src, void* dst, size_t n, void* stream) {
   if (!ctx || !src || !dst) return BSL_EINVAL;
-  cast_f32_bf16_kernel<<<grid_for((long long)n, kThreads * 4, 8 * ctx->sm_count), kThreads, 0,
-                         as_stream(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  bsl_launch(cast_f32_bf16_kernel, dim3(grid_for((long long)n, kThreads * 4, 8 * ctx->sm_count)), dim3(kThreads), 0, as_stream(stream), src, reinterpret_cast<__nv_bfloat16*>(dst), n);
   BSL_LAUNCH_CHECK(ctx, "cast_f32_bf16_kernel");
   return BSL_OK;
 }
 
 int bsl_cast_bf16_to_f32(bsl_ctx* ctx, const void* src, float* dst, size_t n, void* stream) {
   if (!ctx || !src || !dst) return BSL_EINVAL;
-  cast_bf16_f32_kernel<<<grid_for((long long)n, kThreads * 4, 8 * ctx->sm_count), kThreads, 0,
-                         as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+  bsl_launch(cast_bf16_f32_kernel, dim3(grid_for((long long)n, kThreads * 4, 8 * ctx->sm_count)), dim3(kThreads), 0, as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
   BSL_LAUNCH_CHECK(ctx, "cast_bf16_f32_kernel");
   return BSL_OK;
 }

@@ -43,6 +43,26 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------- programmatic dependent launch
+// A kernel enqueued with cudaLaunchAttributeProgrammaticStreamSerialization (bsl_launch, internal.h) may become
+// resident while its predecessor in the stream still runs. pdl_trigger() lets the successor's blocks be scheduled
+// as soon as every block of this grid has called it; pdl_wait() returns once the predecessor grid has completed
+// and its writes are visible. Nothing may read or write global data the predecessor touches before pdl_wait().
+// Both are no-ops in a launch without the attribute.
+#ifndef BSL_PDL_TRIGGER
+#define BSL_PDL_TRIGGER 0
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if BSL_PDL_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_trigger();
+  pdl_wait();
+}
+
 // ----------------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -42,6 +42,7 @@ __device__ __forceinline__ void st16(__nv_bfloat16* p, const uint4& v) { *reinte
 template <class F, int UNROLL>
 __global__ void pixel_reduce_kernel(F f, long long pixels_per_group, long long ppb, int c,
                                     float* __restrict__ part) {
+  bsl::pdl_enter();
   extern __shared__ float sm[];  // [rows][K][c]
   constexpr int K = F::K;
   constexpr int NIN = F::NIN;
@@ -129,11 +130,11 @@ int run_pixel_reduce(bsl_ctx* ctx, const F& f, long long pixels_per_group, int g
   float* part = nullptr;
   int rc = bsl_scratch(ctx, p.scratch_bytes, &part, stream);
   if (rc) return rc;
-  pixel_reduce_kernel<F, F::UNROLL><<<dim3(p.blocks, groups), p.threads, p.smem, stream>>>(f, pixels_per_group,
+  bsl_launch(pixel_reduce_kernel<F, F::UNROLL>, dim3(dim3(p.blocks, groups)), dim3(p.threads), p.smem, stream, f, pixels_per_group,
                                                                                           p.ppb, c, part);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_kernel");
   const int kc = F::K * c;
-  pixel_reduce_final_kernel<<<dim3((kc + 31) / 32, groups), 256, 0, stream>>>(part, p.blocks, kc, out);
+  bsl_launch(pixel_reduce_final_kernel, dim3(dim3((kc + 31) / 32, groups)), dim3(256), 0, stream, part, p.blocks, kc, out);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel");
   return BSL_OK;
 }

@@ -2,9 +2,22 @@
 // This is the part of the boundary the TF wrapper would NOT use (TF owns memory and streams,
 // SURVEY.md section 8b); the ctypes host in boxsegliver_b200/ uses it instead of PyTorch.
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include "internal.h"
+
+// -1 = not read yet; BSL_PDL in the environment sets the initial value, bsl_debug_set(ctx, 4, v) changes it at run time
+// (the engine turns it off for the phases where a second stream shares the SMs, see engine.py).
+static int g_bsl_pdl = -1;
+bool bsl_pdl_enabled() {
+  if (g_bsl_pdl < 0) {
+    const char* e = getenv("BSL_PDL");
+    g_bsl_pdl = e ? (atoi(e) != 0) : 1;
+  }
+  return g_bsl_pdl != 0;
+}
+void bsl_pdl_set(int on) { g_bsl_pdl = on ? 1 : 0; }
 
 int bsl_fail(bsl_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];

@@ -15,6 +15,7 @@ template <int CIN>
 __global__ void stem_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                   __nv_bfloat16* __restrict__ y, int y_ld, int n, int h, int wd, int cout, int kh,
                                   int kw) {
+  bsl::pdl_enter();
   extern __shared__ float sw[];  // [taps*CIN][cout]
   const int taps = kh * kw;
   for (int i = threadIdx.x; i < taps * CIN * cout; i += blockDim.x) sw[i] = w[i];
@@ -68,6 +69,7 @@ __global__ void stem_fprop_kernel(const float* __restrict__ x, const float* __re
 constexpr int IM2COL_STRIP = 256;
 __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int n, int h, int wd,
                                    int cin, int kh, int kw) {
+  bsl::pdl_enter();
   extern __shared__ float patch[];  // [kh][strip + kw - 1][cin]
   const int strips = (wd + IM2COL_STRIP - 1) / IM2COL_STRIP;
   const int ph = (kh - 1) / 2, pw = (kw - 1) / 2;
@@ -108,6 +110,7 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* _
 template <int CIN, int KW>
 __global__ void stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dy, int dy_ld, int n,
                                   int h, int wd, int cout, int kh, long long ppb, float* __restrict__ part) {
+  bsl::pdl_enter();
   const int lane = threadIdx.x & 31;
   const int cg = threadIdx.x >> 5;  // 8-channel group handled by this warp
   const int groups = cout / 8;
@@ -162,6 +165,7 @@ __global__ void stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat
 }
 
 __global__ void sum_chunks_kernel(const float* __restrict__ part, int chunks, int n, float* __restrict__ out) {
+  bsl::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double s = 0.0;
@@ -174,6 +178,7 @@ __global__ void sum_chunks_kernel(const float* __restrict__ part, int chunks, in
 template <int COUT>
 __global__ void head_fprop_kernel(const __nv_bfloat16* __restrict__ x, int x_ld, const float* __restrict__ w,
                                   const float* __restrict__ bias, float* __restrict__ y, long long pixels, int cin) {
+  bsl::pdl_enter();
   extern __shared__ float sw[];  // [cin][COUT]
   for (int i = threadIdx.x; i < cin * COUT; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -219,6 +224,7 @@ __global__ void head_fprop_kernel(const __nv_bfloat16* __restrict__ x, int x_ld,
 template <int COUT>
 __global__ void head_dgrad_kernel(const float* __restrict__ dl, const float* __restrict__ w,
                                   __nv_bfloat16* __restrict__ dx, int dx_ld, long long pixels, int cin) {
+  bsl::pdl_enter();
   extern __shared__ float sw[];
   for (int i = threadIdx.x; i < cin * COUT; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -286,6 +292,7 @@ struct HeadWgradF {
 
 // sums[k*cin + c] (fp64) -> dw[c*COUT + k] (fp32, [1,1,cin,cout] = HWIO)
 __global__ void head_wgrad_finish_kernel(const double* __restrict__ sums, float* __restrict__ dw, int cin, int cout) {
+  bsl::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cin * cout) return;
   const int c = i / cout, k = i - c * cout;
@@ -295,6 +302,7 @@ __global__ void head_wgrad_finish_kernel(const double* __restrict__ sums, float*
 // column sums of a dense fp32 [rows][cols] matrix, cols <= 8 (bias gradient of the logits layer)
 __global__ void colsum_partial_kernel(const float* __restrict__ a, long long rows, int cols, long long rpb,
                                       float* __restrict__ part) {
+  bsl::pdl_enter();
   __shared__ float sm[8][8];  // [warp][col]
   const long long r0 = blockIdx.x * rpb, r1 = min(rows, r0 + rpb);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -340,7 +348,7 @@ int bsl_conv2d_stem_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x
   const size_t smem = (size_t)d->kh * d->kw * d->cin * d->cout * sizeof(float);
   const long long items = (long long)d->n * d->h * d->w * (d->cout / 16);
   auto go = [&](auto kern) {
-    kern<<<ew_grid(ctx, items), 256, smem, as_stream(stream)>>>(x, w, reinterpret_cast<__nv_bfloat16*>(y), d->y_ld,
+    bsl_launch(kern, dim3(ew_grid(ctx, items)), dim3(256), smem, as_stream(stream), x, w, reinterpret_cast<__nv_bfloat16*>(y), d->y_ld,
                                                                 d->n, d->h, d->w, d->cout, d->kh, d->kw);
   };
   switch (d->cin) {
@@ -364,7 +372,7 @@ int bsl_stem_im2col(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x, void
   const long long blocks = (long long)d->n * d->h * ((d->w + IM2COL_STRIP - 1) / IM2COL_STRIP);
   const size_t smem = (size_t)d->kh * (IM2COL_STRIP + d->kw - 1) * d->cin * sizeof(float);
   const long long cap = 16LL * ctx->sm_count;
-  stem_im2col_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, smem, as_stream(stream)>>>(
+  bsl_launch(stem_im2col_kernel, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(256), smem, as_stream(stream), 
       x, reinterpret_cast<__nv_bfloat16*>(col), d->n, d->h, d->w, d->cin, d->kh, d->kw);
   BSL_LAUNCH_CHECK(ctx, "stem_im2col_kernel");
   return BSL_OK;
@@ -388,7 +396,7 @@ int bsl_conv2d_stem_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x
   if (rc) return rc;
   const int threads = 32 * (d->cout / 8);
   auto go = [&](auto kern) {
-    kern<<<dim3((unsigned)chunks, d->kh), threads, 0, as_stream(stream)>>>(
+    bsl_launch(kern, dim3(dim3((unsigned)chunks, d->kh)), dim3(threads), 0, as_stream(stream), 
         x, reinterpret_cast<const __nv_bfloat16*>(dy), d->y_ld, d->n, d->h, d->w, d->cout, d->kh, ppb, part);
   };
   switch (d->cin) {
@@ -400,7 +408,7 @@ int bsl_conv2d_stem_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x
     default: return bsl_fail(ctx, BSL_EUNSUPPORTED, "stem_wgrad: cin=%d (1..5)", d->cin);
   }
   BSL_LAUNCH_CHECK(ctx, "stem_wgrad_kernel");
-  sum_chunks_kernel<<<(nout + 127) / 128, 128, 0, as_stream(stream)>>>(part, (int)chunks, nout, dw);
+  bsl_launch(sum_chunks_kernel, dim3((nout + 127) / 128), dim3(128), 0, as_stream(stream), part, (int)chunks, nout, dw);
   BSL_LAUNCH_CHECK(ctx, "sum_chunks_kernel");
   return BSL_OK;
 }
@@ -430,7 +438,7 @@ int bsl_conv2d_head_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x,
   if (!x || !w || !logits) return bsl_fail(ctx, BSL_EINVAL, "head_fprop: null buffer");
   const long long pixels = (long long)d->n * d->h * d->w;
   const size_t smem = (size_t)d->cin * d->cout * sizeof(float);
-  HEAD_SWITCH(d->cout, (head_fprop_kernel<CO><<<ew_grid(ctx, pixels * (d->cin / 8)), 256, smem, as_stream(stream)>>>(
+  HEAD_SWITCH(d->cout, (bsl_launch(head_fprop_kernel<CO>, dim3(ew_grid(ctx, pixels * (d->cin / 8))), dim3(256), smem, as_stream(stream), 
                            reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld, w, bias, logits, pixels, d->cin)));
   BSL_LAUNCH_CHECK(ctx, "head_fprop_kernel");
   return BSL_OK;
@@ -443,7 +451,7 @@ int bsl_conv2d_head_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* d
   if (!dlogits || !w || !dx) return bsl_fail(ctx, BSL_EINVAL, "head_dgrad: null buffer");
   const long long pixels = (long long)d->n * d->h * d->w;
   const size_t smem = (size_t)d->cin * d->cout * sizeof(float);
-  HEAD_SWITCH(d->cout, (head_dgrad_kernel<CO><<<ew_grid(ctx, pixels * (d->cin / 8)), 256, smem, as_stream(stream)>>>(
+  HEAD_SWITCH(d->cout, (bsl_launch(head_dgrad_kernel<CO>, dim3(ew_grid(ctx, pixels * (d->cin / 8))), dim3(256), smem, as_stream(stream), 
                            dlogits, w, reinterpret_cast<__nv_bfloat16*>(dx), d->x_ld, pixels, d->cin)));
   BSL_LAUNCH_CHECK(ctx, "head_dgrad_kernel");
   return BSL_OK;
@@ -469,13 +477,13 @@ int bsl_conv2d_head_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x,
   const __nv_bfloat16* xb = reinterpret_cast<const __nv_bfloat16*>(x);
   HEAD_SWITCH(d->cout, (rc = run_pixel_reduce(ctx, HeadWgradF<CO>{xb, dlogits, d->x_ld}, pixels, 1, d->cin, sums, s)));
   if (rc) return rc;
-  head_wgrad_finish_kernel<<<(d->cin * d->cout + 127) / 128, 128, 0, s>>>(sums, dw, d->cin, d->cout);
+  bsl_launch(head_wgrad_finish_kernel, dim3((d->cin * d->cout + 127) / 128), dim3(128), 0, s, sums, dw, d->cin, d->cout);
   BSL_LAUNCH_CHECK(ctx, "head_wgrad_finish_kernel");
   if (dbias) {
     const long long rpb = (pixels + cblocks - 1) / cblocks;
-    colsum_partial_kernel<<<cblocks, 256, 0, s>>>(dlogits, pixels, d->cout, rpb, cpart);
+    bsl_launch(colsum_partial_kernel, dim3(cblocks), dim3(256), 0, s, dlogits, pixels, d->cout, rpb, cpart);
     BSL_LAUNCH_CHECK(ctx, "colsum_partial_kernel");
-    sum_chunks_kernel<<<1, 32, 0, s>>>(cpart, cblocks, d->cout, dbias);
+    bsl_launch(sum_chunks_kernel, dim3(1), dim3(32), 0, s, cpart, cblocks, d->cout, dbias);
     BSL_LAUNCH_CHECK(ctx, "sum_chunks_kernel");
   }
   return BSL_OK;

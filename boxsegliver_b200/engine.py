@@ -139,6 +139,12 @@ class UNetEngine:
         self._grad_stream = self.stream
         self._overlap_wgrad = cfg.training and os.environ.get("BSL_WGRAD_OVERLAP", "1") != "0"
         self._fork_pre = os.environ.get("BSL_WGRAD_FORK", "pre") == "pre"
+        # Programmatic dependent launch (csrc/internal.h bsl_launch): 0 off, 1 every launch (default), 2 only in the
+        # phases where the compute stream has the SMs to itself (forward, loss head, optimizer). Measured on B200
+        # (tools/pdl_ab.sh): the launch attribute alone, every kernel waiting with griddepcontrol.wait before its first
+        # global access, is worth 0.15-0.25 ms per step; an explicit early trigger (BSL_PDL_TRIGGER in ptx.cuh) makes
+        # the step 0.6-0.9 ms SLOWER with or without the filter-gradient stream, so it is compiled out.
+        self._pdl_mode = int(os.environ.get("BSL_PDL", "1"))
         self._ev_ring, self._ev_ring_i = [ctx.new_event() for _ in range(160)], 0
         if cfg.training:
             self.wg_stream = ctx.new_stream()
@@ -595,9 +601,14 @@ class UNetEngine:
         pipe, ev = pend
         return pipe, lambda: self.ctx.call("bsl_stream_wait_event", s, ev)
 
+    def _pdl(self, on: bool):
+        if self._pdl_mode == 2:
+            self.ctx.call("bsl_debug_set", C.c_int(4), C.c_int(1 if on else 0))
+
     def forward(self, is_training: bool):
         ctx, s = self.ctx, self.stream
         call = ctx.call
+        self._pdl(True)
         self._pipe_epoch += 1
         piping = self._pipe_active()
         self._head_done = False
@@ -725,6 +736,8 @@ class UNetEngine:
         # overlap); a dY buffer is reused two conv layers later, behind an event.
         cur, alt = self.g1, self.g2
         overlap = self._overlap_wgrad and ctx._prof is None
+        if overlap:
+            self._pdl(False)
         piping = self._pipe_active()
         self._pipe_epoch += 1
         relu_fused = set()      # levels whose transposed-conv ReluGrad was applied by the decoder dgrad's epilogue
@@ -862,6 +875,7 @@ class UNetEngine:
     # ------------------------------------------------------------------ optimizer
     def optimizer_step(self, lr: float):
         ctx, s, cfg = self.ctx, self.stream, self.cfg
+        self._pdl(True)
         self.step_count += 1
         l2 = cfg.weight_decay_rate if cfg.weight_decay_rate > 0 else 0.0
         regions = [(0, self.n_reg, l2, self.sumsq.p), (self.n_reg, self.n_train - self.n_reg, 0.0, None)]
