@@ -79,7 +79,9 @@ void set_tiles(IgemmArgs& a, const int tdim[4], const int tbox[4]) {
 
 int nhwc_map(bsl_ctx* ctx, const void* base, int c, int w, int h, int n, int ld, const int box[4],
              CUtensorMap* out) {
-  uint64_t dims[5] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n, 1};
+  // ld < c: the rows hold only ld channels (narrow im2col matrix of the stem); the 64-wide box then reaches past
+  // the innermost extent and TMA zero-fills channels >= ld in shared memory
+  uint64_t dims[5] = {(uint64_t)(ld < c ? ld : c), (uint64_t)w, (uint64_t)h, (uint64_t)n, 1};
   uint64_t str[5] = {2, (uint64_t)ld * 2, (uint64_t)w * ld * 2, (uint64_t)h * w * ld * 2,
                      (uint64_t)n * h * w * ld * 2};
   uint32_t bx[5] = {64, (uint32_t)box[0], (uint32_t)box[1], (uint32_t)box[2], 1};
@@ -113,7 +115,7 @@ int matrix_map(bsl_ctx* ctx, const void* base, int inner, int rows, int box_inne
   return bsl_get_tmap(ctx, base, 2, dims, str, bx, out);
 }
 
-int check_conv(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
+int check_conv(bsl_ctx* ctx, const bsl_conv2d_desc* d, bool narrow_x_ok = false) {
   if (!ctx) return BSL_EINVAL;
   if (!d) return bsl_fail(ctx, BSL_EINVAL, "conv2d: null descriptor");
   if (d->n <= 0 || d->h <= 0 || d->w <= 0 || d->cin <= 0 || d->cout <= 0)
@@ -124,7 +126,8 @@ int check_conv(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
     return bsl_fail(ctx, BSL_EUNSUPPORTED,
                     "conv2d tcgen05 path needs cin,cout multiples of 64 (got %d,%d); use "
                     "bsl_conv2d_small_* for the stem / logits layers", d->cin, d->cout);
-  if (d->x_ld < d->cin || d->y_ld < d->cout || d->x_ld % 8 || d->y_ld % 8)
+  const bool narrow = narrow_x_ok && d->kh == 1 && d->cin == 64 && d->x_ld >= 8;   // x_ld < cin: see bsl_conv2d_desc
+  if ((d->x_ld < d->cin && !narrow) || d->y_ld < d->cout || d->x_ld % 8 || d->y_ld % 8)
     return bsl_fail(ctx, BSL_EINVAL, "conv2d: channel strides must be >= channels and multiples of 8");
   return BSL_OK;
 }
@@ -576,7 +579,7 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
 
 int bsl_conv2d_fprop_stats(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
                            double* sums, void* stream) {
-  int rc = check_conv(ctx, d);
+  int rc = check_conv(ctx, d, true);
   if (rc) return rc;
   if (!x || !w || !y || !sums) return bsl_fail(ctx, BSL_EINVAL, "conv2d_fprop_stats: null buffer");
   if (halo_eligible(d->w, d->h)) return conv2d_fprop_halo(ctx, d, x, w, y, sums, as_stream(stream));
@@ -586,7 +589,7 @@ int bsl_conv2d_fprop_stats(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x
 
 int bsl_conv2d_fprop_pipe(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
                           double* sums, const bsl_pipe* wait, void* stream) {
-  int rc = check_conv(ctx, d);
+  int rc = check_conv(ctx, d, true);
   if (rc) return rc;
   if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "conv2d_fprop_pipe: null buffer");
   if (!halo_eligible(d->w, d->h))
@@ -601,7 +604,7 @@ int bsl_conv2d_pipe_ok(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
 
 int bsl_conv2d_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
                      void* stream) {
-  int rc = check_conv(ctx, d);
+  int rc = check_conv(ctx, d, true);
   if (rc) return rc;
   if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "conv2d_fprop: null buffer");
   if (halo_eligible(d->w, d->h)) return conv2d_fprop_halo(ctx, d, x, w, y, nullptr, as_stream(stream));
@@ -715,7 +718,7 @@ static int conv2d_dgrad_impl(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
 }
 
 size_t bsl_conv2d_wgrad_workspace(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
-  if (!ctx || !d || check_conv(ctx, d)) return 0;
+  if (!ctx || !d || check_conv(ctx, d, true)) return 0;
   if (wgrad2_eligible(d)) return cached_wgrad2(ctx, d).ws_floats * sizeof(float);
   if (wgrad_halo_eligible(d)) {
     const WgradPlan p = plan_wgrad_halo(ctx, d);
@@ -733,7 +736,7 @@ size_t bsl_conv2d_wgrad_workspace(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
 
 int bsl_conv2d_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* dy, float* dw,
                      void* workspace, size_t workspace_bytes, void* stream) {
-  int rc = check_conv(ctx, d);
+  int rc = check_conv(ctx, d, true);
   if (rc) return rc;
   if (!x || !dy || !dw) return bsl_fail(ctx, BSL_EINVAL, "conv2d_wgrad: null buffer");
   if (wgrad2_eligible(d)) return conv2d_wgrad2(ctx, d, x, dy, dw, workspace, workspace_bytes, as_stream(stream));

@@ -68,14 +68,16 @@ __global__ void stem_fprop_kernel(const float* __restrict__ x, const float* __re
 // (held in registers) and writes one 16-byte chunk: a warp writes 512 contiguous bytes.
 constexpr int IM2COL_STRIP = 256;
 __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int n, int h, int wd,
-                                   int cin, int kh, int kw) {
+                                   int cin, int kh, int kw, int cols) {
   bsl::pdl_enter();
   extern __shared__ float patch[];  // [kh][strip + kw - 1][cin]
   const int strips = (wd + IM2COL_STRIP - 1) / IM2COL_STRIP;
   const int ph = (kh - 1) / 2, pw = (kw - 1) / 2;
   const int kcols = kh * kw * cin;
   const int pitch = (IM2COL_STRIP + kw - 1) * cin;
-  const int g = threadIdx.x & 7;
+  const int ngrp = cols >> 3;                 // 8-column groups per row: 8 (64 columns) or 4 (32 columns)
+  const int g = threadIdx.x & (ngrp - 1);
+  const int px0 = threadIdx.x / ngrp, pxs = blockDim.x / ngrp;
   int off[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -94,11 +96,11 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* _
       patch[i] = (yy >= 0 && yy < h && xx >= 0 && xx < wd) ? __ldg(x + ((img * h + yy) * wd + xx) * cin + rem % cin) : 0.f;
     }
     __syncthreads();
-    for (int px = threadIdx.x >> 3; px < IM2COL_STRIP && sx + px < wd; px += blockDim.x >> 3) {
+    for (int px = px0; px < IM2COL_STRIP && sx + px < wd; px += pxs) {
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? patch[off[j] + px * cin] : 0.f;
-      st16(col + ((img * h + yh) * wd + sx + px) * 64 + g * 8, pack8(v));
+      st16(col + ((img * h + yh) * wd + sx + px) * cols + g * 8, pack8(v));
     }
   }
 }
@@ -363,19 +365,26 @@ int bsl_conv2d_stem_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x
   return BSL_OK;
 }
 
-int bsl_stem_im2col(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x, void* col, void* stream) {
+int bsl_stem_im2col_ld(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x, void* col, int col_ld, void* stream) {
   int rc = check_small(ctx, d);
   if (rc) return rc;
   if (!x || !col) return bsl_fail(ctx, BSL_EINVAL, "stem_im2col: null buffer");
   if (d->kh * d->kw * d->cin > 64 || d->cin < 1)
     return bsl_fail(ctx, BSL_EUNSUPPORTED, "stem_im2col: kh*kw*cin = %d must be <= 64", d->kh * d->kw * d->cin);
+  if ((col_ld != 32 && col_ld != 64) || d->kh * d->kw * d->cin > col_ld)
+    return bsl_fail(ctx, BSL_EINVAL, "stem_im2col: col_ld = %d must be 32 or 64 and >= kh*kw*cin = %d", col_ld,
+                    d->kh * d->kw * d->cin);
   const long long blocks = (long long)d->n * d->h * ((d->w + IM2COL_STRIP - 1) / IM2COL_STRIP);
   const size_t smem = (size_t)d->kh * (IM2COL_STRIP + d->kw - 1) * d->cin * sizeof(float);
   const long long cap = 16LL * ctx->sm_count;
-  bsl_launch(stem_im2col_kernel, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(256), smem, as_stream(stream), 
-      x, reinterpret_cast<__nv_bfloat16*>(col), d->n, d->h, d->w, d->cin, d->kh, d->kw);
+  bsl_launch(stem_im2col_kernel, dim3((unsigned)(blocks < cap ? blocks : cap)), dim3(256), smem, as_stream(stream),
+             x, reinterpret_cast<__nv_bfloat16*>(col), d->n, d->h, d->w, d->cin, d->kh, d->kw, col_ld);
   BSL_LAUNCH_CHECK(ctx, "stem_im2col_kernel");
   return BSL_OK;
+}
+
+int bsl_stem_im2col(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x, void* col, void* stream) {
+  return bsl_stem_im2col_ld(ctx, d, x, col, 64, stream);
 }
 
 int bsl_conv2d_stem_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x, const void* dy, float* dw,

@@ -420,7 +420,11 @@ class UNetEngine:
                 L.x = prev_a
         self.cat = cat
         self.images = self._alloc(n * cfg.height * cfg.width * cfg.channel * F32)
-        self.stem_col = View(self._alloc(n * cfg.height * cfg.width * 64 * BF16), n, cfg.height, cfg.width, 64)
+        # im2col rows of the stem: 9 * channels live columns in a pitch of 32 (3 input channels) or 64 columns; the conv
+        # kernels read a 32-column matrix as cin = 64 with the upper half zero-filled by TMA (bsl_stem_im2col_ld)
+        sc = int(os.environ.get("BSL_STEM_COLS", "0")) or (32 if 9 * cfg.channel <= 32 else 64)
+        self.stem_cols = sc
+        self.stem_col = View(self._alloc(n * cfg.height * cfg.width * sc * BF16), n, cfg.height, cfg.width, sc)
         self.labels = self._alloc(n * cfg.height * cfg.width * 4)
         npx = n * cfg.height * cfg.width
         self.logits = self._alloc(npx * cfg.num_classes * F32)
@@ -443,7 +447,7 @@ class UNetEngine:
             ws = 0
             for L in self.layers:
                 if L.kind == "stem":
-                    d = _lib.Conv2dDesc(n, L.h, L.w, 64, L.cout, 1, 1, 64, L.cout)
+                    d = _lib.Conv2dDesc(n, L.h, L.w, 64, L.cout, 1, 1, self.stem_cols, L.cout)
                     ws = max(ws, self.ctx.lib.bsl_conv2d_wgrad_workspace(self.ctx.h, C.byref(d)))
                 elif L.kind == "conv":
                     d = self._conv_desc(L)
@@ -627,8 +631,8 @@ class UNetEngine:
                 wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
                 if L.kind == "stem":
                     # im2col (27 -> 64 columns, bf16) + 1x1 conv on the tensor cores
-                    call("bsl_stem_im2col", C.byref(d), self.images.p, self.stem_col.p, s)
-                    d1 = _lib.Conv2dDesc(self.cfg.batch, L.h, L.w, 64, L.cout, 1, 1, 64, L.y.ld)
+                    call("bsl_stem_im2col_ld", C.byref(d), self.images.p, self.stem_col.p, C.c_int(self.stem_cols), s)
+                    d1 = _lib.Conv2dDesc(self.cfg.batch, L.h, L.w, 64, L.cout, 1, 1, self.stem_cols, L.y.ld)
                     self._tc("fprop", self._flops(L), fn, C.byref(d1), self.stem_col.p, wbf, L.y.p, *extra, s)
                 else:
                     pw, done = self._take_pending(s)
@@ -834,7 +838,7 @@ class UNetEngine:
                 if not self._fork_pre:
                     fork()
                 if L.kind == "stem":
-                    d1 = _lib.Conv2dDesc(n, L.h, L.w, 64, L.cout, 1, 1, 64, L.cout)
+                    d1 = _lib.Conv2dDesc(n, L.h, L.w, 64, L.cout, 1, 1, self.stem_cols, L.cout)
                     self._tc("wgrad", self._flops(L), "bsl_conv2d_wgrad", C.byref(d1), self.stem_col.p, dyb.p, gw,
                              self.wgrad_ws.p, wsb, ws, stream=ws)
                 else:

@@ -95,7 +95,8 @@ typedef struct {
   int n, h, w;     /* batch and spatial size (output == input size: stride 1, SAME) */
   int cin, cout;
   int kh, kw;      /* 3x3 or 1x1 */
-  int x_ld;        /* channel stride of the input buffer (elements), >= cin */
+  int x_ld;        /* channel stride of the input buffer (elements), >= cin. fprop / wgrad also take x_ld < cin
+                    * (multiple of 8): rows then hold only x_ld channels and channels >= x_ld read as zero */
   int y_ld;        /* channel stride of the output buffer (elements), >= cout */
 } bsl_conv2d_desc;
 
@@ -219,6 +220,11 @@ int bsl_add_bf16(bsl_ctx* ctx, long long pixels, int c, const void* a_bf16, int 
  * >= kh*kw*cin are zero. The stem then runs as bsl_conv2d_fprop / bsl_conv2d_wgrad with k = 1,
  * cin = 64 on the tensor cores (filter rows >= kh*kw*cin are zero padding). */
 int bsl_stem_im2col(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x_f32, void* col_bf16, void* stream);
+/* Same with a row pitch of col_ld = 32 or 64 columns (>= kh*kw*cin). A 32-column matrix is handed to
+ * bsl_conv2d_fprop / bsl_conv2d_wgrad as cin = 64, x_ld = 32: the TMA box is wider than the tensor and its upper
+ * half is zero-filled on chip, so the K = 64 GEMM reads half the bytes (see x_ld in bsl_conv2d_desc). */
+int bsl_stem_im2col_ld(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x_f32, void* col_bf16, int col_ld,
+                       void* stream);
 int bsl_conv2d_stem_fprop(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x_f32, const float* w_hwio_f32,
                           void* y_bf16, void* stream);
 int bsl_conv2d_stem_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x_f32, const void* dy_bf16,

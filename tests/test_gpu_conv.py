@@ -73,6 +73,48 @@ def test_conv2d_fprop_dgrad_wgrad(ctx, n, h, w, cin, cout, k, x_ld, y_ld):
         b.free()
 
 
+@pytest.mark.parametrize("n,h,w,cout", [(2, 16, 32, 64), (3, 12, 20, 64), (1, 32, 32, 128)])
+def test_conv2d_narrow_rows_equal_zero_padded(ctx, n, h, w, cout):
+    """x_ld = 32 < cin = 64 (the stem's 32-column im2col matrix, bsl_stem_im2col_ld): the TMA box is wider than the
+    tensor and its upper half is zero-filled, so fprop (+ statistics) and wgrad are bit-identical to the same call on
+    a 64-column matrix whose columns 32..63 are zero. Halo-tile and general kernels."""
+    rng = np.random.default_rng(h * 3 + cout)
+    x = bf16_randn(rng, (n, h, w, 32))
+    wt = bf16_randn(rng, (1, 1, 64, cout), 0.05)
+    dy = bf16_randn(rng, (n, h, w, cout))
+    xn, xw = ctx.bf16_from_f32(x), ctx.bf16_from_f32(padded(x, 64))
+    dw_, ddy = ctx.bf16_from_f32(wt), ctx.bf16_from_f32(dy)
+    outs = []
+    for buf, ld in ((xw, 64), (xn, 32)):
+        desc = _lib.Conv2dDesc(n, h, w, 64, cout, 1, 1, ld, cout)
+        yo = ctx.alloc(n * h * w * cout * 2).zero()
+        sums = ctx.alloc(2 * cout * 8).zero()
+        ctx.call("bsl_conv2d_fprop_stats", C.byref(desc), buf.p, dw_.p, yo.p, sums.p, ctx.stream)
+        ws_bytes = ctx.lib.bsl_conv2d_wgrad_workspace(ctx.h, C.byref(desc))
+        ws = ctx.alloc(max(ws_bytes, 16))
+        dwo = ctx.alloc(64 * cout * 4).zero()
+        ctx.call("bsl_conv2d_wgrad", C.byref(desc), buf.p, ddy.p, dwo.p, ws.p, C.c_size_t(ws_bytes), ctx.stream)
+        ctx.check_device()
+        outs.append((yo.download(np.uint16, (n, h, w, cout)), sums.download(np.float64, (2, cout)),
+                     dwo.download(np.float32, (64, cout))))
+        for b in (yo, sums, ws, dwo):
+            b.free()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    assert rel(ctx_bf16(outs[1][0]), O.conv2d(x.astype(np.float64), wt[:, :, :32].astype(np.float64))) < TOL_BF16
+    assert not outs[1][2][32:].any(), "filter-gradient rows of the zero-filled channels must be zero"
+    # dgrad writes x_ld-pitched rows: a narrow pitch is rejected there
+    desc = _lib.Conv2dDesc(n, h, w, 64, cout, 1, 1, 32, cout)
+    with pytest.raises(Exception):
+        ctx.call("bsl_conv2d_dgrad", C.byref(desc), ddy.p, dw_.p, xw.p, ctx.stream)
+    for b in (xn, xw, dw_, ddy):
+        b.free()
+
+
+def ctx_bf16(bits):
+    return (bits.astype(np.uint32) << 16).view(np.float32)
+
+
 def test_conv2d_fprop_fused_statistics(ctx):
     """bsl_conv2d_fprop_stats == bsl_conv2d_fprop followed by bsl_norm_stats (batch mode), on both kernel paths."""
     for (n, h, w, cin, cout, y_ld) in [(2, 32, 32, 64, 64, 64), (3, 16, 24, 128, 192, 256), (2, 12, 20, 64, 128, 128),

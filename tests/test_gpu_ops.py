@@ -157,21 +157,26 @@ def test_stem_conv(ctx, cin):
         b.free()
 
 
-@pytest.mark.parametrize("n,h,w,cin", [(2, 12, 20, 3), (1, 5, 300, 1), (3, 16, 128, 5), (2, 7, 131, 7)])
-def test_stem_im2col_bit_exact(ctx, n, h, w, cin):
-    """col[p, t*cin+ci] = bf16(x[p + tap t, ci]) with zero SAME padding; columns >= 9*cin are zero."""
+@pytest.mark.parametrize("n,h,w,cin,ld", [(2, 12, 20, 3, 64), (1, 5, 300, 1, 64), (3, 16, 128, 5, 64), (2, 7, 131, 7, 64),
+                                          (2, 12, 20, 3, 32), (1, 5, 300, 1, 32), (2, 16, 131, 2, 32)])
+def test_stem_im2col_bit_exact(ctx, n, h, w, cin, ld):
+    """col[p, t*cin+ci] = bf16(x[p + tap t, ci]) with zero SAME padding; columns >= 9*cin are zero. Row pitch 64
+    (bsl_stem_im2col) or 32 columns (bsl_stem_im2col_ld)."""
     rng = np.random.default_rng(w)
     x = rng.uniform(-1, 1, (n, h, w, cin)).astype(np.float32)
     dx_ = ctx.from_numpy(x)
-    col = ctx.alloc(n * h * w * 64 * 2)
+    col = ctx.alloc(n * h * w * ld * 2)
     ctx.call("bsl_memset", col.p, C.c_int(0xff), C.c_size_t(col.nbytes), ctx.stream)
     d = _lib.Conv2dDesc(n, h, w, cin, 64, 3, 3, cin, 64)
-    ctx.call("bsl_stem_im2col", C.byref(d), dx_.p, col.p, ctx.stream)
+    if ld == 64:
+        ctx.call("bsl_stem_im2col", C.byref(d), dx_.p, col.p, ctx.stream)
+    else:
+        ctx.call("bsl_stem_im2col_ld", C.byref(d), dx_.p, col.p, C.c_int(ld), ctx.stream)
     ctx.check_device()
-    got = col.download(np.uint16, (n, h, w, 64))
+    got = col.download(np.uint16, (n, h, w, ld))
     xp = np.zeros((n, h + 2, w + 2, cin), np.float32)
     xp[:, 1:-1, 1:-1] = x
-    ref = np.zeros((n, h, w, 64), np.float32)
+    ref = np.zeros((n, h, w, ld), np.float32)
     for t in range(9):
         ref[..., t * cin:(t + 1) * cin] = xp[:, t // 3:t // 3 + h, t % 3:t % 3 + w]
     from boxsegliver_b200.device import f32_to_bf16_bits

@@ -77,7 +77,9 @@ def alg_bytes(fn, L):
     return {"bsl_norm_apply_mod": 2 * full, "bsl_norm_apply": 2 * full, "bsl_norm_apply_pool_mod": 2.25 * full,
             "bsl_norm_apply_pool": 2.25 * full, "bsl_norm_stats": full, "bsl_norm_bwd_reduce": 2 * full,
             "bsl_norm_bwd_apply": 3 * full, "bsl_maxpool2x2_bwd_add": 3.25 * full, "bsl_relu_bwd": 3 * full,
-            "bsl_stem_im2col": n * L.h * L.w * (L.cin * 4 + 128), "bsl_conv2d_head_fprop": n * L.h * L.w * (L.cin * 2 + 4 * L.cout),
+            "bsl_stem_im2col": n * L.h * L.w * (L.cin * 4 + 128),
+            "bsl_stem_im2col_ld": n * L.h * L.w * (L.cin * 4 + 2 * (32 if 9 * L.cin <= 32 else 64)),
+            "bsl_conv2d_head_fprop": n * L.h * L.w * (L.cin * 2 + 4 * L.cout),
             "bsl_conv2d_head_dgrad": n * L.h * L.w * (L.cin * 2 + 4 * L.cout),
             "bsl_conv2d_head_wgrad": n * L.h * L.w * (L.cin * 2 + 4 * L.cout)}.get(fn)
 
