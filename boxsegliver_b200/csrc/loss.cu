@@ -5,6 +5,7 @@
 //   sparse_dice_loss                      <- /root/reference/loss_metrics.py:180-226
 //   softmax + (p > 0.5) uint8 masks       <- /root/reference/NetworksV2/UNet.py:107-117
 //   metric_dice/voe/vd I, L, R sums       <- /root/reference/loss_metrics.py:261-339
+#include <cstdint>
 #include "reduce.cuh"
 
 using namespace bsl;
@@ -50,12 +51,13 @@ __global__ void label_counts_kernel(const int* __restrict__ labels, int hw, int 
 
 // Per-image class weights after the reference's per-image renormalisation, and the number of
 // pixels with non-zero weight (denominator of SUM_BY_NONZERO_WEIGHTS). One thread; n*classes is tiny.
+// One warp: lane i takes images i, i + 32, ...; the count of weighted pixels is a sum of integers, exact in any order.
 __global__ void weight_table_kernel(bsl_loss_desc d, const int* __restrict__ counts, float* __restrict__ wtab,
                                     double* __restrict__ nz_out) {
   bsl::pdl_enter();
-  if (threadIdx.x || blockIdx.x) return;
+  if (blockIdx.x || threadIdx.x >= 32) return;
   double nz = 0.0;
-  for (int img = 0; img < d.n; ++img) {
+  for (int img = threadIdx.x; img < d.n; img += 32) {
     float w[MAXC];
     if (d.weight_type == 0) {
       for (int c = 0; c < d.classes; ++c) w[c] = 1.f;  // constant 1.0, no renormalisation (:123-124)
@@ -81,7 +83,9 @@ __global__ void weight_table_kernel(bsl_loss_desc d, const int* __restrict__ cou
       if (w[c] != 0.f) nz += counts[img * d.classes + c];
     }
   }
-  *nz_out = nz;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+  if (threadIdx.x == 0) *nz_out = nz;
 }
 
 template <int C>
@@ -102,7 +106,25 @@ __device__ __forceinline__ void softmax_c(const float* __restrict__ lg, float (&
   lse_minus_max = logf(s);
 }
 
+// One pixel of the weighted cross entropy: returns w * ce and writes the C gradient entries to g.
 template <int C>
+__device__ __forceinline__ float wxent_pixel(const float* lg, int l, const float* __restrict__ wrow, float loss_scale,
+                                             float inv_nz, float* g) {
+  float pr[C], lse, mx;
+  softmax_c<C>(lg, pr, lse, mx);
+  const bool ok = l >= 0 && l < C;
+  const float w = ok ? wrow[l] : 0.f;
+  float ce = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) ce = (c == l) ? -(lg[c] - mx - lse) : ce;
+#pragma unroll
+  for (int c = 0; c < C; ++c) g[c] = loss_scale * w * (pr[c] - (c == l ? 1.f : 0.f)) * inv_nz;
+  return w * ce;
+}
+
+// VEC: a thread takes 4 consecutive pixels of one image (hw % 4 == 0): C 16-byte loads of logits, one of labels,
+// C 16-byte stores of the gradient, one image-index division per quad. Otherwise one pixel per thread.
+template <int C, bool VEC>
 __global__ void wxent_kernel(const float* __restrict__ logits, const int* __restrict__ labels, int hw,
                              long long pixels, const float* __restrict__ wtab, const double* __restrict__ nz_p,
                              float loss_scale, float* __restrict__ dlogits, double* __restrict__ part) {
@@ -111,37 +133,57 @@ __global__ void wxent_kernel(const float* __restrict__ logits, const int* __rest
   const double nz = *nz_p;
   const float inv_nz = nz > 0.0 ? (float)(1.0 / nz) : 0.f;
   double acc = 0.0;
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < pixels;
-       p += (long long)gridDim.x * blockDim.x) {
-    float lg[C], pr[C], lse, mx;
+  const long long t0 = blockIdx.x * (long long)blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  if (VEC) {
+    const bool small = pixels <= 0xffffffffLL;
+    for (long long q = t0; q < (pixels >> 2); q += nt) {
+      float lg[4 * C], g[4 * C];
+      const float4* src = reinterpret_cast<const float4*>(logits + q * 4 * C);
 #pragma unroll
-    for (int c = 0; c < C; ++c) lg[c] = logits[p * C + c];
-    softmax_c<C>(lg, pr, lse, mx);
-    const int l = labels[p];
-    const int img = (int)(p / hw);
-    const bool ok = l >= 0 && l < C;
-    const float w = ok ? wtab[img * C + l] : 0.f;
-    float ce = 0.f;
+      for (int i = 0; i < C; ++i) {
+        const float4 t = src[i];
+        lg[4 * i] = t.x, lg[4 * i + 1] = t.y, lg[4 * i + 2] = t.z, lg[4 * i + 3] = t.w;
+      }
+      const int4 lb = *reinterpret_cast<const int4*>(labels + q * 4);
+      const int img = small ? (int)((unsigned)(q << 2) / (unsigned)hw) : (int)((q << 2) / hw);
+      const float* wrow = wtab + img * C;
+      acc += (double)wxent_pixel<C>(lg, lb.x, wrow, loss_scale, inv_nz, g);
+      acc += (double)wxent_pixel<C>(lg + C, lb.y, wrow, loss_scale, inv_nz, g + C);
+      acc += (double)wxent_pixel<C>(lg + 2 * C, lb.z, wrow, loss_scale, inv_nz, g + 2 * C);
+      acc += (double)wxent_pixel<C>(lg + 3 * C, lb.w, wrow, loss_scale, inv_nz, g + 3 * C);
+      if (dlogits) {
+        float4* dst = reinterpret_cast<float4*>(dlogits + q * 4 * C);
 #pragma unroll
-    for (int c = 0; c < C; ++c) ce = (c == l) ? -(lg[c] - mx - lse) : ce;
-    acc += (double)(w * ce);
-    if (dlogits) {
+        for (int i = 0; i < C; ++i) dst[i] = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
+      }
+    }
+  } else {
+    for (long long p = t0; p < pixels; p += nt) {
+      float lg[C], g[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) dlogits[p * C + c] = loss_scale * w * (pr[c] - (c == l ? 1.f : 0.f)) * inv_nz;
+      for (int c = 0; c < C; ++c) lg[c] = logits[p * C + c];
+      acc += (double)wxent_pixel<C>(lg, labels[p], wtab + (int)(p / hw) * C, loss_scale, inv_nz, g);
+      if (dlogits) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) dlogits[p * C + c] = g[c];
+      }
     }
   }
   const double s = block_sum(acc, sm);
   if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
 
+// One warp: lane i adds partials i, i + 32, ... in order, then a fixed xor tree over the lanes.
 __global__ void wxent_final_kernel(const double* __restrict__ part, int blocks, const double* __restrict__ nz_p,
                                    float* __restrict__ loss) {
   bsl::pdl_enter();
-  if (threadIdx.x || blockIdx.x) return;
+  if (blockIdx.x || threadIdx.x >= 32) return;
   double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += part[b];
+  for (int b = threadIdx.x; b < blocks; b += 32) s += part[b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const double nz = *nz_p;
-  *loss = nz > 0.0 ? (float)(s / nz) : 0.f;
+  if (threadIdx.x == 0) *loss = nz > 0.0 ? (float)(s / nz) : 0.f;
 }
 
 template <int C>
@@ -363,8 +405,14 @@ int bsl_wxent_fwd_bwd(bsl_ctx* ctx, const bsl_loss_desc* d, const float* logits,
   BSL_LAUNCH_CHECK(ctx, "weight_table_kernel");
   const long long pixels = (long long)d->n * d->hw;
   const unsigned blocks = px_grid(ctx, pixels);
-  CLASS_SWITCH(d->classes, (bsl_launch(wxent_kernel<C>, dim3(blocks), dim3(256), 0, s, logits, labels, d->hw, pixels, w.wtab, w.nz,
-                                                                    d->loss_scale, dlogits, w.part)));
+  const bool vec = d->hw % 4 == 0 && ((uintptr_t)logits | (uintptr_t)labels | (uintptr_t)dlogits) % 16 == 0;
+  if (vec) {
+    CLASS_SWITCH(d->classes, (bsl_launch(wxent_kernel<C, true>, dim3(blocks), dim3(256), 0, s, logits, labels, d->hw, pixels,
+                                         w.wtab, w.nz, d->loss_scale, dlogits, w.part)));
+  } else {
+    CLASS_SWITCH(d->classes, (bsl_launch(wxent_kernel<C, false>, dim3(blocks), dim3(256), 0, s, logits, labels, d->hw, pixels,
+                                         w.wtab, w.nz, d->loss_scale, dlogits, w.part)));
+  }
   BSL_LAUNCH_CHECK(ctx, "wxent_kernel");
   bsl_launch(wxent_final_kernel, dim3(1), dim3(32), 0, s, w.part, (int)blocks, w.nz, loss);
   BSL_LAUNCH_CHECK(ctx, "wxent_final_kernel");

@@ -72,10 +72,12 @@ __global__ void momentum_kernel(float* __restrict__ w, const float* __restrict__
 
 __global__ void sumsq_final_kernel(const double* __restrict__ part, int blocks, double* __restrict__ out) {
   bsl::pdl_enter();
-  if (threadIdx.x || blockIdx.x) return;
+  if (blockIdx.x || threadIdx.x >= 32) return;   // one warp: lane i adds partials i, i + 32, ..., then a fixed xor tree
   double s = 0.0;
-  for (int b = 0; b < blocks; ++b) s += part[b];
-  *out = s;
+  for (int b = threadIdx.x; b < blocks; b += 32) s += part[b];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (threadIdx.x == 0) *out = s;
 }
 
 int opt_blocks(bsl_ctx* ctx, size_t n) {

@@ -166,13 +166,16 @@ __global__ void stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat
   }
 }
 
+// One warp per output: lane l adds chunks l, l + 32, ... in order (fp64), then a fixed xor tree over the lanes.
 __global__ void sum_chunks_kernel(const float* __restrict__ part, int chunks, int n, float* __restrict__ out) {
   bsl::pdl_enter();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;   // warp-uniform
   double s = 0.0;
-  for (int b = 0; b < chunks; ++b) s += (double)part[(long long)b * n + i];
-  out[i] = (float)s;
+  for (int b = lane; b < chunks; b += 32) s += (double)part[(long long)b * n + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[i] = (float)s;
 }
 
 // ---------------------------------------------------------------------------------- logits (1x1)
@@ -417,7 +420,7 @@ int bsl_conv2d_stem_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const float* x
     default: return bsl_fail(ctx, BSL_EUNSUPPORTED, "stem_wgrad: cin=%d (1..5)", d->cin);
   }
   BSL_LAUNCH_CHECK(ctx, "stem_wgrad_kernel");
-  bsl_launch(sum_chunks_kernel, dim3((nout + 127) / 128), dim3(128), 0, as_stream(stream), part, (int)chunks, nout, dw);
+  bsl_launch(sum_chunks_kernel, dim3((nout + 3) / 4), dim3(128), 0, as_stream(stream), part, (int)chunks, nout, dw);
   BSL_LAUNCH_CHECK(ctx, "sum_chunks_kernel");
   return BSL_OK;
 }
@@ -492,7 +495,7 @@ int bsl_conv2d_head_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x,
     const long long rpb = (pixels + cblocks - 1) / cblocks;
     bsl_launch(colsum_partial_kernel, dim3(cblocks), dim3(256), 0, s, dlogits, pixels, d->cout, rpb, cpart);
     BSL_LAUNCH_CHECK(ctx, "colsum_partial_kernel");
-    bsl_launch(sum_chunks_kernel, dim3(1), dim3(32), 0, s, cpart, cblocks, d->cout, dbias);
+    bsl_launch(sum_chunks_kernel, dim3((d->cout + 3) / 4), dim3(128), 0, s, cpart, cblocks, d->cout, dbias);
     BSL_LAUNCH_CHECK(ctx, "sum_chunks_kernel");
   }
   return BSL_OK;
