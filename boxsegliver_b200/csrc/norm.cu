@@ -910,20 +910,51 @@ namespace {
 // needs 126 registers (512 threads per SM) and reads at 4.1-4.8 TB/s; a read-only stream reaches 7.1 TB/s
 // (profiles/r01_hbm_read_probe.log). Same partial layout as pixel_reduce_kernel with K = 2 ([group][block][2][c]),
 // finished by pixel_reduce_final_kernel in block order: deterministic, no atomics.
-template <int U>
+// HEAD > 0 (last normalised layer, followed only by the 1x1 logits conv with HEAD classes): the gradient w.r.t. the
+// activation is not read from memory but recomputed per pixel from the HEAD fp32 logit gradients,
+//   da[ch] = bf16(sum_k dl[k] * w_head[ch][k])    (same FMA order and rounding as head_dgrad_kernel, small_conv.cu),
+// so Conv2DBackpropInput of the logits layer never writes its 128 bytes per pixel and the two backward passes of
+// this layer read 12 instead of 128 bytes per pixel for it. Bit-identical to the three-kernel path.
+template <int HEAD>
+__device__ __forceinline__ uint2 head_grad4(const float (&dl)[HEAD ? HEAD : 1], const float (&wq)[4][HEAD ? HEAD : 1]) {
+  float s[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    s[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < HEAD; ++k) s[j] = fmaf(dl[k], wq[j][k], s[j]);
+  }
+  uint2 out;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&out);
+  h[0] = __floats2bfloat162_rn(s[0], s[1]);
+  h[1] = __floats2bfloat162_rn(s[2], s[3]);
+  return out;
+}
+
+template <int U, int HEAD>
 __global__ void __launch_bounds__(256, 4)
 norm_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ da, int da_ld,
                         const float* __restrict__ mean, const float* __restrict__ rstd,
                         const float* __restrict__ scale, const float* __restrict__ shift, int c, int relu,
-                        long long pixels_per_group, long long ppb, float* __restrict__ part) {
+                        long long pixels_per_group, long long ppb, float* __restrict__ part,
+                        const float* __restrict__ dl, const float* __restrict__ wh) {
   bsl::pdl_enter();
   extern __shared__ float sm[];   // [rows][2][c]
+  constexpr int HK = HEAD ? HEAD : 1;
   const int cg = c / 4;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
   const int group = blockIdx.y;
   const int ch0 = g * 4;
   float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+  // filter of the logits layer in shared memory, re-read per batch of U pixels (volatile: kept out of registers,
+  // the kernel stays at 4 resident blocks per SM)
+  __shared__ float s_wh[HEAD ? 256 * HK : 1];
+  if (HEAD) {
+    for (int i = threadIdx.x; i < c * HK; i += blockDim.x) s_wh[i] = wh[i];
+    __syncthreads();
+  }
+  const volatile float* wv = s_wh + ch0 * HK;
   if (r < rows) {
     float sc[4], sh[4], rs[4], mr[4];
     const int o = group * c + ch0;
@@ -955,19 +986,49 @@ norm_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __n
       }
     };
     long long p = p0 + r;
-    for (; p + (long long)(U - 1) * rows < p1; p += (long long)U * rows) {
-      uint2 ry[U], rd[U];
+    if (HEAD) {
+      for (; p + (long long)(U - 1) * rows < p1; p += (long long)U * rows) {
+        uint2 ry[U];
+        float dv[U][HK];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        ry[u] = *reinterpret_cast<const uint2*>(y + (base + p + (long long)u * rows) * y_ld + ch0);
-        rd[u] = *reinterpret_cast<const uint2*>(da + (base + p + (long long)u * rows) * da_ld + ch0);
+        for (int u = 0; u < U; ++u) {
+          ry[u] = *reinterpret_cast<const uint2*>(y + (base + p + (long long)u * rows) * y_ld + ch0);
+#pragma unroll
+          for (int k = 0; k < HK; ++k) dv[u][k] = __ldg(dl + (base + p + (long long)u * rows) * HK + k);
+        }
+        float wq[4][HK];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < HK; ++k) wq[j][k] = wv[j * HK + k];
+#pragma unroll
+        for (int u = 0; u < U; ++u) one(ry[u], head_grad4<HEAD>(dv[u], wq));
       }
+      for (; p < p1; p += rows) {
+        float dv[HK], wq[4][HK];
 #pragma unroll
-      for (int u = 0; u < U; ++u) one(ry[u], rd[u]);
+        for (int k = 0; k < HK; ++k) dv[k] = __ldg(dl + (base + p) * HK + k);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < HK; ++k) wq[j][k] = wv[j * HK + k];
+        one(*reinterpret_cast<const uint2*>(y + (base + p) * y_ld + ch0), head_grad4<HEAD>(dv, wq));
+      }
+    } else {
+      for (; p + (long long)(U - 1) * rows < p1; p += (long long)U * rows) {
+        uint2 ry[U], rd[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          ry[u] = *reinterpret_cast<const uint2*>(y + (base + p + (long long)u * rows) * y_ld + ch0);
+          rd[u] = *reinterpret_cast<const uint2*>(da + (base + p + (long long)u * rows) * da_ld + ch0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) one(ry[u], rd[u]);
+      }
+      for (; p < p1; p += rows)
+        one(*reinterpret_cast<const uint2*>(y + (base + p) * y_ld + ch0),
+            *reinterpret_cast<const uint2*>(da + (base + p) * da_ld + ch0));
     }
-    for (; p < p1; p += rows)
-      one(*reinterpret_cast<const uint2*>(y + (base + p) * y_ld + ch0),
-          *reinterpret_cast<const uint2*>(da + (base + p) * da_ld + ch0));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       sm[(r * 2 + 0) * c + ch0 + j] = a0[j];
@@ -985,14 +1046,16 @@ norm_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __n
 
 // The un-guided backward apply with 4 channels per thread (8-byte loads / stores): ~48 registers instead of 80.
 //   dy = scale * dz + k1 * v + k0,  k1 = -scale * c2 * rstd,  k0 = scale * (c2 * rstd * mean - c1)
-template <int U>
+template <int U, int HEAD>
 __global__ void __launch_bounds__(256, 4)
 norm_bwd_apply4_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv_bfloat16* __restrict__ da, int da_ld,
                        __nv_bfloat16* __restrict__ dy, int dy_ld, long long pixels_per_group, int c, int relu,
                        const float* __restrict__ mean, const float* __restrict__ rstd,
                        const float* __restrict__ scale, const float* __restrict__ shift,
-                       const float* __restrict__ c1, const float* __restrict__ c2, int gstride) {
+                       const float* __restrict__ c1, const float* __restrict__ c2, int gstride,
+                       const float* __restrict__ dl, const float* __restrict__ wh) {
   bsl::pdl_enter();
+  constexpr int HK = HEAD ? HEAD : 1;
   const int cg = c / 4;
   const int rows = blockDim.x / cg;
   const int g = threadIdx.x % cg, r = threadIdx.x / cg;
@@ -1030,7 +1093,44 @@ norm_bwd_apply4_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv
     }
     return outv;
   };
-  if (r < rows) {
+  __shared__ float s_wh[HEAD ? 256 * HK : 1];   // see norm_bwd_reduce4_kernel
+  if (HEAD) {
+    for (int i = threadIdx.x; i < c * HK; i += blockDim.x) s_wh[i] = wh[i];
+    __syncthreads();
+  }
+  const volatile float* wv = s_wh + ch0 * HK;
+  if (r < rows && HEAD) {
+    long long p = (long long)blockIdx.x * rows + r;
+    for (; p + (U - 1) * stride < pixels_per_group; p += U * stride) {
+      uint2 ry[U];
+      float dv[U][HK];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        ry[u] = *reinterpret_cast<const uint2*>(y + (base + p + u * stride) * y_ld + ch0);
+#pragma unroll
+        for (int k = 0; k < HK; ++k) dv[u][k] = __ldg(dl + (base + p + u * stride) * HK + k);
+      }
+      float wq[4][HK];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < HK; ++k) wq[j][k] = wv[j * HK + k];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        *reinterpret_cast<uint2*>(dy + (base + p + u * stride) * dy_ld + ch0) = one(ry[u], head_grad4<HEAD>(dv[u], wq));
+    }
+    for (; p < pixels_per_group; p += stride) {
+      float dv[HK], wq[4][HK];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < HK; ++k) wq[j][k] = wv[j * HK + k];
+#pragma unroll
+      for (int k = 0; k < HK; ++k) dv[k] = __ldg(dl + (base + p) * HK + k);
+      *reinterpret_cast<uint2*>(dy + (base + p) * dy_ld + ch0) =
+          one(*reinterpret_cast<const uint2*>(y + (base + p) * y_ld + ch0), head_grad4<HEAD>(dv, wq));
+    }
+  } else if (r < rows) {
     long long p = (long long)blockIdx.x * rows + r;
     for (; p + (U - 1) * stride < pixels_per_group; p += U * stride) {
       uint2 ry[U], rd[U];
@@ -1052,7 +1152,8 @@ norm_bwd_apply4_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv
 
 int run_bwd_reduce4(bsl_ctx* ctx, const bsl_norm_desc* d, const __nv_bfloat16* xb, const __nv_bfloat16* db, int dy_ld,
                     const float* mean, const float* rstd, const float* scale, const float* shift, long long ppg,
-                    int groups, double* sums, cudaStream_t stream) {
+                    int groups, double* sums, cudaStream_t stream, const float* dl = nullptr,
+                    const float* wh = nullptr, int classes = 0) {
   const int c = d->c, cg = c / 4;
   const int rows = 256 / cg;
   const int threads = rows * cg;
@@ -1066,8 +1167,16 @@ int run_bwd_reduce4(bsl_ctx* ctx, const bsl_norm_desc* d, const __nv_bfloat16* x
   int rc = bsl_scratch(ctx, (size_t)groups * blocks * 2 * c * sizeof(float), &part, stream);
   if (rc) return rc;
   const size_t smem = (size_t)rows * 2 * c * sizeof(float);
-  bsl_launch(norm_bwd_reduce4_kernel<4>, dim3(dim3(blocks, groups)), dim3(threads), smem, stream, xb, d->x_ld, db, dy_ld, mean, rstd, scale,
-                                                                            shift, c, d->relu, ppg, ppb, part);
+  auto go = [&](auto kern) {
+    bsl_launch(kern, dim3(blocks, groups), dim3(threads), smem, stream, xb, d->x_ld, db, dy_ld, mean, rstd, scale, shift, c,
+               d->relu, ppg, ppb, part, dl, wh);
+  };
+  switch (classes) {
+    case 0: go(norm_bwd_reduce4_kernel<4, 0>); break;
+    case 2: go(norm_bwd_reduce4_kernel<4, 2>); break;
+    case 3: go(norm_bwd_reduce4_kernel<4, 3>); break;
+    default: go(norm_bwd_reduce4_kernel<4, 4>); break;
+  }
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_reduce4_kernel");
   bsl_launch(pixel_reduce_final_kernel, dim3(dim3((2 * c + 31) / 32, groups)), dim3(256), 0, stream, part, blocks, 2 * c, sums);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel");
@@ -1109,6 +1218,65 @@ int bsl_norm_bwd_reduce(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, con
                         const float* mean, const float* rstd, const float* scale, const float* shift,
                         double* sums, void* stream) {
   return bsl_norm_bwd_reduce_mod(ctx, d, x, dy, dy_ld, mean, rstd, scale, shift, nullptr, sums, stream);
+}
+
+// ---- last normalised layer + logits layer: backward passes that recompute the activation gradient from dlogits
+static bool bwd_head_ok(const bsl_norm_desc* d, int classes, int dx_ld) {
+  return d->c % 4 == 0 && d->c <= 256 && 256 % (d->c / 4) == 0 && d->x_ld % 4 == 0 && dx_ld % 4 == 0 && classes >= 2 &&
+         classes <= 4;
+}
+
+int bsl_norm_bwd_head_ok(bsl_ctx* ctx, const bsl_norm_desc* d, int classes) {
+  return ctx && d && check_norm(ctx, d) == BSL_OK && bwd_head_ok(d, classes, 4) ? 1 : 0;
+}
+
+int bsl_norm_bwd_reduce_head(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const float* dlogits,
+                             const float* w_head, int classes, const float* mean, const float* rstd,
+                             const float* scale, const float* shift, double* sums, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (!x || !dlogits || !w_head || !mean || !rstd || !scale || !shift || !sums)
+    return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_reduce_head: null buffer");
+  if (!bwd_head_ok(d, classes, 4))
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "norm_bwd_reduce_head: c=%d (multiple of 4 dividing 1024, <= 256), classes=%d (2..4)",
+                    d->c, classes);
+  const int groups = d->mode ? d->n : 1;
+  const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
+  return run_bwd_reduce4(ctx, d, reinterpret_cast<const __nv_bfloat16*>(x), nullptr, 0, mean, rstd, scale, shift, ppg,
+                         groups, sums, as_stream(stream), dlogits, w_head, classes);
+}
+
+int bsl_norm_bwd_apply_head(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const float* dlogits,
+                            const float* w_head, int classes, const float* mean, const float* rstd,
+                            const float* scale, const float* shift, const float* c1, const float* c2, void* dx,
+                            int dx_ld, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (!x || !dlogits || !w_head || !mean || !rstd || !scale || !shift || !c1 || !c2 || !dx)
+    return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_apply_head: null buffer");
+  if (!bwd_head_ok(d, classes, dx_ld))
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "norm_bwd_apply_head: c=%d (multiple of 4 dividing 1024, <= 256), classes=%d (2..4)",
+                    d->c, classes);
+  const int groups = d->mode ? d->n : 1;
+  const long long ppg = d->mode ? d->hw : (long long)d->n * d->hw;
+  const int cg4 = d->c / 4, rows4 = 256 / cg4;
+  long long want = (ppg + (long long)rows4 * 4 - 1) / ((long long)rows4 * 4);
+  const long long cap = (16LL * ctx->sm_count + groups - 1) / groups;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  auto go = [&](auto kern) {
+    bsl_launch(kern, dim3((unsigned)want, groups), dim3(rows4 * cg4), 0, as_stream(stream),
+               reinterpret_cast<const __nv_bfloat16*>(x), d->x_ld, (const __nv_bfloat16*)nullptr, 0,
+               reinterpret_cast<__nv_bfloat16*>(dx), dx_ld, ppg, d->c, d->relu, mean, rstd, scale, shift, c1, c2,
+               d->mode ? d->c : 0, dlogits, w_head);
+  };
+  switch (classes) {
+    case 2: go(norm_bwd_apply4_kernel<4, 2>); break;
+    case 3: go(norm_bwd_apply4_kernel<4, 3>); break;
+    default: go(norm_bwd_apply4_kernel<4, 4>); break;
+  }
+  BSL_LAUNCH_CHECK(ctx, "norm_bwd_apply4_kernel (logits gradient recomputed)");
+  return BSL_OK;
 }
 
 int bsl_norm_bwd_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, const double* sums, float* c1, float* c2,
@@ -1199,8 +1367,9 @@ int bsl_norm_bwd_apply_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, const void
     const long long cap = (16LL * ctx->sm_count + groups - 1) / groups;
     if (want > cap) want = cap;
     if (want < 1) want = 1;
-    bsl_launch(norm_bwd_apply4_kernel<4>, dim3(dim3((unsigned)want, groups)), dim3(rows4 * cg4), 0, s, 
-        xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean, rstd, scale, shift, c1, c2, gstride);
+    bsl_launch(norm_bwd_apply4_kernel<4, 0>, dim3((unsigned)want, groups), dim3(rows4 * cg4), 0, s,
+               xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean, rstd, scale, shift, c1, c2, gstride,
+               (const float*)nullptr, (const float*)nullptr);
     BSL_LAUNCH_CHECK(ctx, "norm_bwd_apply4_kernel");
     return BSL_OK;
   }

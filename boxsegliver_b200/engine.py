@@ -160,6 +160,10 @@ class UNetEngine:
         # measured: the mask loads in the epilogue cost dgrad +0.45 ms, more than the 0.49 ms relu_bwd pass they replace
         self._fuse_relu_bwd = os.environ.get("BSL_FUSE_RELU_BWD", "0") != "0"
         self._fuse_head = os.environ.get("BSL_FUSE_HEAD", "1") != "0"
+        # backward of the last normalised layer with the logits-layer dgrad recomputed per pixel from dlogits
+        # (bsl_norm_bwd_reduce_head / _apply_head) instead of a 128-byte-per-pixel gradient tensor; bit-identical
+        self._fuse_head_bwd = os.environ.get("BSL_FUSE_HEAD_BWD", "0") != "0"
+        self._head_grad = None
         self.aux_stream = ctx.new_stream()
         self._pipe_rows = 2 * len(self.layers)
         self.pipe_buf = self._alloc(2 * self._pipe_rows * 64 * 4).zero()
@@ -694,17 +698,32 @@ class UNetEngine:
         """Hook between norm_finalize and norm_apply; returns the bsl_guide of the layer (or None)."""
         return None
 
+    def _is_modulated(self, L: ConvL) -> bool:
+        return False
+
     def _norm_backward_reduce(self, L: ConvL, nd, q, cur):
         """First half of the gradient through ReLU + normalisation of layer L: the per-channel sums over `cur` (the
         gradient w.r.t. the activation) and the gradients of the normaliser's own parameters (into G)."""
         call, s, ns = self.ctx.call, self.stream, self.norm_scope
-        call("bsl_norm_bwd_reduce", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"],
-             q["scale"], q["shift"], q["sums"], s)
+        if self._head_grad is not None:
+            dl, wh, classes = self._head_grad
+            call("bsl_norm_bwd_reduce_head", C.byref(nd), L.y.p, dl, wh, C.c_int(classes), q["mean"], q["rstd"],
+                 q["scale"], q["shift"], q["sums"], s)
+        else:
+            call("bsl_norm_bwd_reduce", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"],
+                 q["scale"], q["shift"], q["sums"], s)
         call("bsl_norm_bwd_finalize", C.byref(nd), q["sums"], q["c1"], q["c2"],
              self._pp(self.G, f"{L.scope}/{ns}/gamma"), self._pp(self.G, f"{L.scope}/{ns}/beta"), s)
 
     def _norm_backward_apply(self, L: ConvL, nd, q, cur, oth, stream, sig=None):
         """Second half: `cur` -> `oth` (gradient w.r.t. the conv output), optionally publishing image slices."""
+        if self._head_grad is not None:
+            dl, wh, classes = self._head_grad
+            self._head_grad = None
+            assert sig is None
+            self.ctx.call("bsl_norm_bwd_apply_head", C.byref(nd), L.y.p, dl, wh, C.c_int(classes), q["mean"], q["rstd"],
+                          q["scale"], q["shift"], q["c1"], q["c2"], oth.p, C.c_int(L.cout), stream)
+            return
         self.ctx.call("bsl_norm_bwd_apply_mod_pipe", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"],
                       q["scale"], q["shift"], q["c1"], q["c2"], None, oth.p, C.c_int(L.cout),
                       C.byref(sig) if sig is not None else None, stream)
@@ -765,8 +784,15 @@ class UNetEngine:
                 fork()
                 call("bsl_conv2d_head_wgrad", C.byref(d), L.x.p, self.dlogits.p, self._pp(self.G, f"{L.scope}/weights"),
                      self._pp(self.G, f"{L.scope}/biases"), ws)
-                call("bsl_conv2d_head_dgrad", C.byref(d), self.dlogits.p, self._pp(self.W, f"{L.scope}/weights"),
-                     cur.p, s)
+                prev = self.layers[idx - 1]
+                if (self._fuse_head_bwd and not piping and prev.kind == "conv" and prev.pooled is None
+                        and not self._is_modulated(prev) and prev.a is L.x
+                        and ctx.lib.bsl_norm_bwd_head_ok(ctx.h, C.byref(self._norm_desc(prev)), C.c_int(L.cout))):
+                    # no Conv2DBackpropInput launch: the two normalisation-backward passes of `prev` recompute it
+                    self._head_grad = (self.dlogits.p, self._pp(self.W, f"{L.scope}/weights"), L.cout)
+                else:
+                    call("bsl_conv2d_head_dgrad", C.byref(d), self.dlogits.p, self._pp(self.W, f"{L.scope}/weights"),
+                         cur.p, s)
                 self._after_grad(L)
                 continue
             if L.kind in ("stem", "conv"):

@@ -239,6 +239,9 @@ class GUNetEngine(UNetEngine):
         return self._guide_struct(L)
 
     # ------------------------------------------------------------------ backward
+    def _is_modulated(self, L: ConvL) -> bool:
+        return L.mod_off is not None or L.sp_off is not None
+
     def _norm_backward_reduce(self, L: ConvL, nd, q, cur):
         if L.mod_off is None and L.sp_off is None:
             return super()._norm_backward_reduce(L, nd, q, cur)
@@ -259,6 +262,8 @@ class GUNetEngine(UNetEngine):
              C.c_int(2 * L.cout), dbg, s)
 
     def _norm_backward_apply(self, L: ConvL, nd, q, cur, oth, stream, sig=None):
+        if self._head_grad is not None:
+            return super()._norm_backward_apply(L, nd, q, cur, oth, stream, sig)
         guide = self._guide_struct(L)
         self.ctx.call("bsl_norm_bwd_apply_mod_pipe", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"],
                       q["scale"], q["shift"], q["c1"], q["c2"], C.byref(guide) if guide is not None else None, oth.p,

@@ -271,6 +271,19 @@ int bsl_norm_bwd_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, const double* su
 int bsl_norm_bwd_apply(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const void* dy_bf16, int dy_ld,
                        const float* mean, const float* rstd, const float* scale, const float* shift,
                        const float* c1, const float* c2, void* dx_bf16, int dx_ld, void* stream);
+/* Backward of the LAST normalised layer when only the 1x1 logits conv reads its activation (NetworksV2/UNet.py:94,100):
+ * the gradient w.r.t. the activation, da[p][ch] = bf16(sum_k dlogits[p][k] * w_head[ch][k]), is recomputed per pixel
+ * inside the two passes instead of being written by bsl_conv2d_head_dgrad and read back twice (12 instead of 128
+ * bytes per pixel and pass). Bit-identical to head_dgrad -> norm_bwd_reduce -> norm_bwd_apply. classes in 2..4,
+ * c <= 256 (bsl_norm_bwd_head_ok). */
+int bsl_norm_bwd_head_ok(bsl_ctx* ctx, const bsl_norm_desc* d, int classes);
+int bsl_norm_bwd_reduce_head(bsl_ctx* ctx, const bsl_norm_desc* d, const void* y_bf16, const float* dlogits,
+                             const float* w_head /*[c][classes]*/, int classes, const float* mean, const float* rstd,
+                             const float* scale, const float* shift, double* sums, void* stream);
+int bsl_norm_bwd_apply_head(bsl_ctx* ctx, const bsl_norm_desc* d, const void* y_bf16, const float* dlogits,
+                            const float* w_head, int classes, const float* mean, const float* rstd, const float* scale,
+                            const float* shift, const float* c1, const float* c2, void* dx_bf16, int dx_ld,
+                            void* stream);
 /* ---- GUNet guide modulation of an instance-norm layer (NetworksV2/GUNet.py:162-217, modulated_conv_block):
  *   conv -> norm(center, scale per YAML) -> * gamma_mod[n, c] -> + (sp_guide[n, p, :] . w[:, c] + b[c]) -> ReLU
  * gamma_mod is this layer's slice of the context MLP output (conditional_normalization, GUNet.py:119-133); the

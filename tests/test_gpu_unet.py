@@ -234,10 +234,12 @@ def test_image_slice_pipelining_is_bit_identical(ctx):
     out = []
     # also: the logits conv fused into the last normalisation pass (bsl_norm_apply_head) against the two-pass path,
     # and the transposed-conv ReluGrad fused into the decoder dgrad's epilogue
-    for pipe, head, relu in ((False, False, False), (True, True, False), (False, True, True)):
+    # and the logits-layer dgrad recomputed inside the last layer's normalisation backward (bsl_norm_bwd_*_head)
+    for pipe, head, relu, head_bwd in ((False, False, False, False), (True, True, False, False),
+                                       (False, True, True, True), (False, False, False, True)):
         eng = UNetEngine(ctx, EngineConfig(batch=n, height=hw, width=hw, weight_decay_rate=1e-5,
                                            loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4)))
-        eng._pipe_on, eng._fuse_head, eng._fuse_relu_bwd = pipe, head, relu
+        eng._pipe_on, eng._fuse_head, eng._fuse_relu_bwd, eng._fuse_head_bwd = pipe, head, relu, head_bwd
         eng.init_weights(seed=5)
         eng.set_inputs(images, labels)
         for _ in range(2):
