@@ -6,6 +6,7 @@ the product path raises. (The CPU oracle lives under oracle/ and is test infrast
 from __future__ import annotations
 
 import ctypes as C
+import os
 import re
 from pathlib import Path
 
@@ -108,6 +109,9 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    global LIB_PATH
+    if os.environ.get("BSL_LIB"):       # tuning aid: A/B of two builds of the library in one process launch each
+        LIB_PATH = Path(os.environ["BSL_LIB"]).resolve()
     if not LIB_PATH.exists():
         raise ImportError(
             f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "

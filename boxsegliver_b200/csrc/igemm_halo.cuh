@@ -148,6 +148,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
       }
       if (ok) umma_commit(tfull);
+      pdl_trigger_late();
     }
   } else {
     const int q4 = warp & 3;
@@ -310,6 +311,7 @@ wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if (++stage == WG2_STAGES) { stage = 0; phase ^= 1; }
       }
       if (ok) umma_commit(tfull);
+      pdl_trigger_late();
     }
   } else {
     const int q4 = warp & 3;
@@ -715,6 +717,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (ok) umma_commit(acc_full + 8 * buf);
         if (++buf == ACC_BUFS) { buf = 0; pacc ^= 1; }
       }
+      pdl_trigger_late();
       if (p.dbg != nullptr) {
         p.dbg[blockIdx.x * 4 + 0] = clock64() - t_all;
         p.dbg[blockIdx.x * 4 + 1] = w_acc;

@@ -57,6 +57,16 @@ __device__ __forceinline__ void pdl_trigger() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
+// Late trigger (one thread per CTA is enough): issued by the UMMA issuer of the tensor-core kernels once its last
+// accumulator is committed, so the successor's blocks are scheduled, and run their prologue, under the last epilogue.
+#ifndef BSL_PDL_LATE
+#define BSL_PDL_LATE 0
+#endif
+__device__ __forceinline__ void pdl_trigger_late() {
+#if BSL_PDL_LATE
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() {
   pdl_trigger();
