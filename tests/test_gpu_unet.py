@@ -249,7 +249,10 @@ def test_image_slice_pipelining_is_bit_identical(ctx):
         eng.close()
     for other in out[1:]:
         assert np.array_equal(out[0][0], other[0])
-        assert out[0][1] == other[1]
+        # (data loss, L2 term): the L2 term is 0.5 * rate * sum w^2 over ALL weights after the first step, the
+        # transposed-conv biases included -- their gradient may differ in the last bits (below), so may their square sum
+        assert out[0][1][0] == other[1][0]
+        assert abs(out[0][1][1] - other[1][1]) <= 1e-12 * abs(out[0][1][1])
         for k, g in out[0][2].items():
             if k.endswith("Conv2d_transpose/biases"):
                 # the bias gradient is a sum over pixels: the fused-ReluGrad schedule takes it from the filter-gradient
