@@ -12,35 +12,36 @@
 using namespace bsl;
 
 namespace bsl {
-// Block = 32 consecutive outputs x 8 partial lanes (256 threads): lane q sums partials q, q+8, ...
-// (coalesced across outputs, 4 independent loads in flight), then the 8 lane sums are added in a
-// fixed order.
-__global__ void pixel_reduce_final_kernel(const float* __restrict__ part, int blocks, int kc,
-                                          double* __restrict__ out) {
+// Block = 32 consecutive outputs x 32 partial lanes (1024 threads): lane q sums partials q, q + 32, ... in order
+// (coalesced across outputs, 4 independent loads in flight), then the 32 lane sums are added in a fixed order.
+// With up to 1184 partial blocks per output the 8-lane version spent ~10 us per launch on its chain of dependent
+// L2 round trips, 41 launches per training step.
+__global__ void __launch_bounds__(1024) pixel_reduce_final_kernel(const float* __restrict__ part, int blocks, int kc,
+                                                                  double* __restrict__ out) {
   bsl::pdl_enter();
-  __shared__ double sm[8][32];
+  __shared__ double sm[32][33];
   const int il = threadIdx.x & 31, q = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + il;
   double s = 0.0;
   if (i < kc) {
     const float* p = part + (long long)blockIdx.y * blocks * kc + i;
     int b = q;
-    for (; b + 24 < blocks; b += 32) {
-      const float v0 = p[(long long)b * kc], v1 = p[(long long)(b + 8) * kc], v2 = p[(long long)(b + 16) * kc],
-                  v3 = p[(long long)(b + 24) * kc];
+    for (; b + 96 < blocks; b += 128) {
+      const float v0 = p[(long long)b * kc], v1 = p[(long long)(b + 32) * kc], v2 = p[(long long)(b + 64) * kc],
+                  v3 = p[(long long)(b + 96) * kc];
       s += (double)v0;
       s += (double)v1;
       s += (double)v2;
       s += (double)v3;
     }
-    for (; b < blocks; b += 8) s += (double)p[(long long)b * kc];
+    for (; b < blocks; b += 32) s += (double)p[(long long)b * kc];
   }
   sm[q][il] = s;
   __syncthreads();
   if (q == 0 && i < kc) {
     double t = sm[0][il];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) t += sm[k][il];
+    for (int k = 1; k < 32; ++k) t += sm[k][il];
     out[(long long)blockIdx.y * kc + i] = t;
   }
 }
@@ -1178,7 +1179,7 @@ int run_bwd_reduce4(bsl_ctx* ctx, const bsl_norm_desc* d, const __nv_bfloat16* x
     default: go(norm_bwd_reduce4_kernel<4, 4>); break;
   }
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_reduce4_kernel");
-  bsl_launch(pixel_reduce_final_kernel, dim3(dim3((2 * c + 31) / 32, groups)), dim3(256), 0, stream, part, blocks, 2 * c, sums);
+  bsl_launch(pixel_reduce_final_kernel, dim3(dim3((2 * c + 31) / 32, groups)), dim3(1024), 0, stream, part, blocks, 2 * c, sums);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel");
   return BSL_OK;
 }

@@ -179,7 +179,8 @@ relu_bwd_bias4_kernel(const __nv_bfloat16* __restrict__ y, int y_ld, const __nv_
 }  // namespace
 
 namespace bsl {
-__global__ void pixel_reduce_final_kernel(const float* __restrict__ part, int blocks, int kc, double* __restrict__ out);
+__global__ void __launch_bounds__(1024) pixel_reduce_final_kernel(const float* __restrict__ part, int blocks, int kc,
+                                                                  double* __restrict__ out);
 }
 
 extern "C" int bsl_relu_bwd_bias(bsl_ctx* ctx, long long pixels, int c, const void* y, int y_ld, const void* dy,
@@ -206,7 +207,7 @@ extern "C" int bsl_relu_bwd_bias(bsl_ctx* ctx, long long pixels, int c, const vo
         reinterpret_cast<const __nv_bfloat16*>(y), y_ld, reinterpret_cast<const __nv_bfloat16*>(dy), dy_ld,
         reinterpret_cast<__nv_bfloat16*>(out), out_ld, c, pixels, ppb, base);
     BSL_LAUNCH_CHECK(ctx, "relu_bwd_bias4_kernel");
-    bsl_launch(bsl::pixel_reduce_final_kernel, dim3(dim3((c + 31) / 32, 1)), dim3(256), 0, s, base, blocks, c, tmp);
+    bsl_launch(bsl::pixel_reduce_final_kernel, dim3(dim3((c + 31) / 32, 1)), dim3(1024), 0, s, base, blocks, c, tmp);
     BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel");
     bsl_launch(f64_to_f32_kernel, dim3((c + 127) / 128), dim3(128), 0, s, tmp, dbias, c);
     BSL_LAUNCH_CHECK(ctx, "f64_to_f32_kernel");

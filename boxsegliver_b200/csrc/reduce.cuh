@@ -90,7 +90,7 @@ __global__ void pixel_reduce_kernel(F f, long long pixels_per_group, long long p
 }
 
 // out[group][i] = sum_b part[group][b][i], i in [0, kc), fp64 accumulation in block order.
-__global__ void pixel_reduce_final_kernel(const float* __restrict__ part, int blocks, int kc,
+__global__ void __launch_bounds__(1024) pixel_reduce_final_kernel(const float* __restrict__ part, int blocks, int kc,
                                           double* __restrict__ out);
 
 struct ReducePlan {
@@ -134,7 +134,7 @@ int run_pixel_reduce(bsl_ctx* ctx, const F& f, long long pixels_per_group, int g
                                                                                           p.ppb, c, part);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_kernel");
   const int kc = F::K * c;
-  bsl_launch(pixel_reduce_final_kernel, dim3(dim3((kc + 31) / 32, groups)), dim3(256), 0, stream, part, p.blocks, kc, out);
+  bsl_launch(pixel_reduce_final_kernel, dim3(dim3((kc + 31) / 32, groups)), dim3(1024), 0, stream, part, p.blocks, kc, out);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel");
   return BSL_OK;
 }

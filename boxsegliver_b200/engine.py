@@ -162,7 +162,7 @@ class UNetEngine:
         self._fuse_head = os.environ.get("BSL_FUSE_HEAD", "1") != "0"
         # backward of the last normalised layer with the logits-layer dgrad recomputed per pixel from dlogits
         # (bsl_norm_bwd_reduce_head / _apply_head) instead of a 128-byte-per-pixel gradient tensor; bit-identical
-        self._fuse_head_bwd = os.environ.get("BSL_FUSE_HEAD_BWD", "0") != "0"
+        self._fuse_head_bwd = os.environ.get("BSL_FUSE_HEAD_BWD", "1") != "0"
         self._head_grad = None
         self.aux_stream = ctx.new_stream()
         self._pipe_rows = 2 * len(self.layers)
