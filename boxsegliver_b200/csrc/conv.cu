@@ -157,67 +157,47 @@ SplitPlan plan_split(bsl_ctx* ctx, int mn_tiles, int k_tiles) {
   return {k_tiles, per, splits};
 }
 
-// out[i] = sum_s part[s * stride + i], float4 per thread. Q = 1: one thread walks all splits (few splits, large n).
-// Q = 8: block = 32 float4 outputs x 8 lanes, lane q adds splits q, q + 8, ... in order and the 8 lane sums are added
-// in a fixed order -- the 64- and 128-channel layers have 74-148 splits of a small filter, and a single thread's chain
-// of dependent L2 round trips made their reducer take 15-25 us. Fixed order either way => bit-reproducible.
-template <int Q>
 __global__ void reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, long long n,
-                                     int splits, long long stride) {
+                                     int splits) {
   bsl::pdl_enter();
-  __shared__ float4 sm[Q > 1 ? Q : 1][32];
-  const int il = Q > 1 ? (threadIdx.x & 31) : 0, q = Q > 1 ? (threadIdx.x >> 5) : 0;
-  const long long i = Q > 1 ? (blockIdx.x * 32LL + il) * 4 : (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < n) {
-    int sp = q;
-    for (; sp + 3 * Q < splits; sp += 4 * Q) {
-      const float4 v0 = *reinterpret_cast<const float4*>(part + sp * stride + i);
-      const float4 v1 = *reinterpret_cast<const float4*>(part + (sp + Q) * stride + i);
-      const float4 v2 = *reinterpret_cast<const float4*>(part + (sp + 2 * Q) * stride + i);
-      const float4 v3 = *reinterpret_cast<const float4*>(part + (sp + 3 * Q) * stride + i);
-      acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
-      acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
-      acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
-      acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
-    }
-    for (; sp < splits; sp += Q) {
-      const float4 v = *reinterpret_cast<const float4*>(part + sp * stride + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-    }
+  long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 acc = *reinterpret_cast<const float4*>(part + i);
+  for (int s = 1; s < splits; ++s) {  // fixed order => bit-reproducible
+    float4 v = *reinterpret_cast<const float4*>(part + s * n + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  if (Q == 1) {
-    if (i < n) *reinterpret_cast<float4*>(out + i) = acc;
-    return;
+  *reinterpret_cast<float4*>(out + i) = acc;
+}
+
+__global__ void reduce_splits_strided_kernel(const float* __restrict__ part, float* __restrict__ out, long long n,
+                                             int splits, long long stride) {
+  bsl::pdl_enter();
+  long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float4 acc = *reinterpret_cast<const float4*>(part + i);
+  for (int s = 1; s < splits; ++s) {  // fixed order => bit-reproducible
+    float4 v = *reinterpret_cast<const float4*>(part + s * stride + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
-  sm[q][il] = acc;
-  __syncthreads();
-  if (q == 0 && i < n) {
-    float4 t = sm[0][il];
-#pragma unroll
-    for (int k = 1; k < Q; ++k) {
-      const float4 v = sm[k][il];
-      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-    }
-    *reinterpret_cast<float4*>(out + i) = t;
-  }
+  *reinterpret_cast<float4*>(out + i) = acc;
 }
 
 int reduce_splits_strided(bsl_ctx* ctx, const float* part, float* out, long long n, int splits, long long stride,
                           cudaStream_t s) {
-  if (splits >= 16) {
-    const long long blocks = (n / 4 + 31) / 32;
-    bsl_launch(reduce_splits_kernel<8>, dim3((unsigned)blocks), dim3(256), 0, s, part, out, n, splits, stride);
-  } else {
-    const long long blocks = (n / 4 + 255) / 256;
-    bsl_launch(reduce_splits_kernel<1>, dim3((unsigned)blocks), dim3(256), 0, s, part, out, n, splits, stride);
-  }
-  BSL_LAUNCH_CHECK(ctx, "reduce_splits_kernel");
+  const int threads = 256;
+  const long long blocks = (n / 4 + threads - 1) / threads;
+  bsl_launch(reduce_splits_strided_kernel, dim3((unsigned)blocks), dim3(threads), 0, s, part, out, n, splits, stride);
+  BSL_LAUNCH_CHECK(ctx, "reduce_splits_strided_kernel");
   return BSL_OK;
 }
 
 int reduce_splits(bsl_ctx* ctx, const float* part, float* out, long long n, int splits, cudaStream_t s) {
-  return reduce_splits_strided(ctx, part, out, n, splits, n, s);
+  int threads = 256;
+  long long blocks = (n / 4 + threads - 1) / threads;
+  bsl_launch(reduce_splits_kernel, dim3((unsigned)blocks), dim3(threads), 0, s, part, out, n, splits);
+  BSL_LAUNCH_CHECK(ctx, "reduce_splits_kernel");
+  return BSL_OK;
 }
 
 
