@@ -141,7 +141,7 @@ class UNetEngine:
         self._fork_pre = os.environ.get("BSL_WGRAD_FORK", "pre") == "pre"
         # Programmatic dependent launch (csrc/internal.h bsl_launch): 0 off, 1 every launch (default), 2 only in the
         # phases where the compute stream has the SMs to itself (forward, loss head, optimizer). Measured on B200
-        # (tools/pdl_ab.sh): the launch attribute alone, every kernel waiting with griddepcontrol.wait before its first
+        # (tools/ab.sh, profiles/r01_ab_experiments.md): the launch attribute alone, every kernel waiting with griddepcontrol.wait before its first
         # global access, is worth 0.15-0.25 ms per step; an explicit early trigger (BSL_PDL_TRIGGER in ptx.cuh) makes
         # the step 0.6-0.9 ms SLOWER with or without the filter-gradient stream, so it is compiled out.
         self._pdl_mode = int(os.environ.get("BSL_PDL", "1"))
