@@ -16,6 +16,7 @@ head -24 gpurun_out/breakdown.log
 if [ "${SKIP_NCU:-0}" != "1" ]; then
   ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv \
       python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches exit=$?"
+  [ "${SKIP_FULL:-0}" = "1" ] && exit 0
   for spec in "dec1_1 wgrad wgrad_halo_kernel" "dec1_1 fprop conv_halo_kernel" "dec3_1 dgrad conv_halo_kernel" "enc1_2 dgrad conv_halo_kernel"; do
     set -- $spec
     extra=""; [ "$2" = "fprop" ] && extra="--stats"
