@@ -90,7 +90,7 @@ class LossDesc(C.Structure):
 class AdamDesc(C.Structure):
     _fields_ = [
         ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-        ("l2_rate", C.c_float), ("grad_scale", C.c_float), ("step", C.c_int),
+        ("l2_rate", C.c_float), ("grad_scale", C.c_float), ("step", C.c_int), ("decoupled_decay", C.c_float),
     ]
 
 

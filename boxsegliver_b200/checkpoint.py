@@ -23,6 +23,7 @@ trips (tests/test_checkpoint.py).
 from __future__ import annotations
 
 import ctypes as C
+import os
 import struct
 from pathlib import Path
 
@@ -41,9 +42,52 @@ DT = {1: np.float32, 2: np.float64, 3: np.int32, 4: np.uint8, 5: np.int16, 6: np
 DT_OF = {np.dtype(v): k for k, v in DT.items()}
 
 
+_CRC_TABLES = None
+
+
+def _crc32c_tables():
+    """Slicing-by-8 tables of the Castagnoli polynomial (reflected 0x82F63B78), built once with numpy."""
+    global _CRC_TABLES
+    if _CRC_TABLES is None:
+        t0 = np.arange(256, dtype=np.uint32)
+        for _ in range(8):
+            t0 = np.where(t0 & 1, (t0 >> 1) ^ np.uint32(0x82F63B78), t0 >> 1).astype(np.uint32)
+        tabs = [t0]
+        for _ in range(7):
+            prev = tabs[-1]
+            tabs.append((t0[prev & 0xFF] ^ (prev >> 8)).astype(np.uint32))
+        _CRC_TABLES = tabs
+    return _CRC_TABLES
+
+
+def crc32c_host(data: bytes | np.ndarray, crc: int = 0) -> int:
+    """Pure numpy / Python CRC-32C (RFC 3720): the checkpoint tools (list / rename / read) must run on machines without
+    the CUDA toolchain, like the reference's utils/ckpt_kits.py. 8 bytes per Python-level iteration over a whole
+    column of the message would need carried state, so the loop is over 8-byte words with table look-ups."""
+    buf = np.ascontiguousarray(data).view(np.uint8).ravel() if isinstance(data, np.ndarray) else np.frombuffer(data, np.uint8)
+    T = [t.tolist() for t in _crc32c_tables()]
+    t0, t1, t2, t3, t4, t5, t6, t7 = T
+    c = (~crc) & 0xFFFFFFFF
+    n8 = buf.size // 8
+    if n8:
+        words = buf[:n8 * 8].view("<u4").reshape(n8, 2)
+        lo, hi = words[:, 0].tolist(), words[:, 1].tolist()
+        for a, b in zip(lo, hi):
+            a ^= c
+            c = (t7[a & 0xFF] ^ t6[(a >> 8) & 0xFF] ^ t5[(a >> 16) & 0xFF] ^ t4[a >> 24]
+                 ^ t3[b & 0xFF] ^ t2[(b >> 8) & 0xFF] ^ t1[(b >> 16) & 0xFF] ^ t0[b >> 24])
+    for x in buf[n8 * 8:].tolist():
+        c = t0[(c ^ x) & 0xFF] ^ (c >> 8)
+    return (~c) & 0xFFFFFFFF
+
+
 def crc32c(data: bytes | np.ndarray, crc: int = 0) -> int:
-    buf = np.ascontiguousarray(data).view(np.uint8) if isinstance(data, np.ndarray) else np.frombuffer(data, np.uint8)
-    return int(_lib.load().bsl_crc32c(crc, buf.ctypes.data_as(C.c_void_p), buf.size))
+    """CRC-32C through libbsl_b200.so's bsl_crc32c when the library is built (fast path for multi-hundred-MB tensors),
+    else the host implementation above (identical results, pinned by the RFC 3720 vectors in tests/test_checkpoint.py)."""
+    if _lib.LIB_PATH.exists() and not os.environ.get("BSL_CRC_HOST"):
+        buf = np.ascontiguousarray(data).view(np.uint8) if isinstance(data, np.ndarray) else np.frombuffer(data, np.uint8)
+        return int(_lib.load().bsl_crc32c(crc, buf.ctypes.data_as(C.c_void_p), buf.size))
+    return crc32c_host(data, crc)
 
 
 def mask_crc(crc: int) -> int:
@@ -302,6 +346,11 @@ class CheckpointReader:
             raise NotImplementedError(f"{name}: partitioned variables are not used by the reference's models")
         if e["dtype"] not in DT:
             raise TypeError(f"{name}: unsupported DataType {e['dtype']}")
+        if not 0 <= e["shard_id"] < self.num_shards:
+            raise ValueError(f"{name}: shard_id {e['shard_id']} outside the bundle's {self.num_shards} shard(s)")
+        want = int(np.prod(e["shape"], dtype=np.int64)) * np.dtype(DT[e["dtype"]]).itemsize
+        if want != e["size"]:
+            raise ValueError(f"{name}: entry size {e['size']} != prod(shape {list(e['shape'])}) * itemsize = {want}")
         with open(_data_path(self.prefix, e["shard_id"], self.num_shards), "rb") as f:
             f.seek(e["offset"])
             raw = f.read(e["size"])
@@ -323,12 +372,23 @@ def checkpoint_exists(prefix) -> bool:
 # ------------------------------------------------------------------ CheckpointState text proto
 def update_checkpoint_state(save_dir, model_checkpoint_path, all_model_checkpoint_paths=None,
                             latest_filename: str = "checkpoint"):
-    """tf.train.update_checkpoint_state: paths inside save_dir are stored relative to it."""
+    """tf.train.update_checkpoint_state: paths inside save_dir are stored relative to it (for absolute AND relative
+    inputs -- TF relativises with os.path.relpath(path, save_dir) when save_dir itself is relative), so that
+    get_checkpoint_state, which joins every non-absolute entry onto the directory, finds them again."""
     save_dir = Path(save_dir)
-    rel = lambda p: str(Path(p).relative_to(save_dir)) if Path(p).is_absolute() and save_dir in Path(p).parents else str(p)  # noqa: E731
-    paths = list(all_model_checkpoint_paths or [])
-    if not paths or paths[-1] != model_checkpoint_path:
-        paths.append(model_checkpoint_path)
+    root = os.path.abspath(save_dir)
+
+    def rel(p):
+        ap = os.path.abspath(str(p))
+        if ap == root or ap.startswith(root + os.sep):
+            return os.path.relpath(ap, root)
+        if not save_dir.is_absolute() and not os.path.isabs(str(p)):
+            return os.path.relpath(ap, root)       # TF: relative paths are rewritten relative to a relative save_dir
+        return str(p)
+
+    paths = [str(p) for p in (all_model_checkpoint_paths or [])]
+    if not paths or os.path.abspath(paths[-1]) != os.path.abspath(str(model_checkpoint_path)):
+        paths.append(str(model_checkpoint_path))
     lines = [f'model_checkpoint_path: "{rel(model_checkpoint_path)}"']
     lines += [f'all_model_checkpoint_paths: "{rel(p)}"' for p in paths]
     (save_dir / latest_filename).write_text("\n".join(lines) + "\n")
@@ -364,26 +424,27 @@ def latest_checkpoint(checkpoint_dir, latest_filename: str = "checkpoint"):
 
 
 # ------------------------------------------------------------------ engines <-> checkpoints
+def _slot_suffixes(engine):
+    """Slot names the TF optimizers create (Optimizer._zeros_slot(var, slot, self._name)): Adam -> Adam, Adam_1;
+    AdamW -> AdamW, AdamW_1; Momentum -> Momentum."""
+    opt = engine.cfg.optimizer
+    return {"adam": ("Adam", "Adam_1"), "adamw": ("AdamW", "AdamW_1"), "momentum": ("Momentum",)}[opt]
+
+
 def _slot_arrays(engine) -> dict:
-    """Adam / Momentum slots under the names `optimizer.minimize` gives them inside variable_scope("Optimizer")
-    (core/solver.py:232-239): Optimizer/<variable>/Adam, /Adam_1 (or /Momentum), plus beta1_power / beta2_power."""
+    """Adam / AdamW / Momentum slots under the names `optimizer.minimize` gives them inside variable_scope("Optimizer")
+    (core/solver.py:232-239): Optimizer/<variable>/Adam, /Adam_1 (or /Momentum), plus beta1_power / beta2_power.
+    Goes through engine.get_slots(), which un-pads / un-permutes the engine's own arena layout."""
     out = {}
-    n = engine.n_train
-    m = engine.M.download(np.float32, (n,))
-    v = engine.V.download(np.float32, (n,)) if engine.V is not None else None
-    for name, p in engine.params.items():
-        if p.region == "S":
-            continue
-        sl = slice(p.offset, p.offset + p.size)
-        if v is not None:
-            out[f"Optimizer/{name}/Adam"] = m[sl].reshape(p.shape).copy()
-            out[f"Optimizer/{name}/Adam_1"] = v[sl].reshape(p.shape).copy()
-        else:
-            out[f"Optimizer/{name}/Momentum"] = m[sl].reshape(p.shape).copy()
-    if v is not None:
+    suffixes = _slot_suffixes(engine)
+    for name, arrs in engine.get_slots().items():
+        for sfx, a in zip(suffixes, arrs):
+            out[f"Optimizer/{name}/{sfx}"] = a
+    if len(suffixes) == 2:
         t = engine.step_count
-        out["Optimizer/beta1_power"] = np.float32(0.9) ** np.float32(t + 1)       # TF stores beta^(t+1) after t steps
-        out["Optimizer/beta2_power"] = np.float32(0.99) ** np.float32(t + 1)      # beta2 = 0.99, solver.py:206
+        cfg = engine.cfg                                             # TF stores beta^(t+1) after t steps
+        out["Optimizer/beta1_power"] = np.float32(cfg.adam_beta1) ** np.float32(t + 1)
+        out["Optimizer/beta2_power"] = np.float32(cfg.adam_beta2) ** np.float32(t + 1)
     return out
 
 
@@ -437,20 +498,14 @@ def restore_engine(engine, path, weights_scope: str | None = None, latest_filena
     engine.set_weights(weights)
     step = int(reader.get_tensor("global_step")) if reader.has_tensor("global_step") else None
     if with_slots and engine.cfg.training:
-        n = engine.n_train
-        m, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
-        adam = engine.V is not None
+        suffixes = _slot_suffixes(engine)
+        slots = {}
         for name, prm in engine.params.items():
-            if prm.region == "S":
+            if getattr(prm, "region", "A") == "S":
                 continue
-            sl = slice(prm.offset, prm.offset + prm.size)
             base = f"Optimizer/{ren(name)}"
-            m[sl] = reader.get_tensor(base + ("/Adam" if adam else "/Momentum")).ravel()
-            if adam:
-                v[sl] = reader.get_tensor(base + "/Adam_1").ravel()
-        engine.M.upload(m)
-        if adam:
-            engine.V.upload(v)
+            slots[name] = tuple(reader.get_tensor(f"{base}/{sfx}") for sfx in suffixes)
+        engine.set_slots(slots)
         if step is not None:
             engine.step_count = step
     return step

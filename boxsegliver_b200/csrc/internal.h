@@ -27,7 +27,18 @@ struct bsl_ctx {
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
   unsigned long long launches = 0;  // kernels enqueued through this context (bench.py gpu_launches)
+  // Scratch arenas of the two-level reductions, one per stream of THIS context (reduce.cuh bsl_scratch): released by
+  // bsl_stream_destroy / bsl_destroy, never shared between contexts or devices.
+  struct Scratch {
+    float* ptr = nullptr;
+    size_t bytes = 0;
+  };
+  std::mutex scratch_mu;
+  std::unordered_map<cudaStream_t, Scratch> scratch;
 };
+
+// Frees the scratch arena attached to `stream` (all of them when stream_or_all is true).
+void bsl_scratch_release(bsl_ctx* ctx, cudaStream_t stream, bool all);
 
 int bsl_fail(bsl_ctx* ctx, int code, const char* fmt, ...);
 int bsl_check_cuda(bsl_ctx* ctx, cudaError_t e, const char* what);

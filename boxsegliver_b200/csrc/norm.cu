@@ -46,19 +46,19 @@ __global__ void __launch_bounds__(1024) pixel_reduce_final_kernel(const float* _
   }
 }
 
-// Scratch arena for the two-level reductions: one per stream, so reductions enqueued on the side streams (filter
-// gradients, all-reduce tails) never share partials with the ones on the compute stream. Grows on demand; growth
-// frees the old arena with cudaFree, which synchronises the device first.
-struct ScratchArena {
-  float* ptr = nullptr;
-  size_t bytes = 0;
-};
-static std::mutex g_scratch_mu;
-static std::unordered_map<cudaStream_t, ScratchArena> g_scratch;
+// Scratch arena for the two-level reductions: one per (context, stream), so reductions enqueued on the side streams
+// (filter gradients, all-reduce tails) never share partials with the ones on the compute stream. Grows on demand;
+// growth frees the old arena with cudaFree (which synchronises the device first) and is refused while the stream is
+// being captured into a CUDA graph: the pointer would be baked into the graph and cudaMalloc is illegal there.
 int bsl_scratch(bsl_ctx* ctx, size_t bytes, float** out, cudaStream_t stream) {
-  std::lock_guard<std::mutex> g(g_scratch_mu);
-  ScratchArena& a = g_scratch[stream];
+  std::lock_guard<std::mutex> g(ctx->scratch_mu);
+  bsl_ctx::Scratch& a = ctx->scratch[stream];
   if (bytes > a.bytes) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+      return bsl_fail(ctx, BSL_EINVAL,
+                      "scratch arena of this stream must grow (%zu > %zu bytes) while the stream is capturing: run the "
+                      "sequence once outside capture first", bytes, a.bytes);
     if (a.ptr) cudaFree(a.ptr);
     size_t want = bytes < (16u << 20) ? (16u << 20) : bytes;
     a.ptr = nullptr;
@@ -70,6 +70,18 @@ int bsl_scratch(bsl_ctx* ctx, size_t bytes, float** out, cudaStream_t stream) {
   return BSL_OK;
 }
 }  // namespace bsl
+
+void bsl_scratch_release(bsl_ctx* ctx, cudaStream_t stream, bool all) {
+  std::lock_guard<std::mutex> g(ctx->scratch_mu);
+  for (auto it = ctx->scratch.begin(); it != ctx->scratch.end();) {
+    if (all || it->first == stream) {
+      if (it->second.ptr) cudaFree(it->second.ptr);
+      it = ctx->scratch.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
 
 namespace {
 

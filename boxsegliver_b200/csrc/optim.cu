@@ -2,7 +2,9 @@
 // L2 term folded into the gradient, moments, update, and the bf16 shadow copy the conv kernels
 // read next step -- all in one pass over HBM.
 //   tf.train.AdamOptimizer(lr, beta1=0.9, beta2=0.99) / ApplyAdam       <- /root/reference/core/solver.py:204-207
-//   tf.train.MomentumOptimizer(lr, 0.9) / ApplyMomentum                 <- /root/reference/core/solver.py:208-210
+//   tf.train.MomentumOptimizer(lr, 0.9[, use_nesterov]) / ApplyMomentum <- /root/reference/core/solver.py:208-210
+//   tf.contrib.opt.AdamWOptimizer(weight_decay, lr, 0.9, 0.99)          <- /root/reference/core/solver.py:211-216
+//   (--adam_beta1/2, --adam_eps, --mm_mm, --mm_nesterov replace the defaults, solver.py:86-97)
 //   slim.l2_regularizer(rate): loss += rate*sum(w^2)/2, grad += rate*w   <- /root/reference/NetworksV2/base.py:128-135
 #include <cuda_bf16.h>
 #include "reduce.cuh"
@@ -13,7 +15,7 @@ namespace {
 
 __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, size_t n, float lr_t,
-                            float beta1, float beta2, float eps, float l2, float gscale,
+                            float beta1, float beta2, float eps, float l2, float gscale, float decay,
                             double* __restrict__ sq_part) {
   bsl::pdl_enter();
   __shared__ double sm[32];
@@ -24,7 +26,8 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, 
     const float gi = fmaf(l2, wi, g[i] * gscale);
     const float mi = beta1 * m[i] + (1.f - beta1) * gi;
     const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    const float wn = wi - lr_t * mi / (sqrtf(vi) + eps);
+    const float wd = decay != 0.f ? wi - decay * wi : wi;   // AdamW: decay first, Adam update on the decayed value
+    const float wn = wd - lr_t * mi / (sqrtf(vi) + eps);
     m[i] = mi;
     v[i] = vi;
     w[i] = wn;
@@ -43,8 +46,8 @@ __global__ void adam_kernel(float* __restrict__ w, const float* __restrict__ g, 
 }
 
 __global__ void momentum_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ acc,
-                                __nv_bfloat16* __restrict__ shadow, size_t n, float lr, float mom, float l2,
-                                float gscale, double* __restrict__ sq_part) {
+                                __nv_bfloat16* __restrict__ shadow, size_t n, float lr, float mom, int nesterov,
+                                float l2, float gscale, double* __restrict__ sq_part) {
   bsl::pdl_enter();
   __shared__ double sm[32];
   double sq = 0.0;
@@ -53,7 +56,7 @@ __global__ void momentum_kernel(float* __restrict__ w, const float* __restrict__
     sq += (double)wi * (double)wi;
     const float gi = fmaf(l2, wi, g[i] * gscale);
     const float a = mom * acc[i] + gi;
-    const float wn = wi - lr * a;
+    const float wn = nesterov ? wi - (gi * lr + a * mom * lr) : wi - lr * a;
     acc[i] = a;
     w[i] = wn;
     if (shadow) shadow[i] = __float2bfloat16_rn(wn);
@@ -107,7 +110,7 @@ int bsl_adam_step(bsl_ctx* ctx, const bsl_adam_desc* d, float* w, const float* g
   }
   cudaStream_t s = as_stream(stream);
   bsl_launch(adam_kernel, dim3(blocks), dim3(256), 0, s, w, g, m, v, reinterpret_cast<__nv_bfloat16*>(w_bf16), n, (float)lr_t, d->beta1,
-                                     d->beta2, d->eps, d->l2_rate, d->grad_scale, part);
+                                     d->beta2, d->eps, d->l2_rate, d->grad_scale, d->decoupled_decay, part);
   BSL_LAUNCH_CHECK(ctx, "adam_kernel");
   if (sumsq_out) {
     bsl_launch(sumsq_final_kernel, dim3(1), dim3(32), 0, s, part, blocks, sumsq_out);
@@ -116,8 +119,8 @@ int bsl_adam_step(bsl_ctx* ctx, const bsl_adam_desc* d, float* w, const float* g
   return BSL_OK;
 }
 
-int bsl_momentum_step(bsl_ctx* ctx, float lr, float momentum, float l2_rate, float grad_scale, float* w,
-                      const float* g, float* acc, void* w_bf16, size_t n, double* sumsq_out, void* stream) {
+int bsl_momentum_step(bsl_ctx* ctx, float lr, float momentum, int use_nesterov, float l2_rate, float grad_scale,
+                      float* w, const float* g, float* acc, void* w_bf16, size_t n, double* sumsq_out, void* stream) {
   if (!ctx) return BSL_EINVAL;
   if (!w || !g || !acc) return bsl_fail(ctx, BSL_EINVAL, "momentum_step: null argument");
   if (n == 0) return BSL_OK;
@@ -131,7 +134,7 @@ int bsl_momentum_step(bsl_ctx* ctx, float lr, float momentum, float l2_rate, flo
   }
   cudaStream_t s = as_stream(stream);
   bsl_launch(momentum_kernel, dim3(blocks), dim3(256), 0, s, w, g, acc, reinterpret_cast<__nv_bfloat16*>(w_bf16), n, lr, momentum,
-                                         l2_rate, grad_scale, part);
+                                         use_nesterov, l2_rate, grad_scale, part);
   BSL_LAUNCH_CHECK(ctx, "momentum_kernel");
   if (sumsq_out) {
     bsl_launch(sumsq_final_kernel, dim3(1), dim3(32), 0, s, part, blocks, sumsq_out);

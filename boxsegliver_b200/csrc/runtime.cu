@@ -1,6 +1,7 @@
 // Context, device memory, streams/events/graphs and TMA tensor-map encoding for libbsl_b200.so.
 // This is the part of the boundary the TF wrapper would NOT use (TF owns memory and streams,
 // SURVEY.md section 8b); the ctypes host in boxsegliver_b200/ uses it instead of PyTorch.
+#include <atomic>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstdio>
@@ -9,15 +10,19 @@
 
 // -1 = not read yet; BSL_PDL in the environment sets the initial value, bsl_debug_set(ctx, 4, v) changes it at run time
 // (the engine turns it off for the phases where a second stream shares the SMs, see engine.py).
-static int g_bsl_pdl = -1;
+// A process-wide tuning knob (bsl_launch has no context argument): atomic, so engines on different threads may flip it
+// without a data race; the launch attribute only changes scheduling, never results.
+static std::atomic<int> g_bsl_pdl{-1};
 bool bsl_pdl_enabled() {
-  if (g_bsl_pdl < 0) {
+  int v = g_bsl_pdl.load(std::memory_order_relaxed);
+  if (v < 0) {
     const char* e = getenv("BSL_PDL");
-    g_bsl_pdl = e ? (atoi(e) != 0) : 1;
+    v = e ? (atoi(e) != 0) : 1;
+    g_bsl_pdl.store(v, std::memory_order_relaxed);
   }
-  return g_bsl_pdl != 0;
+  return v != 0;
 }
-void bsl_pdl_set(int on) { g_bsl_pdl = on ? 1 : 0; }
+void bsl_pdl_set(int on) { g_bsl_pdl.store(on ? 1 : 0, std::memory_order_relaxed); }
 
 int bsl_fail(bsl_ctx* ctx, int code, const char* fmt, ...) {
   char buf[512];
@@ -115,6 +120,7 @@ void bsl_destroy(bsl_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->d_status) cudaFree(ctx->d_status);
+  bsl_scratch_release(ctx, nullptr, true);
   delete ctx;
 }
 
@@ -182,6 +188,9 @@ int bsl_stream_create(bsl_ctx* ctx, void** out) {
   return BSL_OK;
 }
 int bsl_stream_destroy(bsl_ctx* ctx, void* stream) {
+  if (!ctx) return BSL_EINVAL;
+  BSL_CUDA(ctx, cudaStreamSynchronize(as_stream(stream)));
+  bsl_scratch_release(ctx, as_stream(stream), false);
   BSL_CUDA(ctx, cudaStreamDestroy(as_stream(stream)));
   return BSL_OK;
 }

@@ -44,7 +44,14 @@ class EngineConfig:
     loss_weight_type: str = "none"
     loss_numeric_w: tuple = ()
     loss_proportion_decay: float = 1000.0
-    optimizer: str = "adam"
+    optimizer: str = "adam"            # adam | momentum | adamw (core/solver.py:204-219)
+    adam_beta1: float = 0.9            # reference defaults {"beta1": 0.9, "beta2": 0.99} (solver.py:206)
+    adam_beta2: float = 0.99
+    adam_eps: float = 1e-8
+    momentum: float = 0.9              # solver.py:209
+    use_nesterov: bool = False
+    adamw_weight_decay: float = None   # AdamW decoupled decay; None -> weight_decay_rate (solver.py:212)
+    weight_init: str = "xavier"        # xavier | trunc_norm (base.py:137-151)
     bn_decay: float = 0.999
     bn_eps: float = 1e-3
     in_eps: float = 1e-6
@@ -113,6 +120,46 @@ def _align(n, a=64):
     return (n + a - 1) // a * a
 
 
+def truncated_normal(rng, shape, stddev: float, mean: float = 0.0) -> np.ndarray:
+    """tf.truncated_normal semantics: N(mean, stddev) samples, values beyond 2 stddev are dropped and re-drawn."""
+    out = rng.standard_normal(shape)
+    bad = np.abs(out) > 2.0
+    while bad.any():
+        out[bad] = rng.standard_normal(int(bad.sum()))
+        bad = np.abs(out) > 2.0
+    return (mean + stddev * out).astype(np.float32)
+
+
+OPTIMIZERS = ("adam", "momentum", "adamw")
+
+
+def enqueue_optimizer(eng, lr: float):
+    """One fused update over the flat arenas of `eng` (2-D and 3-D engines share the layout: region A = L2-regularised
+    [0, n_reg), region B = the rest). Hyper-parameters come from the config (core/solver.py:86-97,204-219)."""
+    ctx, s, cfg = eng.ctx, eng.stream, eng.cfg
+    l2 = cfg.weight_decay_rate if cfg.weight_decay_rate > 0 else 0.0
+    regions = [(0, eng.n_reg, l2, eng.sumsq.p), (eng.n_reg, eng.n_train - eng.n_reg, 0.0, None)]
+    if cfg.optimizer not in OPTIMIZERS:
+        raise ValueError("Not supported optimizer: " + cfg.optimizer)
+    decay = 0.0
+    if cfg.optimizer == "adamw":       # DecoupledWeightDecayExtension decays EVERY variable (decay_var_list=None)
+        decay = cfg.weight_decay_rate if cfg.adamw_weight_decay is None else cfg.adamw_weight_decay
+    for off, n, rate, sq in regions:
+        if n <= 0:
+            continue
+        w = C.c_void_p(eng.W.ptr + off * F32)
+        g = C.c_void_p(eng.G.ptr + off * F32)
+        m = C.c_void_p(eng.M.ptr + off * F32)
+        wb = C.c_void_p(eng.Wbf.ptr + off * BF16)
+        if cfg.optimizer in ("adam", "adamw"):
+            v = C.c_void_p(eng.V.ptr + off * F32)
+            d = _lib.AdamDesc(lr, cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps, rate, 1.0, eng.step_count, decay)
+            ctx.call("bsl_adam_step", C.byref(d), w, g, m, v, wb, C.c_size_t(n), sq, s)
+        else:
+            ctx.call("bsl_momentum_step", C.c_float(lr), C.c_float(cfg.momentum), C.c_int(int(cfg.use_nesterov)),
+                     C.c_float(rate), C.c_float(1.0), w, g, m, wb, C.c_size_t(n), sq, s)
+
+
 class UNetEngine:
     def __init__(self, ctx: Context, cfg: EngineConfig):
         self.ctx, self.cfg = ctx, cfg
@@ -129,6 +176,10 @@ class UNetEngine:
             raise ValueError("Not supported weight type: " + cfg.loss_weight_type)
         if cfg.loss_weight_type == "numerical" and len(cfg.loss_numeric_w) != cfg.num_classes:
             raise KeyError("w_type `numerical` need keyword argument `numeric_w` (one value per class)")
+        if cfg.optimizer not in OPTIMIZERS:
+            raise ValueError("Not supported optimizer: " + cfg.optimizer)       # solver.py:217
+        if cfg.weight_init not in ("xavier", "trunc_norm"):
+            raise ValueError("Not supported weight initializer: " + cfg.weight_init)   # base.py:147
         self.step_count = 0
         self._bufs = []
         self._plan_params()
@@ -309,7 +360,7 @@ class UNetEngine:
             h //= 2
             w //= 2
         for j in (1, 2):
-            specs.append(ConvL("conv", f"UNet/ED-Bridge/convolution2d_{j}", cin, c, h, w, cfg.num_down_samples,
+            specs.append(ConvL("conv", f"UNet/ED-Bridge/ED-Bridge_{j}", cin, c, h, w, cfg.num_down_samples,
                                role=f"bridge{j}"))
             cin = c
         for i in reversed(range(cfg.num_down_samples)):
@@ -372,7 +423,7 @@ class UNetEngine:
         if cfg.training:
             self.G = self._alloc(self.n_train * F32).zero()
             self.M = self._alloc(self.n_train * F32).zero()
-            self.V = self._alloc(self.n_train * F32).zero() if cfg.optimizer == "adam" else None
+            self.V = self._alloc(self.n_train * F32).zero() if cfg.optimizer in ("adam", "adamw") else None
         self.sumsq = self._alloc(16)
 
     def _extra_params(self):
@@ -560,16 +611,53 @@ class UNetEngine:
         return {name: hostG[p.offset:p.offset + p.size].reshape(p.shape).copy()
                 for name, p in self.params.items() if p.region != "S"}
 
+    def get_slots(self) -> dict:
+        """Optimizer slots in TF variable shapes: {variable name: (m, v)} for Adam / AdamW, {name: (acc,)} for Momentum."""
+        m = self.M.download(np.float32, (self.n_train,))
+        v = self.V.download(np.float32, (self.n_train,)) if self.V is not None else None
+        out = {}
+        for name, p in self.params.items():
+            if p.region == "S":
+                continue
+            sl = slice(p.offset, p.offset + p.size)
+            out[name] = tuple(a[sl].reshape(p.shape).copy() for a in ((m, v) if v is not None else (m,)))
+        return out
+
+    def set_slots(self, slots: dict):
+        """Inverse of get_slots (every trainable variable must be present)."""
+        m = np.zeros(self.n_train, np.float32)
+        v = np.zeros(self.n_train, np.float32) if self.V is not None else None
+        for name, p in self.params.items():
+            if p.region == "S":
+                continue
+            if name not in slots:
+                raise KeyError(f"missing optimizer slots of {name}")
+            for dst, a in zip((m, v), slots[name]):
+                a = np.asarray(a, np.float32)
+                if tuple(a.shape) != tuple(p.shape):
+                    raise ValueError(f"{name}: slot shape {a.shape} != {p.shape}")
+                dst[p.offset:p.offset + p.size] = a.ravel()
+        self.M.upload(m)
+        if v is not None:
+            self.V.upload(v)
+
+    def _draw_weight(self, rng, shp, fan_in, fan_out):
+        """--weight_init (/root/reference/NetworksV2/base.py:137-151): slim.xavier_initializer() (uniform) or
+        tf.truncated_normal_initializer(stddev=0.01) -- normal samples re-drawn while |x| > 2 sigma."""
+        if getattr(self.cfg, "weight_init", "xavier") == "trunc_norm":
+            return truncated_normal(rng, shp, 0.01)
+        lim = np.sqrt(6.0 / (fan_in + fan_out))
+        return rng.uniform(-lim, lim, size=shp).astype(np.float32)
+
     def init_weights(self, seed: int = 0):
-        """slim.xavier_initializer() weights (seeded numpy stream), zero biases, gamma 1, beta 0, moving 0 / 1."""
+        """--weight_init weights (seeded numpy stream), zero biases, gamma 1, beta 0, moving 0 / 1."""
         rng = np.random.default_rng(seed)
         w = {}
         for name, p in self.params.items():
             if name.endswith("/weights"):
                 shp = p.shape
                 rf = shp[0] * shp[1]
-                lim = np.sqrt(6.0 / (rf * shp[2] + rf * shp[3]))
-                w[name] = rng.uniform(-lim, lim, size=shp).astype(np.float32)
+                w[name] = self._draw_weight(rng, shp, rf * shp[2], rf * shp[3])
             elif name.endswith(("gamma", "moving_variance")):
                 w[name] = np.ones(p.shape, np.float32)
             else:
@@ -904,27 +992,9 @@ class UNetEngine:
 
     # ------------------------------------------------------------------ optimizer
     def optimizer_step(self, lr: float):
-        ctx, s, cfg = self.ctx, self.stream, self.cfg
         self._pdl(True)
         self.step_count += 1
-        l2 = cfg.weight_decay_rate if cfg.weight_decay_rate > 0 else 0.0
-        regions = [(0, self.n_reg, l2, self.sumsq.p), (self.n_reg, self.n_train - self.n_reg, 0.0, None)]
-        for off, n, rate, sq in regions:
-            if n <= 0:
-                continue
-            w = C.c_void_p(self.W.ptr + off * F32)
-            g = C.c_void_p(self.G.ptr + off * F32)
-            m = C.c_void_p(self.M.ptr + off * F32)
-            wb = C.c_void_p(self.Wbf.ptr + off * BF16)
-            if cfg.optimizer == "adam":
-                v = C.c_void_p(self.V.ptr + off * F32)
-                d = _lib.AdamDesc(lr, 0.9, 0.99, 1e-8, rate, 1.0, self.step_count)   # solver.py:206
-                ctx.call("bsl_adam_step", C.byref(d), w, g, m, v, wb, C.c_size_t(n), sq, s)
-            elif cfg.optimizer == "momentum":
-                ctx.call("bsl_momentum_step", C.c_float(lr), C.c_float(0.9), C.c_float(rate), C.c_float(1.0), w, g, m,
-                         wb, C.c_size_t(n), sq, s)
-            else:
-                raise ValueError("Not supported optimizer: " + cfg.optimizer)
+        enqueue_optimizer(self, lr)
 
     # ------------------------------------------------------------------ results
     def read_loss(self):

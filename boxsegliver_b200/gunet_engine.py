@@ -174,8 +174,7 @@ class GUNetEngine(UNetEngine):
             shp = p.shape
             if name.endswith("/weights") and len(shp) == 4:
                 rf = shp[0] * shp[1]
-                lim = np.sqrt(6.0 / (rf * shp[2] + rf * shp[3]))
-                w[name] = rng.uniform(-lim, lim, size=shp).astype(np.float32)
+                w[name] = self._draw_weight(rng, shp, rf * shp[2], rf * shp[3])
             elif name.endswith("/weights"):
                 last = name.startswith(f"GUNet/context/fc{len(self._fc_specs())}/")
                 if last:

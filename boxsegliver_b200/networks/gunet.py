@@ -5,6 +5,7 @@ from __future__ import annotations
 import numpy as np
 
 from ..gunet_engine import GUNetConfig, GUNetEngine
+from ..solver import engine_optimizer_kwargs
 from .base import ModeKeys
 from .unet import LossHandle, UNet
 
@@ -37,7 +38,7 @@ class GUNet(UNet):
             loss_weight_type=getattr(self.args, "loss_weight_type", "none"),
             loss_numeric_w=tuple(getattr(self.args, "loss_numeric_w", None) or ()),
             loss_proportion_decay=getattr(self.args, "loss_proportion_decay", 1000.0),
-            optimizer=getattr(self.args, "optimizer", "Adam").lower(),
+            **engine_optimizer_kwargs(self.args), weight_init=self._get_initializer(),
             training=self.mode == ModeKeys.TRAIN, world=getattr(self, "world", 1),
             mod_layers=tuple(kwargs.get("mod_layers", [])),
             context_fc_channels=tuple(kwargs.get("context_fc_channels", [256])),

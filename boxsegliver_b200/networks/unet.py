@@ -9,6 +9,7 @@ import numpy as np
 from .. import distribution_utils
 from ..engine import EngineConfig, UNetEngine
 from ..loss_metrics import metrics_from_counts
+from ..solver import engine_optimizer_kwargs
 from .base import BaseNet, ModeKeys
 
 
@@ -58,7 +59,7 @@ class UNet(BaseNet):
             loss_weight_type=getattr(self.args, "loss_weight_type", "none"),
             loss_numeric_w=tuple(getattr(self.args, "loss_numeric_w", None) or ()),
             loss_proportion_decay=getattr(self.args, "loss_proportion_decay", 1000.0),
-            optimizer=getattr(self.args, "optimizer", "Adam").lower(),
+            **engine_optimizer_kwargs(self.args), weight_init=self._get_initializer(),
             training=self.mode == ModeKeys.TRAIN, world=getattr(self, "world", 1))
         if self.engine is None or self.engine.cfg != cfg:
             if self.engine is not None:

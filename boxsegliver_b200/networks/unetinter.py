@@ -6,6 +6,7 @@ from __future__ import annotations
 import numpy as np
 
 from ..gunet_engine import UNetInterConfig, UNetInterEngine
+from ..solver import engine_optimizer_kwargs
 from .base import ModeKeys
 from .unet import LossHandle, UNet
 
@@ -33,7 +34,7 @@ class UNetInter(UNet):
             loss_weight_type=getattr(self.args, "loss_weight_type", "none"),
             loss_numeric_w=tuple(getattr(self.args, "loss_numeric_w", None) or ()),
             loss_proportion_decay=getattr(self.args, "loss_proportion_decay", 1000.0),
-            optimizer=getattr(self.args, "optimizer", "Adam").lower(),
+            **engine_optimizer_kwargs(self.args), weight_init=self._get_initializer(),
             training=self.mode == ModeKeys.TRAIN, world=getattr(self, "world", 1),
             guide_channel=getattr(self.args, "guide_channel", 2), dropout_seed=getattr(self.args, "seed", 0))
         if self.engine is None or self.engine.user_cfg != cfg:

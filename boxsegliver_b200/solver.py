@@ -5,8 +5,6 @@ backward, gradient all-reduce, fused optimizer step (BN moving statistics are up
 forward pass, which is the UPDATE_OPS control dependency of solver.py:236-239)."""
 from __future__ import annotations
 
-import math
-
 
 def add_arguments(parser):
     """solver.py:23-82 -- same flags, same defaults."""
@@ -32,6 +30,61 @@ def add_arguments(parser):
     g.add_argument("--mm_mm", type=float)
     g.add_argument("--mm_nesterov", action="store_true")
     g.add_argument("--lr_patience", type=int, default=30)
+
+
+def optimizer_params_from_args(args):
+    """get_solver_params (solver.py:84-96): the dict handed to Solver(optimizer_params=...), or None.
+    Falsy values (0, None) are skipped exactly as the reference's `if args.adam_beta1:` tests do."""
+    p = {}
+    if getattr(args, "adam_beta1", None):
+        p["beta1"] = args.adam_beta1
+    if getattr(args, "adam_beta2", None):
+        p["beta2"] = args.adam_beta2
+    if getattr(args, "adam_eps", None):
+        p["epsilon"] = args.adam_eps
+    if getattr(args, "mm_mm", None):
+        p["momentum"] = args.mm_mm
+    if getattr(args, "mm_nesterov", False):
+        p["use_nesterov"] = True
+    return p or None
+
+
+def engine_optimizer_kwargs(args) -> dict:
+    """Engine-config fields equivalent to Solver._get_model_optimizer (solver.py:204-219).
+
+    The reference's `self.optimizer_params or {defaults}` means ANY explicit flag replaces the whole default dict: with
+    only --adam_beta1 given, beta2 falls back to TensorFlow's 0.999 (not the repo's 0.99). Flags that do not belong to
+    the chosen optimizer reach its constructor as unexpected keywords, and a Momentum / AdamW optimizer built from a
+    flag dict lacks its required `momentum` / `weight_decay` argument: both are TypeErrors in the reference and here."""
+    name = getattr(args, "optimizer", "Adam").lower()
+    params = optimizer_params_from_args(args)
+    allowed = {"adam": {"beta1", "beta2", "epsilon"}, "momentum": {"momentum", "use_nesterov"},
+               "adamw": {"beta1", "beta2", "epsilon", "weight_decay", "learning_rate"}}
+    ctor = {"adam": "AdamOptimizer", "momentum": "MomentumOptimizer", "adamw": "AdamWOptimizer"}
+    if name not in allowed:
+        raise ValueError("Not supported optimizer: " + name)
+    out = {"optimizer": name}
+    if params is None:
+        if name in ("adam", "adamw"):
+            out.update(adam_beta1=0.9, adam_beta2=0.99, adam_eps=1e-8)       # solver.py:206,212-214
+        if name == "momentum":
+            out.update(momentum=0.9, use_nesterov=False)                      # solver.py:209
+        if name == "adamw":
+            out.update(adamw_weight_decay=getattr(args, "weight_decay_rate", 0.0) or 0.0)
+        return out
+    bad = sorted(set(params) - allowed[name])
+    if bad:
+        raise TypeError("{}.__init__() got an unexpected keyword argument '{}'".format(ctor[name], bad[0]))
+    if name == "momentum":
+        if "momentum" not in params:
+            raise TypeError("MomentumOptimizer.__init__() missing 1 required positional argument: 'momentum'")
+        out.update(momentum=params["momentum"], use_nesterov=params.get("use_nesterov", False))
+    elif name == "adam":     # TensorFlow's own defaults for what the dict leaves out
+        out.update(adam_beta1=params.get("beta1", 0.9), adam_beta2=params.get("beta2", 0.999),
+                   adam_eps=params.get("epsilon", 1e-8))
+    else:
+        raise TypeError("AdamWOptimizer.__init__() missing 1 required positional argument: 'weight_decay'")
+    return out
 
 
 class TrainOp:
@@ -75,8 +128,8 @@ class Solver(object):
             if len(v) - len(b) != 1:
                 raise ValueError("Make sure len(lr_custom_values) - len(lr_decay_boundaries) = 1")
         self.optimizer = args.optimizer.lower()
-        if self.optimizer == "adamw":
-            raise NotImplementedError("AdamW (tf.contrib.opt, decoupled decay) is not on the accelerated path yet")
+        self.optimizer_params = optimizer_params_from_args(args)
+        self.engine_kwargs = engine_optimizer_kwargs(args)     # raises where the reference's constructor would
         self.slow_start_step = args.slow_start_step if getattr(args, "lr_warm_up", False) else 0
         self.slow_start_lr = args.slow_start_lr
         self.global_step = 0
@@ -119,12 +172,10 @@ class Solver(object):
             self.slow_start_step = kwargs.pop("slow_start_step")
         if "slow_start_learning_rate" in kwargs:
             self.slow_start_lr = kwargs.pop("slow_start_learning_rate")
-        if self.optimizer not in ("adam", "momentum"):
+        if self.optimizer not in ("adam", "momentum", "adamw"):
             raise ValueError("Not supported optimizer: " + self.optimizer)
-        if loss.model.engine.cfg.optimizer != self.optimizer:
-            raise ValueError("engine was planned for optimizer %r" % loss.model.engine.cfg.optimizer)
+        ecfg = loss.model.engine.cfg
+        for k, v in self.engine_kwargs.items():
+            if getattr(ecfg, k) != v:
+                raise ValueError("engine was planned with %s=%r, the solver asks for %r" % (k, getattr(ecfg, k), v))
         return TrainOp(self, loss)
-
-
-def _unused():  # keeps `math` referenced for static checkers when policies change
-    return math.pi

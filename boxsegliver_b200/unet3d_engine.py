@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _lib
 from .device import Context, DeviceBuffer, f32_to_bf16_bits
-from .engine import BF16, F32, _align
+from .engine import BF16, F32, OPTIMIZERS, _align, enqueue_optimizer, truncated_normal
 
 CPAD = 64
 
@@ -50,7 +50,14 @@ class UNet3DConfig:
     loss_weight_type: str = "numerical"
     loss_numeric_w: tuple = (1.0, 1.0)
     loss_proportion_decay: float = 1000.0
-    optimizer: str = "adam"
+    optimizer: str = "adam"            # adam | momentum | adamw; hyper-parameters as in engine.EngineConfig
+    adam_beta1: float = 0.9
+    adam_beta2: float = 0.99
+    adam_eps: float = 1e-8
+    momentum: float = 0.9
+    use_nesterov: bool = False
+    adamw_weight_decay: float = None
+    weight_init: str = "xavier"
     in_eps: float = 1e-6
     training: bool = True
     world: int = 1
@@ -150,6 +157,10 @@ class UNet3DEngine:
             raise ValueError("Not supported weight type: " + cfg.loss_weight_type)
         if cfg.loss_weight_type == "numerical" and len(cfg.loss_numeric_w) != cfg.num_classes:
             raise KeyError("w_type `numerical` need keyword argument `numeric_w` (one value per class)")
+        if cfg.optimizer not in OPTIMIZERS:
+            raise ValueError("Not supported optimizer: " + cfg.optimizer)
+        if cfg.weight_init not in ("xavier", "trunc_norm"):
+            raise ValueError("Not supported weight initializer: " + cfg.weight_init)
         if 9 * cfg.in_channels > 64:
             raise ValueError("input channels must be <= 7 (the stem's im2col row holds 9 * channels <= 64 columns)")
         ds = 2 ** cfg.num_pool_layers
@@ -250,7 +261,7 @@ class UNet3DEngine:
         if cfg.training:
             self.G = self._alloc(self.n_train * F32).zero()
             self.M = self._alloc(self.n_train * F32).zero()
-            self.V = self._alloc(self.n_train * F32).zero() if cfg.optimizer == "adam" else None
+            self.V = self._alloc(self.n_train * F32).zero() if cfg.optimizer in ("adam", "adamw") else None
         self.sumsq = self._alloc(16)
 
     def _pp(self, arena, name, esize=F32):
@@ -422,6 +433,27 @@ class UNet3DEngine:
         host = self.G.download(np.float32, (self.n_train,))
         return {name: self._unpack(p, host) for name, p in self.params.items()}
 
+    def get_slots(self) -> dict:
+        """Optimizer slots in TF variable shapes (un-padded, [encoder | up] channel order): {name: (m, v)} / {name: (acc,)}."""
+        arenas = [self.M.download(np.float32, (self.n_train,))]
+        if self.V is not None:
+            arenas.append(self.V.download(np.float32, (self.n_train,)))
+        return {name: tuple(self._unpack(p, a) for a in arenas) for name, p in self.params.items()}
+
+    def set_slots(self, slots: dict):
+        arenas = [np.zeros(self.n_train, np.float32) for _ in range(2 if self.V is not None else 1)]
+        for name, p in self.params.items():
+            if name not in slots:
+                raise KeyError(f"missing optimizer slots of {name}")
+            for dst, a in zip(arenas, slots[name]):
+                a = np.asarray(a, np.float32)
+                if tuple(a.shape) != tuple(p.shape):
+                    raise ValueError(f"{name}: slot shape {a.shape} != {p.shape}")
+                dst[p.offset:p.offset + p.size] = self._pack(p, a).ravel()
+        self.M.upload(arenas[0])
+        if self.V is not None:
+            self.V.upload(arenas[1])
+
     def init_weights(self, seed: int = 0):
         rng = np.random.default_rng(seed)
         w = {}
@@ -429,8 +461,11 @@ class UNet3DEngine:
             shp = p.shape
             if name.endswith("/weights"):
                 rf = int(np.prod(shp[:3]))
-                lim = np.sqrt(6.0 / (rf * shp[3] + rf * shp[4]))
-                w[name] = rng.uniform(-lim, lim, size=shp).astype(np.float32)
+                if self.cfg.weight_init == "trunc_norm":        # base.py:138-139
+                    w[name] = truncated_normal(rng, shp, 0.01)
+                else:
+                    lim = np.sqrt(6.0 / (rf * shp[3] + rf * shp[4]))
+                    w[name] = rng.uniform(-lim, lim, size=shp).astype(np.float32)
             elif name.endswith("gamma"):
                 w[name] = np.ones(shp, np.float32)
             else:
@@ -607,23 +642,8 @@ class UNet3DEngine:
         self.ctx.call("bsl_comm_init", buf, C.c_int(rank), C.c_int(world))
 
     def optimizer_step(self, lr: float):
-        ctx, s, cfg = self.ctx, self.stream, self.cfg
         self.step_count += 1
-        l2 = cfg.weight_decay_rate if cfg.weight_decay_rate > 0 else 0.0
-        for off, cnt, rate, sq in ((0, self.n_reg, l2, self.sumsq.p), (self.n_reg, self.n_train - self.n_reg, 0.0, None)):
-            if cnt <= 0:
-                continue
-            w, g, m = (C.c_void_p(a.ptr + off * F32) for a in (self.W, self.G, self.M))
-            wb = C.c_void_p(self.Wbf.ptr + off * BF16)
-            if cfg.optimizer == "adam":
-                v = C.c_void_p(self.V.ptr + off * F32)
-                d = _lib.AdamDesc(lr, 0.9, 0.99, 1e-8, rate, 1.0, self.step_count)
-                ctx.call("bsl_adam_step", C.byref(d), w, g, m, v, wb, C.c_size_t(cnt), sq, s)
-            elif cfg.optimizer == "momentum":
-                ctx.call("bsl_momentum_step", C.c_float(lr), C.c_float(0.9), C.c_float(rate), C.c_float(1.0), w, g, m, wb,
-                         C.c_size_t(cnt), sq, s)
-            else:
-                raise ValueError("Not supported optimizer: " + cfg.optimizer)
+        enqueue_optimizer(self, lr)
 
     def train_step(self, lr: float, with_metrics: bool = False):
         self.forward(True)

@@ -420,7 +420,8 @@ int bsl_confusion_counts(bsl_ctx* ctx, long long n, const uint8_t* test_u8, int 
                          int ref_value, unsigned long long* counts4, void* stream);
 
 /* ------------------------------------------------------------------ fused optimizer step
- * tf.train.AdamOptimizer(lr, 0.9, 0.99) / MomentumOptimizer(lr, 0.9) -- /root/reference/core/solver.py:204-219,
+ * tf.train.AdamOptimizer(lr, beta1, beta2, epsilon) / MomentumOptimizer(lr, momentum, use_nesterov) /
+ * tf.contrib.opt.AdamWOptimizer(weight_decay, lr, ...) -- /root/reference/core/solver.py:86-97,204-219,
  * with slim.l2_regularizer folded in (grad += l2_rate * w) -- NetworksV2/base.py:128-135.
  * Works on flat arenas; also emits the bf16 shadow weights and (optionally) sum(w^2) of the
  * pre-update weights for the reported regularisation loss. */
@@ -429,12 +430,15 @@ typedef struct {
   float l2_rate;     /* 0 for parameters without a regulariser (norm gamma / beta) */
   float grad_scale;  /* applied to g before use */
   int step;          /* t >= 1 */
+  float decoupled_decay; /* AdamW (DecoupledWeightDecayExtension): w <- w - decoupled_decay * w, THEN the Adam
+                          * update on the decayed value with the gradient taken at the old w; 0 = plain Adam */
 } bsl_adam_desc;
 
 int bsl_adam_step(bsl_ctx* ctx, const bsl_adam_desc* d, float* w, const float* g, float* m, float* v,
                   void* w_bf16 /*nullable*/, size_t n, double* sumsq_out /*nullable*/, void* stream);
-int bsl_momentum_step(bsl_ctx* ctx, float lr, float momentum, float l2_rate, float grad_scale, float* w,
-                      const float* g, float* acc, void* w_bf16, size_t n, double* sumsq_out, void* stream);
+/* ApplyMomentum: acc = momentum * acc + g; w -= lr * acc, or with use_nesterov: w -= lr * g + lr * momentum * acc */
+int bsl_momentum_step(bsl_ctx* ctx, float lr, float momentum, int use_nesterov, float l2_rate, float grad_scale,
+                      float* w, const float* g, float* acc, void* w_bf16, size_t n, double* sumsq_out, void* stream);
 
 /* ------------------------------------------------------------------ data-parallel gradient exchange
  * Replaces MirroredStrategy's NCCL all-reduce -- /root/reference/utils/distribution_utils.py:85-98.

@@ -58,7 +58,7 @@ def conv_specs(cfg: UNetCfg):
             cin = c
         c *= 2
     for j in (1, 2):
-        specs.append(("conv", f"UNet/ED-Bridge/convolution2d_{j}", cin, c, cfg.num_down_samples))
+        specs.append(("conv", f"UNet/ED-Bridge/ED-Bridge_{j}", cin, c, cfg.num_down_samples))
         cin = c
     for i in reversed(range(cfg.num_down_samples)):
         c //= 2
@@ -166,7 +166,7 @@ def forward(params: dict, images: np.ndarray, cfg: UNetCfg, is_training: bool, r
         tape.layers.append(dict(kind="pool", x=x))
         x = pooled
     for j in (1, 2):
-        x = conv_block(x, f"UNet/ED-Bridge/convolution2d_{j}")
+        x = conv_block(x, f"UNet/ED-Bridge/ED-Bridge_{j}")
     for i in reversed(range(cfg.num_down_samples)):
         scope = f"UNet/Decode{i + 1}/Conv2d_transpose"
         w = W(scope)
@@ -219,7 +219,7 @@ def tape_from_stored(params: dict, images: np.ndarray, stored: dict, logits: np.
         tape.layers.append(dict(kind="pool", x=x))
         x = O.max_pool_2x2(x)
     for j in (1, 2):
-        x = block(x, f"UNet/ED-Bridge/convolution2d_{j}")
+        x = block(x, f"UNet/ED-Bridge/ED-Bridge_{j}")
     for i in reversed(range(cfg.num_down_samples)):
         scope = f"UNet/Decode{i + 1}/Conv2d_transpose"
         w = wrnd(params[f"{scope}/weights"].astype(dt)).astype(dt)
@@ -280,7 +280,7 @@ def layerwise_forward_errors(params: dict, images: np.ndarray, stored: dict, log
         skips.append(x)
         x = O.max_pool_2x2(x)
     for j in (1, 2):
-        x = block(x, f"UNet/ED-Bridge/convolution2d_{j}")
+        x = block(x, f"UNet/ED-Bridge/ED-Bridge_{j}")
     for i in reversed(range(cfg.num_down_samples)):
         scope = f"UNet/Decode{i + 1}/Conv2d_transpose"
         w = wrnd(params[f"{scope}/weights"].astype(dt)).astype(dt)

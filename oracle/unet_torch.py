@@ -71,7 +71,7 @@ def forward(p: dict, images: torch.Tensor, cfg: R.UNetCfg, is_training: bool):
         skips.append(x)
         x = F.max_pool2d(x, 2)
     for j in (1, 2):
-        x = block(x, f"UNet/ED-Bridge/convolution2d_{j}")
+        x = block(x, f"UNet/ED-Bridge/ED-Bridge_{j}")
     for i in reversed(range(cfg.num_down_samples)):
         scope = f"UNet/Decode{i + 1}/Conv2d_transpose"
         up = F.relu(F.conv_transpose2d(x, _convT_w(p[f"{scope}/weights"]), p[f"{scope}/biases"], stride=2))

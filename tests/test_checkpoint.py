@@ -124,3 +124,57 @@ def test_checkpoint_state_and_rename(tmp_path):
     r = K.load_checkpoint(tmp_path / "renamed")
     assert np.array_equal(r.get_tensor("pre/GUNet/x/weights"), w["UNet/x/weights"])
     assert K.ckpt_vars_rename(p2, replace_from=["x"], replace_to=["empty"])["UNet/x/weights"] == "UNet//weights"
+
+
+def test_crc32c_host_fallback_matches(monkeypatch):
+    """The checkpoint tools must work without the CUDA toolchain (the reference's utils/ckpt_kits.py is CPU-only):
+    the numpy/Python CRC-32C gives the RFC 3720 answers and the library's results."""
+    assert K.crc32c_host(b"123456789") == 0xE3069283 and K.crc32c_host(bytes(32)) == 0x8A9136AA
+    assert K.crc32c_host(bytes([0xFF] * 32)) == 0x62A8AB43 and K.crc32c_host(bytes(range(32))) == 0x46DD794E
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 7, 8, 9, 15, 16, 17, 1000, 4099):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        assert K.crc32c_host(d) == _crc32c_bitwise(d), n
+    d = rng.integers(0, 256, 999, dtype=np.uint8).tobytes()
+    assert K.crc32c_host(d[100:], K.crc32c_host(d[:100])) == K.crc32c_host(d)
+    monkeypatch.setenv("BSL_CRC_HOST", "1")          # route crc32c() itself through the fallback
+    assert K.crc32c(d) == K.crc32c_host(d)
+    a = rng.standard_normal((5, 3)).astype(np.float32)
+    assert K.crc32c(a) == K.crc32c_host(a.tobytes())
+
+
+def test_relative_model_dir_round_trip(tmp_path, monkeypatch):
+    """A relative model_dir (the reference's default `--model_dir model_dir/<tag>`): entries inside the directory are
+    stored relative to it and found again; re-feeding the state never doubles the directory."""
+    monkeypatch.chdir(tmp_path)
+    w = {"UNet/x/weights": np.arange(4, dtype=np.float32).reshape(2, 2)}
+    p1 = K.save_checkpoint("out/model-5", w)
+    K.update_checkpoint_state("out", p1)
+    assert (tmp_path / "out" / "checkpoint").read_text().splitlines()[0] == 'model_checkpoint_path: "model-5"'
+    assert K.latest_checkpoint("out") is not None and K.checkpoint_exists(K.latest_checkpoint("out"))
+    st = K.get_checkpoint_state("out")
+    p2 = K.save_checkpoint("out/model-9", w)
+    K.update_checkpoint_state("out", p2, st.all_model_checkpoint_paths)
+    txt = (tmp_path / "out" / "checkpoint").read_text()
+    assert "out/" not in txt and txt.count("all_model_checkpoint_paths") == 2
+    st = K.get_checkpoint_state("out")
+    assert [K.checkpoint_exists(p) for p in st.all_model_checkpoint_paths] == [True, True]
+    assert np.array_equal(K.load_checkpoint(K.latest_checkpoint("out")).get_tensor("UNet/x/weights"), w["UNet/x/weights"])
+    # a checkpoint outside the directory keeps the path it was given
+    p3 = K.save_checkpoint("elsewhere/m", w)
+    K.update_checkpoint_state("out", p3)
+    assert (tmp_path / "out" / "checkpoint").read_text().splitlines()[0] == 'model_checkpoint_path: "../elsewhere/m"'
+    assert K.checkpoint_exists(K.get_checkpoint_state("out").model_checkpoint_path)
+
+
+def test_reader_validates_entries(tmp_path):
+    """Inconsistent BundleEntryProtos give a clear error instead of an opaque numpy reshape failure."""
+    K.save_checkpoint(tmp_path / "m", {"a": np.zeros((4, 4), np.float32)})
+    r = K.load_checkpoint(tmp_path / "m")
+    r.entries["a"]["shard_id"] = 3
+    with pytest.raises(ValueError, match="shard_id 3 outside"):
+        r.get_tensor("a")
+    r = K.load_checkpoint(tmp_path / "m")
+    r.entries["a"]["shape"] = (4, 5)
+    with pytest.raises(ValueError, match="entry size 64 != prod"):
+        r.get_tensor("a")

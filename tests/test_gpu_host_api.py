@@ -98,3 +98,75 @@ def test_unsupported_flags_raise(ctx):
     params.update(args=args, solver=solver.Solver, ctx=ctx, world=1)
     with pytest.raises(NotImplementedError, match="mid_cat"):
         models.model_fn(dict(images=None), None, ModeKeys.TRAIN, params)
+
+
+def test_engine_variable_names_follow_slim_scoping(ctx):
+    from boxsegliver_b200.engine import EngineConfig, UNetEngine
+    from tests.slim_names import unet_variable_names
+    for norm in ("batch_norm", "instance_norm"):
+        eng = UNetEngine(ctx, EngineConfig(batch=1, height=32, width=32, normalizer=norm, training=False))
+        assert set(eng.params) == set(unet_variable_names(4, norm)), norm
+        eng.close()
+
+
+def _one_step(ctx, **kw):
+    from boxsegliver_b200.engine import EngineConfig, UNetEngine
+    cfg = EngineConfig(batch=2, height=32, width=32, weight_decay_rate=1e-4, loss_weight_type="numerical",
+                       loss_numeric_w=(0.2, 0.4, 4.4), **kw)
+    eng = UNetEngine(ctx, cfg)
+    w0 = eng.init_weights(seed=5)
+    images, labels = synthetic.make_batch(2, 32, 32, 3, seed=1400)
+    eng.set_inputs(images, labels)
+    eng.forward(True)
+    eng.loss_backward()
+    g = eng.get_grads()
+    eng.optimizer_step(1e-3)
+    w1 = eng.get_weights()
+    eng.close()
+    return cfg, w0, g, w1
+
+
+@pytest.mark.parametrize("kw", [
+    dict(optimizer="adam", adam_beta1=0.5, adam_beta2=0.999, adam_eps=1e-4),
+    dict(optimizer="adamw", adamw_weight_decay=0.05),
+    dict(optimizer="momentum", momentum=0.7, use_nesterov=True),
+])
+def test_engine_honours_optimizer_hyperparameters(ctx, kw):
+    """--adam_beta1/2/eps, --mm_mm, --mm_nesterov and AdamW are not silently ignored: the engine's post-step weights
+    equal oracle.tf_ops applied to the engine's own gradients with the SAME hyper-parameters."""
+    from oracle import tf_ops as O
+    cfg, w0, g, w1 = _one_step(ctx, **kw)
+    for name in ("UNet/ED-Bridge/ED-Bridge_1/weights", "UNet/Decode1/Conv2d_transpose/biases",
+                 "UNet/Encode2/Repeat/convolution2d_1/BatchNorm/gamma"):
+        w = w0[name].astype(np.float64)
+        reg = not name.endswith(("gamma", "beta"))
+        ge = g[name].astype(np.float64) + (cfg.weight_decay_rate * w if reg else 0.0)
+        if cfg.optimizer == "momentum":
+            want, _ = O.momentum_step(w, ge, 0.0 * w, 1e-3, cfg.momentum, cfg.use_nesterov)
+        else:
+            decay = cfg.adamw_weight_decay if cfg.optimizer == "adamw" else 0.0
+            want, _, _ = O.adam_step(w, ge, 0.0 * w, 0.0 * w, 1, 1e-3, cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps,
+                                     decoupled_decay=decay)
+        upd, ref = w1[name].astype(np.float64) - w, want - w
+        assert np.linalg.norm(upd - ref) <= 1e-4 * np.linalg.norm(ref) + 1e-9, (name, kw)
+
+
+def test_trunc_norm_initializer_and_flag_plumbing(ctx):
+    """--weight_init trunc_norm (NetworksV2/base.py:137-139): N(0, 0.01) truncated at 2 sigma, through the model class."""
+    args = _args("UNet", weight_init="trunc_norm", adam_beta1=0.8)
+    params = models.get_model_params(args)
+    params.update(args=args, solver=solver.Solver, ctx=ctx, world=1)
+    images, labels = synthetic.make_batch(2, 64, 64, 3, seed=1400)
+    spec = models.model_fn(dict(images=images), labels, ModeKeys.TRAIN, params)
+    eng = spec.model.engine
+    assert (eng.cfg.weight_init, eng.cfg.adam_beta1, eng.cfg.adam_beta2) == ("trunc_norm", 0.8, 0.999)
+    w = eng.get_weights()["UNet/Decode2/Repeat/convolution2d_1/weights"]
+    assert np.abs(w).max() <= 0.02 + 1e-7 and 0.0085 < w.std() < 0.0090        # sd of N(0,1) cut at 2 sigma = 0.8796
+    assert abs(w.mean()) < 1e-4
+    spec.model.engine = None
+    eng.close()
+    with pytest.raises(TypeError, match="momentum"):
+        bad = _args("UNet", optimizer="Momentum", mm_nesterov=True)
+        p2 = models.get_model_params(bad)
+        p2.update(args=bad, solver=solver.Solver, ctx=ctx, world=1)
+        models.model_fn(dict(images=images), labels, ModeKeys.TRAIN, p2)

@@ -302,7 +302,7 @@ def test_adam_and_momentum_steps(ctx):
     v0 = rng.uniform(0, 0.1, nel).astype(np.float32)
     dw, dg, dm, dv = (ctx.from_numpy(a) for a in (w, g, m0, v0))
     shadow, sq = ctx.alloc(nel * 2), ctx.alloc(8)
-    d = _lib.AdamDesc(1e-3, 0.9, 0.99, 1e-8, 1e-5, 0.5, 7)
+    d = _lib.AdamDesc(1e-3, 0.9, 0.99, 1e-8, 1e-5, 0.5, 7, 0.0)
     ctx.call("bsl_adam_step", C.byref(d), dw.p, dg.p, dm.p, dv.p, shadow.p, C.c_size_t(nel), sq.p, ctx.stream)
     ctx.check_device()
     geff = 0.5 * g.astype(np.float64) + 1e-5 * w
@@ -314,12 +314,45 @@ def test_adam_and_momentum_steps(ctx):
     assert abs(sq.download(np.float64, (1,))[0] - float((w.astype(np.float64) ** 2).sum())) < 1e-6 * nel
     acc = ctx.from_numpy(m0)
     dw2 = ctx.from_numpy(w)
-    ctx.call("bsl_momentum_step", C.c_float(0.01), C.c_float(0.9), C.c_float(0.0), C.c_float(1.0), dw2.p, dg.p, acc.p,
-             None, C.c_size_t(nel), None, ctx.stream)
+    ctx.call("bsl_momentum_step", C.c_float(0.01), C.c_float(0.9), C.c_int(0), C.c_float(0.0), C.c_float(1.0), dw2.p,
+             dg.p, acc.p, None, C.c_size_t(nel), None, ctx.stream)
     rw2, racc = O.momentum_step(w.astype(np.float64), g.astype(np.float64), m0.astype(np.float64), 0.01)
     assert rel(dw2.download(np.float32, (nel,)), rw2) < 1e-6
     for b in (dw, dg, dm, dv, shadow, sq, acc, dw2):
         b.free()
+
+
+def test_optimizer_flag_variants(ctx):
+    """--adam_beta1/2/eps, AdamW's decoupled decay, --mm_mm / --mm_nesterov (/root/reference/core/solver.py:86-97,
+    204-219) against oracle.tf_ops in fp64."""
+    nel = 50_001
+    rng = np.random.default_rng(16)
+    w = rng.standard_normal(nel).astype(np.float32)
+    g = rng.standard_normal(nel).astype(np.float32)
+    m0 = (rng.standard_normal(nel) * 0.1).astype(np.float32)
+    v0 = rng.uniform(0, 0.1, nel).astype(np.float32)
+    f8 = lambda a: a.astype(np.float64)  # noqa: E731
+    for b1, b2, eps, decay in ((0.5, 0.999, 1e-8, 0.0), (0.9, 0.99, 1e-3, 0.0), (0.9, 0.99, 1e-8, 3e-2)):
+        dw, dg, dm, dv = (ctx.from_numpy(a) for a in (w, g, m0, v0))
+        d = _lib.AdamDesc(2e-3, b1, b2, eps, 0.0, 1.0, 3, decay)
+        ctx.call("bsl_adam_step", C.byref(d), dw.p, dg.p, dm.p, dv.p, None, C.c_size_t(nel), None, ctx.stream)
+        rw, rm, rv = O.adam_step(f8(w), f8(g), f8(m0), f8(v0), 3, 2e-3, b1, b2, eps, decoupled_decay=decay)
+        assert rel(dw.download(np.float32, (nel,)) - w, rw - w) < 1e-4, (b1, b2, eps, decay)
+        assert rel(dm.download(np.float32, (nel,)), rm) < 1e-6 and rel(dv.download(np.float32, (nel,)), rv) < 1e-6
+        if decay:    # the decay really is decoupled: it differs from folding wd * w into the gradient
+            rw_l2, _, _ = O.adam_step(f8(w), f8(g) + decay * f8(w), f8(m0), f8(v0), 3, 2e-3, b1, b2, eps)
+            assert rel(rw - w, rw_l2 - w) > 1e-2
+        for b in (dw, dg, dm, dv):
+            b.free()
+    for mom, nesterov in ((0.5, 0), (0.9, 1), (0.7, 1)):
+        dw, dg, acc = (ctx.from_numpy(a) for a in (w, g, m0))
+        ctx.call("bsl_momentum_step", C.c_float(0.01), C.c_float(mom), C.c_int(nesterov), C.c_float(1e-4),
+                 C.c_float(1.0), dw.p, dg.p, acc.p, None, C.c_size_t(nel), None, ctx.stream)
+        rw, racc = O.momentum_step(f8(w), f8(g) + 1e-4 * f8(w), f8(m0), 0.01, mom, bool(nesterov))
+        assert rel(dw.download(np.float32, (nel,)) - w, rw - w) < 1e-5, (mom, nesterov)
+        assert rel(acc.download(np.float32, (nel,)), racc) < 1e-6
+        for b in (dw, dg, acc):
+            b.free()
 
 
 def test_casts_roundtrip(ctx):

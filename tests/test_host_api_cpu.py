@@ -68,3 +68,43 @@ def test_per_device_batch_size():
     assert distribution_utils.per_device_batch_size(8, 1) == 8
     with pytest.raises(ValueError):
         distribution_utils.per_device_batch_size(10, 4)
+
+
+def test_optimizer_flags_follow_get_solver_params():
+    """core/solver.py:84-97,204-219: no flag -> the reference's defaults; ANY flag -> the flag dict replaces them (so
+    TensorFlow's own defaults fill the rest); keywords the chosen optimizer's constructor lacks are TypeErrors."""
+    base = ("--model", "UNet", "--classes", "Liver")
+    k = solver.engine_optimizer_kwargs
+    assert k(_args(*base)) == dict(optimizer="adam", adam_beta1=0.9, adam_beta2=0.99, adam_eps=1e-8)
+    assert k(_args(*base, "--adam_beta1", "0.5")) == dict(optimizer="adam", adam_beta1=0.5, adam_beta2=0.999, adam_eps=1e-8)
+    assert k(_args(*base, "--adam_beta2", "0.9", "--adam_eps", "1e-4")) == dict(optimizer="adam", adam_beta1=0.9,
+                                                                               adam_beta2=0.9, adam_eps=1e-4)
+    assert k(_args(*base, "--optimizer", "Momentum")) == dict(optimizer="momentum", momentum=0.9, use_nesterov=False)
+    assert k(_args(*base, "--optimizer", "Momentum", "--mm_mm", "0.8", "--mm_nesterov")) == dict(
+        optimizer="momentum", momentum=0.8, use_nesterov=True)
+    a = _args(*base, "--optimizer", "AdamW")
+    a.weight_decay_rate = 3e-5
+    assert k(a) == dict(optimizer="adamw", adam_beta1=0.9, adam_beta2=0.99, adam_eps=1e-8, adamw_weight_decay=3e-5)
+    with pytest.raises(TypeError, match="missing 1 required positional argument: 'momentum'"):
+        k(_args(*base, "--optimizer", "Momentum", "--mm_nesterov"))       # MomentumOptimizer(lr, use_nesterov=True)
+    with pytest.raises(TypeError, match="unexpected keyword argument 'momentum'"):
+        k(_args(*base, "--mm_mm", "0.5"))                                   # AdamOptimizer(lr, momentum=0.5)
+    with pytest.raises(TypeError, match="unexpected keyword argument 'beta1'"):
+        k(_args(*base, "--optimizer", "Momentum", "--adam_beta1", "0.5", "--mm_mm", "0.9"))
+    with pytest.raises(TypeError, match="weight_decay"):
+        k(_args(*base, "--optimizer", "AdamW", "--adam_beta1", "0.5"))
+    assert solver.Solver(_args(*base, "--adam_beta1", "0.5")).optimizer_params == {"beta1": 0.5}
+    assert solver.Solver(_args(*base)).optimizer_params is None
+
+
+def test_oracle_variable_names_follow_slim_scoping():
+    """The oracle's (and, in tests/test_gpu_host_api.py, the engine's) variable list equals the list derived from
+    slim's scoping rules alone -- a reference model_dir restores only if every name matches."""
+    from oracle import unet_ref as R
+    from tests.slim_names import unet_variable_names
+    for norm in ("batch_norm", "instance_norm"):
+        cfg = R.UNetCfg(height=32, width=32, normalizer=norm)
+        got = set(R.init_params(cfg, seed=0))
+        assert got == set(unet_variable_names(4, norm)), sorted(got ^ set(unet_variable_names(4, norm)))
+    assert "UNet/ED-Bridge/ED-Bridge_2/BatchNorm/moving_variance" in unet_variable_names()
+    assert len(unet_variable_names(with_moving=False)) == 64      # SURVEY 8(a) a10: 64 trainable variables
