@@ -559,6 +559,70 @@ __global__ void norm_bwd_finalize_mod_kernel(int n, int c, int K, double m, cons
   if (dbias_guide) dbias_guide[ch] = (float)s0all;
 }
 
+// after_affine fold (GUNet.py:213-214): z = ga*(y*sc + sh + guide.w) + ba = y*(sc*ga) + (sh*ga + ba) + guide.(w*ga)
+__global__ void norm_affine_fold_kernel(int n, int c, int G, const float* __restrict__ ga, const float* __restrict__ ba,
+                                        float* __restrict__ scale, float* __restrict__ shift,
+                                        float* __restrict__ scale_pre, float* __restrict__ shift_pre,
+                                        const float* __restrict__ w, int w_ld, float* __restrict__ w_eff) {
+  bsl::pdl_enter();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * c) {
+    const int ch = i % c;
+    const float sc = scale[i], sh = shift[i];
+    scale_pre[i] = sc;
+    shift_pre[i] = sh;
+    scale[i] = sc * ga[ch];
+    shift[i] = fmaf(sh, ga[ch], ba[ch]);
+  }
+  if (i < G * c) {
+    const int g = i / c, ch = i - g * c;
+    w_eff[i] = w[g * w_ld + ch] * ga[ch];
+  }
+}
+
+// norm_bwd_finalize_mod_kernel with the folded channel-wise affine. S0 = sum dz, S1 = sum dz*xhat, T_g = sum dz*guide_g
+// are sums of the gradient AFTER the affine; u = xhat*(scale_pre/rstd) + (shift_pre + mean*scale_pre) + guide.w.
+__global__ void norm_bwd_finalize_affine_kernel(int n, int c, int K, double m, const double* __restrict__ sums,
+                                                const float* __restrict__ gamma_mod, int gm_ld,
+                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                const float* __restrict__ ga, const float* __restrict__ mean,
+                                                const float* __restrict__ rstd, const float* __restrict__ scale_pre,
+                                                const float* __restrict__ shift_pre, const float* __restrict__ w,
+                                                int w_ld, float* __restrict__ c1, float* __restrict__ c2,
+                                                float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                float* __restrict__ dgamma_mod, float* __restrict__ dw_guide, int dw_ld,
+                                                float* __restrict__ dbias_guide, float* __restrict__ dga,
+                                                float* __restrict__ dba) {
+  bsl::pdl_enter();
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double gam = gamma ? (double)gamma[ch] : 1.0, be = beta ? (double)beta[ch] : 0.0, a = (double)ga[ch];
+  double sg = 0.0, sb = 0.0, s0all = 0.0, t[2] = {0.0, 0.0}, acc_ga = 0.0;
+  for (int s = 0; s < n; ++s) {  // fixed order
+    const double* q = sums + (long long)s * K * c + ch;
+    const double s0 = q[0], s1 = q[c];
+    const int o = s * c + ch;
+    c1[o] = (float)(s0 / m);
+    c2[o] = (float)(s1 / m);
+    const double sp = (double)scale_pre[o], hp = (double)shift_pre[o];
+    double du = sp / (double)rstd[o] * s1 + (hp + (double)mean[o] * sp) * s0;
+    for (int g = 0; g < K - 2; ++g) du += (double)w[g * w_ld + ch] * q[(long long)(2 + g) * c];
+    acc_ga += du;
+    const double gm = gamma_mod ? (double)gamma_mod[(long long)s * gm_ld + ch] : 1.0;
+    if (dgamma_mod) dgamma_mod[(long long)s * gm_ld + ch] = (float)(a * (gam * s1 + be * s0));
+    sg += gm * s1;
+    sb += gm * s0;
+    s0all += s0;
+    for (int g = 0; g < K - 2; ++g) t[g] += q[(long long)(2 + g) * c];
+  }
+  if (dgamma) dgamma[ch] = (float)(a * sg);
+  if (dbeta) dbeta[ch] = (float)(a * sb);
+  for (int g = 0; g < K - 2; ++g) dw_guide[g * dw_ld + ch] = (float)(a * t[g]);
+  if (dbias_guide) dbias_guide[ch] = (float)(a * s0all);
+  dga[ch] = (float)acc_ga;
+  dba[ch] = (float)s0all;
+}
+
 // da[n,2i+a,2j+b,:] = dskip (optional) + (first max of the window in scan order ? dpool[n,i,j,:] : 0)
 __global__ void maxpool_bwd_add_kernel(const __nv_bfloat16* __restrict__ act, int a_ld,
                                        const __nv_bfloat16* __restrict__ dpool, int p_ld,
@@ -1332,6 +1396,43 @@ int bsl_norm_bwd_finalize_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const double
       d->n, d->c, 2 + guide_channels, (double)d->hw, sums, gamma_mod, gm_ld, d->scale ? gamma : nullptr,
       d->center ? beta : nullptr, c1, c2, dgamma, dbeta, dgamma_mod, dw_guide, dw_ld, dbias_guide);
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_finalize_mod_kernel");
+  return BSL_OK;
+}
+
+int bsl_norm_affine_fold(bsl_ctx* ctx, const bsl_norm_desc* d, const float* gamma_a, const float* beta_a, float* scale,
+                         float* shift, float* scale_pre, float* shift_pre, const float* w_guide, int w_ld,
+                         int guide_channels, float* w_eff, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (d->mode != 1) return bsl_fail(ctx, BSL_EUNSUPPORTED, "norm_affine_fold: instance_norm layers only");
+  if (!gamma_a || !beta_a || !scale || !shift || !scale_pre || !shift_pre || guide_channels < 0 || guide_channels > 2 ||
+      (guide_channels && (!w_guide || !w_eff || w_ld < d->c)))
+    return bsl_fail(ctx, BSL_EINVAL, "norm_affine_fold: bad argument");
+  const int total = d->n > guide_channels ? d->n * d->c : guide_channels * d->c;
+  bsl_launch(norm_affine_fold_kernel, dim3((total + 127) / 128), dim3(128), 0, as_stream(stream), d->n, d->c,
+             guide_channels, gamma_a, beta_a, scale, shift, scale_pre, shift_pre, w_guide, w_ld, w_eff);
+  BSL_LAUNCH_CHECK(ctx, "norm_affine_fold_kernel");
+  return BSL_OK;
+}
+
+int bsl_norm_bwd_finalize_affine(bsl_ctx* ctx, const bsl_norm_desc* d, const double* sums, int guide_channels,
+                                 const float* gamma_mod, int gm_ld, const float* gamma, const float* beta,
+                                 const float* gamma_a, const float* mean, const float* rstd, const float* scale_pre,
+                                 const float* shift_pre, const float* w_guide, int w_ld, float* c1, float* c2,
+                                 float* dgamma, float* dbeta, float* dgamma_mod, float* dw_guide, int dw_ld,
+                                 float* dbias_guide, float* dgamma_a, float* dbeta_a, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (d->mode != 1) return bsl_fail(ctx, BSL_EUNSUPPORTED, "norm_bwd_finalize_affine: instance_norm layers only");
+  if (!sums || !c1 || !c2 || !gamma_a || !mean || !rstd || !scale_pre || !shift_pre || !dgamma_a || !dbeta_a ||
+      guide_channels < 0 || guide_channels > 2 || (gamma_mod && !dgamma_mod) ||
+      (guide_channels && (!dw_guide || dw_ld < d->c || !w_guide || w_ld < d->c)))
+    return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_finalize_affine: bad argument");
+  bsl_launch(norm_bwd_finalize_affine_kernel, dim3((d->c + 127) / 128), dim3(128), 0, as_stream(stream), d->n, d->c,
+             2 + guide_channels, (double)d->hw, sums, gamma_mod, gm_ld, d->scale ? gamma : nullptr,
+             d->center ? beta : nullptr, gamma_a, mean, rstd, scale_pre, shift_pre, w_guide, w_ld, c1, c2, dgamma, dbeta,
+             dgamma_mod, dw_guide, dw_ld, dbias_guide, dgamma_a, dbeta_a);
+  BSL_LAUNCH_CHECK(ctx, "norm_bwd_finalize_affine_kernel");
   return BSL_OK;
 }
 

@@ -145,6 +145,12 @@ int bsl_launch_count(bsl_ctx* ctx, unsigned long long* out) {
   return BSL_OK;
 }
 
+int bsl_mem_info(bsl_ctx* ctx, size_t* free_bytes, size_t* total_bytes) {
+  if (!ctx || !free_bytes || !total_bytes) return BSL_EINVAL;
+  BSL_CUDA(ctx, cudaMemGetInfo(free_bytes, total_bytes));
+  return BSL_OK;
+}
+
 int bsl_malloc(bsl_ctx* ctx, size_t bytes, void** out) {
   if (!ctx || !out) return BSL_EINVAL;
   BSL_CUDA(ctx, cudaMalloc(out, bytes ? bytes : 16));

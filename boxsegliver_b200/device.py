@@ -94,7 +94,7 @@ class Context:
         self.stream = s
 
     # -- plumbing
-    _NO_PROF = ("bsl_malloc", "bsl_free", "bsl_stream_", "bsl_event_", "bsl_host_", "bsl_device_status",
+    _NO_PROF = ("bsl_malloc", "bsl_free", "bsl_mem_info", "bsl_stream_", "bsl_event_", "bsl_host_", "bsl_device_status",
                 "bsl_launch_count", "bsl_graph_", "bsl_comm_", "bsl_debug_set")
 
     def call(self, name: str, *args) -> int:
@@ -186,6 +186,20 @@ class Context:
         return ms.value
 
     # -- memory
+    def mem_info(self):
+        """(free bytes, total bytes) of the device."""
+        f, t = C.c_size_t(), C.c_size_t()
+        self.call("bsl_mem_info", C.byref(f), C.byref(t))
+        return f.value, t.value
+
+    def attach_comm(self, rank: int, world: int, unique_id: bytes):
+        """Join the NCCL communicator once per context; engines built later on this context share it."""
+        if getattr(self, "_comm", None) is None:
+            buf = (C.c_char * 128).from_buffer_copy(unique_id)
+            self.call("bsl_comm_init", buf, C.c_int(rank), C.c_int(world))
+            self._comm = (rank, world)
+        assert self._comm == (rank, world), (self._comm, rank, world)
+
     def alloc(self, nbytes: int) -> DeviceBuffer:
         return DeviceBuffer(self, nbytes)
 

@@ -108,6 +108,7 @@ class ConvL:
     scale: bool = True
     mod_off: int = None      # GUNet: first column of this layer's slice of the context-MLP output
     sp_off: int = None       # GUNet: first column of this layer's slice of the level's 1x1 guide conv
+    affine: str = None       # GUNet after_affine: scope of the ChannelWiseAffine variables of this encoder layer
     x: View = None
     y: View = None           # pre-norm conv output (conv/stem), or output (convT)
     a: View = None           # post-activation
@@ -182,6 +183,7 @@ class UNetEngine:
             raise ValueError("Not supported weight initializer: " + cfg.weight_init)   # base.py:147
         self.step_count = 0
         self._bufs = []
+        self._skip_exchange = False   # bench.py's data-parallel check runs one backward without the gradient exchange
         self._plan_params()
         self._plan_activations()
         self.stream = ctx.stream
@@ -274,8 +276,7 @@ class UNetEngine:
     def attach_comm(self, rank: int, world: int, unique_id: bytes):
         """Join the NCCL communicator (one process per GPU). cfg.world must equal `world`."""
         assert world == self.cfg.world, (world, self.cfg.world)
-        buf = (C.c_char * 128).from_buffer_copy(unique_id)
-        self.ctx.call("bsl_comm_init", buf, C.c_int(rank), C.c_int(world))
+        self.ctx.attach_comm(rank, world, unique_id)
         self.rank = rank
         self._plan_buckets()
 
@@ -289,17 +290,23 @@ class UNetEngine:
         self.comm_stream = self.ctx.new_stream()
         self._ev_ready = [self.ctx.new_event() for _ in range(16)]
         self._ev_done = self.ctx.new_event()
+        self._ev_stats = self.ctx.new_event()
         self._bucket_at = {}          # scope of the layer that closes a bucket -> (offset, count)
         # parameters outside the conv trunk (GUNet guide convs) sit after the last layer in region A and get their
         # gradients late in backward: they travel with the tail
         lastp = [p for p in self.params.values() if p.region == "A" and p.name.startswith(self.layers[-1].scope + "/")]
         self._trunk_end = max(p.offset + _align(max(p.size, p.alloc)) for p in lastp)
         end, acc, last = self._trunk_end, 0, None
+        # the final bucket closes at the stem's filter gradient, the last kernel of backward, and overlaps nothing: a
+        # boundary at the first conv of the second level keeps it down to the first level's ~40 K values
+        early = next((L.scope for L in self.layers if L.kind == "conv" and L.level == 1), None)
+        split_early = os.environ.get("BSL_BUCKET_EARLY_SPLIT", "1") != "0"
         for L in reversed(self.layers):
             p = self.params[f"{L.scope}/weights"]
             acc = end - p.offset
             last = L
-            if acc >= self.BUCKET_ELEMS and len(self._bucket_at) < len(self._ev_ready) - 1:
+            full = acc >= self.BUCKET_ELEMS or (split_early and L.scope == early and acc > 0)
+            if full and len(self._bucket_at) < len(self._ev_ready) - 1:
                 self._bucket_at[L.scope] = (p.offset, acc)
                 end, acc = p.offset, 0
         if end > 0:
@@ -308,7 +315,7 @@ class UNetEngine:
 
     def _after_grad(self, L: ConvL):
         """Called when layer L's parameter gradients have been enqueued (backward order)."""
-        if self.cfg.world <= 1 or L.scope not in getattr(self, "_bucket_at", {}):
+        if self.cfg.world <= 1 or self._skip_exchange or L.scope not in getattr(self, "_bucket_at", {}):
             return
         off, cnt = self._bucket_at[L.scope]
         ev = self._ev_ready[self._bucket_i]
@@ -318,27 +325,37 @@ class UNetEngine:
         self.ctx.call("bsl_allreduce_sum_f32", C.c_void_p(self.G.ptr + off * F32), C.c_size_t(cnt), self.comm_stream)
 
     def _allreduce_grads(self):
-        """Tail of the exchange: the un-regularised region (gamma / beta / FC, tiny), then join the side stream."""
-        if self.cfg.world <= 1:
+        """Tail of the exchange: the un-regularised region (gamma / beta / FC, tiny) follows the buckets on the side
+        stream -- every gradient has been enqueued once loss_backward returns -- then the compute stream joins it, so
+        the only collective work the optimizer waits for is the last bucket and this tail."""
+        if self.cfg.world <= 1 or self._skip_exchange:
             return
         if self.comm_stream is None:       # attach_comm not called: single all-reduce on the compute stream
             self.ctx.call("bsl_allreduce_sum_f32", self.G.p, C.c_size_t(self.n_train), self.stream)
             return
         nb = self.n_train - self._trunk_end
         if nb > 0:
+            ev = self._ev_ready[-1]
+            self.ctx.record(ev, self.stream)
+            self.ctx.call("bsl_stream_wait_event", self.comm_stream, ev)
             self.ctx.call("bsl_allreduce_sum_f32", C.c_void_p(self.G.ptr + self._trunk_end * F32), C.c_size_t(nb),
-                          self.stream)
+                          self.comm_stream)
         self.ctx.record(self._ev_done, self.comm_stream)
         self.ctx.call("bsl_stream_wait_event", self.stream, self._ev_done)
         self._bucket_i = 0
 
     def _allreduce_moving_stats(self):
         # MirroredStrategy aggregates the moving-average updates with MEAN across replicas
-        # (/root/reference/core/estimator.py:570-613); batch statistics themselves stay per replica.
-        if self.cfg.world > 1 and self.n_stats > 0:
-            self.ctx.call("bsl_allreduce_sum_f32", self.S.p, C.c_size_t(self.n_stats), self.stream)
-            self.ctx.call("bsl_scale_f32", self.S.p, C.c_size_t(self.n_stats), C.c_float(1.0 / self.cfg.world),
-                          self.stream)
+        # (/root/reference/core/estimator.py:570-613); batch statistics themselves stay per replica. Nothing reads the
+        # moving statistics before the next step's forward, so the exchange rides the side stream (ahead of the
+        # gradient buckets) and is ordered before the optimizer by the same join as the gradients.
+        if self.cfg.world > 1 and self.n_stats > 0 and not self._skip_exchange:
+            st = self.comm_stream if self.comm_stream is not None else self.stream
+            if st is not self.stream:
+                self.ctx.record(self._ev_stats, self.stream)
+                self.ctx.call("bsl_stream_wait_event", st, self._ev_stats)
+            self.ctx.call("bsl_allreduce_sum_f32", self.S.p, C.c_size_t(self.n_stats), st)
+            self.ctx.call("bsl_scale_f32", self.S.p, C.c_size_t(self.n_stats), C.c_float(1.0 / self.cfg.world), st)
 
     # ------------------------------------------------------------------ planning
     def _alloc(self, nbytes) -> DeviceBuffer:

@@ -8,9 +8,11 @@ listed in `mod_layers` are modulated (modulated_conv_block, GUNet.py:162-217):
 
 gamma_mod is a slice of the context MLP output (GUNet.py:31-59: fc(200 -> 256 -> 256 -> 3840), dropout after the
 hidden layers); the additive map is the level's 1x1 guide convolution (GUNet.py:136-159) evaluated on the fly inside
-the normalisation kernels, so modulation adds no pass over the activations. Scope: instance_norm (what every
-shipped GUNet script uses), context_model "fc"; --use_se, --fix, --without_norm, --dropout, after_affine, --img_grad
-and ct_conv raise NotImplementedError.
+the normalisation kernels, so modulation adds no pass over the activations. `after_affine` (5 of the 13 shipped
+ext_config/*.yml; slim_nets.channel_wise_affine before every encoder ReLU, GUNet.py:213-214) folds into the same
+per-(sample, channel) scale / shift and a gamma-scaled copy of the guide filter (bsl_norm_affine_fold): no extra pass.
+Scope: instance_norm (what every shipped GUNet script uses), context_model "fc"; --use_se, --fix, --without_norm,
+--dropout, --img_grad and ct_conv raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -57,7 +59,7 @@ class GUNetEngine(UNetEngine):
     def __init__(self, ctx, cfg: GUNetConfig):
         if cfg.normalizer != "instance_norm":
             raise NotImplementedError("GUNet engine: guide modulation is implemented for --normalizer instance_norm")
-        for flag in ("use_se", "fix", "without_norm", "dropout", "after_affine"):
+        for flag in ("use_se", "fix", "without_norm", "dropout"):
             if getattr(cfg, flag):
                 raise NotImplementedError(f"GUNet engine: --{flag} is not supported")
         if cfg.context_model != "fc":
@@ -83,8 +85,14 @@ class GUNetEngine(UNetEngine):
             for j in (1, 2):
                 kind = "stem" if (i == 0 and j == 1) else "conv"
                 role = f"enc{j}" if i < nd else f"bridge{j}"
+                aa = bool(getattr(cfg, "after_affine", False))
+                # encoder_arg_scope (GUNet.py:313-330): after_affine turns centre / scale of the MODULATED blocks' normaliser
+                # off; un-modulated blocks pass normalizer_params={} (slim defaults, both on) and still get the affine
                 L = ConvL(kind, f"{self.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/Conv", cin, c, h, w, i, role=role,
-                          center=cfg.norm_with_center if mod else True, scale=cfg.norm_with_scale if mod else True)
+                          center=(cfg.norm_with_center and not aa) if mod else True,
+                          scale=(cfg.norm_with_scale and not aa) if mod else True)
+                if aa:
+                    L.affine = f"{self.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/ChannelWiseAffine"
                 if mod and cfg.use_context:
                     L.mod_off = off
                     off += c
@@ -120,6 +128,10 @@ class GUNetEngine(UNetEngine):
     def _extra_params(self):
         cfg = self.cfg
         plist = []
+        for L in self.layers:
+            if L.affine:           # variables.model_variable without a regulariser (slim_nets.py:186-201)
+                plist.append(Param(f"{L.affine}/gamma", (L.cout,), region="B"))
+                plist.append(Param(f"{L.affine}/beta", (L.cout,), region="B"))
         if cfg.use_context:
             for sc, cin, cout, _ in self._fc_specs():      # slim.fully_connected: no regulariser in GUNet's arg scope
                 plist.append(Param(f"{sc}/weights", (cin, cout), region="B"))
@@ -139,6 +151,9 @@ class GUNetEngine(UNetEngine):
     def _plan_guides(self):
         cfg, n = self.cfg, self.cfg.batch
         self.guides = []
+        # after_affine: un-folded scale / shift of every encoder layer (backward finaliser) + the gamma-scaled guide filter
+        self.aff_bufs = {L.scope: self._alloc((2 * _align(n * L.cout, 16) + 2 * L.cout) * F32)
+                         for L in self.layers if L.affine}
         if cfg.use_spatial:
             h, w = cfg.height, cfg.width
             for _ in range(cfg.num_down_samples + 1):
@@ -221,28 +236,41 @@ class GUNetEngine(UNetEngine):
         self._fwd_training = is_training
         super().forward(is_training)
 
+    def _aff_ptrs(self, L: ConvL):
+        """(scale_pre, shift_pre, w_eff) of an after_affine layer."""
+        base, n = self.aff_bufs[L.scope].ptr, _align(self.cfg.batch * L.cout, 16)
+        return C.c_void_p(base), C.c_void_p(base + n * F32), C.c_void_p(base + 2 * n * F32)
+
     def _guide_struct(self, L: ConvL):
         if L.sp_off is None:
             return None
         sc = f"GUNet/spatial/conv{L.level + 1}"
+        if L.affine:     # the passes read the filter scaled by the affine's gamma (bsl_norm_affine_fold wrote it)
+            return _lib.Guide(self.guides[L.level][0].ptr, self.cfg.guide_channel, self._aff_ptrs(L)[2].value, L.cout)
         return _lib.Guide(self.guides[L.level][0].ptr, self.cfg.guide_channel,
                           self._pp(self.W, f"{sc}/weights", off=L.sp_off).value, 2 * L.cout)
 
     def _modulate(self, L: ConvL, nd, q):
-        if L.mod_off is None and L.sp_off is None:
-            return None
-        gm = C.c_void_p(self.ctx_params.ptr + L.mod_off * F32) if L.mod_off is not None else None
-        bsp = self._pp(self.W, f"GUNet/spatial/conv{L.level + 1}/biases", off=L.sp_off) if L.sp_off is not None else None
-        self.ctx.call("bsl_norm_modulate", C.byref(nd), gm, C.c_int(self.cfg.n_modulator_param), bsp, q["scale"],
-                      q["shift"], self.stream)
+        if L.mod_off is not None or L.sp_off is not None:
+            gm = C.c_void_p(self.ctx_params.ptr + L.mod_off * F32) if L.mod_off is not None else None
+            bsp = self._pp(self.W, f"GUNet/spatial/conv{L.level + 1}/biases", off=L.sp_off) if L.sp_off is not None else None
+            self.ctx.call("bsl_norm_modulate", C.byref(nd), gm, C.c_int(self.cfg.n_modulator_param), bsp, q["scale"],
+                          q["shift"], self.stream)
+        if L.affine:
+            sp, hp, weff = self._aff_ptrs(L)
+            g = self._guide_channels(L)
+            wsp = self._pp(self.W, f"GUNet/spatial/conv{L.level + 1}/weights", off=L.sp_off) if g else None
+            self.ctx.call("bsl_norm_affine_fold", C.byref(nd), self._pp(self.W, f"{L.affine}/gamma"),
+                          self._pp(self.W, f"{L.affine}/beta"), q["scale"], q["shift"], sp, hp, wsp,
+                          C.c_int(2 * L.cout), C.c_int(g), weff if g else None, self.stream)
         return self._guide_struct(L)
 
     # ------------------------------------------------------------------ backward
     def _is_modulated(self, L: ConvL) -> bool:
-        return L.mod_off is not None or L.sp_off is not None
+        return L.mod_off is not None or L.sp_off is not None or bool(L.affine)
 
     def _norm_backward_reduce(self, L: ConvL, nd, q, cur):
-        if L.mod_off is None and L.sp_off is None:
+        if not self._is_modulated(L):
             return super()._norm_backward_reduce(L, nd, q, cur)
         call, s, ns = self.ctx.call, self.stream, self.norm_scope
         guide = self._guide_struct(L)
@@ -255,6 +283,16 @@ class GUNetEngine(UNetEngine):
         dbg = self._pp(self.G, f"{ssc}/biases", off=L.sp_off) if L.sp_off is not None else None
         call("bsl_norm_bwd_reduce_mod", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"], q["scale"],
              q["shift"], gp, q["sums"], s)
+        if L.affine:
+            sp, hp, _ = self._aff_ptrs(L)
+            wsp = self._pp(self.W, f"{ssc}/weights", off=L.sp_off) if L.sp_off is not None else None
+            call("bsl_norm_bwd_finalize_affine", C.byref(nd), q["sums"], C.c_int(self._guide_channels(L)), gm,
+                 C.c_int(nmod), self._pp(self.W, f"{L.scope}/{ns}/gamma"), self._pp(self.W, f"{L.scope}/{ns}/beta"),
+                 self._pp(self.W, f"{L.affine}/gamma"), q["mean"], q["rstd"], sp, hp, wsp, C.c_int(2 * L.cout),
+                 q["c1"], q["c2"], self._pp(self.G, f"{L.scope}/{ns}/gamma"), self._pp(self.G, f"{L.scope}/{ns}/beta"),
+                 dgm, dwg, C.c_int(2 * L.cout), dbg, self._pp(self.G, f"{L.affine}/gamma"),
+                 self._pp(self.G, f"{L.affine}/beta"), s)
+            return
         call("bsl_norm_bwd_finalize_mod", C.byref(nd), q["sums"], C.c_int(self._guide_channels(L)), gm, C.c_int(nmod),
              self._pp(self.W, f"{L.scope}/{ns}/gamma"), self._pp(self.W, f"{L.scope}/{ns}/beta"), q["c1"], q["c2"],
              self._pp(self.G, f"{L.scope}/{ns}/gamma"), self._pp(self.G, f"{L.scope}/{ns}/beta"), dgm, dwg,

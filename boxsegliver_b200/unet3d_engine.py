@@ -638,8 +638,7 @@ class UNet3DEngine:
     # ------------------------------------------------------------------ optimizer / step
     def attach_comm(self, rank: int, world: int, unique_id: bytes):
         assert world == self.cfg.world
-        buf = (C.c_char * 128).from_buffer_copy(unique_id)
-        self.ctx.call("bsl_comm_init", buf, C.c_int(rank), C.c_int(world))
+        self.ctx.attach_comm(rank, world, unique_id)
 
     def optimizer_step(self, lr: float):
         self.step_count += 1

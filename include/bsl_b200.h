@@ -57,6 +57,8 @@ int bsl_debug_set(bsl_ctx* ctx, int key, int value);
  * cycles waiting for a free accumulator, for an activation stage, for a filter stage} of its last launch. */
 int bsl_debug_read_waits(bsl_ctx* ctx, long long* out /*[ctas][4]*/, int ctas);
 
+/* cudaMemGetInfo of the context's device (bench.py sizes the strong-scaling points with it). */
+int bsl_mem_info(bsl_ctx* ctx, size_t* free_bytes, size_t* total_bytes);
 int bsl_malloc(bsl_ctx* ctx, size_t bytes, void** out);
 int bsl_free(bsl_ctx* ctx, void* ptr);
 int bsl_memset(bsl_ctx* ctx, void* dst, int value, size_t bytes, void* stream);
@@ -333,6 +335,24 @@ int bsl_norm_bwd_finalize_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const double
                               const float* gamma_mod, int gm_ld, const float* gamma, const float* beta, float* c1,
                               float* c2, float* dgamma, float* dbeta, float* dgamma_mod, float* dw_guide, int dw_ld,
                               float* dbias_guide, void* stream);
+/* ---- GUNet `after_affine` (NetworksV2/GUNet.py:213-214, Backbone/slim_nets.py:152-212 channel_wise_affine): a per-channel
+ * gamma_a * u + beta_a between the modulation and the ReLU of every encoder block. With u = y*scale + shift + guide.w
+ * the affine folds into the same three quantities, so no pass changes: bsl_norm_affine_fold rewrites scale *= gamma_a,
+ * shift = shift*gamma_a + beta_a in place (keeping the un-folded values in scale_pre / shift_pre for the backward
+ * finaliser) and writes the gamma_a-scaled guide filter w_eff[g * c + ch] the *_mod passes then read. */
+int bsl_norm_affine_fold(bsl_ctx* ctx, const bsl_norm_desc* d, const float* gamma_a, const float* beta_a, float* scale,
+                         float* shift, float* scale_pre, float* shift_pre, const float* w_guide /*nullable*/, int w_ld,
+                         int guide_channels, float* w_eff /*[guide_channels][c], nullable*/, void* stream);
+/* bsl_norm_bwd_finalize_mod for a layer with the folded affine. `sums` were reduced with the FOLDED scale / shift /
+ * w_eff (they are sums of dz, the gradient after the affine); scale_pre / shift_pre / w_guide are the un-folded ones.
+ * Emits dgamma_a[c] = sum_n (scale_pre/rstd * S1 + (shift_pre + mean*scale_pre) * S0 + sum_g w_g * T_g) and
+ * dbeta_a[c] = sum_n S0, and every other gradient with the sums scaled by gamma_a (du = gamma_a * dz). */
+int bsl_norm_bwd_finalize_affine(bsl_ctx* ctx, const bsl_norm_desc* d, const double* sums, int guide_channels,
+                                 const float* gamma_mod, int gm_ld, const float* gamma, const float* beta,
+                                 const float* gamma_a, const float* mean, const float* rstd, const float* scale_pre,
+                                 const float* shift_pre, const float* w_guide, int w_ld, float* c1, float* c2,
+                                 float* dgamma, float* dbeta, float* dgamma_mod, float* dw_guide, int dw_ld,
+                                 float* dbias_guide, float* dgamma_a, float* dbeta_a, void* stream);
 int bsl_norm_bwd_apply_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const void* dy_bf16, int dy_ld,
                            const float* mean, const float* rstd, const float* scale, const float* shift,
                            const float* c1, const float* c2, const bsl_guide* guide, void* dx_bf16, int dx_ld,

@@ -33,6 +33,8 @@ class GUNetCfg:
     context_fc_channels: tuple = (256, 256)
     norm_with_center: bool = True        # GUNet.yml; ext_config/GUNet_BOTH.yml has False
     norm_with_scale: bool = False
+    after_affine: bool = False           # ext_config/GUNet*_AA.yml, GUNetV2.yml, GUNet_BOTHV2.yml: slim_nets.affine
+                                         # (channel_wise_affine, Backbone/slim_nets.py:152-212) before every encoder ReLU
     use_context: bool = True             # --use_context
     use_spatial: bool = True             # --use_spatial
     guide_channel: int = 1               # --guide_channel
@@ -83,9 +85,13 @@ def layer_specs(cfg: GUNetCfg):
     for i in range(cfg.num_down_samples + 1):
         mod = i in cfg.mod_layers and (cfg.use_context or cfg.use_spatial)
         for j in (1, 2):
+            # encoder_arg_scope (GUNet.py:313-330): the modulated blocks' normaliser takes center / scale from the YAML,
+            # both forced off by after_affine; un-modulated blocks pass normalizer_params={} (slim defaults: both on)
+            aa = cfg.after_affine
             s = dict(kind="conv", scope=f"{cfg.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/Conv", cin=cin, cout=c, level=i,
-                     role=f"enc{j}", mod=mod, center=cfg.norm_with_center if mod else True,
-                     scale=cfg.norm_with_scale if mod else True, mod_off=None, sp_off=None)
+                     role=f"enc{j}", mod=mod, center=(cfg.norm_with_center and not aa) if mod else True,
+                     scale=(cfg.norm_with_scale and not aa) if mod else True, mod_off=None, sp_off=None,
+                     affine=f"{cfg.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/ChannelWiseAffine" if aa else None)
             if mod and cfg.use_context:
                 s["mod_off"] = off
                 off += c
@@ -101,7 +107,7 @@ def layer_specs(cfg: GUNetCfg):
         for j in (1, 2):
             specs.append(dict(kind="conv", scope=f"{cfg.prefix}/Decode/up_conv{i + 1}/up_conv{i + 1}_{j}",
                               cin=c + cin // 2 if j == 1 else c, cout=c, level=i, role=f"dec{j}", mod=False, center=True,
-                              scale=True, mod_off=None, sp_off=None))
+                              scale=True, mod_off=None, sp_off=None, affine=None))
         cin = c
     specs.append(dict(kind="logits", scope=f"{cfg.prefix}/AdjustChannels", cin=cin, cout=cfg.num_classes, level=0))
     return specs
@@ -128,6 +134,9 @@ def init_params(cfg: GUNetCfg, seed: int = 0, dtype=np.float32) -> dict:
                 p[f"{sc}/InstanceNorm/gamma"] = np.ones(cout, dtype)
             if s["center"]:
                 p[f"{sc}/InstanceNorm/beta"] = np.zeros(cout, dtype)
+            if s["affine"]:
+                p[f"{s['affine']}/gamma"] = np.ones(cout, dtype)
+                p[f"{s['affine']}/beta"] = np.zeros(cout, dtype)
         elif s["kind"] == "convT":
             p[f"{sc}/weights"] = O.xavier_uniform(rng, (2, 2, cout, cin), 4 * cout, 4 * cin, dtype)
             p[f"{sc}/biases"] = np.zeros(cout, dtype)
@@ -254,11 +263,15 @@ def forward(params: dict, inputs: dict, cfg: GUNetCfg, is_training: bool, rnd=_i
             bsp = params[f"{ssc}/biases"].astype(dt)[s["sp_off"]:s["sp_off"] + cout]
             sp = dict(scope=ssc, guide=tape.guides[s["level"]], w=wsp)
             z = z + (sp["guide"] @ wsp + bsp)
+        u = z
+        if s["affine"]:                      # modulated_conv_block: `if after_affine: net = slim_nets.affine(net)`
+            z = z * params[f"{s['affine']}/gamma"].astype(dt) + params[f"{s['affine']}/beta"].astype(dt)
         a = rnd(O.relu(z)).astype(dt)
         if stored is not None:
             tape.errs[f"{sc}:a"] = rel(stored[sc]["a"], a)
             a = stored[sc]["a"].astype(dt)
-        tape.layers.append(dict(kind="conv", spec=s, x=x, w=w, z=z, zn=zn, a=a, cache=cache, first=first, gm=gm, sp=sp))
+        tape.layers.append(dict(kind="conv", spec=s, x=x, w=w, z=z, zn=zn, u=u, a=a, cache=cache, first=first, gm=gm,
+                                sp=sp, ga=params[f"{s['affine']}/gamma"].astype(dt) if s["affine"] else None))
         return a
 
     specs = layer_specs(cfg)
@@ -335,6 +348,10 @@ def backward(tape: Tape, dlogits: np.ndarray, cfg: GUNetCfg, rnd=_identity) -> d
             s = L["spec"]
             sc, cout = s["scope"], s["cout"]
             dz = O.relu_grad(d, L["a"])   # a > 0 <=> z > 0; with a stored tape the mask is the other side's bits
+            if L["ga"] is not None:
+                grads[f"{s['affine']}/gamma"] = (dz * L["u"]).sum(axis=(0, 1, 2))
+                grads[f"{s['affine']}/beta"] = dz.sum(axis=(0, 1, 2))
+                dz = dz * L["ga"]
             if L["sp"] is not None:
                 ssc, off = L["sp"]["scope"], s["sp_off"]
                 gw = np.einsum("nhwg,nhwc->gc", L["sp"]["guide"], dz)

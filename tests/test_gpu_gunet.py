@@ -3,8 +3,7 @@ loss, backward) against oracle/gunet_ref.py, through the C ABI.
 
 Gates (relative L2 per tensor; bf16 path, north_star tolerance 1e-2):
   * every layer evaluated by the fp64 oracle on the tensor the device stored as its input ........ <= 1e-2
-  * gradients: oracle backward over the device's stored forward tape (same ReLU masks) ........... median <= 1e-2,
-    worst <= 1.5e-2; fp32-only paths (context MLP, guide convs) ................................... <= 1e-3
+  * gradients: oracle backward over the device's stored forward tape (same ReLU masks) ........... every tensor <= 1e-2
   * dropout multipliers (Philox4x32-10) ........................................................... bit-exact
 """
 import ctypes as C
@@ -17,7 +16,7 @@ from boxsegliver_b200.device import round_bf16
 from boxsegliver_b200.gunet_engine import GUNetConfig, GUNetEngine
 from oracle import gunet_ref as G
 from oracle import tf_ops as O
-from tests.gpu_util import rel
+from tests.gpu_util import TOL_BF16, rel, report
 
 pytestmark = pytest.mark.gpu
 
@@ -82,6 +81,13 @@ def _make(n, hw, **kw):
     (2, 64, dict(use_context=False, use_spatial=True, guide_channel=2, norm_with_scale=True, mod_layers=(0, 2, 4),
                  loss_type="dice")),
     (2, 64, dict(use_context=True, use_spatial=False, side_dropout=0.0, loss_type="xentropy")),
+    # after_affine (slim_nets.channel_wise_affine before every encoder ReLU): ext_config/GUNet_BOTH_AA.yml,
+    # GUNet_DE_AA.yml (context only), and an un-modulated first block that keeps its own centre / scale
+    (2, 64, dict(use_context=True, use_spatial=True, guide_channel=1, norm_with_center=True, norm_with_scale=True,
+                 after_affine=True, context_fc_channels=(200, 200), loss_type="xentropy+dice")),
+    (2, 64, dict(use_context=True, use_spatial=False, after_affine=True, loss_type="xentropy")),
+    (2, 64, dict(use_context=False, use_spatial=True, guide_channel=2, after_affine=True, mod_layers=(0, 1),
+                 loss_type="xentropy")),
 ])
 def test_gunet_train_step_parity(ctx, n, hw, kw):
     ecfg, rcfg, inputs, labels = _make(n, hw, **kw)
@@ -129,8 +135,10 @@ def test_gunet_train_step_parity(ctx, n, hw, kw):
     g_ref = G.backward(tft, dl, rcfg, rnd=round_bf16)
     assert set(g_ref) == set(grads)
     errs = {name: rel(grads[name], g) for name, g in g_ref.items()}
-    assert np.median(list(errs.values())) < 1e-2, errs
-    assert max(errs.values()) < 1.5e-2, max(errs.items(), key=lambda t: t[1])
+    worst = max(errs.items(), key=lambda t: t[1])
+    report("gunet/unetinter step", layer_worst=max(tft.errs.values()), grad_median=float(np.median(list(errs.values()))),
+           grad_worst=worst[1], grad_worst_name=worst[0])
+    assert worst[1] < TOL_BF16, worst
 
 
 def test_unetinter_train_step_parity(ctx):
@@ -179,5 +187,7 @@ def test_unetinter_train_step_parity(ctx):
     g_ref = G.backward(tft, dl, rcfg, rnd=round_bf16)
     errs = {name: rel(grads[name], g) for name, g in g_ref.items()}
     assert set(g_ref) == set(grads)
-    assert np.median(list(errs.values())) < 1e-2, errs
-    assert max(errs.values()) < 1.5e-2, max(errs.items(), key=lambda t: t[1])
+    worst = max(errs.items(), key=lambda t: t[1])
+    report("gunet/unetinter step", layer_worst=max(tft.errs.values()), grad_median=float(np.median(list(errs.values()))),
+           grad_worst=worst[1], grad_worst_name=worst[0])
+    assert worst[1] < TOL_BF16, worst

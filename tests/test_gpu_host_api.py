@@ -148,7 +148,8 @@ def test_engine_honours_optimizer_hyperparameters(ctx, kw):
             want, _, _ = O.adam_step(w, ge, 0.0 * w, 0.0 * w, 1, 1e-3, cfg.adam_beta1, cfg.adam_beta2, cfg.adam_eps,
                                      decoupled_decay=decay)
         upd, ref = w1[name].astype(np.float64) - w, want - w
-        assert np.linalg.norm(upd - ref) <= 1e-4 * np.linalg.norm(ref) + 1e-9, (name, kw)
+        # the update is rounded onto the fp32 grid of w (half an ulp per element on top of the 1e-4 gate)
+        assert np.linalg.norm(upd - ref) <= 1e-4 * np.linalg.norm(ref) + 2.0 ** -24 * np.linalg.norm(w) + 1e-9, (name, kw)
 
 
 def test_trunc_norm_initializer_and_flag_plumbing(ctx):

@@ -2,11 +2,12 @@
 numpy oracle, plus full-size properties at BASELINE cfg2 (batch 64, 256x256x3).
 
 Gates (relative L2 norm per tensor, bf16 path, north_star tolerance 1e-2):
-  * logits vs the oracle run with bf16-storage emulation ......................... <= 1.5e-2 (tiny-batch BN
-    statistics amplify last-ulp differences; at these test sizes the fp64 oracle itself sits at ~2e-2)
+  * every forward op on identical inputs (fp64 oracle op vs the stored device output) ............ <= 1e-2
   * gradients: oracle backward over the DEVICE's stored forward tensors, so that ReLU masks and max-pool
-    arg-maxes are the same bits on both sides ...................................... median <= 1e-2, worst <= 1.5e-2
+    arg-maxes are the same bits on both sides ...................................... every tensor <= 1e-2
   * `p > 0.5` masks, argmax and Dice I/L/R counts ................................ bit-exact given the logits
+Reported, bounded only by a sanity limit (tests/gpu_util.FREE_RUNNING_SANITY): the free-running logits vs the oracle
+with bf16-storage emulation (tiny-batch BN statistics amplify last-ulp differences).
 """
 import numpy as np
 import pytest
@@ -15,7 +16,7 @@ from boxsegliver_b200 import synthetic
 from boxsegliver_b200.device import round_bf16
 from boxsegliver_b200.engine import EngineConfig, UNetEngine
 from oracle import unet_ref as R
-from tests.gpu_util import rel
+from tests.gpu_util import FREE_RUNNING_SANITY, TOL_BF16, rel, report
 
 pytestmark = pytest.mark.gpu
 
@@ -71,7 +72,8 @@ def test_train_step_parity(ctx, n, hw, normalizer, loss_type, wtype):
     # forward: free-running oracle with bf16 storage emulation
     tape = R.forward(params, round_bf16(images), rcfg, True, rnd=round_bf16, stem_fp32=False)
     loss_o, _ = R.loss_and_dlogits(tape, labels, rcfg)
-    assert rel(logits, tape.logits) < 1.5e-2
+    e_free = rel(logits, tape.logits)
+    assert e_free < FREE_RUNNING_SANITY
     assert abs(data_loss - float(loss_o)) < 1e-3 * abs(float(loss_o))
     assert abs(reg_loss - R.regularization_loss(params, rcfg)) < 1e-6
     if normalizer == "batch_norm":
@@ -88,8 +90,11 @@ def test_train_step_parity(ctx, n, hw, normalizer, loss_type, wtype):
     assert rel(dlogits, dl) < 1e-5
     g_ref = R.backward(tft, dl, rcfg, rnd=round_bf16)
     errs = {name: rel(grads[name], g) for name, g in g_ref.items()}
-    assert np.median(list(errs.values())) < 1e-2, errs
-    assert max(errs.values()) < 1.5e-2, max(errs.items(), key=lambda t: t[1])
+    worst = max(errs.items(), key=lambda t: t[1])
+    report(f"unet {n}x{hh}x{ww} {normalizer} {loss_type}/{wtype}", op_by_op_worst=max(lw.values()),
+           grad_median=float(np.median(list(errs.values()))), grad_worst=worst[1], grad_worst_name=worst[0],
+           free_running_logits=e_free)
+    assert worst[1] < TOL_BF16, worst
 
     # masks / argmax / counts: bit-exact functions of the device's own logits
     prob = R.O.softmax(logits)
@@ -135,7 +140,7 @@ def test_eval_mode_uses_moving_statistics(ctx):
     stored = eng.get_stored_forward()
     eng.close()
     tape = R.forward(params, round_bf16(images), rcfg, False, rnd=round_bf16, stem_fp32=False)
-    assert rel(logits, tape.logits) < 1.5e-2
+    assert rel(logits, tape.logits) < FREE_RUNNING_SANITY
     lw = R.layerwise_forward_errors(params, round_bf16(images), stored, logits, rcfg, False, wrnd=round_bf16)
     assert max(lw.values()) < 1e-2, max(lw.items(), key=lambda t: t[1])
     for name in params:

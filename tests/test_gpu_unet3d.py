@@ -1,6 +1,6 @@
 """Parity of the UNet3D engine against oracle/unet3d_ref.py through the C ABI: every layer on the device's stored
-input (fp64 oracle, rel <= 1e-2), loss, dlogits, and all gradients over the device's stored tape (median <= 1e-2,
-worst <= 1.5e-2; north_star bf16 tolerance), with the true channel counts 30/60/120/240/320 (zero-padded storage)."""
+input (fp64 oracle, rel <= 1e-2), loss, dlogits, and all gradients over the device's stored tape (every tensor whose
+layer normalises over >= 64 voxels <= 1e-2, north_star bf16 tolerance), with the true channel counts 30/60/120/240/320 (zero-padded storage)."""
 import numpy as np
 import pytest
 
@@ -8,7 +8,7 @@ from boxsegliver_b200 import synthetic
 from boxsegliver_b200.device import round_bf16
 from boxsegliver_b200.unet3d_engine import UNet3DConfig, UNet3DEngine
 from oracle import unet3d_ref as U
-from tests.gpu_util import rel
+from tests.gpu_util import rel, report
 
 pytestmark = pytest.mark.gpu
 
@@ -72,15 +72,20 @@ def test_unet3d_train_step_parity(ctx, n, d, hw, kw):
     g_ref = U.backward(tft, dl, rcfg, rnd=round_bf16)
     errs = {name: rel(grads[name], g) for name, g in g_ref.items()}
     assert np.median(list(errs.values())) < 1e-2, errs
-    # Layers whose instance-norm statistics run over fewer than 64 voxels (the deepest blocks of these deliberately
-    # tiny test volumes) amplify single bf16 roundings of the incoming gradient: gate them at 5e-2, the rest at 1.5e-2.
+    # north_star's 1e-2 is gated on every gradient whose layer normalises over >= 64 voxels. The deepest blocks of these
+    # deliberately tiny test volumes normalise over 2 .. 32 voxels: a single bf16 rounding of the incoming gradient moves
+    # such statistics by percents in ANY bf16 implementation, so those are reported and bounded at 5e-2 (the full-size
+    # volumes of BASELINE cfg4, where every layer has >= 4096 voxels, are covered by tests/test_gpu_baseline_shapes.py).
     vox = {}
     for sp in U.layer_specs(rcfg):
         o = [-(-sp["dhw"][i] // sp["s"][i]) for i in range(3)] if sp["kind"] == "conv" else [sp["dhw"][i] * sp["s"][i] for i in range(3)]
         vox[sp["scope"]] = int(np.prod(o))
     for name, e in errs.items():
         scope = name.rsplit("/InstanceNorm", 1)[0].rsplit("/weights", 1)[0].rsplit("/biases", 1)[0]
-        assert e < (1.5e-2 if vox[scope] >= 64 else 5e-2), (name, e, vox[scope])
+        assert e < (1e-2 if vox[scope] >= 64 else 5e-2), (name, e, vox[scope])
+    big = [e for nm, e in errs.items() if vox[nm.rsplit("/InstanceNorm", 1)[0].rsplit("/weights", 1)[0].rsplit("/biases", 1)[0]] >= 64]
+    report(f"unet3d {n}x{d}x{hw}x{hw}", layer_worst=max(tft.errs.values()), grad_median=float(np.median(list(errs.values()))),
+           grad_worst_ge64_voxels=max(big), grad_worst_tiny_statistics=max(errs.values()))
     # masks and integer Dice counts: bit-exact functions of the device's logits
     prob = U.O.softmax(logits)
     decided = np.abs(prob[..., 1] - 0.5) > 1e-6

@@ -73,6 +73,8 @@ def _torch_gunet(params, inputs, labels, cfg, mults):
             ssc = f"GUNet/spatial/conv{s['level'] + 1}"
             full = F.conv2d(guides[s["level"]], P[f"{ssc}/weights"].permute(3, 2, 0, 1), P[f"{ssc}/biases"])
             y = y + full[:, s["sp_off"]:s["sp_off"] + co]
+        if s.get("affine"):
+            y = y * P[f"{s['affine']}/gamma"][None, :, None, None] + P[f"{s['affine']}/beta"][None, :, None, None]
         return torch.relu(y)
 
     it = iter(G.layer_specs(cfg))
@@ -113,6 +115,10 @@ def _torch_gunet(params, inputs, labels, cfg, mults):
     dict(use_context=True, use_spatial=True, guide_channel=2, norm_with_center=True, loss_type="xentropy+dice"),
     dict(use_context=True, use_spatial=False, norm_with_center=False, side_dropout=0.0, loss_type="xentropy"),
     dict(use_context=False, use_spatial=True, guide_channel=1, norm_with_scale=True, mod_layers=(0, 2), loss_type="dice"),
+    # ext_config/GUNet_BOTH_AA.yml: channel-wise affine after the modulation of every encoder block
+    dict(use_context=True, use_spatial=True, guide_channel=1, norm_with_center=True, norm_with_scale=True,
+         after_affine=True, loss_type="xentropy+dice"),
+    dict(use_context=True, use_spatial=False, after_affine=True, side_dropout=0.0, mod_layers=(0, 1), loss_type="xentropy"),
 ])
 def test_oracle_matches_torch_autograd(kw):
     cfg = G.GUNetCfg(height=16, width=16, init_channels=4, num_down_samples=2, mod_layers=kw.pop("mod_layers", (1, 2)),
@@ -179,3 +185,13 @@ def test_parameter_inventory_matches_reference_naming():
     assert "GUNet/Decode/up_conv1/up_conv1_2/InstanceNorm/beta" in p
     reg = G.regularized_names(cfg, p)
     assert "GUNet/spatial/conv2/weights" in reg and "GUNet/context/fc1/weights" not in reg
+    # after_affine (ext_config/GUNet_BOTH_AA.yml): every encoder block gets ChannelWiseAffine/{gamma,beta} next to its
+    # Conv scope; the modulated blocks' normaliser loses centre and scale (GUNet.py:318-319), block 0 keeps both
+    pa = G.init_params(G.GUNetCfg(height=32, width=32, after_affine=True, norm_with_scale=True))
+    assert "GUNet/Encode/down_conv3/mod_conv2/ChannelWiseAffine/gamma" in pa
+    assert "GUNet/Encode/down_conv1/mod_conv1/ChannelWiseAffine/beta" in pa
+    assert "GUNet/Encode/down_conv3/mod_conv2/Conv/InstanceNorm/beta" not in pa
+    assert "GUNet/Encode/down_conv3/mod_conv2/Conv/InstanceNorm/gamma" not in pa
+    assert "GUNet/Encode/down_conv1/mod_conv1/Conv/InstanceNorm/gamma" in pa
+    assert not any("ChannelWiseAffine" in k for k in G.regularized_names(G.GUNetCfg(after_affine=True), pa))
+    assert not any("Decode" in k and "ChannelWiseAffine" in k for k in pa)
