@@ -530,8 +530,9 @@ int bsl_debug_read_waits(bsl_ctx* ctx, long long* out, int ctas) {
 
 // fprop on the halo-tile kernel; `sums` (fp64 [2][cout], nullable) receives the per-channel sum and
 // sum of squares of the bf16 outputs, reduced deterministically from per-CTA partials.
+// group_imgs > 0: instance statistics, sums is [n / group_imgs][2][cout] (one group = group_imgs consecutive images).
 static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
-                             double* sums, cudaStream_t stream, const bsl_pipe* wait = nullptr) {
+                             double* sums, cudaStream_t stream, const bsl_pipe* wait = nullptr, int group_imgs = 0) {
   const int halo = d->kh == 3 ? 1 : 0;
   HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, d->cout);
   int res_stages = 0, res_smem = 0;
@@ -559,13 +560,31 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
   if (!sums)
     return res ? launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
                : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
-  if (pl.bn == 256) {
+  const int groups = group_imgs > 0 ? d->n / group_imgs : 1;
+  const long long ppg = group_imgs > 0 ? (long long)group_imgs * d->h * d->w : (long long)d->n * d->h * d->w;
+  if (pl.bn == 256 || (group_imgs > 0 && pl.grid % pl.n_ntiles != 0)) {
     // long-reduction layers: small, L2-resident outputs; a separate statistics pass is cheaper than an
     // un-overlapped epilogue butterfly
     if ((rc = launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream))) return rc;
-    return bsl_stats_bf16(ctx, y, (long long)d->n * d->h * d->w, 1, d->cout, d->y_ld, sums, stream);
+    return bsl_stats_bf16(ctx, y, ppg, groups, d->cout, d->y_ld, sums, stream);
   }
   float* part = nullptr;
+  if (group_imgs > 0) {
+    // [group][slot * 4 + lane quarter][2][cout], zero-filled: a CTA only writes the groups its units fall into
+    const size_t bytes = (size_t)groups * pl.slots * 4 * 2 * d->cout * sizeof(float);
+    if ((rc = bsl_scratch(ctx, bytes, &part, stream))) return rc;
+    BSL_CUDA(ctx, cudaMemsetAsync(part, 0, bytes, stream));
+    a.stats_part = part;
+    a.stats_group_imgs = group_imgs;
+    a.stats_blocks = pl.slots * 4;
+    rc = res ? launch_halo_res<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
+             : launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+    if (rc) return rc;
+    const int kc2 = 2 * d->cout;
+    bsl_launch(pixel_reduce_final_kernel, dim3((kc2 + 31) / 32, groups), dim3(1024), 0, stream, part, pl.slots * 4, kc2, sums);
+    BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel (conv instance statistics)");
+    return BSL_OK;
+  }
   if ((rc = bsl_scratch(ctx, (size_t)pl.slots * 2 * d->cout * sizeof(float), &part, stream))) return rc;
   a.stats_part = part;
   rc = res ? launch_halo_res<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
@@ -585,6 +604,19 @@ int bsl_conv2d_fprop_stats(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x
   if (halo_eligible(d->w, d->h)) return conv2d_fprop_halo(ctx, d, x, w, y, sums, as_stream(stream));
   if ((rc = bsl_conv2d_fprop(ctx, d, x, w, y, stream))) return rc;
   return bsl_stats_bf16(ctx, y, (long long)d->n * d->h * d->w, 1, d->cout, d->y_ld, sums, as_stream(stream));
+}
+
+int bsl_conv2d_fprop_group_stats(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
+                                 int imgs_per_group, double* sums, void* stream) {
+  int rc = check_conv(ctx, d, true);
+  if (rc) return rc;
+  if (!x || !w || !y || !sums) return bsl_fail(ctx, BSL_EINVAL, "conv2d_fprop_group_stats: null buffer");
+  if (imgs_per_group < 1 || d->n % imgs_per_group)
+    return bsl_fail(ctx, BSL_EINVAL, "conv2d_fprop_group_stats: imgs_per_group=%d must divide n=%d", imgs_per_group, d->n);
+  if (halo_eligible(d->w, d->h)) return conv2d_fprop_halo(ctx, d, x, w, y, sums, as_stream(stream), nullptr, imgs_per_group);
+  if ((rc = bsl_conv2d_fprop(ctx, d, x, w, y, stream))) return rc;
+  return bsl_stats_bf16(ctx, y, (long long)imgs_per_group * d->h * d->w, d->n / imgs_per_group, d->cout, d->y_ld, sums,
+                        as_stream(stream));
 }
 
 int bsl_conv2d_fprop_pipe(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,

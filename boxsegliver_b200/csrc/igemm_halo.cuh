@@ -366,6 +366,12 @@ struct ConvHaloArgs {
   int relu;
   int n_total;
   float* stats_part;             // [slot][2][n_total] per-CTA partial sums (nullptr: no statistics)
+  // instance statistics (stats_group_imgs > 0): a statistics group is stats_group_imgs consecutive images (1 for 2-D
+  // instance norm, the depth of a volume whose slices run as images); each epilogue warp flushes its running sums
+  // whenever the group of the sub-tile it is about to add changes (images come in non-decreasing order), into
+  // stats_part[group][slot * 4 + lane quarter][2][n_total] (zero-filled by the host: not every CTA meets every group)
+  int stats_group_imgs;
+  int stats_blocks;              // slots * 4
   int a_stages;                  // B_RES kernels: activation stages that fit beside the resident filter
   int kd;                        // filter depth (1, or 3 for the (3,3,3) layers of UNet3D): the reduction runs over
   int depth;                     //   (kd, 64-channel block, tap); an "image" is slice z = img % depth of volume img / depth
@@ -748,6 +754,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int bias_n0 = -1;
     uint32_t gphase = 0;
     float* sb = s_bias + (SCATTER ? e * 256 : 0);
+    // instance statistics: this warp's sums of statistics group `g` -> stats_part[g][slot * 4 + q][2][n_total]
+    int cur_grp = -1, last_n0 = 0;
+    auto flush_group = [&](int g, int n0) {
+      if (!STATS) return;
+      float* dst = p.stats_part + ((long long)g * p.stats_blocks + (blockIdx.x / p.n_ntiles) * 4 + q) * (2LL * p.n_total) +
+                   n0 + sc0;
+#pragma unroll
+      for (int c = 0; c < SC; c += 32) {
+        if (PERSIST) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            s1[i] = acc1[c + i];
+            s2[i] = acc2[c + i];
+            acc1[c + i] = acc2[c + i] = 0.f;
+          }
+          ch_transpose_reduce(s1, s2, lane);
+          dst[c + lane] = s1[0];
+          dst[p.n_total + c + lane] = s2[0];
+        } else {
+          const int i0 = (e * 2 + 0) * BN + sc0 + c + lane;
+          dst[c + lane] = s_stats[i0];
+          dst[p.n_total + c + lane] = s_stats[i0 + BN];
+          s_stats[i0] = 0.f;
+          s_stats[i0 + BN] = 0.f;
+        }
+      }
+    };
     for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const int pu = u / p.n_ntiles;
       const int n0 = (u % p.n_ntiles) * BN;
@@ -857,6 +891,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // added first, then one transpose-reduce per 32-column strip and unit.
         const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (NSUB * BN) + sc0;
         __nv_bfloat16* ob[NSUB];
+        int grp[NSUB];
 #pragma unroll
         for (int jj = 0; jj < NSUB; ++jj) {
           int s = pu * NSUB + jj;
@@ -864,45 +899,65 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           s /= p.ntile_w;
           const int ty = s % p.ntile_h;
           const int img = s / p.ntile_h;
+          grp[jj] = p.stats_group_imgs > 0 ? img / p.stats_group_imgs : 0;
           ob[jj] = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)(tx * 8 + (r & 7)) * p.ostride_x +
                    (long long)(ty * 16 + (r >> 3)) * p.ostride_y + (long long)img * p.ostride_n + n0 + sc0;
         }
+        // sub-tiles [j0, j1) of this unit, all of one statistics group
+        auto body = [&](int j0, int j1) {
 #pragma unroll
-        for (int c = 0; c < SC; c += 32) {
-          float s1[32], s2[32];
-          if (!PERSIST) {
+          for (int c = 0; c < SC; c += 32) {
+            float s1[32], s2[32];
+            if (!PERSIST) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) s1[i] = s2[i] = 0.f;
-          }
+              for (int i = 0; i < 32; ++i) s1[i] = s2[i] = 0.f;
+            }
 #pragma unroll
-          for (int jj = 0; jj < NSUB; ++jj) {
-            if (jj < nsub) {
-              uint32_t v[32], packed[16];
-              tmem_ld_32x32(tq + jj * BN + c, v);
-              tmem_ld_wait();
-              ch_store_chunk<false>(v, ob[jj] + c, nullptr, 0, packed, p.narrow_store);
+            for (int jj = 0; jj < NSUB; ++jj) {
+              if (jj >= j0 && jj < j1) {
+                uint32_t v[32], packed[16];
+                tmem_ld_32x32(tq + jj * BN + c, v);
+                tmem_ld_wait();
+                ch_store_chunk<false>(v, ob[jj] + c, nullptr, 0, packed, p.narrow_store);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {   // the bf16 values just stored: what the normalisation pass reads back
-                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[i]));
-                if (PERSIST) {
-                  acc1[c + 2 * i] += f.x;
-                  acc1[c + 2 * i + 1] += f.y;
-                  acc2[c + 2 * i] = fmaf(f.x, f.x, acc2[c + 2 * i]);
-                  acc2[c + 2 * i + 1] = fmaf(f.y, f.y, acc2[c + 2 * i + 1]);
-                } else {
-                  s1[2 * i] += f.x;
-                  s1[2 * i + 1] += f.y;
-                  s2[2 * i] = fmaf(f.x, f.x, s2[2 * i]);
-                  s2[2 * i + 1] = fmaf(f.y, f.y, s2[2 * i + 1]);
+                for (int i = 0; i < 16; ++i) {   // the bf16 values just stored: what the normalisation pass reads back
+                  const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[i]));
+                  if (PERSIST) {
+                    acc1[c + 2 * i] += f.x;
+                    acc1[c + 2 * i + 1] += f.y;
+                    acc2[c + 2 * i] = fmaf(f.x, f.x, acc2[c + 2 * i]);
+                    acc2[c + 2 * i + 1] = fmaf(f.y, f.y, acc2[c + 2 * i + 1]);
+                  } else {
+                    s1[2 * i] += f.x;
+                    s1[2 * i + 1] += f.y;
+                    s2[2 * i] = fmaf(f.x, f.x, s2[2 * i]);
+                    s2[2 * i + 1] = fmaf(f.y, f.y, s2[2 * i + 1]);
+                  }
                 }
               }
             }
+            if (!PERSIST) {
+              ch_transpose_reduce(s1, s2, lane);
+              s_stats[(e * 2 + 0) * BN + sc0 + c + lane] += s1[0];
+              s_stats[(e * 2 + 1) * BN + sc0 + c + lane] += s2[0];
+            }
           }
-          if (!PERSIST) {
-            ch_transpose_reduce(s1, s2, lane);
-            s_stats[(e * 2 + 0) * BN + sc0 + c + lane] += s1[0];
-            s_stats[(e * 2 + 1) * BN + sc0 + c + lane] += s2[0];
+        };
+        if (p.stats_group_imgs > 0) {
+          int j0 = 0;
+          while (j0 < nsub) {
+            int j1 = j0 + 1;
+            while (j1 < nsub && grp[j1] == grp[j0]) ++j1;
+            if (grp[j0] != cur_grp) {
+              if (cur_grp >= 0) flush_group(cur_grp, n0);
+              cur_grp = grp[j0];
+            }
+            body(j0, j1);
+            j0 = j1;
           }
+          last_n0 = n0;
+        } else {
+          body(0, nsub);
         }
       }
       tc_fence_before();
@@ -911,7 +966,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++buf == ACC_BUFS) { buf = 0; pacc ^= 1; }
     }
     if (TMA_ST && q == 0 && lane == 0) bulk_wait_all();   // the staging tiles stay valid until the last store is done
-    if (PERSIST) {
+    if (STATS && p.stats_group_imgs > 0) {
+      if (cur_grp >= 0) flush_group(cur_grp, last_n0);
+    } else if (PERSIST) {
 #pragma unroll
       for (int c = 0; c < SC; c += 32) {
         float s1[32], s2[32];
@@ -925,7 +982,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   __syncthreads();
-  if (STATS && p.stats_part != nullptr) {
+  if (STATS && p.stats_part != nullptr && p.stats_group_imgs == 0) {
     // this CTA always works on column tile blockIdx.x % n_ntiles (the host makes gridDim.x a multiple of it)
     const int n0 = (blockIdx.x % p.n_ntiles) * BN;
     const int slot = blockIdx.x / p.n_ntiles;

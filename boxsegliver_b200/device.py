@@ -89,6 +89,7 @@ class Context:
         self.tag = ""            # label attached to profiled calls (the engine sets it per layer)
         self._prof = None
         self._timeline = None
+        self._trace = None        # list of C-ABI entry-point names in call order (tests: launch-sequence equality)
         s = C.c_void_p()
         self.call("bsl_stream_create", C.byref(s))
         self.stream = s
@@ -107,6 +108,8 @@ class Context:
             st = args[-1] if args and isinstance(args[-1], C.c_void_p) and args[-1].value else self.stream
             e0, e1 = self._prof_event(), self._prof_event()
             self.lib.bsl_event_record(self.h, e0, st)
+        if self._trace is not None and not name.startswith(self._NO_PROF):
+            self._trace.append(name)
         rc = getattr(self.lib, name)(self.h, *args)
         if rc != 0:
             raise BslError(rc, (self.lib.bsl_last_error(self.h) or b"").decode())

@@ -213,6 +213,8 @@ class UNetEngine:
         # measured: the mask loads in the epilogue cost dgrad +0.45 ms, more than the 0.49 ms relu_bwd pass they replace
         self._fuse_relu_bwd = os.environ.get("BSL_FUSE_RELU_BWD", "0") != "0"
         self._fuse_head = os.environ.get("BSL_FUSE_HEAD", "1") != "0"
+        # instance-norm statistics out of the conv epilogue instead of a pass over the conv output (bit-identical outputs)
+        self._fuse_inst_stats = os.environ.get("BSL_FUSE_INST_STATS", "1") != "0"
         # backward of the last normalised layer with the logits-layer dgrad recomputed per pixel from dlogits
         # (bsl_norm_bwd_reduce_head / _apply_head) instead of a 128-byte-per-pixel gradient tensor; bit-identical
         self._fuse_head_bwd = os.environ.get("BSL_FUSE_HEAD_BWD", "1") != "0"
@@ -733,10 +735,14 @@ class UNetEngine:
                 q = self._norm_ptrs(L)
                 ns = self.norm_scope
                 bn = self.cfg.normalizer == "batch_norm"
-                # batch-norm training: the per-channel sums come out of the conv epilogue (no pass over y)
+                # batch-norm training: the per-channel sums come out of the conv epilogue (no pass over y); instance norm
+                # (training and inference): per-(sample, channel) sums from the same epilogue (bsl_conv2d_fprop_group_stats)
                 fused = bn and is_training
+                inst = (not bn) and self._fuse_inst_stats
                 fn = "bsl_conv2d_fprop_stats" if fused else "bsl_conv2d_fprop"
                 extra = (q["sums"],) if fused else ()
+                if inst:
+                    fn, extra = "bsl_conv2d_fprop_group_stats", (C.c_int(1), q["sums"])
                 wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
                 if L.kind == "stem":
                     # im2col (27 -> 64 columns, bf16) + 1x1 conv on the tensor cores
@@ -746,12 +752,13 @@ class UNetEngine:
                 else:
                     pw, done = self._take_pending(s)
                     if pw is not None:
+                        inst = False
                         self._tc("fprop", self._flops(L), "bsl_conv2d_fprop_pipe", C.byref(d), L.x.p, wbf, L.y.p,
                                  q["sums"] if fused else None, C.byref(pw), s)
                         done()
                     else:
                         self._tc("fprop", self._flops(L), fn, C.byref(d), L.x.p, wbf, L.y.p, *extra, s)
-                if not fused and (not bn or is_training):
+                if not fused and not inst and (not bn or is_training):
                     call("bsl_norm_stats", C.byref(nd), L.y.p, q["sums"], s)
                 mm = C.c_void_p(self.S.ptr + self.params[f"{L.scope}/{ns}/moving_mean"].offset * F32) if bn else None
                 mv = C.c_void_p(self.S.ptr + self.params[f"{L.scope}/{ns}/moving_variance"].offset * F32) if bn else None

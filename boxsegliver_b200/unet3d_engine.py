@@ -171,6 +171,7 @@ class UNet3DEngine:
         self.stream = ctx.stream
         # filter gradients on a side stream, as in engine.UNetEngine.loss_backward
         self._overlap_wgrad = cfg.training and os.environ.get("BSL_WGRAD_OVERLAP", "1") != "0"
+        self._fuse_inst_stats = os.environ.get("BSL_FUSE_INST_STATS", "1") != "0"
         if cfg.training:
             self.wg_stream = ctx.new_stream()
             self._dy_events = [ctx.new_event(), ctx.new_event()]
@@ -508,17 +509,24 @@ class UNet3DEngine:
             ctx.tag = L.scope
             if L.kind in ("stem", "conv"):
                 wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
+                nd, q = self._norm_desc(L), self._norm_ptrs(L)
+                # layers that run as 2-D convolutions over n*d images take their per-(volume, channel) statistics from
+                # the conv epilogue: a statistics group is the `depth` consecutive images of one volume
+                fuse = self._fuse_inst_stats
+                fn = "bsl_conv2d_fprop_group_stats" if fuse else "bsl_conv2d_fprop"
+                extra = (C.c_int(L.dhw[0]), q["sums"]) if fuse else ()
                 if L.kind == "stem":
                     d0 = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], L.cin, 64, 3, 3, L.cin, 64)
                     call("bsl_stem_im2col", C.byref(d0), self.images.p, self.stem_col.p, s)
                     d1 = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], 64, L.coutp, 1, 1, 64, L.y.ld)
-                    call("bsl_conv2d_fprop", C.byref(d1), self.stem_col.p, wbf, L.y.p, s)
+                    call(fn, C.byref(d1), self.stem_col.p, wbf, L.y.p, *extra, s)
                 elif self._is2d(L):
-                    call("bsl_conv2d_fprop", C.byref(self._desc2(L)), L.x.p, wbf, L.y.p, s)
+                    call(fn, C.byref(self._desc2(L)), L.x.p, wbf, L.y.p, *extra, s)
                 else:
+                    fuse = False
                     call("bsl_conv3d_fprop", C.byref(self._desc3(L)), L.x.p, wbf, L.y.p, s)
-                nd, q = self._norm_desc(L), self._norm_ptrs(L)
-                call("bsl_norm_stats", C.byref(nd), L.y.p, q["sums"], s)
+                if not fuse:
+                    call("bsl_norm_stats", C.byref(nd), L.y.p, q["sums"], s)
                 call("bsl_norm_finalize", C.byref(nd), C.c_int(1 if is_training else 0), q["sums"],
                      self._pp(self.W, f"{L.scope}/InstanceNorm/gamma"), self._pp(self.W, f"{L.scope}/InstanceNorm/beta"),
                      None, None, q["mean"], q["rstd"], q["scale"], q["shift"], s)

@@ -137,6 +137,12 @@ int bsl_conv2d_dgrad_relu(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy
  * exactly what bsl_norm_stats(mode = batch) computes from y in a separate pass. */
 int bsl_conv2d_fprop_stats(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x_bf16,
                            const void* w_hwio_bf16, void* y_bf16, double* sums, void* stream);
+/* Same fusion for slim.instance_norm (and UNet3D's (1,3,3) layers, whose depth slices run as images): sums is
+ * fp64 [n / imgs_per_group][2][cout], one statistics group per `imgs_per_group` consecutive images (1 for a 2-D
+ * instance norm, the volume depth for NDHWC tensors viewed as n*d images). Equals bsl_conv2d_fprop followed by
+ * bsl_norm_stats in instance mode; the bf16 outputs are bit-identical. */
+int bsl_conv2d_fprop_group_stats(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x_bf16, const void* w_bf16,
+                                 void* y_bf16, int imgs_per_group, double* sums, void* stream);
 /* dx = dgrad(dy, w); dy has stride y_ld, dx has stride x_ld. */
 int bsl_conv2d_dgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* dy_bf16,
                      const void* w_hwio_bf16, void* dx_bf16, void* stream);

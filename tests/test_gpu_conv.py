@@ -146,6 +146,51 @@ def test_conv2d_fprop_fused_statistics(ctx):
             b.free()
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout,y_ld,gi", [
+    (4, 32, 32, 64, 64, 64, 1),      # column tile 64 (per-thread running sums), several units per image
+    (6, 16, 8, 64, 64, 64, 1),       # one 8x16 sub-tile per image: a unit of two sub-tiles spans two groups
+    (6, 16, 8, 64, 128, 128, 2),     # column tile 128, groups of two images
+    (3, 16, 24, 128, 192, 256, 1),   # three column tiles of 64, odd sub-tile count, output inside a wider buffer
+    (8, 32, 32, 64, 128, 128, 4),    # UNet3D-style: 4 depth slices per volume
+    (2, 64, 64, 64, 64, 64, 1),      # more units than CTAs would take in one round
+    (5, 32, 32, 64, 256, 256, 1),    # column tile 256: falls back to the separate statistics pass
+    (2, 12, 20, 64, 128, 128, 1),    # not halo-eligible: general kernel + statistics pass
+])
+def test_conv2d_fprop_group_statistics(ctx, n, h, w, cin, cout, y_ld, gi):
+    """bsl_conv2d_fprop_group_stats == bsl_conv2d_fprop followed by bsl_norm_stats in instance mode over groups of `gi`
+    consecutive images: bit-identical bf16 outputs, sums equal to 1e-5 (different fixed summation order), and
+    bit-reproducible across runs."""
+    rng = np.random.default_rng(h + cout + gi)
+    from boxsegliver_b200.device import round_bf16
+    # distinct statistics per image
+    x = round_bf16(bf16_randn(rng, (n, h, w, cin)) + np.arange(n, dtype=np.float32)[:, None, None, None] * 0.25)
+    wt = bf16_randn(rng, (3, 3, cin, cout), 0.05)
+    dx_, dw_ = ctx.bf16_from_f32(x), ctx.bf16_from_f32(wt)
+    y1 = ctx.alloc(n * h * w * y_ld * 2).zero()
+    y2 = ctx.alloc(n * h * w * y_ld * 2).zero()
+    groups = n // gi
+    s1, s2 = ctx.alloc(groups * 2 * cout * 8).zero(), ctx.alloc(groups * 2 * cout * 8).zero()
+    desc = _lib.Conv2dDesc(n, h, w, cin, cout, 3, 3, cin, y_ld)
+    ctx.call("bsl_conv2d_fprop_group_stats", C.byref(desc), dx_.p, dw_.p, y1.p, C.c_int(gi), s1.p, ctx.stream)
+    ctx.call("bsl_conv2d_fprop", C.byref(desc), dx_.p, dw_.p, y2.p, ctx.stream)
+    nd = _lib.NormDesc(1, groups, gi * h * w, cout, y_ld, y_ld, 1e-6, 0.0, 1, 1, 1)
+    ctx.call("bsl_norm_stats", C.byref(nd), y2.p, s2.p, ctx.stream)
+    ctx.check_device()
+    assert np.array_equal(y1.download(np.uint16, (n, h, w, y_ld)), y2.download(np.uint16, (n, h, w, y_ld)))
+    yv = ctx.bf16_to_f32(y1, (n, h, w, y_ld))[..., :cout].astype(np.float64).reshape(groups, -1, cout)
+    got = s1.download(np.float64, (groups, 2, cout))
+    assert rel(got[:, 0], yv.sum(axis=1)) < 1e-5
+    assert rel(got[:, 1], (yv * yv).sum(axis=1)) < 1e-5
+    for g in range(groups):     # per group, so that a small group cannot hide behind a large one
+        assert rel(got[g], s2.download(np.float64, (groups, 2, cout))[g]) < 1e-5, g
+    ctx.call("bsl_conv2d_fprop_group_stats", C.byref(desc), dx_.p, dw_.p, y1.p, C.c_int(gi), s2.p, ctx.stream)
+    assert np.array_equal(got, s2.download(np.float64, (groups, 2, cout)))
+    with pytest.raises(Exception):
+        ctx.call("bsl_conv2d_fprop_group_stats", C.byref(desc), dx_.p, dw_.p, y1.p, C.c_int(n + 1), s1.p, ctx.stream)
+    for b in (dx_, dw_, y1, y2, s1, s2):
+        b.free()
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,y_ld", [
     (2, 8, 8, 128, 64, None), (1, 16, 16, 64, 64, None), (2, 4, 8, 256, 128, None), (1, 6, 10, 128, 64, None),
     (2, 8, 8, 128, 64, 128), (1, 2, 2, 1024, 512, 1024),
