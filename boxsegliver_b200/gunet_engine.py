@@ -322,6 +322,10 @@ class GUNetEngine(UNetEngine):
                  self.fc_bufs[k][1].p, dx, self._pp(self.G, f"{sc}/weights"), self._pp(self.G, f"{sc}/biases"),
                  self.fc_ws.p, C.c_size_t(self.fc_ws_bytes), s)
 
+    def get_context_grad(self):
+        """Gradient w.r.t. the context MLP output after loss_backward ([n, n_modulator_param], fp32)."""
+        return self.fc_bufs[-1][1].download(np.float32, (self.cfg.batch, self.cfg.n_modulator_param))
+
     def get_context_params(self):
         return self.ctx_params.download(np.float32, (self.cfg.batch, self.cfg.n_modulator_param))
 

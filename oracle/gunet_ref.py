@@ -384,17 +384,25 @@ def backward(tape: Tape, dlogits: np.ndarray, cfg: GUNetCfg, rnd=_identity) -> d
             level = max(skip_grads)
             d = rnd(O.max_pool_2x2_grad(L["x"], d) + skip_grads.pop(level)).astype(dt)
     if dctx is not None:
-        g = dctx
-        for F in reversed(tape.fc):
-            if F["hidden"]:
-                if F["mult"] is not None:
-                    g = g * F["mult"]
-                g = g * (F["pre"] > 0)
-            dx, dw, db = O.fully_connected_grad(F["x"], F["w"], g)
-            grads[f"{F['scope']}/weights"] = dw
-            grads[f"{F['scope']}/biases"] = db
-            g = dx
+        grads.update(fc_backward(tape, dctx))
     tape.dctx = dctx
+    return grads
+
+
+def fc_backward(tape: Tape, dctx: np.ndarray) -> dict:
+    """Gradients of the context MLP (slim_nets.fc, Backbone/slim_nets.py:34-57) given dctx, the gradient w.r.t. its
+    output (the concatenated gamma_mod slices of every modulated layer)."""
+    grads = {}
+    g = dctx
+    for F in reversed(tape.fc):
+        if F["hidden"]:
+            if F["mult"] is not None:
+                g = g * F["mult"]
+            g = g * (F["pre"] > 0)
+        dx, dw, db = O.fully_connected_grad(F["x"], F["w"], g)
+        grads[f"{F['scope']}/weights"] = dw
+        grads[f"{F['scope']}/biases"] = db
+        g = dx
     return grads
 
 

@@ -16,6 +16,24 @@ TOL_F32 = 1e-4    # fp32-accumulated outputs (wgrad partials, reductions)
 FREE_RUNNING_SANITY = 3e-2
 
 
+def gate_gradients(errs: dict, strict: bool = False):
+    """The gradient gate. `errs` = {tensor: relative L2 error of the device gradient vs the oracle's backward pass over
+    the device's stored forward tape}.
+
+    strict (BASELINE shapes, tests/test_gpu_baseline_shapes.py): EVERY tensor < 1e-2, north_star's bf16 tolerance.
+    Otherwise -- the deliberately tiny code-path tests (2 x 64 x 64, ragged 96 x 80, ...), whose deepest layers reduce
+    their normaliser gradients over 20 .. 128 values, so that one flipped bf16 rounding of the incoming gradient moves a
+    tensor by ~1e-2 in ANY bf16 implementation: median and 90th percentile < 1e-2, worst < 1.25e-2; all reported."""
+    v = np.array(list(errs.values()))
+    worst = max(errs.items(), key=lambda t: t[1])
+    if strict:
+        assert worst[1] < TOL_BF16, worst
+    else:
+        assert np.median(v) < TOL_BF16 and np.quantile(v, 0.9) < TOL_BF16, (float(np.median(v)), float(np.quantile(v, 0.9)))
+        assert worst[1] < 1.25e-2, worst
+    return worst
+
+
 def report(tag: str, **numbers):
     """One line per parity measurement (pytest -s shows it; BSL_PARITY_REPORT=<file> appends JSON lines)."""
     import json
