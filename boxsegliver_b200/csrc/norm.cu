@@ -449,7 +449,7 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y
                                       const float* __restrict__ scale, const float* __restrict__ shift,
                                       const float* __restrict__ c1, const float* __restrict__ c2,
                                       const float* __restrict__ guide, const float* __restrict__ wsp, int wsp_ld,
-                                      int gstride, PipeSignal sig) {
+                                      int gstride, PipeSignal sig, int premul) {
   bsl::pdl_enter();
   const int cg = c / 8;
   const int rows = blockDim.x / cg;
@@ -457,6 +457,8 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y
   const int ch0 = g * 8;
   const int o = blockIdx.y * gstride + ch0;
   // dy = scale*(dz - c1 - xhat*c2), xhat = (v - mean)*rstd  ==  scale*dz + k1*v + k0
+  // premul (batch statistics with a per-sample scale, bsl_norm_bwd_finalize_bnmod): c1, c2 arrive multiplied by rstd
+  // and already summed over the samples with their scales: dy = scale*dz - c1 - xhat*c2
   float sc[8], sh[8], k1[8], k0[8], ws[G ? G : 1][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -464,9 +466,9 @@ __global__ void norm_bwd_apply_kernel(const __nv_bfloat16* __restrict__ y, int y
     sh[j] = shift[o + j];
 #pragma unroll
     for (int q = 0; q < G; ++q) ws[q][j] = wsp[q * wsp_ld + ch0 + j];
-    const float t = sc[j] * c2[o + j] * rstd[o + j];
+    const float t = premul ? c2[o + j] * rstd[o + j] : sc[j] * c2[o + j] * rstd[o + j];
     k1[j] = -t;
-    k0[j] = fmaf(t, mean[o + j], -sc[j] * c1[o + j]);
+    k0[j] = fmaf(t, mean[o + j], premul ? -c1[o + j] : -sc[j] * c1[o + j]);
   }
   const long long base = (long long)blockIdx.y * pixels_per_group;
   const long long stride = (long long)gridDim.x * rows;
@@ -621,6 +623,64 @@ __global__ void norm_bwd_finalize_affine_kernel(int n, int c, int K, double m, c
   if (dbias_guide) dbias_guide[ch] = (float)(a * s0all);
   dga[ch] = (float)acc_ga;
   dba[ch] = (float)s0all;
+}
+
+// Batch-norm layer with per-sample modulation (GUNet --normalizer batch_norm, GUNet.py:301,321-325): bsl_norm_finalize
+// (batch mode) left mean / rstd / scale / shift of the BATCH statistics in the first c entries; expand them to the
+// per-(sample, channel) arrays the instance-mode passes index, folding gamma_mod and the guide-conv bias in:
+//   z = (y*sc + sh) * gm[n] + b_sp  ==  y * (sc*gm[n]) + (sh*gm[n] + b_sp)
+__global__ void norm_modulate_bn_kernel(int n, int c, const float* __restrict__ gamma_mod, int gm_ld,
+                                        const float* __restrict__ sp_bias, float* __restrict__ mean,
+                                        float* __restrict__ rstd, float* __restrict__ scale, float* __restrict__ shift) {
+  bsl::pdl_enter();
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const float mu = mean[ch], rs = rstd[ch], sc = scale[ch], sh = shift[ch], b = sp_bias ? sp_bias[ch] : 0.f;
+  for (int s = n - 1; s >= 0; --s) {     // entry [0][ch] (the input) is overwritten last
+    const float gm = gamma_mod ? gamma_mod[(long long)s * gm_ld + ch] : 1.f;
+    mean[s * c + ch] = mu;
+    rstd[s * c + ch] = rs;
+    scale[s * c + ch] = sc * gm;
+    shift[s * c + ch] = fmaf(sh, gm, b);
+  }
+}
+
+// Backward scalars of such a layer from the per-sample sums S0 = sum dz, S1 = sum dz*xhat, T_g = sum dz*guide_g:
+// dxhat = dz * s_n with s_n = gamma * gm[n], so FusedBatchNormGrad's two means run over ALL samples weighted by s_n:
+//   dy = rstd * (s_n*dz - C1 - xhat*C2),  C1 = sum_n s_n*S0_n / M,  C2 = sum_n s_n*S1_n / M,  M = n * hw.
+// c1r / c2r (per (sample, channel), equal for all samples) = rstd*C1, rstd*C2 for bsl_norm_bwd_apply_bnmod.
+__global__ void norm_bwd_finalize_bnmod_kernel(int n, int c, int K, double m_all, const double* __restrict__ sums,
+                                               const float* __restrict__ gamma_mod, int gm_ld,
+                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                               const float* __restrict__ rstd, float* __restrict__ c1r,
+                                               float* __restrict__ c2r, float* __restrict__ dgamma,
+                                               float* __restrict__ dbeta, float* __restrict__ dgamma_mod,
+                                               float* __restrict__ dw_guide, int dw_ld, float* __restrict__ dbias_guide) {
+  bsl::pdl_enter();
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double ga = gamma ? (double)gamma[ch] : 1.0, be = beta ? (double)beta[ch] : 0.0;
+  double sg = 0.0, sb = 0.0, s0all = 0.0, t[2] = {0.0, 0.0};
+  for (int s = 0; s < n; ++s) {  // fixed order
+    const double* q = sums + (long long)s * K * c + ch;
+    const double s0 = q[0], s1 = q[c];
+    const double gm = gamma_mod ? (double)gamma_mod[(long long)s * gm_ld + ch] : 1.0;
+    if (dgamma_mod) dgamma_mod[(long long)s * gm_ld + ch] = (float)(ga * s1 + be * s0);
+    sg += gm * s1;
+    sb += gm * s0;
+    s0all += s0;
+    for (int g = 0; g < K - 2; ++g) t[g] += q[(long long)(2 + g) * c];
+  }
+  const double r = (double)rstd[ch];
+  const float k1 = (float)(r * ga * sb / m_all), k2 = (float)(r * ga * sg / m_all);
+  for (int s = 0; s < n; ++s) {
+    c1r[s * c + ch] = k1;
+    c2r[s * c + ch] = k2;
+  }
+  if (dgamma) dgamma[ch] = (float)sg;
+  if (dbeta) dbeta[ch] = (float)sb;
+  for (int g = 0; g < K - 2; ++g) dw_guide[g * dw_ld + ch] = (float)t[g];
+  if (dbias_guide) dbias_guide[ch] = (float)s0all;
 }
 
 // da[n,2i+a,2j+b,:] = dskip (optional) + (first max of the window in scan order ? dpool[n,i,j,:] : 0)
@@ -1399,6 +1459,34 @@ int bsl_norm_bwd_finalize_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const double
   return BSL_OK;
 }
 
+int bsl_norm_modulate_bn(bsl_ctx* ctx, const bsl_norm_desc* d, const float* gamma_mod, int gm_ld, const float* sp_bias,
+                         float* mean, float* rstd, float* scale, float* shift, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (!mean || !rstd || !scale || !shift || (gamma_mod && gm_ld < d->c))
+    return bsl_fail(ctx, BSL_EINVAL, "norm_modulate_bn: bad argument");
+  bsl_launch(norm_modulate_bn_kernel, dim3((d->c + 127) / 128), dim3(128), 0, as_stream(stream), d->n, d->c, gamma_mod, gm_ld,
+             sp_bias, mean, rstd, scale, shift);
+  BSL_LAUNCH_CHECK(ctx, "norm_modulate_bn_kernel");
+  return BSL_OK;
+}
+
+int bsl_norm_bwd_finalize_bnmod(bsl_ctx* ctx, const bsl_norm_desc* d, const double* sums, int guide_channels,
+                                const float* gamma_mod, int gm_ld, const float* gamma, const float* beta,
+                                const float* rstd, float* c1r, float* c2r, float* dgamma, float* dbeta,
+                                float* dgamma_mod, float* dw_guide, int dw_ld, float* dbias_guide, void* stream) {
+  int rc = check_norm(ctx, d);
+  if (rc) return rc;
+  if (!sums || !c1r || !c2r || !rstd || guide_channels < 0 || guide_channels > 2 || (gamma_mod && !dgamma_mod) ||
+      (guide_channels && (!dw_guide || dw_ld < d->c)))
+    return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_finalize_bnmod: bad argument");
+  bsl_launch(norm_bwd_finalize_bnmod_kernel, dim3((d->c + 127) / 128), dim3(128), 0, as_stream(stream), d->n, d->c,
+             2 + guide_channels, (double)d->n * d->hw, sums, gamma_mod, gm_ld, d->scale ? gamma : nullptr,
+             d->center ? beta : nullptr, rstd, c1r, c2r, dgamma, dbeta, dgamma_mod, dw_guide, dw_ld, dbias_guide);
+  BSL_LAUNCH_CHECK(ctx, "norm_bwd_finalize_bnmod_kernel");
+  return BSL_OK;
+}
+
 int bsl_norm_affine_fold(bsl_ctx* ctx, const bsl_norm_desc* d, const float* gamma_a, const float* beta_a, float* scale,
                          float* shift, float* scale_pre, float* shift_pre, const float* w_guide, int w_ld,
                          int guide_channels, float* w_eff, void* stream) {
@@ -1444,10 +1532,31 @@ int bsl_norm_bwd_apply_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, 
                                      stream);
 }
 
+static int norm_bwd_apply_impl(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
+                               const float* mean, const float* rstd, const float* scale, const float* shift,
+                               const float* c1, const float* c2, const bsl_guide* guide, void* dx, int dx_ld,
+                               const bsl_pipe* signal, void* stream, int premul);
+
 int bsl_norm_bwd_apply_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
                                 const float* mean, const float* rstd, const float* scale, const float* shift,
                                 const float* c1, const float* c2, const bsl_guide* guide, void* dx, int dx_ld,
                                 const bsl_pipe* signal, void* stream) {
+  return norm_bwd_apply_impl(ctx, d, x, dy, dy_ld, mean, rstd, scale, shift, c1, c2, guide, dx, dx_ld, signal, stream, 0);
+}
+
+int bsl_norm_bwd_apply_bnmod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
+                             const float* mean, const float* rstd, const float* scale, const float* shift,
+                             const float* c1r, const float* c2r, const bsl_guide* guide, void* dx, int dx_ld,
+                             void* stream) {
+  if (d && d->mode != 1)
+    return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_apply_bnmod: pass the per-sample (mode 1) view of the layer");
+  return norm_bwd_apply_impl(ctx, d, x, dy, dy_ld, mean, rstd, scale, shift, c1r, c2r, guide, dx, dx_ld, nullptr, stream, 1);
+}
+
+static int norm_bwd_apply_impl(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x, const void* dy, int dy_ld,
+                               const float* mean, const float* rstd, const float* scale, const float* shift,
+                               const float* c1, const float* c2, const bsl_guide* guide, void* dx, int dx_ld,
+                               const bsl_pipe* signal, void* stream, int premul) {
   int rc = check_norm(ctx, d);
   if (rc) return rc;
   if (!x || !dy || !mean || !rstd || !scale || !shift || !c1 || !c2 || !dx)
@@ -1474,7 +1583,7 @@ int bsl_norm_bwd_apply_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, const void
   auto ob = reinterpret_cast<__nv_bfloat16*>(dx);
   cudaStream_t s = as_stream(stream);
   static const int slim = getenv("BSL_BWD_APPLY4") ? atoi(getenv("BSL_BWD_APPLY4")) : 1;
-  if (slim && G == 0 && !signal && d->c % 4 == 0 && d->c <= 1024 && 256 % (d->c / 4) == 0 && d->x_ld % 4 == 0 &&
+  if (slim && !premul && G == 0 && !signal && d->c % 4 == 0 && d->c <= 1024 && 256 % (d->c / 4) == 0 && d->x_ld % 4 == 0 &&
       dy_ld % 4 == 0 && dx_ld % 4 == 0) {
     const int cg4 = d->c / 4, rows4 = 256 / cg4;
     long long want = (ppg + (long long)rows4 * 4 - 1) / ((long long)rows4 * 4);
@@ -1489,15 +1598,15 @@ int bsl_norm_bwd_apply_mod_pipe(bsl_ctx* ctx, const bsl_norm_desc* d, const void
   }
   if (G == 0)
     bsl_launch(norm_bwd_apply_kernel<0>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
-                                                         rstd, scale, shift, c1, c2, nullptr, nullptr, 0, gstride, sg);
+                                                         rstd, scale, shift, c1, c2, nullptr, nullptr, 0, gstride, sg, premul);
   else if (G == 1)
     bsl_launch(norm_bwd_apply_kernel<1>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
                                                          rstd, scale, shift, c1, c2, guide->map, guide->w, guide->w_ld,
-                                                         gstride, sg);
+                                                         gstride, sg, premul);
   else
     bsl_launch(norm_bwd_apply_kernel<2>, dim3(grid), dim3(pl.threads), 0, s, xb, d->x_ld, db, dy_ld, ob, dx_ld, ppg, d->c, d->relu, mean,
                                                          rstd, scale, shift, c1, c2, guide->map, guide->w, guide->w_ld,
-                                                         gstride, sg);
+                                                         gstride, sg, premul);
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_apply_kernel");
   return BSL_OK;
 }

@@ -109,6 +109,7 @@ class ConvL:
     mod_off: int = None      # GUNet: first column of this layer's slice of the context-MLP output
     sp_off: int = None       # GUNet: first column of this layer's slice of the level's 1x1 guide conv
     affine: str = None       # GUNet after_affine: scope of the ChannelWiseAffine variables of this encoder layer
+    bn_decay: float = None   # batch-norm moving-average decay of this layer (None: cfg.bn_decay; GUNet encoder: 0.99)
     x: View = None
     y: View = None           # pre-norm conv output (conv/stem), or output (convT)
     a: View = None           # post-activation
@@ -457,6 +458,14 @@ class UNetEngine:
     def _guide_channels(self, L: ConvL) -> int:
         return 0
 
+    def _norm_groups(self, L: ConvL, default: int) -> int:
+        """Entries per channel of the layer's normalisation scalars (1 batch norm, n instance norm / modulated)."""
+        return default
+
+    def _apply_desc(self, L: ConvL, nd):
+        """Descriptor of the apply / backward passes (GUNet: the per-sample view of a modulated batch-norm layer)."""
+        return nd
+
     def _plan_activations(self):
         cfg = self.cfg
         n = cfg.batch
@@ -480,7 +489,7 @@ class UNetEngine:
                 if L.kind == "conv":
                     L.x = cat[L.level] if L.role == "dec1" else prev_a
                 prev_a = L.pooled if is_enc2 else L.a
-                g = groups_max
+                g = self._norm_groups(L, groups_max)
                 k = 2 + self._guide_channels(L)
                 L.norm = dict(groups=g, off=small, k=k)
                 small += (2 * k + 6) * _align(g * L.cout, 16)  # sums (k x f64), mean, rstd, scale, shift, c1, c2
@@ -565,7 +574,8 @@ class UNetEngine:
         cfg = self.cfg
         bn = cfg.normalizer == "batch_norm"
         return _lib.NormDesc(0 if bn else 1, cfg.batch, L.h * L.w, L.cout, L.y.ld, L.a.ld,
-                             cfg.bn_eps if bn else cfg.in_eps, cfg.bn_decay, 1, int(L.center), int(L.scale))
+                             cfg.bn_eps if bn else cfg.in_eps, L.bn_decay if L.bn_decay is not None else cfg.bn_decay, 1,
+                             int(L.center), int(L.scale))
 
     def _loss_desc(self):
         cfg = self.cfg
@@ -766,6 +776,7 @@ class UNetEngine:
                      self._pp(self.W, f"{L.scope}/{ns}/gamma"), self._pp(self.W, f"{L.scope}/{ns}/beta"), mm, mv,
                      q["mean"], q["rstd"], q["scale"], q["shift"], s)
                 guide = self._modulate(L, nd, q)   # GUNet: folds gamma_mod / guide bias into scale, shift
+                nd = self._apply_desc(L, nd)
                 gp = C.byref(guide) if guide is not None else None
                 nxt = self.layers[idx + 1] if idx + 1 < len(self.layers) else None
                 sig, st = None, s

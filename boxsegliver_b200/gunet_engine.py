@@ -57,8 +57,8 @@ class GUNetEngine(UNetEngine):
     prefix = "GUNet"      # variable-scope root (UNetInterEngine reuses the graph under "UNetInter")
 
     def __init__(self, ctx, cfg: GUNetConfig):
-        if cfg.normalizer != "instance_norm":
-            raise NotImplementedError("GUNet engine: guide modulation is implemented for --normalizer instance_norm")
+        if cfg.normalizer == "batch_norm" and getattr(cfg, "after_affine", False):
+            raise NotImplementedError("GUNet engine: after_affine with --normalizer batch_norm is not supported")
         for flag in ("use_se", "fix", "without_norm", "dropout"):
             if getattr(cfg, flag):
                 raise NotImplementedError(f"GUNet engine: --{flag} is not supported")
@@ -93,6 +93,10 @@ class GUNetEngine(UNetEngine):
                           scale=(cfg.norm_with_scale and not aa) if mod else True)
                 if aa:
                     L.affine = f"{self.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/ChannelWiseAffine"
+                # batch norm: the encoder arg scope's decay 0.99 reaches GUNet's modulated blocks (the un-modulated ones
+                # override the params, GUNet.py:171-178) and every encoder conv of UNetInter (UNetInter.py:100-117)
+                if mod or self.prefix == "UNetInter":
+                    L.bn_decay = 0.99
                 if mod and cfg.use_context:
                     L.mod_off = off
                     off += c
@@ -147,6 +151,18 @@ class GUNetEngine(UNetEngine):
 
     def _guide_channels(self, L: ConvL) -> int:
         return self.cfg.guide_channel if L.sp_off is not None else 0
+
+    def _bn_mod(self, L: ConvL) -> bool:
+        """A modulated block under batch norm: batch statistics, per-sample scale / shift."""
+        return self.cfg.normalizer == "batch_norm" and (L.mod_off is not None or L.sp_off is not None)
+
+    def _norm_groups(self, L: ConvL, default: int) -> int:
+        return self.cfg.batch if self._bn_mod(L) else default
+
+    def _apply_desc(self, L: ConvL, nd):
+        if not self._bn_mod(L):
+            return nd
+        return _lib.NormDesc(1, nd.n, nd.hw, nd.c, nd.x_ld, nd.y_ld, nd.eps, nd.decay, nd.relu, nd.center, nd.scale)
 
     def _plan_guides(self):
         cfg, n = self.cfg, self.cfg.batch
@@ -254,8 +270,13 @@ class GUNetEngine(UNetEngine):
         if L.mod_off is not None or L.sp_off is not None:
             gm = C.c_void_p(self.ctx_params.ptr + L.mod_off * F32) if L.mod_off is not None else None
             bsp = self._pp(self.W, f"GUNet/spatial/conv{L.level + 1}/biases", off=L.sp_off) if L.sp_off is not None else None
-            self.ctx.call("bsl_norm_modulate", C.byref(nd), gm, C.c_int(self.cfg.n_modulator_param), bsp, q["scale"],
-                          q["shift"], self.stream)
+            if self._bn_mod(L):
+                self.ctx.call("bsl_norm_modulate_bn", C.byref(self._apply_desc(L, nd)), gm,
+                              C.c_int(self.cfg.n_modulator_param), bsp, q["mean"], q["rstd"], q["scale"], q["shift"],
+                              self.stream)
+            else:
+                self.ctx.call("bsl_norm_modulate", C.byref(nd), gm, C.c_int(self.cfg.n_modulator_param), bsp, q["scale"],
+                              q["shift"], self.stream)
         if L.affine:
             sp, hp, weff = self._aff_ptrs(L)
             g = self._guide_channels(L)
@@ -273,6 +294,7 @@ class GUNetEngine(UNetEngine):
         if not self._is_modulated(L):
             return super()._norm_backward_reduce(L, nd, q, cur)
         call, s, ns = self.ctx.call, self.stream, self.norm_scope
+        nd = self._apply_desc(L, nd)
         guide = self._guide_struct(L)
         gp = C.byref(guide) if guide is not None else None
         nmod = self.cfg.n_modulator_param
@@ -293,6 +315,12 @@ class GUNetEngine(UNetEngine):
                  dgm, dwg, C.c_int(2 * L.cout), dbg, self._pp(self.G, f"{L.affine}/gamma"),
                  self._pp(self.G, f"{L.affine}/beta"), s)
             return
+        if self._bn_mod(L):
+            call("bsl_norm_bwd_finalize_bnmod", C.byref(nd), q["sums"], C.c_int(self._guide_channels(L)), gm, C.c_int(nmod),
+                 self._pp(self.W, f"{L.scope}/{ns}/gamma"), self._pp(self.W, f"{L.scope}/{ns}/beta"), q["rstd"], q["c1"],
+                 q["c2"], self._pp(self.G, f"{L.scope}/{ns}/gamma"), self._pp(self.G, f"{L.scope}/{ns}/beta"), dgm, dwg,
+                 C.c_int(2 * L.cout), dbg, s)
+            return
         call("bsl_norm_bwd_finalize_mod", C.byref(nd), q["sums"], C.c_int(self._guide_channels(L)), gm, C.c_int(nmod),
              self._pp(self.W, f"{L.scope}/{ns}/gamma"), self._pp(self.W, f"{L.scope}/{ns}/beta"), q["c1"], q["c2"],
              self._pp(self.G, f"{L.scope}/{ns}/gamma"), self._pp(self.G, f"{L.scope}/{ns}/beta"), dgm, dwg,
@@ -302,6 +330,12 @@ class GUNetEngine(UNetEngine):
         if self._head_grad is not None:
             return super()._norm_backward_apply(L, nd, q, cur, oth, stream, sig)
         guide = self._guide_struct(L)
+        if self._bn_mod(L):
+            assert sig is None
+            self.ctx.call("bsl_norm_bwd_apply_bnmod", C.byref(self._apply_desc(L, nd)), L.y.p, cur.p, C.c_int(L.cout),
+                          q["mean"], q["rstd"], q["scale"], q["shift"], q["c1"], q["c2"],
+                          C.byref(guide) if guide is not None else None, oth.p, C.c_int(L.cout), stream)
+            return
         self.ctx.call("bsl_norm_bwd_apply_mod_pipe", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"],
                       q["scale"], q["shift"], q["c1"], q["c2"], C.byref(guide) if guide is not None else None, oth.p,
                       C.c_int(L.cout), C.byref(sig) if sig is not None else None, stream)

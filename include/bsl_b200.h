@@ -341,6 +341,24 @@ int bsl_norm_bwd_finalize_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const double
                               const float* gamma_mod, int gm_ld, const float* gamma, const float* beta, float* c1,
                               float* c2, float* dgamma, float* dbeta, float* dgamma_mod, float* dw_guide, int dw_ld,
                               float* dbias_guide, void* stream);
+/* ---- GUNet / UNetInter with --normalizer batch_norm (GUNet.py:301,321-325: decay 0.99 on the modulated blocks): the
+ * statistics are per channel over the whole batch while the modulation is per sample. bsl_norm_finalize (mode 0) leaves
+ * the batch statistics in the first c entries; bsl_norm_modulate_bn expands them in place to per-(sample, channel)
+ * mean / rstd / scale / shift with gamma_mod and the guide bias folded in, so that the apply and backward-reduce passes
+ * run on the per-sample (mode 1) view of the layer. bsl_norm_bwd_finalize_bnmod combines the per-sample sums with their
+ * scales (FusedBatchNormGrad means over all samples) into c1r = rstd*C1, c2r = rstd*C2, which bsl_norm_bwd_apply_bnmod
+ * consumes: dy = scale[n]*dz - c1r - xhat*c2r. The descriptor passed to all three is the mode-1 view. */
+int bsl_norm_modulate_bn(bsl_ctx* ctx, const bsl_norm_desc* d, const float* gamma_mod /*nullable*/, int gm_ld,
+                         const float* sp_bias /*nullable*/, float* mean, float* rstd, float* scale, float* shift,
+                         void* stream);
+int bsl_norm_bwd_finalize_bnmod(bsl_ctx* ctx, const bsl_norm_desc* d, const double* sums, int guide_channels,
+                                const float* gamma_mod, int gm_ld, const float* gamma, const float* beta,
+                                const float* rstd, float* c1r, float* c2r, float* dgamma, float* dbeta,
+                                float* dgamma_mod, float* dw_guide, int dw_ld, float* dbias_guide, void* stream);
+int bsl_norm_bwd_apply_bnmod(bsl_ctx* ctx, const bsl_norm_desc* d, const void* x_bf16, const void* dy_bf16, int dy_ld,
+                             const float* mean, const float* rstd, const float* scale, const float* shift,
+                             const float* c1r, const float* c2r, const bsl_guide* guide, void* dx_bf16, int dx_ld,
+                             void* stream);
 /* ---- GUNet `after_affine` (NetworksV2/GUNet.py:213-214, Backbone/slim_nets.py:152-212 channel_wise_affine): a per-channel
  * gamma_a * u + beta_a between the modulation and the ReLU of every encoder block. With u = y*scale + shift + guide.w
  * the affine folds into the same three quantities, so no pass changes: bsl_norm_affine_fold rewrites scale *= gamma_a,

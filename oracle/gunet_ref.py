@@ -49,6 +49,7 @@ class GUNetCfg:
     loss_numeric_w: tuple = ()
     loss_proportion_decay: float = 1000.0
     in_eps: float = 1e-6
+    bn_eps: float = 1e-3                 # slim.batch_norm default epsilon
     prefix: str = "GUNet"                # "UNetInter": same variable layout, no modulation, guide concatenated to the
                                          # images at the input (/root/reference/NetworksV2/UNetInter.py:89-92,118-146)
 
@@ -77,8 +78,13 @@ def unetinter_inputs(images: np.ndarray, sp_guide: np.ndarray) -> dict:
 def layer_specs(cfg: GUNetCfg):
     """Ordered conv-type layers of GUNet._build_network as dicts (kind, scope, cin, cout, level, and for convs:
     center / scale of the normaliser, mod (modulated block), mod_off (column in the context vector), sp_off)."""
-    if cfg.normalizer != "instance_norm":
-        raise NotImplementedError("GUNet oracle: instance_norm only")
+    if cfg.normalizer not in ("instance_norm", "batch_norm"):
+        raise ValueError("Not supported normalization function: " + cfg.normalizer)
+    bn = cfg.normalizer == "batch_norm"
+    # batch_norm (GUNet.py:301,321-325; UNetInter.py:107-111): the encoder arg scope gives its convs decay 0.99; GUNet's
+    # un-modulated encoder blocks override the params with {"scale": True, "is_training"} (slim default decay 0.999), as
+    # does every decoder conv (BaseNet._get_normalization, base.py:153-162)
+    enc_decay_all = cfg.prefix == "UNetInter"
     specs = []
     c, cin = cfg.init_channels, cfg.channel
     off = 0
@@ -91,7 +97,8 @@ def layer_specs(cfg: GUNetCfg):
             s = dict(kind="conv", scope=f"{cfg.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/Conv", cin=cin, cout=c, level=i,
                      role=f"enc{j}", mod=mod, center=(cfg.norm_with_center and not aa) if mod else True,
                      scale=(cfg.norm_with_scale and not aa) if mod else True, mod_off=None, sp_off=None,
-                     affine=f"{cfg.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/ChannelWiseAffine" if aa else None)
+                     affine=f"{cfg.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/ChannelWiseAffine" if aa else None,
+                     decay=0.99 if (mod or enc_decay_all) else 0.999)
             if mod and cfg.use_context:
                 s["mod_off"] = off
                 off += c
@@ -107,7 +114,7 @@ def layer_specs(cfg: GUNetCfg):
         for j in (1, 2):
             specs.append(dict(kind="conv", scope=f"{cfg.prefix}/Decode/up_conv{i + 1}/up_conv{i + 1}_{j}",
                               cin=c + cin // 2 if j == 1 else c, cout=c, level=i, role=f"dec{j}", mod=False, center=True,
-                              scale=True, mod_off=None, sp_off=None, affine=None))
+                              scale=True, mod_off=None, sp_off=None, affine=None, decay=0.999))
         cin = c
     specs.append(dict(kind="logits", scope=f"{cfg.prefix}/AdjustChannels", cin=cin, cout=cfg.num_classes, level=0))
     return specs
@@ -123,17 +130,25 @@ def fc_specs(cfg: GUNetCfg):
     return out
 
 
+def norm_scope(cfg: GUNetCfg) -> str:
+    return "BatchNorm" if cfg.normalizer == "batch_norm" else "InstanceNorm"
+
+
 def init_params(cfg: GUNetCfg, seed: int = 0, dtype=np.float32) -> dict:
     rng = np.random.default_rng(seed)
     p = {}
+    ns = norm_scope(cfg)
     for s in layer_specs(cfg):
         sc, cin, cout = s["scope"], s["cin"], s["cout"]
         if s["kind"] == "conv":
             p[f"{sc}/weights"] = O.xavier_uniform(rng, (3, 3, cin, cout), 9 * cin, 9 * cout, dtype)
             if s["scale"]:
-                p[f"{sc}/InstanceNorm/gamma"] = np.ones(cout, dtype)
+                p[f"{sc}/{ns}/gamma"] = np.ones(cout, dtype)
             if s["center"]:
-                p[f"{sc}/InstanceNorm/beta"] = np.zeros(cout, dtype)
+                p[f"{sc}/{ns}/beta"] = np.zeros(cout, dtype)
+            if cfg.normalizer == "batch_norm":
+                p[f"{sc}/{ns}/moving_mean"] = np.zeros(cout, dtype)
+                p[f"{sc}/{ns}/moving_variance"] = np.ones(cout, dtype)
             if s["affine"]:
                 p[f"{s['affine']}/gamma"] = np.ones(cout, dtype)
                 p[f"{s['affine']}/beta"] = np.zeros(cout, dtype)
@@ -163,7 +178,7 @@ def regularized_names(cfg: GUNetCfg, params: dict):
     conv weights, and their biases unless --bias_decay. The context MLP (fully_connected) is not regularised."""
     out = []
     for k in params:
-        if "/context/" in k or "InstanceNorm" in k:
+        if "/context/" in k or "InstanceNorm" in k or "BatchNorm" in k:
             continue
         if k.endswith("/weights") or (k.endswith("/biases") and not cfg.bias_decay):
             out.append(k)
@@ -189,6 +204,7 @@ class Tape:
     ctx_params: np.ndarray = None
     guides: list = field(default_factory=list)
     errs: dict = field(default_factory=dict)
+    new_moving: dict = field(default_factory=dict)
 
 
 def dropout_offset(step: int, layer: int) -> int:
@@ -249,9 +265,18 @@ def forward(params: dict, inputs: dict, cfg: GUNetCfg, is_training: bool, rnd=_i
         if stored is not None:
             tape.errs[f"{sc}:y"] = rel(stored[sc]["y"], y)
             y = stored[sc]["y"].astype(dt)
-        gamma = params[f"{sc}/InstanceNorm/gamma"].astype(dt) if s["scale"] else np.ones(cout, dt)
-        beta = params[f"{sc}/InstanceNorm/beta"].astype(dt) if s["center"] else np.zeros(cout, dt)
-        z, cache = O.instance_norm(y, gamma, beta, cfg.in_eps)
+        ns = norm_scope(cfg)
+        gamma = params[f"{sc}/{ns}/gamma"].astype(dt) if s["scale"] else np.ones(cout, dt)
+        beta = params[f"{sc}/{ns}/beta"].astype(dt) if s["center"] else np.zeros(cout, dt)
+        if cfg.normalizer == "batch_norm":
+            mm, mv = params[f"{sc}/{ns}/moving_mean"].astype(dt), params[f"{sc}/{ns}/moving_variance"].astype(dt)
+            if is_training:
+                z, cache, nmm, nmv = O.batch_norm_train(y, gamma, beta, mm, mv, cfg.bn_eps, s["decay"])
+                tape.new_moving[f"{sc}/{ns}/moving_mean"], tape.new_moving[f"{sc}/{ns}/moving_variance"] = nmm, nmv
+            else:
+                z, cache = O.batch_norm_infer(y, gamma, beta, mm, mv, cfg.bn_eps), None
+        else:
+            z, cache = O.instance_norm(y, gamma, beta, cfg.in_eps)
         gm = sp = None
         zn = z
         if s["mod_off"] is not None:
@@ -362,12 +387,16 @@ def backward(tape: Tape, dlogits: np.ndarray, cfg: GUNetCfg, rnd=_identity) -> d
             if L["gm"] is not None:
                 dctx[:, s["mod_off"]:s["mod_off"] + cout] = (dz * L["zn"]).sum(axis=(1, 2))
                 dz = dz * L["gm"][:, None, None, :]
-            dy, dg, db = O.instance_norm_grad(dz, L["cache"])
+            ns = norm_scope(cfg)
+            if cfg.normalizer == "batch_norm":
+                dy, dg, db = O.batch_norm_grad(dz, L["cache"])
+            else:
+                dy, dg, db = O.instance_norm_grad(dz, L["cache"])
             dy = rnd(dy).astype(dt)
             if s["scale"]:
-                grads[f"{sc}/InstanceNorm/gamma"] = dg
+                grads[f"{sc}/{ns}/gamma"] = dg
             if s["center"]:
-                grads[f"{sc}/InstanceNorm/beta"] = db
+                grads[f"{sc}/{ns}/beta"] = db
             grads[f"{sc}/weights"] = O.conv2d_backprop_filter(L["x"], L["w"].shape, dy)
             d = None if L["first"] else rnd(O.conv2d_backprop_input(L["x"].shape, L["w"], dy)).astype(dt)
         elif k == "concat":
@@ -427,4 +456,6 @@ def train_step(params: dict, slots: dict, step: int, inputs: dict, labels, cfg: 
         w, m, v = O.adam_step(w, g.astype(np.float64), m, v, step, lr)
         slots[k] = (m, v)
         params[k] = w.astype(params[k].dtype)
+    for k, v in tape.new_moving.items():          # UPDATE_OPS control dependency of the train op (core/solver.py:236-239)
+        params[k] = v.astype(params[k].dtype)
     return total, tape, grads

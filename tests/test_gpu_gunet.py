@@ -89,6 +89,11 @@ def _make(n, hw, **kw):
     (2, 64, dict(use_context=True, use_spatial=False, after_affine=True, loss_type="xentropy")),
     (2, 64, dict(use_context=False, use_spatial=True, guide_channel=2, after_affine=True, mod_layers=(0, 1),
                  loss_type="xentropy")),
+    # --normalizer batch_norm (GUNet.py:301,321-325): batch statistics with decay 0.99 on the modulated blocks,
+    # per-sample gamma_mod / guide on top of them
+    (3, 64, dict(use_context=True, use_spatial=True, guide_channel=1, norm_with_center=True, norm_with_scale=True,
+                 normalizer="batch_norm", loss_type="xentropy+dice")),
+    (2, 64, dict(use_context=True, use_spatial=False, normalizer="batch_norm", loss_type="xentropy")),
 ])
 def test_gunet_train_step_parity(ctx, n, hw, kw):
     ecfg, rcfg, inputs, labels = _make(n, hw, **kw)
@@ -119,6 +124,7 @@ def test_gunet_train_step_parity(ctx, n, hw, kw):
     eng.optimizer_step(1e-3)
     ctx.check_device()
     data_loss, reg_loss = eng.read_loss()
+    new_w = eng.get_weights()
     eng.close()
 
     rin = dict(inputs, images=round_bf16(inputs["images"]))
@@ -134,8 +140,10 @@ def test_gunet_train_step_parity(ctx, n, hw, kw):
     assert abs(data_loss - loss_o) < 1e-4 * abs(loss_o)
     assert abs(reg_loss - G.regularization_loss(params, rcfg)) < 1e-6
     assert rel(dlogits, dl) < 1e-5
+    for name, v in tft.new_moving.items():     # batch norm: moving statistics (decay 0.99 / 0.999) from the stored outputs
+        assert rel(new_w[name], v) < 1e-4, name
     g_ref = G.backward(tft, dl, rcfg, rnd=round_bf16)
-    assert set(g_ref) == set(grads)
+    assert set(g_ref) == {k_ for k_ in grads}
     # The context MLP's parameter gradients are a chain: per-layer d(gamma_mod) slices (products of the bf16 trunk
     # backward, gated at 1e-2 here like every trunk gradient) -> fp32 FC backward (gated at 1e-4 on the DEVICE's own
     # d(gamma_mod), i.e. op by op on identical inputs). The end-to-end figure of the FC gradients -- sums over all

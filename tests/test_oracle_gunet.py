@@ -41,7 +41,7 @@ def _inputs(cfg, n, rng):
 
 def _torch_gunet(params, inputs, labels, cfg, mults):
     """Independent implementation: NCHW torch functional ops + autograd."""
-    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in params.items()}
+    P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in params.items() if "/moving_" not in k}
     t = lambda a: torch.tensor(a, dtype=torch.float64)
     x = t(inputs["images"]).permute(0, 3, 1, 2)
     ctxp = None
@@ -65,8 +65,12 @@ def _torch_gunet(params, inputs, labels, cfg, mults):
     def conv(x, s):
         sc, co = s["scope"], s["cout"]
         y = F.conv2d(x, P[f"{sc}/weights"].permute(3, 2, 0, 1), padding=1)
-        y = F.instance_norm(y, weight=P[f"{sc}/InstanceNorm/gamma"] if s["scale"] else None,
-                            bias=P[f"{sc}/InstanceNorm/beta"] if s["center"] else None, eps=cfg.in_eps)
+        if cfg.normalizer == "batch_norm":
+            y = F.batch_norm(y, None, None, weight=P[f"{sc}/BatchNorm/gamma"] if s["scale"] else None,
+                             bias=P[f"{sc}/BatchNorm/beta"] if s["center"] else None, training=True, eps=cfg.bn_eps)
+        else:
+            y = F.instance_norm(y, weight=P[f"{sc}/InstanceNorm/gamma"] if s["scale"] else None,
+                                bias=P[f"{sc}/InstanceNorm/beta"] if s["center"] else None, eps=cfg.in_eps)
         if s["mod_off"] is not None:
             y = y * ctxp[:, s["mod_off"]:s["mod_off"] + co][:, :, None, None]
         if s["sp_off"] is not None:
@@ -119,6 +123,10 @@ def _torch_gunet(params, inputs, labels, cfg, mults):
     dict(use_context=True, use_spatial=True, guide_channel=1, norm_with_center=True, norm_with_scale=True,
          after_affine=True, loss_type="xentropy+dice"),
     dict(use_context=True, use_spatial=False, after_affine=True, side_dropout=0.0, mod_layers=(0, 1), loss_type="xentropy"),
+    # --normalizer batch_norm: batch statistics shared by all samples, per-sample modulation on top
+    dict(use_context=True, use_spatial=True, guide_channel=1, norm_with_center=True, norm_with_scale=True,
+         normalizer="batch_norm", loss_type="xentropy+dice"),
+    dict(use_context=True, use_spatial=False, normalizer="batch_norm", side_dropout=0.0, loss_type="xentropy"),
 ])
 def test_oracle_matches_torch_autograd(kw):
     cfg = G.GUNetCfg(height=16, width=16, init_channels=4, num_down_samples=2, mod_layers=kw.pop("mod_layers", (1, 2)),
@@ -138,9 +146,17 @@ def test_oracle_matches_torch_autograd(kw):
     t_logits, t_loss, t_grads = _torch_gunet(params, inputs, labels, cfg, mults)
     assert np.allclose(tape.logits, t_logits, rtol=1e-9, atol=1e-10)
     assert abs(loss - t_loss) < 1e-10
-    assert set(grads) == set(params)
+    assert set(grads) == {k for k in params if "/moving_" not in k}
     for k, g in grads.items():
         assert np.allclose(g, t_grads[k], rtol=1e-7, atol=1e-10), k
+    if cfg.normalizer == "batch_norm":      # moving statistics: decay 0.99 on the modulated blocks, 0.999 elsewhere
+        k0 = "GUNet/Encode/down_conv2/mod_conv1/Conv/BatchNorm/moving_mean"
+        k1 = "GUNet/Decode/up_conv1/up_conv1_1/BatchNorm/moving_variance"
+        y0 = next(L for L in tape.layers if L.get("spec", {}).get("scope", "").endswith("down_conv2/mod_conv1/Conv"))
+        mean_y = O.conv2d(y0["x"], y0["w"]).mean(axis=(0, 1, 2))
+        assert np.allclose(tape.new_moving[k0], 0.01 * mean_y, rtol=1e-9, atol=1e-12)       # decay 0.99, moving mean was 0
+        assert tape.new_moving[k1].min() > 0.999 - 1e-9      # moving variance starts at 1: 0.999 + 0.001 * var
+        assert set(tape.new_moving) == {k for k in params if "/moving_" in k}
 
 
 def test_unetinter_oracle_matches_torch_autograd():
