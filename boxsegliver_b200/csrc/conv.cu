@@ -89,12 +89,18 @@ int nhwc_map(bsl_ctx* ctx, const void* base, int c, int w, int h, int n, int ld,
 }
 
 // [n, 2h, 2w, c] seen as (c, b:2, w, a:2, n*h): taps of a k2 s2 transposed conv become coordinates.
+// c == 32 (UNet3D's 30-channel level stored with 32 lanes): one box takes both column parities b, so that a shared-memory
+// row still holds 64 values -- (b, c) pairs -- and a 64-wide reduction / row block is one row parity `a` of the filter.
 int upsampled_map(bsl_ctx* ctx, const void* base, int c, int w, int h, int n, int ld, int tw, int th,
                   CUtensorMap* out) {
   uint64_t dims[5] = {(uint64_t)c, 2, (uint64_t)w, 2, (uint64_t)n * h};
   uint64_t str[5] = {2, (uint64_t)ld * 2, (uint64_t)2 * ld * 2, (uint64_t)2 * w * ld * 2,
                      (uint64_t)4 * w * ld * 2};
   uint32_t bx[5] = {64, 1, (uint32_t)tw, 1, (uint32_t)th};
+  if (c == 32) {
+    bx[0] = 32;
+    bx[1] = 2;
+  }
   return bsl_get_tmap(ctx, base, 5, dims, str, bx, out);
 }
 
@@ -846,9 +852,11 @@ static int check_convT(bsl_ctx* ctx, const bsl_convT2d_desc* d) {
   if (!ctx) return BSL_EINVAL;
   if (!d) return bsl_fail(ctx, BSL_EINVAL, "convT2d: null descriptor");
   if (d->n <= 0 || d->h <= 0 || d->w <= 0) return bsl_fail(ctx, BSL_EINVAL, "convT2d: non-positive size");
-  if (d->cin % 64 || d->cout % 64)
-    return bsl_fail(ctx, BSL_EUNSUPPORTED, "convT2d needs cin,cout multiples of 64 (got %d,%d)", d->cin,
-                    d->cout);
+  // cout == 32: the half-block form (see upsampled_map), halo-tile shapes only
+  const bool half = d->cout == 32 && halo_eligible(d->w, d->h) && halo_eligible(d->w, d->n * d->h);
+  if (d->cin % 64 || (d->cout % 64 && !half))
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "convT2d needs cin,cout multiples of 64, or cout = 32 on 8x16-tileable "
+                    "shapes (got %d,%d at %dx%d)", d->cin, d->cout, d->h, d->w);
   if (d->x_ld < d->cin || d->y_ld < d->cout || d->x_ld % 8 || d->y_ld % 8)
     return bsl_fail(ctx, BSL_EINVAL, "convT2d: bad channel strides");
   return BSL_OK;
@@ -959,8 +967,8 @@ int bsl_convT2d_bwd_data(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* dy
     a.halo = 0;
     a.kd = 2;
     a.depth = 1;
-    a.cblocks = 2 * d->cout / 64;
-    a.up_cpb = d->cout / 64;
+    a.cblocks = std::max(1, 2 * d->cout / 64);   // cout = 32: one 64-wide block per row parity holds both column parities
+    a.up_cpb = std::max(1, d->cout / 64);
     a.out = dx;
     a.ostride_x = d->x_ld;
     a.ostride_y = (long long)d->w * d->x_ld;
@@ -1047,6 +1055,17 @@ int bsl_convT2d_bwd_filter(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* 
       o[3] = 0;
     }
   a.cblocks = d->cout / 64;
+  if (d->cout == 32) {   // half-block form: a 64-row block = (b, co) of one row parity a
+    a.ntaps = 2;
+    a.cblocks = 1;
+    for (int ta_ = 0; ta_ < 2; ++ta_) {
+      signed char* o = a.tapoff[ta_];
+      o[0] = 0;
+      o[1] = 0;
+      o[2] = (signed char)ta_;
+      o[3] = 0;
+    }
+  }
   a.m_total = 4 * d->cout;
   a.n_total = d->cin;
   a.k_tiles_total = p.k_tiles;

@@ -51,6 +51,26 @@ __global__ void scale_f32_kernel(float* __restrict__ x, size_t n, float a) {
     x[i] *= a;
 }
 
+// Filter re-layout by index table (UNet3D pixel-pair packing, unet3d_engine.py): dst[i] = bf16(src[idx[i]]) or 0.
+__global__ void gather_f32_bf16_kernel(const float* __restrict__ src, const int* __restrict__ idx, size_t n,
+                                       __nv_bfloat16* __restrict__ dst) {
+  bsl::pdl_enter();
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = idx[i];
+    dst[i] = __float2bfloat16_rn(j >= 0 ? src[j] : 0.f);
+  }
+}
+
+// ... and its adjoint for the gradient: dst[j] = src[idx2[j][0]] + src[idx2[j][1]] (negative index: no term).
+__global__ void gather_add2_f32_kernel(const float* __restrict__ src, const int* __restrict__ idx2, size_t n,
+                                       float* __restrict__ dst) {
+  bsl::pdl_enter();
+  for (size_t j = blockIdx.x * (size_t)blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x) {
+    const int a = idx2[2 * j], b = idx2[2 * j + 1];
+    dst[j] = (a >= 0 ? src[a] : 0.f) + (b >= 0 ? src[b] : 0.f);
+  }
+}
+
 struct SumF {
   static constexpr int K = 1, NIN = 1, UNROLL = 8;
   struct State {};
@@ -234,6 +254,24 @@ int bsl_scale_f32(bsl_ctx* ctx, float* x, size_t n, float a, void* stream) {
   if (n == 0) return BSL_OK;
   bsl_launch(scale_f32_kernel, dim3(grid_for((long long)n, kThreads, 8 * ctx->sm_count)), dim3(kThreads), 0, as_stream(stream), x, n, a);
   BSL_LAUNCH_CHECK(ctx, "scale_f32_kernel");
+  return BSL_OK;
+}
+
+int bsl_gather_f32_bf16(bsl_ctx* ctx, const float* src, const int* idx, size_t n, void* dst_bf16, void* stream) {
+  if (!ctx || !src || !idx || !dst_bf16) return BSL_EINVAL;
+  if (n == 0) return BSL_OK;
+  bsl_launch(gather_f32_bf16_kernel, dim3(grid_for((long long)n, kThreads, 8 * ctx->sm_count)), dim3(kThreads), 0,
+             as_stream(stream), src, idx, n, reinterpret_cast<__nv_bfloat16*>(dst_bf16));
+  BSL_LAUNCH_CHECK(ctx, "gather_f32_bf16_kernel");
+  return BSL_OK;
+}
+
+int bsl_gather_add2_f32(bsl_ctx* ctx, const float* src, const int* idx2, size_t n, float* dst, void* stream) {
+  if (!ctx || !src || !idx2 || !dst) return BSL_EINVAL;
+  if (n == 0) return BSL_OK;
+  bsl_launch(gather_add2_f32_kernel, dim3(grid_for((long long)n, kThreads, 8 * ctx->sm_count)), dim3(kThreads), 0,
+             as_stream(stream), src, idx2, n, dst);
+  BSL_LAUNCH_CHECK(ctx, "gather_add2_f32_kernel");
   return BSL_OK;
 }
 

@@ -13,7 +13,17 @@ concat [encoder, up], 1x1x1 logits, weighted cross-entropy. What differs from th
   * parameter arenas hold the PADDED layouts; set_weights / get_weights / get_grads pack and unpack TF-shaped
     variables ([kd,kh,kw,Cin,Cout], concat inputs split as [encoder | up]);
   * there is no pooling: an encoder block's output feeds the skip and the next strided conv, so its gradient is an
-    explicit add (bsl_add_bf16) of the two branches.
+    explicit add (bsl_add_bf16) of the two branches;
+  * PIXEL-PAIR PACKING of the full-resolution level (init_channels <= 32, W % 16 == 0, H % 32 == 0; BSL_UNET3D_PAIR=0
+    turns it off): its tensors are stored with 32 channel lanes, not 64, and its (1,3,3) convolutions run on the SAME
+    64-channel tcgen05 kernels over PAIRS of horizontally adjacent voxels -- the NDHWC tensor [n,d,h,w,32] reinterpreted
+    as [n,d,h,w/2,64] ("super" voxels). A 3-tap row of the real filter becomes a 3-tap row of a 2*cin x 64 super filter
+    (tap S of the super filter, input half hi, output half ho holds the real tap 2S + hi - ho + 1), a fixed
+    re-arrangement built from the slim variable by an index table (bsl_gather_f32_bf16) and undone for the filter
+    gradient (bsl_gather_add2_f32). Half the MMAs and half the HBM bytes of the 64-lane storage on the layers that
+    hold most of the voxels; the normalisation / ReLU / add passes see the real 32-lane view. The strided conv that
+    leaves the level reads super voxels with horizontal stride 1 (pixel stride 2), the transposed conv that enters it
+    uses the 32-channel half-block form of bsl_convT2d_* (both column parities in one 64-wide block).
 """
 from __future__ import annotations
 
@@ -107,6 +117,7 @@ class Layer3:
     coutp: int = 0
     cin_map: np.ndarray = None   # real input channel -> stored input channel
     fork: bool = False        # encoder conv2: output also feeds the skip connection
+    pair: str = ""            # pixel-pair packing: "conv" (stride-1 super conv), "strided" (level 0 -> 1), "stem", or ""
     x: View3 = None
     y: View3 = None
     a: View3 = None
@@ -169,6 +180,8 @@ class UNet3DEngine:
         self.step_count = 0
         self._bufs = []
         self.stream = ctx.stream
+        self._pair = (cfg.init_channels <= 32 and cfg.width % 16 == 0 and cfg.height % 32 == 0
+                      and 9 * cfg.in_channels <= 32 and os.environ.get("BSL_UNET3D_PAIR", "0") != "0")
         # filter gradients on a side stream, as in engine.UNetEngine.loss_backward
         self._overlap_wgrad = cfg.training and os.environ.get("BSL_WGRAD_OVERLAP", "1") != "0"
         self._fuse_inst_stats = os.environ.get("BSL_FUSE_INST_STATS", "1") != "0"
@@ -193,30 +206,47 @@ class UNet3DEngine:
         dhw = (cfg.depth, cfg.height, cfg.width)
         enc = {}
         first = True
+        pair = self._pair
+
+        def cpb(ch, block):
+            """stored channel lanes of a tensor produced in `block` (32 on the pixel-pair packed level, else 64-padded)"""
+            return _align(ch, 32) if pair and block in ("conv_e0", "conv_d0") else _cp(ch)
+
+        prev_block = None
         for block, layer, k, s in _model_config(cfg.num_pool_layers):
             scope = f"UNet3D/{block}/{layer}"
             if layer == "up":
                 e = enc[block.replace("d", "e")]
                 c = e["c"]
-                L = Layer3("convT", scope, block, layer, cin, c, k, s, dhw, cinp=_cp(cin), coutp=_cp(c))
+                L = Layer3("convT", scope, block, layer, cin, c, k, s, dhw, cinp=_cp(cin), coutp=cpb(c, block))
                 L.odhw = tuple(dhw[i] * s[i] for i in range(3))
                 assert L.odhw == e["dhw"]
                 dhw = L.odhw
                 layers.append(L)
                 cin = 2 * c
                 continue
-            L = Layer3("stem" if first else "conv", scope, block, layer, cin, c, k, s, dhw, coutp=_cp(c))
+            L = Layer3("stem" if first else "conv", scope, block, layer, cin, c, k, s, dhw, coutp=cpb(c, block))
             L.odhw = tuple(-(-dhw[i] // s[i]) for i in range(3))
+            lvl0 = pair and block in ("conv_e0", "conv_d0")
             if first:
-                L.cinp = 64
+                L.cinp = 32 if lvl0 else 64          # im2col pitch
+                L.pair = "stem" if lvl0 else ""
             elif block.startswith("conv_d") and layer == "conv1":
-                L.cinp = 2 * _cp(c)
-                L.cin_map = np.r_[0:c, _cp(c):_cp(c) + c]
+                cp_ = cpb(c, block)
+                L.cinp = 2 * cp_
+                L.cin_map = np.r_[0:c, cp_:cp_ + c]
+                L.pair = "conv" if lvl0 else ""
+            elif pair and block == "conv_e1" and layer == "conv1":
+                # reads the encoder half of the level-0 concat buffer: whole 64-lane voxels (the `up` half meets zero rows)
+                L.cinp = 2 * cpb(cin, "conv_e0")
+                L.pair = "strided"
             else:
-                L.cinp = _cp(cin)
+                L.cinp = cpb(cin, prev_block)
+                L.pair = "conv" if lvl0 else ""
             if L.cin_map is None:
                 L.cin_map = np.arange(cin)
             first = False
+            prev_block = block
             dhw = L.odhw
             layers.append(L)
             cin = c
@@ -226,7 +256,7 @@ class UNet3DEngine:
                     enc[block] = dict(c=c, dhw=dhw)
                 c = min(c * 2, cfg.max_channels)
         L = Layer3("logits", "UNet3D/logits", "logits", "logits", cin, cfg.num_classes, (1, 1, 1), (1, 1, 1), dhw,
-                   cinp=_cp(cin), coutp=cfg.num_classes)
+                   cinp=cpb(cin, "conv_d0"), coutp=cfg.num_classes)
         L.odhw = dhw
         L.cin_map = np.arange(cin)
         layers.append(L)
@@ -237,7 +267,7 @@ class UNet3DEngine:
         plist = []
         for L in self.layers:
             if L.kind in ("stem", "conv"):
-                ps = (64, L.coutp) if L.kind == "stem" else L.k + (L.cinp, L.coutp)
+                ps = (L.cinp, L.coutp) if L.kind == "stem" else L.k + (L.cinp, L.coutp)
                 plist.append(Param3(f"{L.scope}/weights", L.k + (L.cin, L.cout), ps, L))
                 plist.append(Param3(f"{L.scope}/InstanceNorm/gamma", (L.cout,), (L.coutp,), L, region="B"))
                 plist.append(Param3(f"{L.scope}/InstanceNorm/beta", (L.cout,), (L.coutp,), L, region="B"))
@@ -264,13 +294,96 @@ class UNet3DEngine:
             self.M = self._alloc(self.n_train * F32).zero()
             self.V = self._alloc(self.n_train * F32).zero() if cfg.optimizer in ("adam", "adamw") else None
         self.sumsq = self._alloc(16)
+        self._plan_super_filters()
+
+    # ------------------------------------------------------------------ pixel-pair packing: super filters
+    @staticmethod
+    def _super_index(L: Layer3):
+        """idx[i] = flat index into the layer's stored (master) filter that super-filter element i copies, or -1.
+        Shapes: master (3, 3, cinp, coutp) [depth extent 1 dropped] / (cinp, coutp) for the stem;
+        super (3, 3, 2*cinp, 64) / (64, 64)."""
+        cinp, coutp = L.cinp, L.coutp
+        if L.pair == "stem":
+            idx = np.full((2, cinp, 2, coutp), -1, np.int64)
+            m = np.arange(cinp * coutp).reshape(cinp, coutp)
+            idx[0, :, 0, :] = m
+            idx[1, :, 1, :] = m
+            return idx.reshape(2 * cinp, 2 * coutp)
+        m = np.arange(3 * 3 * cinp * coutp).reshape(3, 3, cinp, coutp)
+        if L.pair == "strided":     # output voxel X reads input voxels 2X + s: super voxel X + (s >> 1), half s & 1
+            idx = np.full((3, 3, 2, cinp, coutp), -1, np.int64)
+            for s_ in range(3):
+                idx[:, 1 + (s_ >> 1), s_ & 1] = m[:, s_]
+            return idx.reshape(3, 3, 2 * cinp, coutp)
+        idx = np.full((3, 3, 2, cinp, 2, coutp), -1, np.int64)
+        for sx in (-1, 0, 1):
+            for hi in (0, 1):
+                for ho in (0, 1):
+                    s_ = 2 * sx + hi - ho + 1      # input voxel 2(X + sx) + hi, output voxel 2X + ho
+                    if 0 <= s_ <= 2:
+                        idx[:, sx + 1, hi, :, ho, :] = m[:, s_]
+        return idx.reshape(3, 3, 2 * cinp, 2 * coutp)
+
+    @staticmethod
+    def _fold_table(idx: np.ndarray, msize: int) -> np.ndarray:
+        """Adjoint of the gather: fold[j] = the (at most two) super elements that copy stored element j, -1 = none."""
+        idx = np.asarray(idx).ravel()
+        order = np.argsort(idx, kind="stable")
+        srt = idx[order]
+        first = np.searchsorted(srt, np.arange(msize), side="left")
+        last = np.searchsorted(srt, np.arange(msize), side="right")
+        cnt = last - first
+        assert cnt.max() <= 2, "a filter element is copied at most twice"
+        fold = np.full((msize, 2), -1, np.int32)
+        has1, has2 = cnt >= 1, cnt >= 2
+        fold[has1, 0] = order[first[has1]]
+        fold[has2, 1] = order[first[has2] + 1]
+        return fold
+
+    def _plan_super_filters(self):
+        self.sup = {}
+        pairs = [L for L in self.layers if L.pair]
+        if not pairs:
+            return
+        off, gmax = 0, 0
+        for L in pairs:
+            idx = self._super_index(L).ravel()
+            msize = self.params[f"{L.scope}/weights"].size
+            fold = self._fold_table(idx, msize)
+            self.sup[L.scope] = dict(off=off, size=idx.size, msize=msize,
+                                     idx=self._upload_i32(idx.astype(np.int32)), fold=self._upload_i32(fold))
+            off += _align(idx.size)
+            gmax = max(gmax, idx.size)
+        self.Wsup = self._alloc(off * BF16)
+        self.Gsup = self._alloc(gmax * F32) if self.cfg.training else None
+
+    def _upload_i32(self, a: np.ndarray) -> DeviceBuffer:
+        b = self._alloc(a.nbytes)
+        b.upload(np.ascontiguousarray(a, np.int32))
+        return b
+
+    def _wsup(self, L: Layer3):
+        return C.c_void_p(self.Wsup.ptr + self.sup[L.scope]["off"] * BF16)
+
+    def _pack_super_filters(self):
+        """master fp32 filters -> bf16 super filters (start of every forward: the optimizer has just moved the masters)"""
+        for L in self.layers:
+            if L.pair:
+                t = self.sup[L.scope]
+                self.ctx.call("bsl_gather_f32_bf16", self._pp(self.W, f"{L.scope}/weights"), t["idx"].p,
+                              C.c_size_t(t["size"]), self._wsup(L), self.stream)
+
+    def _fold_super_grad(self, L: Layer3, stream):
+        t = self.sup[L.scope]
+        self.ctx.call("bsl_gather_add2_f32", self.Gsup.p, t["fold"].p, C.c_size_t(t["msize"]),
+                      self._pp(self.G, f"{L.scope}/weights"), stream)
 
     def _pp(self, arena, name, esize=F32):
         return C.c_void_p(arena.ptr + self.params[name].offset * esize)
 
     def _plan_activations(self):
         cfg, n = self.cfg, self.cfg.batch
-        cat, max_act, small = {}, 0, 0
+        cat, max_act, max_grad, small = {}, 0, 0, 0
         prev = None
         for L in self.layers:
             vox = int(np.prod(L.odhw))
@@ -288,7 +401,10 @@ class UNet3DEngine:
                 L.norm_off = small
                 small += 10 * _align(n * L.coutp, 16)
                 max_act = max(max_act, vox * L.coutp)
+                if L.kind == "conv" and not is_dec1:      # its dgrad writes in-voxels x cinp lanes into a ping-pong buffer
+                    max_grad = max(max_grad, int(np.prod(L.dhw)) * L.cinp)
             elif L.kind == "convT":
+                max_grad = max(max_grad, int(np.prod(L.dhw)) * L.cinp)
                 L.x = prev
                 cb = cat[L.block.replace("d", "e")]
                 L.a = cb.slice(L.coutp, L.coutp)
@@ -300,7 +416,7 @@ class UNet3DEngine:
         d, h, w = cfg.depth, cfg.height, cfg.width
         nvox = n * d * h * w
         self.images = self._alloc(nvox * cfg.in_channels * F32)
-        self.stem_col = self._alloc(nvox * 64 * BF16)
+        self.stem_col = self._alloc(nvox * self.layers[0].cinp * BF16)
         self.labels = self._alloc(nvox * 4)
         k = cfg.num_classes
         self.logits = self._alloc(nvox * k * F32)
@@ -316,17 +432,20 @@ class UNet3DEngine:
         self.loss_ws = self._alloc(self.loss_ws_bytes)
         if cfg.training:
             self.dlogits = self._alloc(nvox * k * F32)
-            self.g1 = self._alloc(n * max_act * BF16)
-            self.g2 = self._alloc(n * max_act * BF16)
+            max_grad = max(max_grad, max_act, int(np.prod(self.layers[-1].dhw)) * self.layers[-1].cinp)
+            self.g1 = self._alloc(n * max_grad * BF16)
+            self.g2 = self._alloc(n * max_grad * BF16)
             self.dyb = [self._alloc(n * max_act * BF16), self._alloc(n * max_act * BF16)]
             self.dcat = {b: View3(self._alloc(v.voxels * v.c * BF16), n, v.dhw, v.c) for b, v in cat.items()}
             ws = 0
             for L in self.layers:
                 if L.kind == "stem":
-                    dd = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], 64, L.coutp, 1, 1, 64, L.coutp)
+                    dd = self._desc_stem(L)
                     ws = max(ws, self.ctx.lib.bsl_conv2d_wgrad_workspace(self.ctx.h, C.byref(dd)))
                 elif L.kind == "conv":
-                    if self._is2d(L):
+                    if L.pair == "strided":
+                        ws = max(ws, self.ctx.lib.bsl_conv3d_wgrad_workspace(self.ctx.h, C.byref(self._desc3s(L))))
+                    elif self._is2d(L):
                         ws = max(ws, self.ctx.lib.bsl_conv2d_wgrad_workspace(self.ctx.h, C.byref(self._desc2(L))))
                     else:
                         ws = max(ws, self.ctx.lib.bsl_conv3d_wgrad_workspace(self.ctx.h, C.byref(self._desc3(L))))
@@ -345,7 +464,24 @@ class UNet3DEngine:
 
     def _desc2(self, L: Layer3):
         n = self.cfg.batch
+        if L.pair == "conv":   # super voxels: [.., w, ld] seen as [.., w/2, 2*ld]; 2*coutp = 64 output lanes
+            return _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2] // 2, 2 * L.cinp, 2 * L.coutp, L.k[1], L.k[2],
+                                   2 * L.x.ld, 2 * L.y.ld)
         return _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.coutp, L.k[1], L.k[2], L.x.ld, L.y.ld)
+
+    def _desc_stem(self, L: Layer3):
+        """The stem as a 1x1 convolution over its im2col matrix (pitch cinp; pixel pairs when packed)."""
+        n = self.cfg.batch
+        if L.pair == "stem":
+            return _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2] // 2, 2 * L.cinp, 2 * L.coutp, 1, 1, 2 * L.cinp,
+                                   2 * L.y.ld)
+        return _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], 64, L.coutp, 1, 1, 64, L.y.ld)
+
+    def _desc3s(self, L: Layer3):
+        """The strided conv that leaves the pixel-pair packed level: super voxels along W (stride 1 there, taps S = -1
+        (all zero), 0, +1), the real strides along D and H."""
+        return _lib.Conv3dDesc(self.cfg.batch, L.dhw[0], L.dhw[1], L.dhw[2] // 2, 2 * L.cinp, L.coutp, L.k[0], L.k[1], 3,
+                               L.s[0], L.s[1], 1, 2 * L.x.ld, L.y.ld)
 
     def _desc3(self, L: Layer3):
         return _lib.Conv3dDesc(self.cfg.batch, L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.coutp, L.k[0], L.k[1], L.k[2],
@@ -505,21 +641,25 @@ class UNet3DEngine:
         ctx, s, cfg = self.ctx, self.stream, self.cfg
         call = ctx.call
         n = cfg.batch
+        self._pack_super_filters()
         for L in self.layers:
             ctx.tag = L.scope
             if L.kind in ("stem", "conv"):
-                wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
+                wbf = self._wsup(L) if L.pair else self._pp(self.Wbf, f"{L.scope}/weights", BF16)
                 nd, q = self._norm_desc(L), self._norm_ptrs(L)
                 # layers that run as 2-D convolutions over n*d images take their per-(volume, channel) statistics from
-                # the conv epilogue: a statistics group is the `depth` consecutive images of one volume
-                fuse = self._fuse_inst_stats
+                # the conv epilogue: a statistics group is the `depth` consecutive images of one volume. (Not the pixel-
+                # pair packed layers: their epilogue sees super channels, and the real 32-lane tensor is half the bytes.)
+                fuse = self._fuse_inst_stats and not L.pair
                 fn = "bsl_conv2d_fprop_group_stats" if fuse else "bsl_conv2d_fprop"
                 extra = (C.c_int(L.dhw[0]), q["sums"]) if fuse else ()
                 if L.kind == "stem":
                     d0 = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], L.cin, 64, 3, 3, L.cin, 64)
-                    call("bsl_stem_im2col", C.byref(d0), self.images.p, self.stem_col.p, s)
-                    d1 = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], 64, L.coutp, 1, 1, 64, L.y.ld)
-                    call(fn, C.byref(d1), self.stem_col.p, wbf, L.y.p, *extra, s)
+                    call("bsl_stem_im2col_ld", C.byref(d0), self.images.p, self.stem_col.p, C.c_int(L.cinp), s)
+                    call(fn, C.byref(self._desc_stem(L)), self.stem_col.p, wbf, L.y.p, *extra, s)
+                elif L.pair == "strided":
+                    fuse = False
+                    call("bsl_conv3d_fprop", C.byref(self._desc3s(L)), L.x.p, wbf, L.y.p, s)
                 elif self._is2d(L):
                     call(fn, C.byref(self._desc2(L)), L.x.p, wbf, L.y.p, *extra, s)
                 else:
@@ -557,6 +697,7 @@ class UNet3DEngine:
         call("bsl_wxent_fwd_bwd", C.byref(ld), self.logits.p, self.labels.p, self.counts.p, self.loss_dev.p,
              self.dlogits.p, self.loss_ws.p, C.c_size_t(self.loss_ws_bytes), s)
         cur, alt = self.g1, self.g2
+        cur_ld = 0          # channel stride of the gradient currently in `cur`
         wsb = C.c_size_t(self.wgrad_ws_bytes)
         overlap = self._overlap_wgrad and ctx._prof is None
         ws = self.wg_stream if overlap else s
@@ -579,13 +720,16 @@ class UNet3DEngine:
                      self._pp(self.G, f"{L.scope}/biases"), ws)
                 dh2 = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.cout, 1, 1, L.cinp, L.cout)
                 call("bsl_conv2d_head_dgrad", C.byref(dh2), self.dlogits.p, self._pp(self.W, f"{L.scope}/weights"), cur.p, s)
+                cur_ld = L.cinp
             elif L.kind in ("stem", "conv"):
                 vox = n * int(np.prod(L.odhw))
                 if L.fork:   # AddN: gradient through the next block's strided conv + gradient through the skip
                     dc = self.dcat[L.block]
-                    call("bsl_add_bf16", C.c_longlong(vox), C.c_int(L.coutp), cur.p, C.c_int(L.coutp), dc.p,
+                    call("bsl_add_bf16", C.c_longlong(vox), C.c_int(L.coutp), cur.p, C.c_int(cur_ld), dc.p,
                          C.c_int(dc.ld), alt.p, C.c_int(L.coutp), s)
                     cur, alt = alt, cur
+                    cur_ld = L.coutp
+                assert cur_ld == L.coutp, (L.scope, cur_ld, L.coutp)
                 dyb = self.dyb[k]
                 if overlap and busy[k] is not None:
                     call("bsl_stream_wait_event", s, busy[k])
@@ -596,25 +740,35 @@ class UNet3DEngine:
                      self._pp(self.G, f"{L.scope}/InstanceNorm/gamma"), self._pp(self.G, f"{L.scope}/InstanceNorm/beta"), s)
                 call("bsl_norm_bwd_apply", C.byref(nd), L.y.p, cur.p, C.c_int(L.coutp), q["mean"], q["rstd"], q["scale"],
                      q["shift"], q["c1"], q["c2"], dyb.p, C.c_int(L.coutp), s)
-                gw = self._pp(self.G, f"{L.scope}/weights")
-                wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
+                # pixel-pair packed layers: the filter gradient of the SUPER filter goes to scratch and is folded back onto
+                # the stored filter (each stored element is the sum of the <= 2 super elements that copy it)
+                gw = self.Gsup.p if L.pair else self._pp(self.G, f"{L.scope}/weights")
+                wbf = self._wsup(L) if L.pair else self._pp(self.Wbf, f"{L.scope}/weights", BF16)
+                sup = 2 if L.pair in ("conv", "stem") else 1        # output lanes per super voxel / coutp
                 fork()
                 if L.kind == "stem":
-                    d1 = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], 64, L.coutp, 1, 1, 64, L.coutp)
+                    d1 = self._desc_stem(L)
+                    d1.y_ld = sup * L.coutp
                     call("bsl_conv2d_wgrad", C.byref(d1), self.stem_col.p, dyb.p, gw, self.wgrad_ws.p, wsb, ws)
                 else:
                     is_dec1 = L.block.startswith("conv_d") and L.layer == "conv1"
                     dx = self.dcat[L.block.replace("d", "e")] if is_dec1 else None
-                    two_d = self._is2d(L)
-                    d = self._desc2(L) if two_d else self._desc3(L)
-                    d.y_ld = L.coutp
+                    two_d = self._is2d(L) and L.pair != "strided"
+                    mk = (lambda: self._desc3s(L)) if L.pair == "strided" else ((lambda: self._desc2(L)) if two_d else
+                                                                                 (lambda: self._desc3(L)))
+                    d = mk()
+                    d.y_ld = sup * L.coutp
                     call("bsl_conv2d_wgrad" if two_d else "bsl_conv3d_wgrad", C.byref(d), L.x.p, dyb.p, gw,
                          self.wgrad_ws.p, wsb, ws)
-                    dd = self._desc2(L) if two_d else self._desc3(L)
-                    dd.y_ld = L.coutp
-                    dd.x_ld = dx.ld if dx is not None else L.cinp
+                    dd = mk()
+                    dd.y_ld = sup * L.coutp
+                    xin = 2 if L.pair else 1                        # input lanes per super voxel / stored lanes
+                    dd.x_ld = xin * (dx.ld if dx is not None else L.cinp)
                     call("bsl_conv2d_dgrad" if two_d else "bsl_conv3d_dgrad", C.byref(dd), dyb.p, wbf,
                          dx.p if dx is not None else cur.p, s)
+                    cur_ld = L.cinp
+                if L.pair:
+                    self._fold_super_grad(L, ws)
                 if overlap:
                     busy[k] = self._dy_events[k]
                     ctx.record(busy[k], ws)
@@ -637,6 +791,7 @@ class UNet3DEngine:
                 dd.y_ld = dup.ld
                 dd.x_ld = L.cinp
                 call("bsl_convT2d_bwd_data" if two_d else "bsl_convT3d_bwd_data", C.byref(dd), dup.p, wbf, cur.p, s)
+                cur_ld = L.cinp
         if overlap:
             ev = self._ev_ring[self._ev_ring_i]
             self._ev_ring_i = (self._ev_ring_i + 1) % len(self._ev_ring)

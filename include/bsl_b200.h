@@ -87,6 +87,12 @@ int bsl_cast_f32_to_bf16(bsl_ctx* ctx, const float* src, void* dst, size_t n, vo
 int bsl_cast_bf16_to_f32(bsl_ctx* ctx, const void* src, float* dst, size_t n, void* stream);
 /* x *= a in place (cross-replica MEAN of the batch-norm moving statistics after a SUM all-reduce). */
 int bsl_scale_f32(bsl_ctx* ctx, float* x, size_t n, float a, void* stream);
+/* Filter re-layout by index table and its adjoint (the UNet3D engine's pixel-pair packing: the 30-channel full-resolution
+ * layers of NetworksV2/UNet3D.py:31-91 run as 64-channel convolutions over PAIRS of horizontally adjacent voxels, whose
+ * "super" filter is a fixed re-arrangement of the slim variable): dst[i] = bf16(src[idx[i]]) (0 where idx[i] < 0), and
+ * dst[j] = src[idx2[2j]] + src[idx2[2j+1]] (terms with a negative index dropped) for the filter gradient. */
+int bsl_gather_f32_bf16(bsl_ctx* ctx, const float* src, const int* idx, size_t n, void* dst_bf16, void* stream);
+int bsl_gather_add2_f32(bsl_ctx* ctx, const float* src, const int* idx2, size_t n, float* dst, void* stream);
 
 /* ------------------------------------------------------------------ conv2d, stride 1, SAME
  * Replaces TF ops Conv2D / Conv2DBackpropInput / Conv2DBackpropFilter behind
