@@ -89,8 +89,10 @@ int nhwc_map(bsl_ctx* ctx, const void* base, int c, int w, int h, int n, int ld,
 }
 
 // [n, 2h, 2w, c] seen as (c, b:2, w, a:2, n*h): taps of a k2 s2 transposed conv become coordinates.
-// c == 32 (UNet3D's 30-channel level stored with 32 lanes): one box takes both column parities b, so that a shared-memory
-// row still holds 64 values -- (b, c) pairs -- and a 64-wide reduction / row block is one row parity `a` of the filter.
+// c == 32 (UNet3D's 30-channel level stored with 32 lanes; the gradient tensor must be DENSE, ld == 32): the two column
+// parities b of an input pixel are 64 contiguous values -- (b, c) pairs -- so the view is (64, 1, w, a:2, n*h) and a
+// 64-wide reduction / row block is one row parity `a` of the filter. (A 32-wide box over a strided tensor does not work:
+// with the 128-byte swizzle TMA does not pack two 64-byte inner rows into one 128-byte shared-memory row.)
 int upsampled_map(bsl_ctx* ctx, const void* base, int c, int w, int h, int n, int ld, int tw, int th,
                   CUtensorMap* out) {
   uint64_t dims[5] = {(uint64_t)c, 2, (uint64_t)w, 2, (uint64_t)n * h};
@@ -98,8 +100,9 @@ int upsampled_map(bsl_ctx* ctx, const void* base, int c, int w, int h, int n, in
                      (uint64_t)4 * w * ld * 2};
   uint32_t bx[5] = {64, 1, (uint32_t)tw, 1, (uint32_t)th};
   if (c == 32) {
-    bx[0] = 32;
-    bx[1] = 2;
+    if (ld != 32) return bsl_fail(ctx, BSL_EUNSUPPORTED, "convT2d backward with cout = 32 needs a dense gradient (y_ld = 32, got %d)", ld);
+    dims[0] = 64;
+    dims[1] = 1;
   }
   return bsl_get_tmap(ctx, base, 5, dims, str, bx, out);
 }

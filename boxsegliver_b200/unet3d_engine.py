@@ -181,7 +181,7 @@ class UNet3DEngine:
         self._bufs = []
         self.stream = ctx.stream
         self._pair = (cfg.init_channels <= 32 and cfg.width % 16 == 0 and cfg.height % 32 == 0
-                      and 9 * cfg.in_channels <= 32 and os.environ.get("BSL_UNET3D_PAIR", "0") != "0")
+                      and 9 * cfg.in_channels <= 32 and os.environ.get("BSL_UNET3D_PAIR", "1") != "0")
         # filter gradients on a side stream, as in engine.UNetEngine.loss_backward
         self._overlap_wgrad = cfg.training and os.environ.get("BSL_WGRAD_OVERLAP", "1") != "0"
         self._fuse_inst_stats = os.environ.get("BSL_FUSE_INST_STATS", "1") != "0"
@@ -437,6 +437,9 @@ class UNet3DEngine:
             self.g2 = self._alloc(n * max_grad * BF16)
             self.dyb = [self._alloc(n * max_act * BF16), self._alloc(n * max_act * BF16)]
             self.dcat = {b: View3(self._alloc(v.voxels * v.c * BF16), n, v.dhw, v.c) for b, v in cat.items()}
+            # pixel-pair packed level: the transposed conv's backward kernels read its 32-lane gradient DENSE (the two
+            # column parities of an input voxel are then 64 contiguous values), so ReluGrad writes it here
+            self.dup_dense = self._alloc(nvox * 32 * BF16) if self._pair else None
             ws = 0
             for L in self.layers:
                 if L.kind == "stem":
@@ -777,8 +780,13 @@ class UNet3DEngine:
                 dc = self.dcat[L.block.replace("d", "e")]
                 dup = dc.slice(L.coutp, L.coutp)
                 vox = n * int(np.prod(L.odhw))
+                if L.coutp == 32:
+                    dout = View3(self.dup_dense, n, L.odhw, 32)
+                else:
+                    dout = dup
                 call("bsl_relu_bwd", C.c_longlong(vox), C.c_int(L.coutp), L.a.p, C.c_int(L.a.ld), dup.p, C.c_int(dup.ld),
-                     dup.p, C.c_int(dup.ld), s)
+                     dout.p, C.c_int(dout.ld), s)
+                dup = dout
                 gw = self._pp(self.G, f"{L.scope}/weights")
                 wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
                 two_d = L.s[0] == 1

@@ -161,7 +161,9 @@ int bsl_conv2d_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x_bf16,
 /* ------------------------------------------------------------------ conv2d_transpose k2 s2
  * Replaces Conv2DBackpropInput-as-forward + BiasAdd + Relu behind
  * slim.conv2d_transpose(x, C/2, 2, 2) -- NetworksV2/UNet.py:91 -- and its gradients.
- * x: [n,h,w,cin]; y: [n,2h,2w,cout] written with stride y_ld (the upper half of a concat buffer). */
+ * x: [n,h,w,cin]; y: [n,2h,2w,cout] written with stride y_ld (the upper half of a concat buffer).
+ * cin, cout multiples of 64; cout = 32 is accepted on 8x16-tileable shapes (UNet3D's 30-channel level stored with 32
+ * lanes), where the two backward entry points need the gradient dense (y_ld = 32). */
 typedef struct {
   int n, h, w;  /* INPUT spatial size */
   int cin, cout;

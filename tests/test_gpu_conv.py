@@ -194,7 +194,9 @@ def test_conv2d_fprop_group_statistics(ctx, n, h, w, cin, cout, y_ld, gi):
 @pytest.mark.parametrize("n,h,w,cin,cout,y_ld", [
     (2, 8, 8, 128, 64, None), (1, 16, 16, 64, 64, None), (2, 4, 8, 256, 128, None), (1, 6, 10, 128, 64, None),
     (2, 8, 8, 128, 64, 128), (1, 2, 2, 1024, 512, 1024),
-    (2, 16, 16, 128, 64, 128), (3, 32, 8, 256, 128, None), (1, 16, 24, 64, 64, 192)])   # 1-tap halo-kernel path
+    (2, 16, 16, 128, 64, 128), (3, 32, 8, 256, 128, None), (1, 16, 24, 64, 64, 192),    # 1-tap halo-kernel path
+    # cout = 32: the half-block form (UNet3D's pixel-pair packed level: both column parities in one 64-wide block)
+    (8, 16, 16, 64, 32, 64), (2, 32, 16, 128, 32, None), (4, 16, 8, 64, 32, 64)])
 def test_conv2d_transpose(ctx, n, h, w, cin, cout, y_ld):
     rng = np.random.default_rng(cin + cout + h)
     y_ld = y_ld or cout
@@ -203,7 +205,6 @@ def test_conv2d_transpose(ctx, n, h, w, cin, cout, y_ld):
     bias = (rng.standard_normal(cout) * 0.1).astype(np.float32)
     dy = bf16_randn(rng, (n, 2 * h, 2 * w, cout))
     dx_, dw_, db_ = ctx.bf16_from_f32(x), ctx.bf16_from_f32(wt), ctx.from_numpy(bias)
-    ddy = ctx.bf16_from_f32(padded(dy, y_ld))
     yo = ctx.alloc(n * 4 * h * w * y_ld * 2).zero()
     dxo = ctx.alloc(n * h * w * cin * 2).zero()
     desc = _lib.ConvT2dDesc(n, h, w, cin, cout, cin, y_ld, 1)
@@ -214,6 +215,15 @@ def test_conv2d_transpose(ctx, n, h, w, cin, cout, y_ld):
     assert rel(got[..., :cout], O.relu(O.conv2d_transpose(x64, w64) + bias)) < TOL_BF16
     assert not got[..., cout:].any()
     rdx, rdw = O.conv2d_transpose_grad(x64, w64, dy64)
+    if cout == 32:      # the half-block form reads a dense gradient (both column parities = 64 contiguous values)
+        if y_ld != 32:
+            ddy = ctx.bf16_from_f32(padded(dy, y_ld))
+            with pytest.raises(Exception):
+                ctx.call("bsl_convT2d_bwd_data", C.byref(desc), ddy.p, dw_.p, dxo.p, ctx.stream)
+            ddy.free()
+        y_ld = 32
+        desc = _lib.ConvT2dDesc(n, h, w, cin, cout, cin, y_ld, 1)
+    ddy = ctx.bf16_from_f32(padded(dy, y_ld))
     ctx.call("bsl_convT2d_bwd_data", C.byref(desc), ddy.p, dw_.p, dxo.p, ctx.stream)
     ctx.check_device()
     assert rel(ctx.bf16_to_f32(dxo, (n, h, w, cin)), rdx) < TOL_BF16

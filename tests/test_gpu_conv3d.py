@@ -25,6 +25,8 @@ CASES = [  # (n, d, h, w, cin, cout, kernel, stride)
     (1, 4, 16, 32, 128, 64, (3, 3, 3), (1, 1, 1)),     # cout 64: first wgrad kernel, resident filter in dgrad
     (1, 2, 32, 16, 64, 320, (3, 3, 3), (1, 1, 1)),     # cout 320 (bridge width): not a multiple of 128
     (2, 2, 16, 16, 256, 128, (1, 3, 3), (1, 1, 1)),
+    # the strided conv that leaves the pixel-pair packed level: super voxels along W (stride 1 there), stride 2 along H
+    (2, 4, 32, 16, 128, 64, (1, 3, 3), (1, 2, 1)),
 ]
 
 
