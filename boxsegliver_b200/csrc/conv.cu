@@ -537,6 +537,53 @@ int bsl_debug_read_waits(bsl_ctx* ctx, long long* out, int ctas) {
   return BSL_OK;
 }
 
+// Launch of an fprop on the halo-tile kernel with optional fused statistics of its bf16 outputs (shared by the 2-D
+// layers and the stride-1 3-D layers, whose "images" are the n * d slices and whose statistics group is one volume).
+static int launch_fprop_halo_stats(bsl_ctx* ctx, const HaloPlan& pl, bool res, int res_smem, const CUtensorMap& ta,
+                                   const CUtensorMap& tb, ConvHaloArgs& a, double* sums, int group_imgs, int n_imgs, int h,
+                                   int w, int cout, void* y, int y_ld, cudaStream_t stream) {
+  int rc;
+  if (!sums)
+    return res ? launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
+               : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+  const int groups = group_imgs > 0 ? n_imgs / group_imgs : 1;
+  const long long ppg = group_imgs > 0 ? (long long)group_imgs * h * w : (long long)n_imgs * h * w;
+  if (pl.bn == 256 || (group_imgs > 0 && pl.grid % pl.n_ntiles != 0)) {
+    // long-reduction layers: small, L2-resident outputs; a separate statistics pass is cheaper than an
+    // un-overlapped epilogue butterfly
+    if ((rc = res ? launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
+                  : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream)))
+      return rc;
+    return bsl_stats_bf16(ctx, y, ppg, groups, cout, y_ld, sums, stream);
+  }
+  float* part = nullptr;
+  if (group_imgs > 0) {
+    // [group][slot * 4 + lane quarter][2][cout], zero-filled: a CTA only writes the groups its units fall into
+    const size_t bytes = (size_t)groups * pl.slots * 4 * 2 * cout * sizeof(float);
+    if ((rc = bsl_scratch(ctx, bytes, &part, stream))) return rc;
+    BSL_CUDA(ctx, cudaMemsetAsync(part, 0, bytes, stream));
+    a.stats_part = part;
+    a.stats_group_imgs = group_imgs;
+    a.stats_blocks = pl.slots * 4;
+    rc = res ? launch_halo_res<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
+             : launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+    if (rc) return rc;
+    const int kc2 = 2 * cout;
+    bsl_launch(pixel_reduce_final_kernel, dim3((kc2 + 31) / 32, groups), dim3(1024), 0, stream, part, pl.slots * 4, kc2, sums);
+    BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel (conv instance statistics)");
+    return BSL_OK;
+  }
+  if ((rc = bsl_scratch(ctx, (size_t)pl.slots * 2 * cout * sizeof(float), &part, stream))) return rc;
+  a.stats_part = part;
+  rc = res ? launch_halo_res<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
+           : launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+  if (rc) return rc;
+  const int kc = 2 * cout;
+  bsl_launch(pixel_reduce_final_kernel, dim3(dim3((kc + 31) / 32, 1)), dim3(1024), 0, stream, part, pl.slots, kc, sums);
+  BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel (conv statistics)");
+  return BSL_OK;
+}
+
 // fprop on the halo-tile kernel; `sums` (fp64 [2][cout], nullable) receives the per-channel sum and
 // sum of squares of the bf16 outputs, reduced deterministically from per-CTA partials.
 // group_imgs > 0: instance statistics, sums is [n / group_imgs][2][cout] (one group = group_imgs consecutive images).
@@ -566,43 +613,8 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
   a.a_stages = res_stages;
   a.status = ctx->d_status;
   if ((rc = attach_wait(ctx, a, wait, d->n))) return rc;
-  if (!sums)
-    return res ? launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
-               : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
-  const int groups = group_imgs > 0 ? d->n / group_imgs : 1;
-  const long long ppg = group_imgs > 0 ? (long long)group_imgs * d->h * d->w : (long long)d->n * d->h * d->w;
-  if (pl.bn == 256 || (group_imgs > 0 && pl.grid % pl.n_ntiles != 0)) {
-    // long-reduction layers: small, L2-resident outputs; a separate statistics pass is cheaper than an
-    // un-overlapped epilogue butterfly
-    if ((rc = launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream))) return rc;
-    return bsl_stats_bf16(ctx, y, ppg, groups, d->cout, d->y_ld, sums, stream);
-  }
-  float* part = nullptr;
-  if (group_imgs > 0) {
-    // [group][slot * 4 + lane quarter][2][cout], zero-filled: a CTA only writes the groups its units fall into
-    const size_t bytes = (size_t)groups * pl.slots * 4 * 2 * d->cout * sizeof(float);
-    if ((rc = bsl_scratch(ctx, bytes, &part, stream))) return rc;
-    BSL_CUDA(ctx, cudaMemsetAsync(part, 0, bytes, stream));
-    a.stats_part = part;
-    a.stats_group_imgs = group_imgs;
-    a.stats_blocks = pl.slots * 4;
-    rc = res ? launch_halo_res<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
-             : launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
-    if (rc) return rc;
-    const int kc2 = 2 * d->cout;
-    bsl_launch(pixel_reduce_final_kernel, dim3((kc2 + 31) / 32, groups), dim3(1024), 0, stream, part, pl.slots * 4, kc2, sums);
-    BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel (conv instance statistics)");
-    return BSL_OK;
-  }
-  if ((rc = bsl_scratch(ctx, (size_t)pl.slots * 2 * d->cout * sizeof(float), &part, stream))) return rc;
-  a.stats_part = part;
-  rc = res ? launch_halo_res<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
-           : launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
-  if (rc) return rc;
-  const int kc = 2 * d->cout;
-  bsl_launch(pixel_reduce_final_kernel, dim3(dim3((kc + 31) / 32, 1)), dim3(1024), 0, stream, part, pl.slots, kc, sums);
-  BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel (conv statistics)");
-  return BSL_OK;
+  return launch_fprop_halo_stats(ctx, pl, res, res_smem, ta, tb, a, sums, group_imgs, d->n, d->h, d->w, d->cout, y,
+                                 d->y_ld, stream);
 }
 
 int bsl_conv2d_fprop_stats(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* w, void* y,
@@ -870,6 +882,46 @@ int bsl_convT2d_fwd(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, cons
   return bsl_convT2d_fwd_pipe(ctx, d, x, w, bias, y, nullptr, stream);
 }
 
+// cout = 32 into a pixel-pair packed tensor: output voxel (2y + a, 2x + b) lane co lives at
+// y[((n * 2h + 2y + a) * w + x) * y_ld + b * 32 + co], y_ld = lanes per voxel PAIR. The GEMM columns (a, b, co) are
+// the filter's own row order, so this is a transposed conv with 2 "taps" (a) of 64 columns each.
+int bsl_convT2d_fwd_pairs(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, const void* w, void* y, void* stream) {
+  int rc = check_convT(ctx, d);
+  if (rc) return rc;
+  if (!x || !w || !y) return bsl_fail(ctx, BSL_EINVAL, "convT2d_fwd_pairs: null buffer");
+  if (d->cout != 32 || d->y_ld < 64) return bsl_fail(ctx, BSL_EUNSUPPORTED, "convT2d_fwd_pairs: cout = 32, y_ld >= 64 (lanes per voxel pair)");
+  HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, 128);
+  if (pl.bn == 256) return bsl_fail(ctx, BSL_EUNSUPPORTED, "convT2d_fwd_pairs: column tile");
+  int res_stages = 0, res_smem = 0;
+  const bool res = plan_resident(pl.bn, 1, d->cin / 64, &pl.nsub, &res_stages, &res_smem);
+  if (res) replan_units(ctx, pl);
+  const int hbox[4] = {8, 16, 1, 1};
+  CUtensorMap ta, tb;
+  if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, hbox, &ta))) return rc;
+  if ((rc = matrix_map(ctx, w, d->cin, 128, 64, pl.bn, &tb))) return rc;
+  ConvHaloArgs a = {};
+  halo_common(a, pl, d->w, d->h, d->n);
+  a.ntaps = 1;
+  a.halo = 0;
+  a.cblocks = d->cin / 64;
+  a.b_rows_per_tap = 0;
+  a.out = y;
+  const long long row = (long long)d->w * d->y_ld;   // one output row of voxel pairs
+  a.ostride_x = d->y_ld;
+  a.ostride_y = 2 * row;
+  a.ostride_n = (long long)2 * d->h * row;
+  a.n_group = 64;
+  a.group_off[0] = 0;
+  a.group_off[1] = row;
+  a.bias = nullptr;
+  a.relu = d->relu;
+  a.n_total = 128;
+  a.a_stages = res_stages;
+  a.status = ctx->d_status;
+  return res ? launch_halo_res<false, false, true>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream))
+             : launch_halo<false, false, true>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
+}
+
 int bsl_convT2d_fwd_pipe(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x, const void* w,
                          const float* bias, void* y, const bsl_pipe* wait, void* stream) {
   int rc = check_convT(ctx, d);
@@ -1114,7 +1166,7 @@ bool d3_stride1(const bsl_conv3d_desc* d) {
 bool bsl_conv3d_halo_ok(const bsl_conv3d_desc* d) { return d3_stride1(d) && halo_eligible(d->w, d->h); }
 
 int bsl_conv3d_halo_fprop(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x, const void* w, void* y,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, double* sums) {
   HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n * d->d, d->cout);
   int res_stages = 0, res_smem = 0;
   const bool res = plan_resident(pl.bn, 9 * d->kd, d->cin / 64, &pl.nsub, &res_stages, &res_smem);
@@ -1138,8 +1190,9 @@ int bsl_conv3d_halo_fprop(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x,
   a.n_total = d->cout;
   a.a_stages = res_stages;
   a.status = ctx->d_status;
-  return res ? launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
-             : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+  // instance statistics per (volume, channel): a statistics group is the d slices of one volume
+  return launch_fprop_halo_stats(ctx, pl, res, res_smem, ta, tb, a, sums, d->d, d->n * d->d, d->h, d->w, d->cout, y,
+                                 d->y_ld, stream);
 }
 
 int bsl_conv3d_halo_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy, const void* w, void* dx,

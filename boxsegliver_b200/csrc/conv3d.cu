@@ -78,8 +78,10 @@ int geometry(bsl_ctx* ctx, const bsl_conv3d_desc* d, Geo* g) {
     return bsl_fail(ctx, BSL_EINVAL, "conv3d: non-positive size");
   const int in[3] = {d->w, d->h, d->d}, k[3] = {d->kw, d->kh, d->kd}, s[3] = {d->sw, d->sh, d->sd};
   for (int i = 0; i < 3; ++i) {
-    if (!(k[i] == 1 || k[i] == 3) || !(s[i] == 1 || s[i] == 2))
-      return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv3d: kernel extents 1|3 and strides 1|2 only");
+    // extent 2 (SAME: one voxel of padding on the far side): the strided conv that leaves UNet3D's pixel-pair packed
+    // level reads super voxels X and X + 1
+    if (k[i] < 1 || k[i] > 3 || !(s[i] == 1 || s[i] == 2))
+      return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv3d: kernel extents 1..3 and strides 1|2 only");
     g->in[i] = in[i];
     g->k[i] = k[i];
     g->s[i] = s[i];
@@ -241,6 +243,20 @@ int bsl_conv3d_fprop(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x, cons
   a.status = ctx->d_status;
   dim3 grid(a.ntile[0] * a.ntile[1] * a.ntile[2] * a.ntile[3], d->cout / bn, 1);
   return launch3<MODE_PIX_M, true>(ctx, bn, ta, tb, a, grid, as_stream(stream));
+}
+
+// fprop + per-(volume, channel) sum and sum of squares of the bf16 outputs (instance norm over a volume): fused into
+// the epilogue where the layer runs on the halo-tile kernel, else a separate pass over y.
+int bsl_conv3d_fprop_group_stats(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x, const void* w, void* y,
+                                 double* sums, void* stream) {
+  Geo g;
+  int rc = geometry(ctx, d, &g);
+  if (rc) return rc;
+  if (!x || !w || !y || !sums) return bsl_fail(ctx, BSL_EINVAL, "conv3d_fprop_group_stats: null buffer");
+  if (bsl_conv3d_halo_ok(d)) return bsl_conv3d_halo_fprop(ctx, d, x, w, y, as_stream(stream), sums);
+  if ((rc = bsl_conv3d_fprop(ctx, d, x, w, y, stream))) return rc;
+  return bsl_stats_bf16(ctx, y, (long long)g.out[0] * g.out[1] * g.out[2], d->n, d->cout, d->y_ld, sums,
+                        as_stream(stream));
 }
 
 int bsl_conv3d_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy, const void* w, void* dx, void* stream) {

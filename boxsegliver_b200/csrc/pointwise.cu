@@ -71,6 +71,16 @@ __global__ void gather_add2_f32_kernel(const float* __restrict__ src, const int*
   }
 }
 
+// Statistics of a pixel-pair packed tensor: the conv epilogue sums over 2 * c "super" channels (voxel parity, lane);
+// the real channel's moments are the sum of its two halves. src [groups][2][2c] -> dst [groups][2][c].
+__global__ void fold_pair_sums_kernel(const double* __restrict__ src, int total, int c, double* __restrict__ dst) {
+  bsl::pdl_enter();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int row = i / c, ch = i - row * c;
+  dst[i] = src[(long long)row * 2 * c + ch] + src[(long long)row * 2 * c + c + ch];
+}
+
 struct SumF {
   static constexpr int K = 1, NIN = 1, UNROLL = 8;
   struct State {};
@@ -272,6 +282,14 @@ int bsl_gather_add2_f32(bsl_ctx* ctx, const float* src, const int* idx2, size_t 
   bsl_launch(gather_add2_f32_kernel, dim3(grid_for((long long)n, kThreads, 8 * ctx->sm_count)), dim3(kThreads), 0,
              as_stream(stream), src, idx2, n, dst);
   BSL_LAUNCH_CHECK(ctx, "gather_add2_f32_kernel");
+  return BSL_OK;
+}
+
+int bsl_fold_pair_sums(bsl_ctx* ctx, const double* src, int groups, int c, double* dst, void* stream) {
+  if (!ctx || !src || !dst || groups < 1 || c < 1) return BSL_EINVAL;
+  const int total = groups * 2 * c;
+  bsl_launch(fold_pair_sums_kernel, dim3((total + 127) / 128), dim3(128), 0, as_stream(stream), src, total, c, dst);
+  BSL_LAUNCH_CHECK(ctx, "fold_pair_sums_kernel");
   return BSL_OK;
 }
 

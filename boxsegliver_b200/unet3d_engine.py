@@ -21,9 +21,12 @@ concat [encoder, up], 1x1x1 logits, weighted cross-entropy. What differs from th
     (tap S of the super filter, input half hi, output half ho holds the real tap 2S + hi - ho + 1), a fixed
     re-arrangement built from the slim variable by an index table (bsl_gather_f32_bf16) and undone for the filter
     gradient (bsl_gather_add2_f32). Half the MMAs and half the HBM bytes of the 64-lane storage on the layers that
-    hold most of the voxels; the normalisation / ReLU / add passes see the real 32-lane view. The strided conv that
-    leaves the level reads super voxels with horizontal stride 1 (pixel stride 2), the transposed conv that enters it
-    uses the 32-channel half-block form of bsl_convT2d_* (both column parities in one 64-wide block).
+    hold most of the voxels; the normalisation / ReLU / add passes see the real 32-lane view. The level's concat buffer
+    holds 128 lanes per voxel PAIR, [encoder even | encoder odd | up even | up odd]: the encoder half alone is again a
+    64-lane super tensor (stride 128), so the strided conv that leaves the level reads only it -- super voxels X and
+    X + 1 (a 2-tap row, horizontal stride 1 = pixel stride 2) -- and the transposed conv that enters the level writes
+    the `up` half with bsl_convT2d_fwd_pairs; its backward kernels read the ReluGrad output as a dense 32-lane tensor
+    (both column parities = 64 contiguous values).
 """
 from __future__ import annotations
 
@@ -101,6 +104,19 @@ class View3:
         return View3(self.buf, self.n, self.dhw, c, self.ld, self.c0 + c0)
 
 
+class PairView(View3):
+    """One half (part 0 = encoder, 1 = up) of the pixel-pair packed level's concat buffer: voxel pairs of 64 lanes
+    ((voxel parity, 32 lanes)) with stride 128. `ld` and `c` are those of the voxel-PAIR view."""
+
+    def __init__(self, buf: DeviceBuffer, n, dhw, part):
+        super().__init__(buf, n, dhw, 64, 128, 64 * part)
+        self.part = part
+
+    @property
+    def pairs(self):
+        return self.voxels // 2
+
+
 @dataclass
 class Layer3:
     kind: str                 # stem | conv | convT | logits
@@ -118,6 +134,7 @@ class Layer3:
     cin_map: np.ndarray = None   # real input channel -> stored input channel
     fork: bool = False        # encoder conv2: output also feeds the skip connection
     pair: str = ""            # pixel-pair packing: "conv" (stride-1 super conv), "strided" (level 0 -> 1), "stem", or ""
+    catpair: bool = False     # pair == "conv" reading the level's concat buffer ([enc even | enc odd | up even | up odd])
     x: View3 = None
     y: View3 = None
     a: View3 = None
@@ -236,9 +253,10 @@ class UNet3DEngine:
                 L.cinp = 2 * cp_
                 L.cin_map = np.r_[0:c, cp_:cp_ + c]
                 L.pair = "conv" if lvl0 else ""
+                L.catpair = bool(lvl0)
             elif pair and block == "conv_e1" and layer == "conv1":
-                # reads the encoder half of the level-0 concat buffer: whole 64-lane voxels (the `up` half meets zero rows)
-                L.cinp = 2 * cpb(cin, "conv_e0")
+                # reads the encoder half of the level-0 concat buffer: 64-lane voxel pairs with stride 128
+                L.cinp = cpb(cin, "conv_e0")
                 L.pair = "strided"
             else:
                 L.cinp = cpb(cin, prev_block)
@@ -301,7 +319,7 @@ class UNet3DEngine:
     def _super_index(L: Layer3):
         """idx[i] = flat index into the layer's stored (master) filter that super-filter element i copies, or -1.
         Shapes: master (3, 3, cinp, coutp) [depth extent 1 dropped] / (cinp, coutp) for the stem;
-        super (3, 3, 2*cinp, 64) / (64, 64)."""
+        super (3, 3, 2*cinp, 64) / (3, 2, 2*cinp, coutp) for the strided layer / (64, 64)."""
         cinp, coutp = L.cinp, L.coutp
         if L.pair == "stem":
             idx = np.full((2, cinp, 2, coutp), -1, np.int64)
@@ -311,10 +329,10 @@ class UNet3DEngine:
             return idx.reshape(2 * cinp, 2 * coutp)
         m = np.arange(3 * 3 * cinp * coutp).reshape(3, 3, cinp, coutp)
         if L.pair == "strided":     # output voxel X reads input voxels 2X + s: super voxel X + (s >> 1), half s & 1
-            idx = np.full((3, 3, 2, cinp, coutp), -1, np.int64)
+            idx = np.full((3, 2, 2, cinp, coutp), -1, np.int64)
             for s_ in range(3):
-                idx[:, 1 + (s_ >> 1), s_ & 1] = m[:, s_]
-            return idx.reshape(3, 3, 2 * cinp, coutp)
+                idx[:, s_ >> 1, s_ & 1] = m[:, s_]
+            return idx.reshape(3, 2, 2 * cinp, coutp)
         idx = np.full((3, 3, 2, cinp, 2, coutp), -1, np.int64)
         for sx in (-1, 0, 1):
             for hi in (0, 1):
@@ -322,6 +340,11 @@ class UNet3DEngine:
                     s_ = 2 * sx + hi - ho + 1      # input voxel 2(X + sx) + hi, output voxel 2X + ho
                     if 0 <= s_ <= 2:
                         idx[:, sx + 1, hi, :, ho, :] = m[:, s_]
+        if getattr(L, "catpair", False):
+            # the input is the level's concat buffer: lanes [encoder even | encoder odd | up even | up odd] per voxel
+            # pair, while the stored filter's input axis is [encoder | up] -> reduction order (part, half, lane)
+            half = cinp // 2
+            idx = idx.reshape(3, 3, 2, 2, half, 2, coutp).transpose(0, 1, 3, 2, 4, 5, 6)
         return idx.reshape(3, 3, 2 * cinp, 2 * coutp)
 
     @staticmethod
@@ -392,7 +415,7 @@ class UNet3DEngine:
                 if L.fork:
                     cb = View3(self._alloc(n * vox * 2 * L.coutp * BF16).zero(), n, L.odhw, 2 * L.coutp)
                     cat[L.block] = cb
-                    L.a = cb.slice(0, L.coutp)
+                    L.a = PairView(cb.buf, n, L.odhw, 0) if L.pair else cb.slice(0, L.coutp)
                 else:
                     L.a = View3(self._alloc(n * vox * L.coutp * BF16), n, L.odhw, L.coutp)
                 is_dec1 = L.block.startswith("conv_d") and L.layer == "conv1"
@@ -407,7 +430,7 @@ class UNet3DEngine:
                 max_grad = max(max_grad, int(np.prod(L.dhw)) * L.cinp)
                 L.x = prev
                 cb = cat[L.block.replace("d", "e")]
-                L.a = cb.slice(L.coutp, L.coutp)
+                L.a = PairView(cb.buf, n, L.odhw, 1) if L.coutp == 32 else cb.slice(L.coutp, L.coutp)
                 L.y = L.a
                 prev = cb
             else:
@@ -427,6 +450,7 @@ class UNet3DEngine:
         self.counts = self._alloc(n * k * 4)
         self.loss_dev = self._alloc(16)
         self.small = self._alloc(max(small, 16) * F32)
+        self.sums_sup = self._alloc(n * 2 * 64 * 8)       # fp64 [n][2][64]: statistics over super channels
         ld = self._loss_desc()
         self.loss_ws_bytes = self.ctx.lib.bsl_loss_workspace(self.ctx.h, C.byref(ld))
         self.loss_ws = self._alloc(self.loss_ws_bytes)
@@ -481,10 +505,10 @@ class UNet3DEngine:
         return _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], 64, L.coutp, 1, 1, 64, L.y.ld)
 
     def _desc3s(self, L: Layer3):
-        """The strided conv that leaves the pixel-pair packed level: super voxels along W (stride 1 there, taps S = -1
-        (all zero), 0, +1), the real strides along D and H."""
-        return _lib.Conv3dDesc(self.cfg.batch, L.dhw[0], L.dhw[1], L.dhw[2] // 2, 2 * L.cinp, L.coutp, L.k[0], L.k[1], 3,
-                               L.s[0], L.s[1], 1, 2 * L.x.ld, L.y.ld)
+        """The strided conv that leaves the pixel-pair packed level: super voxels along W (stride 1 there, a 2-tap row:
+        super voxels X and X + 1), the real strides along D and H. Its input is the encoder half of the concat buffer."""
+        return _lib.Conv3dDesc(self.cfg.batch, L.dhw[0], L.dhw[1], L.dhw[2] // 2, 2 * L.cinp, L.coutp, L.k[0], L.k[1], 2,
+                               L.s[0], L.s[1], 1, L.x.ld, L.y.ld)
 
     def _desc3(self, L: Layer3):
         return _lib.Conv3dDesc(self.cfg.batch, L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.coutp, L.k[0], L.k[1], L.k[2],
@@ -497,7 +521,8 @@ class UNet3DEngine:
         return _lib.ConvT3dDesc(self.cfg.batch, L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.coutp, L.s[0], L.x.ld, L.a.ld, 1)
 
     def _norm_desc(self, L: Layer3):
-        return _lib.NormDesc(1, self.cfg.batch, int(np.prod(L.odhw)), L.coutp, L.y.ld, L.a.ld, self.cfg.in_eps, 0.0,
+        a_ld = L.coutp if isinstance(L.a, PairView) else L.a.ld     # (the pair view is written by two half calls)
+        return _lib.NormDesc(1, self.cfg.batch, int(np.prod(L.odhw)), L.coutp, L.y.ld, a_ld, self.cfg.in_eps, 0.0,
                              1, 1, 1)
 
     def _norm_ptrs(self, L: Layer3):
@@ -632,9 +657,15 @@ class UNet3DEngine:
                 continue
             dct = {}
             for key, v in (("y", L.y), ("a", L.a)):
-                full = self.ctx.bf16_to_f32(v.buf, (v.n,) + v.dhw + (v.ld,))
-                dct[key] = full[..., v.c0:v.c0 + L.cout].copy()
-                pad = full[..., v.c0 + L.cout:v.c0 + v.c]
+                if isinstance(v, PairView):     # [.., w/2, 128] -> this half's 64 lanes -> [.., w, 32]
+                    full = self.ctx.bf16_to_f32(v.buf, (v.n,) + v.dhw[:2] + (v.dhw[2] // 2, 128))
+                    full = full[..., v.c0:v.c0 + 64].reshape((v.n,) + v.dhw + (32,))
+                    dct[key] = full[..., :L.cout].copy()
+                    pad = full[..., L.cout:]
+                else:
+                    full = self.ctx.bf16_to_f32(v.buf, (v.n,) + v.dhw + (v.ld,))
+                    dct[key] = full[..., v.c0:v.c0 + L.cout].copy()
+                    pad = full[..., v.c0 + L.cout:v.c0 + v.c]
                 assert not pad.any(), f"{L.scope}: pad lanes of {key} are not zero"
             out[L.scope] = dct
         return out
@@ -650,33 +681,46 @@ class UNet3DEngine:
             if L.kind in ("stem", "conv"):
                 wbf = self._wsup(L) if L.pair else self._pp(self.Wbf, f"{L.scope}/weights", BF16)
                 nd, q = self._norm_desc(L), self._norm_ptrs(L)
-                # layers that run as 2-D convolutions over n*d images take their per-(volume, channel) statistics from
-                # the conv epilogue: a statistics group is the `depth` consecutive images of one volume. (Not the pixel-
-                # pair packed layers: their epilogue sees super channels, and the real 32-lane tensor is half the bytes.)
-                fuse = self._fuse_inst_stats and not L.pair
+                # per-(volume, channel) statistics come from the conv epilogue: for layers that run as 2-D convolutions over
+                # n*d images a statistics group is the `depth` consecutive images of one volume; pixel-pair packed layers
+                # sum over super channels (voxel parity, lane), folded to the real channels afterwards.
+                fuse = self._fuse_inst_stats
+                sums = self.sums_sup.p if (fuse and L.pair in ("conv", "stem")) else q["sums"]
                 fn = "bsl_conv2d_fprop_group_stats" if fuse else "bsl_conv2d_fprop"
-                extra = (C.c_int(L.dhw[0]), q["sums"]) if fuse else ()
+                extra = (C.c_int(L.dhw[0]), sums) if fuse else ()
                 if L.kind == "stem":
                     d0 = _lib.Conv2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], L.cin, 64, 3, 3, L.cin, 64)
                     call("bsl_stem_im2col_ld", C.byref(d0), self.images.p, self.stem_col.p, C.c_int(L.cinp), s)
                     call(fn, C.byref(self._desc_stem(L)), self.stem_col.p, wbf, L.y.p, *extra, s)
-                elif L.pair == "strided":
-                    fuse = False
-                    call("bsl_conv3d_fprop", C.byref(self._desc3s(L)), L.x.p, wbf, L.y.p, s)
-                elif self._is2d(L):
+                elif self._is2d(L) and L.pair != "strided":
                     call(fn, C.byref(self._desc2(L)), L.x.p, wbf, L.y.p, *extra, s)
                 else:
-                    fuse = False
-                    call("bsl_conv3d_fprop", C.byref(self._desc3(L)), L.x.p, wbf, L.y.p, s)
+                    d3 = self._desc3s(L) if L.pair == "strided" else self._desc3(L)
+                    if fuse:
+                        call("bsl_conv3d_fprop_group_stats", C.byref(d3), L.x.p, wbf, L.y.p, sums, s)
+                    else:
+                        call("bsl_conv3d_fprop", C.byref(d3), L.x.p, wbf, L.y.p, s)
+                if fuse and L.pair in ("conv", "stem"):
+                    call("bsl_fold_pair_sums", sums, C.c_int(n), C.c_int(L.coutp), q["sums"], s)
                 if not fuse:
                     call("bsl_norm_stats", C.byref(nd), L.y.p, q["sums"], s)
                 call("bsl_norm_finalize", C.byref(nd), C.c_int(1 if is_training else 0), q["sums"],
                      self._pp(self.W, f"{L.scope}/InstanceNorm/gamma"), self._pp(self.W, f"{L.scope}/InstanceNorm/beta"),
                      None, None, q["mean"], q["rstd"], q["scale"], q["shift"], s)
-                call("bsl_norm_apply", C.byref(nd), L.y.p, q["scale"], q["shift"], L.a.p, s)
+                if isinstance(L.a, PairView):
+                    # even / odd voxels of the dense 32-lane tensor -> the two 32-lane quarters of the encoder half
+                    ndh = _lib.NormDesc(1, n, nd.hw // 2, 32, 64, L.a.ld, cfg.in_eps, 0.0, 1, 1, 1)
+                    for b in (0, 1):
+                        call("bsl_norm_apply", C.byref(ndh), C.c_void_p(L.y.p.value + b * 32 * BF16), q["scale"], q["shift"],
+                             C.c_void_p(L.a.p.value + b * 32 * BF16), s)
+                else:
+                    call("bsl_norm_apply", C.byref(nd), L.y.p, q["scale"], q["shift"], L.a.p, s)
             elif L.kind == "convT":
                 wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
-                if L.s[0] == 1:
+                if isinstance(L.a, PairView):
+                    dT = _lib.ConvT2dDesc(n * L.dhw[0], L.dhw[1], L.dhw[2], L.cinp, L.coutp, L.x.ld, L.a.ld, 1)
+                    call("bsl_convT2d_fwd_pairs", C.byref(dT), L.x.p, wbf, L.a.p, s)
+                elif L.s[0] == 1:
                     call("bsl_convT2d_fwd", C.byref(self._descT2(L)), L.x.p, wbf, None, L.a.p, s)
                 else:
                     call("bsl_convT3d_fwd", C.byref(self._descT3(L)), L.x.p, wbf, None, L.a.p, s)
@@ -728,8 +772,13 @@ class UNet3DEngine:
                 vox = n * int(np.prod(L.odhw))
                 if L.fork:   # AddN: gradient through the next block's strided conv + gradient through the skip
                     dc = self.dcat[L.block]
-                    call("bsl_add_bf16", C.c_longlong(vox), C.c_int(L.coutp), cur.p, C.c_int(cur_ld), dc.p,
-                         C.c_int(dc.ld), alt.p, C.c_int(L.coutp), s)
+                    if isinstance(L.a, PairView):    # voxel pairs: 64 dense lanes + the encoder half of the concat gradient
+                        assert cur_ld == 32
+                        call("bsl_add_bf16", C.c_longlong(vox // 2), C.c_int(64), cur.p, C.c_int(64), dc.p,
+                             C.c_int(L.a.ld), alt.p, C.c_int(64), s)
+                    else:
+                        call("bsl_add_bf16", C.c_longlong(vox), C.c_int(L.coutp), cur.p, C.c_int(cur_ld), dc.p,
+                             C.c_int(dc.ld), alt.p, C.c_int(L.coutp), s)
                     cur, alt = alt, cur
                     cur_ld = L.coutp
                 assert cur_ld == L.coutp, (L.scope, cur_ld, L.coutp)
@@ -780,13 +829,14 @@ class UNet3DEngine:
                 dc = self.dcat[L.block.replace("d", "e")]
                 dup = dc.slice(L.coutp, L.coutp)
                 vox = n * int(np.prod(L.odhw))
-                if L.coutp == 32:
-                    dout = View3(self.dup_dense, n, L.odhw, 32)
+                if isinstance(L.a, PairView):   # voxel pairs of the `up` half -> dense 32-lane gradient
+                    dpv = PairView(dc.buf, n, L.odhw, 1)
+                    dup = View3(self.dup_dense, n, L.odhw, 32)
+                    call("bsl_relu_bwd", C.c_longlong(vox // 2), C.c_int(64), L.a.p, C.c_int(L.a.ld), dpv.p,
+                         C.c_int(dpv.ld), dup.p, C.c_int(64), s)
                 else:
-                    dout = dup
-                call("bsl_relu_bwd", C.c_longlong(vox), C.c_int(L.coutp), L.a.p, C.c_int(L.a.ld), dup.p, C.c_int(dup.ld),
-                     dout.p, C.c_int(dout.ld), s)
-                dup = dout
+                    call("bsl_relu_bwd", C.c_longlong(vox), C.c_int(L.coutp), L.a.p, C.c_int(L.a.ld), dup.p,
+                         C.c_int(dup.ld), dup.p, C.c_int(dup.ld), s)
                 gw = self._pp(self.G, f"{L.scope}/weights")
                 wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
                 two_d = L.s[0] == 1

@@ -93,6 +93,9 @@ int bsl_scale_f32(bsl_ctx* ctx, float* x, size_t n, float a, void* stream);
  * dst[j] = src[idx2[2j]] + src[idx2[2j+1]] (terms with a negative index dropped) for the filter gradient. */
 int bsl_gather_f32_bf16(bsl_ctx* ctx, const float* src, const int* idx, size_t n, void* dst_bf16, void* stream);
 int bsl_gather_add2_f32(bsl_ctx* ctx, const float* src, const int* idx2, size_t n, float* dst, void* stream);
+/* Moments of a pixel-pair packed tensor from the statistics of its 2c "super" channels (voxel parity, lane):
+ * src fp64 [groups][2][2c] -> dst fp64 [groups][2][c], dst[g][k][ch] = src[g][k][ch] + src[g][k][c + ch]. */
+int bsl_fold_pair_sums(bsl_ctx* ctx, const double* src, int groups, int c, double* dst, void* stream);
 
 /* ------------------------------------------------------------------ conv2d, stride 1, SAME
  * Replaces TF ops Conv2D / Conv2DBackpropInput / Conv2DBackpropFilter behind
@@ -173,6 +176,11 @@ typedef struct {
 
 int bsl_convT2d_fwd(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x_bf16,
                     const void* w_kkoi_bf16, const float* bias_f32, void* y_bf16, void* stream);
+/* cout = 32 written into a pixel-pair packed tensor (UNet3D's full-resolution level, unet3d_engine.py): output voxel
+ * (2y + a, 2x + b), lane co -> y[((n * 2h + 2y + a) * w + x) * y_ld + b * 32 + co]; y_ld = lanes per voxel pair. No bias
+ * (slim.conv3d_transpose(..., biases_initializer=None), NetworksV2/UNet3D.py:160-163). */
+int bsl_convT2d_fwd_pairs(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x_bf16, const void* w_kkoi_bf16,
+                          void* y_bf16, void* stream);
 int bsl_convT2d_fwd_pipe(bsl_ctx* ctx, const bsl_convT2d_desc* d, const void* x_bf16, const void* w_kkoi_bf16,
                          const float* bias_f32, void* y_bf16, const bsl_pipe* wait, void* stream);
 /* dyr must already carry the ReLU mask (dy * (y > 0)); see bsl_relu_bwd. */
@@ -200,6 +208,10 @@ typedef struct {
 
 int bsl_conv3d_fprop(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x_bf16, const void* w_dhwio_bf16,
                      void* y_bf16, void* stream);
+/* fprop + instance statistics: sums is fp64 [n][2][cout] (sum, sum of squares of the bf16 outputs per volume and
+ * channel), what slim.instance_norm's moments need (NetworksV2/UNet3D.py:151-158). */
+int bsl_conv3d_fprop_group_stats(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x_bf16, const void* w_dhwio_bf16,
+                                 void* y_bf16, double* sums, void* stream);
 int bsl_conv3d_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy_bf16, const void* w_dhwio_bf16,
                      void* dx_bf16, void* stream);
 size_t bsl_conv3d_wgrad_workspace(bsl_ctx* ctx, const bsl_conv3d_desc* d);

@@ -31,9 +31,20 @@ NSAMP = 256
 TOL = 1e-2
 
 
-def _bits(view, dims5):
-    """uint16 bit patterns of a View / View3's whole buffer, shaped [n, d, h, w, ld]."""
+def _bits(view, dims5, catpair=False):
+    """uint16 bit patterns of a View / View3's whole buffer, shaped [n, d, h, w, ld]. UNet3D's pixel-pair packed concat
+    buffer (128 lanes per voxel pair: [enc even | enc odd | up even | up odd]) is re-arranged to the per-voxel view the
+    samplers index: a PairView half -> its 32 lanes at [c0, c0 + 32); the whole buffer (catpair) -> [enc 32 | up 32]."""
+    from boxsegliver_b200.unet3d_engine import PairView
     n, d, h, w = dims5
+    if isinstance(view, PairView) or catpair:
+        full = view.buf.download(np.uint16, (n, d, h, w // 2, 128))
+        enc, up = full[..., :64].reshape(n, d, h, w, 32), full[..., 64:].reshape(n, d, h, w, 32)
+        if catpair:
+            return np.concatenate((enc, up), axis=-1)
+        out = np.zeros((n, d, h, w, view.c0 + 32), np.uint16)
+        out[..., view.c0:] = up if view.part else enc
+        return out
     return view.buf.download(np.uint16, (n, d, h, w, view.ld))
 
 
@@ -354,7 +365,7 @@ def test_cfg4_unet3d_full_size_sampled_parity(ctx):
         if L.kind == "stem":
             xb, c0, cmap = f32_to_bf16_bits(im).reshape(n, d, h, w, cfg.in_channels), 0, None
         else:
-            xb, c0, cmap = _bits(L.x, (n,) + L.dhw), L.x.c0, L.cin_map
+            xb, c0, cmap = _bits(L.x, (n,) + L.dhw, getattr(L, "catpair", False)), L.x.c0, L.cin_map
         want = S.conv_at(xb, c0, L.cin, wt, pos, stride=L.s, cin_map=cmap)
         yb = _bits(L.y, (n,) + L.odhw)
         got = S.gather(yb, L.y.c0, L.cout, pos)

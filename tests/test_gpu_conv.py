@@ -238,6 +238,26 @@ def test_conv2d_transpose(ctx, n, h, w, cin, cout, y_ld):
         b.free()
 
 
+@pytest.mark.parametrize("n,h,w,cin", [(8, 16, 16, 64), (2, 32, 8, 128)])
+def test_conv2d_transpose_into_voxel_pairs(ctx, n, h, w, cin):
+    """bsl_convT2d_fwd_pairs: 32 output channels written into the `up` half of UNet3D's pixel-pair packed concat buffer
+    (128 lanes per voxel pair: [enc even | enc odd | up even | up odd]); the other half must stay untouched."""
+    rng = np.random.default_rng(cin + h)
+    x = bf16_randn(rng, (n, h, w, cin))
+    wt = bf16_randn(rng, (2, 2, 32, cin), 0.05)
+    dx_, dw_ = ctx.bf16_from_f32(x), ctx.bf16_from_f32(wt)
+    yo = ctx.alloc(n * 2 * h * w * 128 * 2).zero()
+    desc = _lib.ConvT2dDesc(n, h, w, cin, 32, cin, 128, 1)
+    ctx.call("bsl_convT2d_fwd_pairs", C.byref(desc), dx_.p, dw_.p, C.c_void_p(yo.ptr + 64 * 2), ctx.stream)
+    ctx.check_device()
+    got = ctx.bf16_to_f32(yo, (n, 2 * h, w, 128))
+    ref = O.relu(O.conv2d_transpose(x.astype(np.float64), wt.astype(np.float64)))      # [n, 2h, 2w, 32]
+    assert rel(got[..., 64:].reshape(n, 2 * h, 2 * w, 32), ref) < TOL_BF16
+    assert not got[..., :64].any()
+    for b in (dx_, dw_, yo):
+        b.free()
+
+
 def test_full_size_adjoint_identity(ctx):
     """BASELINE-size layer (Decode1 conv1 of cfg2: 64 x 256 x 256, 128 -> 64): the oracle cannot run it in
     seconds, but <fprop(x), dy> == <x, dgrad(dy)> == <w, wgrad(x, dy)> must hold for any correct triple."""

@@ -27,6 +27,7 @@ CASES = [  # (n, d, h, w, cin, cout, kernel, stride)
     (2, 2, 16, 16, 256, 128, (1, 3, 3), (1, 1, 1)),
     # the strided conv that leaves the pixel-pair packed level: super voxels along W (stride 1 there), stride 2 along H
     (2, 4, 32, 16, 128, 64, (1, 3, 3), (1, 2, 1)),
+    (2, 4, 32, 16, 64, 64, (1, 3, 2), (1, 2, 1)),      # ... as the engine runs it: 2-tap rows (super voxels X, X + 1)
 ]
 
 

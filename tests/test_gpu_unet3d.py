@@ -1,6 +1,6 @@
 """Parity of the UNet3D engine against oracle/unet3d_ref.py through the C ABI: every layer on the device's stored
 input (fp64 oracle, rel <= 1e-2), loss, dlogits, and all gradients over the device's stored tape (every tensor whose
-layer normalises over >= 64 voxels <= 1e-2, north_star bf16 tolerance), with the true channel counts 30/60/120/240/320 (zero-padded storage)."""
+layer normalises over >= 256 voxels <= 1e-2, north_star bf16 tolerance), with the true channel counts 30/60/120/240/320 (zero-padded storage)."""
 import numpy as np
 import pytest
 

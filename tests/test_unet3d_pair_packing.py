@@ -44,7 +44,7 @@ def test_strided_layer_leaving_the_packed_level():
     n, d, h, w, cinp, coutp = 2, 2, 8, 8, 4, 5
     x, wt = rng.standard_normal((n, d, h, w, cinp)), rng.standard_normal((1, 3, 3, cinp, coutp))
     idx = E._super_index(NS(pair="strided", cinp=cinp, coutp=coutp))
-    ws = _super(idx, wt).reshape(1, 3, 3, 2 * cinp, coutp)
+    ws = _super(idx, wt).reshape(1, 3, 2, 2 * cinp, coutp)            # 2-tap rows: super voxels X and X + 1
     xs = x.reshape(n, d, h, w // 2, 2 * cinp)
     y = O.conv3d(x, wt, (1, 2, 2))
     assert np.allclose(O.conv3d(xs, ws, (1, 2, 1)), y, atol=1e-12)    # stride 1 over super voxels = stride 2 over voxels
@@ -53,7 +53,20 @@ def test_strided_layer_leaving_the_packed_level():
                        O.conv3d_backprop_input(x.shape, wt, dy, (1, 2, 2)), atol=1e-12)
     g = _fold(idx, O.conv3d_backprop_filter(xs, ws.shape, dy, (1, 2, 1)), wt.size)
     assert np.allclose(g, O.conv3d_backprop_filter(x, wt.shape, dy, (1, 2, 2)).ravel(), atol=1e-12)
-    assert not (idx.reshape(3, 3, 2 * cinp, coutp)[:, 0] >= 0).any()  # super tap S = -1 is empty
+    assert not (idx.reshape(3, 2, 2, cinp, coutp)[:, 1, 1] >= 0).any()   # voxel 2X + 3 is outside the 3-tap row
+
+
+def test_super_conv_over_the_concat_buffer():
+    """conv_d0/conv1 reads the level's concat buffer, 128 lanes per voxel pair: [enc even | enc odd | up even | up odd]."""
+    rng = np.random.default_rng(3)
+    n, d, h, w, half, coutp = 1, 2, 4, 8, 3, 2
+    enc, up = rng.standard_normal((n, d, h, w, half)), rng.standard_normal((n, d, h, w, half))
+    wt = rng.standard_normal((1, 3, 3, 2 * half, coutp))
+    idx = E._super_index(NS(pair="conv", catpair=True, cinp=2 * half, coutp=coutp))
+    ws = _super(idx, wt)
+    cat = np.concatenate((enc.reshape(n * d, h, w // 2, 2 * half), up.reshape(n * d, h, w // 2, 2 * half)), axis=-1)
+    ref = O.conv3d(np.concatenate((enc, up), axis=-1), wt)
+    assert np.allclose(O.conv2d(cat, ws).reshape(ref.shape), ref, atol=1e-12)
 
 
 def test_stem_block_diagonal():
