@@ -6,6 +6,7 @@
 // normalisation passes of the layer they modulate.
 #include "internal.h"
 #include "philox.cuh"
+#include <cuda_bf16.h>
 
 namespace {
 using bsl::philox4x32_10;
@@ -92,6 +93,26 @@ __global__ void avgpool2x2_f32_kernel(int n, int h, int w, int c, const float* _
   }
 }
 
+// UNetInter --mid_cat (NetworksV2/UNetInter.py:124-125): max_pool2d(concat(net, sp_guide), 2) -- the guide's share of the
+// pooled tensor, written as bf16 lanes [0, c) of y rows with stride y_ld (the activation lanes are written by the fused
+// norm + ReLU + pool pass). bf16 rounding is monotonic, so round(max) == max(round).
+__global__ void maxpool2x2_f32_bf16_kernel(int n, int h, int w, int c, const float* __restrict__ x,
+                                           __nv_bfloat16* __restrict__ y, int y_ld) {
+  bsl::pdl_enter();
+  const int ho = h / 2, wo = w / 2;
+  const long long total = (long long)n * ho * wo * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int ch = (int)(t % c); t /= c;
+    const int xo = (int)(t % wo); t /= wo;
+    const int yo = (int)(t % ho);
+    const int s = (int)(t / ho);
+    const float* p = x + (((long long)s * h + 2 * yo) * w + 2 * xo) * c + ch;
+    const float m = fmaxf(fmaxf(p[0], p[c]), fmaxf(p[(long long)w * c], p[(long long)w * c + c]));
+    y[(((long long)s * ho + yo) * wo + xo) * y_ld + ch] = __float2bfloat16_rn(m);
+  }
+}
+
 __global__ void dropout_mask_kernel(int total, bsl_dropout_desc dd, float* __restrict__ out) {
   bsl::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -175,6 +196,22 @@ int bsl_avgpool2x2_f32(bsl_ctx* ctx, int n, int h, int w, int c, const float* x,
   if (blocks > cap) blocks = cap;
   bsl_launch(avgpool2x2_f32_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), n, h, w, c, x, y);
   BSL_LAUNCH_CHECK(ctx, "avgpool2x2_f32_kernel");
+  return BSL_OK;
+}
+
+int bsl_maxpool2x2_f32_bf16(bsl_ctx* ctx, int n, int h, int w, int c, const float* x, void* y_bf16, int y_ld,
+                            void* stream) {
+  if (!ctx) return BSL_EINVAL;
+  if (!x || !y_bf16) return bsl_fail(ctx, BSL_EINVAL, "maxpool2x2_f32_bf16: null buffer");
+  if (n <= 0 || c <= 0 || h <= 0 || w <= 0 || (h & 1) || (w & 1) || y_ld < c)
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "maxpool2x2_f32_bf16: h=%d w=%d must be even, y_ld=%d >= c=%d", h, w, y_ld, c);
+  const long long total = (long long)n * (h / 2) * (w / 2) * c;
+  long long blocks = (total + 255) / 256;
+  const long long cap = 16LL * ctx->sm_count;
+  if (blocks > cap) blocks = cap;
+  bsl_launch(maxpool2x2_f32_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), n, h, w, c, x,
+             reinterpret_cast<__nv_bfloat16*>(y_bf16), y_ld);
+  BSL_LAUNCH_CHECK(ctx, "maxpool2x2_f32_bf16_kernel");
   return BSL_OK;
 }
 

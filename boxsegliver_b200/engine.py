@@ -92,6 +92,21 @@ class Param:
     size: int = 0
     alloc: int = 0           # elements reserved in the arena (>= size; the stem filter is padded to 64 x 64)
     region: str = "A"        # "A" regularised, "B" not, "S" moving statistics (not trained)
+    dev_shape: tuple = None  # stored shape when the input-channel axis is zero-padded to a 64-channel block (else `shape`)
+
+    def to_dev(self, a: np.ndarray) -> np.ndarray:
+        """TF-shaped variable -> flat stored layout (zero rows for the padded input channels)."""
+        if self.dev_shape is None:
+            return a.ravel()
+        out = np.zeros(self.dev_shape, np.float32)
+        out[:, :, :self.shape[2], :] = a
+        return out.ravel()
+
+    def from_dev(self, flat: np.ndarray) -> np.ndarray:
+        a = flat[self.offset:self.offset + self.size]
+        if self.dev_shape is None:
+            return a.reshape(self.shape).copy()
+        return a.reshape(self.dev_shape)[:, :, :self.shape[2], :].copy()
 
 
 @dataclass
@@ -103,6 +118,7 @@ class ConvL:
     h: int
     w: int                   # INPUT spatial size
     level: int
+    cin_dev: int = 0         # stored input channels when cin is not a multiple of 64 (UNetInter --mid_cat: 66 -> 128); 0 = cin
     role: str = ""           # enc1 | enc2 (pooled afterwards) | bridge1 | bridge2 | dec1 (reads the concat) | dec2
     center: bool = True      # normaliser has beta / gamma (GUNet's modulated blocks take them from the YAML)
     scale: bool = True
@@ -404,7 +420,8 @@ class UNetEngine:
         for L in self.layers:
             if L.kind in ("stem", "conv"):
                 plist.append(Param(f"{L.scope}/weights", (3, 3, L.cin, L.cout),
-                                   alloc=64 * L.cout if L.kind == "stem" else 0))
+                                   alloc=64 * L.cout if L.kind == "stem" else 0,
+                                   dev_shape=(3, 3, L.cin_dev, L.cout) if L.cin_dev else None))
                 if L.scale:
                     plist.append(Param(f"{L.scope}/{ns}/gamma", (L.cout,), region="B"))
                 if L.center:
@@ -423,7 +440,7 @@ class UNetEngine:
         for region in ("A", "B"):
             for p in plist:
                 if p.region == region:
-                    p.size = int(np.prod(p.shape))
+                    p.size = int(np.prod(p.dev_shape or p.shape))
                     p.offset = off
                     off += _align(max(p.size, p.alloc))
             if region == "A":
@@ -458,6 +475,13 @@ class UNetEngine:
     def _guide_channels(self, L: ConvL) -> int:
         return 0
 
+    def _pooled_lanes(self, L: ConvL) -> int:
+        """Channel stride of the pooled tensor behind an encoder block."""
+        return L.cout
+
+    def _after_pool(self, L: ConvL, stream):
+        """Hook behind the fused norm + ReLU + pool pass of an encoder block (UNetInter --mid_cat adds the guide lanes)."""
+
     def _norm_groups(self, L: ConvL, default: int) -> int:
         """Entries per channel of the layer's normalisation scalars (1 batch norm, n instance norm / modulated)."""
         return default
@@ -482,13 +506,18 @@ class UNetEngine:
                     cbuf = View(self._alloc(n * L.h * L.w * 2 * L.cout * BF16), n, L.h, L.w, 2 * L.cout)
                     cat[L.level] = cbuf
                     L.a = cbuf.slice(0, L.cout)
-                    L.pooled = View(self._alloc(n * (L.h // 2) * (L.w // 2) * L.cout * BF16), n, L.h // 2, L.w // 2,
-                                    L.cout)
+                    pl = self._pooled_lanes(L)      # > cout: extra lanes behind the activation's (UNetInter --mid_cat)
+                    pbuf = self._alloc(n * (L.h // 2) * (L.w // 2) * pl * BF16)
+                    if pl != L.cout:
+                        pbuf.zero()
+                    L.pooled = View(pbuf, n, L.h // 2, L.w // 2, L.cout, pl)
                 else:
                     L.a = View(self._alloc(n * L.h * L.w * L.cout * BF16), n, L.h, L.w, L.cout)
                 if L.kind == "conv":
                     L.x = cat[L.level] if L.role == "dec1" else prev_a
                 prev_a = L.pooled if is_enc2 else L.a
+                if is_enc2 and L.pooled.ld != L.cout:
+                    prev_a = View(L.pooled.buf, n, L.h // 2, L.w // 2, L.pooled.ld)
                 g = self._norm_groups(L, groups_max)
                 k = 2 + self._guide_channels(L)
                 L.norm = dict(groups=g, off=small, k=k)
@@ -565,7 +594,7 @@ class UNetEngine:
         k = 1 if L.kind == "logits" else 3
         x_ld = L.x.ld if L.x is not None else L.cin
         y_ld = L.y.ld if L.y is not None else L.cout
-        return _lib.Conv2dDesc(self.cfg.batch, L.h, L.w, L.cin, L.cout, k, k, x_ld, y_ld)
+        return _lib.Conv2dDesc(self.cfg.batch, L.h, L.w, L.cin_dev or L.cin, L.cout, k, k, x_ld, y_ld)
 
     def _convT_desc(self, L: ConvL):
         return _lib.ConvT2dDesc(self.cfg.batch, L.h, L.w, L.cin, L.cout, L.x.ld, L.a.ld, 1)
@@ -606,7 +635,7 @@ class UNetEngine:
             a = np.asarray(weights[name], np.float32)
             if tuple(a.shape) != tuple(p.shape):
                 raise ValueError(f"{name}: shape {a.shape} != {p.shape}")
-            (hostS if p.region == "S" else hostW)[p.offset:p.offset + p.size] = a.ravel()
+            (hostS if p.region == "S" else hostW)[p.offset:p.offset + p.size] = p.to_dev(a)
         self.W.upload(hostW)
         self.Wbf.upload(f32_to_bf16_bits(hostW))
         self.S.upload(hostS)
@@ -616,8 +645,7 @@ class UNetEngine:
         hostS = self.S.download(np.float32, (max(self.n_stats, 1),))
         out = {}
         for name, p in self.params.items():
-            src = hostS if p.region == "S" else hostW
-            out[name] = src[p.offset:p.offset + p.size].reshape(p.shape).copy()
+            out[name] = p.from_dev(hostS if p.region == "S" else hostW)
         return out
 
     def get_stored_forward(self) -> dict:
@@ -637,8 +665,7 @@ class UNetEngine:
 
     def get_grads(self) -> dict:
         hostG = self.G.download(np.float32, (self.n_train,))
-        return {name: hostG[p.offset:p.offset + p.size].reshape(p.shape).copy()
-                for name, p in self.params.items() if p.region != "S"}
+        return {name: p.from_dev(hostG) for name, p in self.params.items() if p.region != "S"}
 
     def get_slots(self) -> dict:
         """Optimizer slots in TF variable shapes: {variable name: (m, v)} for Adam / AdamW, {name: (acc,)} for Momentum."""
@@ -648,8 +675,7 @@ class UNetEngine:
         for name, p in self.params.items():
             if p.region == "S":
                 continue
-            sl = slice(p.offset, p.offset + p.size)
-            out[name] = tuple(a[sl].reshape(p.shape).copy() for a in ((m, v) if v is not None else (m,)))
+            out[name] = tuple(p.from_dev(a) for a in ((m, v) if v is not None else (m,)))
         return out
 
     def set_slots(self, slots: dict):
@@ -665,7 +691,7 @@ class UNetEngine:
                 a = np.asarray(a, np.float32)
                 if tuple(a.shape) != tuple(p.shape):
                     raise ValueError(f"{name}: slot shape {a.shape} != {p.shape}")
-                dst[p.offset:p.offset + p.size] = a.ravel()
+                dst[p.offset:p.offset + p.size] = p.to_dev(a)
         self.M.upload(m)
         if v is not None:
             self.V.upload(v)
@@ -799,6 +825,7 @@ class UNetEngine:
                 elif L.pooled is not None:
                     call("bsl_norm_apply_pool_mod_pipe", C.byref(nd), C.c_int(L.h), C.c_int(L.w), L.y.p, q["scale"],
                          q["shift"], gp, L.a.p, L.pooled.p, C.c_int(L.pooled.ld), sp, st)
+                    self._after_pool(L, st)
                 else:
                     call("bsl_norm_apply_mod_pipe", C.byref(nd), L.y.p, q["scale"], q["shift"], gp, L.a.p, sp, st)
                 if sig is not None:
@@ -923,7 +950,7 @@ class UNetEngine:
                     # `cur` is the gradient w.r.t. the POOLED tensor; merge MaxPoolGrad with the skip gradient
                     dc = self.dcat[L.level]
                     call("bsl_maxpool2x2_bwd_add", C.c_int(n), C.c_int(L.h), C.c_int(L.w), C.c_int(L.cout), L.a.p,
-                         C.c_int(L.a.ld), cur.p, C.c_int(L.cout), dc.p, C.c_int(dc.ld), alt.p, C.c_int(L.cout), s)
+                         C.c_int(L.a.ld), cur.p, C.c_int(L.pooled.ld), dc.p, C.c_int(dc.ld), alt.p, C.c_int(L.cout), s)
                     cur, alt = alt, cur
                 dyb = self.dyb[k]
                 nd = self._norm_desc(L)
@@ -976,7 +1003,7 @@ class UNetEngine:
                         else:
                             self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad_pipe", C.byref(dd), dyb.p, wbf, dc.p, wp, s)
                     else:
-                        dd.x_ld = L.cin
+                        dd.x_ld = L.cin_dev or L.cin
                         dst = alt if pipe_b else cur
                         self._tc("dgrad", self._flops(L), "bsl_conv2d_dgrad_pipe", C.byref(dd), dyb.p, wbf, dst.p, wp, s)
                         if pipe_b:

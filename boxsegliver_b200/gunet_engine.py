@@ -91,6 +91,8 @@ class GUNetEngine(UNetEngine):
                 L = ConvL(kind, f"{self.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/Conv", cin, c, h, w, i, role=role,
                           center=(cfg.norm_with_center and not aa) if mod else True,
                           scale=(cfg.norm_with_scale and not aa) if mod else True)
+                if cin % 64 and kind == "conv":      # UNetInter --mid_cat: 64 + guide_channel inputs, stored as 128 lanes
+                    L.cin_dev = _align(cin, 64)
                 if aa:
                     L.affine = f"{self.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/ChannelWiseAffine"
                 # batch norm: the encoder arg scope's decay 0.99 reaches GUNet's modulated blocks (the un-modulated ones
@@ -104,6 +106,8 @@ class GUNetEngine(UNetEngine):
                     L.sp_off = (j - 1) * c
                 specs.append(L)
                 cin = c
+            if i == 0 and getattr(cfg, "mid_cat", False):
+                cin = c + cfg.guide_channel          # UNetInter.py:124-125: concat(block output, sp_guide) is what gets pooled
             if i < nd:
                 c *= 2
                 h //= 2
@@ -380,23 +384,42 @@ class UNetInterConfig(GUNetConfig):
 class UNetInterEngine(GUNetEngine):
     """UNetInter = GUNet's variable layout (Encode/down_conv*/mod_conv*/Conv, Decode/up*, up_conv*) without modulation:
     every conv is conv -> norm(center, scale) -> ReLU, and the network input is concat(images, sp_guide)
-    (UNetInter.py:89-92). --mid_cat (guide re-concatenated after the first block: 66 input channels to the next
-    conv) is not a multiple of the tensor-core channel block and raises NotImplementedError."""
+    (UNetInter.py:89-92). With --mid_cat (UNetInter.py:87-92,124-125) the images alone enter the first block and the guide
+    is concatenated to its output in front of the first max-pool: the pooled tensor is stored with 128 lanes (64
+    activation lanes from the fused norm + ReLU + pool pass, guide_channel lanes from bsl_maxpool2x2_f32_bf16, zeros), and
+    the second block's first conv runs with its 64 + guide_channel input channels zero-padded to 128."""
     prefix = "UNetInter"
 
     def __init__(self, ctx, cfg: UNetInterConfig):
-        if cfg.mid_cat:
-            raise NotImplementedError("UNetInter --mid_cat is outside the accelerated path")
         if cfg.use_context or cfg.use_spatial or cfg.mod_layers:
             raise ValueError("UNetInter has no guide modulation: the guide is an input channel")
+        if cfg.mid_cat and cfg.init_channels % 64:
+            raise ValueError("--mid_cat: init_channels must be a multiple of 64 (the guide lanes follow a whole channel block)")
         self.image_channels = cfg.channel
         self.user_cfg = cfg
-        super().__init__(ctx, dataclasses.replace(cfg, channel=cfg.channel + cfg.guide_channel))
+        super().__init__(ctx, cfg if cfg.mid_cat else dataclasses.replace(cfg, channel=cfg.channel + cfg.guide_channel))
+        if cfg.mid_cat:
+            self.guide_in = self._alloc(cfg.batch * cfg.height * cfg.width * cfg.guide_channel * F32)
+
+    def _pooled_lanes(self, L: ConvL) -> int:
+        if self.cfg.mid_cat and L.level == 0:
+            return _align(L.cout + self.cfg.guide_channel, 64)
+        return L.cout
+
+    def _after_pool(self, L: ConvL, stream):
+        cfg = self.cfg
+        if cfg.mid_cat and L.level == 0:
+            self.ctx.call("bsl_maxpool2x2_f32_bf16", C.c_int(cfg.batch), C.c_int(L.h), C.c_int(L.w),
+                          C.c_int(cfg.guide_channel), self.guide_in.p, C.c_void_p(L.pooled.p.value + L.cout * BF16),
+                          C.c_int(L.pooled.ld), stream)
 
     def set_inputs(self, images: np.ndarray, labels: np.ndarray | None = None, sp_guide: np.ndarray | None = None,
                    stream=None):
         cfg = self.cfg
-        if images.shape[-1] == self.image_channels:
+        if cfg.mid_cat:
+            assert sp_guide is not None and sp_guide.shape == images.shape[:3] + (cfg.guide_channel,), "sp_guide"
+            self.guide_in.upload(np.ascontiguousarray(sp_guide, np.float32), stream)
+        elif images.shape[-1] == self.image_channels:
             assert sp_guide is not None and sp_guide.shape == images.shape[:3] + (cfg.guide_channel,), "sp_guide"
             images = np.concatenate((images, sp_guide), axis=-1)          # UNetInter.py:90
         super().set_inputs(images, labels, stream)

@@ -1,6 +1,6 @@
 """`UNetInter` with the reference's constructor / call contract (/root/reference/NetworksV2/UNetInter.py:30-209) on the
 sm_100a engine: `model(inputs, mode, **yaml)` with inputs {images, sp_guide, labels}; the click guide enters as extra
-input channels (UNetInter.py:89-90)."""
+input channels (UNetInter.py:89-90), or -- with --mid_cat -- in front of the first max-pool (UNetInter.py:124-125)."""
 from __future__ import annotations
 
 import numpy as np
@@ -17,7 +17,7 @@ class UNetInter(UNet):
         self.use_spatial_guide = getattr(args, "use_spatial", False)        # UNetInter.py:41
 
     def _build_network(self, *args, **kwargs):
-        for flag in ("img_grad", "without_norm", "mid_cat"):
+        for flag in ("img_grad", "without_norm"):
             if getattr(self.args, flag, False):
                 raise NotImplementedError(f"--{flag} is outside the accelerated path")
         if self.ctx is None:
@@ -36,7 +36,8 @@ class UNetInter(UNet):
             loss_proportion_decay=getattr(self.args, "loss_proportion_decay", 1000.0),
             **engine_optimizer_kwargs(self.args), weight_init=self._get_initializer(),
             training=self.mode == ModeKeys.TRAIN, world=getattr(self, "world", 1),
-            guide_channel=getattr(self.args, "guide_channel", 2), dropout_seed=getattr(self.args, "seed", 0))
+            guide_channel=getattr(self.args, "guide_channel", 2), dropout_seed=getattr(self.args, "seed", 0),
+            mid_cat=bool(getattr(self.args, "mid_cat", False)))
         if self.engine is None or self.engine.user_cfg != cfg:
             if self.engine is not None:
                 self.engine.close()

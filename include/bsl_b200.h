@@ -427,6 +427,10 @@ int bsl_fc_bwd(bsl_ctx* ctx, const bsl_fc_desc* d, const float* x, const float* 
 /* out[i] = 1 / keep_prob or 0: the dropout multipliers themselves (tests, and backbone --dropout). */
 int bsl_dropout_mask(bsl_ctx* ctx, const bsl_dropout_desc* d, size_t n, float* out, void* stream);
 int bsl_avgpool2x2_f32(bsl_ctx* ctx, int n, int h, int w, int c, const float* x, float* y, void* stream);
+/* UNetInter --mid_cat (NetworksV2/UNetInter.py:124-125, slim.max_pool2d(concat(net, sp_guide), 2)): the guide's share of
+ * the pooled tensor, y_bf16[pixel * y_ld + ch] = bf16(max of the 2x2 window of x[n,h,w,c]), ch < c. */
+int bsl_maxpool2x2_f32_bf16(bsl_ctx* ctx, int n, int h, int w, int c, const float* x, void* y_bf16, int y_ld,
+                            void* stream);
 
 /* MaxPoolGrad (first maximum in scan order wins ties) fused with the skip-connection add:
  * dact = dskip (nullable) + unpool(dpool). */

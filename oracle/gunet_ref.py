@@ -52,6 +52,8 @@ class GUNetCfg:
     bn_eps: float = 1e-3                 # slim.batch_norm default epsilon
     prefix: str = "GUNet"                # "UNetInter": same variable layout, no modulation, guide concatenated to the
                                          # images at the input (/root/reference/NetworksV2/UNetInter.py:89-92,118-146)
+    mid_cat: bool = False                # UNetInter --mid_cat (UNetInter.py:87-92,124-125): the guide is NOT an input channel;
+                                         # it is concatenated to the first block's output in front of the first max-pool
 
     @property
     def num_classes(self):
@@ -62,16 +64,19 @@ class GUNetCfg:
         return self.init_channels * sum(2 ** i for i in range(self.num_down_samples + 1) if i in self.mod_layers) * 2
 
 
-def unetinter_cfg(channel: int = 3, guide_channel: int = 2, **kw) -> GUNetCfg:
+def unetinter_cfg(channel: int = 3, guide_channel: int = 2, mid_cat: bool = False, **kw) -> GUNetCfg:
     """UNetInter (/root/reference/NetworksV2/UNetInter.py:73-146) expressed on the GUNet restatement: scope root
     "UNetInter", no modulated block, every conv followed by norm(center, scale) + ReLU (encoder_arg_scope, :100-117),
-    and `channel + guide_channel` network input channels (the guide is concatenated to the images, :89-90)."""
-    return GUNetCfg(channel=channel + guide_channel, guide_channel=guide_channel, prefix="UNetInter", use_context=False,
-                    use_spatial=False, mod_layers=(), **kw)
+    and `channel + guide_channel` network input channels (the guide is concatenated to the images, :89-90) -- or, with
+    --mid_cat, `channel` input channels and the guide concatenated in front of the first max-pool (:124-125)."""
+    return GUNetCfg(channel=channel if mid_cat else channel + guide_channel, guide_channel=guide_channel,
+                    prefix="UNetInter", use_context=False, use_spatial=False, mod_layers=(), mid_cat=mid_cat, **kw)
 
 
-def unetinter_inputs(images: np.ndarray, sp_guide: np.ndarray) -> dict:
-    """tf.concat((images, sp_guide), axis=-1) -- UNetInter.py:90."""
+def unetinter_inputs(images: np.ndarray, sp_guide: np.ndarray, mid_cat: bool = False) -> dict:
+    """tf.concat((images, sp_guide), axis=-1) -- UNetInter.py:90; with --mid_cat the guide stays a separate input."""
+    if mid_cat:
+        return dict(images=images, sp_guide=sp_guide)
     return dict(images=np.concatenate((images, sp_guide), axis=-1))
 
 
@@ -106,6 +111,8 @@ def layer_specs(cfg: GUNetCfg):
                 s["sp_off"] = (j - 1) * c
             specs.append(s)
             cin = c
+        if i == 0 and cfg.mid_cat:
+            cin = c + cfg.guide_channel         # the pooled concat(block output, sp_guide) feeds the second block
         if i < cfg.num_down_samples:
             c *= 2
     for i in reversed(range(cfg.num_down_samples)):
@@ -310,7 +317,10 @@ def forward(params: dict, inputs: dict, cfg: GUNetCfg, is_training: bool, rnd=_i
             first = False
         if i < cfg.num_down_samples:
             skips.append(x)
-            tape.layers.append(dict(kind="pool", x=x))
+            keep = x.shape[-1]
+            if cfg.mid_cat and i == 0:      # UNetInter.py:124-125: only the pooled branch sees the guide
+                x = np.concatenate((x, rnd(inputs["sp_guide"].astype(dt)).astype(dt)), axis=-1)
+            tape.layers.append(dict(kind="pool", x=x, keep=keep))
             x = O.max_pool_2x2(x)
     for i in reversed(range(cfg.num_down_samples)):
         s = next(it)
@@ -411,7 +421,7 @@ def backward(tape: Tape, dlogits: np.ndarray, cfg: GUNetCfg, rnd=_identity) -> d
             d = rnd(dx).astype(dt)
         elif k == "pool":
             level = max(skip_grads)
-            d = rnd(O.max_pool_2x2_grad(L["x"], d) + skip_grads.pop(level)).astype(dt)
+            d = rnd(O.max_pool_2x2_grad(L["x"], d)[..., :L["keep"]] + skip_grads.pop(level)).astype(dt)
     if dctx is not None:
         grads.update(fc_backward(tape, dctx))
     tape.dctx = dctx

@@ -164,13 +164,15 @@ def test_gunet_train_step_parity(ctx, n, hw, kw):
     assert e_fc_end_to_end < 3e-2
 
 
-def test_unetinter_train_step_parity(ctx):
+@pytest.mark.parametrize("mid_cat", [False, True])
+def test_unetinter_train_step_parity(ctx, mid_cat):
     """UNetInter (/root/reference/NetworksV2/UNetInter.py:73-146): image + 2-channel click guide as a 5-channel
-    input, variables under "UNetInter/", no modulation; same gates as the GUNet parity test."""
+    input, variables under "UNetInter/", no modulation; same gates as the GUNet parity test. --mid_cat (:87-92,124-125):
+    the guide joins the first block's output in front of the first max-pool (66 -> 128 channel conv, stored 128 -> 128)."""
     from boxsegliver_b200.gunet_engine import UNetInterConfig, UNetInterEngine
     n, hw = 2, 64
     base = dict(height=hw, width=hw, init_channels=64, num_down_samples=4, weight_decay_rate=1e-5,
-                loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4), loss_type="xentropy+dice")
+                loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4), loss_type="xentropy+dice", mid_cat=mid_cat)
     ecfg = UNetInterConfig(batch=n, channel=3, guide_channel=2, **base)
     rcfg = G.unetinter_cfg(channel=3, guide_channel=2, **base)
     images, labels = synthetic.make_batch(n, hw, hw, 3, seed=1377)
@@ -199,7 +201,9 @@ def test_unetinter_train_step_parity(ctx):
     ctx.check_device()
     data_loss, reg_loss = eng.read_loss()
     eng.close()
-    rin = {k_: round_bf16(v).astype(np.float64) for k_, v in G.unetinter_inputs(images, guide).items()}
+    rin = {k_: round_bf16(v).astype(np.float64) for k_, v in G.unetinter_inputs(images, guide, mid_cat).items()}
+    if mid_cat:
+        assert params["UNetInter/Encode/down_conv2/mod_conv1/Conv/weights"].shape == (3, 3, 66, 128)
     tft = G.forward({k_: v.astype(np.float64) for k_, v in params.items()}, rin, rcfg, True, wrnd=round_bf16,
                     stored=stored)
     assert max(tft.errs.values()) < 1e-2, max(tft.errs.items(), key=lambda t: t[1])
@@ -211,6 +215,6 @@ def test_unetinter_train_step_parity(ctx):
     errs = {name: rel(grads[name], g) for name, g in g_ref.items()}
     assert set(g_ref) == set(grads)
     worst = max(errs.items(), key=lambda t: t[1])
-    report("unetinter step", layer_worst=max(tft.errs.values()), grad_median=float(np.median(list(errs.values()))),
+    report("unetinter step" + (" mid_cat" if mid_cat else ""), layer_worst=max(tft.errs.values()), grad_median=float(np.median(list(errs.values()))),
            grad_worst=worst[1], grad_worst_name=worst[0])
     gate_gradients(errs)

@@ -84,6 +84,14 @@ def test_unetinter_through_model_fn(ctx):
            loss_type="xentropy+dice", mid_cat=False)
 
 
+def test_unetinter_mid_cat_through_model_fn(ctx):
+    """--mid_cat as in run_scripts/template: the guide joins the first block's output in front of the first max-pool."""
+    def feed(images, labels):
+        return dict(sp_guide=synthetic.make_guides(images, labels, 200, 2, seed=1)[1])
+    _drive(ctx, "UNetInter", feed, normalizer="instance_norm", use_spatial=True, guide_channel=2,
+           loss_type="xentropy+dice", mid_cat=True)
+
+
 def test_gunet_through_model_fn(ctx):
     def feed(images, labels):
         c, g = synthetic.make_guides(images, labels, 200, 1, seed=1)
@@ -93,10 +101,10 @@ def test_gunet_through_model_fn(ctx):
 
 
 def test_unsupported_flags_raise(ctx):
-    args = _args("UNetInter", normalizer="instance_norm", mid_cat=True)
+    args = _args("UNetInter", normalizer="instance_norm", img_grad=True)
     params = models.get_model_params(args)
     params.update(args=args, solver=solver.Solver, ctx=ctx, world=1)
-    with pytest.raises(NotImplementedError, match="mid_cat"):
+    with pytest.raises(NotImplementedError, match="img_grad"):
         models.model_fn(dict(images=None), None, ModeKeys.TRAIN, params)
 
 

@@ -87,6 +87,8 @@ def _torch_gunet(params, inputs, labels, cfg, mults):
         x = conv(conv(x, next(it)), next(it))
         if i < cfg.num_down_samples:
             skips.append(x)
+            if getattr(cfg, "mid_cat", False) and i == 0:
+                x = torch.cat((x, t(inputs["sp_guide"]).permute(0, 3, 1, 2)), dim=1)
             x = F.max_pool2d(x, 2)
     for i in reversed(range(cfg.num_down_samples)):
         s = next(it)
@@ -178,6 +180,35 @@ def test_unetinter_oracle_matches_torch_autograd():
     assert "UNetInter/Encode/down_conv3/mod_conv2/Conv/InstanceNorm/gamma" in params
     assert "UNetInter/Decode/up2/biases" in params and "UNetInter/AdjustChannels/biases" in params
     assert not any("context" in k or "spatial" in k for k in params)
+    tape = G.forward(params, inputs, cfg, True)
+    loss, dl = G.loss_and_dlogits(tape, labels, cfg)
+    grads = G.backward(tape, dl, cfg)
+    t_logits, t_loss, t_grads = _torch_gunet(params, inputs, labels, cfg, None)
+    assert np.allclose(tape.logits, t_logits, rtol=1e-9, atol=1e-10)
+    assert abs(loss - t_loss) < 1e-10
+    assert set(grads) == set(params)
+    for k, g in grads.items():
+        assert np.allclose(g, t_grads[k], rtol=1e-7, atol=1e-10), k
+
+
+def test_unetinter_mid_cat_oracle_matches_torch_autograd():
+    """--mid_cat (/root/reference/NetworksV2/UNetInter.py:87-92,124-125): the images alone enter the first block; the guide
+    is concatenated to its output in front of the first max-pool only (the skip connection keeps the block's channels),
+    so the second block's first conv has init_channels + guide_channel inputs."""
+    cfg = G.unetinter_cfg(channel=3, guide_channel=2, mid_cat=True, height=16, width=16, init_channels=4,
+                          num_down_samples=2, loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4),
+                          weight_decay_rate=0.0, loss_type="xentropy")
+    rng = np.random.default_rng(9)
+    n = 2
+    images, guide = rng.uniform(0, 1, (n, 16, 16, 3)), rng.uniform(0, 1, (n, 16, 16, 2))
+    labels = rng.integers(0, 3, (n, 16, 16)).astype(np.int32)
+    inputs = G.unetinter_inputs(images, guide, mid_cat=True)
+    assert inputs["images"].shape == (n, 16, 16, 3)
+    params = {k: v.astype(np.float64) + (0.1 * rng.standard_normal(v.shape) if k.endswith(("beta", "gamma", "biases")) else 0)
+              for k, v in G.init_params(cfg, seed=2, dtype=np.float64).items()}
+    assert params["UNetInter/Encode/down_conv1/mod_conv1/Conv/weights"].shape == (3, 3, 3, 4)
+    assert params["UNetInter/Encode/down_conv2/mod_conv1/Conv/weights"].shape == (3, 3, 4 + 2, 8)
+    assert params["UNetInter/Decode/up_conv1/up_conv1_1/weights"].shape == (3, 3, 8, 4)     # the skip has no guide lanes
     tape = G.forward(params, inputs, cfg, True)
     loss, dl = G.loss_and_dlogits(tape, labels, cfg)
     grads = G.backward(tape, dl, cfg)
