@@ -1226,6 +1226,93 @@ int bsl_conv3d_halo_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy
              : launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
 }
 
+// dgrad of a layer with stride 2 along H and / or W (stride 1 along D): one launch of the halo-tile kernel per output
+// phase (parity class of the input coordinate). Within a phase, dx[s * u' + phase] = sum over the taps r with
+// (phase + pad - r) % s == 0 of dy[u' + (phase + pad - r) / s] w[r]: a stride-1 correlation over dy whose offsets lie in
+// {-1, 0, +1}, i.e. inside the 1-pixel halo of the box the kernel loads anyway, written to the strided positions of dx.
+namespace {
+struct PhaseTaps {
+  int cnt, r[3], off[3];
+};
+PhaseTaps phase_taps(int in, int k, int s, int phase) {
+  const int out = (in + s - 1) / s;
+  const int pad = std::max((out - 1) * s + k - in, 0) / 2;
+  PhaseTaps t = {};
+  for (int r = 0; r < k; ++r) {
+    const int v = phase + pad - r;
+    if (((v % s) + s) % s) continue;
+    t.r[t.cnt] = r;
+    t.off[t.cnt] = (v >= 0 ? v : v - (s - 1)) / s;
+    ++t.cnt;
+  }
+  return t;
+}
+}  // namespace
+
+bool bsl_conv3d_halo_dgrad_strided_ok(const bsl_conv3d_desc* d) {
+  if (force_v1() || d->sd != 1 || !(d->kd == 1 || d->kd == 3) || (d->sh == 1 && d->sw == 1)) return false;
+  if (d->kh < 2 || d->kh > 3 || d->kw < 2 || d->kw > 3 || d->h % d->sh || d->w % d->sw) return false;
+  if (!halo_eligible(d->w / d->sw, d->h / d->sh)) return false;
+  for (int ph = 0; ph < d->sh; ++ph)
+    for (int pw = 0; pw < d->sw; ++pw) {
+      const PhaseTaps th = phase_taps(d->h, d->kh, d->sh, ph), tw = phase_taps(d->w, d->kw, d->sw, pw);
+      if (th.cnt == 0 || tw.cnt == 0) return false;
+      for (int i = 0; i < th.cnt; ++i)
+        if (th.off[i] < -1 || th.off[i] > 1) return false;
+      for (int i = 0; i < tw.cnt; ++i)
+        if (tw.off[i] < -1 || tw.off[i] > 1) return false;
+    }
+  return true;
+}
+
+int bsl_conv3d_halo_dgrad_strided(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy, const void* w, void* dx,
+                                  cudaStream_t stream) {
+  const int pw_ = d->w / d->sw, ph_ = d->h / d->sh;          // phase grid = output grid (extents divide the strides)
+  int rc;
+  CUtensorMap ta;
+  if ((rc = ndhwc_halo_map(ctx, dy, d->cout, pw_, ph_, d->d, d->n, d->y_ld, 10, 18, &ta))) return rc;
+  for (int ph = 0; ph < d->sh; ++ph)
+    for (int pw = 0; pw < d->sw; ++pw) {
+      const PhaseTaps th = phase_taps(d->h, d->kh, d->sh, ph), tw = phase_taps(d->w, d->kw, d->sw, pw);
+      HaloPlan pl = plan_halo(ctx, pw_, ph_, d->n * d->d, d->cin);
+      const int ntaps = th.cnt * tw.cnt;
+      int res_stages = 0, res_smem = 0;
+      const bool res = plan_resident(pl.bn, ntaps * d->kd, d->cout / 64, &pl.nsub, &res_stages, &res_smem);
+      if (res) replan_units(ctx, pl);
+      CUtensorMap tb;
+      if ((rc = matrix_map(ctx, w, d->cout, d->kd * d->kh * d->kw * d->cin, 64, pl.bn, &tb))) return rc;
+      ConvHaloArgs a = {};
+      halo_common(a, pl, pw_, ph_, d->n * d->d);
+      a.ntaps = ntaps;
+      a.halo = 1;
+      a.cblocks = d->cout / 64;
+      a.kd = d->kd;
+      a.depth = d->d;
+      a.b_rows_per_tap = d->cin;
+      a.tap_table = 1;
+      for (int i = 0; i < th.cnt; ++i)
+        for (int j = 0; j < tw.cnt; ++j) {
+          const int t = i * tw.cnt + j;
+          a.tap_off[t] = ((th.off[i] + 1) * 10 + (tw.off[j] + 1)) * 128;
+          // slice z + kdi - (kd >> 1) of dy meets filter depth tap q = kd - 1 - kdi (stride 1, SAME)
+          for (int kdi = 0; kdi < d->kd; ++kdi)
+            a.tap_b[kdi * ntaps + t] = (signed char)(((d->kd - 1 - kdi) * d->kh + th.r[i]) * d->kw + tw.r[j]);
+        }
+      a.out = reinterpret_cast<__nv_bfloat16*>(dx) + (long long)pw * d->x_ld + (long long)ph * d->w * d->x_ld;
+      a.ostride_x = (long long)d->sw * d->x_ld;
+      a.ostride_y = (long long)d->sh * d->w * d->x_ld;
+      a.ostride_n = (long long)d->h * d->w * d->x_ld;
+      a.n_group = d->cin;
+      a.n_total = d->cin;
+      a.a_stages = res_stages;
+      a.status = ctx->d_status;
+      rc = res ? launch_halo_res<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
+               : launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+      if (rc) return rc;
+    }
+  return BSL_OK;
+}
+
 bool bsl_conv3d_halo_wgrad_ok(const bsl_conv3d_desc* d) {
   return !force_v1() && d3_stride1(d) && d->w % WG_TW == 0 && d->h % WG_TH == 0;
 }

@@ -389,6 +389,12 @@ struct ConvHaloArgs {
   //      activation stored at the same (pixel, column) of `relu_mask` (same strides as `out`) is not positive
   const void* relu_mask;
   int mask_col0;
+  // ---- optional per-tap tables (tap_table != 0): one output phase of a STRIDED layer's dgrad is a stride-1 correlation
+  //      over dy with a subset of the filter taps -- tap t reads the halo tile at byte offset tap_off[t] and the filter
+  //      tap tap_b[kdi * ntaps + t] (conv3d.cu / bsl_conv3d_halo_dgrad_strided)
+  int tap_table;
+  int tap_off[9];
+  signed char tap_b[27];
   DeviceStatus* status;
 };
 
@@ -629,7 +635,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int tap = 0; tap < p.ntaps; ++tap) {
             const uint32_t sb = sB0 + (cbx * p.ntaps + tap) * B_BYTES;
             const int kdi = cbx / p.cblocks, cb = cbx - kdi * p.cblocks;
-            const int tapb = p.b_flip ? (p.kd * p.ntaps - 1 - (kdi * p.ntaps + tap)) : kdi * p.ntaps + tap;
+            const int tapb = p.tap_table ? p.tap_b[kdi * p.ntaps + tap]
+                                         : (p.b_flip ? (p.kd * p.ntaps - 1 - (kdi * p.ntaps + tap)) : kdi * p.ntaps + tap);
             if (B_MN) {
               const int krow = (tapb * p.cblocks + cb) * 64;
 #pragma unroll
@@ -652,7 +659,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t fb = b_full + 8 * stage;
             const uint32_t sb = sB0 + stage * B_BYTES;
             mbar_arrive_expect_tx(fb, B_BYTES);
-            const int tapb = p.b_flip ? (p.kd * p.ntaps - 1 - (kdi * p.ntaps + tap)) : kdi * p.ntaps + tap;
+            const int tapb = p.tap_table ? p.tap_b[kdi * p.ntaps + tap]
+                                         : (p.b_flip ? (p.kd * p.ntaps - 1 - (kdi * p.ntaps + tap)) : kdi * p.ntaps + tap);
             if (B_MN) {
               const int krow = (tapb * p.cblocks + cb) * 64;
 #pragma unroll
@@ -698,7 +706,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tc_fence_after();
             }
             const uint32_t b_stage = B_RES ? sB0 + (cb * p.ntaps + tap) * B_BYTES : sB0 + sb * B_BYTES;
-            const int toff = p.halo ? ((tap / 3) * box_w + tap % 3) * 128 : 0;
+            const int toff = p.tap_table ? p.tap_off[tap] : (p.halo ? ((tap / 3) * box_w + tap % 3) * 128 : 0);
             // descriptors differ only in the 14-bit start-address field: one add per operand per UMMA
             const uint64_t da0 = make_smem_desc_sw128(a_stage + toff, 16, a_sbo);
             const uint64_t db0 = B_MN ? make_smem_desc_sw128(b_stage, 8192, 1024) : make_smem_desc_sw128(b_stage, 16, 1024);

@@ -97,6 +97,9 @@ int bsl_stats_bf16(bsl_ctx* ctx, const void* x, long long pixels_per_group, int 
 
 // (3,3,3) / (1,3,3) stride-1 layers on the halo-tile kernels (conv.cu), used by conv3d.cu when the shape allows.
 bool bsl_conv3d_halo_ok(const bsl_conv3d_desc* d);
+bool bsl_conv3d_halo_dgrad_strided_ok(const bsl_conv3d_desc* d);
+int bsl_conv3d_halo_dgrad_strided(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy, const void* w, void* dx,
+                                  cudaStream_t s);
 int bsl_conv3d_halo_fprop(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x, const void* w, void* y, cudaStream_t s,
                           double* sums = nullptr);
 int bsl_conv3d_halo_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy, const void* w, void* dx, cudaStream_t s);

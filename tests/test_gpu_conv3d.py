@@ -28,6 +28,11 @@ CASES = [  # (n, d, h, w, cin, cout, kernel, stride)
     # the strided conv that leaves the pixel-pair packed level: super voxels along W (stride 1 there), stride 2 along H
     (2, 4, 32, 16, 128, 64, (1, 3, 3), (1, 2, 1)),
     (2, 4, 32, 16, 64, 64, (1, 3, 2), (1, 2, 1)),      # ... as the engine runs it: 2-tap rows (super voxels X, X + 1)
+    # strided layers whose output grid tiles into 8x16 boxes: dgrad = one halo-tile launch per output phase (tap tables)
+    (1, 3, 32, 32, 64, 128, (3, 3, 3), (1, 2, 2)),     # conv_e2/conv1: 4 phases, depth loop
+    (2, 2, 64, 16, 64, 64, (1, 3, 2), (1, 2, 1)),      # conv_e1/conv1 on the pair-packed level: 2 phases
+    (1, 2, 32, 16, 128, 64, (1, 3, 3), (1, 2, 2)),     # resident filter, two reduction blocks
+    (1, 3, 32, 32, 128, 256, (3, 3, 3), (1, 2, 2)),    # conv_e3/conv1: cout 256
 ]
 
 
