@@ -113,6 +113,44 @@ __global__ void maxpool2x2_f32_bf16_kernel(int n, int h, int w, int c, const flo
   }
 }
 
+// Backbone --dropout of GUNet (slim.dropout between normaliser and modulation, NetworksV2/GUNet.py:189-190) and its
+// gradient (the same multiplication): out[p][ch] = bf16(x[p][ch] * multiplier(p * c + ch)), 8 channels per thread = two
+// Philox counters (flat element index over the dense [pixels, c] tensor, as bsl_dropout_mask enumerates it).
+__global__ void dropout_bf16_kernel(long long pixels, int c, bsl_dropout_desc dd, const __nv_bfloat16* __restrict__ x,
+                                    int x_ld, __nv_bfloat16* __restrict__ out, int o_ld) {
+  bsl::pdl_enter();
+  const int cg = c / 8;
+  const long long total = pixels * cg;
+  const float inv = 1.0f / dd.keep_prob;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / cg;
+    const int ch0 = (int)(i - p * cg) * 8;
+    const unsigned long long idx = (unsigned long long)p * c + ch0;      // multiple of 8
+    const uint4 raw = *reinterpret_cast<const uint4*>(x + p * x_ld + ch0);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    uint4 res;
+    __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(&res);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const unsigned long long blk = (idx >> 2) + q;
+      const uint4 r = philox4x32_10(make_uint4((unsigned)blk, (unsigned)(blk >> 32), (unsigned)dd.offset,
+                                               (unsigned)(dd.offset >> 32)),
+                                    make_uint2((unsigned)dd.seed, (unsigned)(dd.seed >> 32)));
+      const unsigned bits[4] = {r.x, r.y, r.z, r.w};
+      float m[4];
+#pragma unroll
+      for (int l = 0; l < 4; ++l) {
+        const float u = __uint_as_float((bits[l] & 0x7fffffu) | 0x3f800000u) - 1.0f;
+        m[l] = floorf(dd.keep_prob + u) >= 1.0f ? inv : 0.0f;
+      }
+      const float2 a = __bfloat1622float2(h[2 * q]), b = __bfloat1622float2(h[2 * q + 1]);
+      o[2 * q] = __floats2bfloat162_rn(a.x * m[0], a.y * m[1]);
+      o[2 * q + 1] = __floats2bfloat162_rn(b.x * m[2], b.y * m[3]);
+    }
+    *reinterpret_cast<uint4*>(out + p * o_ld + ch0) = res;
+  }
+}
+
 __global__ void dropout_mask_kernel(int total, bsl_dropout_desc dd, float* __restrict__ out) {
   bsl::pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -196,6 +234,23 @@ int bsl_avgpool2x2_f32(bsl_ctx* ctx, int n, int h, int w, int c, const float* x,
   if (blocks > cap) blocks = cap;
   bsl_launch(avgpool2x2_f32_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), n, h, w, c, x, y);
   BSL_LAUNCH_CHECK(ctx, "avgpool2x2_f32_kernel");
+  return BSL_OK;
+}
+
+int bsl_dropout_bf16(bsl_ctx* ctx, const bsl_dropout_desc* d, long long pixels, int c, const void* x_bf16, int x_ld,
+                     void* out_bf16, int out_ld, void* stream) {
+  if (!ctx) return BSL_EINVAL;
+  if (!d || !x_bf16 || !out_bf16) return bsl_fail(ctx, BSL_EINVAL, "dropout_bf16: null argument");
+  if (!(d->keep_prob > 0.f && d->keep_prob <= 1.f)) return bsl_fail(ctx, BSL_EINVAL, "dropout_bf16: keep_prob %f outside (0, 1]", d->keep_prob);
+  if (pixels <= 0 || c <= 0 || c % 8 || x_ld < c || out_ld < c || x_ld % 8 || out_ld % 8)
+    return bsl_fail(ctx, BSL_EUNSUPPORTED, "dropout_bf16: c=%d (multiple of 8), strides %d / %d", c, x_ld, out_ld);
+  const long long total = pixels * (c / 8);
+  long long blocks = (total + 255) / 256;
+  const long long cap = 16LL * ctx->sm_count;
+  if (blocks > cap) blocks = cap;
+  bsl_launch(dropout_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), pixels, c, *d,
+             reinterpret_cast<const __nv_bfloat16*>(x_bf16), x_ld, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_ld);
+  BSL_LAUNCH_CHECK(ctx, "dropout_bf16_kernel");
   return BSL_OK;
 }
 

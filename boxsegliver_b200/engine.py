@@ -801,6 +801,7 @@ class UNetEngine:
                 call("bsl_norm_finalize", C.byref(nd), C.c_int(1 if is_training else 0), q["sums"],
                      self._pp(self.W, f"{L.scope}/{ns}/gamma"), self._pp(self.W, f"{L.scope}/{ns}/beta"), mm, mv,
                      q["mean"], q["rstd"], q["scale"], q["shift"], s)
+                src = self._dropout_stage(L, nd, q, is_training)   # GUNet --dropout: a dropped copy of the normalised tensor
                 guide = self._modulate(L, nd, q)   # GUNet: folds gamma_mod / guide bias into scale, shift
                 nd = self._apply_desc(L, nd)
                 gp = C.byref(guide) if guide is not None else None
@@ -818,16 +819,16 @@ class UNetEngine:
                 if (self._fuse_head and nxt is not None and nxt.kind == "logits" and gp is None and L.pooled is None
                         and cg <= 32 and cg & (cg - 1) == 0 and 2 <= self.cfg.num_classes <= 4):
                     # last normalised layer: the logits come out of the same pass (no second read of the activation)
-                    call("bsl_norm_apply_head", C.byref(nd), L.y.p, q["scale"], q["shift"], L.a.p,
+                    call("bsl_norm_apply_head", C.byref(nd), src, q["scale"], q["shift"], L.a.p,
                          self._pp(self.W, f"{nxt.scope}/weights"), self._pp(self.W, f"{nxt.scope}/biases"),
                          C.c_int(self.cfg.num_classes), self.logits.p, s)
                     self._head_done = True
                 elif L.pooled is not None:
-                    call("bsl_norm_apply_pool_mod_pipe", C.byref(nd), C.c_int(L.h), C.c_int(L.w), L.y.p, q["scale"],
+                    call("bsl_norm_apply_pool_mod_pipe", C.byref(nd), C.c_int(L.h), C.c_int(L.w), src, q["scale"],
                          q["shift"], gp, L.a.p, L.pooled.p, C.c_int(L.pooled.ld), sp, st)
                     self._after_pool(L, st)
                 else:
-                    call("bsl_norm_apply_mod_pipe", C.byref(nd), L.y.p, q["scale"], q["shift"], gp, L.a.p, sp, st)
+                    call("bsl_norm_apply_mod_pipe", C.byref(nd), src, q["scale"], q["shift"], gp, L.a.p, sp, st)
                 if sig is not None:
                     ev = self._next_event()
                     ctx.record(ev, st)
@@ -847,6 +848,11 @@ class UNetEngine:
     def _modulate(self, L: ConvL, nd, q):
         """Hook between norm_finalize and norm_apply; returns the bsl_guide of the layer (or None)."""
         return None
+
+    def _dropout_stage(self, L: ConvL, nd, q, is_training: bool):
+        """Hook behind norm_finalize: the tensor the apply pass reads (GUNet's backbone --dropout substitutes a dropped
+        copy of the normalised conv output and turns (scale, shift) into the identity)."""
+        return L.y.p
 
     def _is_modulated(self, L: ConvL) -> bool:
         return False

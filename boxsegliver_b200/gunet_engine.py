@@ -11,8 +11,11 @@ hidden layers); the additive map is the level's 1x1 guide convolution (GUNet.py:
 the normalisation kernels, so modulation adds no pass over the activations. `after_affine` (5 of the 13 shipped
 ext_config/*.yml; slim_nets.channel_wise_affine before every encoder ReLU, GUNet.py:213-214) folds into the same
 per-(sample, channel) scale / shift and a gamma-scaled copy of the guide filter (bsl_norm_affine_fold): no extra pass.
-Scope: instance_norm (what every shipped GUNet script uses), context_model "fc"; --use_se, --fix, --without_norm,
---dropout, --img_grad and ct_conv raise NotImplementedError.
+Backbone `--dropout` (GUNet.py:189-190: slim.dropout behind the normaliser of the first conv of every encoder block, in
+front of the modulation; no shipped script enables it) runs un-fused: normalise without ReLU into a bf16 copy, multiply it
+by the Philox mask in place (bsl_dropout_bf16), then the ordinary modulated apply pass over that copy with an identity
+normaliser; backward mirrors the three stages.
+Scope: context_model "fc"; --use_se, --fix, --without_norm, --img_grad and ct_conv raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -59,15 +62,21 @@ class GUNetEngine(UNetEngine):
     def __init__(self, ctx, cfg: GUNetConfig):
         if cfg.normalizer == "batch_norm" and getattr(cfg, "after_affine", False):
             raise NotImplementedError("GUNet engine: after_affine with --normalizer batch_norm is not supported")
-        for flag in ("use_se", "fix", "without_norm", "dropout"):
+        for flag in ("use_se", "fix", "without_norm"):
             if getattr(cfg, flag):
                 raise NotImplementedError(f"GUNet engine: --{flag} is not supported")
+        if cfg.dropout:
+            if not 0.0 < cfg.dropout < 1.0:
+                raise ValueError("--dropout must lie in (0, 1)")
+            if cfg.normalizer != "instance_norm" or getattr(cfg, "after_affine", False):
+                raise NotImplementedError("GUNet engine: --dropout is built for instance_norm without after_affine")
         if cfg.context_model != "fc":
             raise ValueError("Not supported context model")          # GUNet.py:79
         if cfg.use_spatial and cfg.guide_channel not in (1, 2):
             raise ValueError("guide_channel must be 1 or 2")
         super().__init__(ctx, cfg)
         self._plan_guides()
+        self._plan_dropout()
 
     # ------------------------------------------------------------------ graph
     def _loss_terms(self):
@@ -193,6 +202,57 @@ class GUNetEngine(UNetEngine):
             self.fc_ws_bytes = int(ws)
             self.fc_ws = self._alloc(max(ws, 16))
 
+    # ------------------------------------------------------------------ backbone --dropout
+    def _drops(self, L: ConvL) -> bool:
+        return bool(self.cfg.dropout) and self.prefix == "GUNet" and L.role in ("enc1", "bridge1")
+
+    def _plan_dropout(self):
+        """Per dropped layer: the normalised-and-dropped bf16 tensor (kept for backward) and the normaliser's own
+        scalars (the layer's main scalar set then describes the identity normaliser of the modulation stage)."""
+        cfg, n = self.cfg, self.cfg.batch
+        self.drop = {}
+        layers = [L for L in self.layers if L.kind in ("stem", "conv") and self._drops(L)]
+        if not layers:
+            return
+        cmax = max(L.cout for L in layers)
+        ones = np.ones(_align(n * cmax, 16), np.float32)
+        self._ones = self._alloc(ones.nbytes)
+        self._ones.upload(ones)
+        self._zeros = self._alloc(ones.nbytes).zero()
+        for L in layers:
+            m = _align(n * L.cout, 16)
+            self.drop[L.scope] = dict(T=self._alloc(n * L.h * L.w * L.cout * BF16), small=self._alloc(10 * m * F32), m=m)
+        if cfg.training:
+            self.drop_grad = self._alloc(n * max(L.h * L.w * L.cout for L in layers) * BF16)
+
+    def _drop_ptrs(self, L: ConvL):
+        d = self.drop[L.scope]
+        base, m = d["small"].ptr, d["m"]
+        names = ["sums", "_s1", "_s2", "_s3", "mean", "rstd", "scale", "shift", "c1", "c2"]
+        return {nm: C.c_void_p(base + i * m * F32) for i, nm in enumerate(names)}
+
+    def _drop_desc(self, L: ConvL):
+        return _lib.DropoutDesc(1.0 - self.cfg.dropout, self.cfg.dropout_seed, (self.step_count + 1) * 16 + 8 + L.level)
+
+    def _dropout_stage(self, L: ConvL, nd, q, is_training: bool):
+        if not (is_training and L.scope in getattr(self, "drop", {})):
+            self._dropped = getattr(self, "_dropped", set()) - {L.scope}
+            return L.y.p
+        cfg, call, s = self.cfg, self.ctx.call, self.stream
+        T, qn = self.drop[L.scope]["T"], self._drop_ptrs(L)
+        nbytes = C.c_size_t(cfg.batch * L.cout * F32)
+        for k in ("mean", "rstd", "scale", "shift"):       # the normaliser's own scalars move aside ...
+            call("bsl_memcpy_d2d", qn[k], q[k], nbytes, s)
+        ndn = _lib.NormDesc(nd.mode, nd.n, nd.hw, nd.c, nd.x_ld, L.cout, nd.eps, nd.decay, 0, nd.center, nd.scale)
+        call("bsl_norm_apply", C.byref(ndn), L.y.p, qn["scale"], qn["shift"], T.p, s)
+        dd = self._drop_desc(L)
+        call("bsl_dropout_bf16", C.byref(dd), C.c_longlong(cfg.batch * L.h * L.w), C.c_int(L.cout), T.p, C.c_int(L.cout),
+             T.p, C.c_int(L.cout), s)
+        for k, src in (("mean", self._zeros), ("rstd", self._ones), ("scale", self._ones), ("shift", self._zeros)):
+            call("bsl_memcpy_d2d", q[k], src.p, nbytes, s)     # ... and the modulation stage sees an identity normaliser
+        self._dropped = getattr(self, "_dropped", set()) | {L.scope}
+        return T.p
+
     def _fc_desc(self, cin, cout, hidden, layer, is_training):
         cfg = self.cfg
         drop = bool(hidden and is_training and cfg.side_dropout)
@@ -292,7 +352,10 @@ class GUNetEngine(UNetEngine):
 
     # ------------------------------------------------------------------ backward
     def _is_modulated(self, L: ConvL) -> bool:
-        return L.mod_off is not None or L.sp_off is not None or bool(L.affine)
+        return L.mod_off is not None or L.sp_off is not None or bool(L.affine) or self._was_dropped(L)
+
+    def _was_dropped(self, L: ConvL) -> bool:
+        return L.scope in getattr(self, "_dropped", ())
 
     def _norm_backward_reduce(self, L: ConvL, nd, q, cur):
         if not self._is_modulated(L):
@@ -307,8 +370,19 @@ class GUNetEngine(UNetEngine):
         ssc = f"GUNet/spatial/conv{L.level + 1}"
         dwg = self._pp(self.G, f"{ssc}/weights", off=L.sp_off) if L.sp_off is not None else None
         dbg = self._pp(self.G, f"{ssc}/biases", off=L.sp_off) if L.sp_off is not None else None
-        call("bsl_norm_bwd_reduce_mod", C.byref(nd), L.y.p, cur.p, C.c_int(L.cout), q["mean"], q["rstd"], q["scale"],
+        dropped = self._was_dropped(L)
+        xin = self.drop[L.scope]["T"].p if dropped else L.y.p
+        call("bsl_norm_bwd_reduce_mod", C.byref(nd), xin, cur.p, C.c_int(L.cout), q["mean"], q["rstd"], q["scale"],
              q["shift"], gp, q["sums"], s)
+        if dropped:
+            # modulation stage over the dropped tensor: identity normaliser (no gamma / beta, no Jacobian: c1 = c2 = 0);
+            # sum(dz * T) is the gradient of gamma_mod, the guide rows those of the 1x1 guide conv
+            call("bsl_norm_bwd_finalize_mod", C.byref(nd), q["sums"], C.c_int(self._guide_channels(L)), gm, C.c_int(nmod),
+                 None, None, q["c1"], q["c2"], None, None, dgm, dwg, C.c_int(2 * L.cout), dbg, s)
+            nbytes = C.c_size_t(self.cfg.batch * L.cout * F32)
+            call("bsl_memset", q["c1"], C.c_int(0), nbytes, s)
+            call("bsl_memset", q["c2"], C.c_int(0), nbytes, s)
+            return
         if L.affine:
             sp, hp, _ = self._aff_ptrs(L)
             wsp = self._pp(self.W, f"{ssc}/weights", off=L.sp_off) if L.sp_off is not None else None
@@ -334,6 +408,23 @@ class GUNetEngine(UNetEngine):
         if self._head_grad is not None:
             return super()._norm_backward_apply(L, nd, q, cur, oth, stream, sig)
         guide = self._guide_struct(L)
+        if self._was_dropped(L):
+            assert sig is None
+            call, ns = self.ctx.call, self.norm_scope
+            T, dT, qn = self.drop[L.scope]["T"], self.drop_grad, self._drop_ptrs(L)
+            c = C.c_int(L.cout)
+            call("bsl_norm_bwd_apply_mod_pipe", C.byref(nd), T.p, cur.p, c, q["mean"], q["rstd"], q["scale"], q["shift"],
+                 q["c1"], q["c2"], C.byref(guide) if guide is not None else None, dT.p, c, None, stream)
+            dd = self._drop_desc(L)
+            call("bsl_dropout_bf16", C.byref(dd), C.c_longlong(self.cfg.batch * L.h * L.w), c, dT.p, c, dT.p, c, stream)
+            ndn = _lib.NormDesc(nd.mode, nd.n, nd.hw, nd.c, nd.x_ld, nd.y_ld, nd.eps, nd.decay, 0, nd.center, nd.scale)
+            call("bsl_norm_bwd_reduce", C.byref(ndn), L.y.p, dT.p, c, qn["mean"], qn["rstd"], qn["scale"], qn["shift"],
+                 qn["sums"], stream)
+            call("bsl_norm_bwd_finalize", C.byref(ndn), qn["sums"], qn["c1"], qn["c2"],
+                 self._pp(self.G, f"{L.scope}/{ns}/gamma"), self._pp(self.G, f"{L.scope}/{ns}/beta"), stream)
+            call("bsl_norm_bwd_apply", C.byref(ndn), L.y.p, dT.p, c, qn["mean"], qn["rstd"], qn["scale"], qn["shift"],
+                 qn["c1"], qn["c2"], oth.p, c, stream)
+            return
         if self._bn_mod(L):
             assert sig is None
             self.ctx.call("bsl_norm_bwd_apply_bnmod", C.byref(self._apply_desc(L, nd)), L.y.p, cur.p, C.c_int(L.cout),

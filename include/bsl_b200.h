@@ -426,6 +426,10 @@ int bsl_fc_bwd(bsl_ctx* ctx, const bsl_fc_desc* d, const float* x, const float* 
                float* dx, float* dw, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
 /* out[i] = 1 / keep_prob or 0: the dropout multipliers themselves (tests, and backbone --dropout). */
 int bsl_dropout_mask(bsl_ctx* ctx, const bsl_dropout_desc* d, size_t n, float* out, void* stream);
+/* slim.dropout on a bf16 NHWC tensor (GUNet backbone --dropout, NetworksV2/GUNet.py:189-190) and, with the same
+ * descriptor, its gradient: out[p][ch] = bf16(x[p][ch] * multiplier(p * c + ch)); in place when out == x. */
+int bsl_dropout_bf16(bsl_ctx* ctx, const bsl_dropout_desc* d, long long pixels, int c, const void* x_bf16, int x_ld,
+                     void* out_bf16, int out_ld, void* stream);
 int bsl_avgpool2x2_f32(bsl_ctx* ctx, int n, int h, int w, int c, const float* x, float* y, void* stream);
 /* UNetInter --mid_cat (NetworksV2/UNetInter.py:124-125, slim.max_pool2d(concat(net, sp_guide), 2)): the guide's share of
  * the pooled tensor, y_bf16[pixel * y_ld + ch] = bf16(max of the 2x2 window of x[n,h,w,c]), ch < c. */

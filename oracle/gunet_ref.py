@@ -52,6 +52,8 @@ class GUNetCfg:
     bn_eps: float = 1e-3                 # slim.batch_norm default epsilon
     prefix: str = "GUNet"                # "UNetInter": same variable layout, no modulation, guide concatenated to the
                                          # images at the input (/root/reference/NetworksV2/UNetInter.py:89-92,118-146)
+    dropout: float = 0.0                 # backbone --dropout (GUNet.py:189-190): slim.dropout behind the normaliser of the
+                                         # FIRST conv of every encoder block, in front of the modulation; training only
     mid_cat: bool = False                # UNetInter --mid_cat (UNetInter.py:87-92,124-125): the guide is NOT an input channel;
                                          # it is concatenated to the first block's output in front of the first max-pool
 
@@ -103,7 +105,7 @@ def layer_specs(cfg: GUNetCfg):
                      role=f"enc{j}", mod=mod, center=(cfg.norm_with_center and not aa) if mod else True,
                      scale=(cfg.norm_with_scale and not aa) if mod else True, mod_off=None, sp_off=None,
                      affine=f"{cfg.prefix}/Encode/down_conv{i + 1}/mod_conv{j}/ChannelWiseAffine" if aa else None,
-                     decay=0.99 if (mod or enc_decay_all) else 0.999)
+                     decay=0.99 if (mod or enc_decay_all) else 0.999, drop=(j == 1))
             if mod and cfg.use_context:
                 s["mod_off"] = off
                 off += c
@@ -284,7 +286,13 @@ def forward(params: dict, inputs: dict, cfg: GUNetCfg, is_training: bool, rnd=_i
                 z, cache = O.batch_norm_infer(y, gamma, beta, mm, mv, cfg.bn_eps), None
         else:
             z, cache = O.instance_norm(y, gamma, beta, cfg.in_eps)
-        gm = sp = None
+        gm = sp = mult = None
+        if cfg.dropout and is_training and s.get("drop") and cfg.prefix == "GUNet":
+            # modulated_conv_block: `if i != repeat - 1 and dropout: net = slim.dropout(net, keep_prob=1 - dropout, ...)`.
+            # The device keeps the normalised tensor in bf16 and multiplies it in place (two roundings, mirrored by rnd)
+            mult = O.dropout_multipliers(z.size, 1.0 - cfg.dropout, cfg.dropout_seed,
+                                         dropout_offset(step, 8 + s["level"])).reshape(z.shape).astype(dt)
+            z = rnd(rnd(z).astype(dt) * mult).astype(dt)
         zn = z
         if s["mod_off"] is not None:
             gm = ctx_params[:, s["mod_off"]:s["mod_off"] + cout]
@@ -303,7 +311,7 @@ def forward(params: dict, inputs: dict, cfg: GUNetCfg, is_training: bool, rnd=_i
             tape.errs[f"{sc}:a"] = rel(stored[sc]["a"], a)
             a = stored[sc]["a"].astype(dt)
         tape.layers.append(dict(kind="conv", spec=s, x=x, w=w, z=z, zn=zn, u=u, a=a, cache=cache, first=first, gm=gm,
-                                sp=sp, ga=params[f"{s['affine']}/gamma"].astype(dt) if s["affine"] else None))
+                                mult=mult, sp=sp, ga=params[f"{s['affine']}/gamma"].astype(dt) if s["affine"] else None))
         return a
 
     specs = layer_specs(cfg)
@@ -397,6 +405,8 @@ def backward(tape: Tape, dlogits: np.ndarray, cfg: GUNetCfg, rnd=_identity) -> d
             if L["gm"] is not None:
                 dctx[:, s["mod_off"]:s["mod_off"] + cout] = (dz * L["zn"]).sum(axis=(1, 2))
                 dz = dz * L["gm"][:, None, None, :]
+            if L.get("mult") is not None:    # gradient of slim.dropout: the same multipliers (bf16 in, bf16 out on the device)
+                dz = rnd(rnd(dz).astype(dt) * L["mult"]).astype(dt)
             ns = norm_scope(cfg)
             if cfg.normalizer == "batch_norm":
                 dy, dg, db = O.batch_norm_grad(dz, L["cache"])

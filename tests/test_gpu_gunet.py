@@ -33,6 +33,22 @@ def test_dropout_mask_bit_exact(ctx):
         assert np.array_equal(got, O.dropout_multipliers(n, keep, seed, off))
 
 
+def test_dropout_bf16_bit_exact(ctx):
+    """bsl_dropout_bf16 (backbone --dropout and its gradient): bf16(x * multiplier(flat index)), strided in / out."""
+    rng = np.random.default_rng(3)
+    pixels, c, ld = 777, 24, 32
+    x = round_bf16(rng.standard_normal((pixels, ld), dtype=np.float32))
+    bx, bo = ctx.bf16_from_f32(x), ctx.alloc(pixels * c * 2)
+    for keep, seed, off in ((0.5, 1, 24), (0.75, 0xABCDEF0123, (1 << 34) + 5)):
+        d = _lib.DropoutDesc(keep, seed, off)
+        ctx.call("bsl_dropout_bf16", C.byref(d), C.c_longlong(pixels), C.c_int(c), bx.p, C.c_int(ld), bo.p, C.c_int(c),
+                 ctx.stream)
+        got = ctx.bf16_to_f32(bo, (pixels, c))
+        want = round_bf16(x[:, :c] * O.dropout_multipliers(pixels * c, keep, seed, off).reshape(pixels, c))
+        assert np.array_equal(got, want)
+    bx.free(), bo.free()
+
+
 def test_fc_and_avgpool_ops(ctx):
     rng = np.random.default_rng(0)
     n, cin, cout = 5, 37, 50
@@ -94,6 +110,11 @@ def _make(n, hw, **kw):
     (3, 64, dict(use_context=True, use_spatial=True, guide_channel=1, norm_with_center=True, norm_with_scale=True,
                  normalizer="batch_norm", loss_type="xentropy+dice")),
     (2, 64, dict(use_context=True, use_spatial=False, normalizer="batch_norm", loss_type="xentropy")),
+    # backbone --dropout (GUNet.py:189-190): Philox mask behind the normaliser of the first conv of every encoder block,
+    # in front of the modulation; the second case drops un-modulated blocks (0 and the bridge) too, keep_prob 0.75
+    (2, 64, dict(use_context=True, use_spatial=True, guide_channel=1, loss_type="xentropy+dice", dropout=0.5)),
+    (2, 64, dict(use_context=True, use_spatial=True, guide_channel=2, norm_with_scale=True, mod_layers=(1, 2, 3),
+                 dropout=0.25, loss_type="xentropy")),
 ])
 def test_gunet_train_step_parity(ctx, n, hw, kw):
     ecfg, rcfg, inputs, labels = _make(n, hw, **kw)
@@ -136,6 +157,9 @@ def test_gunet_train_step_parity(ctx, n, hw, kw):
         assert rel(ctxp, tft.ctx_params) < 1e-5
         if rcfg.side_dropout:
             assert any((f["mult"] == 0).any() for f in tft.fc if f["mult"] is not None)
+    if rcfg.dropout:
+        dropped = [L for L in tft.layers if L.get("mult") is not None]
+        assert len(dropped) == rcfg.num_down_samples + 1 and all((L["mult"] == 0).any() for L in dropped)
     loss_o, dl = G.loss_and_dlogits(tft, labels, rcfg)
     assert abs(data_loss - loss_o) < 1e-4 * abs(loss_o)
     assert abs(reg_loss - G.regularization_loss(params, rcfg)) < 1e-6

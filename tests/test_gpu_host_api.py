@@ -100,6 +100,15 @@ def test_gunet_through_model_fn(ctx):
            side_dropout=0.5)
 
 
+def test_gunet_backbone_dropout_through_model_fn(ctx):
+    """--dropout (core/models.py:87, GUNet.py:189-190) reaches the engine through the reference's flag."""
+    def feed(images, labels):
+        c, g = synthetic.make_guides(images, labels, 200, 1, seed=1)
+        return dict(context=c, sp_guide=g)
+    _drive(ctx, "GUNet", feed, normalizer="instance_norm", use_spatial=True, use_context=True, guide_channel=1,
+           side_dropout=0.5, dropout=0.2)
+
+
 def test_unsupported_flags_raise(ctx):
     args = _args("UNetInter", normalizer="instance_norm", img_grad=True)
     params = models.get_model_params(args)

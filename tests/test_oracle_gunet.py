@@ -71,6 +71,8 @@ def _torch_gunet(params, inputs, labels, cfg, mults):
         else:
             y = F.instance_norm(y, weight=P[f"{sc}/InstanceNorm/gamma"] if s["scale"] else None,
                                 bias=P[f"{sc}/InstanceNorm/beta"] if s["center"] else None, eps=cfg.in_eps)
+        if getattr(cfg, "_drop_mults", None) and s.get("drop") and s["scope"] in cfg._drop_mults:
+            y = y * t(cfg._drop_mults[s["scope"]]).permute(0, 3, 1, 2)
         if s["mod_off"] is not None:
             y = y * ctxp[:, s["mod_off"]:s["mod_off"] + co][:, :, None, None]
         if s["sp_off"] is not None:
@@ -159,6 +161,36 @@ def test_oracle_matches_torch_autograd(kw):
         assert np.allclose(tape.new_moving[k0], 0.01 * mean_y, rtol=1e-9, atol=1e-12)       # decay 0.99, moving mean was 0
         assert tape.new_moving[k1].min() > 0.999 - 1e-9      # moving variance starts at 1: 0.999 + 0.001 * var
         assert set(tape.new_moving) == {k for k in params if "/moving_" in k}
+
+
+def test_backbone_dropout_oracle_matches_torch_autograd():
+    """--dropout (/root/reference/NetworksV2/GUNet.py:189-190): slim.dropout behind the normaliser of the first conv of
+    every encoder block, in front of gamma_mod and the guide map; the same multipliers in the backward pass."""
+    cfg = G.GUNetCfg(height=16, width=16, init_channels=4, num_down_samples=2, mod_layers=(1, 2), context_fc_channels=(8,),
+                     context_dim=10, loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4), weight_decay_rate=0.0,
+                     side_dropout=0.0, dropout=0.25, dropout_seed=5)
+    rng = np.random.default_rng(10)
+    n = 2
+    inputs = dict(images=rng.uniform(0, 1, (n, 16, 16, 3)), context=rng.uniform(0, 1, (n, 10)),
+                  sp_guide=rng.uniform(0.5, 1, (n, 16, 16, 1)))
+    labels = rng.integers(0, 3, (n, 16, 16)).astype(np.int32)
+    params = {k: v.astype(np.float64) + (0.1 * rng.standard_normal(v.shape) if k.endswith(("beta", "gamma", "biases")) else 0)
+              for k, v in G.init_params(cfg, seed=3, dtype=np.float64).items()}
+    tape = G.forward(params, inputs, cfg, True, step=2)
+    drops = {L["spec"]["scope"]: L["mult"] for L in tape.layers if L.get("mult") is not None}
+    assert len(drops) == 3 and all(sc.endswith("mod_conv1/Conv") for sc in drops)      # first conv of blocks 1, 2, 3
+    for m in drops.values():
+        assert set(np.unique(m)) == {0.0, np.float32(1 / 0.75)} and 0.6 < (m > 0).mean() < 0.9
+    loss, dl = G.loss_and_dlogits(tape, labels, cfg)
+    grads = G.backward(tape, dl, cfg)
+    cfg._drop_mults = drops
+    t_logits, t_loss, t_grads = _torch_gunet(params, inputs, labels, cfg, None)
+    assert np.allclose(tape.logits, t_logits, rtol=1e-9, atol=1e-10)
+    assert abs(loss - t_loss) < 1e-10
+    for k, g in grads.items():
+        assert np.allclose(g, t_grads[k], rtol=1e-7, atol=1e-10), k
+    # inference: no dropout
+    assert all(L.get("mult") is None for L in G.forward(params, inputs, cfg, False).layers)
 
 
 def test_unetinter_oracle_matches_torch_autograd():
