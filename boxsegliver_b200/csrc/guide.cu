@@ -113,6 +113,28 @@ __global__ void maxpool2x2_f32_bf16_kernel(int n, int h, int w, int c, const flo
   }
 }
 
+// --img_grad (NetworksV2/GUNet.py:333-337): concat(images, dy, dx) with (dy, dx) = tf.image.image_gradients(images) --
+// forward differences along H and W, zero in the last row / column -- written as bf16 lanes [0, 3c) of rows with stride
+// y_ld (the remaining lanes of the zero-initialised buffer pad the first conv's input to a 64-channel block).
+__global__ void image_gradients_pack_kernel(int n, int h, int w, int c, const float* __restrict__ x,
+                                            __nv_bfloat16* __restrict__ y, int y_ld) {
+  bsl::pdl_enter();
+  const long long total = (long long)n * h * w * c;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int ch = (int)(t % c); t /= c;
+    const int xx = (int)(t % w); t /= w;
+    const int yy = (int)(t % h);
+    const float v = x[i];
+    const float dy = yy + 1 < h ? x[i + (long long)w * c] - v : 0.f;
+    const float dx = xx + 1 < w ? x[i + c] - v : 0.f;
+    __nv_bfloat16* o = y + (i / c) * y_ld;
+    o[ch] = __float2bfloat16_rn(v);
+    o[c + ch] = __float2bfloat16_rn(dy);
+    o[2 * c + ch] = __float2bfloat16_rn(dx);
+  }
+}
+
 // Backbone --dropout of GUNet (slim.dropout between normaliser and modulation, NetworksV2/GUNet.py:189-190) and its
 // gradient (the same multiplication): out[p][ch] = bf16(x[p][ch] * multiplier(p * c + ch)), 8 channels per thread = two
 // Philox counters (flat element index over the dense [pixels, c] tensor, as bsl_dropout_mask enumerates it).
@@ -234,6 +256,22 @@ int bsl_avgpool2x2_f32(bsl_ctx* ctx, int n, int h, int w, int c, const float* x,
   if (blocks > cap) blocks = cap;
   bsl_launch(avgpool2x2_f32_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), n, h, w, c, x, y);
   BSL_LAUNCH_CHECK(ctx, "avgpool2x2_f32_kernel");
+  return BSL_OK;
+}
+
+int bsl_image_gradients_pack(bsl_ctx* ctx, int n, int h, int w, int c, const float* x, void* y_bf16, int y_ld,
+                             void* stream) {
+  if (!ctx) return BSL_EINVAL;
+  if (!x || !y_bf16) return bsl_fail(ctx, BSL_EINVAL, "image_gradients_pack: null buffer");
+  if (n <= 0 || h <= 0 || w <= 0 || c <= 0 || y_ld < 3 * c)
+    return bsl_fail(ctx, BSL_EINVAL, "image_gradients_pack: y_ld=%d must hold 3 * c = %d lanes", y_ld, 3 * c);
+  const long long total = (long long)n * h * w * c;
+  long long blocks = (total + 255) / 256;
+  const long long cap = 16LL * ctx->sm_count;
+  if (blocks > cap) blocks = cap;
+  bsl_launch(image_gradients_pack_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), n, h, w, c, x,
+             reinterpret_cast<__nv_bfloat16*>(y_bf16), y_ld);
+  BSL_LAUNCH_CHECK(ctx, "image_gradients_pack_kernel");
   return BSL_OK;
 }
 

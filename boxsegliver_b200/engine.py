@@ -475,6 +475,9 @@ class UNetEngine:
     def _guide_channels(self, L: ConvL) -> int:
         return 0
 
+    def _first_input(self, L: ConvL) -> View:
+        raise NotImplementedError("the first layer of this engine is the im2col stem")
+
     def _pooled_lanes(self, L: ConvL) -> int:
         """Channel stride of the pooled tensor behind an encoder block."""
         return L.cout
@@ -515,6 +518,8 @@ class UNetEngine:
                     L.a = View(self._alloc(n * L.h * L.w * L.cout * BF16), n, L.h, L.w, L.cout)
                 if L.kind == "conv":
                     L.x = cat[L.level] if L.role == "dec1" else prev_a
+                    if L.x is None:      # a first layer that is not the im2col stem (GUNet --img_grad: 9 input channels)
+                        L.x = self._first_input(L)
                 prev_a = L.pooled if is_enc2 else L.a
                 if is_enc2 and L.pooled.ld != L.cout:
                     prev_a = View(L.pooled.buf, n, L.h // 2, L.w // 2, L.pooled.ld)
@@ -991,7 +996,7 @@ class UNetEngine:
                 # layer runs beside the HBM-bound normalisation backward of the next one instead of beside dgrad
                 if self._fork_pre:
                     fork()
-                if L.kind != "stem":
+                if L.kind != "stem" and idx > 0:     # no gradient w.r.t. the network input
                     wbf = self._pp(self.Wbf, f"{L.scope}/weights", BF16)
                     dd = self._conv_desc(L)
                     dd.y_ld = L.cout

@@ -15,7 +15,10 @@ Backbone `--dropout` (GUNet.py:189-190: slim.dropout behind the normaliser of th
 front of the modulation; no shipped script enables it) runs un-fused: normalise without ReLU into a bf16 copy, multiply it
 by the Philox mask in place (bsl_dropout_bf16), then the ordinary modulated apply pass over that copy with an identity
 normaliser; backward mirrors the three stages.
-Scope: context_model "fc"; --use_se, --fix, --without_norm, --img_grad and ct_conv raise NotImplementedError.
+`--img_grad` (GUNet.py:333-337, scripts/103_grad.sh): the input becomes concat(images, dy, dx) of
+tf.image.image_gradients, packed as bf16 [n, h, w, 64] (9 live lanes) by bsl_image_gradients_pack; the first layer then
+runs as an ordinary 64-lane conv instead of the im2col stem.
+Scope: context_model "fc"; --use_se, --fix, --without_norm and ct_conv raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -26,7 +29,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib
-from .engine import BF16, F32, ConvL, EngineConfig, Param, UNetEngine, _align
+from .engine import BF16, F32, ConvL, EngineConfig, Param, UNetEngine, View, _align
 
 
 @dataclass
@@ -50,6 +53,7 @@ class GUNetConfig(EngineConfig):
     fix: bool = False
     without_norm: bool = False
     dropout: float = None
+    img_grad: bool = False                         # --img_grad: concat(images, dy, dx) of tf.image.image_gradients as input
 
     @property
     def n_modulator_param(self):
@@ -89,10 +93,13 @@ class GUNetEngine(UNetEngine):
         h, w = cfg.height, cfg.width
         nd = cfg.num_down_samples
         off = 0
+        grad_in = bool(getattr(cfg, "img_grad", False)) and self.prefix == "GUNet"
+        if grad_in:
+            cin = 3 * cfg.channel     # GUNet.py:333-337; too many im2col columns for the stem: an ordinary conv, 9 -> 64 lanes
         for i in range(nd + 1):
             mod = i in cfg.mod_layers and (cfg.use_context or cfg.use_spatial)
             for j in (1, 2):
-                kind = "stem" if (i == 0 and j == 1) else "conv"
+                kind = "stem" if (i == 0 and j == 1 and not grad_in) else "conv"
                 role = f"enc{j}" if i < nd else f"bridge{j}"
                 aa = bool(getattr(cfg, "after_affine", False))
                 # encoder_arg_scope (GUNet.py:313-330): after_affine turns centre / scale of the MODULATED blocks' normaliser
@@ -164,6 +171,13 @@ class GUNetEngine(UNetEngine):
 
     def _guide_channels(self, L: ConvL) -> int:
         return self.cfg.guide_channel if L.sp_off is not None else 0
+
+    def _first_input(self, L: ConvL):
+        """--img_grad: the bf16 tensor [n, h, w, 64] that bsl_image_gradients_pack fills with (images, dy, dx)."""
+        cfg = self.cfg
+        self.input_packed = View(self._alloc(cfg.batch * L.h * L.w * L.cin_dev * BF16).zero(), cfg.batch, L.h, L.w,
+                                 L.cin_dev)
+        return self.input_packed
 
     def _bn_mod(self, L: ConvL) -> bool:
         """A modulated block under batch norm: batch statistics, per-sample scale / shift."""
@@ -314,6 +328,10 @@ class GUNetEngine(UNetEngine):
                 call("bsl_avgpool2x2_f32", C.c_int(cfg.batch), C.c_int(h), C.c_int(w), C.c_int(cfg.guide_channel), src.p,
                      dst.p, s)
         self._fwd_training = is_training
+        if getattr(self, "input_packed", None) is not None:
+            self.ctx.tag = "GUNet/image_gradients"
+            call("bsl_image_gradients_pack", C.c_int(cfg.batch), C.c_int(cfg.height), C.c_int(cfg.width), C.c_int(cfg.channel),
+                 self.images.p, self.input_packed.p, C.c_int(self.input_packed.ld), s)
         super().forward(is_training)
 
     def _aff_ptrs(self, L: ConvL):

@@ -22,8 +22,6 @@ class GUNet(UNet):
             raise NotImplementedError("ct_conv (convolutional context sub-network) is outside the accelerated path")
 
     def _build_network(self, *args, **kwargs):
-        if getattr(self.args, "img_grad", False):
-            raise NotImplementedError("--img_grad is outside the accelerated path")
         if self.ctx is None:
             from ..device import Context
             self.ctx = Context(0)
@@ -48,7 +46,8 @@ class GUNet(UNet):
             use_context=self.use_context_guide, use_spatial=self.use_spatial_guide,
             guide_channel=getattr(self.args, "guide_channel", 1), side_dropout=self.side_dropout or 0.0,
             dropout_seed=getattr(self.args, "seed", 0), use_se=self.use_se, fix=getattr(self.args, "fix", False),
-            without_norm=getattr(self.args, "without_norm", False), dropout=self.dropout)
+            without_norm=getattr(self.args, "without_norm", False), dropout=self.dropout,
+            img_grad=bool(getattr(self.args, "img_grad", False)))
         if self.engine is None or self.engine.cfg != cfg:
             if self.engine is not None:
                 self.engine.close()

@@ -17,9 +17,11 @@ class UNetInter(UNet):
         self.use_spatial_guide = getattr(args, "use_spatial", False)        # UNetInter.py:41
 
     def _build_network(self, *args, **kwargs):
-        for flag in ("img_grad", "without_norm"):
-            if getattr(self.args, flag, False):
-                raise NotImplementedError(f"--{flag} is outside the accelerated path")
+        # --img_grad (5 shipped 101_unetinter*.sh scripts): UNetInter.py:82-86 computes tf.image.image_gradients into
+        # self.dy / self.dx, but the concat that would feed them to the network is commented out there -- the graph that
+        # trains is the one without them, so the flag is accepted and changes nothing here either.
+        if getattr(self.args, "without_norm", False):
+            raise NotImplementedError("--without_norm is outside the accelerated path")
         if self.ctx is None:
             from ..device import Context
             self.ctx = Context(0)

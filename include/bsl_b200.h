@@ -431,6 +431,10 @@ int bsl_dropout_mask(bsl_ctx* ctx, const bsl_dropout_desc* d, size_t n, float* o
 int bsl_dropout_bf16(bsl_ctx* ctx, const bsl_dropout_desc* d, long long pixels, int c, const void* x_bf16, int x_ld,
                      void* out_bf16, int out_ld, void* stream);
 int bsl_avgpool2x2_f32(bsl_ctx* ctx, int n, int h, int w, int c, const float* x, float* y, void* stream);
+/* --img_grad (NetworksV2/GUNet.py:333-337, UNet.py:69-71): tf.concat((images, dy, dx), -1) with tf.image.image_gradients
+ * (forward differences, last row / column zero) as bf16 lanes [0, 3c) of y_bf16 rows with stride y_ld. */
+int bsl_image_gradients_pack(bsl_ctx* ctx, int n, int h, int w, int c, const float* x, void* y_bf16, int y_ld,
+                             void* stream);
 /* UNetInter --mid_cat (NetworksV2/UNetInter.py:124-125, slim.max_pool2d(concat(net, sp_guide), 2)): the guide's share of
  * the pooled tensor, y_bf16[pixel * y_ld + ch] = bf16(max of the 2x2 window of x[n,h,w,c]), ch < c. */
 int bsl_maxpool2x2_f32_bf16(bsl_ctx* ctx, int n, int h, int w, int c, const float* x, void* y_bf16, int y_ld,

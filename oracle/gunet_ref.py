@@ -54,6 +54,8 @@ class GUNetCfg:
                                          # images at the input (/root/reference/NetworksV2/UNetInter.py:89-92,118-146)
     dropout: float = 0.0                 # backbone --dropout (GUNet.py:189-190): slim.dropout behind the normaliser of the
                                          # FIRST conv of every encoder block, in front of the modulation; training only
+    img_grad: bool = False               # --img_grad (GUNet.py:333-337): the network input is concat(images, dy, dx) of
+                                         # tf.image.image_gradients, 3 x channel input channels
     mid_cat: bool = False                # UNetInter --mid_cat (UNetInter.py:87-92,124-125): the guide is NOT an input channel;
                                          # it is concatenated to the first block's output in front of the first max-pool
 
@@ -93,7 +95,7 @@ def layer_specs(cfg: GUNetCfg):
     # does every decoder conv (BaseNet._get_normalization, base.py:153-162)
     enc_decay_all = cfg.prefix == "UNetInter"
     specs = []
-    c, cin = cfg.init_channels, cfg.channel
+    c, cin = cfg.init_channels, cfg.channel * (3 if cfg.img_grad and cfg.prefix == "GUNet" else 1)
     off = 0
     for i in range(cfg.num_down_samples + 1):
         mod = i in cfg.mod_layers and (cfg.use_context or cfg.use_spatial)
@@ -317,6 +319,10 @@ def forward(params: dict, inputs: dict, cfg: GUNetCfg, is_training: bool, rnd=_i
     specs = layer_specs(cfg)
     it = iter(specs)
     x = images
+    if cfg.img_grad and cfg.prefix == "GUNet":
+        # the device differences the fp32 images and stores the 3 x channel input in bf16 (one rounding per value)
+        dy, dx = O.image_gradients(images)
+        x = rnd(np.concatenate((images, dy, dx), axis=-1)).astype(dt)
     skips = []
     first = True
     for i in range(cfg.num_down_samples + 1):

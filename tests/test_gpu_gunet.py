@@ -115,6 +115,8 @@ def _make(n, hw, **kw):
     (2, 64, dict(use_context=True, use_spatial=True, guide_channel=1, loss_type="xentropy+dice", dropout=0.5)),
     (2, 64, dict(use_context=True, use_spatial=True, guide_channel=2, norm_with_scale=True, mod_layers=(1, 2, 3),
                  dropout=0.25, loss_type="xentropy")),
+    # --img_grad (GUNet.py:333-337, scripts/103_grad.sh): 9 input channels = concat(images, dy, dx)
+    (2, 64, dict(use_context=True, use_spatial=True, guide_channel=1, loss_type="xentropy+dice", img_grad=True)),
 ])
 def test_gunet_train_step_parity(ctx, n, hw, kw):
     ecfg, rcfg, inputs, labels = _make(n, hw, **kw)
@@ -148,7 +150,8 @@ def test_gunet_train_step_parity(ctx, n, hw, kw):
     new_w = eng.get_weights()
     eng.close()
 
-    rin = dict(inputs, images=round_bf16(inputs["images"]))
+    # (--img_grad: the device differences the fp32 images and rounds the packed input once; the oracle does the same)
+    rin = dict(inputs, images=inputs["images"] if rcfg.img_grad else round_bf16(inputs["images"]))
     # layer by layer on the device's stored inputs (fp64 oracle ops), and the tape for the backward check
     tft = G.forward({k_: v.astype(np.float64) for k_, v in params.items()},
                     {k_: v.astype(np.float64) for k_, v in rin.items()}, rcfg, True, wrnd=round_bf16, stored=stored, step=1)

@@ -89,7 +89,7 @@ def test_unetinter_mid_cat_through_model_fn(ctx):
     def feed(images, labels):
         return dict(sp_guide=synthetic.make_guides(images, labels, 200, 2, seed=1)[1])
     _drive(ctx, "UNetInter", feed, normalizer="instance_norm", use_spatial=True, guide_channel=2,
-           loss_type="xentropy+dice", mid_cat=True)
+           loss_type="xentropy+dice", mid_cat=True, img_grad=True)    # --img_grad: a no-op in UNetInter.py:82-86
 
 
 def test_gunet_through_model_fn(ctx):
@@ -110,10 +110,10 @@ def test_gunet_backbone_dropout_through_model_fn(ctx):
 
 
 def test_unsupported_flags_raise(ctx):
-    args = _args("UNetInter", normalizer="instance_norm", img_grad=True)
+    args = _args("UNetInter", normalizer="instance_norm", without_norm=True)
     params = models.get_model_params(args)
     params.update(args=args, solver=solver.Solver, ctx=ctx, world=1)
-    with pytest.raises(NotImplementedError, match="img_grad"):
+    with pytest.raises(NotImplementedError, match="without_norm"):
         models.model_fn(dict(images=None), None, ModeKeys.TRAIN, params)
 
 

@@ -44,6 +44,10 @@ def _torch_gunet(params, inputs, labels, cfg, mults):
     P = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in params.items() if "/moving_" not in k}
     t = lambda a: torch.tensor(a, dtype=torch.float64)
     x = t(inputs["images"]).permute(0, 3, 1, 2)
+    if getattr(cfg, "img_grad", False) and cfg.prefix == "GUNet":     # tf.image.image_gradients: forward differences
+        dy = F.pad(x[:, :, 1:] - x[:, :, :-1], (0, 0, 0, 1))
+        dx = F.pad(x[:, :, :, 1:] - x[:, :, :, :-1], (0, 1))
+        x = torch.cat((x, dy, dx), dim=1)
     ctxp = None
     if cfg.use_context:
         h = t(inputs["context"])
@@ -191,6 +195,33 @@ def test_backbone_dropout_oracle_matches_torch_autograd():
         assert np.allclose(g, t_grads[k], rtol=1e-7, atol=1e-10), k
     # inference: no dropout
     assert all(L.get("mult") is None for L in G.forward(params, inputs, cfg, False).layers)
+
+
+def test_img_grad_oracle_matches_torch_autograd():
+    """--img_grad (GUNet.py:333-337, scripts/103_grad.sh): concat(images, dy, dx) of tf.image.image_gradients feeds the
+    first conv (9 input channels)."""
+    cfg = G.GUNetCfg(height=16, width=16, init_channels=4, num_down_samples=2, mod_layers=(1, 2), context_fc_channels=(8,),
+                     context_dim=10, loss_weight_type="numerical", loss_numeric_w=(0.2, 0.4, 4.4), weight_decay_rate=0.0,
+                     side_dropout=0.0, img_grad=True)
+    rng = np.random.default_rng(11)
+    n = 2
+    inputs = dict(images=rng.uniform(0, 1, (n, 16, 16, 3)), context=rng.uniform(0, 1, (n, 10)),
+                  sp_guide=rng.uniform(0.5, 1, (n, 16, 16, 1)))
+    labels = rng.integers(0, 3, (n, 16, 16)).astype(np.int32)
+    dy, dx = O.image_gradients(inputs["images"])
+    assert not dy[:, -1].any() and not dx[:, :, -1].any()
+    assert np.allclose(dy[:, 3, 5], inputs["images"][:, 4, 5] - inputs["images"][:, 3, 5])
+    params = {k: v.astype(np.float64) + (0.1 * rng.standard_normal(v.shape) if k.endswith(("beta", "gamma", "biases")) else 0)
+              for k, v in G.init_params(cfg, seed=3, dtype=np.float64).items()}
+    assert params["GUNet/Encode/down_conv1/mod_conv1/Conv/weights"].shape == (3, 3, 9, 4)
+    tape = G.forward(params, inputs, cfg, True)
+    loss, dl = G.loss_and_dlogits(tape, labels, cfg)
+    grads = G.backward(tape, dl, cfg)
+    t_logits, t_loss, t_grads = _torch_gunet(params, inputs, labels, cfg, None)
+    assert np.allclose(tape.logits, t_logits, rtol=1e-9, atol=1e-10)
+    assert abs(loss - t_loss) < 1e-10
+    for k, g in grads.items():
+        assert np.allclose(g, t_grads[k], rtol=1e-7, atol=1e-10), k
 
 
 def test_unetinter_oracle_matches_torch_autograd():
