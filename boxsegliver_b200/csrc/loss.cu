@@ -272,22 +272,35 @@ __global__ void dice_reduce_kernel(const float* __restrict__ logits, const int* 
   }
 }
 
+// One warp per image sums that image's per-block partials (lane-strided, then a fixed shuffle tree: deterministic);
+// thread 0 then averages the per-image terms in image order. (A single thread walking n x blocks dependent fp64 loads
+// took 0.24 ms at batch 32 -- profiles/r02_ncu_launches_cfg3.txt.)
 __global__ void dice_final_kernel(const double* __restrict__ part, int blocks, int n, float eps,
                                   double* __restrict__ iu, float* __restrict__ loss) {
   bsl::pdl_enter();
-  if (threadIdx.x || blockIdx.x) return;
-  double mean = 0.0;
-  for (int img = 0; img < n; ++img) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int img = warp; img < n; img += nwarps) {
     double si = 0.0, su = 0.0;
-    for (int b = 0; b < blocks; ++b) {
+    for (int b = lane; b < blocks; b += 32) {
       si += part[((long long)img * blocks + b) * 2];
       su += part[((long long)img * blocks + b) * 2 + 1];
     }
-    iu[img * 2] = si;
-    iu[img * 2 + 1] = su;
-    mean += 2.0 * si / (su + (double)eps);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      si += __shfl_down_sync(0xffffffffu, si, o);
+      su += __shfl_down_sync(0xffffffffu, su, o);
+    }
+    if (lane == 0) {
+      iu[img * 2] = si;
+      iu[img * 2 + 1] = su;
+    }
   }
-  *loss = (float)(1.0 - mean / n);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mean = 0.0;
+    for (int img = 0; img < n; ++img) mean += 2.0 * iu[img * 2] / (iu[img * 2 + 1] + (double)eps);
+    *loss = (float)(1.0 - mean / n);
+  }
 }
 
 template <int C>
@@ -432,7 +445,7 @@ int bsl_dice_fwd_bwd(bsl_ctx* ctx, const bsl_loss_desc* d, const float* logits, 
   const float eps = 1e-8f;
   CLASS_SWITCH(d->classes, (bsl_launch(dice_reduce_kernel<C>, dim3(dim3(bx, d->n)), dim3(256), 0, s, logits, labels, d->hw, w.dpart)));
   BSL_LAUNCH_CHECK(ctx, "dice_reduce_kernel");
-  bsl_launch(dice_final_kernel, dim3(1), dim3(32), 0, s, w.dpart, bx, d->n, eps, w.iu, loss);
+  bsl_launch(dice_final_kernel, dim3(1), dim3(d->n >= 32 ? 1024 : (d->n >= 8 ? 256 : 32)), 0, s, w.dpart, bx, d->n, eps, w.iu, loss);
   BSL_LAUNCH_CHECK(ctx, "dice_final_kernel");
   if (dlogits) {
     const long long pixels = (long long)d->n * d->hw;

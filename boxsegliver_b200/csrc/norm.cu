@@ -532,33 +532,50 @@ __global__ void norm_modulate_kernel(int n, int c, const float* __restrict__ gam
 }
 
 // Backward scalars of a modulated instance-norm layer. sums[n][K][c]: S0 = sum dz, S1 = sum dz*xhat, T_g = sum dz*guide_g.
-__global__ void norm_bwd_finalize_mod_kernel(int n, int c, int K, double m, const double* __restrict__ sums,
-                                             const float* __restrict__ gamma_mod, int gm_ld,
-                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                             float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
-                                             float* __restrict__ dbeta, float* __restrict__ dgamma_mod,
-                                             float* __restrict__ dw_guide, int dw_ld, float* __restrict__ dbias_guide) {
+// Block = 32 channels x FM_S sample lanes: the per-sample outputs are independent; the sums over samples are combined
+// through shared memory in ascending sample-lane order (fixed order: bit-reproducible; identical to a serial loop over
+// the samples when n <= FM_S). One thread per channel walking all n samples took 57 us per launch at batch 32.
+constexpr int FM_S = 32;
+__global__ void __launch_bounds__(32 * FM_S)
+norm_bwd_finalize_mod_kernel(int n, int c, int K, double m, const double* __restrict__ sums,
+                             const float* __restrict__ gamma_mod, int gm_ld,
+                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                             float* __restrict__ c1, float* __restrict__ c2, float* __restrict__ dgamma,
+                             float* __restrict__ dbeta, float* __restrict__ dgamma_mod,
+                             float* __restrict__ dw_guide, int dw_ld, float* __restrict__ dbias_guide) {
   bsl::pdl_enter();
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  const double ga = gamma ? (double)gamma[ch] : 1.0, be = beta ? (double)beta[ch] : 0.0;
-  double sg = 0.0, sb = 0.0, s0all = 0.0, t[2] = {0.0, 0.0};
-  for (int s = 0; s < n; ++s) {  // fixed order
-    const double* q = sums + (long long)s * K * c + ch;
-    const double s0 = q[0], s1 = q[c];
-    c1[s * c + ch] = (float)(s0 / m);
-    c2[s * c + ch] = (float)(s1 / m);
-    const double gm = gamma_mod ? (double)gamma_mod[(long long)s * gm_ld + ch] : 1.0;
-    if (dgamma_mod) dgamma_mod[(long long)s * gm_ld + ch] = (float)(ga * s1 + be * s0);
-    sg += gm * s1;
-    sb += gm * s0;
-    s0all += s0;
-    for (int g = 0; g < K - 2; ++g) t[g] += q[(long long)(2 + g) * c];
+  __shared__ double red[5][FM_S][33];
+  const int chl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + chl;
+  double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // sg, sb, s0all, t0, t1
+  if (ch < c) {
+    const double ga = gamma ? (double)gamma[ch] : 1.0, be = beta ? (double)beta[ch] : 0.0;
+    for (int s = sl; s < n; s += FM_S) {
+      const double* q = sums + (long long)s * K * c + ch;
+      const double s0 = q[0], s1 = q[c];
+      c1[s * c + ch] = (float)(s0 / m);
+      c2[s * c + ch] = (float)(s1 / m);
+      const double gm = gamma_mod ? (double)gamma_mod[(long long)s * gm_ld + ch] : 1.0;
+      if (dgamma_mod) dgamma_mod[(long long)s * gm_ld + ch] = (float)(ga * s1 + be * s0);
+      acc[0] += gm * s1;
+      acc[1] += gm * s0;
+      acc[2] += s0;
+      for (int g = 0; g < K - 2; ++g) acc[3 + g] += q[(long long)(2 + g) * c];
+    }
   }
-  if (dgamma) dgamma[ch] = (float)sg;
-  if (dbeta) dbeta[ch] = (float)sb;
-  for (int g = 0; g < K - 2; ++g) dw_guide[g * dw_ld + ch] = (float)t[g];
-  if (dbias_guide) dbias_guide[ch] = (float)s0all;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) red[k][sl][chl] = acc[k];
+  __syncthreads();
+  if (sl == 0 && ch < c) {
+    double tot[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int j = 0; j < FM_S; ++j)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) tot[k] += red[k][j][chl];
+    if (dgamma) dgamma[ch] = (float)tot[0];
+    if (dbeta) dbeta[ch] = (float)tot[1];
+    for (int g = 0; g < K - 2; ++g) dw_guide[g * dw_ld + ch] = (float)tot[3 + g];
+    if (dbias_guide) dbias_guide[ch] = (float)tot[2];
+  }
 }
 
 // after_affine fold (GUNet.py:213-214): z = ga*(y*sc + sh + guide.w) + ba = y*(sc*ga) + (sh*ga + ba) + guide.(w*ga)
@@ -1452,7 +1469,7 @@ int bsl_norm_bwd_finalize_mod(bsl_ctx* ctx, const bsl_norm_desc* d, const double
   if (!sums || !c1 || !c2 || guide_channels < 0 || guide_channels > 2 || (gamma_mod && !dgamma_mod) ||
       (guide_channels && (!dw_guide || dw_ld < d->c)))
     return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_finalize_mod: bad argument");
-  bsl_launch(norm_bwd_finalize_mod_kernel, dim3((d->c + 127) / 128), dim3(128), 0, as_stream(stream), 
+  bsl_launch(norm_bwd_finalize_mod_kernel, dim3((d->c + 31) / 32), dim3(32 * FM_S), 0, as_stream(stream), 
       d->n, d->c, 2 + guide_channels, (double)d->hw, sums, gamma_mod, gm_ld, d->scale ? gamma : nullptr,
       d->center ? beta : nullptr, c1, c2, dgamma, dbeta, dgamma_mod, dw_guide, dw_ld, dbias_guide);
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_finalize_mod_kernel");
