@@ -420,24 +420,42 @@ __global__ void norm_apply_pool_kernel(const __nv_bfloat16* __restrict__ y, int 
   if (sig.flags != nullptr) pipe_signal_block(sig, img / sig.imgs_per_slice);
 }
 
-__global__ void norm_bwd_finalize_kernel(int groups, int c, double m, const double* __restrict__ sums,
-                                         const float* __restrict__ rstd_unused, float* __restrict__ c1,
-                                         float* __restrict__ c2, float* __restrict__ dgamma,
-                                         float* __restrict__ dbeta) {
+// Block = 32 channels x 32 group lanes (instance norm: one group per sample): c1 / c2 per (group, channel) are
+// independent; dgamma / dbeta sum over the groups through shared memory in ascending lane order (fixed order; identical
+// to a serial loop when groups <= 32, and batch norm has a single group).
+__global__ void __launch_bounds__(1024)
+norm_bwd_finalize_kernel(int groups, int c, double m, const double* __restrict__ sums,
+                         const float* __restrict__ rstd_unused, float* __restrict__ c1,
+                         float* __restrict__ c2, float* __restrict__ dgamma,
+                         float* __restrict__ dbeta) {
   bsl::pdl_enter();
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+  __shared__ double red[2][32][33];
+  const int chl = threadIdx.x & 31, gl = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + chl;
   double sg = 0.0, sb = 0.0;
-  for (int g = 0; g < groups; ++g) {  // fixed order
-    const double s0 = sums[(long long)g * 2 * c + ch];
-    const double s1 = sums[(long long)g * 2 * c + c + ch];
-    c1[g * c + ch] = (float)(s0 / m);
-    c2[g * c + ch] = (float)(s1 / m);
-    sb += s0;
-    sg += s1;
+  if (ch < c) {
+    for (int g = gl; g < groups; g += (int)(blockDim.x >> 5)) {
+      const double s0 = sums[(long long)g * 2 * c + ch];
+      const double s1 = sums[(long long)g * 2 * c + c + ch];
+      c1[g * c + ch] = (float)(s0 / m);
+      c2[g * c + ch] = (float)(s1 / m);
+      sb += s0;
+      sg += s1;
+    }
   }
-  if (dgamma) dgamma[ch] = (float)sg;
-  if (dbeta) dbeta[ch] = (float)sb;
+  red[0][gl][chl] = sg;
+  red[1][gl][chl] = sb;
+  __syncthreads();
+  if (gl == 0 && ch < c) {
+    double tg = 0.0, tb = 0.0;
+    const int lanes = blockDim.x >> 5;
+    for (int j = 0; j < lanes; ++j) {
+      tg += red[0][j][chl];
+      tb += red[1][j][chl];
+    }
+    if (dgamma) dgamma[ch] = (float)tg;
+    if (dbeta) dbeta[ch] = (float)tb;
+  }
   (void)rstd_unused;
 }
 
@@ -1440,7 +1458,8 @@ int bsl_norm_bwd_finalize(bsl_ctx* ctx, const bsl_norm_desc* d, const double* su
   if (!sums || !c1 || !c2) return bsl_fail(ctx, BSL_EINVAL, "norm_bwd_finalize: null buffer");
   const int groups = d->mode ? d->n : 1;
   const double m = d->mode ? (double)d->hw : (double)d->n * d->hw;
-  bsl_launch(norm_bwd_finalize_kernel, dim3((d->c + 127) / 128), dim3(128), 0, as_stream(stream), groups, d->c, m, sums, nullptr, c1, c2,
+  const int glanes = groups >= 32 ? 32 : (groups >= 8 ? 8 : (groups >= 4 ? 4 : 1));
+  bsl_launch(norm_bwd_finalize_kernel, dim3((d->c + 31) / 32), dim3(32 * glanes), 0, as_stream(stream), groups, d->c, m, sums, nullptr, c1, c2,
                                                                              dgamma, dbeta);
   BSL_LAUNCH_CHECK(ctx, "norm_bwd_finalize_kernel");
   return BSL_OK;
