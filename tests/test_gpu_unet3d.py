@@ -17,9 +17,17 @@ pytestmark = pytest.mark.gpu
     (2, 4, 32, dict()),                                                     # UNet3D.yml channels, 4 pools
     (1, 2, 64, dict(num_pool_layers=5, use_spatial=True, guide_channel=2, loss_numeric_w=(1.0, 10.0))),
     (2, 6, 32, dict(init_channels=16, max_channels=128, loss_weight_type="proportion", loss_numeric_w=())),
+    # the 64-lane zero-padded storage of the full-resolution level (what shapes outside the pixel-pair packing's reach
+    # run on: W % 16 != 0, H % 32 != 0, more than 32 channels), forced here through the tuning switch
+    (2, 4, 32, dict(_pair="0")),
+    (1, 2, 32, dict(init_channels=48, max_channels=96, _pair=None)),         # 48 > 32 channels: never packed
 ])
-def test_unet3d_train_step_parity(ctx, n, d, hw, kw):
+def test_unet3d_train_step_parity(ctx, n, d, hw, kw, monkeypatch):
     base = dict(depth=d, height=hw, width=hw, channel=1, weight_decay_rate=3e-5)
+    kw = dict(kw)
+    pair = kw.pop("_pair", "1")
+    if pair is not None:
+        monkeypatch.setenv("BSL_UNET3D_PAIR", pair)
     base.update(kw)
     ecfg, rcfg = UNet3DConfig(batch=n, **base), U.UNet3DCfg(**base)
     if rcfg.use_spatial:
@@ -35,6 +43,7 @@ def test_unet3d_train_step_parity(ctx, n, d, hw, kw):
         if k.endswith("gamma"):
             params[k] = (1 + 0.1 * rng.standard_normal(params[k].shape)).astype(np.float32)
     eng = UNet3DEngine(ctx, ecfg)
+    assert eng._pair == (pair == "1")
     assert set(eng.params) == set(params)
     eng.set_weights(params)
     back = eng.get_weights()
