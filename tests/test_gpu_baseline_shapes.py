@@ -326,13 +326,18 @@ def test_cfg3_gunet_full_size_sampled_parity(ctx):
     eng.close()
 
 
-def test_cfg4_unet3d_full_size_sampled_parity(ctx):
+@pytest.mark.parametrize("n,d,h,w,kw", [
+    (4, 64, 128, 128, dict()),                                                        # BASELINE configs[3]
+    # the shape the shipped 3-D scripts train on (threed_script/202_unetinter_v8.sh: --im_depth 10 --im_height 512
+    # --im_width 160 --use_spatial, UNet3D_V2.yml = 5 pooling levels): deepest levels 5 x 16 x 5 voxels off the 8x16 tiles
+    (2, 10, 512, 160, dict(use_spatial=True, guide_channel=2, num_pool_layers=5)),
+])
+def test_cfg4_unet3d_full_size_sampled_parity(ctx, n, d, h, w, kw):
     """BASELINE configs[3]: UNet3D 64x128x128, batch 4 -- every conv3d (strided, (1,3,3) and (3,3,3)) and transposed
     conv at sampled output voxels (TF SAME padding with the extra pad on the far side), instance norm + ReLU on the
     smaller levels, pad lanes exactly zero, loss + dlogits over all voxels."""
     from boxsegliver_b200.unet3d_engine import UNet3DConfig, UNet3DEngine
-    n, d, h, w = 4, 64, 128, 128
-    cfg = UNet3DConfig(batch=n, depth=d, height=h, width=w, loss_numeric_w=(1.0, 1.0))
+    cfg = UNet3DConfig(batch=n, depth=d, height=h, width=w, loss_numeric_w=(1.0, 1.0), **kw)
     eng = UNet3DEngine(ctx, cfg)
     params = eng.init_weights(5)
     rng = np.random.default_rng(6)
@@ -342,8 +347,13 @@ def test_cfg4_unet3d_full_size_sampled_parity(ctx):
         if k_.endswith("gamma"):
             params[k_] = (1 + 0.1 * rng.standard_normal(params[k_].shape)).astype(np.float32)
     eng.set_weights(params)
-    im, lb = synthetic.make_volume_batch(n, d, h, w, seed=1357 + 4)
-    eng.set_inputs(im, lb)
+    if cfg.use_spatial:
+        im, lb, guide = synthetic.make_volume_batch(n, d, h, w, seed=1357 + 4, guide_channel=cfg.guide_channel)
+        eng.set_inputs(im, lb, guide)
+        im = np.concatenate((im, guide), axis=-1)           # UNet3D.py:142-144
+    else:
+        im, lb = synthetic.make_volume_batch(n, d, h, w, seed=1357 + 4)
+        eng.set_inputs(im, lb)
     eng.forward(True)
     eng.loss_backward()
     ctx.check_device()
@@ -380,7 +390,7 @@ def test_cfg4_unet3d_full_size_sampled_parity(ctx):
             a_got = S.gather(_bits(L.a, (n,) + L.odhw), L.a.c0, L.cout, pos)
             worst[f"{L.scope} norm+relu"] = S.rel(a_got, a_ref)
     bad = {k: v for k, v in worst.items() if not v < TOL}
-    print(f"\ncfg4: {len(worst)} sampled forward ops, worst {max(worst.values()):.2e} ({max(worst, key=worst.get)})")
+    print(f"\ncfg4 {n}x{d}x{h}x{w}: {len(worst)} sampled forward ops, worst {max(worst.values()):.2e} ({max(worst, key=worst.get)})")
     assert not bad, bad
     logits = eng.logits.download(np.float32, (n, d, h, w, 2))
     loss, dl = O.weighted_sparse_softmax_cross_entropy(logits.reshape(n, d * h, w, 2), lb.reshape(n, d * h, w),
