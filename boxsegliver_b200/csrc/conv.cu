@@ -318,7 +318,7 @@ int launch_halo(bsl_ctx* ctx, int bn, int nsub, const CUtensorMap& a, const CUte
     const int lvl = tma_store_level();
     if (args.relu_mask == nullptr && ((bn == 256 && lvl >= 1) || (bn == 128 && lvl >= 2))) {
       CUtensorMap o;
-      if (out_map(ctx, args, args.ntile_w * 8, args.ntile_h * 16, &o) == 0) {
+      if (out_map(ctx, args, args.vw, args.vh, &o) == 0) {
         if (bn == 256 && nsub == 2) return launch_halo_one<256, 2, B_MN, false, false, true>(ctx, a, b, args, grid, stream, &o);
         if (bn == 256 && nsub == 1) return launch_halo_one<256, 1, B_MN, false, false, true>(ctx, a, b, args, grid, stream, &o);
         if (bn == 128 && nsub == 2) return launch_halo_one<128, 2, B_MN, false, false, true>(ctx, a, b, args, grid, stream, &o);
@@ -338,11 +338,24 @@ int launch_halo(bsl_ctx* ctx, int bn, int nsub, const CUtensorMap& a, const CUte
 }
 
 // Pixel sub-tiles are 8 (w) x 16 (h); `ncols` is the GEMM N extent (a multiple of 64).
-bool halo_eligible(int w, int h) { return !force_v1() && w % 8 == 0 && h % 16 == 0; }
+// Ragged extents: a grid that the tile does not divide runs with ceil(extent / tile) tiles -- TMA zero-fills the reads
+// past the edge (SAME padding already relies on it), the epilogue masks the stores and the statistics of pixels outside
+// the image (ConvHaloArgs::vw / vh), the filter-gradient kernels need nothing (zero dy rows contribute zero). Taken when
+// the padded grid holds at most 2x the pixels; BSL_HALO_RAGGED=0 restores the exact-multiple rule.
+bool ragged_on() {
+  static const bool on = !(getenv("BSL_HALO_RAGGED") && atoi(getenv("BSL_HALO_RAGGED")) == 0);
+  return on;
+}
+bool tiles_ok(int w, int h, int tw, int th) {
+  if (w % tw == 0 && h % th == 0) return true;
+  if (!ragged_on() || w < 1 || h < 1) return false;
+  return (long long)cdiv(w, tw) * tw * cdiv(h, th) * th <= 2LL * w * h;
+}
+bool halo_eligible(int w, int h) { return !force_v1() && tiles_ok(w, h, 8, 16); }
 
 HaloPlan plan_halo(bsl_ctx* ctx, int w, int h, int n, int ncols) {
   HaloPlan p;
-  p.n_sub_total = (w / 8) * (h / 16) * n;
+  p.n_sub_total = cdiv(w, 8) * cdiv(h, 16) * n;
   p.bn = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64);
   p.nsub = p.n_sub_total % 2 == 0 ? 2 : 1;
   static const int env_bn = getenv("BSL_HALO_BN") ? atoi(getenv("BSL_HALO_BN")) : 0;      // tuning overrides
@@ -370,8 +383,10 @@ int attach_wait(bsl_ctx* ctx, ConvHaloArgs& a, const bsl_pipe* wait, int n) {
 }
 
 void halo_common(ConvHaloArgs& a, const HaloPlan& p, int w, int h, int n) {
-  a.ntile_w = w / 8;
-  a.ntile_h = h / 16;
+  a.ntile_w = cdiv(w, 8);
+  a.ntile_h = cdiv(h, 16);
+  a.vw = w;
+  a.vh = h;
   a.n = n;
   a.n_sub_total = p.n_sub_total;
   a.n_units = p.n_units;
@@ -388,7 +403,7 @@ struct WgradPlan {
 };
 
 bool wgrad_halo_eligible(const bsl_conv2d_desc* d) {
-  return !force_v1() && d->kh == 3 && d->kw == 3 && d->w % WG_TW == 0 && d->h % WG_TH == 0;
+  return !force_v1() && d->kh == 3 && d->kw == 3 && tiles_ok(d->w, d->h, WG_TW, WG_TH);
 }
 
 // ---- wide wgrad (wgrad_halo2_kernel): split counts for the two CTA classes, chosen by simulating the hardware's
@@ -400,7 +415,7 @@ struct Wgrad2Plan {
 
 bool wgrad2_eligible(const bsl_conv2d_desc* d) {
   static const int off = getenv("BSL_WGRAD_V2") ? atoi(getenv("BSL_WGRAD_V2")) == 0 : 0;
-  return !off && !force_v1() && d->kh == 3 && d->kw == 3 && d->w % WG_TW == 0 && d->h % WG_TH == 0 && d->cout % 128 == 0;
+  return !off && !force_v1() && d->kh == 3 && d->kw == 3 && tiles_ok(d->w, d->h, WG_TW, WG_TH) && d->cout % 128 == 0;
 }
 
 Wgrad2Plan plan_wgrad2_core(bsl_ctx* ctx, int k, int mn, size_t per_tap) {
@@ -441,7 +456,7 @@ Wgrad2Plan plan_wgrad2_core(bsl_ctx* ctx, int k, int mn, size_t per_tap) {
 }
 
 Wgrad2Plan plan_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
-  return plan_wgrad2_core(ctx, (d->w / WG_TW) * (d->h / WG_TH) * d->n, (d->cin / 64) * (d->cout / 128),
+  return plan_wgrad2_core(ctx, cdiv(d->w, WG_TW) * cdiv(d->h, WG_TH) * d->n, (d->cin / 64) * (d->cout / 128),
                           (size_t)d->cin * d->cout);
 }
 
@@ -469,8 +484,8 @@ int conv2d_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const v
   const long long per_tap = (long long)d->cin * d->cout;
   float* ws = reinterpret_cast<float*>(workspace);
   WgradHalo2Args a = {};
-  a.ntile_w = d->w / WG_TW;
-  a.ntile_h = d->h / WG_TH;
+  a.ntile_w = cdiv(d->w, WG_TW);
+  a.ntile_h = cdiv(d->h, WG_TH);
   a.n = d->n;
   a.k_tiles_total = p.k_tiles;
   a.splits_a = p.splits_a;
@@ -499,7 +514,7 @@ int conv2d_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const v
 
 WgradPlan plan_wgrad_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
   WgradPlan p;
-  p.k_tiles = (d->w / WG_TW) * (d->h / WG_TH) * d->n;
+  p.k_tiles = cdiv(d->w, WG_TW) * cdiv(d->h, WG_TH) * d->n;
   const int mn = (d->cin / 64) * (d->cout / 64);
   int splits = std::max(1, ctx->sm_count / mn);
   splits = std::max(1, std::min(splits, p.k_tiles / 4));
@@ -803,8 +818,8 @@ int bsl_conv2d_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, cons
     if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, xbox, &tx))) return rc;
     if ((rc = nhwc_map(ctx, dy, d->cout, d->w, d->h, d->n, d->y_ld, ybox, &ty))) return rc;
     WgradHaloArgs a = {};
-    a.ntile_w = d->w / WG_TW;
-    a.ntile_h = d->h / WG_TH;
+    a.ntile_w = cdiv(d->w, WG_TW);
+    a.ntile_h = cdiv(d->h, WG_TH);
     a.n = d->n;
     a.k_tiles_total = p.k_tiles;
     a.k_tiles_per_split = p.per;
@@ -1314,7 +1329,7 @@ int bsl_conv3d_halo_dgrad_strided(bsl_ctx* ctx, const bsl_conv3d_desc* d, const 
 }
 
 bool bsl_conv3d_halo_wgrad_ok(const bsl_conv3d_desc* d) {
-  return !force_v1() && d3_stride1(d) && d->w % WG_TW == 0 && d->h % WG_TH == 0;
+  return !force_v1() && d3_stride1(d) && tiles_ok(d->w, d->h, WG_TW, WG_TH);
 }
 
 namespace {
@@ -1340,7 +1355,7 @@ Wgrad3Plan plan_wgrad3_halo(bsl_ctx* ctx, const bsl_conv3d_desc* d) {
 
 Wgrad3Plan plan_wgrad3_halo_uncached(bsl_ctx* ctx, const bsl_conv3d_desc* d) {
   Wgrad3Plan p = {};
-  p.k_tiles = (d->w / WG_TW) * (d->h / WG_TH) * d->n * d->d;
+  p.k_tiles = cdiv(d->w, WG_TW) * cdiv(d->h, WG_TH) * d->n * d->d;
   const size_t per_tap = (size_t)d->cin * d->cout;
   static const int v2off = getenv("BSL_WGRAD_V2") ? atoi(getenv("BSL_WGRAD_V2")) == 0 : 0;
   p.wide = !v2off && d->cout % 128 == 0;
@@ -1377,8 +1392,8 @@ int bsl_conv3d_halo_wgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x,
   if (p.wide) {
     const Wgrad2Plan& q = p.w2;
     WgradHalo2Args a = {};
-    a.ntile_w = d->w / WG_TW;
-    a.ntile_h = d->h / WG_TH;
+    a.ntile_w = cdiv(d->w, WG_TW);
+    a.ntile_h = cdiv(d->h, WG_TH);
     a.n = d->n * d->d;
     a.k_tiles_total = q.k_tiles;
     a.splits_a = q.splits_a;
@@ -1417,8 +1432,8 @@ int bsl_conv3d_halo_wgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x,
     return BSL_OK;
   }
   WgradHaloArgs a = {};
-  a.ntile_w = d->w / WG_TW;
-  a.ntile_h = d->h / WG_TH;
+  a.ntile_w = cdiv(d->w, WG_TW);
+  a.ntile_h = cdiv(d->h, WG_TH);
   a.n = d->n * d->d;
   a.k_tiles_total = p.k_tiles;
   a.k_tiles_per_split = p.per;

@@ -348,7 +348,8 @@ wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
 // ------------------------------------------------------------------------------------------ fprop / dgrad
 struct ConvHaloArgs {
-  int ntile_w, ntile_h, n;       // sub-tiles of 8 (w) x 16 (h) pixels
+  int ntile_w, ntile_h, n;       // sub-tiles of 8 (w) x 16 (h) pixels: ceil(extent / tile)
+  int vw, vh;                    // true extents of the pixel grid: rows of a sub-tile outside are neither stored nor counted
   int n_sub_total;               // ntile_w * ntile_h * n
   int n_units;                   // ceil(n_sub_total / NSUB) * n_ntiles
   int n_ntiles;                  // column tiles (N / BN)
@@ -861,6 +862,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int img = s / p.ntile_h;
         const long long off = (long long)(tx * 8 + (r & 7)) * p.ostride_x + (long long)(ty * 16 + (r >> 3)) * p.ostride_y +
                               (long long)img * p.ostride_n;
+        const bool inside = tx * 8 + (r & 7) < p.vw && ty * 16 + (r >> 3) < p.vh;   // ragged edge tiles
         __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (NSUB * BN) + j * BN;
         {
@@ -887,7 +889,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const __nv_bfloat16* mk = nullptr;
               if (!SCATTER && p.relu_mask != nullptr && col >= p.mask_col0)
                 mk = reinterpret_cast<const __nv_bfloat16*>(p.relu_mask) + (o - reinterpret_cast<__nv_bfloat16*>(p.out));
-              ch_store_chunk<SCATTER>(hc ? v1 : v0, o, bias, p.relu, packed, p.narrow_store, mk);
+              if (inside) ch_store_chunk<SCATTER>(hc ? v1 : v0, o, bias, p.relu, packed, p.narrow_store, mk);
             }
           }
         }
@@ -900,6 +902,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t tq = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * (NSUB * BN) + sc0;
         __nv_bfloat16* ob[NSUB];
         int grp[NSUB];
+        bool inside[NSUB];
 #pragma unroll
         for (int jj = 0; jj < NSUB; ++jj) {
           int s = pu * NSUB + jj;
@@ -907,6 +910,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           s /= p.ntile_w;
           const int ty = s % p.ntile_h;
           const int img = s / p.ntile_h;
+          inside[jj] = tx * 8 + (r & 7) < p.vw && ty * 16 + (r >> 3) < p.vh;
           grp[jj] = p.stats_group_imgs > 0 ? img / p.stats_group_imgs : 0;
           ob[jj] = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)(tx * 8 + (r & 7)) * p.ostride_x +
                    (long long)(ty * 16 + (r >> 3)) * p.ostride_y + (long long)img * p.ostride_n + n0 + sc0;
@@ -926,7 +930,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint32_t v[32], packed[16];
                 tmem_ld_32x32(tq + jj * BN + c, v);
                 tmem_ld_wait();
-                ch_store_chunk<false>(v, ob[jj] + c, nullptr, 0, packed, p.narrow_store);
+                if (inside[jj]) {
+                  ch_store_chunk<false>(v, ob[jj] + c, nullptr, 0, packed, p.narrow_store);
+                } else {                         // a row of a ragged edge tile outside the image: no store, no count
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) packed[i] = 0u;
+                }
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {   // the bf16 values just stored: what the normalisation pass reads back
                   const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[i]));

@@ -29,6 +29,13 @@ CONV_CASES = [
     (4, 16, 16, 512, 64, 3, None, None),     # long reduction (8 k-blocks): ring wrap-around of both pipelines
     (5, 16, 32, 64, 64, 1, None, None),      # 1x1 through the 1-tap path (stem after im2col)
     (2, 64, 64, 64, 64, 3, None, None),      # many tiles per CTA? no: 64 sub-tiles; wgrad split over pixel tiles
+    # ragged extents on the halo-tile kernels (ceil(extent / tile) tiles, masked edge rows): the deep levels of the shipped
+    # 960 x 320 / 512 x 160 / 480 x 160 scripts
+    (1, 60, 20, 256, 256, 3, None, None),    # level 4 of 960 x 320: column tile 256, TMA-store epilogue clips the edge
+    (2, 20, 12, 128, 128, 3, None, None),    # 20 x 12: both extents ragged, wide filter-gradient kernel
+    (2, 30, 40, 64, 64, 3, None, None),      # level 3 of 480 x 160 / 2: resident filter, column tile 64
+    (1, 24, 36, 128, 64, 3, 192, 128),       # ragged + concat views
+    (3, 10, 8, 64, 128, 1, None, None),      # 1x1, ragged rows
 ]
 
 
@@ -118,7 +125,7 @@ def ctx_bf16(bits):
 def test_conv2d_fprop_fused_statistics(ctx):
     """bsl_conv2d_fprop_stats == bsl_conv2d_fprop followed by bsl_norm_stats (batch mode), on both kernel paths."""
     for (n, h, w, cin, cout, y_ld) in [(2, 32, 32, 64, 64, 64), (3, 16, 24, 128, 192, 256), (2, 12, 20, 64, 128, 128),
-                                       (6, 32, 32, 64, 256, 256)]:
+                                       (6, 32, 32, 64, 256, 256), (3, 30, 20, 64, 64, 64), (2, 20, 36, 128, 128, 128)]:
         rng = np.random.default_rng(h + cout)
         x = bf16_randn(rng, (n, h, w, cin))
         wt = bf16_randn(rng, (3, 3, cin, cout), 0.05)
@@ -154,7 +161,9 @@ def test_conv2d_fprop_fused_statistics(ctx):
     (8, 32, 32, 64, 128, 128, 4),    # UNet3D-style: 4 depth slices per volume
     (2, 64, 64, 64, 64, 64, 1),      # more units than CTAs would take in one round
     (5, 32, 32, 64, 256, 256, 1),    # column tile 256: falls back to the separate statistics pass
-    (2, 12, 20, 64, 128, 128, 1),    # not halo-eligible: general kernel + statistics pass
+    (2, 12, 20, 64, 128, 128, 1),    # ragged extents: edge rows of the tiles are not counted
+    (4, 30, 20, 64, 64, 64, 2),      # ragged, column tile 64 (per-thread running sums), groups of two images
+    (3, 20, 36, 128, 128, 128, 1),   # ragged, column tile 128
 ])
 def test_conv2d_fprop_group_statistics(ctx, n, h, w, cin, cout, y_ld, gi):
     """bsl_conv2d_fprop_group_stats == bsl_conv2d_fprop followed by bsl_norm_stats in instance mode over groups of `gi`
@@ -195,6 +204,7 @@ def test_conv2d_fprop_group_statistics(ctx, n, h, w, cin, cout, y_ld, gi):
     (2, 8, 8, 128, 64, None), (1, 16, 16, 64, 64, None), (2, 4, 8, 256, 128, None), (1, 6, 10, 128, 64, None),
     (2, 8, 8, 128, 64, 128), (1, 2, 2, 1024, 512, 1024),
     (2, 16, 16, 128, 64, 128), (3, 32, 8, 256, 128, None), (1, 16, 24, 64, 64, 192),    # 1-tap halo-kernel path
+    (2, 30, 20, 128, 64, None), (1, 12, 20, 256, 128, 192),                             # ragged extents
     # cout = 32: the half-block form (UNet3D's pixel-pair packed level: both column parities in one 64-wide block)
     (8, 16, 16, 64, 32, 64), (2, 32, 16, 128, 32, None), (4, 16, 8, 64, 32, 64)])
 def test_conv2d_transpose(ctx, n, h, w, cin, cout, y_ld):

@@ -33,6 +33,10 @@ CASES = [  # (n, d, h, w, cin, cout, kernel, stride)
     (2, 2, 64, 16, 64, 64, (1, 3, 2), (1, 2, 1)),      # conv_e1/conv1 on the pair-packed level: 2 phases
     (1, 2, 32, 16, 128, 64, (1, 3, 3), (1, 2, 2)),     # resident filter, two reduction blocks
     (1, 3, 32, 32, 128, 256, (3, 3, 3), (1, 2, 2)),    # conv_e3/conv1: cout 256
+    # ragged extents (the deep levels of the shipped 10 x 512 x 160 volumes): halo-tile kernels with masked edge rows
+    (1, 5, 32, 10, 128, 128, (3, 3, 3), (1, 1, 1)),    # level 4: 32 x 10
+    (1, 4, 40, 24, 64, 128, (3, 3, 3), (1, 2, 2)),     # strided: phase grid 20 x 12
+    (2, 2, 20, 12, 64, 64, (1, 3, 3), (1, 1, 1)),
 ]
 
 
