@@ -93,8 +93,9 @@ def _make(n, hw, **kw):
 
 @pytest.mark.parametrize("n,hw,kw", [
     (2, 64, dict(use_context=True, use_spatial=True, guide_channel=1, loss_type="xentropy+dice")),      # GUNet.yml
-    (3, 64, dict(use_context=True, use_spatial=True, guide_channel=2, norm_with_center=False,
+    (3, 96, dict(use_context=True, use_spatial=True, guide_channel=2, norm_with_center=False,
                  context_fc_channels=(200, 200), loss_type="xentropy")),                                # GUNet_BOTH.yml
+                 # (96 x 96: ragged 6 x 6 / 12 x 12 deep levels on the halo-tile kernels)
     (2, 64, dict(use_context=False, use_spatial=True, guide_channel=2, norm_with_scale=True, mod_layers=(0, 2, 4),
                  loss_type="dice")),
     (2, 64, dict(use_context=True, use_spatial=False, side_dropout=0.0, loss_type="xentropy")),
