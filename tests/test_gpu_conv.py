@@ -39,6 +39,18 @@ CONV_CASES = [
 ]
 
 
+GUARD = np.full(8192, 0xABCD, np.uint16)
+
+
+def guarded(ctx, nbytes):
+    """Zeroed device buffer of `nbytes` followed by a canary region (edge tiles must not store past the tensor)."""
+    return ctx.alloc(nbytes + GUARD.nbytes).zero().upload(GUARD, byte_offset=nbytes)
+
+
+def guard_intact(buf, nbytes):
+    return np.array_equal(buf.download(np.uint16, GUARD.shape, byte_offset=nbytes), GUARD)
+
+
 @pytest.mark.parametrize("n,h,w,cin,cout,k,x_ld,y_ld", CONV_CASES)
 def test_conv2d_fprop_dgrad_wgrad(ctx, n, h, w, cin, cout, k, x_ld, y_ld):
     rng = np.random.default_rng(cin * 7 + cout + h)
@@ -49,19 +61,27 @@ def test_conv2d_fprop_dgrad_wgrad(ctx, n, h, w, cin, cout, k, x_ld, y_ld):
     dx_ = ctx.bf16_from_f32(padded(x, x_ld))
     dw_ = ctx.bf16_from_f32(wt)
     ddy = ctx.bf16_from_f32(padded(dy, y_ld))
-    yo = ctx.alloc(n * h * w * y_ld * 2).zero()
-    dxo = ctx.alloc(n * h * w * x_ld * 2).zero()
+    # a canary region behind every output: edge tiles of ragged extents (and of the last image) must not store past it
+    guard = np.full(8192, 0xABCD, np.uint16)
+    ny, nx = n * h * w * y_ld * 2, n * h * w * x_ld * 2
+    yo = ctx.alloc(ny + guard.nbytes).zero().upload(guard, byte_offset=ny)
+    dxo = ctx.alloc(nx + guard.nbytes).zero().upload(guard, byte_offset=nx)
     desc = _lib.Conv2dDesc(n, h, w, cin, cout, k, k, x_ld, y_ld)
     x64, w64, dy64 = x.astype(np.float64), wt.astype(np.float64), dy.astype(np.float64)
 
+    def intact(buf, nbytes):
+        return np.array_equal(buf.download(np.uint16, guard.shape, byte_offset=nbytes), guard)
+
     ctx.call("bsl_conv2d_fprop", C.byref(desc), dx_.p, dw_.p, yo.p, ctx.stream)
     ctx.check_device()
+    assert intact(yo, ny), "fprop stored past the end of its output"
     got = ctx.bf16_to_f32(yo, (n, h, w, y_ld))
     assert rel(got[..., :cout], O.conv2d(x64, w64)) < TOL_BF16
     assert not got[..., cout:].any(), "fprop wrote outside its channel slice"
 
     ctx.call("bsl_conv2d_dgrad", C.byref(desc), ddy.p, dw_.p, dxo.p, ctx.stream)
     ctx.check_device()
+    assert intact(dxo, nx), "dgrad stored past the end of its output"
     got = ctx.bf16_to_f32(dxo, (n, h, w, x_ld))
     assert rel(got[..., :cin], O.conv2d_backprop_input(x.shape, w64, dy64)) < TOL_BF16
     assert not got[..., cin:].any()
@@ -175,7 +195,7 @@ def test_conv2d_fprop_group_statistics(ctx, n, h, w, cin, cout, y_ld, gi):
     x = round_bf16(bf16_randn(rng, (n, h, w, cin)) + np.arange(n, dtype=np.float32)[:, None, None, None] * 0.25)
     wt = bf16_randn(rng, (3, 3, cin, cout), 0.05)
     dx_, dw_ = ctx.bf16_from_f32(x), ctx.bf16_from_f32(wt)
-    y1 = ctx.alloc(n * h * w * y_ld * 2).zero()
+    y1 = guarded(ctx, n * h * w * y_ld * 2)
     y2 = ctx.alloc(n * h * w * y_ld * 2).zero()
     groups = n // gi
     s1, s2 = ctx.alloc(groups * 2 * cout * 8).zero(), ctx.alloc(groups * 2 * cout * 8).zero()
@@ -185,6 +205,7 @@ def test_conv2d_fprop_group_statistics(ctx, n, h, w, cin, cout, y_ld, gi):
     nd = _lib.NormDesc(1, groups, gi * h * w, cout, y_ld, y_ld, 1e-6, 0.0, 1, 1, 1)
     ctx.call("bsl_norm_stats", C.byref(nd), y2.p, s2.p, ctx.stream)
     ctx.check_device()
+    assert guard_intact(y1, n * h * w * y_ld * 2), "the statistics epilogue stored past the end of its output"
     assert np.array_equal(y1.download(np.uint16, (n, h, w, y_ld)), y2.download(np.uint16, (n, h, w, y_ld)))
     yv = ctx.bf16_to_f32(y1, (n, h, w, y_ld))[..., :cout].astype(np.float64).reshape(groups, -1, cout)
     got = s1.download(np.float64, (groups, 2, cout))
@@ -215,12 +236,13 @@ def test_conv2d_transpose(ctx, n, h, w, cin, cout, y_ld):
     bias = (rng.standard_normal(cout) * 0.1).astype(np.float32)
     dy = bf16_randn(rng, (n, 2 * h, 2 * w, cout))
     dx_, dw_, db_ = ctx.bf16_from_f32(x), ctx.bf16_from_f32(wt), ctx.from_numpy(bias)
-    yo = ctx.alloc(n * 4 * h * w * y_ld * 2).zero()
-    dxo = ctx.alloc(n * h * w * cin * 2).zero()
+    yo = guarded(ctx, n * 4 * h * w * y_ld * 2)
+    dxo = guarded(ctx, n * h * w * cin * 2)
     desc = _lib.ConvT2dDesc(n, h, w, cin, cout, cin, y_ld, 1)
     x64, w64, dy64 = x.astype(np.float64), wt.astype(np.float64), dy.astype(np.float64)
     ctx.call("bsl_convT2d_fwd", C.byref(desc), dx_.p, dw_.p, db_.p, yo.p, ctx.stream)
     ctx.check_device()
+    assert guard_intact(yo, n * 4 * h * w * y_ld * 2), "the scatter epilogue stored past the end of its output"
     got = ctx.bf16_to_f32(yo, (n, 2 * h, 2 * w, y_ld))
     assert rel(got[..., :cout], O.relu(O.conv2d_transpose(x64, w64) + bias)) < TOL_BF16
     assert not got[..., cout:].any()
@@ -236,6 +258,7 @@ def test_conv2d_transpose(ctx, n, h, w, cin, cout, y_ld):
     ddy = ctx.bf16_from_f32(padded(dy, y_ld))
     ctx.call("bsl_convT2d_bwd_data", C.byref(desc), ddy.p, dw_.p, dxo.p, ctx.stream)
     ctx.check_device()
+    assert guard_intact(dxo, n * h * w * cin * 2)
     assert rel(ctx.bf16_to_f32(dxo, (n, h, w, cin)), rdx) < TOL_BF16
     ws_bytes = ctx.lib.bsl_convT2d_bwd_filter_workspace(ctx.h, C.byref(desc))
     ws = ctx.alloc(max(ws_bytes, 16))

@@ -50,8 +50,9 @@ def test_conv3d_fprop_dgrad_wgrad(ctx, n, d, h, w, cin, cout, k, s):
     dy = bf16_randn(rng, (n, od, oh, ow, cout))
     desc = _lib.Conv3dDesc(n, d, h, w, cin, cout, k[0], k[1], k[2], s[0], s[1], s[2], cin, cout)
     bx, bw, bdy = ctx.bf16_from_f32(x), ctx.bf16_from_f32(wt), ctx.bf16_from_f32(dy)
-    by = ctx.alloc(y_ref.size * 2)
-    bdx = ctx.alloc(x.size * 2).zero()
+    guard = np.full(8192, 0xABCD, np.uint16)      # canaries: edge tiles of ragged extents must not store past the tensors
+    by = ctx.alloc(y_ref.size * 2 + guard.nbytes).zero().upload(guard, byte_offset=y_ref.size * 2)
+    bdx = ctx.alloc(x.size * 2 + guard.nbytes).zero().upload(guard, byte_offset=x.size * 2)
     bdw = ctx.alloc(wt.size * 4)
     ws_bytes = ctx.lib.bsl_conv3d_wgrad_workspace(ctx.h, C.byref(desc))
     ws = ctx.alloc(max(ws_bytes, 16))
@@ -62,8 +63,11 @@ def test_conv3d_fprop_dgrad_wgrad(ctx, n, d, h, w, cin, cout, k, s):
     y = ctx.bf16_to_f32(by, y_ref.shape)
     dx = ctx.bf16_to_f32(bdx, x.shape)
     dw = bdw.download(np.float32, wt.shape)
+    ok_y = np.array_equal(by.download(np.uint16, guard.shape, byte_offset=y_ref.size * 2), guard)
+    ok_dx = np.array_equal(bdx.download(np.uint16, guard.shape, byte_offset=x.size * 2), guard)
     for b in (bx, bw, bdy, by, bdx, bdw, ws):
         b.free()
+    assert ok_y and ok_dx, "a store past the end of an output tensor"
     assert rel(y, y_ref) < TOL_BF16
     assert rel(y, round_bf16(y_ref.astype(np.float32))) < 2e-3
     dx_ref = O.conv3d_backprop_input(x.shape, wt.astype(np.float64), dy.astype(np.float64), s)
