@@ -18,7 +18,7 @@ using namespace bsl;
 namespace {
 
 int g_mn_lbo = 8192, g_mn_sbo = 1024, g_mn_kadv = 2048;
-long long* g_dbg_waits = nullptr;   // device [256][4], allocated by bsl_debug_set(ctx, 3, 1)
+long long* g_dbg_waits = nullptr;   // device [1024][4], allocated by bsl_debug_set(ctx, 3, 1)
 
 template <int MODE, bool B_MN, int BN, int STAGES>
 int launch_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const IgemmArgs& args_in, dim3 grid,
@@ -422,16 +422,18 @@ Wgrad2Plan plan_wgrad2_core(bsl_ctx* ctx, int k, int mn, size_t per_tap) {
   Wgrad2Plan best = {};
   const int sms = ctx->sm_count;
   const double fixed = 6.0;  // prologue + epilogue of a CTA, in units of one (tile, accumulator) step
+  static const double tb_tile = getenv("BSL_WG2_TB") ? atof(getenv("BSL_WG2_TB")) : 1.0;   // class-b cost of a pixel tile
   double best_t = 1e300;
   const int max_a = std::max(1, std::min(k / 2, (2 * sms) / mn + 2));
   std::vector<double> free_at(sms);
   for (int na = 1; na <= max_a; ++na) {
     const int per_a = cdiv(k, na), sa = cdiv(k, per_a);
     if (sa != na) continue;
-    for (int nb2 = std::max(1, na / 2 - 1); nb2 <= std::min(na, na / 2 + 2); ++nb2) {   // class b has half the work
+    const int nb_hi = tb_tile > 1.0 ? na + 2 : std::min(na, na / 2 + 2);   // class b has half the MMA work per tile
+    for (int nb2 = std::max(1, na / 2 - 1); nb2 <= nb_hi; ++nb2) {
       const int per_b = cdiv(k, nb2), sb = cdiv(k, per_b);
       if (sb != nb2) continue;
-      const double ta = 2.0 * per_a + fixed, tb = 1.0 * per_b + fixed;
+      const double ta = 2.0 * per_a + fixed, tb = tb_tile * per_b + fixed;
       // in-order dispatch: all class-a CTAs, then class-b, each to the SM that frees up first
       std::fill(free_at.begin(), free_at.end(), 0.0);
       const long long ja = (long long)mn * sa, jb = (long long)mn * sb;
@@ -498,6 +500,7 @@ int conv2d_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const v
   a.out_b = p.splits_b > 1 ? ws + (p.splits_a > 1 ? (long long)p.splits_a * 6 * per_tap : 0) : dw + 6 * per_tap;
   a.kd = 1;
   a.depth = d->n;
+  a.dbg = g_dbg_waits;
   a.status = ctx->d_status;
   static bool configured = false;
   if (!configured) {
@@ -510,6 +513,145 @@ int conv2d_wgrad2(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const v
   if (p.splits_a > 1 && (rc = reduce_splits(ctx, a.out_a, dw, 6 * per_tap, p.splits_a, stream))) return rc;
   if (p.splits_b > 1 && (rc = reduce_splits(ctx, a.out_b, dw + 6 * per_tap, 3 * per_tap, p.splits_b, stream))) return rc;
   return BSL_OK;
+}
+
+// ---- wide wgrad, third generation (wgrad_halo3_kernel): every CTA fills two accumulators per pixel tile. Costs per
+// pixel tile in units of 384 tensor cycles, from the per-CTA cycle counters (tools/gpu_conv_bench.py --ops wgrad --waits).
+bool wgrad3_on() {
+  static const int on = getenv("BSL_WGRAD_V3") ? atoi(getenv("BSL_WGRAD_V3")) != 0 : 1;
+  return on;
+}
+
+Wgrad2Plan plan_wgrad3_core(bsl_ctx* ctx, int k, int ncb, int nnbk, size_t per_tap) {
+  static const double cost_a = getenv("BSL_WG3_TA") ? atof(getenv("BSL_WG3_TA")) : 2.0;
+  static const double cost_b2 = getenv("BSL_WG3_TB2") ? atof(getenv("BSL_WG3_TB2")) : 2.1;   // two input blocks
+  static const double cost_b1 = getenv("BSL_WG3_TB1") ? atof(getenv("BSL_WG3_TB1")) : 1.4;   // lone last input block
+  Wgrad2Plan best = {};
+  const int sms = ctx->sm_count;
+  const double fixed = 6.0;   // prologue + epilogue of a CTA
+  const int ncb_b = cdiv(ncb, 2);
+  const long long mn_a = (long long)ncb * nnbk, mn_b = (long long)ncb_b * nnbk;
+  double best_t = 1e300;
+  const int max_a = std::max(1, std::min(k / 2, (int)((2 * sms) / mn_a) + 2));
+  std::vector<double> heap;
+  for (int na = 1; na <= max_a; ++na) {
+    const int per_a = cdiv(k, na), sa = cdiv(k, per_a);
+    if (sa != na) continue;
+    const int mid = std::max(1, (int)(na * (ncb >= 2 ? cost_b2 : cost_b1) / cost_a + 0.5));
+    for (int nb2 = std::max(1, mid - 2); nb2 <= mid + 2; ++nb2) {
+      if (nb2 > k) break;
+      const int per_b = cdiv(k, nb2), sb = cdiv(k, per_b);
+      if (sb != nb2) continue;
+      // in-order dispatch: all class-a CTAs, then class b, each to the SM that frees up first (min-heap of free times)
+      heap.assign(sms, 0.0);
+      double makespan = 0;
+      auto run = [&](double t) {
+        std::pop_heap(heap.begin(), heap.end(), std::greater<double>());
+        heap.back() += t;
+        makespan = std::max(makespan, heap.back());
+        std::push_heap(heap.begin(), heap.end(), std::greater<double>());
+      };
+      const double ta = cost_a * per_a + fixed;
+      for (long long j = 0; j < mn_a * sa; ++j) run(ta);
+      for (long long j = 0; j < mn_b * sb; ++j) {
+        const int col = (int)(j % ncb_b);
+        run((2 * col + 1 < ncb ? cost_b2 : cost_b1) * per_b + fixed);
+      }
+      makespan += 0.02 * (sa + sb);   // a little pressure towards fewer partials to reduce afterwards
+      if (makespan < best_t) {
+        best_t = makespan;
+        best = {k, sa, per_a, sb, per_b, 0};
+      }
+    }
+  }
+  return best;
+}
+
+// Launch + reduction of the partials; shared by the 2-D layers (kd = 1, depth = n) and UNet3D's stride-1 layers.
+// Partials are [split][kd][taps][cin][cout]; a class with a single split writes its rows of dW directly when kd == 1.
+size_t wgrad3_ws_bytes(const Wgrad2Plan& q, int kd, size_t per_tap) {
+  const bool direct_a = q.splits_a == 1 && kd == 1, direct_b = q.splits_b == 1 && kd == 1;
+  return ((direct_a ? 0 : (size_t)q.splits_a * 6) + (direct_b ? 0 : (size_t)q.splits_b * 3)) * kd * per_tap * sizeof(float);
+}
+
+int launch_wgrad3(bsl_ctx* ctx, const Wgrad2Plan& q, const CUtensorMap& txa, const CUtensorMap& txb, const CUtensorMap& ty,
+                  int w, int h, int n_imgs, int cin, int cout, int kd, int depth, float* dw, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream) {
+  const long long per_tap = (long long)cin * cout;
+  const size_t need = wgrad3_ws_bytes(q, kd, per_tap);
+  if (need > workspace_bytes || (need && !workspace))
+    return bsl_fail(ctx, BSL_EWORKSPACE, "conv wgrad: workspace %zu < %zu", workspace_bytes, need);
+  float* ws = reinterpret_cast<float*>(workspace);
+  const bool direct_a = q.splits_a == 1 && kd == 1, direct_b = q.splits_b == 1 && kd == 1;
+  WgradHalo3Args a = {};
+  a.ntile_w = cdiv(w, WG_TW);
+  a.ntile_h = cdiv(h, WG_TH);
+  a.n = n_imgs;
+  a.k_tiles_total = q.k_tiles;
+  a.ncb = cin / 64;
+  a.nnb = cout / 128;
+  a.ncb_b = cdiv(a.ncb, 2);
+  a.splits_a = q.splits_a;
+  a.per_a = q.per_a;
+  a.splits_b = q.splits_b;
+  a.per_b = q.per_b;
+  a.n_cta_a = a.ncb * a.nnb * kd * q.splits_a;
+  a.cin = cin;
+  a.cout = cout;
+  a.out_a = direct_a ? dw : ws;
+  a.out_b = direct_b ? dw + 6 * per_tap : ws + (direct_a ? 0 : (long long)q.splits_a * kd * 6 * per_tap);
+  a.kd = kd;
+  a.depth = depth;
+  a.dbg = g_dbg_waits;
+  a.status = ctx->d_status;
+  static const int st_a = std::min(WG3_MAX_STAGES, std::max(2, getenv("BSL_WG3_STAGES_A") ? atoi(getenv("BSL_WG3_STAGES_A")) : WG3_STAGES_A));
+  static const int st_b = std::min(6, std::max(2, getenv("BSL_WG3_STAGES_B") ? atoi(getenv("BSL_WG3_STAGES_B")) : WG3_STAGES_B));
+  a.stages_a = st_a;
+  a.stages_b = st_b;
+  const int smem = wg3_smem_bytes(st_a, st_b);
+  static bool configured = false;
+  if (!configured) {
+    BSL_CUDA(ctx, cudaFuncSetAttribute(wgrad_halo3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int grid = a.n_cta_a + a.ncb_b * a.nnb * kd * q.splits_b;
+  bsl_launch(wgrad_halo3_kernel, dim3(grid), dim3(WG_THREADS), smem, stream, txa, txb, ty, a);
+  BSL_LAUNCH_CHECK(ctx, "wgrad_halo3_kernel launch");
+  int rc;
+  for (int k = 0; k < kd; ++k) {   // partial[split][kd][taps] -> dW[kd][9]: split stride = kd * taps * per_tap
+    if (!direct_a && (rc = reduce_splits_strided(ctx, a.out_a + (long long)k * 6 * per_tap, dw + (long long)k * 9 * per_tap,
+                                                 6 * per_tap, q.splits_a, (long long)kd * 6 * per_tap, stream)))
+      return rc;
+    if (!direct_b && (rc = reduce_splits_strided(ctx, a.out_b + (long long)k * 3 * per_tap, dw + ((long long)k * 9 + 6) * per_tap,
+                                                 3 * per_tap, q.splits_b, (long long)kd * 3 * per_tap, stream)))
+      return rc;
+  }
+  return BSL_OK;
+}
+
+const Wgrad2Plan& cached_wgrad3(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
+  static std::mutex mu;
+  static std::unordered_map<unsigned long long, Wgrad2Plan> cache;
+  const unsigned long long key = ((unsigned long long)d->n << 48) ^ ((unsigned long long)d->h << 36) ^
+                                 ((unsigned long long)d->w << 24) ^ ((unsigned long long)d->cin << 12) ^ d->cout;
+  std::lock_guard<std::mutex> g(mu);
+  auto it = cache.find(key);
+  if (it == cache.end())
+    it = cache.emplace(key, plan_wgrad3_core(ctx, cdiv(d->w, WG_TW) * cdiv(d->h, WG_TH) * d->n, d->cin / 64, d->cout / 128,
+                                             (size_t)d->cin * d->cout)).first;
+  return it->second;
+}
+
+int conv2d_wgrad3(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, const void* dy, float* dw, void* workspace,
+                  size_t workspace_bytes, cudaStream_t stream) {
+  const Wgrad2Plan& p = cached_wgrad3(ctx, d);
+  const int xbox_a[4] = {WG_TW + 2, WG_TH + 1, 1, 1}, xbox_b[4] = {WG_TW + 2, WG_TH, 1, 1}, ybox[4] = {WG_TW, WG_TH, 1, 1};
+  CUtensorMap txa, txb, ty;
+  int rc;
+  if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, xbox_a, &txa))) return rc;
+  if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, xbox_b, &txb))) return rc;
+  if ((rc = nhwc_map(ctx, dy, d->cout, d->w, d->h, d->n, d->y_ld, ybox, &ty))) return rc;
+  return launch_wgrad3(ctx, p, txa, txb, ty, d->w, d->h, d->n, d->cin, d->cout, 1, d->n, dw, workspace, workspace_bytes, stream);
 }
 
 WgradPlan plan_wgrad_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
@@ -533,8 +675,8 @@ int bsl_debug_set(bsl_ctx* ctx, int key, int value) {
     case 2: g_mn_kadv = value; return BSL_OK;
     case 3:
       if (value && !g_dbg_waits) {
-        BSL_CUDA(ctx, cudaMalloc(&g_dbg_waits, 256 * 4 * sizeof(long long)));
-        BSL_CUDA(ctx, cudaMemset(g_dbg_waits, 0, 256 * 4 * sizeof(long long)));
+        BSL_CUDA(ctx, cudaMalloc(&g_dbg_waits, 1024 * 4 * sizeof(long long)));
+        BSL_CUDA(ctx, cudaMemset(g_dbg_waits, 0, 1024 * 4 * sizeof(long long)));
       } else if (!value && g_dbg_waits) {
         cudaFree(g_dbg_waits);
         g_dbg_waits = nullptr;
@@ -546,7 +688,7 @@ int bsl_debug_set(bsl_ctx* ctx, int key, int value) {
 }
 
 int bsl_debug_read_waits(bsl_ctx* ctx, long long* out, int ctas) {
-  if (!ctx || !out || ctas < 1 || ctas > 256) return BSL_EINVAL;
+  if (!ctx || !out || ctas < 1 || ctas > 1024) return BSL_EINVAL;
   if (!g_dbg_waits) return bsl_fail(ctx, BSL_EINVAL, "debug waits are off (bsl_debug_set(ctx, 3, 1))");
   BSL_CUDA(ctx, cudaMemcpy(out, g_dbg_waits, (size_t)ctas * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
   return BSL_OK;
@@ -787,7 +929,9 @@ static int conv2d_dgrad_impl(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
 
 size_t bsl_conv2d_wgrad_workspace(bsl_ctx* ctx, const bsl_conv2d_desc* d) {
   if (!ctx || !d || check_conv(ctx, d, true)) return 0;
-  if (wgrad2_eligible(d)) return cached_wgrad2(ctx, d).ws_floats * sizeof(float);
+  if (wgrad2_eligible(d))
+    return wgrad3_on() ? wgrad3_ws_bytes(cached_wgrad3(ctx, d), 1, (size_t)d->cin * d->cout)
+                       : cached_wgrad2(ctx, d).ws_floats * sizeof(float);
   if (wgrad_halo_eligible(d)) {
     const WgradPlan p = plan_wgrad_halo(ctx, d);
     return p.splits > 1 ? (size_t)p.splits * 9 * d->cin * d->cout * sizeof(float) : 0;
@@ -807,7 +951,9 @@ int bsl_conv2d_wgrad(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void* x, cons
   int rc = check_conv(ctx, d, true);
   if (rc) return rc;
   if (!x || !dy || !dw) return bsl_fail(ctx, BSL_EINVAL, "conv2d_wgrad: null buffer");
-  if (wgrad2_eligible(d)) return conv2d_wgrad2(ctx, d, x, dy, dw, workspace, workspace_bytes, as_stream(stream));
+  if (wgrad2_eligible(d))
+    return wgrad3_on() ? conv2d_wgrad3(ctx, d, x, dy, dw, workspace, workspace_bytes, as_stream(stream))
+                       : conv2d_wgrad2(ctx, d, x, dy, dw, workspace, workspace_bytes, as_stream(stream));
   if (wgrad_halo_eligible(d)) {
     const WgradPlan p = plan_wgrad_halo(ctx, d);
     const size_t need = p.splits > 1 ? (size_t)p.splits * 9 * d->cin * d->cout * sizeof(float) : 0;
@@ -1359,7 +1505,10 @@ Wgrad3Plan plan_wgrad3_halo_uncached(bsl_ctx* ctx, const bsl_conv3d_desc* d) {
   const size_t per_tap = (size_t)d->cin * d->cout;
   static const int v2off = getenv("BSL_WGRAD_V2") ? atoi(getenv("BSL_WGRAD_V2")) == 0 : 0;
   p.wide = !v2off && d->cout % 128 == 0;
-  if (p.wide) {
+  if (p.wide && wgrad3_on()) {
+    p.w2 = plan_wgrad3_core(ctx, p.k_tiles, d->cin / 64, (d->cout / 128) * d->kd, per_tap);
+    p.ws_bytes = wgrad3_ws_bytes(p.w2, d->kd, per_tap);
+  } else if (p.wide) {
     p.w2 = plan_wgrad2_core(ctx, p.k_tiles, (d->cin / 64) * (d->cout / 128) * d->kd, per_tap);
     const bool direct_a = p.w2.splits_a == 1 && d->kd == 1, direct_b = p.w2.splits_b == 1 && d->kd == 1;
     p.ws_bytes = ((direct_a ? 0 : (size_t)p.w2.splits_a * 6) + (direct_b ? 0 : (size_t)p.w2.splits_b * 3)) * d->kd * per_tap *
@@ -1389,6 +1538,13 @@ int bsl_conv3d_halo_wgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x,
   if ((rc = ndhwc_halo_map(ctx, dy, d->cout, d->w, d->h, d->d, d->n, d->y_ld, WG_TW, WG_TH, &ty))) return rc;
   const long long per_tap = (long long)d->cin * d->cout;
   float* ws = reinterpret_cast<float*>(workspace);
+  if (p.wide && wgrad3_on()) {
+    CUtensorMap txa, txb;
+    if ((rc = ndhwc_halo_map(ctx, x, d->cin, d->w, d->h, d->d, d->n, d->x_ld, WG_TW + 2, WG_TH + 1, &txa))) return rc;
+    if ((rc = ndhwc_halo_map(ctx, x, d->cin, d->w, d->h, d->d, d->n, d->x_ld, WG_TW + 2, WG_TH, &txb))) return rc;
+    return launch_wgrad3(ctx, p.w2, txa, txb, ty, d->w, d->h, d->n * d->d, d->cin, d->cout, d->kd, d->d, dw, workspace,
+                         workspace_bytes, stream);
+  }
   if (p.wide) {
     const Wgrad2Plan& q = p.w2;
     WgradHalo2Args a = {};

@@ -204,6 +204,8 @@ struct WgradHalo2Args {
   float* out_a;                  // [splits_a][kd][6][cin][cout]
   float* out_b;                  // [splits_b][kd][3][cin][cout]
   int kd, depth;                 // filter depth: blockIdx.z = class offset + kdi * splits + split
+  long long* dbg;                // tuning (bsl_debug_set key 3): per CTA (linear id < 1024) {issuer cycles, cycles waiting for
+                                 // a full stage, class (0 = rows 0,1; 1 = row 2) << 32 | pixel tiles, start ns}
   DeviceStatus* status;
 };
 
@@ -292,8 +294,14 @@ wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
+      const bool timed = p.dbg != nullptr;
+      long long t_all = 0, w_full = 0, t0 = 0;
+      unsigned long long ns0 = 0;
+      if (timed) { t_all = clock64(); ns0 = globaltimer_ns(); }
       for (int kk = 0; kk < num_k; ++kk) {
+        if (timed) t0 = clock64();
         if (!mbar_wait(full0 + 8 * stage, phase, st, 15)) { ok = false; break; }
+        if (timed) w_full += clock64() - t0;
         tc_fence_after();
         const uint32_t sx = smem_base + stage * WG2_STAGE_BYTES;
         const uint64_t da0 = make_smem_desc_sw128(sx + WG_X_BYTES, WG_DY_BYTES, 1024);
@@ -312,6 +320,15 @@ wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
       if (ok) umma_commit(tfull);
       pdl_trigger_late();
+      if (timed) {
+        const int id = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        if (id < 1024) {
+          p.dbg[id * 4 + 0] = clock64() - t_all;
+          p.dbg[id * 4 + 1] = w_full;
+          p.dbg[id * 4 + 2] = ((long long)(type_a ? 0 : 1) << 32) | num_k;
+          p.dbg[id * 4 + 3] = (long long)ns0;
+        }
+      }
     }
   } else {
     const int q4 = warp & 3;
@@ -331,6 +348,212 @@ wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           tmem_ld_wait();
           const int tap = a * 3 + c / 64;             // local tap index within this CTA's rows
           float* o = obase + ((long long)tap * p.cin + cb * 64 + (c & 63)) * p.cout;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[(long long)j * p.cout] = num_k ? __uint_as_float(v[j]) : 0.f;
+        }
+      }
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad, wide, v3
+// Third filter-gradient kernel (cout % 128 == 0). Per-CTA cycle counters in wgrad_halo2_kernel (tools/gpu_conv_bench.py
+// --ops wgrad --waits, profiles/r02_wgrad_class_timing.log) showed its two CTA classes apart: the rows-0,1 class issues a
+// pixel tile's 8 UMMAs (768 tensor cycles) every ~790 cycles, but the row-2 class needs ~630 cycles for 4 UMMAs (384 tensor
+// cycles): a CTA cannot take in more than ~48 B per cycle from L2 (30 KB of operands per tile either way), and the split
+// planner, which assumed half the time for half the MMAs, left the row-2 CTAs running long after the others had finished.
+// Here every CTA fills two 192-column accumulators per pixel tile and loads only the halo rows it reads:
+//   class a   filter rows 0, 1 of ONE 64-channel input block:  x box 18 x 5 pixels (11.25 KB) + dy (16 KB) per tile
+//   class b   filter row 2 of TWO input blocks:                 2 x box 18 x 4 pixels (18 KB) + dy (16 KB) per tile
+// (a lone last input block, cin / 64 odd, runs with one accumulator). Linear grid: all class-a CTAs, then class b, with
+// (input block, output block) fastest so that CTAs resident together share x / dy tiles in L2.
+struct WgradHalo3Args {
+  int ntile_w, ntile_h, n;       // pixel tiles of 16 (w) x 4 (h)
+  int k_tiles_total;
+  int ncb, nnb, ncb_b;           // cin / 64, cout / 128, ceil(ncb / 2)
+  int splits_a, per_a;           // class a: pixel tiles [zi * per_a, ...)
+  int splits_b, per_b;
+  int n_cta_a;                   // ncb * nnb * kd * splits_a
+  int cin, cout;
+  float* out_a;                  // [splits_a][kd][6][cin][cout]
+  float* out_b;                  // [splits_b][kd][3][cin][cout]
+  int kd, depth;                 // filter depth (slice z + kdi - kd / 2 of the volume); slices per volume
+  int stages_a, stages_b;        // pipeline depth per class (<= WG3_MAX_STAGES); the launch sizes shared memory to match
+  long long* dbg;                // tuning (bsl_debug_set key 3): per CTA {issuer cycles, cycles waiting for a full stage,
+                                 // class << 32 | pixel tiles, start ns}
+  DeviceStatus* status;
+};
+
+constexpr int WG3_XA_BYTES = 12288;                                  // 18 x 5 pixels x 128 B = 11520, padded to 1024
+constexpr int WG3_XB_BYTES = WG_PITCH * WG_TH * 128;                 // 18 x 4 pixels x 128 B = 9216
+constexpr int WG3_STAGE_A = WG3_XA_BYTES + WG2_DY_BYTES;             // 28672
+constexpr int WG3_STAGE_B = 2 * WG3_XB_BYTES + WG2_DY_BYTES;         // 34816
+// Pipeline depth: 8 / 6 stages fit (225 KB), but a CTA that fills the SM's shared memory keeps the HBM-bound passes of
+// the main stream from running beside it (the filter gradient runs on a side stream). Timed alone the kernel is equally
+// fast with 5 .. 8 stages (4 / 3 stages: 5 % slower); 6 / 5 stages = 171 KB leave room for the neighbours
+// (BSL_WG3_STAGES_A / _B; profiles/r02_ab_experiments.md).
+constexpr int WG3_MAX_STAGES = 8;
+constexpr int WG3_STAGES_A = 6, WG3_STAGES_B = 5;
+constexpr int wg3_smem_bytes(int sa, int sb) {
+  return (sa * WG3_STAGE_A > sb * WG3_STAGE_B ? sa * WG3_STAGE_A : sb * WG3_STAGE_B) + 1024;
+}
+
+__global__ void __launch_bounds__(WG_THREADS)
+wgrad_halo3_kernel(const __grid_constant__ CUtensorMap tmXa, const __grid_constant__ CUtensorMap tmXb,
+                   const __grid_constant__ CUtensorMap tmDY, const WgradHalo3Args p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * WG3_MAX_STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int dead;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t full0 = smem_u32(&bars[0]);
+  const uint32_t empty0 = smem_u32(&bars[WG3_MAX_STAGES]);
+  const uint32_t tfull = smem_u32(&bars[2 * WG3_MAX_STAGES]);
+  DeviceStatus* st = p.status;
+
+  pdl_trigger();
+  if (threadIdx.x == 0) dead = *reinterpret_cast<volatile int*>(&st->error);
+  __syncthreads();
+  if (dead) return;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmXa);
+    prefetch_tensormap(&tmXb);
+    prefetch_tensormap(&tmDY);
+    for (int s = 0; s < WG3_MAX_STAGES; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  } else if (warp == 1) {
+    tmem_alloc<512>(smem_u32(&tmem_slot));
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();   // the prologue above touches no data of the previous kernel in the stream
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
+
+  // ---- which part of dW this CTA owns
+  const bool type_a = (int)blockIdx.x < p.n_cta_a;
+  int id = type_a ? blockIdx.x : blockIdx.x - p.n_cta_a;
+  const int ncol = type_a ? p.ncb : p.ncb_b;
+  const int col = id % ncol;
+  id /= ncol;
+  const int nb = id % p.nnb;
+  const int zz = id / p.nnb;
+  const int nsplit = type_a ? p.splits_a : p.splits_b;
+  const int kdi = zz / nsplit, zi = zz - kdi * nsplit;
+  const int per = type_a ? p.per_a : p.per_b;
+  const int k_begin = zi * per;
+  const int k_end = min(p.k_tiles_total, k_begin + per);
+  const int num_k = max(k_end - k_begin, 0);
+  const int cb0 = type_a ? col : 2 * col;                       // first 64-channel input block
+  const int nacc = type_a ? 2 : min(2, p.ncb - cb0);            // accumulators: filter rows 0, 1 / input blocks cb0, cb0 + 1
+  const int nstage = type_a ? p.stages_a : p.stages_b;
+  const int stage_bytes = type_a ? WG3_STAGE_A : WG3_STAGE_B;
+  const int dy_off = type_a ? WG3_XA_BYTES : 2 * WG3_XB_BYTES;
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = (type_a ? WG_PITCH * (WG_TH + 1) * 128 : nacc * WG3_XB_BYTES) + WG2_DY_BYTES;
+      for (int kk = 0; kk < num_k; ++kk) {
+        if (!mbar_wait(empty0 + 8 * stage, phase ^ 1, st, 17)) break;
+        int t = k_begin + kk;
+        const int tx = t % p.ntile_w;
+        t /= p.ntile_w;
+        const int ty = t % p.ntile_h;
+        const int img = t / p.ntile_h;
+        const uint32_t fb = full0 + 8 * stage;
+        const uint32_t sx = smem_base + stage * stage_bytes;
+        mbar_arrive_expect_tx(fb, tx_bytes);
+        const int z = img % p.depth, vol = img / p.depth;
+        const int zx = z + kdi - (p.kd >> 1);
+        if (type_a) {
+          tma_load_5d(sx, &tmXa, fb, cb0 * 64, tx * WG_TW - 1, ty * WG_TH - 1, zx, vol);
+        } else {
+          tma_load_5d(sx, &tmXb, fb, cb0 * 64, tx * WG_TW - 1, ty * WG_TH + 1, zx, vol);
+          if (nacc == 2) tma_load_5d(sx + WG3_XB_BYTES, &tmXb, fb, cb0 * 64 + 64, tx * WG_TW - 1, ty * WG_TH + 1, zx, vol);
+        }
+        tma_load_5d(sx + dy_off, &tmDY, fb, nb * 128, tx * WG_TW, ty * WG_TH, z, vol);
+        tma_load_5d(sx + dy_off + WG_DY_BYTES, &tmDY, fb, nb * 128 + 64, tx * WG_TW, ty * WG_TH, z, vol);
+        if (++stage == nstage) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 192, true, true);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      const bool timed = p.dbg != nullptr;
+      long long t_all = 0, w_full = 0, t0 = 0;
+      unsigned long long ns0 = 0;
+      if (timed) { t_all = clock64(); ns0 = globaltimer_ns(); }
+      // accumulator a reads the halo tile at acc_off * a: the next filter row (class a) or the next input block (class b)
+      const uint32_t acc_off = type_a ? WG_PITCH * 128 : WG3_XB_BYTES;
+      for (int kk = 0; kk < num_k; ++kk) {
+        if (timed) t0 = clock64();
+        if (!mbar_wait(full0 + 8 * stage, phase, st, 18)) { ok = false; break; }
+        if (timed) w_full += clock64() - t0;
+        tc_fence_after();
+        const uint32_t sx = smem_base + stage * stage_bytes;
+        const uint64_t da0 = make_smem_desc_sw128(sx + dy_off, WG_DY_BYTES, 1024);
+        const uint32_t first = kk != 0;
+#pragma unroll
+        for (int y = 0; y < WG_TH; ++y) {
+          for (int a = 0; a < nacc; ++a) {
+            // three taps of one filter row: 64-channel blocks one pixel (128 B) apart, the 16 pixels of row y as K
+            const uint64_t db = make_smem_desc_sw128(sx + a * acc_off + (y * WG_PITCH) * 128, 128, 1024);
+            umma_bf16(tmem_base + a * 192, da0 + (uint64_t)((y * WG_TW * 128) >> 4), db, idesc,
+                      first | (uint32_t)(y != 0));
+          }
+        }
+        umma_commit(empty0 + 8 * stage);
+        if (++stage == nstage) { stage = 0; phase ^= 1; }
+      }
+      if (ok) umma_commit(tfull);
+      pdl_trigger_late();
+      if (timed && blockIdx.x < 1024) {
+        p.dbg[blockIdx.x * 4 + 0] = clock64() - t_all;
+        p.dbg[blockIdx.x * 4 + 1] = w_full;
+        p.dbg[blockIdx.x * 4 + 2] = ((long long)(type_a ? 0 : 1) << 32) | num_k;
+        p.dbg[blockIdx.x * 4 + 3] = (long long)ns0;
+      }
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;  // accumulator row = output channel within the 128-block
+    const bool alive = mbar_wait(tfull, 0, st, 19);
+    tc_fence_after();
+    if (alive) {
+      const uint32_t trow = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+      const int ntap = type_a ? 6 : 3;
+      float* obase = (type_a ? p.out_a : p.out_b) + ((long long)zi * p.kd + kdi) * ntap * p.cin * p.cout + nb * 128 + row;
+#pragma unroll 1
+      for (int a = 0; a < nacc; ++a) {
+        const int tap0 = type_a ? a * 3 : 0;          // first local tap of this accumulator
+        const int cblk = type_a ? cb0 : cb0 + a;      // its 64-channel input block
+#pragma unroll 1
+        for (int c = 0; c < 192; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + a * 192 + c, v);
+          tmem_ld_wait();
+          float* o = obase + ((long long)(tap0 + c / 64) * p.cin + cblk * 64 + (c & 63)) * p.cout;
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[(long long)j * p.cout] = num_k ? __uint_as_float(v[j]) : 0.f;
         }

@@ -94,6 +94,23 @@ for name in a.layers.split(","):
         ctx.check_device()
         tot[op] = tot.get(op, 0.0) + ms
         print(f"{name:8s} {op:6s} hw={hw:3d} cin={cin:4d} cout={cout:4d}  {ms:7.3f} ms  {flops / ms / 1e9:7.1f} TF/s", flush=True)
+        if a.waits and op == "wgrad" and cout % 128 == 0:
+            wt = np.zeros((1024, 4), np.int64)
+            ctx.call("bsl_debug_read_waits", wt.ctypes.data_as(C.c_void_p), C.c_int(1024))
+            ctx.call("bsl_debug_set", C.c_int(3), C.c_int(0))   # fresh (zeroed) buffer for the next layer
+            ctx.call("bsl_debug_set", C.c_int(3), C.c_int(1))
+            ok = wt[:, 0] > 0
+            cls, tiles = wt[:, 2] >> 32, wt[:, 2] & 0xffffffff
+            t_start = wt[ok, 3].min()
+            for c in (0, 1):
+                m = ok & (cls == c)
+                if not m.any():
+                    continue
+                cyc, wf = wt[m, 0].astype(np.float64), wt[m, 1].astype(np.float64)
+                print(f"         class {'ab'[c]}: {m.sum():4d} CTAs x {tiles[m].mean():6.1f} tiles  issuer {cyc.mean():9.0f} cycles "
+                      f"(max {cyc.max():9.0f}) = {(cyc / np.maximum(tiles[m], 1)).mean():6.0f} / tile, waiting for a stage "
+                      f"{100 * (wf / cyc).mean():5.1f} %, start +{(wt[m, 3] - t_start).mean() / 1e3:6.1f} us "
+                      f"(last +{(wt[m, 3] - t_start).max() / 1e3:6.1f})", flush=True)
         if a.waits and op != "wgrad":
             wt = np.zeros((148, 4), np.int64)
             ctx.call("bsl_debug_read_waits", wt.ctypes.data_as(C.c_void_p), C.c_int(148))
