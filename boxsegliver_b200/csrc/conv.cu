@@ -393,6 +393,8 @@ void halo_common(ConvHaloArgs& a, const HaloPlan& p, int w, int h, int n) {
   a.n_ntiles = p.n_ntiles;
   static const int narrow = getenv("BSL_NARROW_STORE") ? atoi(getenv("BSL_NARROW_STORE")) : 0;
   a.narrow_store = narrow;
+  static const int slow_issue = getenv("BSL_SLOW_ISSUE") ? atoi(getenv("BSL_SLOW_ISSUE")) : 0;
+  a.slow_issue = slow_issue;
   a.dbg = g_dbg_waits;
   a.kd = 1;        // 2-D: every image is its own one-slice "volume" (tensor map dims (c, w, h, n, 1))
   a.depth = n;

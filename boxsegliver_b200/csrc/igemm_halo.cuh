@@ -604,6 +604,7 @@ struct ConvHaloArgs {
   const int* wait_flags;
   int wait_epoch, wait_imgs;
   int narrow_store;              // tuning: 128-bit epilogue stores instead of 256-bit (BSL_NARROW_STORE=1)
+  int slow_issue;                // tuning: the generic UMMA issue loop also for 3x3 windows (BSL_SLOW_ISSUE=1)
   // ---- transposed-conv backward-data: the A tensor map is upsampled_map (c, b, w, a, n*h); the reduction runs over
   //      (a = kd index, b, 64-channel block): K block cbx -> a = cbx / cblocks, b = cb / up_cpb, channel (cb % up_cpb) * 64
   int up_cpb;                    // 0 = ordinary (c, x, y, z, vol) coordinates
@@ -634,7 +635,9 @@ struct ConvHaloCfg {
   static constexpr int A_BYTES = NSUB * CH_SUB_BYTES;
   // three activation stages hide the HBM latency of the one-block-deep reductions (Cin = 64: a unit is
   // ~1.5 us of MMAs); the widest column tile only occurs with long reductions and keeps two.
-  static constexpr int A_STAGES = BN == 256 ? 2 : 3;
+  // 256-wide tiles, and 128-wide tiles over sub-tile pairs: two activation stages (a stage is a whole 64-channel block of
+  // the reduction, 9 taps of MMAs) leave room for 7 instead of 4 filter stages, which is what the issuer waits for there
+  static constexpr int A_STAGES = (BN == 256 || (BN == 128 && NSUB == 2)) ? 2 : 3;
   static constexpr int B_FIT = (212 * 1024 - (TMA_ST ? CH_STAGING_BYTES : 0) - A_STAGES * A_BYTES) / B_BYTES;
   static constexpr int B_STAGES = B_FIT > 8 ? 8 : (B_FIT < 3 ? 3 : B_FIT);
   static constexpr int SMEM_BYTES = A_STAGES * A_BYTES + B_STAGES * B_BYTES + 1024 + (TMA_ST ? CH_STAGING_BYTES : 0);
@@ -906,6 +909,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t pa = 0, pb = 0, pacc = 0;
       bool ok = true;
       long long t_all = clock64(), w_acc = 0, w_a = 0, w_b = 0, t0;
+      const bool timed = p.dbg != nullptr;
+      const bool fast9 = p.ntaps == 9 && p.halo != 0 && p.tap_table == 0 && p.slow_issue == 0;
+      const uint64_t db_base = B_MN ? make_smem_desc_sw128(sB0, 8192, 1024) : make_smem_desc_sw128(sB0, 16, 1024);
       if (B_RES && (int)blockIdx.x < p.n_units) ok = mbar_wait(b_full, 0, st, 27);
       for (int u = blockIdx.x; u < p.n_units && ok; u += gridDim.x) {
         const int pu = u / p.n_ntiles;
@@ -922,6 +928,41 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           w_a += clock64() - t0;
           const uint32_t a_stage = sA0 + sa * A_BYTES;
           if (B_RES) tc_fence_after();
+          if (fast9 && nsub == NSUB) {
+            // 3x3 window over a full unit, straight-line: every descriptor is a base plus an IMMEDIATE (tap offset inside
+            // the halo tile, sub-tile, K slice): ~2.5 instructions per UMMA. The generic loop below spends ~10 (offset
+            // arithmetic, parameter loads, vector-to-uniform moves) in this single thread, which bounded the 128-wide tiles
+            // (8 UMMAs of 64 cycles per tap): -14 % on those layers, -4 % on the 64-wide, -2 % on the 256-wide ones
+            // (tools/gpu_conv_bench.py, BSL_SLOW_ISSUE=1 for the old loop; profiles/r02_ab_experiments.md).
+            const uint64_t da = make_smem_desc_sw128(a_stage, 16, 10 * 128);
+            const uint64_t db_res = db_base + (uint64_t)((cb * 9 * B_BYTES) >> 4);
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              uint64_t db0;
+              if (B_RES) {
+                db0 = db_res + (uint64_t)((tap * B_BYTES) >> 4);
+              } else {
+                if (timed) t0 = clock64();
+                if (!mbar_wait(b_full + 8 * sb, pb, st, 25)) { ok = false; break; }
+                if (timed) w_b += clock64() - t0;
+                tc_fence_after();
+                db0 = db_base + (uint64_t)((sb * B_BYTES) >> 4);
+              }
+              const int toff = ((tap / 3) * 10 + tap % 3) * 128;
+#pragma unroll
+              for (int j = 0; j < NSUB; ++j) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(acc + j * BN, da + (uint64_t)((toff + j * CH_SUB_BYTES + k * 32) >> 4),
+                            db0 + (uint64_t)((B_MN ? k * 2048 : k * 32) >> 4), idesc,
+                            (tap == 0 && k == 0) ? (uint32_t)(cb != 0) : 1u);
+              }
+              if (!B_RES) {
+                umma_commit(b_empty + 8 * sb);
+                if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+              }
+            }
+          } else
           for (int tap = 0; tap < p.ntaps; ++tap) {
             if (!B_RES) {
               t0 = clock64();

@@ -117,7 +117,7 @@ for name in a.layers.split(","):
             cyc = wt[:, 0].astype(np.float64)
             ok = cyc > 0
             f = lambda k: 100.0 * (wt[ok, k] / cyc[ok]).mean()   # noqa: E731
-            print(f"         issuer: {cyc[ok].mean():.0f} cycles; waiting acc_empty {f(1):.1f}%  a_full {f(2):.1f}%  "
+            print(f"         issuer: {cyc[ok].mean():.0f} cycles (min {cyc[ok].min():.0f}, max {cyc[ok].max():.0f}, {ok.sum()} CTAs); waiting acc_empty {f(1):.1f}%  a_full {f(2):.1f}%  "
                   f"b_full {f(3):.1f}%  issuing {100 - f(1) - f(2) - f(3):.1f}%", flush=True)
     for b in (x, dy, w, y, dx, dw, sums, ws):
         b.free()
