@@ -237,6 +237,7 @@ int launch_halo_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, co
 
 struct HaloPlan {
   int bn, nsub, n_ntiles, n_sub_total, n_units, grid, slots;
+  int pair;   // planned for CTA pairs (pair_replan): 128-wide tiles over sub-tile pairs, plain epilogue
 };
 
 template <int BN, int NSUB, bool B_MN, bool STATS, bool SCATTER>
@@ -293,6 +294,26 @@ void replan_units(bsl_ctx* ctx, HaloPlan& p) {
   p.slots = cdiv(p.grid, p.n_ntiles);
 }
 
+bool pair_on() {
+  static const int on = getenv("BSL_PAIR") ? atoi(getenv("BSL_PAIR")) != 0 : 1;
+  return on;
+}
+// CTA pairs run 128-wide tiles: per CTA a pair takes in half of every filter slice, so the narrower tile costs no more
+// filter traffic than a 256-wide tile of a single CTA, and twice as many units fill the 148 SMs evenly (512 units of a
+// 512-channel layer at 32 x 32 are 3.46 per SM -- the last of 4 rounds is half empty; 1024 are 6.92) with the accumulators
+// double-buffered. Measured on the wide cfg2 layers: -10 % against single CTAs with 256-wide tiles
+// (profiles/r02_ab_experiments.md). min_cols: fprop keeps its fused statistics for 128-column layers.
+bool pair_replan(bsl_ctx* ctx, HaloPlan& p, int ncols, int min_cols, int ntaps) {
+  static const int env_bn = getenv("BSL_HALO_BN") ? atoi(getenv("BSL_HALO_BN")) : 0;
+  if (!pair_on() || env_bn || ntaps != 9 || ncols % 128 || ncols < min_cols || p.n_sub_total % 4) return false;
+  p.bn = 128;
+  p.nsub = 2;
+  p.n_ntiles = ncols / 128;
+  replan_units(ctx, p);
+  p.pair = 1;
+  return true;
+}
+
 // Which column-tile widths use the TMA-store epilogue (BSL_TMA_STORE: 0 none, 1 = 256-wide tiles, 2 = also 128).
 int tma_store_level() {
   static const int v = getenv("BSL_TMA_STORE") ? atoi(getenv("BSL_TMA_STORE")) : 1;
@@ -311,11 +332,40 @@ int out_map(bsl_ctx* ctx, const ConvHaloArgs& a, int w, int h, CUtensorMap* out)
   return bsl_get_tmap(ctx, a.out, 4, dims, str, bx, out);
 }
 
+// CTA pairs (conv_halo_kernel<..., PAIR>): 256-wide tiles of 3x3 windows whose sub-tile count is a multiple of 4 (a pair
+// works on two units of two sub-tiles and the same column tile). `b_half`: for a K-major filter (dgrad) the tensor map
+// whose box holds HALF the tile's rows; an MN-major filter (fprop) is loaded in 64-column blocks either way.
+bool pair_eligible(const ConvHaloArgs& a, int bn, int nsub) {
+  return pair_on() && (bn == 256 || bn == 128) && nsub == 2 && a.n_sub_total % 4 == 0 && a.ntaps == 9 && a.halo == 1 && !a.tap_table &&
+         a.wait_flags == nullptr && a.up_cpb == 0 && a.relu_mask == nullptr;
+}
+template <int BN, bool B_MN>
+int launch_halo_pair(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args, cudaStream_t stream,
+                     const CUtensorMap& o) {
+  auto kern = conv_halo_kernel<BN, 2, B_MN, false, false, false, true, true>;
+  constexpr int smem = ConvHaloCfg<BN, 2, true, true>::SMEM_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    BSL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int pairs = std::min(args.n_units / 2, ctx->sm_count / 2);
+  bsl_launch_cluster(kern, dim3(2 * pairs), dim3(CH_THREADS), smem, stream, 2, a, b, o, args);
+  BSL_LAUNCH_CHECK(ctx, "conv_halo_kernel (CTA pairs) launch");
+  return BSL_OK;
+}
+
 template <bool B_MN, bool STATS, bool SCATTER>
 int launch_halo(bsl_ctx* ctx, int bn, int nsub, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args,
-                int grid, cudaStream_t stream) {
+                int grid, cudaStream_t stream, const CUtensorMap* b_half = nullptr) {
   if constexpr (!STATS && !SCATTER) {
     const int lvl = tma_store_level();
+    if (pair_eligible(args, bn, nsub) && (B_MN || b_half != nullptr)) {
+      CUtensorMap o;
+      if (out_map(ctx, args, args.vw, args.vh, &o) == 0)
+        return bn == 256 ? launch_halo_pair<256, B_MN>(ctx, a, B_MN ? b : *b_half, args, stream, o)
+                         : launch_halo_pair<128, B_MN>(ctx, a, B_MN ? b : *b_half, args, stream, o);
+    }
     if (args.relu_mask == nullptr && ((bn == 256 && lvl >= 1) || (bn == 128 && lvl >= 2))) {
       CUtensorMap o;
       if (out_map(ctx, args, args.vw, args.vh, &o) == 0) {
@@ -354,7 +404,7 @@ bool tiles_ok(int w, int h, int tw, int th) {
 bool halo_eligible(int w, int h) { return !force_v1() && tiles_ok(w, h, 8, 16); }
 
 HaloPlan plan_halo(bsl_ctx* ctx, int w, int h, int n, int ncols) {
-  HaloPlan p;
+  HaloPlan p = {};
   p.n_sub_total = cdiv(w, 8) * cdiv(h, 16) * n;
   p.bn = ncols % 256 == 0 ? 256 : (ncols % 128 == 0 ? 128 : 64);
   p.nsub = p.n_sub_total % 2 == 0 ? 2 : 1;
@@ -707,7 +757,7 @@ static int launch_fprop_halo_stats(bsl_ctx* ctx, const HaloPlan& pl, bool res, i
                : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
   const int groups = group_imgs > 0 ? n_imgs / group_imgs : 1;
   const long long ppg = group_imgs > 0 ? (long long)group_imgs * h * w : (long long)n_imgs * h * w;
-  if (pl.bn == 256 || (group_imgs > 0 && pl.grid % pl.n_ntiles != 0)) {
+  if (pl.bn == 256 || pl.pair || (group_imgs > 0 && pl.grid % pl.n_ntiles != 0)) {
     // long-reduction layers: small, L2-resident outputs; a separate statistics pass is cheaper than an
     // un-overlapped epilogue butterfly
     if ((rc = res ? launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
@@ -753,6 +803,7 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
   int res_stages = 0, res_smem = 0;
   const bool res = plan_resident(pl.bn, d->kh * d->kw, d->cin / 64, &pl.nsub, &res_stages, &res_smem);
   if (res) replan_units(ctx, pl);
+  else if (!wait) pair_replan(ctx, pl, d->cout, 256, d->kh * d->kw);
   const int box[4] = {8 + 2 * halo, 16 + 2 * halo, 1, 1};
   CUtensorMap ta, tb;
   int rc;
@@ -879,6 +930,7 @@ static int conv2d_dgrad_impl(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
     int res_stages = 0, res_smem = 0;
     const bool res = plan_resident(pl.bn, d->kh * d->kw, d->cout / 64, &pl.nsub, &res_stages, &res_smem);
     if (res) replan_units(ctx, pl);
+    else if (!wait && !relu_act) pair_replan(ctx, pl, d->cin, 128, d->kh * d->kw);
     const int hbox[4] = {8 + 2 * halo, 16 + 2 * halo, 1, 1};
     CUtensorMap ta, tb;
     if ((rc = nhwc_map(ctx, dy, d->cout, d->w, d->h, d->n, d->y_ld, hbox, &ta))) return rc;
@@ -901,8 +953,11 @@ static int conv2d_dgrad_impl(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
     if ((rc = attach_wait(ctx, a, wait, d->n))) return rc;
     a.relu_mask = relu_act;
     a.mask_col0 = mask_col0;
-    return res ? launch_halo_res<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream))
-               : launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream));
+    if (res) return launch_halo_res<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream));
+    CUtensorMap tbh;
+    const bool pair = pair_eligible(a, pl.bn, pl.nsub) &&
+                      matrix_map(ctx, w, d->cout, d->kh * d->kw * d->cin, 64, pl.bn / 2, &tbh) == 0;
+    return launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream), pair ? &tbh : nullptr);
   }
   int box[4] = {0, 0, 0, 1};
   pick_box(128, d->w, d->h, d->n, &box[0], &box[1], &box[2]);
@@ -1334,6 +1389,7 @@ int bsl_conv3d_halo_fprop(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* x,
   int res_stages = 0, res_smem = 0;
   const bool res = plan_resident(pl.bn, 9 * d->kd, d->cin / 64, &pl.nsub, &res_stages, &res_smem);
   if (res) replan_units(ctx, pl);
+  else pair_replan(ctx, pl, d->cout, 256, 9);
   CUtensorMap ta, tb;
   int rc;
   if ((rc = ndhwc_halo_map(ctx, x, d->cin, d->w, d->h, d->d, d->n, d->x_ld, 10, 18, &ta))) return rc;
@@ -1364,6 +1420,7 @@ int bsl_conv3d_halo_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy
   int res_stages = 0, res_smem = 0;
   const bool res = plan_resident(pl.bn, 9 * d->kd, d->cout / 64, &pl.nsub, &res_stages, &res_smem);
   if (res) replan_units(ctx, pl);
+  else pair_replan(ctx, pl, d->cin, 128, 9);
   CUtensorMap ta, tb;
   int rc;
   if ((rc = ndhwc_halo_map(ctx, dy, d->cout, d->w, d->h, d->d, d->n, d->y_ld, 10, 18, &ta))) return rc;
@@ -1385,8 +1442,11 @@ int bsl_conv3d_halo_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy
   a.n_total = d->cin;
   a.a_stages = res_stages;
   a.status = ctx->d_status;
-  return res ? launch_halo_res<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
-             : launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+  if (res) return launch_halo_res<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream);
+  CUtensorMap tbh;
+  const bool pair = pair_eligible(a, pl.bn, pl.nsub) &&
+                    matrix_map(ctx, w, d->cout, d->kd * 9 * d->cin, 64, pl.bn / 2, &tbh) == 0;
+  return launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream, pair ? &tbh : nullptr);
 }
 
 // dgrad of a layer with stride 2 along H and / or W (stride 1 along D): one launch of the halo-tile kernel per output

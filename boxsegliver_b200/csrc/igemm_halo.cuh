@@ -627,11 +627,13 @@ constexpr int CH_SUB_BYTES = 23552;   // (10 x 18) x 128 B = 23040, padded to a 
 
 constexpr int CH_STAGING_BYTES = 2 * 16384;   // TMA-store epilogue: one 128-pixel x 64-channel tile per warp group
 
-template <int BN, int NSUB, bool TMA_ST = false>
+// PAIR: a cluster of two CTAs issues 256 x BN x 16 MMAs (cta_group::2) from the even CTA; each CTA owns the pixels of its
+// own unit and holds HALF of every filter slice, so a filter stage is half the size (see conv_halo_kernel).
+template <int BN, int NSUB, bool TMA_ST = false, bool PAIR = false>
 struct ConvHaloCfg {
   static constexpr int ACC_BUFS = (512 / (BN * NSUB)) >= 2 ? 2 : 1;
   static constexpr int TMEM_COLS = BN * NSUB * ACC_BUFS;
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * 128;
   static constexpr int A_BYTES = NSUB * CH_SUB_BYTES;
   // three activation stages hide the HBM latency of the one-block-deep reductions (Cin = 64: a unit is
   // ~1.5 us of MMAs); the widest column tile only occurs with long reductions and keeps two.
@@ -722,12 +724,23 @@ constexpr int CH_MAX_A_STAGES = 4;
 // store instruction. A lane-per-pixel global store costs one L1 wavefront per 32 bytes on the data path the UMMA
 // operand fetch also uses, and left the issuer waiting 16-30 % of the time for the un-overlapped epilogue of the
 // 256-wide tiles (gpu_conv_bench --waits); the staged store needs a quarter of the wavefronts and is asynchronous.
-template <int BN, int NSUB, bool B_MN, bool STATS, bool SCATTER, bool B_RES = false, bool TMA_ST = false>
+//
+// PAIR (3x3 windows, sub-tile pairs, plain epilogue, streamed filter): the kernel runs as clusters of two CTAs. Both load
+// their own activation tiles and half of every filter slice (rows [rank * BN / 2, ...) of the column tile); the even CTA's
+// issuer thread drives BOTH tensor cores with 256 x BN x 16 MMAs, whose rows 0..127 are its own sub-tile and rows 128..255
+// the peer's. Per CTA that halves the filter bytes taken in from L2, written to and read back from shared memory -- the
+// 128 x 256 x 16 MMA reads 12 KB of operands per 128 cycles (96 B/clk of the 128 B/clk shared memory moves), and the
+// filter stream written beside it (32 KB per 1024 cycles) is what the single-CTA kernel's issuer waits for a third of
+// the time (`b_full`, tools/gpu_conv_bench.py --waits). Barriers: every TMA load of both CTAs counts its bytes on the
+// EVEN CTA's full barriers (cp.async.bulk.tensor.cta_group::2); the issuer's commits arrive on the empty / accumulator
+// barriers of both CTAs (multicast); the peer's epilogue warps arrive on the even CTA's acc_empty barrier through DSMEM.
+template <int BN, int NSUB, bool B_MN, bool STATS, bool SCATTER, bool B_RES = false, bool TMA_ST = false, bool PAIR = false>
 __global__ void __launch_bounds__(CH_THREADS)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const ConvHaloArgs p) {
   static_assert(!TMA_ST || (!STATS && !SCATTER && !B_RES), "TMA-store epilogue: plain streamed-filter variant only");
-  using Cfg = ConvHaloCfg<BN, NSUB, TMA_ST>;
+  static_assert(!PAIR || (NSUB == 2 && !STATS && !SCATTER && !B_RES), "CTA pairs: plain streamed-filter variant only");
+  using Cfg = ConvHaloCfg<BN, NSUB, TMA_ST, PAIR>;
   constexpr int ACC_BUFS = Cfg::ACC_BUFS;
   constexpr int B_STAGES = Cfg::B_STAGES;
   constexpr int A_BYTES = Cfg::A_BYTES;
@@ -757,13 +770,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t sStage = sB0 + B_STAGES * B_BYTES;                                     // TMA_ST: 2 x 16 KB
   DeviceStatus* st = p.status;
 
+  // CTA pairs: rank in the cluster; a pair walks "pair units" (one pixel unit per CTA, the same column tile for both)
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const int u_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int u_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int u_count = PAIR ? p.n_units >> 1 : p.n_units;
+  auto pixel_unit = [&](int u) { return PAIR ? 2 * (u / p.n_ntiles) + (int)rank : u / p.n_ntiles; };
+
   pdl_trigger();
   if (threadIdx.x == 0) dead = *reinterpret_cast<volatile int*>(&st->error);
   if (STATS) {
     for (int i = threadIdx.x; i < CH_EPI_WARPS * 2 * BN; i += CH_THREADS) s_stats[i] = 0.f;
   }
   __syncthreads();
-  if (dead) return;
+  if (!PAIR && dead) return;   // (a pair never leaves its peer alone at the cluster barriers; the watchdogs unwind it)
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmA);
@@ -778,18 +798,24 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < ACC_BUFS; ++s) {
       mbar_init(acc_full + 8 * s, 1);
-      mbar_init(acc_empty + 8 * s, CH_EPI_WARPS);  // one arrival per epilogue warp
+      mbar_init(acc_empty + 8 * s, (PAIR ? 2 : 1) * CH_EPI_WARPS);  // one arrival per epilogue warp (of both CTAs)
     }
     mbar_init(grp_bar, 4);       // the four lane-quarter warps of a staging group
     mbar_init(grp_bar + 8, 4);
     if (TMA_ST) prefetch_tensormap(&tmO);
     fence_barrier_init();
   } else if (warp == 1) {
-    tmem_alloc<Cfg::TMEM_COLS>(smem_u32(&tmem_slot));
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc2<Cfg::TMEM_COLS>(smem_u32(&tmem_slot));
+      tmem_relinquish2();
+    } else {
+      tmem_alloc<Cfg::TMEM_COLS>(smem_u32(&tmem_slot));
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers exist before anything is counted on them
   tc_fence_after();
   pdl_wait();   // the prologue above touches no data of the previous kernel in the stream
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot);
@@ -805,8 +831,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       bool ok = true;
       unsigned long long ready = 0;   // image slices already seen complete (wait_flags)
-      for (int u = blockIdx.x; u < p.n_units && ok; u += gridDim.x) {
-        const int pu = u / p.n_ntiles;
+      for (int u = u_first; u < u_count && ok; u += u_step) {
+        const int pu = pixel_unit(u);
         int nsub = p.n_sub_total - pu * NSUB;
         nsub = nsub > NSUB ? NSUB : nsub;
         int tx[NSUB], ty[NSUB], img[NSUB];
@@ -836,8 +862,18 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int cbx = 0; cbx < kblocks && ok; ++cbx) {
           if (!mbar_wait(a_empty + 8 * stage, phase ^ 1, st, 21)) { ok = false; break; }
           const uint32_t fb = a_full + 8 * stage;
-          mbar_arrive_expect_tx(fb, nsub * sub_rows * 128);
           const int kdi = cbx / p.cblocks, cb = cbx - kdi * p.cblocks;
+          if (PAIR) {   // both CTAs' tiles are counted on the even CTA's barrier
+            if (rank == 0) mbar_arrive_expect_tx(fb, 2 * NSUB * sub_rows * 128);
+            const uint32_t fbc = mapa_shared(fb, 0);
+#pragma unroll
+            for (int j = 0; j < NSUB; ++j)
+              tma_load_5d_pair(sA0 + stage * A_BYTES + j * CH_SUB_BYTES, &tmA, fbc, cb * 64, tx[j] * 8 - p.halo,
+                               ty[j] * 16 - p.halo, img[j] % p.depth + kdi - (p.kd >> 1), img[j] / p.depth);
+            if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_arrive_expect_tx(fb, nsub * sub_rows * 128);
 #pragma unroll
           for (int j = 0; j < NSUB; ++j)
             if (j < nsub) {
@@ -877,7 +913,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      for (int u = blockIdx.x; u < p.n_units && ok; u += gridDim.x) {
+      for (int u = u_first; u < u_count && ok; u += u_step) {
         const int n0 = (u % p.n_ntiles) * BN;
         for (int cbx = 0; cbx < kblocks && ok; ++cbx) {
           const int kdi = cbx / p.cblocks, cb = cbx - kdi * p.cblocks;
@@ -885,9 +921,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (!mbar_wait(b_empty + 8 * stage, phase ^ 1, st, 22)) { ok = false; break; }
             const uint32_t fb = b_full + 8 * stage;
             const uint32_t sb = sB0 + stage * B_BYTES;
-            mbar_arrive_expect_tx(fb, B_BYTES);
             const int tapb = p.tap_table ? p.tap_b[kdi * p.ntaps + tap]
                                          : (p.b_flip ? (p.kd * p.ntaps - 1 - (kdi * p.ntaps + tap)) : kdi * p.ntaps + tap);
+            if (PAIR) {   // this CTA's half of the slice: columns / rows [n0 + rank * BN / 2, ...), counted on the even CTA
+              if (rank == 0) mbar_arrive_expect_tx(fb, 2 * B_BYTES);
+              const uint32_t fbc = mapa_shared(fb, 0);
+              const int nh = n0 + (int)rank * (BN / 2);
+              if (B_MN) {
+                const int krow = (tapb * p.cblocks + cb) * 64;
+#pragma unroll
+                for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(sb + j * 8192, &tmB, fbc, nh + 64 * j, krow);
+              } else {
+                tma_load_2d_pair(sb, &tmB, fbc, cb * 64, tapb * p.b_rows_per_tap + nh);   // box of BN / 2 rows
+              }
+              if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+              continue;
+            }
+            mbar_arrive_expect_tx(fb, B_BYTES);
             if (B_MN) {
               const int krow = (tapb * p.cblocks + cb) * 64;
 #pragma unroll
@@ -902,8 +952,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ============================== UMMA issuer
-    if (elect_one_sync()) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, false, B_MN);
+    if (elect_one_sync() && rank == 0) {   // (the odd CTA of a pair has no issuer: the even one drives both tensor cores)
+      constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN, false, B_MN);
+      auto mma = [](uint32_t d, uint64_t da_, uint64_t db_, uint32_t id, uint32_t accum) {
+        if (PAIR) umma2_bf16(d, da_, db_, id, accum); else umma_bf16(d, da_, db_, id, accum);
+      };
+      auto commit = [](uint32_t bar) { if (PAIR) umma2_commit(bar); else umma_commit(bar); };
       const uint32_t a_sbo = box_w * 128;
       int sa = 0, sb = 0, buf = 0;
       uint32_t pa = 0, pb = 0, pacc = 0;
@@ -913,8 +967,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool fast9 = p.ntaps == 9 && p.halo != 0 && p.tap_table == 0 && p.slow_issue == 0;
       const uint64_t db_base = B_MN ? make_smem_desc_sw128(sB0, 8192, 1024) : make_smem_desc_sw128(sB0, 16, 1024);
       if (B_RES && (int)blockIdx.x < p.n_units) ok = mbar_wait(b_full, 0, st, 27);
-      for (int u = blockIdx.x; u < p.n_units && ok; u += gridDim.x) {
-        const int pu = u / p.n_ntiles;
+      for (int u = u_first; u < u_count && ok; u += u_step) {
+        const int pu = pixel_unit(u);
         int nsub = p.n_sub_total - pu * NSUB;
         nsub = nsub > NSUB ? NSUB : nsub;
         t0 = clock64();
@@ -953,12 +1007,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int j = 0; j < NSUB; ++j) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16(acc + j * BN, da + (uint64_t)((toff + j * CH_SUB_BYTES + k * 32) >> 4),
+                  mma(acc + j * BN, da + (uint64_t)((toff + j * CH_SUB_BYTES + k * 32) >> 4),
                             db0 + (uint64_t)((B_MN ? k * 2048 : k * 32) >> 4), idesc,
                             (tap == 0 && k == 0) ? (uint32_t)(cb != 0) : 1u);
               }
               if (!B_RES) {
-                umma_commit(b_empty + 8 * sb);
+                commit(b_empty + 8 * sb);
                 if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
               }
             }
@@ -981,19 +1035,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (j < nsub) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                  umma_bf16(acc + j * BN, da0 + (uint64_t)((j * CH_SUB_BYTES + k * 32) >> 4),
+                  mma(acc + j * BN, da0 + (uint64_t)((j * CH_SUB_BYTES + k * 32) >> 4),
                             db0 + (uint64_t)((B_MN ? k * 2048 : k * 32) >> 4), idesc, first | (uint32_t)(k != 0));
               }
             }
             if (!B_RES) {
-              umma_commit(b_empty + 8 * sb);
+              commit(b_empty + 8 * sb);
               if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
             }
           }
-          umma_commit(a_empty + 8 * sa);
+          commit(a_empty + 8 * sa);
           if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
         }
-        if (ok) umma_commit(acc_full + 8 * buf);
+        if (ok) commit(acc_full + 8 * buf);
         if (++buf == ACC_BUFS) { buf = 0; pacc ^= 1; }
       }
       pdl_trigger_late();
@@ -1055,8 +1109,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     };
-    for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-      const int pu = u / p.n_ntiles;
+    for (int u = u_first; u < u_count; u += u_step) {
+      const int pu = pixel_unit(u);
       const int n0 = (u % p.n_ntiles) * BN;
       int nsub = p.n_sub_total - pu * NSUB;
       nsub = nsub > NSUB ? NSUB : nsub;
@@ -1243,7 +1297,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(acc_empty + 8 * buf);
+      if (lane == 0) {
+        if (PAIR && rank != 0) mbar_arrive_cluster(mapa_shared(acc_empty + 8 * buf, 0));   // the issuer lives in the even CTA
+        else mbar_arrive(acc_empty + 8 * buf);
+      }
       if (++buf == ACC_BUFS) { buf = 0; pacc ^= 1; }
     }
     if (TMA_ST && q == 0 && lane == 0) bulk_wait_all();   // the staging tiles stay valid until the last store is done
@@ -1275,9 +1332,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (n0 + c < p.n_total) p.stats_part[((long long)slot * 2 + k) * p.n_total + n0 + c] = t;
     }
   }
+  if (PAIR) cluster_sync_all();   // neither CTA leaves while the other may still signal its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if (PAIR) tmem_dealloc2<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 

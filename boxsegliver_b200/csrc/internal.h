@@ -77,6 +77,27 @@ inline cudaError_t bsl_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
 
+// Same for a kernel that runs as thread-block clusters of `cluster_x` CTAs along x (grid.x a multiple of it).
+template <typename... KArgs, typename... Args>
+inline cudaError_t bsl_launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                      int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = bsl_pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 // Encodes (or fetches from the cache) a bf16 tensor map with 128-byte swizzle and zero OOB fill.
 // dims/strides are innermost-first; strides[0] is implied (2 bytes) and ignored.
 int bsl_get_tmap(bsl_ctx* ctx, const void* base, int rank, const uint64_t* dims,
