@@ -36,6 +36,10 @@ CONV_CASES = [
     (2, 30, 40, 64, 64, 3, None, None),      # level 3 of 480 x 160 / 2: resident filter, column tile 64
     (1, 24, 36, 128, 64, 3, 192, 128),       # ragged + concat views
     (3, 10, 8, 64, 128, 1, None, None),      # 1x1, ragged rows
+    # CTA pairs (cta_group::2, 128-wide tiles): sub-tile count a multiple of 4, several column tiles, reductions long
+    # enough to wrap both operand rings; filter gradient with 4 / 8 input blocks per class-b CTA pair
+    (2, 32, 32, 256, 512, 3, None, None),    # fprop: 4 column tiles x 4 k-blocks; dgrad: 2 column tiles x 8 k-blocks
+    (4, 16, 16, 128, 256, 3, 192, 320),      # pairs writing into / reading from concat views
 ]
 
 
