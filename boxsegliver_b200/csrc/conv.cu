@@ -355,6 +355,73 @@ int launch_halo_pair(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, c
   return BSL_OK;
 }
 
+// ---- CTA pairs with a RESIDENT filter: the layers whose whole column range is one tile (N == 64 or 128) and whose
+// filter slice fits in shared memory. Each CTA keeps half of the slice (rows [rank * N / 2, ...) of a K-MAJOR filter),
+// which also frees room for activation stages. dgrad reads the HWIO filter K-major as it is; fprop gets a K-major copy
+// ([tap][cout][cin], a few hundred KB at most) written into the per-stream filter scratch right before the launch --
+// an MN-major filter would have to be split into 32-column halves, which the 128-byte swizzle cannot express.
+bool pair_res_on() {
+  static const int on = getenv("BSL_PAIR_RES") ? atoi(getenv("BSL_PAIR_RES")) != 0 : 1;
+  return pair_on() && on;
+}
+bool plan_resident_pair(int bn, int ntaps, int cblocks, int n_sub_total, int* nsub, int* a_stages, int* smem) {
+  if (!pair_res_on() || (bn != 64 && bn != 128) || ntaps != 9) return false;
+  const int res = ntaps * cblocks * (bn / 2) * 128;
+  const int left = CH_DYN_BUDGET - 1024 - res;
+  if (left <= 0) return false;
+  const int s2 = std::min(CH_MAX_A_STAGES, left / (2 * CH_SUB_BYTES)), s1 = std::min(CH_MAX_A_STAGES, left / CH_SUB_BYTES);
+  int ns, st;
+  if (n_sub_total % 4 == 0 && s2 >= 3) { ns = 2; st = s2; }
+  else if (n_sub_total % 2 == 0 && s1 >= 3) { ns = 1; st = s1; }
+  else if (n_sub_total % 4 == 0 && s2 >= 2) { ns = 2; st = s2; }
+  else return false;
+  *nsub = ns;
+  *a_stages = st;
+  *smem = st * ns * CH_SUB_BYTES + res + 1024;
+  return true;
+}
+void replan_pair_units(bsl_ctx* ctx, HaloPlan& p) {   // one column tile; both CTAs of a pair always work
+  p.n_ntiles = 1;
+  p.n_units = p.n_sub_total / p.nsub;
+  p.grid = 2 * std::min(p.n_units / 2, ctx->sm_count / 2);
+  p.slots = p.grid;
+  p.pair = 1;
+}
+
+template <int BN, int NSUB, bool STATS>
+int launch_halo_res_pair_one(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args, int grid,
+                             int smem, cudaStream_t stream) {
+  auto kern = conv_halo_kernel<BN, NSUB, false, STATS, false, true, false, true>;
+  static int configured = 0;
+  if (configured < smem) {
+    BSL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
+  }
+  bsl_launch_cluster(kern, dim3(grid), dim3(CH_THREADS), smem, stream, 2, a, b, a, args);
+  BSL_LAUNCH_CHECK(ctx, "conv_halo_kernel (CTA pairs, resident filter) launch");
+  return BSL_OK;
+}
+template <bool STATS>
+int launch_halo_res_pair(bsl_ctx* ctx, int bn, int nsub, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args,
+                         int grid, int smem, cudaStream_t stream) {
+  if (bn == 64 && nsub == 2) return launch_halo_res_pair_one<64, 2, STATS>(ctx, a, b, args, grid, smem, stream);
+  if (bn == 64 && nsub == 1) return launch_halo_res_pair_one<64, 1, STATS>(ctx, a, b, args, grid, smem, stream);
+  if (bn == 128 && nsub == 2) return launch_halo_res_pair_one<128, 2, STATS>(ctx, a, b, args, grid, smem, stream);
+  if (bn == 128 && nsub == 1) return launch_halo_res_pair_one<128, 1, STATS>(ctx, a, b, args, grid, smem, stream);
+  return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv_halo (CTA pairs, resident): tile %d x %d", bn, nsub);
+}
+
+// HWIO [taps][cin][cout] -> [taps][cout][cin] (bf16), the K-major filter of the forward pass of a CTA pair.
+__global__ void filter_kmajor_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ o, int cin, int cout,
+                                     int total) {
+  bsl::pdl_enter();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // output index: (tap, co, ci)
+  if (i >= total) return;
+  const int ci = i % cin, t = i / cin;
+  const int co = t % cout, tap = t / cout;
+  o[i] = w[((long long)tap * cin + ci) * cout + co];
+}
+
 template <bool B_MN, bool STATS, bool SCATTER>
 int launch_halo(bsl_ctx* ctx, int bn, int nsub, const CUtensorMap& a, const CUtensorMap& b, const ConvHaloArgs& args,
                 int grid, cudaStream_t stream, const CUtensorMap* b_half = nullptr) {
@@ -752,17 +819,24 @@ static int launch_fprop_halo_stats(bsl_ctx* ctx, const HaloPlan& pl, bool res, i
                                    const CUtensorMap& tb, ConvHaloArgs& a, double* sums, int group_imgs, int n_imgs, int h,
                                    int w, int cout, void* y, int y_ld, cudaStream_t stream) {
   int rc;
-  if (!sums)
-    return res ? launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
-               : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+  const bool res_pair = res && pl.pair;   // resident filter of a CTA pair: tb is the K-major copy (conv2d_fprop_halo)
+  auto run = [&](bool stats) -> int {
+    if (res_pair)
+      return stats ? launch_halo_res_pair<true>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
+                   : launch_halo_res_pair<false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream);
+    if (res)
+      return stats ? launch_halo_res<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
+                   : launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream);
+    return stats ? launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream)
+                 : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
+  };
+  if (!sums) return run(false);
   const int groups = group_imgs > 0 ? n_imgs / group_imgs : 1;
   const long long ppg = group_imgs > 0 ? (long long)group_imgs * h * w : (long long)n_imgs * h * w;
-  if (pl.bn == 256 || pl.pair || (group_imgs > 0 && pl.grid % pl.n_ntiles != 0)) {
+  if (pl.bn == 256 || (pl.pair && !res) || (group_imgs > 0 && pl.grid % pl.n_ntiles != 0)) {
     // long-reduction layers: small, L2-resident outputs; a separate statistics pass is cheaper than an
     // un-overlapped epilogue butterfly
-    if ((rc = res ? launch_halo_res<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
-                  : launch_halo<true, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream)))
-      return rc;
+    if ((rc = run(false))) return rc;
     return bsl_stats_bf16(ctx, y, ppg, groups, cout, y_ld, sums, stream);
   }
   float* part = nullptr;
@@ -774,9 +848,7 @@ static int launch_fprop_halo_stats(bsl_ctx* ctx, const HaloPlan& pl, bool res, i
     a.stats_part = part;
     a.stats_group_imgs = group_imgs;
     a.stats_blocks = pl.slots * 4;
-    rc = res ? launch_halo_res<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
-             : launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
-    if (rc) return rc;
+    if ((rc = run(true))) return rc;
     const int kc2 = 2 * cout;
     bsl_launch(pixel_reduce_final_kernel, dim3((kc2 + 31) / 32, groups), dim3(1024), 0, stream, part, pl.slots * 4, kc2, sums);
     BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel (conv instance statistics)");
@@ -784,9 +856,7 @@ static int launch_fprop_halo_stats(bsl_ctx* ctx, const HaloPlan& pl, bool res, i
   }
   if ((rc = bsl_scratch(ctx, (size_t)pl.slots * 2 * cout * sizeof(float), &part, stream))) return rc;
   a.stats_part = part;
-  rc = res ? launch_halo_res<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream)
-           : launch_halo<true, true, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream);
-  if (rc) return rc;
+  if ((rc = run(true))) return rc;
   const int kc = 2 * cout;
   bsl_launch(pixel_reduce_final_kernel, dim3(dim3((kc + 31) / 32, 1)), dim3(1024), 0, stream, part, pl.slots, kc, sums);
   BSL_LAUNCH_CHECK(ctx, "pixel_reduce_final_kernel (conv statistics)");
@@ -801,14 +871,34 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
   const int halo = d->kh == 3 ? 1 : 0;
   HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, d->cout);
   int res_stages = 0, res_smem = 0;
-  const bool res = plan_resident(pl.bn, d->kh * d->kw, d->cin / 64, &pl.nsub, &res_stages, &res_smem);
-  if (res) replan_units(ctx, pl);
-  else if (!wait) pair_replan(ctx, pl, d->cout, 256, d->kh * d->kw);
+  bool res = false;
+  const void* w_k = nullptr;   // K-major copy of the filter (resident CTA pairs)
+  if (!wait && d->cout == pl.bn && d->cin % 64 == 0 && d->x_ld >= d->cin &&
+      plan_resident_pair(pl.bn, d->kh * d->kw, d->cin / 64, pl.n_sub_total, &pl.nsub, &res_stages, &res_smem)) {
+    void* wk = nullptr;
+    const int total = 9 * d->cin * d->cout;
+    int rc0;
+    if ((rc0 = bsl_scratch_w(ctx, (size_t)total * 2, &wk, stream))) return rc0;
+    bsl_launch(filter_kmajor_kernel, dim3(cdiv(total, 256)), dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(w),
+               reinterpret_cast<__nv_bfloat16*>(wk), d->cin, d->cout, total);
+    BSL_LAUNCH_CHECK(ctx, "filter_kmajor_kernel");
+    w_k = wk;
+    res = true;
+    replan_pair_units(ctx, pl);
+  } else {
+    res = plan_resident(pl.bn, d->kh * d->kw, d->cin / 64, &pl.nsub, &res_stages, &res_smem);
+    if (res) replan_units(ctx, pl);
+    else if (!wait) pair_replan(ctx, pl, d->cout, 256, d->kh * d->kw);
+  }
   const int box[4] = {8 + 2 * halo, 16 + 2 * halo, 1, 1};
   CUtensorMap ta, tb;
   int rc;
   if ((rc = nhwc_map(ctx, x, d->cin, d->w, d->h, d->n, d->x_ld, box, &ta))) return rc;
-  if ((rc = matrix_map(ctx, w, d->cout, d->kh * d->kw * d->cin, 64, 64, &tb))) return rc;
+  if (w_k) {   // [9 * cout rows][cin]: 64 consecutive input channels = the K block, half the tile's rows per CTA
+    if ((rc = matrix_map(ctx, w_k, d->cin, 9 * d->cout, 64, pl.bn / 2, &tb))) return rc;
+  } else if ((rc = matrix_map(ctx, w, d->cout, d->kh * d->kw * d->cin, 64, 64, &tb))) {
+    return rc;
+  }
   ConvHaloArgs a = {};
   halo_common(a, pl, d->w, d->h, d->n);
   a.ntaps = d->kh * d->kw;
@@ -821,6 +911,7 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
   a.n_group = d->cout;
   a.n_total = d->cout;
   a.a_stages = res_stages;
+  a.b_rows_per_tap = d->cout;   // (K-major copy of a resident CTA pair; unused otherwise)
   a.status = ctx->d_status;
   if ((rc = attach_wait(ctx, a, wait, d->n))) return rc;
   return launch_fprop_halo_stats(ctx, pl, res, res_smem, ta, tb, a, sums, group_imgs, d->n, d->h, d->w, d->cout, y,
@@ -928,13 +1019,20 @@ static int conv2d_dgrad_impl(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
     const int halo = d->kh == 3 ? 1 : 0;
     HaloPlan pl = plan_halo(ctx, d->w, d->h, d->n, d->cin);
     int res_stages = 0, res_smem = 0;
-    const bool res = plan_resident(pl.bn, d->kh * d->kw, d->cout / 64, &pl.nsub, &res_stages, &res_smem);
-    if (res) replan_units(ctx, pl);
-    else if (!wait && !relu_act) pair_replan(ctx, pl, d->cin, 128, d->kh * d->kw);
+    bool res = false, res_pair = false;
+    if (!wait && !relu_act && d->cin == pl.bn &&
+        plan_resident_pair(pl.bn, d->kh * d->kw, d->cout / 64, pl.n_sub_total, &pl.nsub, &res_stages, &res_smem)) {
+      res = res_pair = true;
+      replan_pair_units(ctx, pl);
+    } else {
+      res = plan_resident(pl.bn, d->kh * d->kw, d->cout / 64, &pl.nsub, &res_stages, &res_smem);
+      if (res) replan_units(ctx, pl);
+      else if (!wait && !relu_act) pair_replan(ctx, pl, d->cin, 128, d->kh * d->kw);
+    }
     const int hbox[4] = {8 + 2 * halo, 16 + 2 * halo, 1, 1};
     CUtensorMap ta, tb;
     if ((rc = nhwc_map(ctx, dy, d->cout, d->w, d->h, d->n, d->y_ld, hbox, &ta))) return rc;
-    if ((rc = matrix_map(ctx, w, d->cout, d->kh * d->kw * d->cin, 64, pl.bn, &tb))) return rc;
+    if ((rc = matrix_map(ctx, w, d->cout, d->kh * d->kw * d->cin, 64, res_pair ? pl.bn / 2 : pl.bn, &tb))) return rc;
     ConvHaloArgs a = {};
     halo_common(a, pl, d->w, d->h, d->n);
     a.ntaps = d->kh * d->kw;
@@ -953,6 +1051,7 @@ static int conv2d_dgrad_impl(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
     if ((rc = attach_wait(ctx, a, wait, d->n))) return rc;
     a.relu_mask = relu_act;
     a.mask_col0 = mask_col0;
+    if (res_pair) return launch_halo_res_pair<false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream));
     if (res) return launch_halo_res<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream));
     CUtensorMap tbh;
     const bool pair = pair_eligible(a, pl.bn, pl.nsub) &&

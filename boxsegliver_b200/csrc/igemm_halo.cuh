@@ -739,7 +739,8 @@ __global__ void __launch_bounds__(CH_THREADS)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const ConvHaloArgs p) {
   static_assert(!TMA_ST || (!STATS && !SCATTER && !B_RES), "TMA-store epilogue: plain streamed-filter variant only");
-  static_assert(!PAIR || (NSUB == 2 && !STATS && !SCATTER && !B_RES), "CTA pairs: plain streamed-filter variant only");
+  static_assert(!PAIR || !SCATTER, "CTA pairs: no scatter epilogue");
+  static_assert(!PAIR || !B_MN || BN >= 128, "CTA pairs: an MN-major filter splits in 64-column blocks");
   using Cfg = ConvHaloCfg<BN, NSUB, TMA_ST, PAIR>;
   constexpr int ACC_BUFS = Cfg::ACC_BUFS;
   constexpr int B_STAGES = Cfg::B_STAGES;
@@ -891,6 +892,28 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == 2 + CH_EPI_WARPS) {
     // ============================== B producer: one (tap, 64-channel block) filter slice per stage
     if (B_RES) {
+      if (PAIR) {
+        // resident filter of a CTA pair (one column tile, n_ntiles == 1): this CTA keeps rows / columns
+        // [rank * BN / 2, ...) of every slice; all bytes are counted on the even CTA's barrier
+        if (elect_one_sync() && u_first < u_count) {
+          if (rank == 0) mbar_arrive_expect_tx(b_full, 2 * kblocks * p.ntaps * B_BYTES);
+          const uint32_t fbc = mapa_shared(b_full, 0);
+          const int nh = (int)rank * (BN / 2);
+          for (int cbx = 0; cbx < kblocks; ++cbx)
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              const uint32_t sb = sB0 + (cbx * p.ntaps + tap) * B_BYTES;
+              const int kdi = cbx / p.cblocks, cb = cbx - kdi * p.cblocks;
+              const int tapb = p.b_flip ? (p.kd * p.ntaps - 1 - (kdi * p.ntaps + tap)) : kdi * p.ntaps + tap;
+              if (B_MN) {
+                const int krow = (tapb * p.cblocks + cb) * 64;
+#pragma unroll
+                for (int j = 0; j < BN / 128; ++j) tma_load_2d_pair(sb + j * 8192, &tmB, fbc, nh + 64 * j, krow);
+              } else {
+                tma_load_2d_pair(sb, &tmB, fbc, cb * 64, tapb * p.b_rows_per_tap + nh);   // box of BN / 2 rows
+              }
+            }
+        }
+      } else
       if (elect_one_sync() && (int)blockIdx.x < p.n_units) {
         const int n0 = (blockIdx.x % p.n_ntiles) * BN;
         mbar_arrive_expect_tx(b_full, kblocks * p.ntaps * B_BYTES);
@@ -966,7 +989,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const bool timed = p.dbg != nullptr;
       const bool fast9 = p.ntaps == 9 && p.halo != 0 && p.tap_table == 0 && p.slow_issue == 0;
       const uint64_t db_base = B_MN ? make_smem_desc_sw128(sB0, 8192, 1024) : make_smem_desc_sw128(sB0, 16, 1024);
-      if (B_RES && (int)blockIdx.x < p.n_units) ok = mbar_wait(b_full, 0, st, 27);
+      if (B_RES && u_first < u_count) ok = mbar_wait(b_full, 0, st, 27);
       for (int u = u_first; u < u_count && ok; u += u_step) {
         const int pu = pixel_unit(u);
         int nsub = p.n_sub_total - pu * NSUB;

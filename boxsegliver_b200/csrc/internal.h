@@ -35,6 +35,7 @@ struct bsl_ctx {
   };
   std::mutex scratch_mu;
   std::unordered_map<cudaStream_t, Scratch> scratch;
+  std::unordered_map<cudaStream_t, Scratch> scratch_w;   // re-laid-out filters of the CTA-pair kernels (conv.cu)
 };
 
 // Frees the scratch arena attached to `stream` (all of them when stream_or_all is true).

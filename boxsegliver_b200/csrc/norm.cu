@@ -69,18 +69,39 @@ int bsl_scratch(bsl_ctx* ctx, size_t bytes, float** out, cudaStream_t stream) {
   *out = a.ptr;
   return BSL_OK;
 }
+
+// A second, small arena per (context, stream) for filters re-laid-out in front of a convolution (the K-major copy the
+// CTA-pair kernels read): separate from the reduction arena, which the same call may use for its statistics partials.
+int bsl_scratch_w(bsl_ctx* ctx, size_t bytes, void** out, cudaStream_t stream) {
+  std::lock_guard<std::mutex> g(ctx->scratch_mu);
+  bsl_ctx::Scratch& a = ctx->scratch_w[stream];
+  if (bytes > a.bytes) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) == cudaSuccess && cap != cudaStreamCaptureStatusNone)
+      return bsl_fail(ctx, BSL_EINVAL, "filter scratch of this stream must grow while the stream is capturing");
+    if (a.ptr) cudaFree(a.ptr);
+    const size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+    a.ptr = nullptr;
+    a.bytes = 0;
+    BSL_CUDA(ctx, cudaMalloc(&a.ptr, want));
+    a.bytes = want;
+  }
+  *out = a.ptr;
+  return BSL_OK;
+}
 }  // namespace bsl
 
 void bsl_scratch_release(bsl_ctx* ctx, cudaStream_t stream, bool all) {
   std::lock_guard<std::mutex> g(ctx->scratch_mu);
-  for (auto it = ctx->scratch.begin(); it != ctx->scratch.end();) {
-    if (all || it->first == stream) {
-      if (it->second.ptr) cudaFree(it->second.ptr);
-      it = ctx->scratch.erase(it);
-    } else {
-      ++it;
+  for (auto* m : {&ctx->scratch, &ctx->scratch_w})
+    for (auto it = m->begin(); it != m->end();) {
+      if (all || it->first == stream) {
+        if (it->second.ptr) cudaFree(it->second.ptr);
+        it = m->erase(it);
+      } else {
+        ++it;
+      }
     }
-  }
 }
 
 namespace {

@@ -121,6 +121,7 @@ inline ReducePlan plan_reduce(bsl_ctx* ctx, long long pixels_per_group, int grou
 }
 
 int bsl_scratch(bsl_ctx* ctx, size_t bytes, float** out, cudaStream_t stream);
+int bsl_scratch_w(bsl_ctx* ctx, size_t bytes, void** out, cudaStream_t stream);
 
 template <class F>
 int run_pixel_reduce(bsl_ctx* ctx, const F& f, long long pixels_per_group, int groups, int c, double* out,
