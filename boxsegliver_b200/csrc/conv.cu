@@ -365,7 +365,11 @@ bool pair_res_on() {
   return pair_on() && on;
 }
 bool plan_resident_pair(int bn, int ntaps, int cblocks, int n_sub_total, int* nsub, int* a_stages, int* smem) {
-  if (!pair_res_on() || (bn != 64 && bn != 128) || ntaps != 9) return false;
+  // one-block reductions (K = 64) stay with single CTAs: their units are so short that the epilogue, not the tensor pipe,
+  // sets the pace once the MMAs get faster (measured: 64 -> 64 fprop 0.298 -> 0.314 ms, dgrad unchanged), while
+  // 128 -> 64 fprop gained 19 % and 128 -> 64 dgrad 25 % (profiles/r02_ab_experiments.md)
+  static const int min_cb = getenv("BSL_PAIR_RES_MIN_CB") ? atoi(getenv("BSL_PAIR_RES_MIN_CB")) : 2;
+  if (!pair_res_on() || (bn != 64 && bn != 128) || ntaps != 9 || cblocks < min_cb) return false;
   const int res = ntaps * cblocks * (bn / 2) * 128;
   const int left = CH_DYN_BUDGET - 1024 - res;
   if (left <= 0) return false;
