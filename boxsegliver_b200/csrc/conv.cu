@@ -877,7 +877,9 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
   int res_stages = 0, res_smem = 0;
   bool res = false;
   const void* w_k = nullptr;   // K-major copy of the filter (resident CTA pairs)
-  if (!wait && d->cout == pl.bn && d->cin % 64 == 0 && d->x_ld >= d->cin &&
+  // (also under image-slice flags, `wait`: the fused statistics are summed per CTA, so both schedules must run the same
+  //  kernel to stay bit-identical -- tests/test_gpu_unet.py::test_image_slice_pipelining_is_bit_identical)
+  if (d->cout == pl.bn && d->cin % 64 == 0 && d->x_ld >= d->cin &&
       plan_resident_pair(pl.bn, d->kh * d->kw, d->cin / 64, pl.n_sub_total, &pl.nsub, &res_stages, &res_smem)) {
     void* wk = nullptr;
     const int total = 9 * d->cin * d->cout;
