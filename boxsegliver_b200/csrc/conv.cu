@@ -298,6 +298,37 @@ bool pair_on() {
   static const int on = getenv("BSL_PAIR") ? atoi(getenv("BSL_PAIR")) != 0 : 1;
   return on;
 }
+// How many CTA pairs of the (one-CTA-per-SM) pair kernels the device holds AT ONCE. The kernels are persistent with a
+// static schedule, so a pair that had to wait for a second round would double the launch's time: a GPC with an odd number
+// of usable SMs hosts one pair fewer than sm_count / 2 suggests. Asked from the driver once (the widest configuration).
+int max_pairs(bsl_ctx* ctx) {
+  static std::mutex mu;
+  static int cached = -1;
+  std::lock_guard<std::mutex> g(mu);
+  if (cached >= 0) return cached;
+  auto kern = conv_halo_kernel<128, 2, true, false, false, false, true, true>;
+  constexpr int smem = ConvHaloCfg<128, 2, true, true>::SMEM_BYTES;
+  int n = 0;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (ctx->sm_count / 2));
+    cfg.blockDim = dim3(CH_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) n = 0;
+  }
+  (void)cudaGetLastError();
+  static const int env = getenv("BSL_MAX_PAIRS") ? atoi(getenv("BSL_MAX_PAIRS")) : 0;
+  cached = std::max(0, std::min(n, ctx->sm_count / 2));
+  if (env > 0) cached = std::min(cached, env);
+  return cached;
+}
 // CTA pairs run 128-wide tiles: per CTA a pair takes in half of every filter slice, so the narrower tile costs no more
 // filter traffic than a 256-wide tile of a single CTA, and twice as many units fill the 148 SMs evenly (512 units of a
 // 512-channel layer at 32 x 32 are 3.46 per SM -- the last of 4 rounds is half empty; 1024 are 6.92) with the accumulators
@@ -306,6 +337,7 @@ bool pair_on() {
 bool pair_replan(bsl_ctx* ctx, HaloPlan& p, int ncols, int min_cols, int ntaps) {
   static const int env_bn = getenv("BSL_HALO_BN") ? atoi(getenv("BSL_HALO_BN")) : 0;
   if (!pair_on() || env_bn || ntaps != 9 || ncols % 128 || ncols < min_cols || p.n_sub_total % 4) return false;
+  if (max_pairs(ctx) < 1) return false;
   p.bn = 128;
   p.nsub = 2;
   p.n_ntiles = ncols / 128;
@@ -335,8 +367,8 @@ int out_map(bsl_ctx* ctx, const ConvHaloArgs& a, int w, int h, CUtensorMap* out)
 // CTA pairs (conv_halo_kernel<..., PAIR>): 256-wide tiles of 3x3 windows whose sub-tile count is a multiple of 4 (a pair
 // works on two units of two sub-tiles and the same column tile). `b_half`: for a K-major filter (dgrad) the tensor map
 // whose box holds HALF the tile's rows; an MN-major filter (fprop) is loaded in 64-column blocks either way.
-bool pair_eligible(const ConvHaloArgs& a, int bn, int nsub) {
-  return pair_on() && (bn == 256 || bn == 128) && nsub == 2 && a.n_sub_total % 4 == 0 && a.ntaps == 9 && a.halo == 1 && !a.tap_table &&
+bool pair_eligible(bsl_ctx* ctx, const ConvHaloArgs& a, int bn, int nsub) {
+  return pair_on() && max_pairs(ctx) >= 1 && (bn == 256 || bn == 128) && nsub == 2 && a.n_sub_total % 4 == 0 && a.ntaps == 9 && a.halo == 1 && !a.tap_table &&
          a.wait_flags == nullptr && a.up_cpb == 0 && a.relu_mask == nullptr;
 }
 template <int BN, bool B_MN>
@@ -349,7 +381,8 @@ int launch_halo_pair(bsl_ctx* ctx, const CUtensorMap& a, const CUtensorMap& b, c
     BSL_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  const int pairs = std::min(args.n_units / 2, ctx->sm_count / 2);
+  const int pairs = std::min(args.n_units / 2, max_pairs(ctx));
+  if (pairs < 1) return bsl_fail(ctx, BSL_EUNSUPPORTED, "conv_halo (CTA pairs): the device holds no cluster of two CTAs");
   bsl_launch_cluster(kern, dim3(2 * pairs), dim3(CH_THREADS), smem, stream, 2, a, b, o, args);
   BSL_LAUNCH_CHECK(ctx, "conv_halo_kernel (CTA pairs) launch");
   return BSL_OK;
@@ -364,12 +397,12 @@ bool pair_res_on() {
   static const int on = getenv("BSL_PAIR_RES") ? atoi(getenv("BSL_PAIR_RES")) != 0 : 1;
   return pair_on() && on;
 }
-bool plan_resident_pair(int bn, int ntaps, int cblocks, int n_sub_total, int* nsub, int* a_stages, int* smem) {
+bool plan_resident_pair(bsl_ctx* ctx, int bn, int ntaps, int cblocks, int n_sub_total, int* nsub, int* a_stages, int* smem) {
   // one-block reductions (K = 64) stay with single CTAs: their units are so short that the epilogue, not the tensor pipe,
   // sets the pace once the MMAs get faster (measured: 64 -> 64 fprop 0.298 -> 0.314 ms, dgrad unchanged), while
   // 128 -> 64 fprop gained 19 % and 128 -> 64 dgrad 25 % (profiles/r02_ab_experiments.md)
   static const int min_cb = getenv("BSL_PAIR_RES_MIN_CB") ? atoi(getenv("BSL_PAIR_RES_MIN_CB")) : 2;
-  if (!pair_res_on() || (bn != 64 && bn != 128) || ntaps != 9 || cblocks < min_cb) return false;
+  if (!pair_res_on() || (bn != 64 && bn != 128) || ntaps != 9 || cblocks < min_cb || max_pairs(ctx) < 1) return false;
   const int res = ntaps * cblocks * (bn / 2) * 128;
   const int left = CH_DYN_BUDGET - 1024 - res;
   if (left <= 0) return false;
@@ -387,7 +420,7 @@ bool plan_resident_pair(int bn, int ntaps, int cblocks, int n_sub_total, int* ns
 void replan_pair_units(bsl_ctx* ctx, HaloPlan& p) {   // one column tile; both CTAs of a pair always work
   p.n_ntiles = 1;
   p.n_units = p.n_sub_total / p.nsub;
-  p.grid = 2 * std::min(p.n_units / 2, ctx->sm_count / 2);
+  p.grid = 2 * std::min(p.n_units / 2, max_pairs(ctx));
   p.slots = p.grid;
   p.pair = 1;
 }
@@ -431,7 +464,7 @@ int launch_halo(bsl_ctx* ctx, int bn, int nsub, const CUtensorMap& a, const CUte
                 int grid, cudaStream_t stream, const CUtensorMap* b_half = nullptr) {
   if constexpr (!STATS && !SCATTER) {
     const int lvl = tma_store_level();
-    if (pair_eligible(args, bn, nsub) && (B_MN || b_half != nullptr)) {
+    if (pair_eligible(ctx, args, bn, nsub) && (B_MN || b_half != nullptr)) {
       CUtensorMap o;
       if (out_map(ctx, args, args.vw, args.vh, &o) == 0)
         return bn == 256 ? launch_halo_pair<256, B_MN>(ctx, a, B_MN ? b : *b_half, args, stream, o)
@@ -880,7 +913,7 @@ static int conv2d_fprop_halo(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
   // (also under image-slice flags, `wait`: the fused statistics are summed per CTA, so both schedules must run the same
   //  kernel to stay bit-identical -- tests/test_gpu_unet.py::test_image_slice_pipelining_is_bit_identical)
   if (d->cout == pl.bn && d->cin % 64 == 0 && d->x_ld >= d->cin &&
-      plan_resident_pair(pl.bn, d->kh * d->kw, d->cin / 64, pl.n_sub_total, &pl.nsub, &res_stages, &res_smem)) {
+      plan_resident_pair(ctx, pl.bn, d->kh * d->kw, d->cin / 64, pl.n_sub_total, &pl.nsub, &res_stages, &res_smem)) {
     void* wk = nullptr;
     const int total = 9 * d->cin * d->cout;
     int rc0;
@@ -1027,7 +1060,7 @@ static int conv2d_dgrad_impl(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
     int res_stages = 0, res_smem = 0;
     bool res = false, res_pair = false;
     if (!wait && !relu_act && d->cin == pl.bn &&
-        plan_resident_pair(pl.bn, d->kh * d->kw, d->cout / 64, pl.n_sub_total, &pl.nsub, &res_stages, &res_smem)) {
+        plan_resident_pair(ctx, pl.bn, d->kh * d->kw, d->cout / 64, pl.n_sub_total, &pl.nsub, &res_stages, &res_smem)) {
       res = res_pair = true;
       replan_pair_units(ctx, pl);
     } else {
@@ -1060,7 +1093,7 @@ static int conv2d_dgrad_impl(bsl_ctx* ctx, const bsl_conv2d_desc* d, const void*
     if (res_pair) return launch_halo_res_pair<false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream));
     if (res) return launch_halo_res<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, as_stream(stream));
     CUtensorMap tbh;
-    const bool pair = pair_eligible(a, pl.bn, pl.nsub) &&
+    const bool pair = pair_eligible(ctx, a, pl.bn, pl.nsub) &&
                       matrix_map(ctx, w, d->cout, d->kh * d->kw * d->cin, 64, pl.bn / 2, &tbh) == 0;
     return launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, as_stream(stream), pair ? &tbh : nullptr);
   }
@@ -1549,7 +1582,7 @@ int bsl_conv3d_halo_dgrad(bsl_ctx* ctx, const bsl_conv3d_desc* d, const void* dy
   a.status = ctx->d_status;
   if (res) return launch_halo_res<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, res_smem, stream);
   CUtensorMap tbh;
-  const bool pair = pair_eligible(a, pl.bn, pl.nsub) &&
+  const bool pair = pair_eligible(ctx, a, pl.bn, pl.nsub) &&
                     matrix_map(ctx, w, d->cout, d->kd * 9 * d->cin, 64, pl.bn / 2, &tbh) == 0;
   return launch_halo<false, false, false>(ctx, pl.bn, pl.nsub, ta, tb, a, pl.grid, stream, pair ? &tbh : nullptr);
 }
