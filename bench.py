@@ -513,7 +513,7 @@ def run_b200(args):
             roof.update(
                 kernels_achieved=kt, kernels_frac=kt / peak, kernels_launches_timed=conv["launches"],
                 kernels_ms_per_step=conv["ms"] / args.steps,
-                kernels="bsl::conv_halo_kernel + bsl::wgrad_halo_kernel + bsl::igemm_kernel (every tcgen05 conv / convT "
+                kernels="bsl::conv_halo_kernel (single CTAs and cta_group::2 CTA pairs) + bsl::wgrad_halo3_kernel / wgrad_halo_kernel + bsl::igemm_kernel (every tcgen05 conv / convT "
                         "fprop, dgrad, wgrad launch of K extra steps, CUDA events on the launching stream, overlap off)",
                 per_kind={k: {"launches_per_step": v[0] // args.steps, "ms_per_step": v[1] / args.steps,
                               "tflops": v[2] / (v[1] / 1e3) / 1e12 if v[1] > 0 else 0.0}
